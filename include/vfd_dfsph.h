@@ -1,0 +1,216 @@
+/* vfd_dfsph.h — C ABI of libvfd_dfsph.so: a B200-native (sm_100a) implementation of VFD's DFSPH
+ * solver step, a drop-in for the reference's  class DFSPHSimulation
+ * (reference: VFD/Source/Simulation/DFSPH/DFSPHSimulator.h:10-56, which forwards 1:1 to
+ *  DFSPHImplementation, VFD/Source/Simulation/DFSPH/DFSPHImplementation.h:23-137).
+ *
+ * Plain pointers and sizes only; no C++/torch types.  Ownership: the handle owns all device
+ * memory; every pointer argument is caller-owned and only read/written during the call.
+ * Errors: every function returns 0 on success or a VFD_E_* code; vfd_dfsph_last_error() gives
+ * the message.  The library never calls exit() (the reference prints and exits on any CUDA
+ * error: VFD/Source/Compute/Utility/CUDA/cutil.h:772-778).  Threading: one mutating thread plus
+ * concurrent read-only getters (the reference polls state/debug info from its UI thread while a
+ * worker runs Simulate(): VFD/Source/Simulation/DFSPH/DFSPHSimulator.cpp:156-166).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * VFD_E_CUDA. */
+#ifndef VFD_DFSPH_H
+#define VFD_DFSPH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFD_OK            0
+#define VFD_E_INVALID     1   /* bad argument / call order */
+#define VFD_E_CUDA        2   /* CUDA runtime error (message in last_error) */
+#define VFD_E_CAPACITY    3   /* search grid or buffer larger than the configured limits */
+#define VFD_E_NCCL        4
+
+typedef struct VfdDfsph VfdDfsph;
+
+/* Field-for-field DFSPHSimulationDescription with fixed-width types; the names are the
+ * reference's (and its cereal NVPs: VFD/Source/Scene/Components/DFSPHSimulationComponent.h:11-37).
+ * Reference: VFD/Source/Simulation/DFSPH/Structures/DFSPHSimulationDescription.h:9-50. */
+typedef struct VfdDfsphDescription {
+    float    TimeStepSize;                    /* 0.001  */
+    float    MinTimeStepSize;                 /* 0.0001 */
+    float    MaxTimeStepSize;                 /* 0.005  */
+    float    FrameLength;                     /* 0.0016 */
+    uint32_t FrameCount;                      /* 200    */
+    uint32_t MinPressureSolverIterations;     /* 0   */
+    uint32_t MaxPressureSolverIterations;     /* 100 */
+    float    MaxPressureSolverError;          /* 10 [%] */
+    uint32_t EnableDivergenceSolverError;     /* bool, 1 */
+    uint32_t MinDivergenceSolverIterations;   /* 0   */
+    uint32_t MaxDivergenceSolverIterations;   /* 100 */
+    float    MaxDivergenceSolverError;        /* 10 [%] */
+    uint32_t EnableViscositySolver;           /* bool, 1 */
+    uint32_t MinViscositySolverIterations;    /* 0   */
+    uint32_t MaxViscositySolverIterations;    /* 100 */
+    float    MaxViscositySolverError;         /* 0.1 [%] */
+    float    Viscosity;                       /* 10  */
+    float    BoundaryViscosity;               /* 10  */
+    float    TangentialDistanceFactor;        /* 0.5 */
+    uint32_t EnableSurfaceTensionSolver;      /* bool, 1 */
+    uint32_t SurfaceTensionSmoothPassCount;   /* 1 */
+    float    SurfaceTension;                  /* 1 */
+    uint32_t TemporalSmoothing;               /* bool, 0 */
+    int32_t  CSDFix;                          /* -1 */
+    int32_t  CSD;                             /* 10000 */
+    float    ParticleRadius;                  /* 0.025 */
+    float    Gravity[3];                      /* 0, -9.81, 0 */
+} VfdDfsphDescription;
+
+/* Fills *d with the reference's defaults (values above). */
+void vfd_dfsph_default_description(VfdDfsphDescription* d);
+
+/* Byte-for-byte DFSPHSimulationInfo (128 B; `bool TemporalSmoothing` at offset 96).
+ * Reference: VFD/Source/Simulation/DFSPH/Structures/DFSPHSimulationInfo.h:5-44. */
+typedef struct VfdDfsphInfo {
+    uint32_t ParticleCount, RigidBodyCount;
+    float SupportRadius, SupportRadius2, ParticleRadius, ParticleDiameter;
+    float TimeStepSize, TimeStepSize2, TimeStepSizeInverse, TimeStepSize2Inverse;
+    float Volume, Density0, ParticleMass, ParticleMassInverse;
+    float Viscosity, BoundaryViscosity, DynamicViscosity, DynamicBoundaryViscosity;
+    float TangentialDistanceFactor, TangentialDistance;
+    float SurfaceTension;
+    uint32_t SurfaceTensionSampleCount;
+    float ClassifierSlope, ClassifierConstant;
+    uint8_t TemporalSmoothing; uint8_t _pad[3];
+    float SmoothingFactor, Factor, NeighborParticleRadius, MonteCarloFactor;
+    float Gravity[3];
+} VfdDfsphInfo;
+
+/* Byte-for-byte DFSPHParticle (120 B).  Reference: .../Structures/DFSPHParticle.h:8-32. */
+typedef struct VfdParticle {
+    float Position[3], Velocity[3], Acceleration[3], PressureAcceleration[3];
+    float PressureResiduum, Density, DensityAdvection, PressureRho2, PressureRho2V, Factor;
+    float VelocityDifference[3];
+    float MonteCarloSurfaceNormal[3], MonteCarloSurfaceNormalSmooth[3];
+    float MonteCarloSurfaceCurvature, MonteCarloSurfaceCurvatureSmooth, DeltaFinalCurvature;
+} VfdParticle;
+
+/* Byte-for-byte DFSPHParticleSimple (36 B), the baked-frame / renderer format.
+ * Reference: .../Structures/DFSPHParticleSimple.h:8-13. */
+typedef struct VfdParticleSimple { float Position[3], Velocity[3], Acceleration[3]; } VfdParticleSimple;
+
+/* One rigid body = the flattened SDFDeviceData the reference uploads
+ * (VFD/Source/Utility/SDF/SDFDeviceData.cuh:552-566, flattening in SDF.cu:234-283).
+ * Field 0 = signed distance, field 1 = boundary volume (Bender 2019 volume maps).
+ * nodes: fieldCount x nodeCount floats; cells: fieldCount x cellCount x 32 node ids;
+ * cellMap: fieldCount x cellMapCount.  Host pointers; copied by set_rigid_bodies. */
+typedef struct VfdVolumeMap {
+    float    domainMin[3], domainMax[3];
+    uint32_t resolution[3];
+    float    cellSize[3], cellSizeInverse[3];
+    uint32_t fieldCount, nodeCount, cellCount, cellMapCount;
+    const float*    nodes;
+    const uint32_t* cells;
+    const uint32_t* cellMap;
+} VfdVolumeMap;
+
+/* DFSPHDebugInfo with the six phase timers in microseconds (measured with CUDA events).
+ * Reference: VFD/Source/Simulation/DFSPH/Structures/DFSPHDebugInfo.h:8-28. */
+typedef struct VfdDfsphDebugInfo {
+    float NeighborhoodSearchUs, BaseSolverUs, DivergenceSolverUs, SurfaceTensionSolverUs, ViscositySolverUs, PressureSolverUs;
+    uint32_t IterationCount, DivergenceSolverIterationCount, PressureSolverIterationCount, ViscositySolverIterationCount;
+    float DivergenceSolverError, PressureSolverError, ViscositySolverError;
+    float FrameTime;
+    uint32_t FrameIndex;
+} VfdDfsphDebugInfo;
+
+enum { VFD_STATE_NONE = 0, VFD_STATE_SIMULATING = 1, VFD_STATE_READY = 2 };  /* DFSPHImplementation.h:27-32 */
+
+/* ---- lifetime: ctor DFSPHImplementation.cu:14-21, dtor :23-31 (reference hard-codes device 0) ---- */
+int  vfd_dfsph_create(const VfdDfsphDescription* desc, int device, VfdDfsph** out);
+void vfd_dfsph_destroy(VfdDfsph* h);
+const char* vfd_dfsph_last_error(const VfdDfsph* h);   /* h may be NULL: last create() error */
+
+/* ---- configuration: SetDescription :318-368, GetDescription :313, GetInfo :370 ---- */
+int vfd_dfsph_set_description(VfdDfsph* h, const VfdDfsphDescription* desc);
+int vfd_dfsph_get_description(const VfdDfsph* h, VfdDfsphDescription* out);
+int vfd_dfsph_get_info(VfdDfsph* h, VfdDfsphInfo* out);
+
+/* ---- scene: SetFluidObjects :172-253 (after host-side sampling), SetRigidBodies :255-271 ----
+ * pos/vel: n x 3 floats (vel may be NULL = 0).  All other per-particle fields start at 0.
+ * As in the reference, particles must be set before rigid bodies. */
+int vfd_dfsph_set_particles(VfdDfsph* h, const float* pos_xyz, const float* vel_xyz, uint32_t n);
+/* same, from device pointers (inputs already resident in HBM) */
+int vfd_dfsph_set_particles_device(VfdDfsph* h, const float* d_pos_xyz, const float* d_vel_xyz, uint32_t n);
+int vfd_dfsph_set_rigid_bodies(VfdDfsph* h, uint32_t count, const VfdVolumeMap* maps);
+
+/* ---- run: Simulate :33-61 (bakes FrameCount frames from the stored initial state), OnUpdate :63-170 ---- */
+int vfd_dfsph_simulate(VfdDfsph* h);
+int vfd_dfsph_begin(VfdDfsph* h);                 /* what Simulate() does before its loop (:36-51): reset to the initial state */
+int vfd_dfsph_step(VfdDfsph* h);                  /* one OnUpdate(); asynchronous w.r.t. the host where the solver settings allow */
+int vfd_dfsph_steps(VfdDfsph* h, uint32_t count); /* count x OnUpdate() */
+int vfd_dfsph_synchronize(VfdDfsph* h);
+
+/* ---- getters: GetSimulationState :273, GetDebugInfo :390, GetMaxVelocityMagnitude :298,
+ *      GetCurrentTimeStepSize :303, GetParticleCount :288, GetParticleRadius :293, GetRigidBodyCount :385 ---- */
+int      vfd_dfsph_get_state(const VfdDfsph* h);
+int      vfd_dfsph_get_debug_info(VfdDfsph* h, VfdDfsphDebugInfo* out);
+float    vfd_dfsph_get_max_velocity_magnitude(VfdDfsph* h);
+float    vfd_dfsph_get_current_time_step_size(VfdDfsph* h);
+uint32_t vfd_dfsph_get_particle_count(const VfdDfsph* h);
+float    vfd_dfsph_get_particle_radius(const VfdDfsph* h);
+uint32_t vfd_dfsph_get_rigid_body_count(const VfdDfsph* h);
+
+/* ---- baked frames: GetParticleFrameBuffer :278 -> DFSPHParticleFrame (ParticleBuffer/DFSPHParticleBuffer.h:13-19).
+ * out: n x 36 B in ORIGINAL particle order (the renderer's flow lines index particles across
+ * frames: VFD/Source/Scene/Scene.cpp:361-368). */
+int vfd_dfsph_get_frame_count(const VfdDfsph* h, uint32_t* baked);
+int vfd_dfsph_get_frame(VfdDfsph* h, uint32_t index, VfdParticleSimple* out, float* maxVelocityMagnitude, float* currentTimeStep);
+/* the current state in frame format (what the next captured frame would hold) */
+int vfd_dfsph_get_current_frame(VfdDfsph* h, VfdParticleSimple* out);
+
+/* ---- inspector only: ParticleSearch::GetByteSize ParticleSearch.cu:11, GetBounds ParticleSearch.h:63 ---- */
+int vfd_dfsph_get_search_bytes(const VfdDfsph* h, uint64_t* bytes);
+int vfd_dfsph_get_bounds(VfdDfsph* h, float bmin[3], float bmax[3]);
+
+/* ---- no reference equivalent: state dump / restore (checkpoint-resume, parity tests) ---- */
+int vfd_dfsph_get_particles(VfdDfsph* h, VfdParticle* out);              /* n x 120 B, original order */
+int vfd_dfsph_set_particles_full(VfdDfsph* h, const VfdParticle* in);    /* n x 120 B, original order */
+int vfd_dfsph_set_time_step(VfdDfsph* h, float dt);                      /* override the running dt (restart from a dump) */
+int vfd_dfsph_set_surface_tension_state(VfdDfsph* h, uint32_t sampleCount, float monteCarloFactor);
+/* neighbour search only, on the current positions (ParticleSearch::FindNeighbors, ParticleSearch.h:48-61) */
+int vfd_dfsph_find_neighbors(VfdDfsph* h);
+/* CSR neighbour list of the last search in ORIGINAL particle ids, each list sorted ascending.
+ * counts/offsets: n entries; ids: capacity entries; *total receives the list length (pass ids=NULL to size). */
+int vfd_dfsph_get_neighbors(VfdDfsph* h, uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t capacity, uint64_t* total);
+/* boundary samples of body b after the last step (RigidBody.cuh:39-40): xj n x 3, volume n; original order */
+int vfd_dfsph_get_boundary(VfdDfsph* h, uint32_t body, float* xj, float* volume);
+/* the 10 000-entry cubic-spline lookup tables (Kernel/DFSPHKernels.h:13-41): W[10000], gradW[10001] */
+int vfd_dfsph_get_kernel_tables(VfdDfsph* h, float* W, float* gradW, float* scalars6 /* radius, radius2, invStep, WZero, K, L */);
+/* the regenerated 16384-point Halton sphere table (reference data file: HaltonVec323.cuh:4-1643): 49152 floats */
+int vfd_dfsph_get_halton_table(VfdDfsph* h, float* out49152);
+
+/* the same two tables without a handle or a device (pure host arithmetic; used by CPU-side tests) */
+int vfd_kernel_tables_build(float supportRadius, float* W, float* gradW, float* scalars6);
+int vfd_halton_table_build(float* out49152);
+
+/* options (no reference equivalent) */
+enum {
+    VFD_OPT_SEARCH_FMA = 1,       /* 1 (default): d2 = fma(dz,dz,fma(dx,dx,dy*dy)) as nvcc compiles the reference's test
+                                     (ParticleSearchKernels.cu:123-126); 0: (dx*dx+dy*dy)+dz*dz as a host compiler does */
+    VFD_OPT_TIMERS = 2,           /* 1: record the six phase timers with CUDA events (default 0) */
+    VFD_OPT_MAX_CELLS = 3,        /* upper bound on search-grid cells (default 1<<27) */
+};
+int vfd_dfsph_set_option(VfdDfsph* h, int option, int64_t value);
+
+/* per-kernel accounting for bench.py: number of kernels launched since the last reset */
+int vfd_dfsph_get_launch_count(VfdDfsph* h, uint64_t* launches, int reset);
+
+/* ---- scene preparation helper (reference: RigidBody.cu:32-72 over SDF.cu:45-139) ----
+ * Builds the two-field volume map of an axis-aligned box on the GPU: field 0 = sign*(d_box - (padding - r)),
+ * field 1 = 0.8 * integral over |xi|<h of gamma(phi(x+xi)) by 30^3-point Gauss-Legendre quadrature.
+ * Arrays are returned in malloc'ed host memory owned by the map; release with vfd_volume_map_free. */
+int  vfd_volume_map_build_box(const float bmin[3], const float bmax[3], int inverted, float padding,
+                              const uint32_t resolution[3], float particleRadius, int device, VfdVolumeMap* out);
+void vfd_volume_map_free(VfdVolumeMap* map);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFD_DFSPH_H */

@@ -1,0 +1,77 @@
+"""vfd_b200/build.py — compiles libvfd_dfsph.so (hand-written CUDA for sm_100a + the C ABI) in-tree.
+
+    python -m vfd_b200.build [--force] [--verbose]
+
+Output: vfd_b200/lib/libvfd_dfsph.so (git-ignored; travels to the GPU box with the snapshot).
+"""
+import argparse
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libvfd_dfsph.so")
+OBJDIR = os.path.join(HERE, "build")
+
+CU = ["search.cu", "boundary.cu", "pressure.cu", "viscosity.cu", "surface_tension.cu", "solver.cu", "api.cu", "volume_map.cu"]
+CPP = ["tables.cpp"]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "--expt-relaxed-constexpr"]
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in CU + CPP if os.path.exists(os.path.join(CSRC, f))]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    deps.append(os.path.join(HERE, "..", "include", "vfd_dfsph.h"))
+    return _newest(deps) > os.path.getmtime(LIB)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    srcs = sources()
+    objs = [os.path.join(OBJDIR, os.path.basename(s) + ".o") for s in srcs]
+
+    def cc(i):
+        s, o = srcs[i], objs[i]
+        if s.endswith(".cu"):
+            cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        else:
+            cmd = ["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-I/usr/local/cuda/include", "-c", s, "-o", o]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("compile failed: %s\n%s" % (" ".join(cmd), r.stdout[-8000:]))
+        return r.stdout
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        outs = list(ex.map(cc, range(len(srcs))))
+    if verbose:
+        print("\n".join(outs))
+    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout[-8000:]))
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(a.force, a.verbose))

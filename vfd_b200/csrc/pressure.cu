@@ -1,0 +1,373 @@
+// pressure.cu — the DFSPH core: density, factor, the divergence-free and constant-density Jacobi
+// solvers, time integration and the CFL update.
+//
+// Replaces (reference: DFSPHKernels.cu) ComputeDensityKernel :152, ComputeDFSPHFactorKernel :189,
+// ClearAccelerationKernel :24, ComputeDensityChangeKernel :483, ComputePressureAccelerationAnd-
+// DivergenceKernel :388, DivergenceSolveIterationKernel :531, ComputePressureAccelerationAndFactor-
+// Kernel :555, ComputeDensityAdvectionKernel :233, ComputePressureAccelerationKernel :342,
+// PressureSolveIterationKernel :317, ComputePressureAccelerationAndVelocityKernel :434,
+// ComputeVelocityKernel :39, ComputePositionKernel :54, and the host logic around them
+// (DFSPHImplementation.cu: ComputeDivergence :506-575, ComputePressure :443-504,
+// ComputeTimeStepSize :395-428, ComputeMaxVelocityMagnitude :430-441).
+//
+// All kernels are persistent (grid = SMs x resident CTAs, grid-stride over 256-particle tiles) so the
+// 40-kB kernel lookup table is staged into shared memory once per CTA, one thread per particle,
+// neighbours streamed from the warp-blocked list and gathered with 16-B loads.  Solver control
+// (iteration counters, residual means, continue flags) lives in DevState: the loop-carried decision
+// of the reference's host loops is taken by the last block of the iteration kernel.
+#include "solver.h"
+#include <algorithm>
+
+namespace vfd {
+
+extern __shared__ __align__(16) float smemLut[];
+
+#define FOR_EACH_TILE(p) for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += gridDim.x * blockDim.x)
+
+// ---- K2 + K3 + K8 fused: density, DFSPH factor, a = g --------------------------------------
+__global__ void __launch_bounds__(512) k_density_factor(Params P, Arrays A, const float* __restrict__ lutW, const float* __restrict__ lutG) {
+    float* sW = smemLut;
+    float* sG = smemLut + VFD_LUT_RES;
+    load_lut(sW, lutW);
+    load_lut(sG, lutG);
+    __syncthreads();
+    Lut K{ sW, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 };
+    const float4* __restrict__ pos = A.pos;
+    FOR_EACH_TILE(p) {
+        const float3 xi = f3(pos[p]);
+        const uint32_t m = A.cnt[p];
+        const uint32_t* col = nbr_column(A.list, p);
+        float rho = P.volume * P.wZero;
+        float3 gradI = f3(0.0f, 0.0f, 0.0f);
+        float sumK = 0.0f;
+        for (uint32_t k = 0; k < m; k++) {
+            const uint32_t j = col[(size_t)k * 32];
+            const float3 xij = xi - f3(pos[j]);
+            rho += P.volume * K.w(xij);
+            const float3 gj = -P.volume * K.gradW(xij);
+            sumK += dot3(gj, gj);
+            gradI -= gj;
+        }
+        for (uint32_t b = 0; b < P.nBodies; b++) {
+            const float4 bx = A.bx[b][p];
+            if (bx.w > 0.0f) {
+                const float3 xib = xi - f3(bx);
+                rho += bx.w * K.w(xib);
+                const float3 gj = -bx.w * K.gradW(xib);
+                gradI -= gj;
+            }
+        }
+        rho *= P.rho0;
+        sumK += dot3(gradI, gradI);
+        A.rho[p] = rho;
+        A.posRho[p] = make_float4(xi.x, xi.y, xi.z, rho);
+        A.alpha[p] = (sumK > VFD_EPS_F) ? 1.0f / sumK : 0.0f;
+        A.acc[p] = make_float4(P.gx, P.gy, P.gz, 0.0f);
+    }
+}
+
+// ---- K4 / K10: solver source terms ----------------------------------------------------------
+// rate = V * sum_j (v_i - v_j) . gradW_ij + sum_b V_b v_i . gradW_ib
+__device__ __forceinline__ float velocity_divergence(const Params& P, const Arrays& A, const Lut& K, uint32_t p, uint32_t m) {
+    const float4* __restrict__ pos = A.posRho;
+    const float4* __restrict__ vel = A.vel;
+    const float3 xi = f3(pos[p]);
+    const float3 vi = f3(vel[p]);
+    const uint32_t* col = nbr_column(A.list, p);
+    float s = 0.0f;
+    for (uint32_t k = 0; k < m; k++) {
+        const uint32_t j = col[(size_t)k * 32];
+        s += dot3(vi - f3(vel[j]), K.gradW(xi - f3(pos[j])));
+    }
+    s *= P.volume;
+    for (uint32_t b = 0; b < P.nBodies; b++) {
+        const float4 bx = A.bx[b][p];
+        if (bx.w > 0.0f) s += bx.w * dot3(vi, K.gradW(xi - f3(bx)));
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(VFD_TPB) k_divergence_source(Params P, Arrays A, DevState* S, const float* __restrict__ lutG) {
+    load_lut(smemLut, lutG);
+    __syncthreads();
+    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
+    const float dtInv = S->dtInv;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // loop entry of ComputeDivergence (DFSPHImplementation.cu:526-532): error 0, so the loop is
+        // entered only through the minimum iteration count
+        S->divIt = 0; S->divErr = 0.0f;
+        S->divActive = (0u < P.minDivIt && 0u < P.maxDivIt) ? 1u : 0u;
+    }
+    FOR_EACH_TILE(p) {
+        const uint32_t m = A.cnt[p];
+        float adv = velocity_divergence(P, A, K, p, m);
+        adv = m < 20u ? 0.0f : fmaxf(adv, 0.0f);
+        const float factor = A.alpha[p] * dtInv;
+        A.rhoAdv[p] = adv;
+        A.alpha[p] = factor;
+        A.kappaV[p] = adv * factor;
+    }
+}
+
+__global__ void __launch_bounds__(VFD_TPB) k_pressure_source(Params P, Arrays A, DevState* S, const float* __restrict__ lutG) {
+    load_lut(smemLut, lutG);
+    __syncthreads();
+    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
+    const float dt = S->dt, dt2Inv = S->dt2Inv;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S->pressIt = 0; S->pressErr = 0.0f;
+        S->pressActive = (0u < P.minPressIt && 0u < P.maxPressIt) ? 1u : 0u;   // DFSPHImplementation.cu:455-461
+    }
+    FOR_EACH_TILE(p) {
+        const uint32_t m = A.cnt[p];
+        const float delta = velocity_divergence(P, A, K, p, m);
+        const float adv = A.rho[p] / P.rho0 + dt * delta;
+        const float factor = A.alpha[p] * dt2Inv;
+        const float si = 1.0f - adv;
+        const float residuum = fminf(si, 0.0f);
+        A.rhoAdv[p] = adv;
+        A.alpha[p] = factor;
+        A.kappa[p] = -residuum * factor;
+    }
+}
+
+// ---- K5 / K7 / K11 / K13: pressure acceleration from kappa ---------------------------------
+enum { ACC_DIV_ITER = 0, ACC_DIV_FINISH = 1, ACC_PRESS_ITER = 2, ACC_PRESS_FINISH = 3 };
+
+template<int MODE>
+__global__ void __launch_bounds__(VFD_TPB) k_pressure_accel(Params P, Arrays A, const DevState* __restrict__ S, const float* __restrict__ lutG) {
+    if (MODE == ACC_DIV_ITER && !S->divActive) return;
+    if (MODE == ACC_PRESS_ITER && !S->pressActive) return;
+    load_lut(smemLut, lutG);
+    __syncthreads();
+    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
+    const float4* __restrict__ pos = A.posRho;
+    const float* __restrict__ kap = (MODE == ACC_DIV_ITER || MODE == ACC_DIV_FINISH) ? A.kappaV : A.kappa;
+    const float dt = S->dt;
+    FOR_EACH_TILE(p) {
+        const float3 xi = f3(pos[p]);
+        const float ki = kap[p];
+        const uint32_t m = A.cnt[p];
+        const uint32_t* col = nbr_column(A.list, p);
+        float3 a = f3(0.0f, 0.0f, 0.0f);
+        for (uint32_t k = 0; k < m; k++) {
+            const uint32_t j = col[(size_t)k * 32];
+            const float ks = ki + kap[j];
+            if (fabsf(ks) > VFD_EPS_F) {
+                const float3 gj = -P.volume * K.gradW(xi - f3(pos[j]));
+                a += ks * gj;
+            }
+        }
+        if (fabsf(ki) > VFD_EPS_F) {
+            for (uint32_t b = 0; b < P.nBodies; b++) {
+                const float4 bx = A.bx[b][p];
+                if (bx.w > 0.0f) {
+                    const float3 gj = -bx.w * K.gradW(xi - f3(bx));
+                    a += ki * gj;
+                }
+            }
+        }
+        A.pacc[p] = make_float4(a.x, a.y, a.z, 0.0f);
+        if (MODE == ACC_DIV_FINISH || MODE == ACC_PRESS_FINISH) {
+            float4 v = A.vel[p];
+            v.x += dt * a.x; v.y += dt * a.y; v.z += dt * a.z;
+            A.vel[p] = v;
+        }
+        if (MODE == ACC_DIV_FINISH) A.alpha[p] *= dt;
+    }
+}
+
+// ---- K6 / K12 (+ R1 / R3): one Jacobi update and the fused residual reduction ----------------
+template<bool DIV>
+__global__ void __launch_bounds__(VFD_TPB) k_solve_iteration(Params P, Arrays A, DevState* S, const float* __restrict__ lutG) {
+    if (DIV ? !S->divActive : !S->pressActive) return;
+    __shared__ double shRed[32];
+    load_lut(smemLut, lutG);
+    __syncthreads();
+    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
+    const float4* __restrict__ pos = A.posRho;
+    const float4* __restrict__ pacc = A.pacc;
+    const float scale = DIV ? S->dt : S->dt2;
+    float errSum = 0.0f;
+    FOR_EACH_TILE(p) {
+        const float3 xi = f3(pos[p]);
+        const float3 ai = f3(pacc[p]);
+        const uint32_t m = A.cnt[p];
+        const uint32_t* col = nbr_column(A.list, p);
+        float s = 0.0f;
+        for (uint32_t k = 0; k < m; k++) {
+            const uint32_t j = col[(size_t)k * 32];
+            s += dot3(ai - f3(pacc[j]), K.gradW(xi - f3(pos[j])));
+        }
+        s *= P.volume;
+        for (uint32_t b = 0; b < P.nBodies; b++) {
+            const float4 bx = A.bx[b][p];
+            if (bx.w > 0.0f) s += bx.w * dot3(ai, K.gradW(xi - f3(bx)));
+        }
+        s *= scale;
+        float residuum;
+        if (DIV) {
+            residuum = m < 20u ? 0.0f : fminf(-A.rhoAdv[p] - s, 0.0f);
+            A.kappaV[p] -= residuum * A.alpha[p];
+        } else {
+            residuum = fminf(1.0f - A.rhoAdv[p] - s, 0.0f);
+            A.kappa[p] -= residuum * A.alpha[p];
+        }
+        A.res[p] = residuum;
+        errSum += P.rho0 * residuum;
+    }
+    double v[1] = { (double)errSum };
+    uint32_t* ticket = &S->ticket[DIV ? 1 : 2];
+    if (block_reduce_publish<1>(v, A.partials, ticket, shRed)) {
+        double tot[1];
+        last_block_fold<1>(tot, A.partials, shRed);
+        if (threadIdx.x == 0) {
+            // the reference folds with thrust::minus from 0 (DFSPHImplementation.cu:483-489, 554-560):
+            // as a left fold that is -(sum), the mean of rho0*|residuum|
+            const float err = (float)(-tot[0]) / (float)P.n;
+            if (DIV) {
+                const uint32_t it = S->divIt + 1;
+                const float eta = S->dtInv * P.divErrScale;
+                S->divIt = it; S->divErr = err;
+                S->divActive = ((err > eta || it < P.minDivIt) && it < P.maxDivIt) ? 1u : 0u;
+            } else {
+                const uint32_t it = S->pressIt + 1;
+                S->pressIt = it; S->pressErr = err;
+                S->pressActive = ((err > P.etaPressure || it < P.minPressIt) && it < P.maxPressIt) ? 1u : 0u;
+            }
+            *ticket = 0;
+        }
+    }
+}
+
+// ---- R2 + ComputeTimeStepSize: CFL on the device ---------------------------------------------
+__global__ void __launch_bounds__(VFD_TPB) k_cfl(Params P, Arrays A, DevState* S) {
+    __shared__ double shRed[32];
+    const float dt = S->dt;
+    float mx = 0.0f;
+    FOR_EACH_TILE(p) {
+        const float4 v = A.vel[p], a = A.acc[p];
+        const float3 w = f3(v.x + a.x * dt, v.y + a.y * dt, v.z + a.z * dt);
+        mx = fmaxf(mx, dot3(w, w));
+    }
+    double v[1] = { (double)mx };
+    if (block_reduce_publish<1>(v, A.partials, &S->ticket[3], shRed, true)) {
+        double tot[1];
+        last_block_fold<1>(tot, A.partials, shRed, true);
+        if (threadIdx.x == 0) {
+            float vmax2 = fmaxf((float)tot[0], 0.1f);              // initial value 0.1 (DFSPHImplementation.cu:397)
+            if (vmax2 < 1.0e-9f) vmax2 = 1.0e-9f;
+            float ndt = 0.4f * (P.d / sqrtf(vmax2));
+            ndt = fminf(ndt, P.maxDt);
+            ndt = fmaxf(ndt, P.minDt);
+            S->vmax2 = vmax2;
+            S->dt = ndt; S->dt2 = ndt * ndt; S->dtInv = 1.0f / ndt; S->dt2Inv = 1.0f / (ndt * ndt);
+            S->sampleCount = P.csdFix > 0 ? (uint32_t)P.csdFix : (uint32_t)(int)((float)P.csd * ndt);
+            S->mcFactor = P.mcFactor;
+            S->frameTime += ndt;
+            S->stepCount += 1;
+            S->ticket[3] = 0;
+        }
+    }
+}
+
+// K9: v += dt * a
+__global__ void __launch_bounds__(VFD_TPB) k_velocity(Params P, Arrays A, const DevState* __restrict__ S) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const float dt = S->dt;
+    float4 v = A.vel[p];
+    const float4 a = A.acc[p];
+    v.x += dt * a.x; v.y += dt * a.y; v.z += dt * a.z;
+    A.vel[p] = v;
+}
+
+// K14: x += dt * v
+__global__ void __launch_bounds__(VFD_TPB) k_position(Params P, Arrays A, const DevState* __restrict__ S) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const float dt = S->dt;
+    float4 x = A.posRho[p];
+    const float4 v = A.vel[p];
+    x.x += dt * v.x; x.y += dt * v.y; x.z += dt * v.z;
+    A.pos[p] = x;
+}
+
+__global__ void k_clear_acc(Params P, Arrays A) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P.n) A.acc[p] = make_float4(P.gx, P.gy, P.gz, 0.0f);
+}
+
+// ---- launchers -------------------------------------------------------------------------------
+static const size_t LUT_BYTES = VFD_LUT_RES * sizeof(float);
+
+template<typename Kern>
+static uint32_t persistent_grid(Kern kern, int threads, size_t smem, const LaunchCfg& L, uint32_t n) {
+    static thread_local const void* cachedK[16]; static thread_local int cachedV[16]; static thread_local int nc = 0;
+    int perSM = 0;
+    for (int i = 0; i < nc; i++) if (cachedK[i] == (const void*)kern) perSM = cachedV[i];
+    if (!perSM) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, threads, smem);
+        if (perSM < 1) perSM = 1;
+        if (nc < 16) { cachedK[nc] = (const void*)kern; cachedV[nc] = perSM; nc++; }
+    }
+    const uint32_t tiles = (n + threads - 1) / threads;
+    return std::max(1u, std::min<uint32_t>(tiles, (uint32_t)(perSM * L.numSMs)));
+}
+
+void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState*, const float* lutW, const float* lutG) {
+    const uint32_t g = persistent_grid(k_density_factor, 512, 2 * LUT_BYTES, L, P.n);
+    k_density_factor<<<g, 512, 2 * LUT_BYTES, L.stream>>>(P, A, lutW, lutG);
+    *L.launchCounter += 1;
+}
+void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const uint32_t g = persistent_grid(k_divergence_source, VFD_TPB, LUT_BYTES, L, P.n);
+    k_divergence_source<<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    *L.launchCounter += 1;
+}
+void launch_divergence_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const uint32_t g1 = persistent_grid(k_pressure_accel<ACC_DIV_ITER>, VFD_TPB, LUT_BYTES, L, P.n);
+    k_pressure_accel<ACC_DIV_ITER><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    const uint32_t g2 = persistent_grid(k_solve_iteration<true>, VFD_TPB, LUT_BYTES, L, P.n);
+    k_solve_iteration<true><<<g2, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    *L.launchCounter += 2;
+}
+void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const uint32_t g = persistent_grid(k_pressure_accel<ACC_DIV_FINISH>, VFD_TPB, LUT_BYTES, L, P.n);
+    k_pressure_accel<ACC_DIV_FINISH><<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    *L.launchCounter += 1;
+}
+void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const uint32_t g = persistent_grid(k_pressure_source, VFD_TPB, LUT_BYTES, L, P.n);
+    k_pressure_source<<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    *L.launchCounter += 1;
+}
+void launch_pressure_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const uint32_t g1 = persistent_grid(k_pressure_accel<ACC_PRESS_ITER>, VFD_TPB, LUT_BYTES, L, P.n);
+    k_pressure_accel<ACC_PRESS_ITER><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    const uint32_t g2 = persistent_grid(k_solve_iteration<false>, VFD_TPB, LUT_BYTES, L, P.n);
+    k_solve_iteration<false><<<g2, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    *L.launchCounter += 2;
+}
+void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const uint32_t g = persistent_grid(k_pressure_accel<ACC_PRESS_FINISH>, VFD_TPB, LUT_BYTES, L, P.n);
+    k_pressure_accel<ACC_PRESS_FINISH><<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    *L.launchCounter += 1;
+}
+void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A) {
+    k_clear_acc<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A);
+    *L.launchCounter += 1;
+}
+void launch_cfl_and_velocity(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    const uint32_t tiles = (P.n + VFD_TPB - 1) / VFD_TPB;
+    k_cfl<<<std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 8u)), VFD_TPB, 0, L.stream>>>(P, A, S);
+    k_velocity<<<tiles, VFD_TPB, 0, L.stream>>>(P, A, S);
+    *L.launchCounter += 2;
+}
+void launch_positions(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    k_position<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, S);
+    *L.launchCounter += 1;
+}
+
+} // namespace vfd

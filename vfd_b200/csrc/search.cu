@@ -1,0 +1,268 @@
+// search.cu — neighbourhood search: cell hashing, single-pass radix (counting) sort keyed by
+// the cell id, physical reorder of the particle SoA, cell tables and neighbour lists.
+//
+// Replaces ParticleSearch::FindNeighbors (reference: ParticleSearch/ParticleSearch.h:48-61,
+// ParticleSearch.cu:29-195, kernels ParticleSearchKernels.cu:40-192).  The parity obligation is
+// the neighbour *set* of every particle:  { j : 0 < |x_j - x_i|^2 < h^2 }, capped at 70
+// (ParticleSearchKernels.cu:126,131).  Differences by design:
+//   * particles are physically reordered every step (the reference only builds an index
+//     permutation and gathers 120-B AoS structs through it);
+//   * the cell key is x-fastest inside a (y,z) row, so the 27-cell stencil is 9 contiguous
+//     candidate ranges [cellBegin[c-1], cellBegin[c+2]) instead of 27 table lookups;
+//   * in-cell order is by previous slot index (deterministic), not by atomic arrival;
+//   * one traversal writes the list (fixed-capacity warp-blocked ELL), instead of count+scan+fill;
+//   * no host round trip: the grid is derived on the device.
+#include "solver.h"
+#include <limits.h>
+
+namespace vfd {
+
+#define SCAN_ITEMS 16
+#define SCAN_TILE (VFD_TPB * SCAN_ITEMS)   // 4096 cells per tile
+
+// cell slightly larger than h so that two particles closer than h can never be two cells apart
+// through fp32 rounding of the cell coordinate
+__device__ __forceinline__ float cell_inv(float h) { return (1.0f / h) * (1.0f - 1.0f / 1024.0f); }
+
+__device__ __forceinline__ uint3 cell_of(float4 x, const DevState* S, float invCell) {
+    uint3 c;
+    c.x = (uint32_t)((x.x - S->gridOrigin[0]) * invCell);
+    c.y = (uint32_t)((x.y - S->gridOrigin[1]) * invCell);
+    c.z = (uint32_t)((x.z - S->gridOrigin[2]) * invCell);
+    // robustness against NaN / escaped particles: clamp into the padded interior
+    c.x = min(max(c.x, 1u), S->gridDim[0] - 2u);
+    c.y = min(max(c.y, 1u), S->gridDim[1] - 2u);
+    c.z = min(max(c.z, 1u), S->gridDim[2] - 2u);
+    return c;
+}
+
+// S1: extrema of floor(x/h) (same definition as ComputeMinMaxKernel, ParticleSearchKernels.cu:40-62),
+// then the last block derives the grid.
+__global__ void __launch_bounds__(VFD_TPB) k_bounds(Params P, const float4* __restrict__ pos, DevState* S, uint32_t cellCapacity) {
+    int mn[3] = { INT_MAX, INT_MAX, INT_MAX }, mx[3] = { INT_MIN, INT_MIN, INT_MIN };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += gridDim.x * blockDim.x) {
+        const float4 x = pos[i];
+        const int cx = (int)floorf(x.x / P.h), cy = (int)floorf(x.y / P.h), cz = (int)floorf(x.z / P.h);
+        mn[0] = min(mn[0], cx); mn[1] = min(mn[1], cy); mn[2] = min(mn[2], cz);
+        mx[0] = max(mx[0], cx); mx[1] = max(mx[1], cy); mx[2] = max(mx[2], cz);
+    }
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
+        mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        #pragma unroll
+        for (int k = 0; k < 3; k++) { atomicMin(&S->boundsMin[k], mn[k]); atomicMax(&S->boundsMax[k], mx[k]); }
+    }
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(&S->ticket[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        unsigned long long cells = 1ull;
+        for (int k = 0; k < 3; k++) {
+            const int lo = *(volatile int*)&S->boundsMin[k], hi = *(volatile int*)&S->boundsMax[k];
+            S->gridMinCell[k] = lo;                      // reported bounds (ParticleSearch.cu:50-54)
+            const long long dim = (long long)hi - lo + 5;   // two pad cells below, two above
+            S->gridDim[k] = (uint32_t)min(dim, 1ll << 20);
+            S->gridOrigin[k] = (float)(lo - 2) * P.h;
+            cells *= (unsigned long long)S->gridDim[k];
+        }
+        if (cells + 1 > cellCapacity) { S->errorFlags |= 1u; S->gridDim[0] = S->gridDim[1] = S->gridDim[2] = 3; cells = 27; }
+        S->nCells = (uint32_t)cells;
+        S->boundsMax[0] = S->boundsMax[1] = S->boundsMax[2] = INT_MIN;   // re-arm for the next step
+        // keep the reported maximum cell for GetBounds in the padded slots of boundsMin? no: store in gridMinCell/gridDim
+        S->boundsMin[0] = S->boundsMin[1] = S->boundsMin[2] = INT_MAX;
+        S->ticket[0] = 0;
+    }
+}
+
+// S2: cell key + arrival rank (the digit histogram of the single radix pass)
+__global__ void __launch_bounds__(VFD_TPB) k_hist(Params P, const float4* __restrict__ pos, const DevState* __restrict__ S,
+                                                  uint32_t* __restrict__ key, uint32_t* __restrict__ rank, uint32_t* cellCount) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const uint3 c = cell_of(pos[i], S, cell_inv(P.h));
+    const uint32_t k = (c.z * S->gridDim[1] + c.y) * S->gridDim[0] + c.x;
+    key[i] = k;
+    rank[i] = atomicAdd(&cellCount[k], 1u);
+}
+
+// S3: exclusive scan of the cell histogram in three phases over 4096-cell tiles.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* sh, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (VFD_TPB / 32) ? sh[lane] : 0u, winc = w;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += y; }
+        sh[32 + lane] = winc - w;
+        if (lane == 31) sh[64] = winc;
+    }
+    __syncthreads();
+    total = sh[64];
+    const uint32_t r = sh[32 + warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(VFD_TPB) k_scan_tiles(const DevState* __restrict__ S, const uint32_t* __restrict__ cellCount, uint32_t* __restrict__ tileSums) {
+    __shared__ uint32_t sh[65];
+    const uint32_t nCells = S->nCells, nTiles = (nCells + SCAN_TILE - 1) / SCAN_TILE;
+    for (uint32_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
+        const uint32_t base = t * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+        uint32_t s = 0;
+        #pragma unroll
+        for (int q = 0; q < SCAN_ITEMS; q += 4) {
+            if (base + q + 3 < nCells) { const uint4 v = *reinterpret_cast<const uint4*>(cellCount + base + q); s += v.x + v.y + v.z + v.w; }
+            else for (int u = 0; u < 4; u++) if (base + q + u < nCells) s += cellCount[base + q + u];
+        }
+        uint32_t total;
+        block_exclusive_scan(s, sh, total);
+        if (threadIdx.x == 0) tileSums[t] = total;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(const DevState* __restrict__ S, uint32_t* __restrict__ tileSums) {
+    __shared__ uint32_t sh[33];
+    __shared__ uint32_t carry;
+    const uint32_t nTiles = (S->nCells + SCAN_TILE - 1) / SCAN_TILE;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nTiles; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nTiles ? tileSums[i] : 0u;
+        uint32_t inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+        if (lane == 31) sh[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = sh[lane], winc = w;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += y; }
+            sh[lane] = winc - w;
+            if (lane == 31) sh[32] = winc;
+        }
+        __syncthreads();
+        if (i < nTiles) tileSums[i] = carry + sh[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sh[32];
+        __syncthreads();
+    }
+}
+
+// phase 3 also clears the histogram for the next step (invariant: cellCount is all-zero outside S2..S3)
+__global__ void __launch_bounds__(VFD_TPB) k_scan_apply(Params P, const DevState* __restrict__ S, uint32_t* __restrict__ cellCount,
+                                                        const uint32_t* __restrict__ tileSums, uint32_t* __restrict__ cellBegin) {
+    __shared__ uint32_t sh[65];
+    const uint32_t nCells = S->nCells, nTiles = (nCells + SCAN_TILE - 1) / SCAN_TILE;
+    for (uint32_t t = blockIdx.x; t < nTiles; t += gridDim.x) {
+        const uint32_t base = t * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        uint32_t s = 0;
+        #pragma unroll
+        for (int q = 0; q < SCAN_ITEMS; q++) { v[q] = (base + q < nCells) ? cellCount[base + q] : 0u; s += v[q]; }
+        uint32_t total;
+        uint32_t run = block_exclusive_scan(s, sh, total) + tileSums[t];
+        #pragma unroll
+        for (int q = 0; q < SCAN_ITEMS; q++) {
+            if (base + q < nCells) { cellBegin[base + q] = run; cellCount[base + q] = 0u; }
+            run += v[q];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cellBegin[nCells] = P.n;
+}
+
+// S4: scatter slot indices into cell order (arbitrary order inside a cell)
+__global__ void __launch_bounds__(VFD_TPB) k_scatter(Params P, const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank,
+                                                     const uint32_t* __restrict__ cellBegin, uint32_t* __restrict__ tmpIdx) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    tmpIdx[cellBegin[key[i]] + rank[i]] = i;
+}
+
+// S5: make the in-cell order deterministic (rank by previous slot index) and move the persistent
+// particle state to its sorted slot.
+__global__ void __launch_bounds__(VFD_TPB) k_reorder(Params P, Arrays A) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.n) return;
+    const uint32_t i0 = A.tmpIdx[q];
+    const uint32_t c = A.key[i0];
+    const uint32_t b = A.cellBegin[c], e = A.cellBegin[c + 1];
+    uint32_t r = 0;
+    for (uint32_t t = b; t < e; t++) r += (A.tmpIdx[t] < i0) ? 1u : 0u;
+    const uint32_t dst = b + r;
+    A.pos2[dst] = A.pos[i0];
+    A.vel2[dst] = A.vel[i0];
+    A.dv2[dst] = A.dv[i0];
+    A.nbar2[dst] = A.nbar[i0];
+    A.curv2[dst] = A.curv[i0];
+    A.curvS2[dst] = A.curvS[i0];
+    A.curvD2[dst] = A.curvD[i0];
+    A.id2[dst] = A.id[i0];
+}
+
+// S6/S8: one traversal of the 3x3 rows of 3 cells; candidates of a row are contiguous in memory.
+template<bool FMA>
+__global__ void __launch_bounds__(VFD_TPB) k_build_list(Params P, const float4* __restrict__ pos, const DevState* __restrict__ S,
+                                                        const uint32_t* __restrict__ cellBegin, uint32_t* __restrict__ cnt, uint32_t* __restrict__ list) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const float4 xi = pos[p];
+    const uint3 c = cell_of(xi, S, cell_inv(P.h));
+    const uint32_t dimX = S->gridDim[0], dimY = S->gridDim[1];
+    uint32_t* col = list + (size_t)(p >> 5) * (VFD_MAX_NEIGHBORS * 32) + (p & 31);
+    uint32_t m = 0;
+    for (int dz = -1; dz <= 1 && m < VFD_MAX_NEIGHBORS; dz++) {
+        for (int dy = -1; dy <= 1 && m < VFD_MAX_NEIGHBORS; dy++) {
+            const uint32_t rowKey = ((c.z + dz) * dimY + (c.y + dy)) * dimX + c.x - 1u;
+            const uint32_t jb = cellBegin[rowKey], je = cellBegin[rowKey + 3u];
+            for (uint32_t j = jb; j < je; j++) {
+                const float4 xj = pos[j];
+                const float dx = xj.x - xi.x, dyy = xj.y - xi.y, dzz = xj.z - xi.z;
+                float d2;
+                if (FMA) d2 = __fmaf_rn(dzz, dzz, __fmaf_rn(dx, dx, __fmul_rn(dyy, dyy)));   // how nvcc compiles ParticleSearchKernels.cu:124
+                else     d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dyy, dyy)), __fmul_rn(dzz, dzz));
+                if (d2 < P.h2 && d2 > 0.0f) {
+                    col[(size_t)m * 32] = j;
+                    if (++m == VFD_MAX_NEIGHBORS) break;
+                }
+            }
+        }
+    }
+    cnt[p] = m;
+}
+
+static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, uint32_t cellCapacity, uint32_t cellEstimate) {
+    const uint32_t nb = div_up(P.n, VFD_TPB);
+    const uint32_t gb = std::min<uint32_t>(nb, (uint32_t)L.numSMs * 8u);
+    k_bounds<<<gb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, cellCapacity);
+    k_hist<<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.key, A.rank, A.cellCount);
+    const uint32_t est = std::min<uint64_t>((uint64_t)cellCapacity, std::max<uint64_t>(4ull * cellEstimate, 1u << 16));
+    const uint32_t st = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(est, SCAN_TILE), (uint32_t)L.numSMs * 8u));
+    k_scan_tiles<<<st, VFD_TPB, 0, L.stream>>>(S, A.cellCount, A.tileSums);
+    k_scan_tile_sums<<<1, 1024, 0, L.stream>>>(S, A.tileSums);
+    k_scan_apply<<<st, VFD_TPB, 0, L.stream>>>(P, S, A.cellCount, A.tileSums, A.cellBegin);
+    k_scatter<<<nb, VFD_TPB, 0, L.stream>>>(P, A.key, A.rank, A.cellBegin, A.tmpIdx);
+    k_reorder<<<nb, VFD_TPB, 0, L.stream>>>(P, A);
+    std::swap(A.pos, A.pos2); std::swap(A.vel, A.vel2); std::swap(A.dv, A.dv2); std::swap(A.nbar, A.nbar2);
+    std::swap(A.curv, A.curv2); std::swap(A.curvS, A.curvS2); std::swap(A.curvD, A.curvD2); std::swap(A.id, A.id2);
+    if (P.searchFma) k_build_list<true><<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.cellBegin, A.cnt, A.list);
+    else             k_build_list<false><<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.cellBegin, A.cnt, A.list);
+    *L.launchCounter += 8;
+}
+
+} // namespace vfd

@@ -1,0 +1,693 @@
+// solver.cu — host orchestration of one DFSPH step on one B200 and the dump/restore kernels.
+//
+// Solver::step() is DFSPHImplementation::OnUpdate (reference: DFSPHImplementation.cu:63-170) re-expressed
+// as a stream of kernels with no host round trip unless a solver is convergence-driven (then the
+// continue flag is polled with one batch of look-ahead).  Solver::simulate() is Simulate() (:33-61).
+#include "solver_impl.h"
+#include <algorithm>
+#include <cstring>
+#include <limits.h>
+
+namespace vfd {
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda(e__, #call, __LINE__); } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// dump / restore kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_export_aos(Params P, Arrays A, VfdParticle* __restrict__ out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    VfdParticle q;
+    const float4 x = A.pos[p], v = A.vel[p], a = A.acc[p], pa = A.pacc[p], dv = A.dv[p], n = A.nrm[p], nb = A.nbar[p];
+    q.Position[0] = x.x; q.Position[1] = x.y; q.Position[2] = x.z;
+    q.Velocity[0] = v.x; q.Velocity[1] = v.y; q.Velocity[2] = v.z;
+    q.Acceleration[0] = a.x; q.Acceleration[1] = a.y; q.Acceleration[2] = a.z;
+    q.PressureAcceleration[0] = pa.x; q.PressureAcceleration[1] = pa.y; q.PressureAcceleration[2] = pa.z;
+    q.PressureResiduum = A.res[p]; q.Density = A.rho[p]; q.DensityAdvection = A.rhoAdv[p];
+    q.PressureRho2 = A.kappa[p]; q.PressureRho2V = A.kappaV[p]; q.Factor = A.alpha[p];
+    q.VelocityDifference[0] = dv.x; q.VelocityDifference[1] = dv.y; q.VelocityDifference[2] = dv.z;
+    q.MonteCarloSurfaceNormal[0] = n.x; q.MonteCarloSurfaceNormal[1] = n.y; q.MonteCarloSurfaceNormal[2] = n.z;
+    q.MonteCarloSurfaceNormalSmooth[0] = nb.x; q.MonteCarloSurfaceNormalSmooth[1] = nb.y; q.MonteCarloSurfaceNormalSmooth[2] = nb.z;
+    q.MonteCarloSurfaceCurvature = A.curv[p]; q.MonteCarloSurfaceCurvatureSmooth = A.curvS[p]; q.DeltaFinalCurvature = A.curvD[p];
+    out[A.id[p]] = q;
+}
+
+__global__ void k_import_aos(Params P, Arrays A, const VfdParticle* __restrict__ in) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const VfdParticle q = in[p];
+    A.pos[p] = make_float4(q.Position[0], q.Position[1], q.Position[2], 0.0f);
+    A.posRho[p] = make_float4(q.Position[0], q.Position[1], q.Position[2], q.Density);
+    A.vel[p] = make_float4(q.Velocity[0], q.Velocity[1], q.Velocity[2], 0.0f);
+    A.acc[p] = make_float4(q.Acceleration[0], q.Acceleration[1], q.Acceleration[2], 0.0f);
+    A.pacc[p] = make_float4(q.PressureAcceleration[0], q.PressureAcceleration[1], q.PressureAcceleration[2], 0.0f);
+    A.res[p] = q.PressureResiduum; A.rho[p] = q.Density; A.rhoAdv[p] = q.DensityAdvection;
+    A.kappa[p] = q.PressureRho2; A.kappaV[p] = q.PressureRho2V; A.alpha[p] = q.Factor;
+    A.dv[p] = make_float4(q.VelocityDifference[0], q.VelocityDifference[1], q.VelocityDifference[2], 0.0f);
+    A.nrm[p] = make_float4(q.MonteCarloSurfaceNormal[0], q.MonteCarloSurfaceNormal[1], q.MonteCarloSurfaceNormal[2], q.MonteCarloSurfaceCurvature);
+    A.nbar[p] = make_float4(q.MonteCarloSurfaceNormalSmooth[0], q.MonteCarloSurfaceNormalSmooth[1], q.MonteCarloSurfaceNormalSmooth[2], 0.0f);
+    A.curv[p] = q.MonteCarloSurfaceCurvature; A.curvS[p] = q.MonteCarloSurfaceCurvatureSmooth; A.curvD[p] = q.DeltaFinalCurvature;
+    A.id[p] = p;
+    A.cnt[p] = 0;
+}
+
+// initial state: SetFluidObjects zero-fills everything but position and velocity (DFSPHImplementation.cu:198-220)
+__global__ void k_reset_state(Params P, Arrays A, const float4* __restrict__ pos0, const float4* __restrict__ vel0) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    A.pos[p] = pos0[p]; A.posRho[p] = pos0[p]; A.vel[p] = vel0[p];
+    A.acc[p] = z; A.pacc[p] = z; A.dv[p] = z; A.nrm[p] = z; A.nbar[p] = z;
+    A.res[p] = 0.0f; A.rho[p] = 0.0f; A.rhoAdv[p] = 0.0f; A.kappa[p] = 0.0f; A.kappaV[p] = 0.0f; A.alpha[p] = 0.0f;
+    A.curv[p] = 0.0f; A.curvS[p] = 0.0f; A.curvD[p] = 0.0f;
+    A.id[p] = p; A.cnt[p] = 0;
+    for (uint32_t b = 0; b < P.nBodies; b++) A.bx[b][p] = z;
+}
+
+__global__ void k_pack_posvel(uint32_t n, const float* __restrict__ pos, const float* __restrict__ vel, float4* __restrict__ pos4, float4* __restrict__ vel4) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pos4[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0.0f);
+    vel4[i] = vel ? make_float4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// K15: ConvertParticlesToBuffer (DFSPHKernels.cu:6-22), written in original particle order
+__global__ void k_export_frame(Params P, Arrays A, VfdParticleSimple* __restrict__ out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const float4 x = A.pos[p], v = A.vel[p], a = A.acc[p];
+    VfdParticleSimple q;
+    q.Position[0] = x.x; q.Position[1] = x.y; q.Position[2] = x.z;
+    q.Velocity[0] = v.x; q.Velocity[1] = v.y; q.Velocity[2] = v.z;
+    q.Acceleration[0] = a.x; q.Acceleration[1] = a.y; q.Acceleration[2] = a.z;
+    out[A.id[p]] = q;
+}
+
+__global__ void k_export_neighbors(Params P, Arrays A, uint32_t* __restrict__ counts, uint32_t* __restrict__ idsPadded) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const uint32_t o = A.id[p], m = A.cnt[p];
+    counts[o] = m;
+    const uint32_t* col = nbr_column(A.list, p);
+    for (uint32_t k = 0; k < m; k++) idsPadded[(size_t)o * VFD_MAX_NEIGHBORS + k] = A.id[col[(size_t)k * 32]];
+}
+
+__global__ void k_export_boundary(Params P, Arrays A, uint32_t body, float* __restrict__ xj, float* __restrict__ vol) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const uint32_t o = A.id[p];
+    const float4 b = A.bx[body][p];
+    xj[3 * (size_t)o] = b.x; xj[3 * (size_t)o + 1] = b.y; xj[3 * (size_t)o + 2] = b.z;
+    vol[o] = b.w;
+}
+
+static inline uint32_t nblk(uint32_t n) { return (n + VFD_TPB - 1) / VFD_TPB; }
+
+// ---------------------------------------------------------------------------------------------
+// Solver
+// ---------------------------------------------------------------------------------------------
+int Solver::fail(int code, const std::string& msg) {
+    std::lock_guard<std::mutex> g(errMutex);
+    lastError = msg;
+    return code;
+}
+int Solver::fail_cuda(cudaError_t e, const char* what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at solver.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
+    cudaGetLastError();
+    return fail(VFD_E_CUDA, buf);
+}
+
+int Solver::init(const VfdDfsphDescription& d, int dev) {
+    device = dev;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) { cudaGetLastError(); return fail(VFD_E_CUDA, "no CUDA device available: libvfd_dfsph has no CPU fallback"); }
+    if (dev < 0 || dev >= count) return fail(VFD_E_INVALID, "device index out of range");
+    CK(cudaSetDevice(device));
+    CK(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&dState, sizeof(DevState)));
+    CK(cudaMemset(dState, 0, sizeof(DevState)));
+    CK(cudaMallocHost(&hState, sizeof(DevState) * 4));
+    CK(cudaMallocHost(&hFlags, sizeof(uint32_t) * 64));
+    for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&pollEvent[i], cudaEventDisableTiming));
+    for (int i = 0; i < 7; i++) CK(cudaEventCreate(&phaseEvent[i]));
+    CK(cudaMalloc(&dLutW, VFD_LUT_RES * sizeof(float)));
+    CK(cudaMalloc(&dLutG, VFD_LUT_RES * sizeof(float)));
+    CK(cudaMalloc(&dHalton, VFD_HALTON_N * sizeof(float)));
+    build_halton_table(halton);
+    CK(cudaMemcpy(dHalton, halton.data(), VFD_HALTON_N * sizeof(float), cudaMemcpyHostToDevice));
+    memset(&desc, 0, sizeof desc);
+    memset(&info, 0, sizeof info);          // zero start state
+    return set_description(d);
+}
+
+Solver::~Solver() {
+    if (device >= 0) cudaSetDevice(device);
+    free_particles();
+    free_bodies();
+    cudaFree(dState); cudaFreeHost(hState); cudaFreeHost(hFlags);
+    cudaFree(dLutW); cudaFree(dLutG); cudaFree(dHalton);
+    for (int i = 0; i < 4; i++) if (pollEvent[i]) cudaEventDestroy(pollEvent[i]);
+    for (int i = 0; i < 7; i++) if (phaseEvent[i]) cudaEventDestroy(phaseEvent[i]);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// SetDescription (DFSPHImplementation.cu:318-368): all fp32 host arithmetic, same operations
+int Solver::set_description(const VfdDfsphDescription& d) {
+    CK(cudaSetDevice(device));
+    desc = d;
+    if (desc.ParticleRadius != info.ParticleRadius) {
+        tables.build(4.0f * desc.ParticleRadius);
+        CK(cudaMemcpy(dLutW, tables.Wc.data(), VFD_LUT_RES * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dLutG, tables.Gc.data(), VFD_LUT_RES * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    info.ParticleRadius = desc.ParticleRadius;
+    info.ParticleDiameter = 2.0f * info.ParticleRadius;
+    info.SupportRadius = 4.0f * info.ParticleRadius;
+    info.SupportRadius2 = info.SupportRadius * info.SupportRadius;
+    info.Volume = 0.8f * info.ParticleDiameter * info.ParticleDiameter * info.ParticleDiameter;
+    info.Density0 = 1000.0f;
+    info.ParticleMass = info.Volume * info.Density0;
+    info.ParticleMassInverse = 1.0f / info.ParticleMass;
+    info.Viscosity = desc.Viscosity;
+    info.BoundaryViscosity = desc.BoundaryViscosity;
+    info.DynamicViscosity = info.Viscosity * info.Density0;
+    info.DynamicBoundaryViscosity = info.BoundaryViscosity * info.Density0;
+    info.TangentialDistanceFactor = desc.TangentialDistanceFactor;
+    info.TangentialDistance = info.TangentialDistanceFactor * info.SupportRadius;
+    info.TimeStepSize = desc.TimeStepSize;
+    info.TimeStepSize2 = desc.TimeStepSize * desc.TimeStepSize;
+    info.TimeStepSizeInverse = 1.0f / info.TimeStepSize;
+    info.TimeStepSize2Inverse = 1.0f / info.TimeStepSize2;
+    info.SurfaceTension = desc.SurfaceTension;
+    info.ClassifierSlope = 74.688796680497925f;
+    info.ClassifierConstant = 12.0f;
+    info.TemporalSmoothing = desc.TemporalSmoothing ? 1 : 0;
+    info.SmoothingFactor = 0.5f;
+    info.Factor = 0.8f;
+    info.NeighborParticleRadius = info.ParticleRadius * info.Factor;
+    info.Gravity[0] = desc.Gravity[0]; info.Gravity[1] = desc.Gravity[1]; info.Gravity[2] = desc.Gravity[2];
+    refresh_params();
+    return VFD_OK;
+}
+
+void Solver::refresh_params() {
+    Params& P = params;
+    P.n = info.ParticleCount; P.nBodies = info.RigidBodyCount;
+    P.h = info.SupportRadius; P.h2 = info.SupportRadius2; P.r = info.ParticleRadius; P.d = info.ParticleDiameter;
+    P.volume = info.Volume; P.rho0 = info.Density0; P.mass = info.ParticleMass; P.massInv = info.ParticleMassInverse;
+    P.mu = info.DynamicViscosity; P.muB = info.DynamicBoundaryViscosity; P.tangentialDistance = info.TangentialDistance;
+    P.sigma = info.SurfaceTension; P.clsSlope = info.ClassifierSlope; P.clsConst = info.ClassifierConstant;
+    P.smoothing = info.SmoothingFactor; P.nbrRadius = info.NeighborParticleRadius;
+    // MonteCarloFactor = asin(NeighborParticleRadius / ParticleRadius) (DFSPHImplementation.cu:422), host libm like the reference
+    P.mcFactor = asinf(info.NeighborParticleRadius / info.ParticleRadius);
+    P.temporalSmoothing = info.TemporalSmoothing;
+    P.gx = info.Gravity[0]; P.gy = info.Gravity[1]; P.gz = info.Gravity[2];
+    P.lutInvStep = tables.invStep; P.lutRadius = tables.radius; P.lutRadius2 = tables.radius2; P.wZero = tables.wZero;
+    P.minDt = desc.MinTimeStepSize; P.maxDt = desc.MaxTimeStepSize;
+    P.csdFix = desc.CSDFix; P.csd = desc.CSD;
+    P.frameLength = desc.FrameLength;
+    P.etaPressure = desc.MaxPressureSolverError * 0.0001f * info.Density0;
+    P.divErrScale = desc.MaxDivergenceSolverError * 0.0001f * info.Density0;
+    P.viscErr2 = (desc.MaxViscositySolverError * desc.MaxViscositySolverError) * 0.0001f;
+    P.minPressIt = desc.MinPressureSolverIterations; P.maxPressIt = desc.MaxPressureSolverIterations;
+    P.minDivIt = desc.MinDivergenceSolverIterations; P.maxDivIt = desc.MaxDivergenceSolverIterations;
+    P.minViscIt = desc.MinViscositySolverIterations; P.maxViscIt = desc.MaxViscositySolverIterations;
+    P.searchFma = optSearchFma;
+}
+
+template<typename T> static cudaError_t dalloc(T*& p, size_t count) { return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
+
+void Solver::free_particles() {
+    Arrays& A = arrays;
+    void* ptrs[] = { A.pos, A.vel, A.dv, A.nbar, A.curv, A.curvS, A.curvD, A.id, A.pos2, A.vel2, A.dv2, A.nbar2, A.curv2, A.curvS2, A.curvD2, A.id2,
+                     A.posRho, A.acc, A.pacc, A.nrm, A.res, A.rho, A.rhoAdv, A.kappa, A.kappaV, A.alpha, A.cgG, A.cgR, A.cgP, A.cgQ, A.cgZ, A.minv,
+                     A.cnt, A.list, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.partials, dPos0, dVel0 };
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int b = 0; b < VFD_MAX_BODIES; b++) if (A.bx[b]) cudaFree(A.bx[b]);
+    memset(&A, 0, sizeof A);
+    dPos0 = dVel0 = nullptr;
+    allocBytes = 0;
+}
+
+int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxMax) {
+    free_particles();
+    Arrays& A = arrays;
+    const size_t np = ((size_t)n + 31) / 32 * 32;
+    float4** f4s[] = { &A.pos, &A.vel, &A.dv, &A.nbar, &A.pos2, &A.vel2, &A.dv2, &A.nbar2, &A.posRho, &A.acc, &A.pacc, &A.nrm,
+                       &A.cgG, &A.cgR, &A.cgP, &A.cgQ, &A.cgZ, &dPos0, &dVel0 };
+    for (float4** p : f4s) { CK(dalloc(*p, np)); allocBytes += np * 16; }
+    float** f1s[] = { &A.curv, &A.curvS, &A.curvD, &A.curv2, &A.curvS2, &A.curvD2, &A.res, &A.rho, &A.rhoAdv, &A.kappa, &A.kappaV, &A.alpha };
+    for (float** p : f1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
+    CK(dalloc(A.minv, np * 9)); allocBytes += np * 36;
+    uint32_t** u1s[] = { &A.id, &A.id2, &A.cnt, &A.key, &A.rank, &A.tmpIdx };
+    for (uint32_t** p : u1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
+    CK(dalloc(A.list, np * VFD_MAX_NEIGHBORS)); searchBytes = np * VFD_MAX_NEIGHBORS * 4 + np * 4 * 4;
+    allocBytes += np * VFD_MAX_NEIGHBORS * 4;
+    // search grid capacity: 64x the cells of the initial bounding box (4x per axis of head room)
+    double cells0 = 1.0;
+    for (int k = 0; k < 3; k++) cells0 *= std::ceil((double)(bboxMax[k] - bboxMin[k]) / info.SupportRadius) + 5.0;
+    cellEstimate = (uint32_t)std::min<double>(cells0, (double)optMaxCells);
+    cellCapacity = (uint32_t)std::min<double>(std::max<double>(64.0 * cells0, (double)(1u << 20)), (double)optMaxCells);
+    CK(dalloc(A.cellCount, (size_t)cellCapacity + 4)); CK(dalloc(A.cellBegin, (size_t)cellCapacity + 4));
+    CK(cudaMemset(A.cellCount, 0, ((size_t)cellCapacity + 4) * 4));
+    CK(dalloc(A.tileSums, (size_t)cellCapacity / 4096 + 8));
+    searchBytes += ((size_t)cellCapacity * 2 + 8) * 4;
+    allocBytes += ((size_t)cellCapacity * 2 + 8) * 4;
+    CK(dalloc(A.partials, (size_t)4 * 65536));
+    for (uint32_t b = 0; b < info.RigidBodyCount; b++) { CK(dalloc(A.bx[b], np)); allocBytes += np * 16; }
+    return VFD_OK;
+}
+
+int Solver::set_particles(const float* pos, const float* vel, uint32_t n, bool onDevice) {
+    CK(cudaSetDevice(device));
+    if (!pos && n) return fail(VFD_E_INVALID, "set_particles: null positions");
+    state = VFD_STATE_NONE;
+    info.ParticleCount = n;
+    refresh_params();
+    frames.clear();
+    began = false;
+    if (n == 0) { free_particles(); return VFD_OK; }
+    float *dPos = nullptr, *dVel = nullptr;
+    float bmin[3] = { 0, 0, 0 }, bmax[3] = { 1, 1, 1 };
+    std::vector<float> hostPos;
+    const float* hp = pos;
+    if (onDevice) {
+        hostPos.resize((size_t)3 * n);
+        CK(cudaMemcpy(hostPos.data(), pos, (size_t)12 * n, cudaMemcpyDeviceToHost));
+        hp = hostPos.data();
+    }
+    for (int k = 0; k < 3; k++) { bmin[k] = FLT_MAX; bmax[k] = -FLT_MAX; }
+    for (size_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) { const float v = hp[3 * i + k]; bmin[k] = std::min(bmin[k], v); bmax[k] = std::max(bmax[k], v); }
+    int rc = alloc_particles(n, bmin, bmax);
+    if (rc) return rc;
+    if (onDevice) { dPos = const_cast<float*>(pos); dVel = const_cast<float*>(vel); }
+    else {
+        CK(cudaMalloc(&dPos, (size_t)12 * n));
+        CK(cudaMemcpyAsync(dPos, pos, (size_t)12 * n, cudaMemcpyHostToDevice, stream));
+        if (vel) { CK(cudaMalloc(&dVel, (size_t)12 * n)); CK(cudaMemcpyAsync(dVel, vel, (size_t)12 * n, cudaMemcpyHostToDevice, stream)); }
+    }
+    k_pack_posvel<<<nblk(n), VFD_TPB, 0, stream>>>(n, dPos, dVel, dPos0, dVel0);
+    launches += 1;
+    CK(cudaStreamSynchronize(stream));
+    if (!onDevice) { cudaFree(dPos); if (dVel) cudaFree(dVel); }
+    return begin();
+}
+
+void Solver::free_bodies() {
+    for (auto& p : bodyAllocs) cudaFree(p);
+    bodyAllocs.clear();
+    memset(&bodies, 0, sizeof bodies);
+}
+
+int Solver::set_rigid_bodies(uint32_t count, const VfdVolumeMap* maps) {
+    CK(cudaSetDevice(device));
+    if (count > VFD_MAX_BODIES) return fail(VFD_E_INVALID, "too many rigid bodies (VFD_MAX_BODIES = 8)");
+    if (count && !maps) return fail(VFD_E_INVALID, "set_rigid_bodies: null maps");
+    CK(cudaStreamSynchronize(stream));
+    state = VFD_STATE_NONE;
+    free_bodies();
+    for (uint32_t b = 0; b < count; b++) {
+        const VfdVolumeMap& m = maps[b];
+        if (m.fieldCount < 2 || !m.nodes || !m.cells || !m.cellMap) return fail(VFD_E_INVALID, "volume map needs two fields (SDF, volume) and its three arrays");
+        DevVolumeMap& d = bodies.map[b];
+        for (int k = 0; k < 3; k++) { d.dmin[k] = m.domainMin[k]; d.dmax[k] = m.domainMax[k]; d.res[k] = m.resolution[k]; d.cell[k] = m.cellSize[k]; d.cellInv[k] = m.cellSizeInverse[k]; }
+        d.fieldCount = m.fieldCount; d.nodeCount = m.nodeCount; d.cellCount = m.cellCount; d.cellMapCount = m.cellMapCount;
+        float* dn; uint32_t *dc, *dm;
+        const size_t nn = (size_t)m.fieldCount * m.nodeCount, nc = (size_t)m.fieldCount * m.cellCount * 32, nm = (size_t)m.fieldCount * m.cellMapCount;
+        CK(cudaMalloc(&dn, nn * 4)); bodyAllocs.push_back(dn);
+        CK(cudaMalloc(&dc, nc * 4)); bodyAllocs.push_back(dc);
+        CK(cudaMalloc(&dm, nm * 4)); bodyAllocs.push_back(dm);
+        CK(cudaMemcpy(dn, m.nodes, nn * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dc, m.cells, nc * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dm, m.cellMap, nm * 4, cudaMemcpyHostToDevice));
+        d.nodes = dn; d.cells = dc; d.cellMap = dm;
+    }
+    // per-body boundary sample arrays are sized by the particle count (RigidBody.cu:13-16): particles first
+    const size_t np = ((size_t)info.ParticleCount + 31) / 32 * 32;
+    for (int b = 0; b < VFD_MAX_BODIES; b++) if (arrays.bx[b]) { cudaFree(arrays.bx[b]); arrays.bx[b] = nullptr; }
+    for (uint32_t b = 0; b < count && info.ParticleCount; b++) { CK(dalloc(arrays.bx[b], np)); CK(cudaMemset(arrays.bx[b], 0, np * 16)); }
+    info.RigidBodyCount = count;
+    refresh_params();
+    return VFD_OK;
+}
+
+// What Simulate() does before its loop (DFSPHImplementation.cu:36-51)
+int Solver::begin() {
+    CK(cudaSetDevice(device));
+    if (info.ParticleCount == 0) { began = true; return VFD_OK; }
+    refresh_params();
+    k_reset_state<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dPos0, dVel0);
+    launches += 1;
+    DevState s;
+    memset(&s, 0, sizeof s);
+    s.dt = desc.TimeStepSize; s.dt2 = desc.TimeStepSize * desc.TimeStepSize;
+    s.dtInv = 1.0f / s.dt; s.dt2Inv = 1.0f / s.dt2;
+    s.sampleCount = info.SurfaceTensionSampleCount; s.mcFactor = info.MonteCarloFactor;
+    for (int k = 0; k < 3; k++) { s.boundsMin[k] = INT_MAX; s.boundsMax[k] = INT_MIN; s.gridDim[k] = 3; }
+    s.nCells = 27;
+    hState[0] = s;
+    CK(cudaMemcpyAsync(dState, &hState[0], sizeof(DevState), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    info.TimeStepSize = s.dt; info.TimeStepSize2 = s.dt2; info.TimeStepSizeInverse = s.dtInv; info.TimeStepSize2Inverse = s.dt2Inv;
+    {
+        std::lock_guard<std::mutex> g(dbgMutex);
+        memset(&debug, 0, sizeof debug);
+    }
+    frames.clear();
+    frameTimeHost = 0.0f; frameIndexHost = 0; stepsIssued = 0;
+    began = true;
+    searched = false;
+    return VFD_OK;
+}
+
+int Solver::read_state(DevState& out) {
+    CK(cudaMemcpyAsync(&hState[1], dState, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    out = hState[1];
+    cellEstimate = std::max<uint32_t>(out.nCells, 27u);
+    if (out.errorFlags & 1u) return fail(VFD_E_CAPACITY, "search grid exceeds the cell capacity (raise VFD_OPT_MAX_CELLS; a particle escaped far from the fluid?)");
+    return VFD_OK;
+}
+
+// polls a device flag with one batch of look-ahead; returns true if the loop may stop
+int Solver::run_polled_loop(uint32_t maxIt, uint32_t already, int batch, uint32_t* dFlag, const std::function<void()>& enqueueIteration, uint32_t continueValue) {
+    uint32_t issued = already;
+    int slot = 0, pending = -1;
+    while (issued < maxIt) {
+        for (int b = 0; b < batch && issued < maxIt; b++, issued++) enqueueIteration();
+        CK(cudaMemcpyAsync(&hFlags[slot], dFlag, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CK(cudaEventRecord(pollEvent[slot], stream));
+        if (pending >= 0) {
+            CK(cudaEventSynchronize(pollEvent[pending]));
+            if (hFlags[pending] != continueValue) return VFD_OK;
+        }
+        pending = slot;
+        slot ^= 1;
+    }
+    return VFD_OK;
+}
+
+int Solver::search_only() {
+    CK(cudaSetDevice(device));
+    if (!began) { int rc = begin(); if (rc) return rc; }
+    if (info.ParticleCount == 0) return VFD_OK;
+    refresh_params();
+    LaunchCfg L{ stream, numSMs, &launches };
+    launch_search(L, params, arrays, dState, cellCapacity, cellEstimate);
+    searched = true;
+    CK(cudaGetLastError());
+    return VFD_OK;
+}
+
+int Solver::step() {
+    CK(cudaSetDevice(device));
+    if (!began) { int rc = begin(); if (rc) return rc; }
+    if (info.ParticleCount == 0) return VFD_OK;        // DFSPHImplementation.cu:65-67
+    refresh_params();
+    const Params& P = params;
+    Arrays& A = arrays;
+    LaunchCfg L{ stream, numSMs, &launches };
+    const bool T = optTimers;
+    if (T) cudaEventRecord(phaseEvent[0], stream);
+
+    // 1. neighbourhood search (:71)
+    launch_search(L, P, A, dState, cellCapacity, cellEstimate);
+    searched = true;
+    if (T) cudaEventRecord(phaseEvent[1], stream);
+
+    // 2. boundary samples, density, factor (:79-104); a = g (:112) is fused into the density pass
+    launch_boundary(L, P, A, bodies);
+    launch_density_factor(L, P, A, dState, dLutW, dLutG);
+    if (T) cudaEventRecord(phaseEvent[2], stream);
+
+    // 3. divergence-free solve (:108, :506-575)
+    if (desc.EnableDivergenceSolverError) {
+        launch_divergence_source(L, P, A, dState, dLutG);
+        const uint32_t fixed = std::min(P.minDivIt, P.maxDivIt);
+        for (uint32_t i = 0; i < fixed; i++) launch_divergence_iteration(L, P, A, dState, dLutG);
+        if (fixed > 0 && fixed < P.maxDivIt) {
+            int rc = run_polled_loop(P.maxDivIt, fixed, 2, &dState->divActive, [&] { launch_divergence_iteration(L, P, A, dState, dLutG); }, 1u);
+            if (rc) return rc;
+        }
+        launch_divergence_finish(L, P, A, dState, dLutG);
+    }
+    if (T) cudaEventRecord(phaseEvent[3], stream);
+
+    // 5. surface tension (:119, :810-839)
+    if (desc.EnableSurfaceTensionSolver) launch_surface_tension(L, P, A, dState, dHalton, desc.SurfaceTensionSmoothPassCount);
+    if (T) cudaEventRecord(phaseEvent[4], stream);
+
+    // 6. implicit viscosity (:123, :577-808)
+    if (desc.EnableViscositySolver) {
+        launch_viscosity_setup(L, P, A, dState, dLutG);
+        if (P.minViscIt == 0 && P.maxViscIt > 0) {
+            int rc = run_polled_loop(P.maxViscIt, 0, 4, &dState->viscActive, [&] { launch_viscosity_iteration(L, P, A, dState, dLutG); }, 1u);
+            if (rc) return rc;
+        }
+        launch_viscosity_apply(L, P, A, dState);
+    }
+    if (T) cudaEventRecord(phaseEvent[5], stream);
+
+    // 7.-8. CFL time step, v += dt a (:127-130)
+    launch_cfl_and_velocity(L, P, A, dState);
+
+    // 9. constant-density solve (:137, :443-504)
+    launch_pressure_source(L, P, A, dState, dLutG);
+    {
+        const uint32_t fixed = std::min(P.minPressIt, P.maxPressIt);
+        for (uint32_t i = 0; i < fixed; i++) launch_pressure_iteration(L, P, A, dState, dLutG);
+        if (fixed > 0 && fixed < P.maxPressIt) {
+            int rc = run_polled_loop(P.maxPressIt, fixed, 2, &dState->pressActive, [&] { launch_pressure_iteration(L, P, A, dState, dLutG); }, 1u);
+            if (rc) return rc;
+        }
+        launch_pressure_finish(L, P, A, dState, dLutG);
+    }
+    if (T) cudaEventRecord(phaseEvent[6], stream);
+
+    // 10. x += dt v (:141)
+    launch_positions(L, P, A, dState);
+    CK(cudaGetLastError());
+    stepsIssued++;
+
+    // 11. frame capture (:148-167) — needs the accumulated frame time on the host
+    if (frameIndexHost < desc.FrameCount || T) {
+        DevState s;
+        int rc = read_state(s);
+        if (rc) return rc;
+        frameTimeHost += s.dt;                  // m_DebugInfo.FrameTime += TimeStepSize (:427)
+        update_debug(s, T);
+        if (frameIndexHost < desc.FrameCount && frameTimeHost >= desc.FrameLength) {
+            rc = capture_frame(s);
+            if (rc) return rc;
+        }
+    }
+    return VFD_OK;
+}
+
+void Solver::update_debug(const DevState& s, bool timers) {
+    std::lock_guard<std::mutex> g(dbgMutex);
+    debug.IterationCount = s.stepCount;
+    debug.DivergenceSolverIterationCount = desc.EnableDivergenceSolverError ? s.divIt : 0;
+    debug.PressureSolverIterationCount = s.pressIt;
+    debug.ViscositySolverIterationCount = desc.EnableViscositySolver ? s.viscIt : 0;
+    debug.DivergenceSolverError = desc.EnableDivergenceSolverError ? s.divErr : 0.0f;
+    debug.PressureSolverError = s.pressErr;
+    debug.ViscositySolverError = desc.EnableViscositySolver ? s.viscErr : 0.0f;
+    debug.FrameTime = frameTimeHost;
+    debug.FrameIndex = frameIndexHost;
+    info.TimeStepSize = s.dt; info.TimeStepSize2 = s.dt2; info.TimeStepSizeInverse = s.dtInv; info.TimeStepSize2Inverse = s.dt2Inv;
+    info.SurfaceTensionSampleCount = s.sampleCount; info.MonteCarloFactor = s.mcFactor;
+    maxVel2 = s.vmax2;
+    if (timers) {
+        float ms[6];
+        for (int i = 0; i < 6; i++) { ms[i] = 0.0f; cudaEventElapsedTime(&ms[i], phaseEvent[i], phaseEvent[i + 1]); }
+        debug.NeighborhoodSearchUs = ms[0] * 1000.0f; debug.BaseSolverUs = ms[1] * 1000.0f; debug.DivergenceSolverUs = ms[2] * 1000.0f;
+        debug.SurfaceTensionSolverUs = ms[3] * 1000.0f; debug.ViscositySolverUs = ms[4] * 1000.0f; debug.PressureSolverUs = ms[5] * 1000.0f;
+    }
+}
+
+int Solver::capture_frame(const DevState& s) {
+    Frame f;
+    f.maxVel2 = s.vmax2; f.dt = s.dt;
+    f.data.resize(info.ParticleCount);
+    VfdParticleSimple* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)info.ParticleCount * sizeof(VfdParticleSimple)));
+    k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d);
+    launches += 1;
+    cudaError_t e = cudaMemcpyAsync(f.data.data(), d, (size_t)info.ParticleCount * sizeof(VfdParticleSimple), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail_cuda(e, "frame capture", __LINE__);
+    {
+        std::lock_guard<std::mutex> g(frameMutex);
+        frames.push_back(std::move(f));
+    }
+    frameTimeHost = 0.0f;              // FrameTime = 0 (:164)
+    frameIndexHost++;
+    std::lock_guard<std::mutex> g(dbgMutex);
+    debug.FrameTime = 0.0f; debug.FrameIndex = frameIndexHost;
+    return VFD_OK;
+}
+
+int Solver::simulate() {
+    int rc = begin();
+    if (rc) return rc;
+    state = VFD_STATE_SIMULATING;
+    while (frameIndexHost < desc.FrameCount) {
+        if (info.ParticleCount == 0) break;    // the reference would spin forever here (OnUpdate returns at once)
+        rc = step();
+        if (rc) { state = VFD_STATE_NONE; return rc; }
+    }
+    state = VFD_STATE_READY;
+    return VFD_OK;
+}
+
+int Solver::synchronize() {
+    CK(cudaSetDevice(device));
+    CK(cudaStreamSynchronize(stream));
+    return VFD_OK;
+}
+
+int Solver::sync_debug() {
+    CK(cudaSetDevice(device));
+    if (!began || info.ParticleCount == 0) return VFD_OK;
+    DevState s;
+    int rc = read_state(s);
+    if (rc) return rc;
+    update_debug(s, false);
+    return VFD_OK;
+}
+
+int Solver::get_particles(VfdParticle* out) {
+    CK(cudaSetDevice(device));
+    if (!out) return fail(VFD_E_INVALID, "null output");
+    if (info.ParticleCount == 0) return VFD_OK;
+    VfdParticle* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)info.ParticleCount * sizeof(VfdParticle)));
+    refresh_params();
+    k_export_aos<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d);
+    launches += 1;
+    cudaError_t e = cudaMemcpyAsync(out, d, (size_t)info.ParticleCount * sizeof(VfdParticle), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail_cuda(e, "get_particles", __LINE__);
+    return VFD_OK;
+}
+
+int Solver::set_particles_full(const VfdParticle* in) {
+    CK(cudaSetDevice(device));
+    if (!in) return fail(VFD_E_INVALID, "null input");
+    if (!began) { int rc = begin(); if (rc) return rc; }
+    if (info.ParticleCount == 0) return VFD_OK;
+    VfdParticle* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)info.ParticleCount * sizeof(VfdParticle)));
+    cudaError_t e = cudaMemcpyAsync(d, in, (size_t)info.ParticleCount * sizeof(VfdParticle), cudaMemcpyHostToDevice, stream);
+    refresh_params();
+    if (e == cudaSuccess) { k_import_aos<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d); launches += 1; e = cudaStreamSynchronize(stream); }
+    cudaFree(d);
+    if (e != cudaSuccess) return fail_cuda(e, "set_particles_full", __LINE__);
+    searched = false;
+    return VFD_OK;
+}
+
+int Solver::set_time_step(float dt) {
+    CK(cudaSetDevice(device));
+    if (!began) { int rc = begin(); if (rc) return rc; }
+    float v[4] = { dt, dt * dt, 1.0f / dt, 1.0f / (dt * dt) };
+    CK(cudaMemcpyAsync(&dState->dt, v, sizeof v, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    info.TimeStepSize = v[0]; info.TimeStepSize2 = v[1]; info.TimeStepSizeInverse = v[2]; info.TimeStepSize2Inverse = v[3];
+    return VFD_OK;
+}
+
+int Solver::set_st_state(uint32_t sampleCount, float mcFactor) {
+    CK(cudaSetDevice(device));
+    if (!began) { int rc = begin(); if (rc) return rc; }
+    CK(cudaMemcpyAsync(&dState->sampleCount, &sampleCount, 4, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(&dState->mcFactor, &mcFactor, 4, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    info.SurfaceTensionSampleCount = sampleCount; info.MonteCarloFactor = mcFactor;
+    return VFD_OK;
+}
+
+int Solver::get_current_frame(VfdParticleSimple* out) {
+    CK(cudaSetDevice(device));
+    if (!out) return fail(VFD_E_INVALID, "null output");
+    if (info.ParticleCount == 0) return VFD_OK;
+    if (!dFrame) CK(cudaMalloc(&dFrame, (size_t)info.ParticleCount * sizeof(VfdParticleSimple)));
+    refresh_params();
+    k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dFrame);
+    launches += 1;
+    CK(cudaMemcpyAsync(out, dFrame, (size_t)info.ParticleCount * sizeof(VfdParticleSimple), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return VFD_OK;
+}
+
+int Solver::get_neighbors(uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t capacity, uint64_t* total) {
+    CK(cudaSetDevice(device));
+    const uint32_t n = info.ParticleCount;
+    if (!searched) return fail(VFD_E_INVALID, "get_neighbors: no neighbour search has run on the current state");
+    uint32_t *dC = nullptr, *dI = nullptr;
+    CK(cudaMalloc(&dC, (size_t)n * 4));
+    CK(cudaMalloc(&dI, (size_t)n * VFD_MAX_NEIGHBORS * 4));
+    refresh_params();
+    k_export_neighbors<<<nblk(n), VFD_TPB, 0, stream>>>(params, arrays, dC, dI);
+    launches += 1;
+    std::vector<uint32_t> c(n), padded((size_t)n * VFD_MAX_NEIGHBORS);
+    cudaError_t e = cudaMemcpyAsync(c.data(), dC, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(padded.data(), dI, padded.size() * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(dC); cudaFree(dI);
+    if (e != cudaSuccess) return fail_cuda(e, "get_neighbors", __LINE__);
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < n; i++) { if (counts) counts[i] = c[i]; if (offsets) offsets[i] = (uint32_t)tot; tot += c[i]; }
+    if (total) *total = tot;
+    if (ids) {
+        if (capacity < tot) return fail(VFD_E_INVALID, "get_neighbors: ids capacity too small");
+        uint64_t o = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            uint32_t* row = padded.data() + (size_t)i * VFD_MAX_NEIGHBORS;
+            std::sort(row, row + c[i]);
+            memcpy(ids + o, row, (size_t)c[i] * 4);
+            o += c[i];
+        }
+    }
+    return VFD_OK;
+}
+
+int Solver::get_boundary(uint32_t body, float* xj, float* vol) {
+    CK(cudaSetDevice(device));
+    if (body >= info.RigidBodyCount) return fail(VFD_E_INVALID, "body index out of range");
+    const uint32_t n = info.ParticleCount;
+    float *dX = nullptr, *dV = nullptr;
+    CK(cudaMalloc(&dX, (size_t)n * 12)); CK(cudaMalloc(&dV, (size_t)n * 4));
+    refresh_params();
+    k_export_boundary<<<nblk(n), VFD_TPB, 0, stream>>>(params, arrays, body, dX, dV);
+    launches += 1;
+    cudaError_t e = cudaMemcpyAsync(xj, dX, (size_t)n * 12, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(vol, dV, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(dX); cudaFree(dV);
+    if (e != cudaSuccess) return fail_cuda(e, "get_boundary", __LINE__);
+    return VFD_OK;
+}
+
+int Solver::get_bounds(float* bmin, float* bmax) {
+    DevState s;
+    CK(cudaSetDevice(device));
+    int rc = read_state(s);
+    if (rc) return rc;
+    // ParticleSearch::ComputeMinMax (ParticleSearch.cu:50-54): min cell * h, (max cell + 1) * h
+    for (int k = 0; k < 3; k++) {
+        const int lo = s.gridMinCell[k], hi = lo + (int)s.gridDim[k] - 5;
+        bmin[k] = (float)lo * info.SupportRadius;
+        bmax[k] = (float)(hi + 1) * info.SupportRadius;
+    }
+    return VFD_OK;
+}
+
+} // namespace vfd

@@ -1,0 +1,89 @@
+// solver.h — host-side solver object and kernel launchers of libvfd_dfsph.so.
+#pragma once
+#include "common.cuh"
+#include "../../include/vfd_dfsph.h"
+#include <string>
+#include <vector>
+#include <mutex>
+
+namespace vfd {
+
+// Device pointers of one simulation, in sorted particle order (see common.cuh).
+struct Arrays {
+    // persistent state: follows the particle through the per-step reorder
+    float4 *pos, *vel, *dv, *nbar;          // Position, Velocity, VelocityDifference, MonteCarloSurfaceNormalSmooth
+    float  *curv, *curvS, *curvD;           // MonteCarloSurfaceCurvature, ...Smooth, DeltaFinalCurvature
+    uint32_t* id;                           // original index
+    // reorder targets (swapped with the above after each sort)
+    float4 *pos2, *vel2, *dv2, *nbar2;
+    float  *curv2, *curvS2, *curvD2;
+    uint32_t* id2;
+    // per-step state
+    float4 *posRho;                         // (x, y, z, density): the position array of everything after the density pass
+    float4 *acc, *pacc, *nrm;               // Acceleration, PressureAcceleration, (MonteCarloSurfaceNormal, MonteCarloSurfaceCurvature)
+    float  *res, *rho, *rhoAdv, *kappa, *kappaV, *alpha;   // PressureResiduum, Density, DensityAdvection, PressureRho2, PressureRho2V, Factor
+    // implicit viscosity (matrix-free PCG)
+    float4 *cgG, *cgR, *cgP, *cgQ, *cgZ;
+    float  *minv;                           // 9 x n, SoA: minv[k*n + p], column-major 3x3 like glm
+    // boundary samples per rigid body: (x_b.xyz, V_b)
+    float4* bx[VFD_MAX_BODIES];
+    // neighbour search
+    uint32_t *cnt, *list;
+    uint32_t *key, *rank, *tmpIdx, *cellCount, *cellBegin, *tileSums;
+    // reductions
+    double* partials;
+};
+
+// Flattened volume map on the device (reference: SDFDeviceData, Utility/SDF/SDFDeviceData.cuh:552-566)
+struct DevVolumeMap {
+    float dmin[3], dmax[3];
+    uint32_t res[3];
+    float cell[3], cellInv[3];
+    uint32_t fieldCount, nodeCount, cellCount, cellMapCount;
+    const float* nodes; const uint32_t* cells; const uint32_t* cellMap;
+};
+struct BodySet { DevVolumeMap map[VFD_MAX_BODIES]; };
+
+struct LaunchCfg {
+    cudaStream_t stream;
+    int numSMs;
+    uint64_t* launchCounter;
+};
+
+// ---- kernel launchers (one per reference kernel group; defined in the .cu files) ----
+void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, uint32_t cellCapacity, uint32_t cellEstimate);
+void launch_boundary(const LaunchCfg& L, const Params& P, const Arrays& A, const BodySet& B);
+void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState* S, const float* lutW, const float* lutG);
+void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_divergence_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_pressure_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A);
+void launch_cfl_and_velocity(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
+void launch_positions(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
+void launch_surface_tension(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState* S, const float* halton, uint32_t passes);
+void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_viscosity_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_viscosity_apply(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
+void launch_reset_solver_state(const LaunchCfg& L, DevState* S, int which);   // 0 div, 1 press, 2 visc
+
+// dump / restore helpers (original particle order <-> sorted SoA)
+void launch_export_aos(const LaunchCfg& L, const Params& P, const Arrays& A, VfdParticle* dOut);
+void launch_import_aos(const LaunchCfg& L, const Params& P, const Arrays& A, const VfdParticle* dIn);
+void launch_export_frame(const LaunchCfg& L, const Params& P, const Arrays& A, VfdParticleSimple* dOut);
+void launch_import_posvel(const LaunchCfg& L, const Params& P, const Arrays& A, const float* dPos, const float* dVel);
+void launch_export_neighbors(const LaunchCfg& L, const Params& P, const Arrays& A, uint32_t* dCounts, uint32_t* dIdsPadded);
+void launch_export_boundary(const LaunchCfg& L, const Params& P, const Arrays& A, uint32_t body, float* dXj, float* dVol);
+
+// host-side construction of the kernel lookup tables and the Halton sphere table
+struct KernelTables {
+    std::vector<float> W, gradW;      // the reference's raw tables: 10000 and 10001 entries
+    std::vector<float> Wc, Gc;        // combined midpoint tables, 10000 entries each (last one padding)
+    float radius, radius2, invStep, wZero, k, l;
+    void build(float radius);
+};
+void build_halton_table(std::vector<float>& out);   // 49152 floats
+
+} // namespace vfd

@@ -1,0 +1,342 @@
+// viscosity.cu — implicit viscosity (Weiler et al. 2018): matrix-free preconditioned CG with a 3x3
+// block-Jacobi preconditioner, warm-started from the previous velocity change.
+//
+// Replaces ComputeViscosityPreconditionerKernel (reference: DFSPHKernels.cu:604-684),
+// ComputeViscosityGradientKernel :686-756, ComputeMatrixVecProdFunctionKernel :758-842,
+// ApplyViscosityForceKernel :844-862 and the host PCG DFSPHImplementation::SolveViscosity
+// (DFSPHImplementation.cu:617-808: one mat-vec kernel + 11 thrust launches + 3 host-synchronous
+// scalar reductions per iteration).  Here one PCG iteration is three kernels and no host round trip:
+//   k_visc_matvec  q = A p            (+ p.q reduction, alpha = delta / p.q by the last block)
+//   k_visc_update  g += alpha p; r -= alpha q; z = M^-1 r   (+ |r|^2, r.z; break test, beta)
+//   k_visc_direction  p = z + beta p
+// The recurrence, the break test and the iteration accounting are the reference's.
+#include "solver.h"
+#include <algorithm>
+
+namespace vfd {
+
+extern __shared__ __align__(16) float smemLut[];
+#define FOR_EACH_TILE(p) for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += gridDim.x * blockDim.x)
+
+// Core/Math/Math.h:19-33 (GetOrthogonalVectors)
+__device__ __forceinline__ void orthogonal_vectors(float3 n, float3& t1, float3& t2) {
+    float3 v = f3(1.0f, 0.0f, 0.0f);
+    if (fabsf(dot3(v, n)) >= 0.999f) v = f3(0.0f, 1.0f, 0.0f);   // "> 0.999" against a double literal: see EPS note in common.cuh
+    t1 = cross3(n, v);
+    t2 = cross3(n, t1);
+    t1 = normalize3(t1);
+    t2 = normalize3(t2);
+}
+
+// The four tangentially displaced boundary samples of Weiler's friction model
+// (DFSPHKernels.cu:650-668 / :809-827): x_i - (x_b -/+ delta t1), x_i - (x_b -/+ delta t2)
+__device__ __forceinline__ bool boundary_samples(const Params& P, float3 xi, float3 xb, float3 (&pd)[4]) {
+    const float3 dir = xi - xb;
+    float3 n = -dir;
+    const float nl = sqrtf(dot3(n, n));
+    if (!(nl > 0.0001f)) return false;
+    n = n / nl;
+    float3 t1, t2;
+    orthogonal_vectors(n, t1, t2);
+    pd[0] = xi - (xb - t1 * P.tangentialDistance);
+    pd[1] = xi - (xb + t1 * P.tangentialDistance);
+    pd[2] = xi - (xb - t2 * P.tangentialDistance);
+    pd[3] = xi - (xb + t2 * P.tangentialDistance);
+    return true;
+}
+
+// ---- V1 + V2 fused: preconditioner blocks, warm start, |b|^2 -------------------------------
+__global__ void __launch_bounds__(VFD_TPB) k_visc_setup(Params P, Arrays A, DevState* S, const float* __restrict__ lutG) {
+    __shared__ double shRed[32];
+    load_lut(smemLut, lutG);
+    __syncthreads();
+    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
+    const float4* __restrict__ pr = A.posRho;
+    const float dt = S->dt;
+    const float eps2 = 0.01f * P.h2;
+    float bb = 0.0f;
+    FOR_EACH_TILE(p) {
+        const float4 xr = pr[p];
+        const float3 xi = f3(xr);
+        const uint32_t m = A.cnt[p];
+        const uint32_t* col = nbr_column(A.list, p);
+        float M[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };     // zero-initialised, column-major
+        for (uint32_t k = 0; k < m; k++) {
+            const uint32_t j = col[(size_t)k * 32];
+            const float4 xj = pr[j];
+            const float3 d = xi - f3(xj);
+            const float3 gw = K.gradW(d);
+            const float s = 10.0f * P.mu * (P.mass / xj.w) / (dot3(d, d) + eps2);
+            // glm::outerProduct(c, r): column i = c * r[i]
+            M[0] += s * (d.x * gw.x); M[1] += s * (d.y * gw.x); M[2] += s * (d.z * gw.x);
+            M[3] += s * (d.x * gw.y); M[4] += s * (d.y * gw.y); M[5] += s * (d.z * gw.y);
+            M[6] += s * (d.x * gw.z); M[7] += s * (d.y * gw.z); M[8] += s * (d.z * gw.z);
+        }
+        if (P.muB != 0.0f) {
+            for (uint32_t b = 0; b < P.nBodies; b++) {
+                const float4 bx = A.bx[b][p];
+                if (bx.w > 0.0f) {
+                    float3 pd[4];
+                    if (boundary_samples(P, xi, f3(bx), pd)) {
+                        const float vol = 0.25f * bx.w;
+                        #pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const float3 gw = K.gradW(pd[q]);
+                            const float s = 10.0f * P.muB * vol / (dot3(pd[q], pd[q]) + eps2);
+                            const float3 c = pd[0];    // the reference uses positionDirection1 in all four products (DFSPHKernels.cu:674-677)
+                            M[0] += s * (c.x * gw.x); M[1] += s * (c.y * gw.x); M[2] += s * (c.z * gw.x);
+                            M[3] += s * (c.x * gw.y); M[4] += s * (c.y * gw.y); M[5] += s * (c.z * gw.y);
+                            M[6] += s * (c.x * gw.z); M[7] += s * (c.y * gw.z); M[8] += s * (c.z * gw.z);
+                        }
+                    }
+                }
+            }
+        }
+        // inverse(I - dt/rho_i * M), cofactor formula of glm::inverse(mat3) (glm/detail/func_matrix.inl:322-344)
+        const float f = dt / xr.w;
+        float a[9];
+        #pragma unroll
+        for (int q = 0; q < 9; q++) a[q] = ((q == 0 || q == 4 || q == 8) ? 1.0f : 0.0f) - f * M[q];
+        // a[3*c + r] = m[c][r]
+        const float c00 = a[4] * a[8] - a[7] * a[5];
+        const float c01 = a[1] * a[8] - a[7] * a[2];
+        const float c02 = a[1] * a[5] - a[4] * a[2];
+        const float invDet = 1.0f / (a[0] * c00 - a[3] * c01 + a[6] * c02);
+        float inv[9];
+        inv[0] = +(a[4] * a[8] - a[7] * a[5]) * invDet;   // [0][0]
+        inv[3] = -(a[3] * a[8] - a[6] * a[5]) * invDet;   // [1][0]
+        inv[6] = +(a[3] * a[7] - a[6] * a[4]) * invDet;   // [2][0]
+        inv[1] = -(a[1] * a[8] - a[7] * a[2]) * invDet;   // [0][1]
+        inv[4] = +(a[0] * a[8] - a[6] * a[2]) * invDet;   // [1][1]
+        inv[7] = -(a[0] * a[7] - a[6] * a[1]) * invDet;   // [2][1]
+        inv[2] = +(a[1] * a[5] - a[4] * a[2]) * invDet;   // [0][2]
+        inv[5] = -(a[0] * a[5] - a[3] * a[2]) * invDet;   // [1][2]
+        inv[8] = +(a[0] * a[4] - a[3] * a[1]) * invDet;   // [2][2]
+        #pragma unroll
+        for (int q = 0; q < 9; q++) A.minv[(size_t)q * P.n + p] = inv[q];
+        // V2: b = v (the boundary term multiplies a zero vector: DFSPHKernels.cu:744-754), g = v + dv_prev
+        const float4 v = A.vel[p], dv = A.dv[p];
+        A.cgG[p] = make_float4(v.x + dv.x, v.y + dv.y, v.z + dv.z, 0.0f);
+        bb += (v.x * v.x + v.y * v.y) + v.z * v.z;
+    }
+    double v[1] = { (double)bb };
+    if (block_reduce_publish<1>(v, A.partials, &S->ticket[4], shRed)) {
+        double tot[1];
+        last_block_fold<1>(tot, A.partials, shRed);
+        if (threadIdx.x == 0) {
+            S->rhsNorm2 = (float)tot[0];
+            S->viscIt = 0;
+            S->ticket[4] = 0;
+        }
+    }
+}
+
+// ---- V3: matrix-free product with the viscosity operator -------------------------------------
+__device__ __forceinline__ float3 visc_operator(const Params& P, const Arrays& A, const Lut& K, const float4* __restrict__ pr,
+                                                const float4* __restrict__ x, uint32_t p, float dt) {
+    const float4 xr = pr[p];
+    const float3 xi = f3(xr);
+    const float3 vi = f3(x[p]);
+    const float eps2 = 0.01f * P.h2;
+    const uint32_t m = A.cnt[p];
+    const uint32_t* col = nbr_column(A.list, p);
+    float3 acc = f3(0.0f, 0.0f, 0.0f);
+    for (uint32_t k = 0; k < m; k++) {
+        const uint32_t j = col[(size_t)k * 32];
+        const float4 xj = pr[j];
+        const float3 d = xi - f3(xj);
+        const float3 gw = K.gradW(d);
+        const float s = 10.0f * P.mu * (P.mass / xj.w) * dot3(vi - f3(x[j]), d) / (dot3(d, d) + eps2);
+        acc += s * gw;
+    }
+    if (P.muB != 0.0f) {
+        for (uint32_t b = 0; b < P.nBodies; b++) {
+            const float4 bx = A.bx[b][p];
+            if (bx.w > 0.0f) {
+                float3 pd[4];
+                if (boundary_samples(P, xi, f3(bx), pd)) {
+                    const float vol = 0.25f * bx.w;
+                    float3 a4[4];
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float s = 10.0f * P.muB * vol * dot3(vi, pd[q]) / (dot3(pd[q], pd[q]) + eps2);
+                        a4[q] = s * K.gradW(pd[q]);
+                    }
+                    acc += ((a4[0] + a4[1]) + a4[2]) + a4[3];
+                }
+            }
+        }
+    }
+    return vi - (dt / xr.w) * acc;
+}
+
+__device__ __forceinline__ float3 mat_vec(const float* __restrict__ minv, uint32_t n, uint32_t p, float3 r) {
+    // glm mat3 * vec3: m[0]*v.x + m[1]*v.y + m[2]*v.z
+    float M[9];
+    #pragma unroll
+    for (int q = 0; q < 9; q++) M[q] = minv[(size_t)q * n + p];
+    return f3(M[0] * r.x + M[3] * r.y + M[6] * r.z, M[1] * r.x + M[4] * r.y + M[7] * r.z, M[2] * r.x + M[5] * r.y + M[8] * r.z);
+}
+
+template<bool INIT>
+__global__ void __launch_bounds__(VFD_TPB) k_visc_matvec(Params P, Arrays A, DevState* S, const float* __restrict__ lutG) {
+    if (!INIT && !S->viscActive) return;
+    __shared__ double shRed[64];
+    load_lut(smemLut, lutG);
+    __syncthreads();
+    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
+    const float dt = S->dt;
+    const float4* __restrict__ x = INIT ? A.cgG : A.cgP;
+    float s0 = 0.0f, s1 = 0.0f;
+    FOR_EACH_TILE(p) {
+        const float3 q = visc_operator(P, A, K, A.posRho, x, p, dt);
+        if (INIT) {
+            // r = b - A g ; p = M^-1 r ; |r|^2 ; r.p      (DFSPHImplementation.cu:638-691)
+            const float3 r = f3(A.vel[p]) - q;
+            const float3 z = mat_vec(A.minv, P.n, p, r);
+            A.cgR[p] = make_float4(r.x, r.y, r.z, 0.0f);
+            A.cgP[p] = make_float4(z.x, z.y, z.z, 0.0f);
+            s0 += (r.x * r.x + r.y * r.y) + r.z * r.z;
+            s1 += (r.x * z.x + r.y * z.y) + r.z * z.z;
+        } else {
+            A.cgQ[p] = make_float4(q.x, q.y, q.z, 0.0f);
+            const float3 pi = f3(x[p]);
+            s0 += (pi.x * q.x + pi.y * q.y) + pi.z * q.z;
+        }
+    }
+    double v[2] = { (double)s0, (double)s1 };
+    uint32_t* ticket = &S->ticket[5];
+    if (block_reduce_publish<2>(v, A.partials, ticket, shRed)) {
+        double tot[2];
+        last_block_fold<2>(tot, A.partials, shRed);
+        if (threadIdx.x == 0) {
+            if (INIT) {
+                const float rhs = S->rhsNorm2;
+                const float rr = (float)tot[0];
+                S->resNorm2 = rr;
+                S->delta = fabsf((float)tot[1]);
+                if (rhs == 0.0f) {
+                    S->viscActive = 2u;          // g := 0, error 0 (DFSPHImplementation.cu:656-661); applied by k_visc_apply
+                    S->viscErr = 0.0f;
+                } else {
+                    const float thr = fmaxf(P.viscErr2 * rhs, FLT_MIN);
+                    S->threshold = thr;
+                    S->viscErr = sqrtf(rr / rhs);
+                    // loop condition "it >= Min && it < Max" at it = 0 (:693)
+                    S->viscActive = (!(rr < thr) && 0u >= P.minViscIt && 0u < P.maxViscIt) ? 1u : 0u;
+                }
+            } else {
+                S->alpha = S->delta / (float)tot[0];
+            }
+            *ticket = 0;
+        }
+    }
+}
+
+// g += alpha p ; r -= alpha q ; |r|^2 ; z = M^-1 r ; r.z       (DFSPHImplementation.cu:714-779)
+__global__ void __launch_bounds__(VFD_TPB) k_visc_update(Params P, Arrays A, DevState* S) {
+    if (S->viscActive != 1u) return;
+    __shared__ double shRed[64];
+    const float alpha = S->alpha;
+    float s0 = 0.0f, s1 = 0.0f;
+    FOR_EACH_TILE(p) {
+        const float4 pp = A.cgP[p], qq = A.cgQ[p];
+        float4 g = A.cgG[p], r = A.cgR[p];
+        g.x = g.x + pp.x * alpha; g.y = g.y + pp.y * alpha; g.z = g.z + pp.z * alpha;
+        r.x = r.x - qq.x * alpha; r.y = r.y - qq.y * alpha; r.z = r.z - qq.z * alpha;
+        A.cgG[p] = g; A.cgR[p] = r;
+        const float3 z = mat_vec(A.minv, P.n, p, f3(r));
+        A.cgZ[p] = make_float4(z.x, z.y, z.z, 0.0f);
+        s0 += (r.x * r.x + r.y * r.y) + r.z * r.z;
+        s1 += (r.x * z.x + r.y * z.y) + r.z * z.z;
+    }
+    double v[2] = { (double)s0, (double)s1 };
+    if (block_reduce_publish<2>(v, A.partials, &S->ticket[6], shRed)) {
+        double tot[2];
+        last_block_fold<2>(tot, A.partials, shRed);
+        if (threadIdx.x == 0) {
+            const float rr = (float)tot[0];
+            S->resNorm2 = rr;
+            S->viscErr = sqrtf(rr / S->rhsNorm2);
+            if (rr < S->threshold) {
+                S->viscActive = 0u;                       // break: this iteration is not counted (:770-772)
+            } else {
+                const float dNew = fabsf((float)tot[1]);
+                S->beta = dNew / S->delta;
+                S->delta = dNew;
+                const uint32_t it = S->viscIt + 1;
+                S->viscIt = it;
+                // viscActive 1: continue; 3: direction update still owed for a loop that then ends
+                S->viscActive = (it >= P.minViscIt && it < P.maxViscIt) ? 1u : 0u;
+            }
+            S->ticket[6] = 0;
+        }
+    }
+}
+
+// p = beta p + z   (:788-802)
+__global__ void __launch_bounds__(VFD_TPB) k_visc_direction(Params P, Arrays A, const DevState* __restrict__ S) {
+    if (S->viscActive != 1u) return;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const float beta = S->beta;
+    const float4 z = A.cgZ[p];
+    float4 d = A.cgP[p];
+    d.x = d.x * beta + z.x; d.y = d.y * beta + z.y; d.z = d.z * beta + z.z;
+    A.cgP[p] = d;
+}
+
+// V5: a += (g - v)/dt ; dv = g - v
+__global__ void __launch_bounds__(VFD_TPB) k_visc_apply(Params P, Arrays A, const DevState* __restrict__ S) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n) return;
+    const float dt = S->dt;
+    float4 g = A.cgG[p];
+    if (S->viscActive == 2u) g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const float4 v = A.vel[p];
+    const float3 d = f3(g.x - v.x, g.y - v.y, g.z - v.z);
+    const float s = 1.0f / dt;
+    float4 a = A.acc[p];
+    a.x += s * d.x; a.y += s * d.y; a.z += s * d.z;
+    A.acc[p] = a;
+    A.dv[p] = make_float4(d.x, d.y, d.z, 0.0f);
+}
+
+static const size_t LUT_BYTES = VFD_LUT_RES * sizeof(float);
+
+template<typename Kern>
+static uint32_t persistent_grid(Kern kern, int threads, size_t smem, const LaunchCfg& L, uint32_t n) {
+    static thread_local const void* cachedK[16]; static thread_local int cachedV[16]; static thread_local int nc = 0;
+    int perSM = 0;
+    for (int i = 0; i < nc; i++) if (cachedK[i] == (const void*)kern) perSM = cachedV[i];
+    if (!perSM) {
+        if (smem) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, threads, smem);
+        if (perSM < 1) perSM = 1;
+        if (nc < 16) { cachedK[nc] = (const void*)kern; cachedV[nc] = perSM; nc++; }
+    }
+    const uint32_t tiles = (n + threads - 1) / threads;
+    return std::max(1u, std::min<uint32_t>(tiles, (uint32_t)(perSM * L.numSMs)));
+}
+
+void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const uint32_t g0 = persistent_grid(k_visc_setup, VFD_TPB, LUT_BYTES, L, P.n);
+    k_visc_setup<<<g0, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    const uint32_t g1 = persistent_grid(k_visc_matvec<true>, VFD_TPB, LUT_BYTES, L, P.n);
+    k_visc_matvec<true><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    *L.launchCounter += 2;
+}
+void launch_viscosity_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const uint32_t g1 = persistent_grid(k_visc_matvec<false>, VFD_TPB, LUT_BYTES, L, P.n);
+    k_visc_matvec<false><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    const uint32_t g2 = persistent_grid(k_visc_update, VFD_TPB, 0, L, P.n);
+    k_visc_update<<<g2, VFD_TPB, 0, L.stream>>>(P, A, S);
+    k_visc_direction<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, S);
+    *L.launchCounter += 3;
+}
+void launch_viscosity_apply(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    k_visc_apply<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, S);
+    *L.launchCounter += 1;
+}
+
+} // namespace vfd
