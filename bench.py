@@ -1,0 +1,306 @@
+#!/usr/bin/env python3
+"""bench.py — DFSPH particle-steps/s on a synthetic dam break (BASELINE.json config 3: 1M particles,
+DFSPH + implicit viscosity + surface tension, one B200), with the HBM roofline of the dominant kernel and
+the reference's own solver sources timed on the host cores beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--side 100]
+
+A "step" is one DFSPHImplementation::OnUpdate of the whole scene.  `value` is measured with the state
+resident in HBM (CUDA events on the solver's stream); `e2e` goes through the C ABI with host buffers:
+vfd_dfsph_set_particles (H2D) + vfd_dfsph_simulate with every step captured as a frame (D2H, 36 B/particle).
+Nothing here reads /root/reference; oracle/_ref/*.so (the reference's sources compiled by
+oracle/build_ref.py) is used only for the cpu_baseline leg and for --impl reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R = 0.025
+D = 2 * R
+H = 4 * R
+
+# algorithmic HBM bytes per particle and launch of the neighbour-sum kernels:
+# own fields read/written once, neighbour ids 4 B each, neighbour fields served from L2
+ALGO_BYTES = {
+    # kernel class: (fixed bytes per particle, bytes per neighbour)
+    "search_bounds": (16, 0), "search_hist": (24, 0), "search_scatter": (12, 0), "search_reorder": (168, 0), "search_build_list": (20, 4),
+    "boundary": (32, 0), "density_factor": (76, 4),
+    "div_source": (68, 4), "div_accel": (56, 4), "div_solve": (72, 4), "div_finish": (96, 4),
+    "press_source": (68, 4), "press_accel": (56, 4), "press_solve": (72, 4), "press_finish": (88, 4),
+    "st_classify": (48, 4), "st_smooth": (56, 4), "st_apply": (76, 0),
+    "visc_setup": (120, 4), "visc_matvec0": (136, 4), "visc_matvec": (68, 4), "visc_update": (148, 0), "visc_direction": (48, 0), "visc_apply": (80, 0),
+    "cfl": (32, 0), "velocity": (48, 0), "position": (48, 0),
+}
+
+
+def scene(side):
+    """Dam break: side^3 lattice block in the corner of an inverted box twice as long."""
+    from vfd_b200 import api
+    pos = api.block_positions(side, side, side, R, origin=(2 * D, 2 * D, 2 * D))
+    L = side * D
+    box = ((0.0, 0.0, 0.0), (2 * L + 4 * D, 1.4 * L + 4 * D, L + 4 * D))
+    ext = [b - a + 2 * (8 * H - R) for a, b in zip(*box)]
+    res = tuple(max(8, int(np.ceil(e / (4 * H)))) for e in ext)
+    return pos, box, res
+
+
+def description(api_mod, frames=0, **kw):
+    """Config 3: defaults of the reference (viscosity 10, boundary viscosity 10, surface tension 1) with the
+    Jacobi iteration counts pinned to 2 (the reference's loops run exactly `Min` iterations: SURVEY.md F4/F5)."""
+    d = dict(FrameCount=frames, FrameLength=0.0,
+             MinPressureSolverIterations=2, MaxPressureSolverIterations=2,
+             MinDivergenceSolverIterations=2, MaxDivergenceSolverIterations=2)
+    d.update(kw)
+    return api_mod(**d)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own solver sources on the host cores (oracle/_ref/libvfd_ref_cpu.so)."""
+    if rank != 0:
+        return 0
+    from oracle import refsim
+    side = args.ref_side
+    from vfd_b200 import api
+    pos, box, res = scene(side)
+    threads = os.cpu_count() or 1
+    desc = description(refsim.Desc)
+    with refsim.quiet_stdout():
+        sim = refsim.RefSim(desc, threads=threads)
+        sim.set_particles(pos)
+        sim.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
+        sim.commit_bodies()
+        sim.step(args.ref_settle)
+        sim.step(args.warmup)
+        t0 = time.perf_counter()
+        its = []
+        for _ in range(args.steps):
+            sim.step(1)
+            its.append(sim.debug()["visc_it"])
+        dt = time.perf_counter() - t0
+    n = len(pos)
+    v = n * args.steps / dt
+    sample = "%d^3 = %d-particle dam break (same scene generator and solver settings), %d settle + %d warm-up steps, %d timed; mean PCG it %.1f" % (
+        side, n, args.ref_settle, args.warmup, args.steps, float(np.mean(its)))
+    print(json.dumps({
+        "impl": "reference", "metric": "DFSPH particle-steps/s", "value": v, "unit": "particle-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "dam break, DFSPH + viscosity + surface tension, reference CPU build; " + sample},
+        "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+def cpu_baseline(state, dt, st, pos0, box, res, steps=2):
+    """The reference's solver sources on this box's host cores, from the GPU run's settled state."""
+    from oracle import refsim
+    if not refsim.available("cpu"):
+        return None
+    threads = os.cpu_count() or 1
+    with refsim.quiet_stdout():
+        sim = refsim.RefSim(description(refsim.Desc), threads=threads)
+        sim.set_particles(pos0)
+        sim.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
+        sim.commit_bodies()
+        sim.set_particles_full(state)
+        sim.set_time_step(dt)
+        sim.set_st_state(*st)
+        sim.step(1)                       # untimed: first-touch of the reference's buffers
+        t0 = time.perf_counter()
+        sim.step(steps)
+        el = time.perf_counter() - t0
+    n = len(pos0)
+    return {"value": n * steps / el, "unit": "particle-steps/s", "cores": threads, "kind": "reference",
+            "sample": "%d steps of the same %d-particle settled state (after 1 untimed step), %.1f s; PCG it of last step %d" % (
+                steps, n, el, sim.debug()["visc_it"])}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--side", type=int, default=100, help="block edge in particles (100 -> 1M)")
+    ap.add_argument("--settle", type=int, default=200, help="scene-preparation steps before warm-up (SURVEY.md §8d)")
+    ap.add_argument("--ref-side", type=int, default=50)
+    ap.add_argument("--ref-settle", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop (run under ncu --profile-from-start off); "
+                                                        "skips the event-bracketed pass, e2e and cpu_baseline; numbers printed under a profiler are not bench values")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    from vfd_b200 import api, build
+    build.build()
+    if world > 1:
+        import bench_multi
+        return bench_multi.main(args, rank, local, world)
+
+    pos, box, res = scene(args.side)
+    n = len(pos)
+    vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R, device=local)
+    sim = api.DFSPHSimulation(description(api.DFSPHSimulationDescription), device=local)
+    sim.SetFluidObjects([api.FluidObject(pos)])
+    sim.SetRigidBodies([vm])
+    sim.steps(args.settle)
+    sim.synchronize()
+    settled = sim.particles()
+    info = sim.GetInfo()
+    settled_dt, settled_st = info.TimeStepSize, (info.SurfaceTensionSampleCount, info.MonteCarloFactor)
+
+    sim.steps(args.warmup)
+    sim.synchronize()
+    sim.launch_count(reset=True)
+    if args.ncu:
+        import torch
+        args.no_e2e = args.no_cpu_baseline = True
+        torch.cuda.cudart().cudaProfilerStart()
+    with ClockSampler(local) as clk:
+        sim.record_event(0)
+        for _ in range(args.steps):
+            sim.OnUpdate()
+        sim.record_event(1)
+        ms = sim.elapsed_ms(0, 1)
+    if args.ncu:
+        sim.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+    launches = sim.launch_count()
+    value = n * args.steps / (ms * 1e-3)
+    dbg = sim.GetDebugInfo()
+    counts, _, _ = sim.neighbors()
+    mbar = float(counts.mean())
+
+    # second pass over the next K steps with every launch bracketed by CUDA events on the solver's stream:
+    # per-kernel device time -> roofline of the dominant kernel (the event pairs cost a few us per launch, so
+    # this pass is not the one `value` is taken from)
+    sim.set_option(api.VFD_OPT_KERNEL_TIMERS, 0 if args.ncu else 1)
+    sim.kernel_times(reset=True)
+    sim.record_event(2)
+    for _ in range(0 if args.ncu else args.steps):
+        sim.OnUpdate()
+    sim.record_event(3)
+    ms_prof = sim.elapsed_ms(2, 3)
+    ktimes = sim.kernel_times()
+    sim.set_option(api.VFD_OPT_KERNEL_TIMERS, 0)
+    peak, peak_src = peaks()
+    roof, table = None, {}
+    total_kernel_ms = sum(v[2] for v in ktimes.values())
+    for name, (msa, lna, msall, lnall) in sorted(ktimes.items(), key=lambda kv: -kv[1][2]):
+        fixed, per = ALGO_BYTES.get(name, (0, 0))
+        b = (fixed + per * mbar) * n
+        avg = msa / lna if lna else 0.0
+        gbs = b / (avg * 1e-3) / 1e9 if avg > 0 and b > 0 else None
+        table[name] = {"ms_per_step": round(msall / args.steps, 4), "launches_per_step": round(lnall / args.steps, 2),
+                       "avg_ms_active": round(avg, 5), "algo_GBps": None if gbs is None else round(gbs, 1),
+                       "frac_of_peak": None if gbs is None else round(gbs / peak, 3), "share": round(msall / total_kernel_ms, 4)}
+        if roof is None:
+            roof = {"bound": "hbm", "kernel": name, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak if gbs else None,
+                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg, "active_launches": lna,
+                    "share_of_step": msall / total_kernel_ms, "algorithmic_bytes_per_launch": b,
+                    "note": "event-bracketed pass over the %d steps following the timed region (%.3f ms/step with brackets)" % (args.steps, ms_prof / args.steps)}
+
+    out = {
+        "metric": "DFSPH particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "dam break %d^3 = %d particles, DFSPH (2 divergence + 2 pressure Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; "
+                               "%d settle steps; working set > L2 (neighbour list alone %.0f MB), no flush" % (args.side, n, n, args.settle, n * 70 * 4 / 1e6),
+                   "particles": n, "mean_neighbours": mbar, "pcg_iterations_last_step": int(dbg.ViscositySolverIterationCount),
+                   "kernels": table},
+        "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,
+    }
+
+    if not args.no_e2e:
+        # end to end through the C ABI with host buffers: upload the settled positions/velocities, bake K frames
+        hp = np.ascontiguousarray(settled["Position"])
+        hv = np.ascontiguousarray(settled["Velocity"])
+        e = api.DFSPHSimulation(description(api.DFSPHSimulationDescription, frames=args.steps), device=local)
+        e.SetFluidObjects([api.FluidObject(hp, velocities=hv)])      # sizes the buffers (untimed)
+        e.SetRigidBodies([vm])
+        e.set_time_step(settled_dt)
+        e.steps(args.warmup)
+        e.synchronize()
+        t0 = time.perf_counter()
+        e.SetFluidObjects([api.FluidObject(hp, velocities=hv)])      # H2D of the inputs
+        e.SetRigidBodies([vm])
+        e.Simulate()                                                  # K steps, each captured: D2H 36 B/particle
+        frame, _, _ = e.GetFrame(args.steps - 1)
+        el = time.perf_counter() - t0
+        out["e2e"] = {"value": n * args.steps / el, "unit": "particle-steps/s", "h2d_bytes_per_step": int(24 * n / args.steps),
+                      "d2h_bytes_per_step": 36 * n, "ms_per_step": 1e3 * el / args.steps,
+                      "note": "vfd_dfsph_set_particles + set_rigid_bodies + simulate (FrameLength 0: every step baked to a host frame), wall clock"}
+        e.close()
+
+    if not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline(settled, settled_dt, settled_st, pos, box, res)
+        except Exception as ex:      # the baseline must not take the GPU number down with it
+            out["cpu_baseline"] = {"error": repr(ex)}
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

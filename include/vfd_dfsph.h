@@ -195,12 +195,25 @@ enum {
     VFD_OPT_SEARCH_FMA = 1,       /* 1 (default): d2 = fma(dz,dz,fma(dx,dx,dy*dy)) as nvcc compiles the reference's test
                                      (ParticleSearchKernels.cu:123-126); 0: (dx*dx+dy*dy)+dz*dz as a host compiler does */
     VFD_OPT_TIMERS = 2,           /* 1: record the six phase timers with CUDA events (default 0) */
-    VFD_OPT_MAX_CELLS = 3,        /* upper bound on search-grid cells (default 1<<27) */
+    VFD_OPT_MAX_CELLS = 3,        /* upper bound on search-grid cells (default 1<<26) */
+    VFD_OPT_KERNEL_TIMERS = 4,    /* 1: bracket every kernel launch with CUDA events and accumulate per-kernel device time
+                                     (synchronises at the end of each step; for bench.py's roofline, default 0) */
 };
 int vfd_dfsph_set_option(VfdDfsph* h, int option, int64_t value);
 
 /* per-kernel accounting for bench.py: number of kernels launched since the last reset */
 int vfd_dfsph_get_launch_count(VfdDfsph* h, uint64_t* launches, int reset);
+
+/* per-kernel device time accumulated while VFD_OPT_KERNEL_TIMERS is on.  *count receives the number of kernel
+ * classes; names/ms/launches (each may be NULL) receive up to `capacity` entries.  msActive/launchesActive count only
+ * launches that did work (an iteration kernel whose solver has converged returns immediately). */
+int vfd_dfsph_get_kernel_times(VfdDfsph* h, uint32_t capacity, uint32_t* count, const char** names, double* ms, uint64_t* launches,
+                               double* msActive, uint64_t* launchesActive, int reset);
+
+/* device-side timing on the solver's own stream (torch.cuda.Event only sees torch's streams):
+ * record marks slot (0..15) on the stream; elapsed_ms synchronises on `to` and returns to - from. */
+int vfd_dfsph_record_event(VfdDfsph* h, uint32_t slot);
+int vfd_dfsph_elapsed_ms(VfdDfsph* h, uint32_t from, uint32_t to, float* ms);
 
 /* ---- scene preparation helper (reference: RigidBody.cu:32-72 over SDF.cu:45-139) ----
  * Builds the two-field volume map of an axis-aligned box on the GPU: field 0 = sign*(d_box - (padding - r)),

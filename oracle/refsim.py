@@ -116,6 +116,22 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+class quiet_stdout:
+    """The reference prints banners to std::cout (DFSPHImplementation.cu:174-252 ...); callers that must keep
+    stdout clean (bench.py prints one JSON line) route fd 1 to fd 2 while the reference runs."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class RefSim:
     """The reference solver (its own sources) behind the calls the editor makes."""
 

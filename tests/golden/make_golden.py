@@ -72,6 +72,27 @@ def make(name):
           "boundary particles", int((bvol > 0).sum()), "->", os.path.getsize(path) // 1024, "kB")
 
 
+def make_halton():
+    """sha256 + probes of the reference's 16 384-point Halton sphere table (its data file HaltonVec323.cuh, parsed as
+    text and narrowed to fp32 exactly as a C compiler narrows the literals): pins vfd_halton_table_build."""
+    import hashlib
+    import json
+    import re
+    ref = os.environ.get("VFD_REFERENCE", "/root/reference")
+    txt = open(os.path.join(ref, "VFD", "Source", "Simulation", "DFSPH", "HaltonVec323.cuh")).read()
+    body = txt[txt.index("{") + 1:txt.rindex("}")]
+    vals = re.findall(r"[-+]?\d*\.?\d+(?:[eE][-+]?\d+)?", body)
+    t = np.array([float(v) for v in vals], dtype=np.float64).astype(np.float32)
+    assert t.shape == (49152,)
+    probe = [0, 1, 2, 3, 4, 5, 3 * 1000, 3 * 1000 + 1, 3 * 1000 + 2, 49149, 49150, 49151]
+    out = dict(count=int(t.size), sha256_f32le=hashlib.sha256(t.astype("<f4").tobytes()).hexdigest(),
+               probe_index=probe, probe_value=[float(t[i]) for i in probe])
+    with open(os.path.join(HERE, "halton_ref.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("halton_ref.json", out["sha256_f32le"])
+
+
 if __name__ == "__main__":
-    for n in (sys.argv[1:] or list(scenes.SCENES)):
-        make(n)
+    names = sys.argv[1:] or (list(scenes.SCENES) + ["halton"])
+    for n in names:
+        make_halton() if n == "halton" else make(n)

@@ -106,7 +106,7 @@ PARTICLE_DTYPE = np.dtype([
 PARTICLE_SIMPLE_DTYPE = np.dtype([("Position", "<f4", 3), ("Velocity", "<f4", 3), ("Acceleration", "<f4", 3)])
 assert PARTICLE_DTYPE.itemsize == 120 and PARTICLE_SIMPLE_DTYPE.itemsize == 36
 
-VFD_OPT_SEARCH_FMA, VFD_OPT_TIMERS, VFD_OPT_MAX_CELLS = 1, 2, 3
+VFD_OPT_SEARCH_FMA, VFD_OPT_TIMERS, VFD_OPT_MAX_CELLS, VFD_OPT_KERNEL_TIMERS = 1, 2, 3, 4
 STATE_NONE, STATE_SIMULATING, STATE_READY = 0, 1, 2
 
 # every symbol include/vfd_dfsph.h declares: (name, restype, argtypes)
@@ -152,6 +152,9 @@ SYMBOLS = [
     ("vfd_halton_table_build", _i, [_vp]),
     ("vfd_dfsph_set_option", _i, [_vp, _i, C.c_int64]),
     ("vfd_dfsph_get_launch_count", _i, [_vp, C.POINTER(_u64), _i]),
+    ("vfd_dfsph_get_kernel_times", _i, [_vp, _u32, C.POINTER(_u32), _vp, _vp, _vp, _vp, _vp, _i]),
+    ("vfd_dfsph_record_event", _i, [_vp, _u32]),
+    ("vfd_dfsph_elapsed_ms", _i, [_vp, _u32, _u32, C.POINTER(_f32)]),
     ("vfd_volume_map_build_box", _i, [_vp, _vp, _i, _f32, _vp, _f32, _i, C.POINTER(VfdVolumeMap)]),
     ("vfd_volume_map_free", None, [C.POINTER(VfdVolumeMap)]),
 ]
@@ -428,6 +431,25 @@ class DFSPHSimulation:
         v = C.c_uint64()
         self._ck(self.L.vfd_dfsph_get_launch_count(self.h, C.byref(v), 1 if reset else 0))
         return v.value
+
+    def kernel_times(self, reset=False):
+        """{kernel class: (ms of launches that did work, number of such launches, ms of all launches, all launches)}"""
+        cnt = C.c_uint32()
+        self._ck(self.L.vfd_dfsph_get_kernel_times(self.h, 0, C.byref(cnt), None, None, None, None, None, 0))
+        k = cnt.value
+        names = (C.c_char_p * k)()
+        ms, msa = np.zeros(k, np.float64), np.zeros(k, np.float64)
+        ln, lna = np.zeros(k, np.uint64), np.zeros(k, np.uint64)
+        self._ck(self.L.vfd_dfsph_get_kernel_times(self.h, k, C.byref(cnt), C.cast(names, C.c_void_p), _p(ms), _p(ln), _p(msa), _p(lna), 1 if reset else 0))
+        return {names[i].decode(): (float(msa[i]), int(lna[i]), float(ms[i]), int(ln[i])) for i in range(k) if ln[i]}
+
+    def record_event(self, slot):
+        self._ck(self.L.vfd_dfsph_record_event(self.h, int(slot)))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._ck(self.L.vfd_dfsph_elapsed_ms(self.h, int(a), int(b), C.byref(ms)))
+        return ms.value
 
     def set_particles_device(self, d_pos_ptr, d_vel_ptr, n):
         self.n = int(n)

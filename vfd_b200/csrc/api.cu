@@ -145,10 +145,29 @@ int vfd_dfsph_set_option(VfdDfsph* h, int option, int64_t value) {
     switch (option) {
     case VFD_OPT_SEARCH_FMA: h->s.optSearchFma = value ? 1 : 0; return VFD_OK;
     case VFD_OPT_TIMERS: h->s.optTimers = value ? 1 : 0; return VFD_OK;
+    case VFD_OPT_KERNEL_TIMERS: h->s.prof.enabled = value != 0; return VFD_OK;
     case VFD_OPT_MAX_CELLS: if (value < (1 << 16) || value > (1ll << 30)) return h->s.fail(VFD_E_INVALID, "max cells out of range"); h->s.optMaxCells = (uint64_t)value; return VFD_OK;
     default: return h->s.fail(VFD_E_INVALID, "unknown option");
     }
 }
 int vfd_dfsph_get_launch_count(VfdDfsph* h, uint64_t* launches, int reset) { GUARD(h); if (launches) *launches = h->s.launches; if (reset) h->s.launches = 0; return VFD_OK; }
+
+int vfd_dfsph_get_kernel_times(VfdDfsph* h, uint32_t capacity, uint32_t* count, const char** names, double* ms, uint64_t* launches,
+                               double* msActive, uint64_t* launchesActive, int reset) {
+    GUARD(h);
+    vfd::KernelProf& p = h->s.prof;
+    if (count) *count = vfd::KID_COUNT;
+    for (uint32_t k = 0; k < capacity && k < (uint32_t)vfd::KID_COUNT; k++) {
+        if (names) names[k] = vfd::kKernelNames[k];
+        if (ms) ms[k] = p.ms[k];
+        if (launches) launches[k] = p.launches[k];
+        if (msActive) msActive[k] = p.msActive[k];
+        if (launchesActive) launchesActive[k] = p.launchesActive[k];
+    }
+    if (reset) p.reset();
+    return VFD_OK;
+}
+int vfd_dfsph_record_event(VfdDfsph* h, uint32_t slot) { GUARD(h); TRY(h->s.record_event(slot)); }
+int vfd_dfsph_elapsed_ms(VfdDfsph* h, uint32_t from, uint32_t to, float* ms) { GUARD(h); if (!ms) return h->s.fail(VFD_E_INVALID, "null output"); TRY(h->s.elapsed_ms(from, to, ms)); }
 
 } // extern "C"

@@ -318,56 +318,53 @@ static uint32_t persistent_grid(Kern kern, int threads, size_t smem, const Launc
 
 void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState*, const float* lutW, const float* lutG) {
     const uint32_t g = persistent_grid(k_density_factor, 512, 2 * LUT_BYTES, L, P.n);
+    LaunchScope ls(L, KID_DENSITY_FACTOR);
     k_density_factor<<<g, 512, 2 * LUT_BYTES, L.stream>>>(P, A, lutW, lutG);
-    *L.launchCounter += 1;
 }
 void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
     const uint32_t g = persistent_grid(k_divergence_source, VFD_TPB, LUT_BYTES, L, P.n);
+    LaunchScope ls(L, KID_DIV_SOURCE);
     k_divergence_source<<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
-    *L.launchCounter += 1;
 }
 void launch_divergence_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
     const uint32_t g1 = persistent_grid(k_pressure_accel<ACC_DIV_ITER>, VFD_TPB, LUT_BYTES, L, P.n);
-    k_pressure_accel<ACC_DIV_ITER><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    { LaunchScope ls(L, KID_DIV_ACCEL); k_pressure_accel<ACC_DIV_ITER><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
     const uint32_t g2 = persistent_grid(k_solve_iteration<true>, VFD_TPB, LUT_BYTES, L, P.n);
-    k_solve_iteration<true><<<g2, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
-    *L.launchCounter += 2;
+    { LaunchScope ls(L, KID_DIV_SOLVE); k_solve_iteration<true><<<g2, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
 }
 void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
     const uint32_t g = persistent_grid(k_pressure_accel<ACC_DIV_FINISH>, VFD_TPB, LUT_BYTES, L, P.n);
+    LaunchScope ls(L, KID_DIV_FINISH);
     k_pressure_accel<ACC_DIV_FINISH><<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
-    *L.launchCounter += 1;
 }
 void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
     const uint32_t g = persistent_grid(k_pressure_source, VFD_TPB, LUT_BYTES, L, P.n);
+    LaunchScope ls(L, KID_PRESS_SOURCE);
     k_pressure_source<<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
-    *L.launchCounter += 1;
 }
 void launch_pressure_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
     const uint32_t g1 = persistent_grid(k_pressure_accel<ACC_PRESS_ITER>, VFD_TPB, LUT_BYTES, L, P.n);
-    k_pressure_accel<ACC_PRESS_ITER><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    { LaunchScope ls(L, KID_PRESS_ACCEL); k_pressure_accel<ACC_PRESS_ITER><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
     const uint32_t g2 = persistent_grid(k_solve_iteration<false>, VFD_TPB, LUT_BYTES, L, P.n);
-    k_solve_iteration<false><<<g2, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
-    *L.launchCounter += 2;
+    { LaunchScope ls(L, KID_PRESS_SOLVE); k_solve_iteration<false><<<g2, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
 }
 void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
     const uint32_t g = persistent_grid(k_pressure_accel<ACC_PRESS_FINISH>, VFD_TPB, LUT_BYTES, L, P.n);
+    LaunchScope ls(L, KID_PRESS_FINISH);
     k_pressure_accel<ACC_PRESS_FINISH><<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
-    *L.launchCounter += 1;
 }
 void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A) {
+    LaunchScope ls(L, KID_CLEAR_ACC);
     k_clear_acc<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A);
-    *L.launchCounter += 1;
 }
 void launch_cfl_and_velocity(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     const uint32_t tiles = (P.n + VFD_TPB - 1) / VFD_TPB;
-    k_cfl<<<std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 8u)), VFD_TPB, 0, L.stream>>>(P, A, S);
-    k_velocity<<<tiles, VFD_TPB, 0, L.stream>>>(P, A, S);
-    *L.launchCounter += 2;
+    { LaunchScope ls(L, KID_CFL); k_cfl<<<std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 8u)), VFD_TPB, 0, L.stream>>>(P, A, S); }
+    { LaunchScope ls(L, KID_VELOCITY); k_velocity<<<tiles, VFD_TPB, 0, L.stream>>>(P, A, S); }
 }
 void launch_positions(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    LaunchScope ls(L, KID_POSITION);
     k_position<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, S);
-    *L.launchCounter += 1;
 }
 
 } // namespace vfd

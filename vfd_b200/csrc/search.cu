@@ -249,20 +249,22 @@ static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; 
 void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, uint32_t cellCapacity, uint32_t cellEstimate) {
     const uint32_t nb = div_up(P.n, VFD_TPB);
     const uint32_t gb = std::min<uint32_t>(nb, (uint32_t)L.numSMs * 8u);
-    k_bounds<<<gb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, cellCapacity);
-    k_hist<<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.key, A.rank, A.cellCount);
+    { LaunchScope ls(L, KID_BOUNDS); k_bounds<<<gb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, cellCapacity); }
+    { LaunchScope ls(L, KID_HIST); k_hist<<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.key, A.rank, A.cellCount); }
     const uint32_t est = std::min<uint64_t>((uint64_t)cellCapacity, std::max<uint64_t>(4ull * cellEstimate, 1u << 16));
     const uint32_t st = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(est, SCAN_TILE), (uint32_t)L.numSMs * 8u));
-    k_scan_tiles<<<st, VFD_TPB, 0, L.stream>>>(S, A.cellCount, A.tileSums);
-    k_scan_tile_sums<<<1, 1024, 0, L.stream>>>(S, A.tileSums);
-    k_scan_apply<<<st, VFD_TPB, 0, L.stream>>>(P, S, A.cellCount, A.tileSums, A.cellBegin);
-    k_scatter<<<nb, VFD_TPB, 0, L.stream>>>(P, A.key, A.rank, A.cellBegin, A.tmpIdx);
-    k_reorder<<<nb, VFD_TPB, 0, L.stream>>>(P, A);
+    { LaunchScope ls(L, KID_SCAN); k_scan_tiles<<<st, VFD_TPB, 0, L.stream>>>(S, A.cellCount, A.tileSums); }
+    { LaunchScope ls(L, KID_SCAN); k_scan_tile_sums<<<1, 1024, 0, L.stream>>>(S, A.tileSums); }
+    { LaunchScope ls(L, KID_SCAN); k_scan_apply<<<st, VFD_TPB, 0, L.stream>>>(P, S, A.cellCount, A.tileSums, A.cellBegin); }
+    { LaunchScope ls(L, KID_SCATTER); k_scatter<<<nb, VFD_TPB, 0, L.stream>>>(P, A.key, A.rank, A.cellBegin, A.tmpIdx); }
+    { LaunchScope ls(L, KID_REORDER); k_reorder<<<nb, VFD_TPB, 0, L.stream>>>(P, A); }
     std::swap(A.pos, A.pos2); std::swap(A.vel, A.vel2); std::swap(A.dv, A.dv2); std::swap(A.nbar, A.nbar2);
     std::swap(A.curv, A.curv2); std::swap(A.curvS, A.curvS2); std::swap(A.curvD, A.curvD2); std::swap(A.id, A.id2);
-    if (P.searchFma) k_build_list<true><<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.cellBegin, A.cnt, A.list);
-    else             k_build_list<false><<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.cellBegin, A.cnt, A.list);
-    *L.launchCounter += 8;
+    {
+        LaunchScope ls(L, KID_BUILD_LIST);
+        if (P.searchFma) k_build_list<true><<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.cellBegin, A.cnt, A.list);
+        else             k_build_list<false><<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.cellBegin, A.cnt, A.list);
+    }
 }
 
 } // namespace vfd

@@ -105,6 +105,51 @@ __global__ void k_export_boundary(Params P, Arrays A, uint32_t body, float* __re
 static inline uint32_t nblk(uint32_t n) { return (n + VFD_TPB - 1) / VFD_TPB; }
 
 // ---------------------------------------------------------------------------------------------
+// per-kernel device timers
+// ---------------------------------------------------------------------------------------------
+const char* const kKernelNames[KID_COUNT] = {
+    "search_bounds", "search_hist", "search_scan", "search_scatter", "search_reorder", "search_build_list",
+    "boundary", "density_factor",
+    "div_source", "div_accel", "div_solve", "div_finish",
+    "st_classify", "st_smooth", "st_apply",
+    "visc_setup", "visc_matvec0", "visc_matvec", "visc_update", "visc_direction", "visc_apply",
+    "cfl", "velocity",
+    "press_source", "press_accel", "press_solve", "press_finish",
+    "position", "clear_acc", "io" };
+
+cudaEvent_t KernelProf::take() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+}
+void KernelProf::begin(int kid, cudaStream_t s) {
+    Rec r{ kid, take(), take() };
+    cudaEventRecord(r.a, s);
+    pending.push_back(r);
+}
+void KernelProf::end(cudaStream_t s) { cudaEventRecord(pending.back().b, s); }
+void KernelProf::drain() {
+    std::vector<float> dur(pending.size());
+    float mx[KID_COUNT] = {};
+    for (size_t i = 0; i < pending.size(); i++) {
+        float t = 0.0f;
+        cudaEventElapsedTime(&t, pending[i].a, pending[i].b);
+        dur[i] = t;
+        mx[pending[i].kid] = std::max(mx[pending[i].kid], t);
+    }
+    for (size_t i = 0; i < pending.size(); i++) {
+        const int k = pending[i].kid;
+        ms[k] += dur[i]; launches[k]++;
+        if (dur[i] >= 0.3f * mx[k]) { msActive[k] += dur[i]; launchesActive[k]++; }
+    }
+    pending.clear();
+    used = 0;
+}
+void KernelProf::reset() {
+    for (int k = 0; k < KID_COUNT; k++) { ms[k] = msActive[k] = 0.0; launches[k] = launchesActive[k] = 0; }
+}
+KernelProf::~KernelProf() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
+
+// ---------------------------------------------------------------------------------------------
 // Solver
 // ---------------------------------------------------------------------------------------------
 int Solver::fail(int code, const std::string& msg) {
@@ -152,6 +197,7 @@ Solver::~Solver() {
     cudaFree(dLutW); cudaFree(dLutG); cudaFree(dHalton);
     for (int i = 0; i < 4; i++) if (pollEvent[i]) cudaEventDestroy(pollEvent[i]);
     for (int i = 0; i < 7; i++) if (phaseEvent[i]) cudaEventDestroy(phaseEvent[i]);
+    for (int i = 0; i < 16; i++) if (userEvent[i]) cudaEventDestroy(userEvent[i]);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -396,7 +442,7 @@ int Solver::search_only() {
     if (!began) { int rc = begin(); if (rc) return rc; }
     if (info.ParticleCount == 0) return VFD_OK;
     refresh_params();
-    LaunchCfg L{ stream, numSMs, &launches };
+    LaunchCfg L{ stream, numSMs, &launches, &prof };
     launch_search(L, params, arrays, dState, cellCapacity, cellEstimate);
     searched = true;
     CK(cudaGetLastError());
@@ -410,7 +456,7 @@ int Solver::step() {
     refresh_params();
     const Params& P = params;
     Arrays& A = arrays;
-    LaunchCfg L{ stream, numSMs, &launches };
+    LaunchCfg L{ stream, numSMs, &launches, &prof };
     const bool T = optTimers;
     if (T) cudaEventRecord(phaseEvent[0], stream);
 
@@ -472,6 +518,7 @@ int Solver::step() {
     launch_positions(L, P, A, dState);
     CK(cudaGetLastError());
     stepsIssued++;
+    if (prof.enabled) { CK(cudaStreamSynchronize(stream)); prof.drain(); }
 
     // 11. frame capture (:148-167) — needs the accumulated frame time on the host
     if (frameIndexHost < desc.FrameCount || T) {
@@ -673,6 +720,22 @@ int Solver::get_boundary(uint32_t body, float* xj, float* vol) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(dX); cudaFree(dV);
     if (e != cudaSuccess) return fail_cuda(e, "get_boundary", __LINE__);
+    return VFD_OK;
+}
+
+int Solver::record_event(uint32_t slot) {
+    CK(cudaSetDevice(device));
+    if (slot >= 16) return fail(VFD_E_INVALID, "event slot out of range");
+    if (!userEvent[slot]) CK(cudaEventCreate(&userEvent[slot]));
+    CK(cudaEventRecord(userEvent[slot], stream));
+    return VFD_OK;
+}
+
+int Solver::elapsed_ms(uint32_t from, uint32_t to, float* ms) {
+    CK(cudaSetDevice(device));
+    if (from >= 16 || to >= 16 || !userEvent[from] || !userEvent[to]) return fail(VFD_E_INVALID, "event slot not recorded");
+    CK(cudaEventSynchronize(userEvent[to]));
+    CK(cudaEventElapsedTime(ms, userEvent[from], userEvent[to]));
     return VFD_OK;
 }
 

@@ -44,10 +44,54 @@ struct DevVolumeMap {
 };
 struct BodySet { DevVolumeMap map[VFD_MAX_BODIES]; };
 
+// Kernel classes for the launch counter and the optional per-kernel device timers (VFD_OPT_KERNEL_TIMERS).
+enum KernelId {
+    KID_BOUNDS = 0, KID_HIST, KID_SCAN, KID_SCATTER, KID_REORDER, KID_BUILD_LIST,
+    KID_BOUNDARY, KID_DENSITY_FACTOR,
+    KID_DIV_SOURCE, KID_DIV_ACCEL, KID_DIV_SOLVE, KID_DIV_FINISH,
+    KID_ST_CLASSIFY, KID_ST_SMOOTH, KID_ST_APPLY,
+    KID_VISC_SETUP, KID_VISC_MATVEC0, KID_VISC_MATVEC, KID_VISC_UPDATE, KID_VISC_DIRECTION, KID_VISC_APPLY,
+    KID_CFL, KID_VELOCITY,
+    KID_PRESS_SOURCE, KID_PRESS_ACCEL, KID_PRESS_SOLVE, KID_PRESS_FINISH,
+    KID_POSITION, KID_CLEAR_ACC, KID_IO, KID_COUNT
+};
+extern const char* const kKernelNames[KID_COUNT];
+
+// Brackets every launch with a pair of CUDA events on the solver's stream; drained (after a stream
+// synchronise) into per-class totals.  "active" launches are those that did work: an iteration kernel
+// that finds its solver converged returns at once, and is told apart by its duration.
+struct KernelProf {
+    bool enabled = false;
+    struct Rec { int kid; cudaEvent_t a, b; };
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::vector<Rec> pending;
+    double ms[KID_COUNT] = {}, msActive[KID_COUNT] = {};
+    uint64_t launches[KID_COUNT] = {}, launchesActive[KID_COUNT] = {};
+    cudaEvent_t take();
+    void begin(int kid, cudaStream_t s);
+    void end(cudaStream_t s);
+    void drain();          // caller has synchronised the stream
+    void reset();
+    ~KernelProf();
+};
+
 struct LaunchCfg {
     cudaStream_t stream;
     int numSMs;
     uint64_t* launchCounter;
+    KernelProf* prof;
+};
+
+// One per kernel launch: counts it and, when the timers are on, brackets it with events.
+struct LaunchScope {
+    const LaunchCfg& L;
+    bool on;
+    LaunchScope(const LaunchCfg& cfg, int kid) : L(cfg), on(cfg.prof && cfg.prof->enabled) {
+        *L.launchCounter += 1;
+        if (on) L.prof->begin(kid, L.stream);
+    }
+    ~LaunchScope() { if (on) L.prof->end(L.stream); }
 };
 
 // ---- kernel launchers (one per reference kernel group; defined in the .cu files) ----

@@ -28,6 +28,8 @@ public:
     int get_neighbors(uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t capacity, uint64_t* total);
     int get_boundary(uint32_t body, float* xj, float* vol);
     int get_bounds(float* bmin, float* bmax);
+    int record_event(uint32_t slot);
+    int elapsed_ms(uint32_t from, uint32_t to, float* ms);
     int fail(int code, const std::string& msg);
 
     // configuration / host mirrors
@@ -37,6 +39,7 @@ public:
     KernelTables tables;
     std::vector<float> halton;
     int optSearchFma = 1, optTimers = 0;
+    KernelProf prof;
     uint64_t optMaxCells = 1ull << 26;
     uint64_t launches = 0;
     uint64_t allocBytes = 0, searchBytes = 0;
@@ -67,6 +70,7 @@ private:
     uint32_t* hFlags = nullptr;       // pinned
     cudaEvent_t pollEvent[4] = {};
     cudaEvent_t phaseEvent[7] = {};
+    cudaEvent_t userEvent[16] = {};
     float *dLutW = nullptr, *dLutG = nullptr, *dHalton = nullptr;
     Arrays arrays{};
     BodySet bodies{};

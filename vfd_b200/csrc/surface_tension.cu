@@ -132,10 +132,9 @@ __global__ void __launch_bounds__(VFD_TPB) k_st_apply(Params P, Arrays A) {
 void launch_surface_tension(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState* S, const float* halton, uint32_t passes) {
     const uint32_t tiles = (P.n + VFD_TPB - 1) / VFD_TPB;
     const uint32_t g = std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 6u));
-    k_st_classify<<<g, VFD_TPB, 0, L.stream>>>(P, A, S, halton);
-    k_st_smooth<<<g, VFD_TPB, 0, L.stream>>>(P, A);
-    for (uint32_t i = 0; i < passes; i++) k_st_apply<<<tiles, VFD_TPB, 0, L.stream>>>(P, A);
-    *L.launchCounter += 2 + passes;
+    { LaunchScope ls(L, KID_ST_CLASSIFY); k_st_classify<<<g, VFD_TPB, 0, L.stream>>>(P, A, S, halton); }
+    { LaunchScope ls(L, KID_ST_SMOOTH); k_st_smooth<<<g, VFD_TPB, 0, L.stream>>>(P, A); }
+    for (uint32_t i = 0; i < passes; i++) { LaunchScope ls(L, KID_ST_APPLY); k_st_apply<<<tiles, VFD_TPB, 0, L.stream>>>(P, A); }
 }
 
 } // namespace vfd

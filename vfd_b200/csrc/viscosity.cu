@@ -321,22 +321,20 @@ static uint32_t persistent_grid(Kern kern, int threads, size_t smem, const Launc
 
 void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
     const uint32_t g0 = persistent_grid(k_visc_setup, VFD_TPB, LUT_BYTES, L, P.n);
-    k_visc_setup<<<g0, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    { LaunchScope ls(L, KID_VISC_SETUP); k_visc_setup<<<g0, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
     const uint32_t g1 = persistent_grid(k_visc_matvec<true>, VFD_TPB, LUT_BYTES, L, P.n);
-    k_visc_matvec<true><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
-    *L.launchCounter += 2;
+    { LaunchScope ls(L, KID_VISC_MATVEC0); k_visc_matvec<true><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
 }
 void launch_viscosity_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
     const uint32_t g1 = persistent_grid(k_visc_matvec<false>, VFD_TPB, LUT_BYTES, L, P.n);
-    k_visc_matvec<false><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    { LaunchScope ls(L, KID_VISC_MATVEC); k_visc_matvec<false><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
     const uint32_t g2 = persistent_grid(k_visc_update, VFD_TPB, 0, L, P.n);
-    k_visc_update<<<g2, VFD_TPB, 0, L.stream>>>(P, A, S);
-    k_visc_direction<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, S);
-    *L.launchCounter += 3;
+    { LaunchScope ls(L, KID_VISC_UPDATE); k_visc_update<<<g2, VFD_TPB, 0, L.stream>>>(P, A, S); }
+    { LaunchScope ls(L, KID_VISC_DIRECTION); k_visc_direction<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, S); }
 }
 void launch_viscosity_apply(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    LaunchScope ls(L, KID_VISC_APPLY);
     k_visc_apply<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, S);
-    *L.launchCounter += 1;
 }
 
 } // namespace vfd
