@@ -266,7 +266,7 @@ def main():
         "metric": "DFSPH particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "dam break %d^3 = %d particles, DFSPH (2 divergence + 2 pressure Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; "
-                               "%d settle steps; working set > L2 (neighbour list alone %.0f MB), no flush" % (args.side, n, n, args.settle, n * 70 * 4 / 1e6),
+                               "%d settle steps; working set > L2 (neighbour list alone %.0f MB), no flush" % (args.side, n, args.settle, n * 70 * 4 / 1e6),
                    "particles": n, "mean_neighbours": mbar, "pcg_iterations_last_step": int(dbg.ViscositySolverIterationCount),
                    "kernels": table},
         "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,

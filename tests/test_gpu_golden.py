@@ -22,6 +22,13 @@ def load(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
 
+def field_tolerances(g):
+    """1e-5 of the field's scale, or twice the reference's own run-to-run deviation on this very step where that is
+    larger (recorded in the fixture by make_golden.py: the reference is not reproducible below it)."""
+    noise = dict(zip([str(f) for f in g["noise_fields"]], g["noise_values"]))
+    return {f: max(TOL, 2.0 * float(noise.get(f, 0.0))) for f in parity.ALL_FIELDS}
+
+
 def make_sim(name, g, fma=0):
     from vfd_b200 import api
     sc = scenes.SCENES[name]
@@ -60,8 +67,9 @@ def test_one_step_from_golden_state(name, lib_built):
     assert dbg.DivergenceSolverIterationCount == g["its_out"][0]
     assert dbg.PressureSolverIterationCount == g["its_out"][1]
     assert abs(int(dbg.ViscositySolverIterationCount) - int(g["its_out"][2])) <= 1
-    bad = {k: v for k, v in errs.items() if v[0] > TOL}
-    assert not bad, "fields beyond %.0e of their scale:\n%s" % (TOL, parity.format_errors(bad))
+    tol = field_tolerances(g)
+    bad = {k: v for k, v in errs.items() if v[0] > tol[k]}
+    assert not bad, "fields beyond tolerance %s:\n%s" % ({k: "%.1e" % tol[k] for k in bad}, parity.format_errors(bad))
 
 
 @pytest.mark.parametrize("name", ["dfsph", "viscous"])

@@ -1,10 +1,7 @@
 #!/bin/bash
-# first GPU pass: tests, smoke, bench, launch list
 mkdir -p gpurun_out
-nvidia-smi > gpurun_out/nvidia-smi.txt 2>&1
-nproc > gpurun_out/nproc.txt
-timeout 900 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+timeout 900 python -m pytest tests -m gpu -q -s > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+timeout 300 python tools_diag.py > gpurun_out/diag.log 2>&1
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --ncu > gpurun_out/ncu_bench.log 2>&1
-tail -5 gpurun_out/pytest.log gpurun_out/smoke.log gpurun_out/bench.err; cat gpurun_out/bench.json
+tail -n 5 gpurun_out/pytest.log gpurun_out/smoke.log gpurun_out/bench.err; cat gpurun_out/bench.json
