@@ -5,9 +5,10 @@
 //   float4 arrays : gathered per neighbour with one 16-B load (pos, vel, pressure acceleration,
 //                   PCG direction ...);  .w is a per-array payload or unused.
 //   float  arrays : per-particle scalars, streamed coalesced.
-//   neighbour list: "warp-blocked ELL": the k-th neighbour of the particle in lane l of warp w
-//                   sits at  list[(w*VFD_MAX_NEIGHBORS + k)*32 + l]  — a warp reads one full
-//                   128-B line per k, only rows k < max-count-in-warp are ever touched.
+//   neighbour list: "warp-blocked ELL" of 16-bit TILE-LOCAL indices (tile.cuh): the k-th neighbour
+//                   of the particle in lane l of 32-group w sits at
+//                   list16[(w*VFD_MAX_NEIGHBORS + k)*32 + l]  — a warp reads one 64-B line per k,
+//                   only rows k < max-count-in-warp are ever touched.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -61,8 +62,10 @@ struct DevState {
     uint32_t stepCount;
     // search grid (derived on device each step)
     int32_t  gridMinCell[3];
-    uint32_t gridDim[3];
-    uint32_t nCells;
+    uint32_t gridDim[3];        // cells per axis, a multiple of 4
+    uint32_t tileDim[3];        // tiles (4x4x4 cells) per axis
+    uint32_t nTiles;
+    uint32_t nCells;            // nTiles * 64
     float    gridOrigin[3];
     int32_t  boundsMin[3], boundsMax[3];   // cell = floor(x/h) extrema (ParticleSearchKernels.cu:40-62)
     uint32_t errorFlags;        // bit0: grid larger than capacity
@@ -135,11 +138,6 @@ __device__ __forceinline__ void load_lut(float* dst, const float* __restrict__ s
     const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* d4 = reinterpret_cast<float4*>(dst);
     for (int i = threadIdx.x; i < (VFD_LUT_RES / 4); i += blockDim.x) d4[i] = __ldg(s4 + i);
-}
-
-// ---- neighbour list access -------------------------------------------------------------------
-__device__ __forceinline__ const uint32_t* nbr_column(const uint32_t* __restrict__ list, uint32_t p) {
-    return list + (size_t)(p >> 5) * (VFD_MAX_NEIGHBORS * 32) + (p & 31);
 }
 
 // ---- deterministic grid-wide reductions ------------------------------------------------------

@@ -10,39 +10,45 @@
 // (DFSPHImplementation.cu: ComputeDivergence :506-575, ComputePressure :443-504,
 // ComputeTimeStepSize :395-428, ComputeMaxVelocityMagnitude :430-441).
 //
-// All kernels are persistent (grid = SMs x resident CTAs, grid-stride over 256-particle tiles) so the
-// 40-kB kernel lookup table is staged into shared memory once per CTA, one thread per particle,
-// neighbours streamed from the warp-blocked list and gathered with 16-B loads.  Solver control
+// The neighbour-sum kernels are tile passes (tile.cuh): persistent CTAs, the 40-kB kernel lookup table
+// staged into shared memory once per CTA, the neighbour payload of a tile's 6x6x6-cell halo box staged
+// once per tile, one thread per particle streaming 16-bit local neighbour indices.  Solver control
 // (iteration counters, residual means, continue flags) lives in DevState: the loop-carried decision
 // of the reference's host loops is taken by the last block of the iteration kernel.
 #include "solver.h"
+#include "tile.cuh"
 #include <algorithm>
 
 namespace vfd {
 
-extern __shared__ __align__(16) float smemLut[];
+extern __shared__ __align__(128) unsigned char smemRaw[];
 
 #define FOR_EACH_TILE(p) for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += gridDim.x * blockDim.x)
 
+// shared memory of a tile-pass kernel: [TileShared][NLUT lookup tables][payload]
+template<int NLUT> __device__ __forceinline__ float* smem_lut() { return reinterpret_cast<float*>(smemRaw + smem_header_bytes()); }
+template<int NLUT, class Payload> __device__ __forceinline__ Payload* smem_payload() {
+    return reinterpret_cast<Payload*>(smemRaw + smem_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float));
+}
+template<int NLUT, class Payload> static size_t tile_smem_bytes(uint32_t cap) {
+    return smem_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float) + (size_t)cap * sizeof(Payload);
+}
+
 // ---- K2 + K3 + K8 fused: density, DFSPH factor, a = g --------------------------------------
-__global__ void __launch_bounds__(512) k_density_factor(Params P, Arrays A, const float* __restrict__ lutW, const float* __restrict__ lutG) {
-    float* sW = smemLut;
-    float* sG = smemLut + VFD_LUT_RES;
-    load_lut(sW, lutW);
-    load_lut(sG, lutG);
-    __syncthreads();
-    Lut K{ sW, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 };
-    const float4* __restrict__ pos = A.pos;
-    FOR_EACH_TILE(p) {
-        const float3 xi = f3(pos[p]);
-        const uint32_t m = A.cnt[p];
-        const uint32_t* col = nbr_column(A.list, p);
+struct DensityFactorOp {
+    typedef float4 Payload;
+    static constexpr bool READ_COUNT = true;
+    const Params& P; const Arrays& A; Lut K;
+    __device__ __forceinline__ float4 load(uint32_t g) const { return A.pos[g]; }
+    template<class Acc>
+    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+        const float3 xi = f3(A.pos[p]);
+        const uint16_t* col = A.list16 + ell;
         float rho = P.volume * P.wZero;
         float3 gradI = f3(0.0f, 0.0f, 0.0f);
         float sumK = 0.0f;
         for (uint32_t k = 0; k < m; k++) {
-            const uint32_t j = col[(size_t)k * 32];
-            const float3 xij = xi - f3(pos[j]);
+            const float3 xij = xi - f3(acc(col[(size_t)k * 32]));
             rho += P.volume * K.w(xij);
             const float3 gj = -P.volume * K.gradW(xij);
             sumK += dot3(gj, gj);
@@ -64,97 +70,94 @@ __global__ void __launch_bounds__(512) k_density_factor(Params P, Arrays A, cons
         A.alpha[p] = (sumK > VFD_EPS_F) ? 1.0f / sumK : 0.0f;
         A.acc[p] = make_float4(P.gx, P.gy, P.gz, 0.0f);
     }
+};
+
+__global__ void __launch_bounds__(TILE_THREADS) k_density_factor(const __grid_constant__ Params P, const __grid_constant__ Arrays A, const DevState* S, const float* __restrict__ lutW, const float* __restrict__ lutG) {
+    float* sW = smem_lut<2>();
+    float* sG = sW + VFD_LUT_RES;
+    load_lut_tile(sW, lutW);
+    load_lut_tile(sG, lutG);
+    DensityFactorOp op{ P, A, Lut{ sW, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 } };
+    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), smem_payload<2, float4>(), STAGE_CAP16, op);
 }
 
 // ---- K4 / K10: solver source terms ----------------------------------------------------------
 // rate = V * sum_j (v_i - v_j) . gradW_ij + sum_b V_b v_i . gradW_ib
-__device__ __forceinline__ float velocity_divergence(const Params& P, const Arrays& A, const Lut& K, uint32_t p, uint32_t m) {
-    const float4* __restrict__ pos = A.posRho;
-    const float4* __restrict__ vel = A.vel;
-    const float3 xi = f3(pos[p]);
-    const float3 vi = f3(vel[p]);
-    const uint32_t* col = nbr_column(A.list, p);
-    float s = 0.0f;
-    for (uint32_t k = 0; k < m; k++) {
-        const uint32_t j = col[(size_t)k * 32];
-        s += dot3(vi - f3(vel[j]), K.gradW(xi - f3(pos[j])));
+template<bool DIV>
+struct SourceOp {
+    typedef Pay32 Payload;
+    static constexpr bool READ_COUNT = true;
+    const Params& P; const Arrays& A; Lut K;
+    float dt, dtInv, dt2Inv;
+    __device__ __forceinline__ Pay32 load(uint32_t g) const { return Pay32{ A.posRho[g], A.vel[g] }; }
+    template<class Acc>
+    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+        const float3 xi = f3(A.posRho[p]);
+        const float3 vi = f3(A.vel[p]);
+        const uint16_t* col = A.list16 + ell;
+        float s = 0.0f;
+        for (uint32_t k = 0; k < m; k++) {
+            const Pay32 nb = acc(col[(size_t)k * 32]);
+            s += dot3(vi - f3(nb.b), K.gradW(xi - f3(nb.a)));
+        }
+        s *= P.volume;
+        for (uint32_t b = 0; b < P.nBodies; b++) {
+            const float4 bx = A.bx[b][p];
+            if (bx.w > 0.0f) s += bx.w * dot3(vi, K.gradW(xi - f3(bx)));
+        }
+        if (DIV) {
+            const float adv = m < 20u ? 0.0f : fmaxf(s, 0.0f);
+            const float factor = A.alpha[p] * dtInv;
+            A.rhoAdv[p] = adv;
+            A.alpha[p] = factor;
+            A.kappaV[p] = adv * factor;
+        } else {
+            const float adv = A.rho[p] / P.rho0 + dt * s;
+            const float factor = A.alpha[p] * dt2Inv;
+            const float residuum = fminf(1.0f - adv, 0.0f);
+            A.rhoAdv[p] = adv;
+            A.alpha[p] = factor;
+            A.kappa[p] = -residuum * factor;
+        }
     }
-    s *= P.volume;
-    for (uint32_t b = 0; b < P.nBodies; b++) {
-        const float4 bx = A.bx[b][p];
-        if (bx.w > 0.0f) s += bx.w * dot3(vi, K.gradW(xi - f3(bx)));
-    }
-    return s;
-}
+};
 
-__global__ void __launch_bounds__(VFD_TPB) k_divergence_source(Params P, Arrays A, DevState* S, const float* __restrict__ lutG) {
-    load_lut(smemLut, lutG);
-    __syncthreads();
-    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
-    const float dtInv = S->dtInv;
+template<bool DIV>
+__global__ void __launch_bounds__(TILE_THREADS) k_source(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+    float* sG = smem_lut<1>();
+    load_lut_tile(sG, lutG);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        // loop entry of ComputeDivergence (DFSPHImplementation.cu:526-532): error 0, so the loop is
-        // entered only through the minimum iteration count
-        S->divIt = 0; S->divErr = 0.0f;
-        S->divActive = (0u < P.minDivIt && 0u < P.maxDivIt) ? 1u : 0u;
+        // loop entry of ComputeDivergence / ComputePressure (DFSPHImplementation.cu:526-532, 455-461): error 0, so the
+        // loop is entered only through the minimum iteration count
+        if (DIV) { S->divIt = 0; S->divErr = 0.0f; S->divActive = (0u < P.minDivIt && 0u < P.maxDivIt) ? 1u : 0u; }
+        else     { S->pressIt = 0; S->pressErr = 0.0f; S->pressActive = (0u < P.minPressIt && 0u < P.maxPressIt) ? 1u : 0u; }
     }
-    FOR_EACH_TILE(p) {
-        const uint32_t m = A.cnt[p];
-        float adv = velocity_divergence(P, A, K, p, m);
-        adv = m < 20u ? 0.0f : fmaxf(adv, 0.0f);
-        const float factor = A.alpha[p] * dtInv;
-        A.rhoAdv[p] = adv;
-        A.alpha[p] = factor;
-        A.kappaV[p] = adv * factor;
-    }
-}
-
-__global__ void __launch_bounds__(VFD_TPB) k_pressure_source(Params P, Arrays A, DevState* S, const float* __restrict__ lutG) {
-    load_lut(smemLut, lutG);
-    __syncthreads();
-    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
-    const float dt = S->dt, dt2Inv = S->dt2Inv;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        S->pressIt = 0; S->pressErr = 0.0f;
-        S->pressActive = (0u < P.minPressIt && 0u < P.maxPressIt) ? 1u : 0u;   // DFSPHImplementation.cu:455-461
-    }
-    FOR_EACH_TILE(p) {
-        const uint32_t m = A.cnt[p];
-        const float delta = velocity_divergence(P, A, K, p, m);
-        const float adv = A.rho[p] / P.rho0 + dt * delta;
-        const float factor = A.alpha[p] * dt2Inv;
-        const float si = 1.0f - adv;
-        const float residuum = fminf(si, 0.0f);
-        A.rhoAdv[p] = adv;
-        A.alpha[p] = factor;
-        A.kappa[p] = -residuum * factor;
-    }
+    SourceOp<DIV> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, S->dtInv, S->dt2Inv };
+    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), smem_payload<1, Pay32>(), STAGE_CAP32, op);
 }
 
 // ---- K5 / K7 / K11 / K13: pressure acceleration from kappa ---------------------------------
 enum { ACC_DIV_ITER = 0, ACC_DIV_FINISH = 1, ACC_PRESS_ITER = 2, ACC_PRESS_FINISH = 3 };
 
 template<int MODE>
-__global__ void __launch_bounds__(VFD_TPB) k_pressure_accel(Params P, Arrays A, const DevState* __restrict__ S, const float* __restrict__ lutG) {
-    if (MODE == ACC_DIV_ITER && !S->divActive) return;
-    if (MODE == ACC_PRESS_ITER && !S->pressActive) return;
-    load_lut(smemLut, lutG);
-    __syncthreads();
-    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
-    const float4* __restrict__ pos = A.posRho;
-    const float* __restrict__ kap = (MODE == ACC_DIV_ITER || MODE == ACC_DIV_FINISH) ? A.kappaV : A.kappa;
-    const float dt = S->dt;
-    FOR_EACH_TILE(p) {
-        const float3 xi = f3(pos[p]);
+struct AccelOp {
+    typedef float4 Payload;          // (x, y, z, kappa)
+    static constexpr bool READ_COUNT = true;
+    const Params& P; const Arrays& A; Lut K;
+    const float* __restrict__ kap;
+    float dt;
+    __device__ __forceinline__ float4 load(uint32_t g) const { float4 x = A.posRho[g]; x.w = kap[g]; return x; }
+    template<class Acc>
+    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+        const float3 xi = f3(A.posRho[p]);
         const float ki = kap[p];
-        const uint32_t m = A.cnt[p];
-        const uint32_t* col = nbr_column(A.list, p);
+        const uint16_t* col = A.list16 + ell;
         float3 a = f3(0.0f, 0.0f, 0.0f);
         for (uint32_t k = 0; k < m; k++) {
-            const uint32_t j = col[(size_t)k * 32];
-            const float ks = ki + kap[j];
+            const float4 nb = acc(col[(size_t)k * 32]);
+            const float ks = ki + nb.w;
             if (fabsf(ks) > VFD_EPS_F) {
-                const float3 gj = -P.volume * K.gradW(xi - f3(pos[j]));
+                const float3 gj = -P.volume * K.gradW(xi - f3(nb));
                 a += ks * gj;
             }
         }
@@ -175,29 +178,37 @@ __global__ void __launch_bounds__(VFD_TPB) k_pressure_accel(Params P, Arrays A, 
         }
         if (MODE == ACC_DIV_FINISH) A.alpha[p] *= dt;
     }
+};
+
+template<int MODE>
+__global__ void __launch_bounds__(TILE_THREADS) k_pressure_accel(const __grid_constant__ Params P, const __grid_constant__ Arrays A, const DevState* __restrict__ S, const float* __restrict__ lutG) {
+    if (MODE == ACC_DIV_ITER && !S->divActive) return;
+    if (MODE == ACC_PRESS_ITER && !S->pressActive) return;
+    float* sG = smem_lut<1>();
+    load_lut_tile(sG, lutG);
+    AccelOp<MODE> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 },
+                      (MODE == ACC_DIV_ITER || MODE == ACC_DIV_FINISH) ? A.kappaV : A.kappa, S->dt };
+    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), smem_payload<1, float4>(), STAGE_CAP16, op);
 }
 
 // ---- K6 / K12 (+ R1 / R3): one Jacobi update and the fused residual reduction ----------------
 template<bool DIV>
-__global__ void __launch_bounds__(VFD_TPB) k_solve_iteration(Params P, Arrays A, DevState* S, const float* __restrict__ lutG) {
-    if (DIV ? !S->divActive : !S->pressActive) return;
-    __shared__ double shRed[32];
-    load_lut(smemLut, lutG);
-    __syncthreads();
-    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
-    const float4* __restrict__ pos = A.posRho;
-    const float4* __restrict__ pacc = A.pacc;
-    const float scale = DIV ? S->dt : S->dt2;
-    float errSum = 0.0f;
-    FOR_EACH_TILE(p) {
-        const float3 xi = f3(pos[p]);
-        const float3 ai = f3(pacc[p]);
-        const uint32_t m = A.cnt[p];
-        const uint32_t* col = nbr_column(A.list, p);
+struct SolveOp {
+    typedef Pay32 Payload;           // position, pressure acceleration
+    static constexpr bool READ_COUNT = true;
+    const Params& P; const Arrays& A; Lut K;
+    float scale;
+    float errSum;
+    __device__ __forceinline__ Pay32 load(uint32_t g) const { return Pay32{ A.posRho[g], A.pacc[g] }; }
+    template<class Acc>
+    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+        const float3 xi = f3(A.posRho[p]);
+        const float3 ai = f3(A.pacc[p]);
+        const uint16_t* col = A.list16 + ell;
         float s = 0.0f;
         for (uint32_t k = 0; k < m; k++) {
-            const uint32_t j = col[(size_t)k * 32];
-            s += dot3(ai - f3(pacc[j]), K.gradW(xi - f3(pos[j])));
+            const Pay32 nb = acc(col[(size_t)k * 32]);
+            s += dot3(ai - f3(nb.b), K.gradW(xi - f3(nb.a)));
         }
         s *= P.volume;
         for (uint32_t b = 0; b < P.nBodies; b++) {
@@ -216,11 +227,22 @@ __global__ void __launch_bounds__(VFD_TPB) k_solve_iteration(Params P, Arrays A,
         A.res[p] = residuum;
         errSum += P.rho0 * residuum;
     }
-    double v[1] = { (double)errSum };
+};
+
+template<bool DIV>
+__global__ void __launch_bounds__(TILE_THREADS) k_solve_iteration(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+    if (DIV ? !S->divActive : !S->pressActive) return;
+    TileShared& sh = smem_header(smemRaw);
+    float* sG = smem_lut<1>();
+    load_lut_tile(sG, lutG);
+    SolveOp<DIV> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, DIV ? S->dt : S->dt2, 0.0f };
+    tile_pass(S, A.cellBegin, A.cnt, sh, smem_payload<1, Pay32>(), STAGE_CAP32, op);
+    __syncthreads();
+    double v[1] = { (double)op.errSum };
     uint32_t* ticket = &S->ticket[DIV ? 1 : 2];
-    if (block_reduce_publish<1>(v, A.partials, ticket, shRed)) {
+    if (block_reduce_publish<1>(v, A.partials, ticket, sh.red)) {
         double tot[1];
-        last_block_fold<1>(tot, A.partials, shRed);
+        last_block_fold<1>(tot, A.partials, sh.red);
         if (threadIdx.x == 0) {
             // the reference folds with thrust::minus from 0 (DFSPHImplementation.cu:483-489, 554-560):
             // as a left fold that is -(sum), the mean of rho0*|residuum|
@@ -299,59 +321,64 @@ __global__ void k_clear_acc(Params P, Arrays A) {
 }
 
 // ---- launchers -------------------------------------------------------------------------------
-static const size_t LUT_BYTES = VFD_LUT_RES * sizeof(float);
-
+// persistent grid: resident CTAs per SM (from the occupancy calculator) x SMs
 template<typename Kern>
-static uint32_t persistent_grid(Kern kern, int threads, size_t smem, const LaunchCfg& L, uint32_t n) {
-    static thread_local const void* cachedK[16]; static thread_local int cachedV[16]; static thread_local int nc = 0;
+static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L) {
+    static thread_local const void* cachedK[32]; static thread_local int cachedV[32]; static thread_local int nc = 0;
     int perSM = 0;
     for (int i = 0; i < nc; i++) if (cachedK[i] == (const void*)kern) perSM = cachedV[i];
     if (!perSM) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, TILE_THREADS, smem);
         if (perSM < 1) perSM = 1;
-        if (nc < 16) { cachedK[nc] = (const void*)kern; cachedV[nc] = perSM; nc++; }
+        if (nc < 32) { cachedK[nc] = (const void*)kern; cachedV[nc] = perSM; nc++; }
     }
-    const uint32_t tiles = (n + threads - 1) / threads;
-    return std::max(1u, std::min<uint32_t>(tiles, (uint32_t)(perSM * L.numSMs)));
+    return (uint32_t)(perSM * L.numSMs);
 }
 
-void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState*, const float* lutW, const float* lutG) {
-    const uint32_t g = persistent_grid(k_density_factor, 512, 2 * LUT_BYTES, L, P.n);
+void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState* S, const float* lutW, const float* lutG) {
+    const size_t smem = tile_smem_bytes<2, float4>(STAGE_CAP16);
+    const uint32_t g = tile_grid(k_density_factor, smem, L);
     LaunchScope ls(L, KID_DENSITY_FACTOR);
-    k_density_factor<<<g, 512, 2 * LUT_BYTES, L.stream>>>(P, A, lutW, lutG);
+    k_density_factor<<<g, TILE_THREADS, smem, L.stream>>>(P, A, S, lutW, lutG);
 }
 void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const uint32_t g = persistent_grid(k_divergence_source, VFD_TPB, LUT_BYTES, L, P.n);
+    const size_t smem = tile_smem_bytes<1, Pay32>(STAGE_CAP32);
+    const uint32_t g = tile_grid(k_source<true>, smem, L);
     LaunchScope ls(L, KID_DIV_SOURCE);
-    k_divergence_source<<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    k_source<true><<<g, TILE_THREADS, smem, L.stream>>>(P, A, S, lutG);
 }
 void launch_divergence_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const uint32_t g1 = persistent_grid(k_pressure_accel<ACC_DIV_ITER>, VFD_TPB, LUT_BYTES, L, P.n);
-    { LaunchScope ls(L, KID_DIV_ACCEL); k_pressure_accel<ACC_DIV_ITER><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
-    const uint32_t g2 = persistent_grid(k_solve_iteration<true>, VFD_TPB, LUT_BYTES, L, P.n);
-    { LaunchScope ls(L, KID_DIV_SOLVE); k_solve_iteration<true><<<g2, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
+    const size_t s1 = tile_smem_bytes<1, float4>(STAGE_CAP16), s2 = tile_smem_bytes<1, Pay32>(STAGE_CAP32);
+    const uint32_t g1 = tile_grid(k_pressure_accel<ACC_DIV_ITER>, s1, L);
+    { LaunchScope ls(L, KID_DIV_ACCEL); k_pressure_accel<ACC_DIV_ITER><<<g1, TILE_THREADS, s1, L.stream>>>(P, A, S, lutG); }
+    const uint32_t g2 = tile_grid(k_solve_iteration<true>, s2, L);
+    { LaunchScope ls(L, KID_DIV_SOLVE); k_solve_iteration<true><<<g2, TILE_THREADS, s2, L.stream>>>(P, A, S, lutG); }
 }
 void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const uint32_t g = persistent_grid(k_pressure_accel<ACC_DIV_FINISH>, VFD_TPB, LUT_BYTES, L, P.n);
+    const size_t smem = tile_smem_bytes<1, float4>(STAGE_CAP16);
+    const uint32_t g = tile_grid(k_pressure_accel<ACC_DIV_FINISH>, smem, L);
     LaunchScope ls(L, KID_DIV_FINISH);
-    k_pressure_accel<ACC_DIV_FINISH><<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    k_pressure_accel<ACC_DIV_FINISH><<<g, TILE_THREADS, smem, L.stream>>>(P, A, S, lutG);
 }
 void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const uint32_t g = persistent_grid(k_pressure_source, VFD_TPB, LUT_BYTES, L, P.n);
+    const size_t smem = tile_smem_bytes<1, Pay32>(STAGE_CAP32);
+    const uint32_t g = tile_grid(k_source<false>, smem, L);
     LaunchScope ls(L, KID_PRESS_SOURCE);
-    k_pressure_source<<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    k_source<false><<<g, TILE_THREADS, smem, L.stream>>>(P, A, S, lutG);
 }
 void launch_pressure_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const uint32_t g1 = persistent_grid(k_pressure_accel<ACC_PRESS_ITER>, VFD_TPB, LUT_BYTES, L, P.n);
-    { LaunchScope ls(L, KID_PRESS_ACCEL); k_pressure_accel<ACC_PRESS_ITER><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
-    const uint32_t g2 = persistent_grid(k_solve_iteration<false>, VFD_TPB, LUT_BYTES, L, P.n);
-    { LaunchScope ls(L, KID_PRESS_SOLVE); k_solve_iteration<false><<<g2, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
+    const size_t s1 = tile_smem_bytes<1, float4>(STAGE_CAP16), s2 = tile_smem_bytes<1, Pay32>(STAGE_CAP32);
+    const uint32_t g1 = tile_grid(k_pressure_accel<ACC_PRESS_ITER>, s1, L);
+    { LaunchScope ls(L, KID_PRESS_ACCEL); k_pressure_accel<ACC_PRESS_ITER><<<g1, TILE_THREADS, s1, L.stream>>>(P, A, S, lutG); }
+    const uint32_t g2 = tile_grid(k_solve_iteration<false>, s2, L);
+    { LaunchScope ls(L, KID_PRESS_SOLVE); k_solve_iteration<false><<<g2, TILE_THREADS, s2, L.stream>>>(P, A, S, lutG); }
 }
 void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const uint32_t g = persistent_grid(k_pressure_accel<ACC_PRESS_FINISH>, VFD_TPB, LUT_BYTES, L, P.n);
+    const size_t smem = tile_smem_bytes<1, float4>(STAGE_CAP16);
+    const uint32_t g = tile_grid(k_pressure_accel<ACC_PRESS_FINISH>, smem, L);
     LaunchScope ls(L, KID_PRESS_FINISH);
-    k_pressure_accel<ACC_PRESS_FINISH><<<g, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG);
+    k_pressure_accel<ACC_PRESS_FINISH><<<g, TILE_THREADS, smem, L.stream>>>(P, A, S, lutG);
 }
 void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A) {
     LaunchScope ls(L, KID_CLEAR_ACC);

@@ -1,4 +1,4 @@
-// search.cu — neighbourhood search: cell hashing, single-pass radix (counting) sort keyed by
+// search.cu — neighbourhood search: tile-major cell hashing, single-pass counting (radix) sort keyed by
 // the cell id, physical reorder of the particle SoA, cell tables and neighbour lists.
 //
 // Replaces ParticleSearch::FindNeighbors (reference: ParticleSearch/ParticleSearch.h:48-61,
@@ -7,34 +7,21 @@
 // (ParticleSearchKernels.cu:126,131).  Differences by design:
 //   * particles are physically reordered every step (the reference only builds an index
 //     permutation and gathers 120-B AoS structs through it);
-//   * the cell key is x-fastest inside a (y,z) row, so the 27-cell stencil is 9 contiguous
-//     candidate ranges [cellBegin[c-1], cellBegin[c+2]) instead of 27 table lookups;
-//   * in-cell order is by previous slot index (deterministic), not by atomic arrival;
-//   * one traversal writes the list (fixed-capacity warp-blocked ELL), instead of count+scan+fill;
+//   * the cell key is tile-major (4x4x4-cell tiles, the reference uses 8^3 Morton blocks), so that a
+//     CTA owns one compact tile and stages its 6x6x6-cell halo box in shared memory (tile.cuh);
+//   * in-cell order is by persistent particle id (deterministic, and identical on every GPU that
+//     holds a copy of the cell), not by atomic arrival;
+//   * one traversal writes the list — 16-bit tile-local indices in a warp-blocked ELL — instead of
+//     count + scan + fill of 32-bit global ids;
 //   * no host round trip: the grid is derived on the device.
 #include "solver.h"
+#include "tile.cuh"
 #include <limits.h>
 
 namespace vfd {
 
 #define SCAN_ITEMS 16
 #define SCAN_TILE (VFD_TPB * SCAN_ITEMS)   // 4096 cells per tile
-
-// cell slightly larger than h so that two particles closer than h can never be two cells apart
-// through fp32 rounding of the cell coordinate
-__device__ __forceinline__ float cell_inv(float h) { return (1.0f / h) * (1.0f - 1.0f / 1024.0f); }
-
-__device__ __forceinline__ uint3 cell_of(float4 x, const DevState* S, float invCell) {
-    uint3 c;
-    c.x = (uint32_t)((x.x - S->gridOrigin[0]) * invCell);
-    c.y = (uint32_t)((x.y - S->gridOrigin[1]) * invCell);
-    c.z = (uint32_t)((x.z - S->gridOrigin[2]) * invCell);
-    // robustness against NaN / escaped particles: clamp into the padded interior
-    c.x = min(max(c.x, 1u), S->gridDim[0] - 2u);
-    c.y = min(max(c.y, 1u), S->gridDim[1] - 2u);
-    c.z = min(max(c.z, 1u), S->gridDim[2] - 2u);
-    return c;
-}
 
 // S1: extrema of floor(x/h) (same definition as ComputeMinMaxKernel, ParticleSearchKernels.cu:40-62),
 // then the last block derives the grid.
@@ -68,13 +55,19 @@ __global__ void __launch_bounds__(VFD_TPB) k_bounds(Params P, const float4* __re
         for (int k = 0; k < 3; k++) {
             const int lo = *(volatile int*)&S->boundsMin[k], hi = *(volatile int*)&S->boundsMax[k];
             S->gridMinCell[k] = lo;                      // reported bounds (ParticleSearch.cu:50-54)
-            const long long dim = (long long)hi - lo + 5;   // two pad cells below, two above
-            S->gridDim[k] = (uint32_t)min(dim, 1ll << 20);
+            long long dim = (long long)hi - lo + 5;         // two pad cells below, two above
+            dim = (min(dim, 1ll << 20) + 3) / 4 * 4;        // whole tiles
+            S->gridDim[k] = (uint32_t)dim;
+            S->tileDim[k] = (uint32_t)(dim / 4);
             S->gridOrigin[k] = (float)(lo - 2) * P.h;
-            cells *= (unsigned long long)S->gridDim[k];
+            cells *= (unsigned long long)dim;
         }
-        if (cells + 1 > cellCapacity) { S->errorFlags |= 1u; S->gridDim[0] = S->gridDim[1] = S->gridDim[2] = 3; cells = 27; }
+        if (cells + 1 > cellCapacity) {
+            S->errorFlags |= 1u; cells = 64;
+            for (int k = 0; k < 3; k++) { S->gridDim[k] = 4; S->tileDim[k] = 1; }
+        }
         S->nCells = (uint32_t)cells;
+        S->nTiles = (uint32_t)(cells / 64);
         S->boundsMax[0] = S->boundsMax[1] = S->boundsMax[2] = INT_MIN;   // re-arm for the next step
         // keep the reported maximum cell for GetBounds in the padded slots of boundsMin? no: store in gridMinCell/gridDim
         S->boundsMin[0] = S->boundsMin[1] = S->boundsMin[2] = INT_MAX;
@@ -88,7 +81,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_hist(Params P, const float4* __rest
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const uint3 c = cell_of(pos[i], S, cell_inv(P.h));
-    const uint32_t k = (c.z * S->gridDim[1] + c.y) * S->gridDim[0] + c.x;
+    const uint32_t k = cell_key(c.x, c.y, c.z, S);
     key[i] = k;
     rank[i] = atomicAdd(&cellCount[k], 1u);
 }
@@ -192,7 +185,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_scatter(Params P, const uint32_t* _
     tmpIdx[cellBegin[key[i]] + rank[i]] = i;
 }
 
-// S5: make the in-cell order deterministic (rank by previous slot index) and move the persistent
+// S5: make the in-cell order deterministic (rank by persistent particle id) and move the persistent
 // particle state to its sorted slot.
 __global__ void __launch_bounds__(VFD_TPB) k_reorder(Params P, Arrays A) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,8 +193,9 @@ __global__ void __launch_bounds__(VFD_TPB) k_reorder(Params P, Arrays A) {
     const uint32_t i0 = A.tmpIdx[q];
     const uint32_t c = A.key[i0];
     const uint32_t b = A.cellBegin[c], e = A.cellBegin[c + 1];
+    const uint32_t myId = A.id[i0];
     uint32_t r = 0;
-    for (uint32_t t = b; t < e; t++) r += (A.tmpIdx[t] < i0) ? 1u : 0u;
+    for (uint32_t t = b; t < e; t++) r += (A.id[A.tmpIdx[t]] < myId) ? 1u : 0u;
     const uint32_t dst = b + r;
     A.pos2[dst] = A.pos[i0];
     A.vel2[dst] = A.vel[i0];
@@ -213,35 +207,57 @@ __global__ void __launch_bounds__(VFD_TPB) k_reorder(Params P, Arrays A) {
     A.id2[dst] = A.id[i0];
 }
 
-// S6/S8: one traversal of the 3x3 rows of 3 cells; candidates of a row are contiguous in memory.
+// S6/S8: one traversal of the 3x3 stencil rows (3 x-adjacent cells = one contiguous local range) over the
+// positions staged in shared memory; writes 16-bit tile-local indices.
 template<bool FMA>
-__global__ void __launch_bounds__(VFD_TPB) k_build_list(Params P, const float4* __restrict__ pos, const DevState* __restrict__ S,
-                                                        const uint32_t* __restrict__ cellBegin, uint32_t* __restrict__ cnt, uint32_t* __restrict__ list) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n) return;
-    const float4 xi = pos[p];
-    const uint3 c = cell_of(xi, S, cell_inv(P.h));
-    const uint32_t dimX = S->gridDim[0], dimY = S->gridDim[1];
-    uint32_t* col = list + (size_t)(p >> 5) * (VFD_MAX_NEIGHBORS * 32) + (p & 31);
-    uint32_t m = 0;
-    for (int dz = -1; dz <= 1 && m < VFD_MAX_NEIGHBORS; dz++) {
-        for (int dy = -1; dy <= 1 && m < VFD_MAX_NEIGHBORS; dy++) {
-            const uint32_t rowKey = ((c.z + dz) * dimY + (c.y + dy)) * dimX + c.x - 1u;
-            const uint32_t jb = cellBegin[rowKey], je = cellBegin[rowKey + 3u];
-            for (uint32_t j = jb; j < je; j++) {
-                const float4 xj = pos[j];
-                const float dx = xj.x - xi.x, dyy = xj.y - xi.y, dzz = xj.z - xi.z;
-                float d2;
-                if (FMA) d2 = __fmaf_rn(dzz, dzz, __fmaf_rn(dx, dx, __fmul_rn(dyy, dyy)));   // how nvcc compiles ParticleSearchKernels.cu:124
-                else     d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dyy, dyy)), __fmul_rn(dzz, dzz));
-                if (d2 < P.h2 && d2 > 0.0f) {
-                    col[(size_t)m * 32] = j;
-                    if (++m == VFD_MAX_NEIGHBORS) break;
+struct SearchOp {
+    typedef float4 Payload;
+    static constexpr bool READ_COUNT = false;
+    const float4* __restrict__ pos;
+    const DevState* __restrict__ S;
+    const TileShared* sh;
+    uint32_t* __restrict__ cnt;
+    uint16_t* __restrict__ list;
+    float h2, invCell;
+    __device__ __forceinline__ float4 load(uint32_t g) const { return pos[g]; }
+    template<class Acc>
+    __device__ __forceinline__ void particle(uint32_t p, uint32_t, size_t ell, const Acc& acc) {
+        const float4 xi = pos[p];
+        const uint3 c = cell_of(xi, S, invCell);
+        const uint32_t hx = (c.x & 3u) + 1u, hy = (c.y & 3u) + 1u, hz = (c.z & 3u) + 1u;   // box coordinates of the own cell
+        uint16_t* col = list + ell;
+        uint32_t m = 0;
+        for (int dz = -1; dz <= 1 && m < VFD_MAX_NEIGHBORS; dz++) {
+            for (int dy = -1; dy <= 1 && m < VFD_MAX_NEIGHBORS; dy++) {
+                const uint32_t c0 = ((hz + dz) * 6u + (hy + dy)) * 6u + hx - 1u;
+                const uint32_t jb = sh->local[c0], je = sh->local[c0 + 3u];
+                for (uint32_t j = jb; j < je; j++) {
+                    const float4 xj = acc(j);
+                    const float dx = xj.x - xi.x, dyy = xj.y - xi.y, dzz = xj.z - xi.z;
+                    float d2;
+                    if (FMA) d2 = __fmaf_rn(dzz, dzz, __fmaf_rn(dx, dx, __fmul_rn(dyy, dyy)));   // how nvcc compiles ParticleSearchKernels.cu:124
+                    else     d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dyy, dyy)), __fmul_rn(dzz, dzz));
+                    if (d2 < h2 && d2 > 0.0f) {
+                        col[(size_t)m * 32] = (uint16_t)j;
+                        if (++m == VFD_MAX_NEIGHBORS) break;
+                    }
                 }
             }
         }
+        cnt[p] = m;
     }
-    cnt[p] = m;
+};
+
+#define SEARCH_CAP 4096   // staged positions per tile (16 B each); halo boxes above it take the exact fallback path
+
+template<bool FMA>
+__global__ void __launch_bounds__(TILE_THREADS) k_build_list(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    TileShared& sh = smem_header(smemRaw);
+    float4* sPay = reinterpret_cast<float4*>(smemRaw + smem_header_bytes());
+    SearchOp<FMA> op{ A.pos, S, &sh, A.cnt, A.list16, P.h2, cell_inv(P.h) };
+    // local indices are 16-bit: a halo box beyond 65535 particles cannot be encoded (flagged, caught by the host)
+    tile_pass(S, A.cellBegin, A.cnt, sh, sPay, SEARCH_CAP, op, &S->errorFlags);
 }
 
 static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -262,8 +278,16 @@ void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, 
     std::swap(A.curv, A.curv2); std::swap(A.curvS, A.curvS2); std::swap(A.curvD, A.curvD2); std::swap(A.id, A.id2);
     {
         LaunchScope ls(L, KID_BUILD_LIST);
-        if (P.searchFma) k_build_list<true><<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.cellBegin, A.cnt, A.list);
-        else             k_build_list<false><<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.cellBegin, A.cnt, A.list);
+        const size_t smem = smem_header_bytes() + (size_t)SEARCH_CAP * sizeof(float4);
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(k_build_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_build_list<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr = true;
+        }
+        const uint32_t grid = (uint32_t)L.numSMs * 3u;
+        if (P.searchFma) k_build_list<true><<<grid, TILE_THREADS, smem, L.stream>>>(P, A, S);
+        else             k_build_list<false><<<grid, TILE_THREADS, smem, L.stream>>>(P, A, S);
     }
 }
 

@@ -4,6 +4,7 @@
 // as a stream of kernels with no host round trip unless a solver is convergence-driven (then the
 // continue flag is polled with one batch of look-ahead).  Solver::simulate() is Simulate() (:33-61).
 #include "solver_impl.h"
+#include "tile.cuh"
 #include <algorithm>
 #include <cstring>
 #include <limits.h>
@@ -84,13 +85,26 @@ __global__ void k_export_frame(Params P, Arrays A, VfdParticleSimple* __restrict
     out[A.id[p]] = q;
 }
 
-__global__ void k_export_neighbors(Params P, Arrays A, uint32_t* __restrict__ counts, uint32_t* __restrict__ idsPadded) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n) return;
-    const uint32_t o = A.id[p], m = A.cnt[p];
-    counts[o] = m;
-    const uint32_t* col = nbr_column(A.list, p);
-    for (uint32_t k = 0; k < m; k++) idsPadded[(size_t)o * VFD_MAX_NEIGHBORS + k] = A.id[col[(size_t)k * 32]];
+// neighbour lists hold tile-local indices: translate through the tile's staged persistent ids
+struct ExportNeighborsOp {
+    typedef uint32_t Payload;
+    static constexpr bool READ_COUNT = true;
+    const Arrays& A;
+    uint32_t* __restrict__ counts;
+    uint32_t* __restrict__ idsPadded;
+    __device__ __forceinline__ uint32_t load(uint32_t g) const { return A.id[g]; }
+    template<class Acc>
+    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+        const uint32_t o = A.id[p];
+        counts[o] = m;
+        const uint16_t* col = A.list16 + ell;
+        for (uint32_t k = 0; k < m; k++) idsPadded[(size_t)o * VFD_MAX_NEIGHBORS + k] = acc(col[(size_t)k * 32]);
+    }
+};
+__global__ void __launch_bounds__(TILE_THREADS) k_export_neighbors(const __grid_constant__ Arrays A, const DevState* S, uint32_t* __restrict__ counts, uint32_t* __restrict__ idsPadded) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    ExportNeighborsOp op{ A, counts, idsPadded };
+    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), reinterpret_cast<uint32_t*>(smemRaw + smem_header_bytes()), 8192u, op);
 }
 
 __global__ void k_export_boundary(Params P, Arrays A, uint32_t body, float* __restrict__ xj, float* __restrict__ vol) {
@@ -271,9 +285,9 @@ void Solver::free_particles() {
     Arrays& A = arrays;
     void* ptrs[] = { A.pos, A.vel, A.dv, A.nbar, A.curv, A.curvS, A.curvD, A.id, A.pos2, A.vel2, A.dv2, A.nbar2, A.curv2, A.curvS2, A.curvD2, A.id2,
                      A.posRho, A.acc, A.pacc, A.nrm, A.res, A.rho, A.rhoAdv, A.kappa, A.kappaV, A.alpha, A.cgG, A.cgR, A.cgP, A.cgQ, A.cgZ, A.minv,
-                     A.cnt, A.list, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.partials, dPos0, dVel0 };
+                     A.cnt, A.list16, A.coef, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.partials, dPos0, dVel0 };
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (int b = 0; b < VFD_MAX_BODIES; b++) if (A.bx[b]) cudaFree(A.bx[b]);
+    for (int b = 0; b < VFD_MAX_BODIES; b++) { if (A.bx[b]) cudaFree(A.bx[b]); if (A.bcoef[b]) cudaFree(A.bcoef[b]); }
     memset(&A, 0, sizeof A);
     dPos0 = dVel0 = nullptr;
     allocBytes = 0;
@@ -291,20 +305,22 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
     CK(dalloc(A.minv, np * 9)); allocBytes += np * 36;
     uint32_t** u1s[] = { &A.id, &A.id2, &A.cnt, &A.key, &A.rank, &A.tmpIdx };
     for (uint32_t** p : u1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
-    CK(dalloc(A.list, np * VFD_MAX_NEIGHBORS)); searchBytes = np * VFD_MAX_NEIGHBORS * 4 + np * 4 * 4;
-    allocBytes += np * VFD_MAX_NEIGHBORS * 4;
+    CK(dalloc(A.list16, np * VFD_MAX_NEIGHBORS)); searchBytes = np * VFD_MAX_NEIGHBORS * 2 + np * 4 * 4;
+    CK(dalloc(A.coef, np * VFD_MAX_NEIGHBORS));
+    allocBytes += np * VFD_MAX_NEIGHBORS * 6;
     // search grid capacity: 64x the cells of the initial bounding box (4x per axis of head room)
     double cells0 = 1.0;
-    for (int k = 0; k < 3; k++) cells0 *= std::ceil((double)(bboxMax[k] - bboxMin[k]) / info.SupportRadius) + 5.0;
+    for (int k = 0; k < 3; k++) cells0 *= std::ceil((double)(bboxMax[k] - bboxMin[k]) / info.SupportRadius) + 9.0;
     cellEstimate = (uint32_t)std::min<double>(cells0, (double)optMaxCells);
     cellCapacity = (uint32_t)std::min<double>(std::max<double>(64.0 * cells0, (double)(1u << 20)), (double)optMaxCells);
     CK(dalloc(A.cellCount, (size_t)cellCapacity + 4)); CK(dalloc(A.cellBegin, (size_t)cellCapacity + 4));
     CK(cudaMemset(A.cellCount, 0, ((size_t)cellCapacity + 4) * 4));
+    CK(cudaMemset(A.cellBegin, 0, ((size_t)cellCapacity + 4) * 4));
     CK(dalloc(A.tileSums, (size_t)cellCapacity / 4096 + 8));
     searchBytes += ((size_t)cellCapacity * 2 + 8) * 4;
     allocBytes += ((size_t)cellCapacity * 2 + 8) * 4;
     CK(dalloc(A.partials, (size_t)4 * 65536));
-    for (uint32_t b = 0; b < info.RigidBodyCount; b++) { CK(dalloc(A.bx[b], np)); allocBytes += np * 16; }
+    for (uint32_t b = 0; b < info.RigidBodyCount; b++) { CK(dalloc(A.bx[b], np)); CK(dalloc(A.bcoef[b], np)); allocBytes += np * 32; }
     return VFD_OK;
 }
 
@@ -374,8 +390,14 @@ int Solver::set_rigid_bodies(uint32_t count, const VfdVolumeMap* maps) {
     }
     // per-body boundary sample arrays are sized by the particle count (RigidBody.cu:13-16): particles first
     const size_t np = ((size_t)info.ParticleCount + 31) / 32 * 32;
-    for (int b = 0; b < VFD_MAX_BODIES; b++) if (arrays.bx[b]) { cudaFree(arrays.bx[b]); arrays.bx[b] = nullptr; }
-    for (uint32_t b = 0; b < count && info.ParticleCount; b++) { CK(dalloc(arrays.bx[b], np)); CK(cudaMemset(arrays.bx[b], 0, np * 16)); }
+    for (int b = 0; b < VFD_MAX_BODIES; b++) {
+        if (arrays.bx[b]) { cudaFree(arrays.bx[b]); arrays.bx[b] = nullptr; }
+        if (arrays.bcoef[b]) { cudaFree(arrays.bcoef[b]); arrays.bcoef[b] = nullptr; }
+    }
+    for (uint32_t b = 0; b < count && info.ParticleCount; b++) {
+        CK(dalloc(arrays.bx[b], np)); CK(cudaMemset(arrays.bx[b], 0, np * 16));
+        CK(dalloc(arrays.bcoef[b], np)); CK(cudaMemset(arrays.bcoef[b], 0, np * 16));
+    }
     info.RigidBodyCount = count;
     refresh_params();
     return VFD_OK;
@@ -393,8 +415,8 @@ int Solver::begin() {
     s.dt = desc.TimeStepSize; s.dt2 = desc.TimeStepSize * desc.TimeStepSize;
     s.dtInv = 1.0f / s.dt; s.dt2Inv = 1.0f / s.dt2;
     s.sampleCount = info.SurfaceTensionSampleCount; s.mcFactor = info.MonteCarloFactor;
-    for (int k = 0; k < 3; k++) { s.boundsMin[k] = INT_MAX; s.boundsMax[k] = INT_MIN; s.gridDim[k] = 3; }
-    s.nCells = 27;
+    for (int k = 0; k < 3; k++) { s.boundsMin[k] = INT_MAX; s.boundsMax[k] = INT_MIN; s.gridDim[k] = 4; s.tileDim[k] = 1; }
+    s.nCells = 64; s.nTiles = 1;
     hState[0] = s;
     CK(cudaMemcpyAsync(dState, &hState[0], sizeof(DevState), cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
@@ -416,6 +438,7 @@ int Solver::read_state(DevState& out) {
     out = hState[1];
     cellEstimate = std::max<uint32_t>(out.nCells, 27u);
     if (out.errorFlags & 1u) return fail(VFD_E_CAPACITY, "search grid exceeds the cell capacity (raise VFD_OPT_MAX_CELLS; a particle escaped far from the fluid?)");
+    if (out.errorFlags & 2u) return fail(VFD_E_CAPACITY, "more than 65535 particles in one 6x6x6-cell neighbourhood: beyond the 16-bit tile-local neighbour index");
     return VFD_OK;
 }
 
@@ -682,7 +705,11 @@ int Solver::get_neighbors(uint32_t* counts, uint32_t* offsets, uint32_t* ids, ui
     CK(cudaMalloc(&dC, (size_t)n * 4));
     CK(cudaMalloc(&dI, (size_t)n * VFD_MAX_NEIGHBORS * 4));
     refresh_params();
-    k_export_neighbors<<<nblk(n), VFD_TPB, 0, stream>>>(params, arrays, dC, dI);
+    {
+        const size_t smem = smem_header_bytes() + 8192u * sizeof(uint32_t);
+        cudaFuncSetAttribute(k_export_neighbors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_export_neighbors<<<numSMs * 2, TILE_THREADS, smem, stream>>>(arrays, dState, dC, dI);
+    }
     launches += 1;
     std::vector<uint32_t> c(n), padded((size_t)n * VFD_MAX_NEIGHBORS);
     cudaError_t e = cudaMemcpyAsync(c.data(), dC, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);

@@ -28,7 +28,10 @@ struct Arrays {
     // boundary samples per rigid body: (x_b.xyz, V_b)
     float4* bx[VFD_MAX_BODIES];
     // neighbour search
-    uint32_t *cnt, *list;
+    uint32_t *cnt;
+    uint16_t *list16;                       // neighbour lists: tile-local indices, warp-blocked ELL (tile.cuh)
+    float    *coef;                         // per-pair viscosity coefficient, same ELL layout (frozen during the PCG)
+    float4   *bcoef[VFD_MAX_BODIES];        // per-particle boundary-friction coefficients of the 4 tangential samples
     uint32_t *key, *rank, *tmpIdx, *cellCount, *cellBegin, *tileSums;
     // reductions
     double* partials;
@@ -118,7 +121,6 @@ void launch_export_aos(const LaunchCfg& L, const Params& P, const Arrays& A, Vfd
 void launch_import_aos(const LaunchCfg& L, const Params& P, const Arrays& A, const VfdParticle* dIn);
 void launch_export_frame(const LaunchCfg& L, const Params& P, const Arrays& A, VfdParticleSimple* dOut);
 void launch_import_posvel(const LaunchCfg& L, const Params& P, const Arrays& A, const float* dPos, const float* dVel);
-void launch_export_neighbors(const LaunchCfg& L, const Params& P, const Arrays& A, uint32_t* dCounts, uint32_t* dIdsPadded);
 void launch_export_boundary(const LaunchCfg& L, const Params& P, const Arrays& A, uint32_t body, float* dXj, float* dVol);
 
 // host-side construction of the kernel lookup tables and the Halton sphere table

@@ -7,10 +7,12 @@
 // host (tables.cpp) and read through the read-only path.  The normal and the curvature of a particle
 // are written as one float4 so the smoothing pass gathers both with a single 16-B load.
 #include "solver.h"
+#include "tile.cuh"
 #include <algorithm>
 
 namespace vfd {
 
+extern __shared__ __align__(128) unsigned char smemRaw[];
 #define FOR_EACH_TILE(p) for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += gridDim.x * blockDim.x)
 
 __device__ __forceinline__ float3 normalize_if_nonzero(float3 v) {   // DFSPHKernels.cu:874-879
@@ -20,26 +22,25 @@ __device__ __forceinline__ float3 normalize_if_nonzero(float3 v) {   // DFSPHKer
 
 // T1: classify surface particles by the centre of mass of their neighbourhood; for those, estimate
 // the normal and curvature from the Halton samples on the support sphere not covered by a neighbour.
-__global__ void __launch_bounds__(VFD_TPB) k_st_classify(Params P, Arrays A, const DevState* __restrict__ S, const float* __restrict__ halton) {
-    const float4* __restrict__ pos = A.posRho;
-    const uint32_t sampleCount = S->sampleCount;
-    const float mcFactor = S->mcFactor;
-    const float radiusRatio = P.nbrRadius / P.r;
-    const float cover2 = radiusRatio * radiusRatio * P.h2;
-    FOR_EACH_TILE(p) {
-        const float3 xi = f3(pos[p]);
-        const uint32_t m = A.cnt[p];
-        const uint32_t* col = nbr_column(A.list, p);
+struct StClassifyOp {
+    typedef float4 Payload;
+    static constexpr bool READ_COUNT = true;
+    const Params& P; const Arrays& A;
+    const float* __restrict__ halton;
+    uint32_t sampleCount;
+    float mcFactor, cover2;
+    __device__ __forceinline__ float4 load(uint32_t g) const { return A.posRho[g]; }
+    template<class Acc>
+    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+        const float3 xi = f3(A.posRho[p]);
+        const uint16_t* col = A.list16 + ell;
         float3 n = f3(0.0f, 0.0f, 0.0f);
         float curv = A.curv[p];             // left untouched for interior particles
         if (m == 0u) {
             curv = 1.0f / P.h;
         } else {
             float3 com = f3(0.0f, 0.0f, 0.0f);
-            for (uint32_t k = 0; k < m; k++) {
-                const uint32_t j = col[(size_t)k * 32];
-                com += f3(pos[j]) - xi;
-            }
+            for (uint32_t k = 0; k < m; k++) com += f3(acc(col[(size_t)k * 32])) - xi;
             com = com / P.h;
             const float clsIn = sqrtf(dot3(com, com)) / (float)m;
             const float onLine = P.clsSlope * clsIn + P.clsConst + 0.0f;
@@ -52,8 +53,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_st_classify(Params P, Arrays A, con
                     const float3 pt = P.h * f3(__ldg(halton + i3 % VFD_HALTON_N), __ldg(halton + (i3 + 1u) % VFD_HALTON_N), __ldg(halton + (i3 + 2u) % VFD_HALTON_N));
                     bool covered = false;
                     for (uint32_t k = 0; k < m; k++) {
-                        const uint32_t j = col[(size_t)k * 32];
-                        const float3 dir = f3(pos[j]) - xi;
+                        const float3 dir = f3(acc(col[(size_t)k * 32])) - xi;
                         const float3 v = pt - dir;
                         if (dot3(v, v) <= cover2) { covered = true; break; }
                     }
@@ -72,26 +72,34 @@ __global__ void __launch_bounds__(VFD_TPB) k_st_classify(Params P, Arrays A, con
         A.curv[p] = curv;
         A.nrm[p] = make_float4(n.x, n.y, n.z, curv);
     }
+};
+
+__global__ void __launch_bounds__(TILE_THREADS) k_st_classify(const __grid_constant__ Params P, const __grid_constant__ Arrays A, const DevState* __restrict__ S, const float* __restrict__ halton) {
+    const float radiusRatio = P.nbrRadius / P.r;
+    StClassifyOp op{ P, A, halton, S->sampleCount, S->mcFactor, radiusRatio * radiusRatio * P.h2 };
+    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), reinterpret_cast<float4*>(smemRaw + smem_header_bytes()), STAGE_CAP16, op);
 }
 
 // T2: neighbour-weighted smoothing of normal and curvature among surface particles
-__global__ void __launch_bounds__(VFD_TPB) k_st_smooth(Params P, Arrays A) {
-    const float4* __restrict__ pos = A.posRho;
-    const float4* __restrict__ nrm = A.nrm;
-    const float tau = P.smoothing;
-    FOR_EACH_TILE(p) {
-        const float4 ni4 = nrm[p];
+struct StSmoothOp {
+    typedef Pay32 Payload;           // position, (normal, curvature)
+    static constexpr bool READ_COUNT = true;
+    const Params& P; const Arrays& A;
+    __device__ __forceinline__ Pay32 load(uint32_t g) const { return Pay32{ A.posRho[g], A.nrm[g] }; }
+    template<class Acc>
+    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+        const float tau = P.smoothing;
+        const float4 ni4 = A.nrm[p];
         if (ni4.x != 0.0f || ni4.y != 0.0f || ni4.z != 0.0f) {
-            const float3 xi = f3(pos[p]);
-            const uint32_t m = A.cnt[p];
-            const uint32_t* col = nbr_column(A.list, p);
+            const float3 xi = f3(A.posRho[p]);
+            const uint16_t* col = A.list16 + ell;
             float3 nc = f3(0.0f, 0.0f, 0.0f);
             float cc = 0.0f, wsum = 0.0f;
             for (uint32_t k = 0; k < m; k++) {
-                const uint32_t j = col[(size_t)k * 32];
-                const float4 nj = nrm[j];
+                const Pay32 nb = acc(col[(size_t)k * 32]);
+                const float4 nj = nb.b;
                 if (nj.x != 0.0f || nj.y != 0.0f || nj.z != 0.0f) {
-                    const float3 d = f3(pos[j]) - xi;
+                    const float3 d = f3(nb.a) - xi;
                     const float dist = sqrtf(dot3(d, d));
                     const float w = 1.0f - dist / P.h;
                     nc += f3(nj) * w;
@@ -106,6 +114,11 @@ __global__ void __launch_bounds__(VFD_TPB) k_st_smooth(Params P, Arrays A) {
             A.curvS[p] = ((1.0f - tau) * ni4.w + tau * cc) / (1.0f - tau + tau * wsum);
         }
     }
+};
+
+__global__ void __launch_bounds__(TILE_THREADS) k_st_smooth(const __grid_constant__ Params P, const __grid_constant__ Arrays A, const DevState* __restrict__ S) {
+    StSmoothOp op{ P, A };
+    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), reinterpret_cast<Pay32*>(smemRaw + smem_header_bytes()), STAGE_CAP32, op);
 }
 
 // T3: apply the force (once per smoothing pass: SURVEY.md Q18)
@@ -131,9 +144,17 @@ __global__ void __launch_bounds__(VFD_TPB) k_st_apply(Params P, Arrays A) {
 
 void launch_surface_tension(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState* S, const float* halton, uint32_t passes) {
     const uint32_t tiles = (P.n + VFD_TPB - 1) / VFD_TPB;
-    const uint32_t g = std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 6u));
-    { LaunchScope ls(L, KID_ST_CLASSIFY); k_st_classify<<<g, VFD_TPB, 0, L.stream>>>(P, A, S, halton); }
-    { LaunchScope ls(L, KID_ST_SMOOTH); k_st_smooth<<<g, VFD_TPB, 0, L.stream>>>(P, A); }
+    const size_t s1 = smem_header_bytes() + (size_t)STAGE_CAP16 * sizeof(float4), s2 = smem_header_bytes() + (size_t)STAGE_CAP32 * sizeof(Pay32);
+    static thread_local int per1 = 0, per2 = 0;
+    if (!per1) {
+        cudaFuncSetAttribute(k_st_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
+        cudaFuncSetAttribute(k_st_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per1, k_st_classify, TILE_THREADS, s1);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_st_smooth, TILE_THREADS, s2);
+        per1 = std::max(per1, 1); per2 = std::max(per2, 1);
+    }
+    { LaunchScope ls(L, KID_ST_CLASSIFY); k_st_classify<<<per1 * L.numSMs, TILE_THREADS, s1, L.stream>>>(P, A, S, halton); }
+    { LaunchScope ls(L, KID_ST_SMOOTH); k_st_smooth<<<per2 * L.numSMs, TILE_THREADS, s2, L.stream>>>(P, A, S); }
     for (uint32_t i = 0; i < passes; i++) { LaunchScope ls(L, KID_ST_APPLY); k_st_apply<<<tiles, VFD_TPB, 0, L.stream>>>(P, A); }
 }
 

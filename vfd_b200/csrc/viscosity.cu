@@ -10,13 +10,29 @@
 //   k_visc_update  g += alpha p; r -= alpha q; z = M^-1 r   (+ |r|^2, r.z; break test, beta)
 //   k_visc_direction  p = z + beta p
 // The recurrence, the break test and the iteration accounting are the reference's.
+//
+// Positions, densities and neighbour lists are frozen during the solve, so the per-pair scalar
+//   c_ij = 10 mu (m / rho_j) / (|x_ij|^2 + 0.01 h^2) * (dW/dr)/r
+// is computed once per step by the setup pass (which needs it for the preconditioner anyway) and
+// stored next to the neighbour list (same ELL layout, 4 B/pair); the ~45 mat-vecs of a step then
+// need no square root, no division and no table lookup per pair:  (A p)_i = p_i - dt/rho_i sum_j
+// c_ij ((p_i - p_j) . x_ij) x_ij, with x_j and p_j gathered from the tile's shared-memory stage.
 #include "solver.h"
+#include "tile.cuh"
 #include <algorithm>
 
 namespace vfd {
 
-extern __shared__ __align__(16) float smemLut[];
+extern __shared__ __align__(128) unsigned char smemRaw[];
 #define FOR_EACH_TILE(p) for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += gridDim.x * blockDim.x)
+
+template<int NLUT> __device__ __forceinline__ float* smem_lut() { return reinterpret_cast<float*>(smemRaw + smem_header_bytes()); }
+template<int NLUT, class Payload> __device__ __forceinline__ Payload* smem_payload() {
+    return reinterpret_cast<Payload*>(smemRaw + smem_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float));
+}
+template<int NLUT, class Payload> static size_t tile_smem_bytes(uint32_t cap) {
+    return smem_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float) + (size_t)cap * sizeof(Payload);
+}
 
 // Core/Math/Math.h:19-33 (GetOrthogonalVectors)
 __device__ __forceinline__ void orthogonal_vectors(float3 n, float3& t1, float3& t2) {
@@ -45,28 +61,28 @@ __device__ __forceinline__ bool boundary_samples(const Params& P, float3 xi, flo
     return true;
 }
 
-// ---- V1 + V2 fused: preconditioner blocks, warm start, |b|^2 -------------------------------
-__global__ void __launch_bounds__(VFD_TPB) k_visc_setup(Params P, Arrays A, DevState* S, const float* __restrict__ lutG) {
-    __shared__ double shRed[32];
-    load_lut(smemLut, lutG);
-    __syncthreads();
-    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
-    const float4* __restrict__ pr = A.posRho;
-    const float dt = S->dt;
-    const float eps2 = 0.01f * P.h2;
-    float bb = 0.0f;
-    FOR_EACH_TILE(p) {
-        const float4 xr = pr[p];
+// ---- V1 + V2 fused: preconditioner blocks, per-pair coefficients, warm start, |b|^2 ----------
+struct ViscSetupOp {
+    typedef float4 Payload;          // (x, y, z, rho)
+    static constexpr bool READ_COUNT = true;
+    const Params& P; const Arrays& A; Lut K;
+    float dt, eps2;
+    float bb;
+    __device__ __forceinline__ float4 load(uint32_t g) const { return A.posRho[g]; }
+    template<class Acc>
+    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+        const float4 xr = A.posRho[p];
         const float3 xi = f3(xr);
-        const uint32_t m = A.cnt[p];
-        const uint32_t* col = nbr_column(A.list, p);
+        const uint16_t* col = A.list16 + ell;
+        float* ccol = A.coef + ell;
         float M[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };     // zero-initialised, column-major
         for (uint32_t k = 0; k < m; k++) {
-            const uint32_t j = col[(size_t)k * 32];
-            const float4 xj = pr[j];
+            const float4 xj = acc(col[(size_t)k * 32]);
             const float3 d = xi - f3(xj);
-            const float3 gw = K.gradW(d);
+            const float g = K.gradWScalar(d);
+            const float3 gw = g * d;
             const float s = 10.0f * P.mu * (P.mass / xj.w) / (dot3(d, d) + eps2);
+            ccol[(size_t)k * 32] = s * g;
             // glm::outerProduct(c, r): column i = c * r[i]
             M[0] += s * (d.x * gw.x); M[1] += s * (d.y * gw.x); M[2] += s * (d.z * gw.x);
             M[3] += s * (d.x * gw.y); M[4] += s * (d.y * gw.y); M[5] += s * (d.z * gw.y);
@@ -75,21 +91,27 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_setup(Params P, Arrays A, DevS
         if (P.muB != 0.0f) {
             for (uint32_t b = 0; b < P.nBodies; b++) {
                 const float4 bx = A.bx[b][p];
+                float4 cb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 if (bx.w > 0.0f) {
                     float3 pd[4];
                     if (boundary_samples(P, xi, f3(bx), pd)) {
                         const float vol = 0.25f * bx.w;
+                        float cq[4];
                         #pragma unroll
                         for (int q = 0; q < 4; q++) {
-                            const float3 gw = K.gradW(pd[q]);
+                            const float g = K.gradWScalar(pd[q]);
+                            const float3 gw = g * pd[q];
                             const float s = 10.0f * P.muB * vol / (dot3(pd[q], pd[q]) + eps2);
+                            cq[q] = s * g;
                             const float3 c = pd[0];    // the reference uses positionDirection1 in all four products (DFSPHKernels.cu:674-677)
                             M[0] += s * (c.x * gw.x); M[1] += s * (c.y * gw.x); M[2] += s * (c.z * gw.x);
                             M[3] += s * (c.x * gw.y); M[4] += s * (c.y * gw.y); M[5] += s * (c.z * gw.y);
                             M[6] += s * (c.x * gw.z); M[7] += s * (c.y * gw.z); M[8] += s * (c.z * gw.z);
                         }
+                        cb = make_float4(cq[0], cq[1], cq[2], cq[3]);
                     }
                 }
+                A.bcoef[b][p] = cb;
             }
         }
         // inverse(I - dt/rho_i * M), cofactor formula of glm::inverse(mat3) (glm/detail/func_matrix.inl:322-344)
@@ -119,10 +141,19 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_setup(Params P, Arrays A, DevS
         A.cgG[p] = make_float4(v.x + dv.x, v.y + dv.y, v.z + dv.z, 0.0f);
         bb += (v.x * v.x + v.y * v.y) + v.z * v.z;
     }
-    double v[1] = { (double)bb };
-    if (block_reduce_publish<1>(v, A.partials, &S->ticket[4], shRed)) {
+};
+
+__global__ void __launch_bounds__(TILE_THREADS) k_visc_setup(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+    TileShared& sh = smem_header(smemRaw);
+    float* sG = smem_lut<1>();
+    load_lut_tile(sG, lutG);
+    ViscSetupOp op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, 0.01f * P.h2, 0.0f };
+    tile_pass(S, A.cellBegin, A.cnt, sh, smem_payload<1, float4>(), STAGE_CAP16, op);
+    __syncthreads();
+    double v[1] = { (double)op.bb };
+    if (block_reduce_publish<1>(v, A.partials, &S->ticket[4], sh.red)) {
         double tot[1];
-        last_block_fold<1>(tot, A.partials, shRed);
+        last_block_fold<1>(tot, A.partials, sh.red);
         if (threadIdx.x == 0) {
             S->rhsNorm2 = (float)tot[0];
             S->viscIt = 0;
@@ -132,44 +163,6 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_setup(Params P, Arrays A, DevS
 }
 
 // ---- V3: matrix-free product with the viscosity operator -------------------------------------
-__device__ __forceinline__ float3 visc_operator(const Params& P, const Arrays& A, const Lut& K, const float4* __restrict__ pr,
-                                                const float4* __restrict__ x, uint32_t p, float dt) {
-    const float4 xr = pr[p];
-    const float3 xi = f3(xr);
-    const float3 vi = f3(x[p]);
-    const float eps2 = 0.01f * P.h2;
-    const uint32_t m = A.cnt[p];
-    const uint32_t* col = nbr_column(A.list, p);
-    float3 acc = f3(0.0f, 0.0f, 0.0f);
-    for (uint32_t k = 0; k < m; k++) {
-        const uint32_t j = col[(size_t)k * 32];
-        const float4 xj = pr[j];
-        const float3 d = xi - f3(xj);
-        const float3 gw = K.gradW(d);
-        const float s = 10.0f * P.mu * (P.mass / xj.w) * dot3(vi - f3(x[j]), d) / (dot3(d, d) + eps2);
-        acc += s * gw;
-    }
-    if (P.muB != 0.0f) {
-        for (uint32_t b = 0; b < P.nBodies; b++) {
-            const float4 bx = A.bx[b][p];
-            if (bx.w > 0.0f) {
-                float3 pd[4];
-                if (boundary_samples(P, xi, f3(bx), pd)) {
-                    const float vol = 0.25f * bx.w;
-                    float3 a4[4];
-                    #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const float s = 10.0f * P.muB * vol * dot3(vi, pd[q]) / (dot3(pd[q], pd[q]) + eps2);
-                        a4[q] = s * K.gradW(pd[q]);
-                    }
-                    acc += ((a4[0] + a4[1]) + a4[2]) + a4[3];
-                }
-            }
-        }
-    }
-    return vi - (dt / xr.w) * acc;
-}
-
 __device__ __forceinline__ float3 mat_vec(const float* __restrict__ minv, uint32_t n, uint32_t p, float3 r) {
     // glm mat3 * vec3: m[0]*v.x + m[1]*v.y + m[2]*v.z
     float M[9];
@@ -179,17 +172,44 @@ __device__ __forceinline__ float3 mat_vec(const float* __restrict__ minv, uint32
 }
 
 template<bool INIT>
-__global__ void __launch_bounds__(VFD_TPB) k_visc_matvec(Params P, Arrays A, DevState* S, const float* __restrict__ lutG) {
-    if (!INIT && !S->viscActive) return;
-    __shared__ double shRed[64];
-    load_lut(smemLut, lutG);
-    __syncthreads();
-    Lut K{ nullptr, smemLut, P.lutInvStep, P.lutRadius, P.lutRadius2 };
-    const float dt = S->dt;
-    const float4* __restrict__ x = INIT ? A.cgG : A.cgP;
-    float s0 = 0.0f, s1 = 0.0f;
-    FOR_EACH_TILE(p) {
-        const float3 q = visc_operator(P, A, K, A.posRho, x, p, dt);
+struct ViscMatvecOp {
+    typedef Pay32 Payload;           // (x, y, z, rho), (p.x, p.y, p.z, -)
+    static constexpr bool READ_COUNT = true;
+    const Params& P; const Arrays& A;
+    const float4* __restrict__ x;    // the vector the operator is applied to: g (INIT) or the search direction p
+    float dt;
+    float s0, s1;
+    __device__ __forceinline__ Pay32 load(uint32_t g) const { return Pay32{ A.posRho[g], x[g] }; }
+    template<class Acc>
+    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+        const float4 xr = A.posRho[p];
+        const float3 xi = f3(xr);
+        const float3 vi = f3(x[p]);
+        const uint16_t* col = A.list16 + ell;
+        const float* ccol = A.coef + ell;
+        float3 sum = f3(0.0f, 0.0f, 0.0f);
+        for (uint32_t k = 0; k < m; k++) {
+            const Pay32 nb = acc(col[(size_t)k * 32]);
+            const float c = ccol[(size_t)k * 32];
+            const float3 d = xi - f3(nb.a);
+            const float w = c * dot3(vi - f3(nb.b), d);
+            sum.x = __fmaf_rn(w, d.x, sum.x); sum.y = __fmaf_rn(w, d.y, sum.y); sum.z = __fmaf_rn(w, d.z, sum.z);
+        }
+        if (P.muB != 0.0f) {
+            for (uint32_t b = 0; b < P.nBodies; b++) {
+                const float4 bx = A.bx[b][p];
+                if (bx.w > 0.0f) {
+                    float3 pd[4];
+                    if (boundary_samples(P, xi, f3(bx), pd)) {
+                        const float4 cb = A.bcoef[b][p];
+                        const float3 a0 = (cb.x * dot3(vi, pd[0])) * pd[0], a1 = (cb.y * dot3(vi, pd[1])) * pd[1];
+                        const float3 a2 = (cb.z * dot3(vi, pd[2])) * pd[2], a3 = (cb.w * dot3(vi, pd[3])) * pd[3];
+                        sum += ((a0 + a1) + a2) + a3;
+                    }
+                }
+            }
+        }
+        const float3 q = vi - (dt / xr.w) * sum;
         if (INIT) {
             // r = b - A g ; p = M^-1 r ; |r|^2 ; r.p      (DFSPHImplementation.cu:638-691)
             const float3 r = f3(A.vel[p]) - q;
@@ -200,15 +220,23 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_matvec(Params P, Arrays A, Dev
             s1 += (r.x * z.x + r.y * z.y) + r.z * z.z;
         } else {
             A.cgQ[p] = make_float4(q.x, q.y, q.z, 0.0f);
-            const float3 pi = f3(x[p]);
-            s0 += (pi.x * q.x + pi.y * q.y) + pi.z * q.z;
+            s0 += (vi.x * q.x + vi.y * q.y) + vi.z * q.z;
         }
     }
-    double v[2] = { (double)s0, (double)s1 };
+};
+
+template<bool INIT>
+__global__ void __launch_bounds__(TILE_THREADS) k_visc_matvec(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+    if (!INIT && S->viscActive != 1u) return;
+    TileShared& sh = smem_header(smemRaw);
+    ViscMatvecOp<INIT> op{ P, A, INIT ? A.cgG : A.cgP, S->dt, 0.0f, 0.0f };
+    tile_pass(S, A.cellBegin, A.cnt, sh, smem_payload<0, Pay32>(), STAGE_CAP32, op);
+    __syncthreads();
+    double v[2] = { (double)op.s0, (double)op.s1 };
     uint32_t* ticket = &S->ticket[5];
-    if (block_reduce_publish<2>(v, A.partials, ticket, shRed)) {
+    if (block_reduce_publish<2>(v, A.partials, ticket, sh.red)) {
         double tot[2];
-        last_block_fold<2>(tot, A.partials, shRed);
+        last_block_fold<2>(tot, A.partials, sh.red);
         if (threadIdx.x == 0) {
             if (INIT) {
                 const float rhs = S->rhsNorm2;
@@ -302,35 +330,35 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_apply(Params P, Arrays A, cons
     A.dv[p] = make_float4(d.x, d.y, d.z, 0.0f);
 }
 
-static const size_t LUT_BYTES = VFD_LUT_RES * sizeof(float);
-
 template<typename Kern>
-static uint32_t persistent_grid(Kern kern, int threads, size_t smem, const LaunchCfg& L, uint32_t n) {
+static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L) {
     static thread_local const void* cachedK[16]; static thread_local int cachedV[16]; static thread_local int nc = 0;
     int perSM = 0;
     for (int i = 0; i < nc; i++) if (cachedK[i] == (const void*)kern) perSM = cachedV[i];
     if (!perSM) {
-        if (smem) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, threads, smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, TILE_THREADS, smem);
         if (perSM < 1) perSM = 1;
         if (nc < 16) { cachedK[nc] = (const void*)kern; cachedV[nc] = perSM; nc++; }
     }
-    const uint32_t tiles = (n + threads - 1) / threads;
-    return std::max(1u, std::min<uint32_t>(tiles, (uint32_t)(perSM * L.numSMs)));
+    return (uint32_t)(perSM * L.numSMs);
 }
 
 void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const uint32_t g0 = persistent_grid(k_visc_setup, VFD_TPB, LUT_BYTES, L, P.n);
-    { LaunchScope ls(L, KID_VISC_SETUP); k_visc_setup<<<g0, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
-    const uint32_t g1 = persistent_grid(k_visc_matvec<true>, VFD_TPB, LUT_BYTES, L, P.n);
-    { LaunchScope ls(L, KID_VISC_MATVEC0); k_visc_matvec<true><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
+    const size_t s0 = tile_smem_bytes<1, float4>(STAGE_CAP16), s1 = tile_smem_bytes<0, Pay32>(STAGE_CAP32);
+    const uint32_t g0 = tile_grid(k_visc_setup, s0, L);
+    { LaunchScope ls(L, KID_VISC_SETUP); k_visc_setup<<<g0, TILE_THREADS, s0, L.stream>>>(P, A, S, lutG); }
+    const uint32_t g1 = tile_grid(k_visc_matvec<true>, s1, L);
+    { LaunchScope ls(L, KID_VISC_MATVEC0); k_visc_matvec<true><<<g1, TILE_THREADS, s1, L.stream>>>(P, A, S); }
 }
-void launch_viscosity_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const uint32_t g1 = persistent_grid(k_visc_matvec<false>, VFD_TPB, LUT_BYTES, L, P.n);
-    { LaunchScope ls(L, KID_VISC_MATVEC); k_visc_matvec<false><<<g1, VFD_TPB, LUT_BYTES, L.stream>>>(P, A, S, lutG); }
-    const uint32_t g2 = persistent_grid(k_visc_update, VFD_TPB, 0, L, P.n);
+void launch_viscosity_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
+    const size_t s1 = tile_smem_bytes<0, Pay32>(STAGE_CAP32);
+    const uint32_t g1 = tile_grid(k_visc_matvec<false>, s1, L);
+    { LaunchScope ls(L, KID_VISC_MATVEC); k_visc_matvec<false><<<g1, TILE_THREADS, s1, L.stream>>>(P, A, S); }
+    const uint32_t tiles = (P.n + VFD_TPB - 1) / VFD_TPB;
+    const uint32_t g2 = std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 8u));
     { LaunchScope ls(L, KID_VISC_UPDATE); k_visc_update<<<g2, VFD_TPB, 0, L.stream>>>(P, A, S); }
-    { LaunchScope ls(L, KID_VISC_DIRECTION); k_visc_direction<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, S); }
+    { LaunchScope ls(L, KID_VISC_DIRECTION); k_visc_direction<<<tiles, VFD_TPB, 0, L.stream>>>(P, A, S); }
 }
 void launch_viscosity_apply(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     LaunchScope ls(L, KID_VISC_APPLY);
