@@ -66,11 +66,13 @@ def make(name):
                kernel=sim.kernel_bytes(), info_out=sim.info_bytes())
     # The reference's own reproducibility floor for this step: its neighbour order (atomic arrival order,
     # ParticleSearchKernels.cu:77) and reduction order change from run to run when it runs in parallel; the
-    # same step is repeated with 8 OpenMP threads and the worst deviation from the serial run is recorded
-    # per field (relative to the field's scale).  The parity tests accept max(1e-5, 2 x this).
+    # same step is repeated 16 times with 8 OpenMP threads and the worst deviation from the serial run is recorded
+    # per field (relative to the field's scale).  The parity tests accept max(1e-5, 3 x this): the statistic is
+    # a maximum over particles of a PCG-amplified rounding difference, so a single further sample (ours) sits at
+    # 1-2 x the recorded maximum about as often as the reference's own next run would.
     import parity
     noise = {f: 0.0 for f in parity.ALL_FIELDS}
-    for _ in range(8):
+    for _ in range(16):
         par = RefSim(desc, serial=False, threads=8)
         par.set_particles(pos)
         par.add_box_body(sc["box"][0], sc["box"][1], inverted=True, padding=0.0, res=sc["res"])

@@ -12,7 +12,8 @@
 //
 // The neighbour-sum kernels are tile passes (tile.cuh): persistent CTAs, the 40-kB kernel lookup table
 // staged into shared memory once per CTA, the neighbour payload of a tile's 6x6x6-cell halo box staged
-// once per tile, one thread per particle streaming 16-bit local neighbour indices.  Solver control
+// once per tile, groups of 8 lanes per particle streaming 16-bit local neighbour indices and reducing
+// the kernel-weighted sums with warp shuffles.  Solver control
 // (iteration counters, residual means, continue flags) lives in DevState: the loop-carried decision
 // of the reference's host loops is taken by the last block of the iteration kernel.
 #include "solver.h"
@@ -24,36 +25,30 @@ namespace vfd {
 extern __shared__ __align__(128) unsigned char smemRaw[];
 
 #define FOR_EACH_TILE(p) for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += gridDim.x * blockDim.x)
-
-// shared memory of a tile-pass kernel: [TileShared][NLUT lookup tables][payload]
-template<int NLUT> __device__ __forceinline__ float* smem_lut() { return reinterpret_cast<float*>(smemRaw + smem_header_bytes()); }
-template<int NLUT, class Payload> __device__ __forceinline__ Payload* smem_payload() {
-    return reinterpret_cast<Payload*>(smemRaw + smem_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float));
-}
-template<int NLUT, class Payload> static size_t tile_smem_bytes(uint32_t cap) {
-    return smem_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float) + (size_t)cap * sizeof(Payload);
-}
+#define NO_B __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
 
 // ---- K2 + K3 + K8 fused: density, DFSPH factor, a = g --------------------------------------
 struct DensityFactorOp {
-    typedef float4 Payload;
-    static constexpr bool READ_COUNT = true;
+    static constexpr bool CUSTOM = false;
+    static constexpr int NPAY = 1, NOWN = 3, NSUM = 5, COEF = 0;
     const Params& P; const Arrays& A; Lut K;
-    __device__ __forceinline__ float4 load(uint32_t g) const { return A.pos[g]; }
-    template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
-        const float3 xi = f3(A.pos[p]);
-        const uint16_t* col = A.list16 + ell;
-        float rho = P.volume * P.wZero;
-        float3 gradI = f3(0.0f, 0.0f, 0.0f);
-        float sumK = 0.0f;
-        for (uint32_t k = 0; k < m; k++) {
-            const float3 xij = xi - f3(acc(col[(size_t)k * 32]));
-            rho += P.volume * K.w(xij);
-            const float3 gj = -P.volume * K.gradW(xij);
-            sumK += dot3(gj, gj);
-            gradI -= gj;
-        }
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.pos[g]; }
+    NO_B
+    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
+        const float4 x = A.pos[p]; own[0] = x.x; own[1] = x.y; own[2] = x.z;
+    }
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4, float&, float (&acc)[NSUM]) const {
+        const float3 xij = f3(o[0], o[1], o[2]) - f3(a);
+        acc[0] += P.volume * K.w(xij);
+        const float3 gj = -P.volume * K.gradW(xij);
+        acc[1] += dot3(gj, gj);
+        acc[2] -= gj.x; acc[3] -= gj.y; acc[4] -= gj.z;
+    }
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
+        const float3 xi = f3(o[0], o[1], o[2]);
+        float rho = P.volume * P.wZero + sum[0];
+        float sumK = sum[1];
+        float3 gradI = f3(sum[2], sum[3], sum[4]);
         for (uint32_t b = 0; b < P.nBodies; b++) {
             const float4 bx = A.bx[b][p];
             if (bx.w > 0.0f) {
@@ -72,35 +67,36 @@ struct DensityFactorOp {
     }
 };
 
-__global__ void __launch_bounds__(TILE_THREADS) k_density_factor(const __grid_constant__ Params P, const __grid_constant__ Arrays A, const DevState* S, const float* __restrict__ lutW, const float* __restrict__ lutG) {
-    float* sW = smem_lut<2>();
+__global__ void __launch_bounds__(TT_LUT) k_density_factor(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S,
+                                                                 const float* __restrict__ lutW, const float* __restrict__ lutG) {
+    float* sW = smem_lut<2>(smemRaw);
     float* sG = sW + VFD_LUT_RES;
     load_lut_tile(sW, lutW);
     load_lut_tile(sG, lutG);
     DensityFactorOp op{ P, A, Lut{ sW, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 } };
-    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), smem_payload<2, float4>(), STAGE_CAP16, op);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<2>(smemRaw), nullptr, STAGE_CAP, op);
 }
 
 // ---- K4 / K10: solver source terms ----------------------------------------------------------
 // rate = V * sum_j (v_i - v_j) . gradW_ij + sum_b V_b v_i . gradW_ib
 template<bool DIV>
 struct SourceOp {
-    typedef Pay32 Payload;
-    static constexpr bool READ_COUNT = true;
+    static constexpr bool CUSTOM = false;
+    static constexpr int NPAY = 2, NOWN = 6, NSUM = 1, COEF = 0;
     const Params& P; const Arrays& A; Lut K;
     float dt, dtInv, dt2Inv;
-    __device__ __forceinline__ Pay32 load(uint32_t g) const { return Pay32{ A.posRho[g], A.vel[g] }; }
-    template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
-        const float3 xi = f3(A.posRho[p]);
-        const float3 vi = f3(A.vel[p]);
-        const uint16_t* col = A.list16 + ell;
-        float s = 0.0f;
-        for (uint32_t k = 0; k < m; k++) {
-            const Pay32 nb = acc(col[(size_t)k * 32]);
-            s += dot3(vi - f3(nb.b), K.gradW(xi - f3(nb.a)));
-        }
-        s *= P.volume;
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
+    __device__ __forceinline__ float4 loadB(uint32_t g) const { return A.vel[g]; }
+    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
+        const float4 x = A.posRho[p], v = A.vel[p];
+        own[0] = x.x; own[1] = x.y; own[2] = x.z; own[3] = v.x; own[4] = v.y; own[5] = v.z;
+    }
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float&, float (&acc)[NSUM]) const {
+        acc[0] += dot3(f3(o[3], o[4], o[5]) - f3(b), K.gradW(f3(o[0], o[1], o[2]) - f3(a)));
+    }
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t m, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
+        const float3 xi = f3(o[0], o[1], o[2]), vi = f3(o[3], o[4], o[5]);
+        float s = sum[0] * P.volume;
         for (uint32_t b = 0; b < P.nBodies; b++) {
             const float4 bx = A.bx[b][p];
             if (bx.w > 0.0f) s += bx.w * dot3(vi, K.gradW(xi - f3(bx)));
@@ -123,8 +119,8 @@ struct SourceOp {
 };
 
 template<bool DIV>
-__global__ void __launch_bounds__(TILE_THREADS) k_source(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
-    float* sG = smem_lut<1>();
+__global__ void __launch_bounds__(TT_LUT) k_source(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+    float* sG = smem_lut<1>(smemRaw);
     load_lut_tile(sG, lutG);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // loop entry of ComputeDivergence / ComputePressure (DFSPHImplementation.cu:526-532, 455-461): error 0, so the
@@ -133,7 +129,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_source(const __grid_constant__
         else     { S->pressIt = 0; S->pressErr = 0.0f; S->pressActive = (0u < P.minPressIt && 0u < P.maxPressIt) ? 1u : 0u; }
     }
     SourceOp<DIV> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, S->dtInv, S->dt2Inv };
-    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), smem_payload<1, Pay32>(), STAGE_CAP32, op);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP), STAGE_CAP, op);
 }
 
 // ---- K5 / K7 / K11 / K13: pressure acceleration from kappa ---------------------------------
@@ -141,26 +137,27 @@ enum { ACC_DIV_ITER = 0, ACC_DIV_FINISH = 1, ACC_PRESS_ITER = 2, ACC_PRESS_FINIS
 
 template<int MODE>
 struct AccelOp {
-    typedef float4 Payload;          // (x, y, z, kappa)
-    static constexpr bool READ_COUNT = true;
+    static constexpr bool CUSTOM = false;
+    static constexpr int NPAY = 1, NOWN = 4, NSUM = 3, COEF = 0;       // payload (x, y, z, kappa)
     const Params& P; const Arrays& A; Lut K;
     const float* __restrict__ kap;
     float dt;
-    __device__ __forceinline__ float4 load(uint32_t g) const { float4 x = A.posRho[g]; x.w = kap[g]; return x; }
-    template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
-        const float3 xi = f3(A.posRho[p]);
-        const float ki = kap[p];
-        const uint16_t* col = A.list16 + ell;
-        float3 a = f3(0.0f, 0.0f, 0.0f);
-        for (uint32_t k = 0; k < m; k++) {
-            const float4 nb = acc(col[(size_t)k * 32]);
-            const float ks = ki + nb.w;
-            if (fabsf(ks) > VFD_EPS_F) {
-                const float3 gj = -P.volume * K.gradW(xi - f3(nb));
-                a += ks * gj;
-            }
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { float4 x = A.posRho[g]; x.w = kap[g]; return x; }
+    NO_B
+    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
+        const float4 x = A.posRho[p]; own[0] = x.x; own[1] = x.y; own[2] = x.z; own[3] = kap[p];
+    }
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4, float&, float (&acc)[NSUM]) const {
+        const float ks = o[3] + a.w;
+        if (fabsf(ks) > VFD_EPS_F) {
+            const float3 gj = -P.volume * K.gradW(f3(o[0], o[1], o[2]) - f3(a));
+            acc[0] += ks * gj.x; acc[1] += ks * gj.y; acc[2] += ks * gj.z;
         }
+    }
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
+        const float3 xi = f3(o[0], o[1], o[2]);
+        const float ki = o[3];
+        float3 a = f3(sum[0], sum[1], sum[2]);
         if (fabsf(ki) > VFD_EPS_F) {
             for (uint32_t b = 0; b < P.nBodies; b++) {
                 const float4 bx = A.bx[b][p];
@@ -181,36 +178,36 @@ struct AccelOp {
 };
 
 template<int MODE>
-__global__ void __launch_bounds__(TILE_THREADS) k_pressure_accel(const __grid_constant__ Params P, const __grid_constant__ Arrays A, const DevState* __restrict__ S, const float* __restrict__ lutG) {
+__global__ void __launch_bounds__(TT_LUT) k_pressure_accel(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
     if (MODE == ACC_DIV_ITER && !S->divActive) return;
     if (MODE == ACC_PRESS_ITER && !S->pressActive) return;
-    float* sG = smem_lut<1>();
+    float* sG = smem_lut<1>(smemRaw);
     load_lut_tile(sG, lutG);
     AccelOp<MODE> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 },
                       (MODE == ACC_DIV_ITER || MODE == ACC_DIV_FINISH) ? A.kappaV : A.kappa, S->dt };
-    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), smem_payload<1, float4>(), STAGE_CAP16, op);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<1>(smemRaw), nullptr, STAGE_CAP, op);
 }
 
 // ---- K6 / K12 (+ R1 / R3): one Jacobi update and the fused residual reduction ----------------
 template<bool DIV>
 struct SolveOp {
-    typedef Pay32 Payload;           // position, pressure acceleration
-    static constexpr bool READ_COUNT = true;
+    static constexpr bool CUSTOM = false;
+    static constexpr int NPAY = 2, NOWN = 6, NSUM = 1, COEF = 0;       // payload: position, pressure acceleration
     const Params& P; const Arrays& A; Lut K;
     float scale;
     float errSum;
-    __device__ __forceinline__ Pay32 load(uint32_t g) const { return Pay32{ A.posRho[g], A.pacc[g] }; }
-    template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
-        const float3 xi = f3(A.posRho[p]);
-        const float3 ai = f3(A.pacc[p]);
-        const uint16_t* col = A.list16 + ell;
-        float s = 0.0f;
-        for (uint32_t k = 0; k < m; k++) {
-            const Pay32 nb = acc(col[(size_t)k * 32]);
-            s += dot3(ai - f3(nb.b), K.gradW(xi - f3(nb.a)));
-        }
-        s *= P.volume;
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
+    __device__ __forceinline__ float4 loadB(uint32_t g) const { return A.pacc[g]; }
+    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
+        const float4 x = A.posRho[p], a = A.pacc[p];
+        own[0] = x.x; own[1] = x.y; own[2] = x.z; own[3] = a.x; own[4] = a.y; own[5] = a.z;
+    }
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float&, float (&acc)[NSUM]) const {
+        acc[0] += dot3(f3(o[3], o[4], o[5]) - f3(b), K.gradW(f3(o[0], o[1], o[2]) - f3(a)));
+    }
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t m, const float (&o)[NOWN], const float (&sum)[NSUM]) {
+        const float3 xi = f3(o[0], o[1], o[2]), ai = f3(o[3], o[4], o[5]);
+        float s = sum[0] * P.volume;
         for (uint32_t b = 0; b < P.nBodies; b++) {
             const float4 bx = A.bx[b][p];
             if (bx.w > 0.0f) s += bx.w * dot3(ai, K.gradW(xi - f3(bx)));
@@ -230,13 +227,13 @@ struct SolveOp {
 };
 
 template<bool DIV>
-__global__ void __launch_bounds__(TILE_THREADS) k_solve_iteration(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+__global__ void __launch_bounds__(TT_LUT) k_solve_iteration(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
     if (DIV ? !S->divActive : !S->pressActive) return;
     TileShared& sh = smem_header(smemRaw);
-    float* sG = smem_lut<1>();
+    float* sG = smem_lut<1>(smemRaw);
     load_lut_tile(sG, lutG);
     SolveOp<DIV> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, DIV ? S->dt : S->dt2, 0.0f };
-    tile_pass(S, A.cellBegin, A.cnt, sh, smem_payload<1, Pay32>(), STAGE_CAP32, op);
+    tile_pass(S, A, sh, smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP), STAGE_CAP, op);
     __syncthreads();
     double v[1] = { (double)op.errSum };
     uint32_t* ticket = &S->ticket[DIV ? 1 : 2];
@@ -294,7 +291,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_cfl(Params P, Arrays A, DevState* S
 }
 
 // K9: v += dt * a
-__global__ void __launch_bounds__(VFD_TPB) k_velocity(Params P, Arrays A, const DevState* __restrict__ S) {
+__global__ void __launch_bounds__(VFD_TPB) k_velocity(Params P, Arrays A, DevState* S) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n) return;
     const float dt = S->dt;
@@ -305,7 +302,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_velocity(Params P, Arrays A, const 
 }
 
 // K14: x += dt * v
-__global__ void __launch_bounds__(VFD_TPB) k_position(Params P, Arrays A, const DevState* __restrict__ S) {
+__global__ void __launch_bounds__(VFD_TPB) k_position(Params P, Arrays A, DevState* S) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n) return;
     const float dt = S->dt;
@@ -323,62 +320,62 @@ __global__ void k_clear_acc(Params P, Arrays A) {
 // ---- launchers -------------------------------------------------------------------------------
 // persistent grid: resident CTAs per SM (from the occupancy calculator) x SMs
 template<typename Kern>
-static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L) {
+static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L, int threads) {
     static thread_local const void* cachedK[32]; static thread_local int cachedV[32]; static thread_local int nc = 0;
     int perSM = 0;
     for (int i = 0; i < nc; i++) if (cachedK[i] == (const void*)kern) perSM = cachedV[i];
     if (!perSM) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, TILE_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, threads, smem);
         if (perSM < 1) perSM = 1;
         if (nc < 32) { cachedK[nc] = (const void*)kern; cachedV[nc] = perSM; nc++; }
     }
     return (uint32_t)(perSM * L.numSMs);
 }
 
-void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState* S, const float* lutW, const float* lutG) {
-    const size_t smem = tile_smem_bytes<2, float4>(STAGE_CAP16);
-    const uint32_t g = tile_grid(k_density_factor, smem, L);
+void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutW, const float* lutG) {
+    const size_t smem = tile_smem_bytes<2, 1>(STAGE_CAP);
+    const uint32_t g = tile_grid(k_density_factor, smem, L, TT_LUT);
     LaunchScope ls(L, KID_DENSITY_FACTOR);
-    k_density_factor<<<g, TILE_THREADS, smem, L.stream>>>(P, A, S, lutW, lutG);
+    k_density_factor<<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutW, lutG);
 }
 void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t smem = tile_smem_bytes<1, Pay32>(STAGE_CAP32);
-    const uint32_t g = tile_grid(k_source<true>, smem, L);
+    const size_t smem = tile_smem_bytes<1, 2>(STAGE_CAP);
+    const uint32_t g = tile_grid(k_source<true>, smem, L, TT_LUT);
     LaunchScope ls(L, KID_DIV_SOURCE);
-    k_source<true><<<g, TILE_THREADS, smem, L.stream>>>(P, A, S, lutG);
+    k_source<true><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
 }
 void launch_divergence_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s1 = tile_smem_bytes<1, float4>(STAGE_CAP16), s2 = tile_smem_bytes<1, Pay32>(STAGE_CAP32);
-    const uint32_t g1 = tile_grid(k_pressure_accel<ACC_DIV_ITER>, s1, L);
-    { LaunchScope ls(L, KID_DIV_ACCEL); k_pressure_accel<ACC_DIV_ITER><<<g1, TILE_THREADS, s1, L.stream>>>(P, A, S, lutG); }
-    const uint32_t g2 = tile_grid(k_solve_iteration<true>, s2, L);
-    { LaunchScope ls(L, KID_DIV_SOLVE); k_solve_iteration<true><<<g2, TILE_THREADS, s2, L.stream>>>(P, A, S, lutG); }
+    const size_t s1 = tile_smem_bytes<1, 1>(STAGE_CAP), s2 = tile_smem_bytes<1, 2>(STAGE_CAP);
+    const uint32_t g1 = tile_grid(k_pressure_accel<ACC_DIV_ITER>, s1, L, TT_LUT);
+    { LaunchScope ls(L, KID_DIV_ACCEL); k_pressure_accel<ACC_DIV_ITER><<<g1, TT_LUT, s1, L.stream>>>(P, A, S, lutG); }
+    const uint32_t g2 = tile_grid(k_solve_iteration<true>, s2, L, TT_LUT);
+    { LaunchScope ls(L, KID_DIV_SOLVE); k_solve_iteration<true><<<g2, TT_LUT, s2, L.stream>>>(P, A, S, lutG); }
 }
 void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t smem = tile_smem_bytes<1, float4>(STAGE_CAP16);
-    const uint32_t g = tile_grid(k_pressure_accel<ACC_DIV_FINISH>, smem, L);
+    const size_t smem = tile_smem_bytes<1, 1>(STAGE_CAP);
+    const uint32_t g = tile_grid(k_pressure_accel<ACC_DIV_FINISH>, smem, L, TT_LUT);
     LaunchScope ls(L, KID_DIV_FINISH);
-    k_pressure_accel<ACC_DIV_FINISH><<<g, TILE_THREADS, smem, L.stream>>>(P, A, S, lutG);
+    k_pressure_accel<ACC_DIV_FINISH><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
 }
 void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t smem = tile_smem_bytes<1, Pay32>(STAGE_CAP32);
-    const uint32_t g = tile_grid(k_source<false>, smem, L);
+    const size_t smem = tile_smem_bytes<1, 2>(STAGE_CAP);
+    const uint32_t g = tile_grid(k_source<false>, smem, L, TT_LUT);
     LaunchScope ls(L, KID_PRESS_SOURCE);
-    k_source<false><<<g, TILE_THREADS, smem, L.stream>>>(P, A, S, lutG);
+    k_source<false><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
 }
 void launch_pressure_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s1 = tile_smem_bytes<1, float4>(STAGE_CAP16), s2 = tile_smem_bytes<1, Pay32>(STAGE_CAP32);
-    const uint32_t g1 = tile_grid(k_pressure_accel<ACC_PRESS_ITER>, s1, L);
-    { LaunchScope ls(L, KID_PRESS_ACCEL); k_pressure_accel<ACC_PRESS_ITER><<<g1, TILE_THREADS, s1, L.stream>>>(P, A, S, lutG); }
-    const uint32_t g2 = tile_grid(k_solve_iteration<false>, s2, L);
-    { LaunchScope ls(L, KID_PRESS_SOLVE); k_solve_iteration<false><<<g2, TILE_THREADS, s2, L.stream>>>(P, A, S, lutG); }
+    const size_t s1 = tile_smem_bytes<1, 1>(STAGE_CAP), s2 = tile_smem_bytes<1, 2>(STAGE_CAP);
+    const uint32_t g1 = tile_grid(k_pressure_accel<ACC_PRESS_ITER>, s1, L, TT_LUT);
+    { LaunchScope ls(L, KID_PRESS_ACCEL); k_pressure_accel<ACC_PRESS_ITER><<<g1, TT_LUT, s1, L.stream>>>(P, A, S, lutG); }
+    const uint32_t g2 = tile_grid(k_solve_iteration<false>, s2, L, TT_LUT);
+    { LaunchScope ls(L, KID_PRESS_SOLVE); k_solve_iteration<false><<<g2, TT_LUT, s2, L.stream>>>(P, A, S, lutG); }
 }
 void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t smem = tile_smem_bytes<1, float4>(STAGE_CAP16);
-    const uint32_t g = tile_grid(k_pressure_accel<ACC_PRESS_FINISH>, smem, L);
+    const size_t smem = tile_smem_bytes<1, 1>(STAGE_CAP);
+    const uint32_t g = tile_grid(k_pressure_accel<ACC_PRESS_FINISH>, smem, L, TT_LUT);
     LaunchScope ls(L, KID_PRESS_FINISH);
-    k_pressure_accel<ACC_PRESS_FINISH><<<g, TILE_THREADS, smem, L.stream>>>(P, A, S, lutG);
+    k_pressure_accel<ACC_PRESS_FINISH><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
 }
 void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A) {
     LaunchScope ls(L, KID_CLEAR_ACC);

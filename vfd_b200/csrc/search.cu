@@ -211,17 +211,18 @@ __global__ void __launch_bounds__(VFD_TPB) k_reorder(Params P, Arrays A) {
 // positions staged in shared memory; writes 16-bit tile-local indices.
 template<bool FMA>
 struct SearchOp {
-    typedef float4 Payload;
-    static constexpr bool READ_COUNT = false;
+    static constexpr bool CUSTOM = true;
+    static constexpr int NPAY = 1;
     const float4* __restrict__ pos;
     const DevState* __restrict__ S;
     const TileShared* sh;
     uint32_t* __restrict__ cnt;
     uint16_t* __restrict__ list;
     float h2, invCell;
-    __device__ __forceinline__ float4 load(uint32_t g) const { return pos[g]; }
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { return pos[g]; }
+    __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
     template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, uint32_t, size_t ell, const Acc& acc) {
+    __device__ __forceinline__ void particle(uint32_t p, size_t ell, const Acc& acc) {
         const float4 xi = pos[p];
         const uint3 c = cell_of(xi, S, invCell);
         const uint32_t hx = (c.x & 3u) + 1u, hy = (c.y & 3u) + 1u, hz = (c.z & 3u) + 1u;   // box coordinates of the own cell
@@ -248,16 +249,12 @@ struct SearchOp {
     }
 };
 
-#define SEARCH_CAP 4096   // staged positions per tile (16 B each); halo boxes above it take the exact fallback path
-
 template<bool FMA>
-__global__ void __launch_bounds__(TILE_THREADS) k_build_list(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+__global__ void __launch_bounds__(TT_PLAIN) k_build_list(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     TileShared& sh = smem_header(smemRaw);
-    float4* sPay = reinterpret_cast<float4*>(smemRaw + smem_header_bytes());
     SearchOp<FMA> op{ A.pos, S, &sh, A.cnt, A.list16, P.h2, cell_inv(P.h) };
-    // local indices are 16-bit: a halo box beyond 65535 particles cannot be encoded (flagged, caught by the host)
-    tile_pass(S, A.cellBegin, A.cnt, sh, sPay, SEARCH_CAP, op, &S->errorFlags);
+    tile_pass(S, A, sh, smem_pay_a<0>(smemRaw), nullptr, STAGE_CAP, op, true);
 }
 
 static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -278,7 +275,7 @@ void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, 
     std::swap(A.curv, A.curv2); std::swap(A.curvS, A.curvS2); std::swap(A.curvD, A.curvD2); std::swap(A.id, A.id2);
     {
         LaunchScope ls(L, KID_BUILD_LIST);
-        const size_t smem = smem_header_bytes() + (size_t)SEARCH_CAP * sizeof(float4);
+        const size_t smem = tile_smem_bytes<0, 1>(STAGE_CAP);
         static bool attr = false;
         if (!attr) {
             cudaFuncSetAttribute(k_build_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -286,8 +283,8 @@ void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, 
             attr = true;
         }
         const uint32_t grid = (uint32_t)L.numSMs * 3u;
-        if (P.searchFma) k_build_list<true><<<grid, TILE_THREADS, smem, L.stream>>>(P, A, S);
-        else             k_build_list<false><<<grid, TILE_THREADS, smem, L.stream>>>(P, A, S);
+        if (P.searchFma) k_build_list<true><<<grid, TT_PLAIN, smem, L.stream>>>(P, A, S);
+        else             k_build_list<false><<<grid, TT_PLAIN, smem, L.stream>>>(P, A, S);
     }
 }
 

@@ -85,26 +85,23 @@ __global__ void k_export_frame(Params P, Arrays A, VfdParticleSimple* __restrict
     out[A.id[p]] = q;
 }
 
-// neighbour lists hold tile-local indices: translate through the tile's staged persistent ids
-struct ExportNeighborsOp {
-    typedef uint32_t Payload;
-    static constexpr bool READ_COUNT = true;
-    const Arrays& A;
-    uint32_t* __restrict__ counts;
-    uint32_t* __restrict__ idsPadded;
-    __device__ __forceinline__ uint32_t load(uint32_t g) const { return A.id[g]; }
-    template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
-        const uint32_t o = A.id[p];
-        counts[o] = m;
-        const uint16_t* col = A.list16 + ell;
-        for (uint32_t k = 0; k < m; k++) idsPadded[(size_t)o * VFD_MAX_NEIGHBORS + k] = acc(col[(size_t)k * 32]);
+// neighbour lists hold tile-local indices: translate them back per tile (thread per particle; test/inspection only)
+__global__ void __launch_bounds__(512) k_export_neighbors(const __grid_constant__ Arrays A, const DevState* S, uint32_t* __restrict__ counts, uint32_t* __restrict__ idsPadded) {
+    __shared__ TileShared sh;
+    const uint32_t nTiles = S->nTiles;
+    for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const uint32_t b0 = A.cellBegin[tile * TILE_CELLS], e0 = A.cellBegin[tile * TILE_CELLS + TILE_CELLS];
+        if (b0 == e0) continue;
+        __syncthreads();
+        const TileInfo t = tile_setup(S, A.cellBegin, tile, sh, 0u);
+        (void)t.staged;
+        for (uint32_t p = t.begin + threadIdx.x; p < t.end; p += blockDim.x) {
+            const uint32_t o = A.id[p], m = A.cnt[p];
+            counts[o] = m;
+            const uint16_t* col = A.list16 + ell_base(p);
+            for (uint32_t k = 0; k < m; k++) idsPadded[(size_t)o * VFD_MAX_NEIGHBORS + k] = A.id[tile_local_to_global(sh, col[(size_t)k * 32])];
+        }
     }
-};
-__global__ void __launch_bounds__(TILE_THREADS) k_export_neighbors(const __grid_constant__ Arrays A, const DevState* S, uint32_t* __restrict__ counts, uint32_t* __restrict__ idsPadded) {
-    extern __shared__ __align__(128) unsigned char smemRaw[];
-    ExportNeighborsOp op{ A, counts, idsPadded };
-    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), reinterpret_cast<uint32_t*>(smemRaw + smem_header_bytes()), 8192u, op);
 }
 
 __global__ void k_export_boundary(Params P, Arrays A, uint32_t body, float* __restrict__ xj, float* __restrict__ vol) {
@@ -705,11 +702,7 @@ int Solver::get_neighbors(uint32_t* counts, uint32_t* offsets, uint32_t* ids, ui
     CK(cudaMalloc(&dC, (size_t)n * 4));
     CK(cudaMalloc(&dI, (size_t)n * VFD_MAX_NEIGHBORS * 4));
     refresh_params();
-    {
-        const size_t smem = smem_header_bytes() + 8192u * sizeof(uint32_t);
-        cudaFuncSetAttribute(k_export_neighbors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_export_neighbors<<<numSMs * 2, TILE_THREADS, smem, stream>>>(arrays, dState, dC, dI);
-    }
+    k_export_neighbors<<<numSMs * 2, 512, 0, stream>>>(arrays, dState, dC, dI);
     launches += 1;
     std::vector<uint32_t> c(n), padded((size_t)n * VFD_MAX_NEIGHBORS);
     cudaError_t e = cudaMemcpyAsync(c.data(), dC, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);

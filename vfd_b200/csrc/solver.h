@@ -100,7 +100,7 @@ struct LaunchScope {
 // ---- kernel launchers (one per reference kernel group; defined in the .cu files) ----
 void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, uint32_t cellCapacity, uint32_t cellEstimate);
 void launch_boundary(const LaunchCfg& L, const Params& P, const Arrays& A, const BodySet& B);
-void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState* S, const float* lutW, const float* lutG);
+void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutW, const float* lutG);
 void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
 void launch_divergence_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
 void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
@@ -110,7 +110,7 @@ void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A
 void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A);
 void launch_cfl_and_velocity(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
 void launch_positions(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
-void launch_surface_tension(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState* S, const float* halton, uint32_t passes);
+void launch_surface_tension(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* halton, uint32_t passes);
 void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
 void launch_viscosity_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
 void launch_viscosity_apply(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);

@@ -23,15 +23,17 @@ __device__ __forceinline__ float3 normalize_if_nonzero(float3 v) {   // DFSPHKer
 // T1: classify surface particles by the centre of mass of their neighbourhood; for those, estimate
 // the normal and curvature from the Halton samples on the support sphere not covered by a neighbour.
 struct StClassifyOp {
-    typedef float4 Payload;
-    static constexpr bool READ_COUNT = true;
+    static constexpr bool CUSTOM = true;
+    static constexpr int NPAY = 1;
     const Params& P; const Arrays& A;
     const float* __restrict__ halton;
     uint32_t sampleCount;
     float mcFactor, cover2;
-    __device__ __forceinline__ float4 load(uint32_t g) const { return A.posRho[g]; }
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
+    __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
     template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+    __device__ __forceinline__ void particle(uint32_t p, size_t ell, const Acc& acc) {
+        const uint32_t m = A.cnt[p];
         const float3 xi = f3(A.posRho[p]);
         const uint16_t* col = A.list16 + ell;
         float3 n = f3(0.0f, 0.0f, 0.0f);
@@ -74,51 +76,49 @@ struct StClassifyOp {
     }
 };
 
-__global__ void __launch_bounds__(TILE_THREADS) k_st_classify(const __grid_constant__ Params P, const __grid_constant__ Arrays A, const DevState* __restrict__ S, const float* __restrict__ halton) {
+__global__ void __launch_bounds__(TT_PLAIN) k_st_classify(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ halton) {
     const float radiusRatio = P.nbrRadius / P.r;
     StClassifyOp op{ P, A, halton, S->sampleCount, S->mcFactor, radiusRatio * radiusRatio * P.h2 };
-    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), reinterpret_cast<float4*>(smemRaw + smem_header_bytes()), STAGE_CAP16, op);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<0>(smemRaw), nullptr, STAGE_CAP, op);
 }
 
 // T2: neighbour-weighted smoothing of normal and curvature among surface particles
 struct StSmoothOp {
-    typedef Pay32 Payload;           // position, (normal, curvature)
-    static constexpr bool READ_COUNT = true;
+    static constexpr bool CUSTOM = false;
+    static constexpr int NPAY = 2, NOWN = 4, NSUM = 5, COEF = 0;       // payload: position, (normal, curvature)
     const Params& P; const Arrays& A;
-    __device__ __forceinline__ Pay32 load(uint32_t g) const { return Pay32{ A.posRho[g], A.nrm[g] }; }
-    template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
+    __device__ __forceinline__ float4 loadB(uint32_t g) const { return A.nrm[g]; }
+    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
+        const float4 x = A.posRho[p], n = A.nrm[p];
+        own[0] = x.x; own[1] = x.y; own[2] = x.z;
+        own[3] = (n.x != 0.0f || n.y != 0.0f || n.z != 0.0f) ? 1.0f : 0.0f;
+    }
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 nj, float&, float (&acc)[NSUM]) const {
+        if (o[3] != 0.0f && (nj.x != 0.0f || nj.y != 0.0f || nj.z != 0.0f)) {
+            const float3 d = f3(a) - f3(o[0], o[1], o[2]);
+            const float dist = sqrtf(dot3(d, d));
+            const float w = 1.0f - dist / P.h;
+            acc[0] += nj.x * w; acc[1] += nj.y * w; acc[2] += nj.z * w;
+            acc[3] += nj.w * w;
+            acc[4] += w;
+        }
+    }
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
+        if (o[3] == 0.0f) return;
         const float tau = P.smoothing;
         const float4 ni4 = A.nrm[p];
-        if (ni4.x != 0.0f || ni4.y != 0.0f || ni4.z != 0.0f) {
-            const float3 xi = f3(A.posRho[p]);
-            const uint16_t* col = A.list16 + ell;
-            float3 nc = f3(0.0f, 0.0f, 0.0f);
-            float cc = 0.0f, wsum = 0.0f;
-            for (uint32_t k = 0; k < m; k++) {
-                const Pay32 nb = acc(col[(size_t)k * 32]);
-                const float4 nj = nb.b;
-                if (nj.x != 0.0f || nj.y != 0.0f || nj.z != 0.0f) {
-                    const float3 d = f3(nb.a) - xi;
-                    const float dist = sqrtf(dot3(d, d));
-                    const float w = 1.0f - dist / P.h;
-                    nc += f3(nj) * w;
-                    cc += nj.w * w;
-                    wsum += w;
-                }
-            }
-            nc = normalize_if_nonzero(nc);
-            float3 ns = (1.0f - tau) * f3(ni4) + tau * nc;
-            ns = normalize_if_nonzero(ns);
-            A.nbar[p] = make_float4(ns.x, ns.y, ns.z, 0.0f);
-            A.curvS[p] = ((1.0f - tau) * ni4.w + tau * cc) / (1.0f - tau + tau * wsum);
-        }
+        const float3 nc = normalize_if_nonzero(f3(sum[0], sum[1], sum[2]));
+        float3 ns = (1.0f - tau) * f3(ni4) + tau * nc;
+        ns = normalize_if_nonzero(ns);
+        A.nbar[p] = make_float4(ns.x, ns.y, ns.z, 0.0f);
+        A.curvS[p] = ((1.0f - tau) * ni4.w + tau * sum[3]) / (1.0f - tau + tau * sum[4]);
     }
 };
 
-__global__ void __launch_bounds__(TILE_THREADS) k_st_smooth(const __grid_constant__ Params P, const __grid_constant__ Arrays A, const DevState* __restrict__ S) {
+__global__ void __launch_bounds__(TT_PLAIN) k_st_smooth(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     StSmoothOp op{ P, A };
-    tile_pass(S, A.cellBegin, A.cnt, smem_header(smemRaw), reinterpret_cast<Pay32*>(smemRaw + smem_header_bytes()), STAGE_CAP32, op);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<0>(smemRaw), smem_pay_b<0>(smemRaw, STAGE_CAP), STAGE_CAP, op);
 }
 
 // T3: apply the force (once per smoothing pass: SURVEY.md Q18)
@@ -142,19 +142,19 @@ __global__ void __launch_bounds__(VFD_TPB) k_st_apply(Params P, Arrays A) {
     }
 }
 
-void launch_surface_tension(const LaunchCfg& L, const Params& P, const Arrays& A, const DevState* S, const float* halton, uint32_t passes) {
+void launch_surface_tension(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* halton, uint32_t passes) {
     const uint32_t tiles = (P.n + VFD_TPB - 1) / VFD_TPB;
-    const size_t s1 = smem_header_bytes() + (size_t)STAGE_CAP16 * sizeof(float4), s2 = smem_header_bytes() + (size_t)STAGE_CAP32 * sizeof(Pay32);
+    const size_t s1 = tile_smem_bytes<0, 1>(STAGE_CAP), s2 = tile_smem_bytes<0, 2>(STAGE_CAP);
     static thread_local int per1 = 0, per2 = 0;
     if (!per1) {
         cudaFuncSetAttribute(k_st_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
         cudaFuncSetAttribute(k_st_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per1, k_st_classify, TILE_THREADS, s1);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_st_smooth, TILE_THREADS, s2);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per1, k_st_classify, TT_PLAIN, s1);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_st_smooth, TT_PLAIN, s2);
         per1 = std::max(per1, 1); per2 = std::max(per2, 1);
     }
-    { LaunchScope ls(L, KID_ST_CLASSIFY); k_st_classify<<<per1 * L.numSMs, TILE_THREADS, s1, L.stream>>>(P, A, S, halton); }
-    { LaunchScope ls(L, KID_ST_SMOOTH); k_st_smooth<<<per2 * L.numSMs, TILE_THREADS, s2, L.stream>>>(P, A, S); }
+    { LaunchScope ls(L, KID_ST_CLASSIFY); k_st_classify<<<per1 * L.numSMs, TT_PLAIN, s1, L.stream>>>(P, A, S, halton); }
+    { LaunchScope ls(L, KID_ST_SMOOTH); k_st_smooth<<<per2 * L.numSMs, TT_PLAIN, s2, L.stream>>>(P, A, S); }
     for (uint32_t i = 0; i < passes; i++) { LaunchScope ls(L, KID_ST_APPLY); k_st_apply<<<tiles, VFD_TPB, 0, L.stream>>>(P, A); }
 }
 

@@ -13,8 +13,8 @@
 //      acceleration / PCG direction ...) is staged ONCE for all halo particles from HBM/L2 into
 //      shared memory with coalesced loads;
 //   3. each thread owns one particle of the tile and streams its neighbour list — 16-bit tile-local
-//      indices in a warp-blocked ELL layout, so a warp reads one 64-B line per neighbour slot —
-//      gathering payloads from shared memory instead of through L1/L2.
+//      indices in a warp-blocked ELL layout, so a warp reads one 64-B line per neighbour slot, four slots
+//      ahead of their use — gathering payloads from shared memory instead of through L1/L2.
 // Per pass and particle HBM sees: own fields once + 2 B per neighbour; neighbour fields never.
 //
 // If a halo box holds more particles than the staging buffer (pathological clumping), the pass
@@ -25,14 +25,14 @@
 
 namespace vfd {
 
-#define TILE_THREADS 512
-#define TILE_WARPS (TILE_THREADS / 32)
+#define TILE_THREADS_MAX 1024   // CTA sizes are chosen per kernel (shared-memory and register budget differ); the drivers use blockDim
+#define TILE_WARPS (blockDim.x >> 5)
 #define HALO_CELLS 216
 #define TILE_CELLS 64
-#define STAGE_CAP16 2560      // staged halo particles for 16-B payloads (40 KB)
-#define STAGE_CAP32 2304      // ... for 32-B payloads (72 KB)
-
-struct Pay32 { float4 a, b; };
+#define TT_LUT 768             // kernels holding the 40-kB lookup table: one CTA per SM
+#define TT_MATVEC 512          // PCG mat-vec (no table): two CTAs per SM
+#define TT_PLAIN 512
+#define STAGE_CAP 2432        // staged halo particles per tile (one or two float4 arrays: 38 / 76 KB)
 
 // ---- grid / key helpers ---------------------------------------------------------------------------
 // cell slightly larger than h so that two particles closer than h can never be two cells apart
@@ -111,13 +111,18 @@ __device__ __forceinline__ TileInfo tile_setup(const DevState* __restrict__ S, c
 }
 
 // Step 2: stage the payload of every halo particle; half a warp per cell (cells hold ~8 particles).
-template<class Payload, class Load>
-__device__ __forceinline__ void tile_stage(const TileShared& sh, Payload* __restrict__ sPay, const Load& load) {
+// The payload is kept as one or two float4 arrays (SoA): a gather of consecutive local indices by the 8 lanes
+// of a group then touches 8 different 16-B bank groups.
+template<int NPAY, class Op>
+__device__ __forceinline__ void tile_stage(const TileShared& sh, float4* __restrict__ sA, float4* __restrict__ sB, const Op& op) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int half = lane >> 4, l16 = lane & 15;
     for (int c = warp * 2 + half; c < HALO_CELLS; c += TILE_WARPS * 2) {
         const uint32_t l0 = sh.local[c], cnt = sh.local[c + 1] - l0, g0 = sh.cellG[c];
-        for (uint32_t k = l16; k < cnt; k += 16) sPay[l0 + k] = load(g0 + k);
+        for (uint32_t k = l16; k < cnt; k += 16) {
+            sA[l0 + k] = op.loadA(g0 + k);
+            if (NPAY > 1) sB[l0 + k] = op.loadB(g0 + k);
+        }
     }
 }
 
@@ -128,58 +133,116 @@ __device__ __forceinline__ uint32_t tile_local_to_global(const TileShared& sh, u
     return sh.cellG[lo] + (L - sh.local[lo]);
 }
 
-template<class Payload> struct StagedAcc {
-    const Payload* sPay;
-    __device__ __forceinline__ Payload operator()(uint32_t L) const { return sPay[L]; }
-};
-template<class Payload, class Load> struct GlobalAcc {
-    const TileShared* sh; const Load* load;
-    __device__ __forceinline__ Payload operator()(uint32_t L) const { return (*load)(tile_local_to_global(*sh, L)); }
-};
-
-// ---- neighbour list access (u16 local indices, warp-blocked ELL) ---------------------------------
-// the k-th neighbour of particle p sits at list16[((p>>5)*VFD_MAX_NEIGHBORS + k)*32 + (p&31)]
+// ---- neighbour list layout ------------------------------------------------------------------------
+// u16 tile-local indices, warp-blocked ELL: the k-th neighbour of particle p sits at
+// list16[((p>>5)*VFD_MAX_NEIGHBORS + k)*32 + (p&31)]; the per-pair viscosity coefficient uses the same layout.
+// One thread per particle: a warp reads 64 B (list) / 128 B (coefficients) per neighbour slot.
 __device__ __forceinline__ size_t ell_base(uint32_t p) { return (size_t)(p >> 5) * (VFD_MAX_NEIGHBORS * 32) + (p & 31); }
 
-// The pass driver.  Op provides:
-//   typedef Payload;  static constexpr bool READ_COUNT;  Payload load(uint32_t g) const;
-//   template<class Acc> void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc);
-// Warps take 32-aligned particle groups so that list reads are full-line coalesced.
-template<class Op>
-__device__ __forceinline__ void tile_pass(const DevState* __restrict__ S, const uint32_t* __restrict__ cellBegin, const uint32_t* __restrict__ cnt,
-                                          TileShared& sh, typename Op::Payload* sPay, uint32_t cap, Op& op, uint32_t* errorFlags = nullptr) {
-    typedef typename Op::Payload Payload;
-    const uint32_t nTiles = S->nTiles;
+// staged / fallback gather of payload array A (for ops that run their own loops: search, classifier)
+template<bool STAGED, class Op> struct TileAcc {
+    const TileShared& sh; const float4* sA; const Op& op;
+    __device__ __forceinline__ float4 operator()(uint32_t L) const { return STAGED ? sA[L] : op.loadA(tile_local_to_global(sh, L)); }
+};
+
+// ---- the pass driver --------------------------------------------------------------------------------
+// One thread per particle of the tile.  Two kinds of Op:
+//  * pair ops (Op::CUSTOM == false): the driver owns the neighbour loop, software-pipelined 4 deep — list
+//    entries (and pair coefficients) of the next 4 neighbours are in flight while the current 4 are gathered
+//    from shared memory and accumulated:
+//       NPAY (1|2), NOWN, NSUM, COEF (0 none, 1 read, 2 write)
+//       float4 loadA(g), loadB(g)                      staged payload of particle g
+//       void load_own(p, float (&own)[NOWN])
+//       void pair(const float (&own)[NOWN], float4 a, float4 b, float& coef, float (&acc)[NSUM])
+//       void finish(p, m, const float (&own)[NOWN], const float (&sum)[NSUM])
+//  * custom ops (Op::CUSTOM == true): NPAY == 1, void particle(p, m, ell, acc) with acc(L) -> float4.
+#define PIPE 4
+template<class Op, bool STAGED>
+__device__ __forceinline__ void tile_particles(const TileInfo& t, const TileShared& sh, const Arrays& A,
+                                               const float4* __restrict__ sA, const float4* __restrict__ sB, Op& op) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nBatch = (t.end - t.begin + 31u) >> 5;
+    for (uint32_t b = warp; b < nBatch; b += TILE_WARPS) {
+        const uint32_t p = t.begin + (b << 5) + lane;
+        if (p >= t.end) continue;
+        if constexpr (Op::CUSTOM) {
+            const TileAcc<STAGED, Op> acc{ sh, sA, op };
+            op.particle(p, ell_base(p), acc);
+        } else {
+            const uint32_t m = __ldg(A.cnt + p);
+            float own[Op::NOWN];
+            op.load_own(p, own);
+            float acc[Op::NSUM];
+            #pragma unroll
+            for (int s = 0; s < Op::NSUM; s++) acc[s] = 0.0f;
+            const uint16_t* __restrict__ col = A.list16 + ell_base(p);
+            float* __restrict__ ccol = A.coef + ell_base(p);
+            uint32_t Lq[PIPE]; float cq[PIPE];
+            #pragma unroll
+            for (int u = 0; u < PIPE; u++) {
+                Lq[u] = 0u; cq[u] = 0.0f;
+                if ((uint32_t)u < m) { Lq[u] = col[(size_t)u * 32]; if (Op::COEF == 1) cq[u] = ccol[(size_t)u * 32]; }
+            }
+            for (uint32_t k = 0; k < m; k += PIPE) {
+                uint32_t Ln[PIPE]; float cn[PIPE];
+                #pragma unroll
+                for (int u = 0; u < PIPE; u++) {
+                    Ln[u] = 0u; cn[u] = 0.0f;
+                    const uint32_t kk = k + PIPE + u;
+                    if (kk < m) { Ln[u] = col[(size_t)kk * 32]; if (Op::COEF == 1) cn[u] = ccol[(size_t)kk * 32]; }
+                }
+                #pragma unroll
+                for (int u = 0; u < PIPE; u++) {
+                    if (k + u < m) {
+                        float4 a, bb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (STAGED) { a = sA[Lq[u]]; if (Op::NPAY > 1) bb = sB[Lq[u]]; }
+                        else { const uint32_t g = tile_local_to_global(sh, Lq[u]); a = op.loadA(g); if (Op::NPAY > 1) bb = op.loadB(g); }
+                        op.pair(own, a, bb, cq[u], acc);
+                        if (Op::COEF == 2) ccol[(size_t)(k + u) * 32] = cq[u];
+                    }
+                }
+                #pragma unroll
+                for (int u = 0; u < PIPE; u++) { Lq[u] = Ln[u]; cq[u] = cn[u]; }
+            }
+            op.finish(p, m, own, acc);
+        }
+    }
+}
+
+template<class Op>
+__device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays& A, TileShared& sh,
+                                          float4* sA, float4* sB, uint32_t cap, Op& op, bool checkIndexRange = false) {
+    const uint32_t nTiles = S->nTiles;
+    const uint32_t* __restrict__ cellBegin = A.cellBegin;
     for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
         // cheap emptiness test before the full setup
         const uint32_t b0 = __ldg(cellBegin + tile * TILE_CELLS), e0 = __ldg(cellBegin + tile * TILE_CELLS + TILE_CELLS);
         if (b0 == e0) continue;
         __syncthreads();                                   // previous tile's readers are done with shared memory
         const TileInfo t = tile_setup(S, cellBegin, tile, sh, cap);
-        if (errorFlags && t.total > 65535u && threadIdx.x == 0) atomicOr(errorFlags, 2u);
+        // local indices are 16-bit: a halo box beyond 65535 particles cannot be encoded (flagged, caught by the host)
+        if (checkIndexRange && t.total > 65535u && threadIdx.x == 0) atomicOr(&S->errorFlags, 2u);
         if (t.staged) {
-            tile_stage<Payload>(sh, sPay, [&](uint32_t g) { return op.load(g); });
+            tile_stage<Op::NPAY>(sh, sA, sB, op);
             __syncthreads();
-            const StagedAcc<Payload> acc{ sPay };
-            for (uint32_t grp = (t.begin >> 5) + warp; (grp << 5) < t.end; grp += TILE_WARPS) {
-                const uint32_t p = (grp << 5) + lane;
-                if (p >= t.begin && p < t.end) op.particle(p, Op::READ_COUNT ? __ldg(cnt + p) : 0u, ell_base(p), acc);
-            }
+            tile_particles<Op, true>(t, sh, A, sA, sB, op);
         } else {
-            auto ld = [&](uint32_t g) { return op.load(g); };
-            const GlobalAcc<Payload, decltype(ld)> acc{ &sh, &ld };
-            for (uint32_t grp = (t.begin >> 5) + warp; (grp << 5) < t.end; grp += TILE_WARPS) {
-                const uint32_t p = (grp << 5) + lane;
-                if (p >= t.begin && p < t.end) op.particle(p, Op::READ_COUNT ? __ldg(cnt + p) : 0u, ell_base(p), acc);
-            }
+            tile_particles<Op, false>(t, sh, A, sA, sB, op);
         }
     }
 }
 
-// dynamic shared memory carve-up: [TileShared][LUT floats][payload]
+// dynamic shared memory carve-up: [TileShared][NLUT lookup tables][payload A][payload B]
 __device__ __forceinline__ TileShared& smem_header(unsigned char* raw) { return *reinterpret_cast<TileShared*>(raw); }
 __host__ __device__ constexpr size_t smem_header_bytes() { return (sizeof(TileShared) + 127) / 128 * 128; }
+template<int NLUT> __device__ __forceinline__ float* smem_lut(unsigned char* raw) { return reinterpret_cast<float*>(raw + smem_header_bytes()); }
+template<int NLUT> __device__ __forceinline__ float4* smem_pay_a(unsigned char* raw) {
+    return reinterpret_cast<float4*>(raw + smem_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float));
+}
+template<int NLUT> __device__ __forceinline__ float4* smem_pay_b(unsigned char* raw, uint32_t cap) { return smem_pay_a<NLUT>(raw) + cap; }
+template<int NLUT, int NPAY> static inline size_t tile_smem_bytes(uint32_t cap) {
+    return smem_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float) + (size_t)cap * NPAY * sizeof(float4);
+}
 
 __device__ __forceinline__ void load_lut_tile(float* dst, const float* __restrict__ src) {
     const float4* s4 = reinterpret_cast<const float4*>(src);

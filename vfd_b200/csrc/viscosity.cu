@@ -26,14 +26,6 @@ namespace vfd {
 extern __shared__ __align__(128) unsigned char smemRaw[];
 #define FOR_EACH_TILE(p) for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += gridDim.x * blockDim.x)
 
-template<int NLUT> __device__ __forceinline__ float* smem_lut() { return reinterpret_cast<float*>(smemRaw + smem_header_bytes()); }
-template<int NLUT, class Payload> __device__ __forceinline__ Payload* smem_payload() {
-    return reinterpret_cast<Payload*>(smemRaw + smem_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float));
-}
-template<int NLUT, class Payload> static size_t tile_smem_bytes(uint32_t cap) {
-    return smem_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float) + (size_t)cap * sizeof(Payload);
-}
-
 // Core/Math/Math.h:19-33 (GetOrthogonalVectors)
 __device__ __forceinline__ void orthogonal_vectors(float3 n, float3& t1, float3& t2) {
     float3 v = f3(1.0f, 0.0f, 0.0f);
@@ -63,31 +55,33 @@ __device__ __forceinline__ bool boundary_samples(const Params& P, float3 xi, flo
 
 // ---- V1 + V2 fused: preconditioner blocks, per-pair coefficients, warm start, |b|^2 ----------
 struct ViscSetupOp {
-    typedef float4 Payload;          // (x, y, z, rho)
-    static constexpr bool READ_COUNT = true;
+    static constexpr bool CUSTOM = false;
+    static constexpr int NPAY = 1, NOWN = 3, NSUM = 9, COEF = 2;       // payload (x, y, z, rho); writes the pair coefficients
     const Params& P; const Arrays& A; Lut K;
     float dt, eps2;
     float bb;
-    __device__ __forceinline__ float4 load(uint32_t g) const { return A.posRho[g]; }
-    template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
-        const float4 xr = A.posRho[p];
-        const float3 xi = f3(xr);
-        const uint16_t* col = A.list16 + ell;
-        float* ccol = A.coef + ell;
-        float M[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };     // zero-initialised, column-major
-        for (uint32_t k = 0; k < m; k++) {
-            const float4 xj = acc(col[(size_t)k * 32]);
-            const float3 d = xi - f3(xj);
-            const float g = K.gradWScalar(d);
-            const float3 gw = g * d;
-            const float s = 10.0f * P.mu * (P.mass / xj.w) / (dot3(d, d) + eps2);
-            ccol[(size_t)k * 32] = s * g;
-            // glm::outerProduct(c, r): column i = c * r[i]
-            M[0] += s * (d.x * gw.x); M[1] += s * (d.y * gw.x); M[2] += s * (d.z * gw.x);
-            M[3] += s * (d.x * gw.y); M[4] += s * (d.y * gw.y); M[5] += s * (d.z * gw.y);
-            M[6] += s * (d.x * gw.z); M[7] += s * (d.y * gw.z); M[8] += s * (d.z * gw.z);
-        }
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
+    __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
+        const float4 x = A.posRho[p]; own[0] = x.x; own[1] = x.y; own[2] = x.z;
+    }
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 xj, float4, float& coef, float (&M)[NSUM]) const {
+        const float3 d = f3(o[0], o[1], o[2]) - f3(xj);
+        const float g = K.gradWScalar(d);
+        const float3 gw = g * d;
+        const float s = 10.0f * P.mu * (P.mass / xj.w) / (dot3(d, d) + eps2);
+        coef = s * g;
+        // glm::outerProduct(c, r): column i = c * r[i]   (zero-initialised accumulator: SURVEY.md F6/Q3)
+        M[0] += s * (d.x * gw.x); M[1] += s * (d.y * gw.x); M[2] += s * (d.z * gw.x);
+        M[3] += s * (d.x * gw.y); M[4] += s * (d.y * gw.y); M[5] += s * (d.z * gw.y);
+        M[6] += s * (d.x * gw.z); M[7] += s * (d.y * gw.z); M[8] += s * (d.z * gw.z);
+    }
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t, const float (&o)[NOWN], const float (&sum)[NSUM]) {
+        const float3 xi = f3(o[0], o[1], o[2]);
+        const float rhoI = A.posRho[p].w;
+        float M[9];
+        #pragma unroll
+        for (int q = 0; q < 9; q++) M[q] = sum[q];
         if (P.muB != 0.0f) {
             for (uint32_t b = 0; b < P.nBodies; b++) {
                 const float4 bx = A.bx[b][p];
@@ -115,7 +109,7 @@ struct ViscSetupOp {
             }
         }
         // inverse(I - dt/rho_i * M), cofactor formula of glm::inverse(mat3) (glm/detail/func_matrix.inl:322-344)
-        const float f = dt / xr.w;
+        const float f = dt / rhoI;
         float a[9];
         #pragma unroll
         for (int q = 0; q < 9; q++) a[q] = ((q == 0 || q == 4 || q == 8) ? 1.0f : 0.0f) - f * M[q];
@@ -143,12 +137,12 @@ struct ViscSetupOp {
     }
 };
 
-__global__ void __launch_bounds__(TILE_THREADS) k_visc_setup(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+__global__ void __launch_bounds__(TT_LUT) k_visc_setup(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
     TileShared& sh = smem_header(smemRaw);
-    float* sG = smem_lut<1>();
+    float* sG = smem_lut<1>(smemRaw);
     load_lut_tile(sG, lutG);
     ViscSetupOp op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, 0.01f * P.h2, 0.0f };
-    tile_pass(S, A.cellBegin, A.cnt, sh, smem_payload<1, float4>(), STAGE_CAP16, op);
+    tile_pass(S, A, sh, smem_pay_a<1>(smemRaw), nullptr, STAGE_CAP, op);
     __syncthreads();
     double v[1] = { (double)op.bb };
     if (block_reduce_publish<1>(v, A.partials, &S->ticket[4], sh.red)) {
@@ -173,28 +167,27 @@ __device__ __forceinline__ float3 mat_vec(const float* __restrict__ minv, uint32
 
 template<bool INIT>
 struct ViscMatvecOp {
-    typedef Pay32 Payload;           // (x, y, z, rho), (p.x, p.y, p.z, -)
-    static constexpr bool READ_COUNT = true;
+    static constexpr bool CUSTOM = false;
+    static constexpr int NPAY = 2, NOWN = 6, NSUM = 3, COEF = 1;       // payload: (x, y, z, rho), the vector's (x, y, z); reads the pair coefficients
     const Params& P; const Arrays& A;
     const float4* __restrict__ x;    // the vector the operator is applied to: g (INIT) or the search direction p
     float dt;
     float s0, s1;
-    __device__ __forceinline__ Pay32 load(uint32_t g) const { return Pay32{ A.posRho[g], x[g] }; }
-    template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, uint32_t m, size_t ell, const Acc& acc) {
-        const float4 xr = A.posRho[p];
-        const float3 xi = f3(xr);
-        const float3 vi = f3(x[p]);
-        const uint16_t* col = A.list16 + ell;
-        const float* ccol = A.coef + ell;
-        float3 sum = f3(0.0f, 0.0f, 0.0f);
-        for (uint32_t k = 0; k < m; k++) {
-            const Pay32 nb = acc(col[(size_t)k * 32]);
-            const float c = ccol[(size_t)k * 32];
-            const float3 d = xi - f3(nb.a);
-            const float w = c * dot3(vi - f3(nb.b), d);
-            sum.x = __fmaf_rn(w, d.x, sum.x); sum.y = __fmaf_rn(w, d.y, sum.y); sum.z = __fmaf_rn(w, d.z, sum.z);
-        }
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
+    __device__ __forceinline__ float4 loadB(uint32_t g) const { return x[g]; }
+    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
+        const float4 xr = A.posRho[p], v = x[p];
+        own[0] = xr.x; own[1] = xr.y; own[2] = xr.z; own[3] = v.x; own[4] = v.y; own[5] = v.z;
+    }
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
+        const float dx = o[0] - a.x, dy = o[1] - a.y, dz = o[2] - a.z;
+        const float w = c * __fmaf_rn(o[5] - b.z, dz, __fmaf_rn(o[4] - b.y, dy, (o[3] - b.x) * dx));
+        acc[0] = __fmaf_rn(w, dx, acc[0]); acc[1] = __fmaf_rn(w, dy, acc[1]); acc[2] = __fmaf_rn(w, dz, acc[2]);
+    }
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t, const float (&o)[NOWN], const float (&acc)[NSUM]) {
+        const float3 xi = f3(o[0], o[1], o[2]), vi = f3(o[3], o[4], o[5]);
+        const float rhoI = A.posRho[p].w;
+        float3 sum = f3(acc[0], acc[1], acc[2]);
         if (P.muB != 0.0f) {
             for (uint32_t b = 0; b < P.nBodies; b++) {
                 const float4 bx = A.bx[b][p];
@@ -209,7 +202,7 @@ struct ViscMatvecOp {
                 }
             }
         }
-        const float3 q = vi - (dt / xr.w) * sum;
+        const float3 q = vi - (dt / rhoI) * sum;
         if (INIT) {
             // r = b - A g ; p = M^-1 r ; |r|^2 ; r.p      (DFSPHImplementation.cu:638-691)
             const float3 r = f3(A.vel[p]) - q;
@@ -226,11 +219,11 @@ struct ViscMatvecOp {
 };
 
 template<bool INIT>
-__global__ void __launch_bounds__(TILE_THREADS) k_visc_matvec(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+__global__ void __launch_bounds__(TT_MATVEC) k_visc_matvec(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (!INIT && S->viscActive != 1u) return;
     TileShared& sh = smem_header(smemRaw);
     ViscMatvecOp<INIT> op{ P, A, INIT ? A.cgG : A.cgP, S->dt, 0.0f, 0.0f };
-    tile_pass(S, A.cellBegin, A.cnt, sh, smem_payload<0, Pay32>(), STAGE_CAP32, op);
+    tile_pass(S, A, sh, smem_pay_a<0>(smemRaw), smem_pay_b<0>(smemRaw, STAGE_CAP), STAGE_CAP, op);
     __syncthreads();
     double v[2] = { (double)op.s0, (double)op.s1 };
     uint32_t* ticket = &S->ticket[5];
@@ -303,7 +296,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_update(Params P, Arrays A, Dev
 }
 
 // p = beta p + z   (:788-802)
-__global__ void __launch_bounds__(VFD_TPB) k_visc_direction(Params P, Arrays A, const DevState* __restrict__ S) {
+__global__ void __launch_bounds__(VFD_TPB) k_visc_direction(Params P, Arrays A, DevState* S) {
     if (S->viscActive != 1u) return;
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n) return;
@@ -315,7 +308,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_direction(Params P, Arrays A, 
 }
 
 // V5: a += (g - v)/dt ; dv = g - v
-__global__ void __launch_bounds__(VFD_TPB) k_visc_apply(Params P, Arrays A, const DevState* __restrict__ S) {
+__global__ void __launch_bounds__(VFD_TPB) k_visc_apply(Params P, Arrays A, DevState* S) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n) return;
     const float dt = S->dt;
@@ -331,13 +324,13 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_apply(Params P, Arrays A, cons
 }
 
 template<typename Kern>
-static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L) {
+static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L, int threads) {
     static thread_local const void* cachedK[16]; static thread_local int cachedV[16]; static thread_local int nc = 0;
     int perSM = 0;
     for (int i = 0; i < nc; i++) if (cachedK[i] == (const void*)kern) perSM = cachedV[i];
     if (!perSM) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, TILE_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, threads, smem);
         if (perSM < 1) perSM = 1;
         if (nc < 16) { cachedK[nc] = (const void*)kern; cachedV[nc] = perSM; nc++; }
     }
@@ -345,16 +338,16 @@ static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L) {
 }
 
 void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s0 = tile_smem_bytes<1, float4>(STAGE_CAP16), s1 = tile_smem_bytes<0, Pay32>(STAGE_CAP32);
-    const uint32_t g0 = tile_grid(k_visc_setup, s0, L);
-    { LaunchScope ls(L, KID_VISC_SETUP); k_visc_setup<<<g0, TILE_THREADS, s0, L.stream>>>(P, A, S, lutG); }
-    const uint32_t g1 = tile_grid(k_visc_matvec<true>, s1, L);
-    { LaunchScope ls(L, KID_VISC_MATVEC0); k_visc_matvec<true><<<g1, TILE_THREADS, s1, L.stream>>>(P, A, S); }
+    const size_t s0 = tile_smem_bytes<1, 1>(STAGE_CAP), s1 = tile_smem_bytes<0, 2>(STAGE_CAP);
+    const uint32_t g0 = tile_grid(k_visc_setup, s0, L, TT_LUT);
+    { LaunchScope ls(L, KID_VISC_SETUP); k_visc_setup<<<g0, TT_LUT, s0, L.stream>>>(P, A, S, lutG); }
+    const uint32_t g1 = tile_grid(k_visc_matvec<true>, s1, L, TT_MATVEC);
+    { LaunchScope ls(L, KID_VISC_MATVEC0); k_visc_matvec<true><<<g1, TT_MATVEC, s1, L.stream>>>(P, A, S); }
 }
 void launch_viscosity_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    const size_t s1 = tile_smem_bytes<0, Pay32>(STAGE_CAP32);
-    const uint32_t g1 = tile_grid(k_visc_matvec<false>, s1, L);
-    { LaunchScope ls(L, KID_VISC_MATVEC); k_visc_matvec<false><<<g1, TILE_THREADS, s1, L.stream>>>(P, A, S); }
+    const size_t s1 = tile_smem_bytes<0, 2>(STAGE_CAP);
+    const uint32_t g1 = tile_grid(k_visc_matvec<false>, s1, L, TT_MATVEC);
+    { LaunchScope ls(L, KID_VISC_MATVEC); k_visc_matvec<false><<<g1, TT_MATVEC, s1, L.stream>>>(P, A, S); }
     const uint32_t tiles = (P.n + VFD_TPB - 1) / VFD_TPB;
     const uint32_t g2 = std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 8u));
     { LaunchScope ls(L, KID_VISC_UPDATE); k_visc_update<<<g2, VFD_TPB, 0, L.stream>>>(P, A, S); }
