@@ -30,8 +30,11 @@ namespace vfd {
 
 // Everything constant between two SetDescription() calls; passed to kernels by value.
 struct Params {
-    uint32_t n;                 // particles
+    uint32_t n;                 // particles held by this rank (owned + ghost copies of the neighbour slabs' edge tiles)
+    uint32_t nGlobal;           // particles of the whole simulation
     uint32_t nBodies;
+    uint32_t nRanks, rank;      // spatial decomposition in slabs of tile columns along x (distributed.cu); 1, 0 on one GPU
+    uint32_t tile0, tile1;      // owned tiles [tile0, tile1) of this rank's local grid; tile1 = 0xffffffff: all tiles
     float h, h2, r, d;          // SupportRadius, SupportRadius2, ParticleRadius, ParticleDiameter
     float volume, rho0, mass, massInv;
     float mu, muB, tangentialDistance;
@@ -78,6 +81,11 @@ struct DevState {
     float rhsNorm2, threshold, resNorm2, delta, alpha, beta;
     // last-block tickets (one per reduction site)
     uint32_t ticket[8];
+    // multi-GPU: this rank's partial reduction results per site (control.cuh), all-reduced in place
+    double red[16];
+    // multi-GPU: global cell coordinates of the local grid's cell (0,0,0)
+    int32_t cellOffset[3];
+    uint32_t pad_;
 };
 
 struct float3x3 { float m[9]; };   // column-major like glm::mat3x3: m[3*c + r]

@@ -18,13 +18,17 @@
 // of the reference's host loops is taken by the last block of the iteration kernel.
 #include "solver.h"
 #include "tile.cuh"
+#include "control.cuh"
 #include <algorithm>
 
 namespace vfd {
 
 extern __shared__ __align__(128) unsigned char smemRaw[];
 
-#define FOR_EACH_TILE(p) for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += gridDim.x * blockDim.x)
+#define FOR_EACH_OWNED(p) uint32_t ownB_, ownE_; owned_range(P, A.cellBegin, ownB_, ownE_); \
+    for (uint32_t p = ownB_ + blockIdx.x * blockDim.x + threadIdx.x; p < ownE_; p += gridDim.x * blockDim.x)
+#define OWNED_INDEX(p) uint32_t ownB_, ownE_; owned_range(P, A.cellBegin, ownB_, ownE_); \
+    const uint32_t p = ownB_ + blockIdx.x * blockDim.x + threadIdx.x; if (p >= ownE_) return
 #define NO_B __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
 
 // ---- K2 + K3 + K8 fused: density, DFSPH factor, a = g --------------------------------------
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(TT_LUT) k_density_factor(const __grid_constant
     load_lut_tile(sW, lutW);
     load_lut_tile(sG, lutG);
     DensityFactorOp op{ P, A, Lut{ sW, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 } };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<2>(smemRaw), nullptr, STAGE_CAP, op);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<2>(smemRaw), nullptr, STAGE_CAP, op, P.tile0, P.tile1);
 }
 
 // ---- K4 / K10: solver source terms ----------------------------------------------------------
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(TT_LUT) k_source(const __grid_constant__ Param
         else     { S->pressIt = 0; S->pressErr = 0.0f; S->pressActive = (0u < P.minPressIt && 0u < P.maxPressIt) ? 1u : 0u; }
     }
     SourceOp<DIV> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, S->dtInv, S->dt2Inv };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP), STAGE_CAP, op);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP), STAGE_CAP, op, P.tile0, P.tile1);
 }
 
 // ---- K5 / K7 / K11 / K13: pressure acceleration from kappa ---------------------------------
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(TT_LUT) k_pressure_accel(const __grid_constant
     load_lut_tile(sG, lutG);
     AccelOp<MODE> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 },
                       (MODE == ACC_DIV_ITER || MODE == ACC_DIV_FINISH) ? A.kappaV : A.kappa, S->dt };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<1>(smemRaw), nullptr, STAGE_CAP, op);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<1>(smemRaw), nullptr, STAGE_CAP, op, P.tile0, P.tile1);
 }
 
 // ---- K6 / K12 (+ R1 / R3): one Jacobi update and the fused residual reduction ----------------
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(TT_LUT) k_solve_iteration(const __grid_constan
     float* sG = smem_lut<1>(smemRaw);
     load_lut_tile(sG, lutG);
     SolveOp<DIV> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, DIV ? S->dt : S->dt2, 0.0f };
-    tile_pass(S, A, sh, smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP), STAGE_CAP, op);
+    tile_pass(S, A, sh, smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP), STAGE_CAP, op, P.tile0, P.tile1);
     __syncthreads();
     double v[1] = { (double)op.errSum };
     uint32_t* ticket = &S->ticket[DIV ? 1 : 2];
@@ -241,19 +245,7 @@ __global__ void __launch_bounds__(TT_LUT) k_solve_iteration(const __grid_constan
         double tot[1];
         last_block_fold<1>(tot, A.partials, sh.red);
         if (threadIdx.x == 0) {
-            // the reference folds with thrust::minus from 0 (DFSPHImplementation.cu:483-489, 554-560):
-            // as a left fold that is -(sum), the mean of rho0*|residuum|
-            const float err = (float)(-tot[0]) / (float)P.n;
-            if (DIV) {
-                const uint32_t it = S->divIt + 1;
-                const float eta = S->dtInv * P.divErrScale;
-                S->divIt = it; S->divErr = err;
-                S->divActive = ((err > eta || it < P.minDivIt) && it < P.maxDivIt) ? 1u : 0u;
-            } else {
-                const uint32_t it = S->pressIt + 1;
-                S->pressIt = it; S->pressErr = err;
-                S->pressActive = ((err > P.etaPressure || it < P.minPressIt) && it < P.maxPressIt) ? 1u : 0u;
-            }
+            finish_reduction<1>(DIV ? SITE_DIV : SITE_PRESS, P, S, tot);
             *ticket = 0;
         }
     }
@@ -264,7 +256,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_cfl(Params P, Arrays A, DevState* S
     __shared__ double shRed[32];
     const float dt = S->dt;
     float mx = 0.0f;
-    FOR_EACH_TILE(p) {
+    FOR_EACH_OWNED(p) {
         const float4 v = A.vel[p], a = A.acc[p];
         const float3 w = f3(v.x + a.x * dt, v.y + a.y * dt, v.z + a.z * dt);
         mx = fmaxf(mx, dot3(w, w));
@@ -274,17 +266,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_cfl(Params P, Arrays A, DevState* S
         double tot[1];
         last_block_fold<1>(tot, A.partials, shRed, true);
         if (threadIdx.x == 0) {
-            float vmax2 = fmaxf((float)tot[0], 0.1f);              // initial value 0.1 (DFSPHImplementation.cu:397)
-            if (vmax2 < 1.0e-9f) vmax2 = 1.0e-9f;
-            float ndt = 0.4f * (P.d / sqrtf(vmax2));
-            ndt = fminf(ndt, P.maxDt);
-            ndt = fmaxf(ndt, P.minDt);
-            S->vmax2 = vmax2;
-            S->dt = ndt; S->dt2 = ndt * ndt; S->dtInv = 1.0f / ndt; S->dt2Inv = 1.0f / (ndt * ndt);
-            S->sampleCount = P.csdFix > 0 ? (uint32_t)P.csdFix : (uint32_t)(int)((float)P.csd * ndt);
-            S->mcFactor = P.mcFactor;
-            S->frameTime += ndt;
-            S->stepCount += 1;
+            finish_reduction<1>(SITE_CFL, P, S, tot);
             S->ticket[3] = 0;
         }
     }
@@ -292,8 +274,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_cfl(Params P, Arrays A, DevState* S
 
 // K9: v += dt * a
 __global__ void __launch_bounds__(VFD_TPB) k_velocity(Params P, Arrays A, DevState* S) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n) return;
+    OWNED_INDEX(p);
     const float dt = S->dt;
     float4 v = A.vel[p];
     const float4 a = A.acc[p];
@@ -303,8 +284,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_velocity(Params P, Arrays A, DevSta
 
 // K14: x += dt * v
 __global__ void __launch_bounds__(VFD_TPB) k_position(Params P, Arrays A, DevState* S) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n) return;
+    OWNED_INDEX(p);
     const float dt = S->dt;
     float4 x = A.posRho[p];
     const float4 v = A.vel[p];

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(TT_PLAIN) k_build_list(const __grid_constant__
     extern __shared__ __align__(128) unsigned char smemRaw[];
     TileShared& sh = smem_header(smemRaw);
     SearchOp<FMA> op{ A.pos, S, &sh, A.cnt, A.list16, P.h2, cell_inv(P.h) };
-    tile_pass(S, A, sh, smem_pay_a<0>(smemRaw), nullptr, STAGE_CAP, op, true);
+    tile_pass(S, A, sh, smem_pay_a<0>(smemRaw), nullptr, STAGE_CAP, op, P.tile0, P.tile1, true);
 }
 
 static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }

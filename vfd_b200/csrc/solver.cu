@@ -254,6 +254,7 @@ int Solver::set_description(const VfdDfsphDescription& d) {
 void Solver::refresh_params() {
     Params& P = params;
     P.n = info.ParticleCount; P.nBodies = info.RigidBodyCount;
+    P.nGlobal = info.ParticleCount; P.nRanks = 1; P.rank = 0; P.tile0 = 0; P.tile1 = 0xffffffffu;
     P.h = info.SupportRadius; P.h2 = info.SupportRadius2; P.r = info.ParticleRadius; P.d = info.ParticleDiameter;
     P.volume = info.Volume; P.rho0 = info.Density0; P.mass = info.ParticleMass; P.massInv = info.ParticleMassInverse;
     P.mu = info.DynamicViscosity; P.muB = info.DynamicBoundaryViscosity; P.tangentialDistance = info.TangentialDistance;

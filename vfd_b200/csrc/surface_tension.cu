@@ -13,7 +13,8 @@
 namespace vfd {
 
 extern __shared__ __align__(128) unsigned char smemRaw[];
-#define FOR_EACH_TILE(p) for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += gridDim.x * blockDim.x)
+#define OWNED_INDEX(p) uint32_t ownB_, ownE_; owned_range(P, A.cellBegin, ownB_, ownE_); \
+    const uint32_t p = ownB_ + blockIdx.x * blockDim.x + threadIdx.x; if (p >= ownE_) return
 
 __device__ __forceinline__ float3 normalize_if_nonzero(float3 v) {   // DFSPHKernels.cu:874-879
     if (dot3(v, v) > 0.0f) v = normalize3(v);
@@ -79,7 +80,7 @@ struct StClassifyOp {
 __global__ void __launch_bounds__(TT_PLAIN) k_st_classify(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ halton) {
     const float radiusRatio = P.nbrRadius / P.r;
     StClassifyOp op{ P, A, halton, S->sampleCount, S->mcFactor, radiusRatio * radiusRatio * P.h2 };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<0>(smemRaw), nullptr, STAGE_CAP, op);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<0>(smemRaw), nullptr, STAGE_CAP, op, P.tile0, P.tile1);
 }
 
 // T2: neighbour-weighted smoothing of normal and curvature among surface particles
@@ -118,13 +119,12 @@ struct StSmoothOp {
 
 __global__ void __launch_bounds__(TT_PLAIN) k_st_smooth(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     StSmoothOp op{ P, A };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<0>(smemRaw), smem_pay_b<0>(smemRaw, STAGE_CAP), STAGE_CAP, op);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<0>(smemRaw), smem_pay_b<0>(smemRaw, STAGE_CAP), STAGE_CAP, op, P.tile0, P.tile1);
 }
 
 // T3: apply the force (once per smoothing pass: SURVEY.md Q18)
 __global__ void __launch_bounds__(VFD_TPB) k_st_apply(Params P, Arrays A) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n) return;
+    OWNED_INDEX(p);
     const float4 n = A.nrm[p];
     if (n.x != 0.0f || n.y != 0.0f || n.z != 0.0f) {
         const float4 fn = A.nbar[p];

@@ -211,10 +211,10 @@ __device__ __forceinline__ void tile_particles(const TileInfo& t, const TileShar
 
 template<class Op>
 __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays& A, TileShared& sh,
-                                          float4* sA, float4* sB, uint32_t cap, Op& op, bool checkIndexRange = false) {
-    const uint32_t nTiles = S->nTiles;
+                                          float4* sA, float4* sB, uint32_t cap, Op& op, uint32_t tile0, uint32_t tile1, bool checkIndexRange = false) {
+    const uint32_t nTiles = min(S->nTiles, tile1);
     const uint32_t* __restrict__ cellBegin = A.cellBegin;
-    for (uint32_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    for (uint32_t tile = tile0 + blockIdx.x; tile < nTiles; tile += gridDim.x) {
         // cheap emptiness test before the full setup
         const uint32_t b0 = __ldg(cellBegin + tile * TILE_CELLS), e0 = __ldg(cellBegin + tile * TILE_CELLS + TILE_CELLS);
         if (b0 == e0) continue;
@@ -230,6 +230,13 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
             tile_particles<Op, false>(t, sh, A, sA, sB, op);
         }
     }
+}
+
+// The particles this rank owns (multi-GPU: the tiles [tile0, tile1) of the local grid; the tile columns before and
+// after hold ghost copies of the neighbour slabs' edge particles): a contiguous range because tiles are x-slowest.
+__device__ __forceinline__ void owned_range(const Params& P, const uint32_t* __restrict__ cellBegin, uint32_t& b, uint32_t& e) {
+    b = P.tile0 ? __ldg(cellBegin + (size_t)P.tile0 * TILE_CELLS) : 0u;
+    e = P.tile1 != 0xffffffffu ? __ldg(cellBegin + (size_t)P.tile1 * TILE_CELLS) : P.n;
 }
 
 // dynamic shared memory carve-up: [TileShared][NLUT lookup tables][payload A][payload B]

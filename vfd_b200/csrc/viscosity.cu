@@ -19,12 +19,16 @@
 // c_ij ((p_i - p_j) . x_ij) x_ij, with x_j and p_j gathered from the tile's shared-memory stage.
 #include "solver.h"
 #include "tile.cuh"
+#include "control.cuh"
 #include <algorithm>
 
 namespace vfd {
 
 extern __shared__ __align__(128) unsigned char smemRaw[];
-#define FOR_EACH_TILE(p) for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += gridDim.x * blockDim.x)
+#define FOR_EACH_OWNED(p) uint32_t ownB_, ownE_; owned_range(P, A.cellBegin, ownB_, ownE_); \
+    for (uint32_t p = ownB_ + blockIdx.x * blockDim.x + threadIdx.x; p < ownE_; p += gridDim.x * blockDim.x)
+#define OWNED_INDEX(p) uint32_t ownB_, ownE_; owned_range(P, A.cellBegin, ownB_, ownE_); \
+    const uint32_t p = ownB_ + blockIdx.x * blockDim.x + threadIdx.x; if (p >= ownE_) return
 
 // Core/Math/Math.h:19-33 (GetOrthogonalVectors)
 __device__ __forceinline__ void orthogonal_vectors(float3 n, float3& t1, float3& t2) {
@@ -142,15 +146,14 @@ __global__ void __launch_bounds__(TT_LUT) k_visc_setup(const __grid_constant__ P
     float* sG = smem_lut<1>(smemRaw);
     load_lut_tile(sG, lutG);
     ViscSetupOp op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, 0.01f * P.h2, 0.0f };
-    tile_pass(S, A, sh, smem_pay_a<1>(smemRaw), nullptr, STAGE_CAP, op);
+    tile_pass(S, A, sh, smem_pay_a<1>(smemRaw), nullptr, STAGE_CAP, op, P.tile0, P.tile1);
     __syncthreads();
     double v[1] = { (double)op.bb };
     if (block_reduce_publish<1>(v, A.partials, &S->ticket[4], sh.red)) {
         double tot[1];
         last_block_fold<1>(tot, A.partials, sh.red);
         if (threadIdx.x == 0) {
-            S->rhsNorm2 = (float)tot[0];
-            S->viscIt = 0;
+            finish_reduction<1>(SITE_VISC_BB, P, S, tot);
             S->ticket[4] = 0;
         }
     }
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(TT_MATVEC) k_visc_matvec(const __grid_constant
     if (!INIT && S->viscActive != 1u) return;
     TileShared& sh = smem_header(smemRaw);
     ViscMatvecOp<INIT> op{ P, A, INIT ? A.cgG : A.cgP, S->dt, 0.0f, 0.0f };
-    tile_pass(S, A, sh, smem_pay_a<0>(smemRaw), smem_pay_b<0>(smemRaw, STAGE_CAP), STAGE_CAP, op);
+    tile_pass(S, A, sh, smem_pay_a<0>(smemRaw), smem_pay_b<0>(smemRaw, STAGE_CAP), STAGE_CAP, op, P.tile0, P.tile1);
     __syncthreads();
     double v[2] = { (double)op.s0, (double)op.s1 };
     uint32_t* ticket = &S->ticket[5];
@@ -231,24 +234,8 @@ __global__ void __launch_bounds__(TT_MATVEC) k_visc_matvec(const __grid_constant
         double tot[2];
         last_block_fold<2>(tot, A.partials, sh.red);
         if (threadIdx.x == 0) {
-            if (INIT) {
-                const float rhs = S->rhsNorm2;
-                const float rr = (float)tot[0];
-                S->resNorm2 = rr;
-                S->delta = fabsf((float)tot[1]);
-                if (rhs == 0.0f) {
-                    S->viscActive = 2u;          // g := 0, error 0 (DFSPHImplementation.cu:656-661); applied by k_visc_apply
-                    S->viscErr = 0.0f;
-                } else {
-                    const float thr = fmaxf(P.viscErr2 * rhs, FLT_MIN);
-                    S->threshold = thr;
-                    S->viscErr = sqrtf(rr / rhs);
-                    // loop condition "it >= Min && it < Max" at it = 0 (:693)
-                    S->viscActive = (!(rr < thr) && 0u >= P.minViscIt && 0u < P.maxViscIt) ? 1u : 0u;
-                }
-            } else {
-                S->alpha = S->delta / (float)tot[0];
-            }
+            if (INIT) finish_reduction<2>(SITE_VISC_INIT, P, S, tot);
+            else { const double t1[1] = { tot[0] }; finish_reduction<1>(SITE_VISC_PQ, P, S, t1); }
             *ticket = 0;
         }
     }
@@ -260,7 +247,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_update(Params P, Arrays A, Dev
     __shared__ double shRed[64];
     const float alpha = S->alpha;
     float s0 = 0.0f, s1 = 0.0f;
-    FOR_EACH_TILE(p) {
+    FOR_EACH_OWNED(p) {
         const float4 pp = A.cgP[p], qq = A.cgQ[p];
         float4 g = A.cgG[p], r = A.cgR[p];
         g.x = g.x + pp.x * alpha; g.y = g.y + pp.y * alpha; g.z = g.z + pp.z * alpha;
@@ -276,20 +263,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_update(Params P, Arrays A, Dev
         double tot[2];
         last_block_fold<2>(tot, A.partials, shRed);
         if (threadIdx.x == 0) {
-            const float rr = (float)tot[0];
-            S->resNorm2 = rr;
-            S->viscErr = sqrtf(rr / S->rhsNorm2);
-            if (rr < S->threshold) {
-                S->viscActive = 0u;                       // break: this iteration is not counted (:770-772)
-            } else {
-                const float dNew = fabsf((float)tot[1]);
-                S->beta = dNew / S->delta;
-                S->delta = dNew;
-                const uint32_t it = S->viscIt + 1;
-                S->viscIt = it;
-                // viscActive 1: continue; 3: direction update still owed for a loop that then ends
-                S->viscActive = (it >= P.minViscIt && it < P.maxViscIt) ? 1u : 0u;
-            }
+            finish_reduction<2>(SITE_VISC_UPDATE, P, S, tot);
             S->ticket[6] = 0;
         }
     }
@@ -298,8 +272,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_update(Params P, Arrays A, Dev
 // p = beta p + z   (:788-802)
 __global__ void __launch_bounds__(VFD_TPB) k_visc_direction(Params P, Arrays A, DevState* S) {
     if (S->viscActive != 1u) return;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n) return;
+    OWNED_INDEX(p);
     const float beta = S->beta;
     const float4 z = A.cgZ[p];
     float4 d = A.cgP[p];
@@ -309,8 +282,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_direction(Params P, Arrays A, 
 
 // V5: a += (g - v)/dt ; dv = g - v
 __global__ void __launch_bounds__(VFD_TPB) k_visc_apply(Params P, Arrays A, DevState* S) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n) return;
+    OWNED_INDEX(p);
     const float dt = S->dt;
     float4 g = A.cgG[p];
     if (S->viscActive == 2u) g = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
