@@ -204,6 +204,26 @@ int vfd_dfsph_set_option(VfdDfsph* h, int option, int64_t value);
 /* per-kernel accounting for bench.py: number of kernels launched since the last reset */
 int vfd_dfsph_get_launch_count(VfdDfsph* h, uint64_t* launches, int reset);
 
+/* ---- several GPUs: one process (rank) per GPU, the domain cut into slabs of tile columns along x ----------------
+ * No reference equivalent (the reference drives device 0 only: VFD/Source/Debug/SystemInfo.cpp:34-35).
+ * Call order on every rank:  create -> init_distributed -> get_grid / set_slab -> set_particles_distributed ->
+ * set_rigid_bodies -> step ...  Ranks own consecutive slabs in rank order; rank r exchanges with r-1 and r+1 only.
+ * NCCL (libnccl.so.2) is loaded at run time by init_distributed; single-GPU use never needs it. */
+int vfd_dist_unique_id(char out[128]);     /* on rank 0; hand the 128 bytes to every rank (ncclGetUniqueId) */
+int vfd_dfsph_init_distributed(VfdDfsph* h, int rank, int nranks, const char id[128], const float domainMin[3], const float domainMax[3]);
+/* the global search grid over the domain: origin, cell size, tiles (4x4x4 cells) per axis; identical on all ranks */
+int vfd_dfsph_get_grid(VfdDfsph* h, float origin[3], float* cellSize, uint32_t tiles[3]);
+/* this rank owns the tile columns [lo, hi) along x (lo of rank r+1 == hi of rank r) */
+int vfd_dfsph_set_slab(VfdDfsph* h, uint32_t tileColumnLo, uint32_t tileColumnHi);
+/* this rank's particles with their global ids (unique over all ranks), the global particle count, and the number
+ * of particle slots to allocate (owned + two ghost columns + head room for migration) */
+int vfd_dfsph_set_particles_distributed(VfdDfsph* h, const float* pos_xyz, const float* vel_xyz, const uint32_t* ids,
+                                        uint32_t n, uint32_t nGlobal, uint32_t capacity);
+/* the particles this rank owns now, in local order, with their ids (pass ids = out = NULL to get the count) */
+int vfd_dfsph_get_owned(VfdDfsph* h, uint32_t capacity, uint32_t* count, uint32_t* ids, VfdParticle* out);
+/* halo exchanges, all-reduces, halo bytes sent, state-exchange bytes sent since creation */
+int vfd_dfsph_get_comm_stats(VfdDfsph* h, uint64_t stats[4]);
+
 /* per-kernel device time accumulated while VFD_OPT_KERNEL_TIMERS is on.  *count receives the number of kernel
  * classes; names/ms/launches (each may be NULL) receive up to `capacity` entries.  msActive/launchesActive count only
  * launches that did work (an iteration kernel whose solver has converged returns immediately). */

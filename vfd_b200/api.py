@@ -152,6 +152,13 @@ SYMBOLS = [
     ("vfd_halton_table_build", _i, [_vp]),
     ("vfd_dfsph_set_option", _i, [_vp, _i, C.c_int64]),
     ("vfd_dfsph_get_launch_count", _i, [_vp, C.POINTER(_u64), _i]),
+    ("vfd_dist_unique_id", _i, [_vp]),
+    ("vfd_dfsph_init_distributed", _i, [_vp, _i, _i, _vp, _vp, _vp]),
+    ("vfd_dfsph_get_grid", _i, [_vp, _vp, C.POINTER(_f32), _vp]),
+    ("vfd_dfsph_set_slab", _i, [_vp, _u32, _u32]),
+    ("vfd_dfsph_set_particles_distributed", _i, [_vp, _vp, _vp, _vp, _u32, _u32, _u32]),
+    ("vfd_dfsph_get_owned", _i, [_vp, _u32, C.POINTER(_u32), _vp, _vp]),
+    ("vfd_dfsph_get_comm_stats", _i, [_vp, _vp]),
     ("vfd_dfsph_get_kernel_times", _i, [_vp, _u32, C.POINTER(_u32), _vp, _vp, _vp, _vp, _vp, _i]),
     ("vfd_dfsph_record_event", _i, [_vp, _u32]),
     ("vfd_dfsph_elapsed_ms", _i, [_vp, _u32, _u32, C.POINTER(_f32)]),
@@ -451,9 +458,60 @@ class DFSPHSimulation:
         self._ck(self.L.vfd_dfsph_elapsed_ms(self.h, int(a), int(b), C.byref(ms)))
         return ms.value
 
+    # ---- several GPUs (one process per GPU): slabs of tile columns along x -------------------------------
+    def init_distributed(self, rank, world, unique_id, domain_min, domain_max):
+        a = np.ascontiguousarray(domain_min, np.float32)
+        b = np.ascontiguousarray(domain_max, np.float32)
+        uid = np.frombuffer(bytes(unique_id), np.uint8).copy()
+        assert uid.size == 128
+        self._ck(self.L.vfd_dfsph_init_distributed(self.h, int(rank), int(world), _p(uid), _p(a), _p(b)))
+
+    def grid(self):
+        origin = np.zeros(3, np.float32)
+        tiles = np.zeros(3, np.uint32)
+        cell = C.c_float()
+        self._ck(self.L.vfd_dfsph_get_grid(self.h, _p(origin), C.byref(cell), _p(tiles)))
+        return origin, cell.value, tiles
+
+    def set_slab(self, lo, hi):
+        self._ck(self.L.vfd_dfsph_set_slab(self.h, int(lo), int(hi)))
+
+    def set_particles_distributed(self, pos, vel, ids, n_global, capacity):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        velp = None
+        if vel is not None:
+            vel = np.ascontiguousarray(vel, np.float32).reshape(-1, 3)
+            velp = _p(vel)
+        self.n = pos.shape[0]
+        self._ck(self.L.vfd_dfsph_set_particles_distributed(self.h, _p(pos), velp, _p(ids), self.n, int(n_global), int(capacity)))
+
+    def owned(self):
+        """(ids, particles) this rank owns now."""
+        cnt = C.c_uint32()
+        self._ck(self.L.vfd_dfsph_get_owned(self.h, 0, C.byref(cnt), None, None))
+        ids = np.zeros(max(cnt.value, 1), np.uint32)
+        out = np.zeros(max(cnt.value, 1), PARTICLE_DTYPE)
+        self._ck(self.L.vfd_dfsph_get_owned(self.h, cnt.value, C.byref(cnt), _p(ids), _p(out)))
+        return ids[:cnt.value], out[:cnt.value]
+
+    def comm_stats(self):
+        st = np.zeros(4, np.uint64)
+        self._ck(self.L.vfd_dfsph_get_comm_stats(self.h, _p(st)))
+        return dict(halos=int(st[0]), reductions=int(st[1]), halo_bytes=int(st[2]), state_bytes=int(st[3]))
+
     def set_particles_device(self, d_pos_ptr, d_vel_ptr, n):
         self.n = int(n)
         self._ck(self.L.vfd_dfsph_set_particles_device(self.h, C.c_void_p(d_pos_ptr), C.c_void_p(d_vel_ptr) if d_vel_ptr else None, self.n))
+
+
+def dist_unique_id():
+    """128 bytes identifying a new communicator (rank 0 calls it and hands the bytes to all ranks)."""
+    buf = np.zeros(128, np.uint8)
+    rc = lib().vfd_dist_unique_id(_p(buf))
+    if rc:
+        raise VfdError(rc, (lib().vfd_dfsph_last_error(None) or b"").decode())
+    return buf.tobytes()
 
 
 def kernel_tables(support_radius):

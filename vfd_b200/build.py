@@ -16,7 +16,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libvfd_dfsph.so")
 OBJDIR = os.path.join(HERE, "build")
 
-CU = ["search.cu", "boundary.cu", "pressure.cu", "viscosity.cu", "surface_tension.cu", "solver.cu", "api.cu", "volume_map.cu"]
+CU = ["search.cu", "boundary.cu", "pressure.cu", "viscosity.cu", "surface_tension.cu", "solver.cu", "distributed.cu", "api.cu", "volume_map.cu"]
 CPP = ["tables.cpp"]
 
 # -fmad=false: no implicit FMA contraction.  The reference's lookup-table kernel is piecewise constant in r
@@ -67,7 +67,7 @@ def build(force=False, verbose=False):
         outs = list(ex.map(cc, range(len(srcs))))
     if verbose:
         print("\n".join(outs))
-    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout[-8000:]))

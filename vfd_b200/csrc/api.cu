@@ -152,6 +152,29 @@ int vfd_dfsph_set_option(VfdDfsph* h, int option, int64_t value) {
 }
 int vfd_dfsph_get_launch_count(VfdDfsph* h, uint64_t* launches, int reset) { GUARD(h); if (launches) *launches = h->s.launches; if (reset) h->s.launches = 0; return VFD_OK; }
 
+int vfd_dist_unique_id(char out[128]) {
+    if (!out) return VFD_E_INVALID;
+    std::string err;
+    int rc = vfd::dist_unique_id(out, err);
+    if (rc) { std::lock_guard<std::mutex> g(g_createMutex); g_createError = err; }
+    return rc;
+}
+int vfd_dfsph_init_distributed(VfdDfsph* h, int rank, int nranks, const char id[128], const float dmin[3], const float dmax[3]) {
+    GUARD(h); if (!id || !dmin || !dmax) return h->s.fail(VFD_E_INVALID, "null argument"); TRY(h->s.dist_init(rank, nranks, id, dmin, dmax));
+}
+int vfd_dfsph_get_grid(VfdDfsph* h, float origin[3], float* cellSize, uint32_t tiles[3]) { GUARD(h); if (!origin || !cellSize || !tiles) return h->s.fail(VFD_E_INVALID, "null argument"); TRY(h->s.dist_get_grid(origin, cellSize, tiles)); }
+int vfd_dfsph_set_slab(VfdDfsph* h, uint32_t lo, uint32_t hi) { GUARD(h); TRY(h->s.dist_set_slab(lo, hi)); }
+int vfd_dfsph_set_particles_distributed(VfdDfsph* h, const float* pos, const float* vel, const uint32_t* ids, uint32_t n, uint32_t nGlobal, uint32_t capacity) {
+    GUARD(h); TRY(h->s.dist_set_particles(pos, vel, ids, n, nGlobal, capacity));
+}
+int vfd_dfsph_get_owned(VfdDfsph* h, uint32_t capacity, uint32_t* count, uint32_t* ids, VfdParticle* out) { GUARD(h); TRY(h->s.dist_get_owned(capacity, count, ids, out)); }
+int vfd_dfsph_get_comm_stats(VfdDfsph* h, uint64_t stats[4]) {
+    GUARD(h); if (!stats) return VFD_E_INVALID;
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (h->s.dist) { stats[0] = h->s.dist->halos; stats[1] = h->s.dist->reductions; stats[2] = h->s.dist->bytesHalo; stats[3] = h->s.dist->bytesState; }
+    return VFD_OK;
+}
+
 int vfd_dfsph_get_kernel_times(VfdDfsph* h, uint32_t capacity, uint32_t* count, const char** names, double* ms, uint64_t* launches,
                                double* msActive, uint64_t* launchesActive, int reset) {
     GUARD(h);

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_boundary(Params P, Arrays A, BodySe
 void launch_boundary(const LaunchCfg& L, const Params& P, const Arrays& A, const BodySet& B) {
     if (P.nBodies == 0) return;
     LaunchScope ls(L, KID_BOUNDARY);
-    k_boundary<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, B);
+    k_boundary<<<std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB), VFD_TPB, 0, L.stream>>>(P, A, B);
 }
 
 } // namespace vfd

@@ -1,0 +1,336 @@
+// distributed.cu — spatial decomposition of one simulation over the GPUs of an NVSwitch box: one process (rank) per
+// GPU, slabs of whole tile columns along x, NCCL point-to-point for the particle state and the halos, NCCL
+// all-reduce for the solver's scalars.  The reference has nothing of the kind (single device 0, default stream:
+// SURVEY.md F10); the obligation is that an N-rank run reproduces the 1-rank run of this library.
+//
+// Geometry: every rank uses the SAME global grid (origin, cell size, tiles) over a fixed domain, so a particle's
+// cell — and with it the in-cell order by persistent id — is identical on every rank that holds a copy of it.
+// Rank r owns the tile columns [colLo, colHi); its local arrays additionally hold a ghost copy of the last owned
+// column of rank r-1 and of the first owned column of rank r+1.  Because tiles are ordered x-slowest the local
+// arrays read   [ ghost L | first owned column ... last owned column | ghost R ]   and every halo exchange is a
+// pair of contiguous copies with no packing: "my first owned column -> left neighbour's ghost R" and
+// "my last owned column -> right neighbour's ghost L".
+//
+// Per step:
+//   1. state exchange (exchange_state): owned particles are classified by the tile column of their new position;
+//      those in [colLo-1, colHi] stay in the local arrays (as owned or ghost), those in columns <= colLo are sent
+//      left and those in columns >= colHi-1 are sent right (80-B records: position, velocity, velocity change,
+//      smoothed normal, curvatures, id) — migration and ghost refresh in one message per neighbour;
+//   2. the usual sort / search over owned + ghost particles; neighbour sums run over the owned tiles only;
+//   3. after every kernel that produces a field a later kernel gathers from neighbours (density, kappa, pressure
+//      acceleration, PCG direction, normals, velocity) the two edge columns are exchanged (halo);
+//   4. every reduction (Jacobi residual, CFL maximum, PCG dot products) is all-reduced and the control decision
+//      (control.cuh) is then taken by a one-thread kernel, identically on all ranks.
+#include "solver_impl.h"
+#include "tile.cuh"
+#include "control.cuh"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cstring>
+
+namespace vfd {
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda(e__, #call, __LINE__); } while (0)
+#define NK(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return fail(VFD_E_NCCL, std::string("NCCL error: ") + dist->api.GetErrorString(r__) + " in " #call); } while (0)
+
+// NCCL is resolved at run time (the library has no link-time dependency on it; a single-GPU user never loads it).
+bool NcclApi::load(std::string& err) {
+    if (handle) return true;
+    handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);            // the copy torch already mapped, if any
+    if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!handle) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define SYM(name) *(void**)(&name) = dlsym(handle, "nccl" #name); if (!name) { err = "libnccl lacks nccl" #name; return false; }
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(GetErrorString) SYM(GroupStart) SYM(GroupEnd) SYM(Send) SYM(Recv) SYM(AllReduce)
+#undef SYM
+    return true;
+}
+
+struct Record { float4 pos, vel, dv, nbar; float curv, curvS, curvD; uint32_t id; };   // 80 B
+static_assert(sizeof(Record) == 80, "state record");
+
+// tile column (global) of a position
+__device__ __forceinline__ int tile_column(float x, float originX, float invCell, int gdimX) {
+    int c = (int)floorf((x - originX) * invCell);
+    c = min(max(c, 1), gdimX - 2);
+    return c >> 2;
+}
+
+// step 1 of the state exchange: classify the owned particles, compact the ones that stay, pack the ones that leave
+__global__ void __launch_bounds__(VFD_TPB) k_migrate(Params P, Arrays A, uint32_t ownB, uint32_t ownE, float originX, float invCell, int gdimX,
+                                                     int colLo, int colHi, int hasLeft, int hasRight,
+                                                     Record* __restrict__ sendL, Record* __restrict__ sendR, uint32_t sendCap, uint32_t* __restrict__ counters) {
+    const uint32_t p = ownB + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ownE) return;
+    const float4 x = A.pos[p];
+    const int col = tile_column(x.x, originX, invCell, gdimX);
+    const bool keep = col >= colLo - 1 && col <= colHi;
+    const bool toL = hasLeft && col <= colLo, toR = hasRight && col >= colHi - 1;
+    Record r{ x, A.vel[p], A.dv[p], A.nbar[p], A.curv[p], A.curvS[p], A.curvD[p], A.id[p] };
+    if (keep) {
+        const uint32_t q = atomicAdd(&counters[0], 1u);
+        A.pos2[q] = r.pos; A.vel2[q] = r.vel; A.dv2[q] = r.dv; A.nbar2[q] = r.nbar;
+        A.curv2[q] = r.curv; A.curvS2[q] = r.curvS; A.curvD2[q] = r.curvD; A.id2[q] = r.id;
+    }
+    if (toL) { const uint32_t q = atomicAdd(&counters[1], 1u); if (q < sendCap) sendL[q] = r; }
+    if (toR) { const uint32_t q = atomicAdd(&counters[2], 1u); if (q < sendCap) sendR[q] = r; }
+}
+
+// step 2: append the received records behind the kept particles; the receiver keeps only what lies in its local grid
+__global__ void __launch_bounds__(VFD_TPB) k_unpack(Arrays A, const Record* __restrict__ recv, uint32_t count, float originX, float invCell, int gdimX,
+                                                    int colLo, int colHi, uint32_t capacity, uint32_t* __restrict__ counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const Record r = recv[i];
+    const int col = tile_column(r.pos.x, originX, invCell, gdimX);
+    if (col < colLo - 1 || col > colHi) return;
+    const uint32_t q = atomicAdd(&counters[0], 1u);
+    if (q >= capacity) return;
+    A.pos2[q] = r.pos; A.vel2[q] = r.vel; A.dv2[q] = r.dv; A.nbar2[q] = r.nbar;
+    A.curv2[q] = r.curv; A.curvS2[q] = r.curvS; A.curvD2[q] = r.curvD; A.id2[q] = r.id;
+}
+
+__global__ void k_control(Params P, DevState* S, int site) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) control_site(site, P, S, &S->red[site * 2]);
+}
+
+// owned particles in local order, with their persistent ids (frame / dump gathering on the host)
+__global__ void k_export_owned(Params P, Arrays A, uint32_t ownB, uint32_t ownE, uint32_t* __restrict__ ids, VfdParticle* __restrict__ out) {
+    const uint32_t p = ownB + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ownE) return;
+    VfdParticle q;
+    const float4 x = A.pos[p], v = A.vel[p], a = A.acc[p], pa = A.pacc[p], dv = A.dv[p], n = A.nrm[p], nb = A.nbar[p];
+    q.Position[0] = x.x; q.Position[1] = x.y; q.Position[2] = x.z;
+    q.Velocity[0] = v.x; q.Velocity[1] = v.y; q.Velocity[2] = v.z;
+    q.Acceleration[0] = a.x; q.Acceleration[1] = a.y; q.Acceleration[2] = a.z;
+    q.PressureAcceleration[0] = pa.x; q.PressureAcceleration[1] = pa.y; q.PressureAcceleration[2] = pa.z;
+    q.PressureResiduum = A.res[p]; q.Density = A.rho[p]; q.DensityAdvection = A.rhoAdv[p];
+    q.PressureRho2 = A.kappa[p]; q.PressureRho2V = A.kappaV[p]; q.Factor = A.alpha[p];
+    q.VelocityDifference[0] = dv.x; q.VelocityDifference[1] = dv.y; q.VelocityDifference[2] = dv.z;
+    q.MonteCarloSurfaceNormal[0] = n.x; q.MonteCarloSurfaceNormal[1] = n.y; q.MonteCarloSurfaceNormal[2] = n.z;
+    q.MonteCarloSurfaceNormalSmooth[0] = nb.x; q.MonteCarloSurfaceNormalSmooth[1] = nb.y; q.MonteCarloSurfaceNormalSmooth[2] = nb.z;
+    q.MonteCarloSurfaceCurvature = A.curv[p]; q.MonteCarloSurfaceCurvatureSmooth = A.curvS[p]; q.DeltaFinalCurvature = A.curvD[p];
+    out[p - ownB] = q;
+    ids[p - ownB] = A.id[p];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int dist_unique_id(char* out128, std::string& err) {
+    NcclApi api;
+    if (!api.load(err)) return VFD_E_NCCL;
+    ncclUniqueId id;
+    ncclResult_t r = api.GetUniqueId(&id);
+    if (r != ncclSuccess) { err = std::string("ncclGetUniqueId: ") + api.GetErrorString(r); return VFD_E_NCCL; }
+    memcpy(out128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return VFD_OK;
+}
+
+// the global grid of a domain: cell = h (1 + 1/1023) like the single-GPU search, two pad cells below, whole tiles
+void dist_grid(const float* dmin, const float* dmax, float h, float origin[3], uint32_t dim[3]) {
+    const double cell = (double)h / (1.0 - 1.0 / 1024.0);
+    for (int k = 0; k < 3; k++) {
+        origin[k] = dmin[k] - 2.0f * (float)cell;
+        const int cells = (int)std::ceil(((double)dmax[k] - (double)origin[k]) / cell) + 2;
+        dim[k] = (uint32_t)((cells + 3) / 4 * 4);
+    }
+}
+
+int Solver::dist_init(int rank, int nranks, const char* id128, const float* dmin, const float* dmax) {
+    CK(cudaSetDevice(device));
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(VFD_E_INVALID, "bad rank / world size");
+    if (info.ParticleCount) return fail(VFD_E_INVALID, "init_distributed must precede set_particles");
+    dist.reset(new Dist());
+    dist->rank = rank; dist->nranks = nranks;
+    std::string err;
+    if (!dist->api.load(err)) return fail(VFD_E_NCCL, err);
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    NK(dist->api.CommInitRank(&dist->comm, nranks, id, rank));
+    dist_grid(dmin, dmax, info.SupportRadius, dist->origin, dist->gdim);
+    for (int k = 0; k < 3; k++) dist->gtiles[k] = dist->gdim[k] / 4;
+    dist->colLo = 0; dist->colHi = dist->gtiles[0];
+    CK(cudaMalloc(&dist->dCounters, 16 * sizeof(uint32_t)));
+    CK(cudaMallocHost(&dist->hCounters, 16 * sizeof(uint32_t)));
+    return VFD_OK;
+}
+
+int Solver::dist_get_grid(float* origin3, float* cellSize, uint32_t* tiles3) {
+    if (!dist) return fail(VFD_E_INVALID, "not distributed");
+    for (int k = 0; k < 3; k++) { origin3[k] = dist->origin[k]; tiles3[k] = dist->gtiles[k]; }
+    *cellSize = (float)((double)info.SupportRadius / (1.0 - 1.0 / 1024.0));
+    return VFD_OK;
+}
+
+int Solver::dist_set_slab(uint32_t colLo, uint32_t colHi) {
+    if (!dist) return fail(VFD_E_INVALID, "not distributed");
+    if (colLo >= colHi || colHi > dist->gtiles[0]) return fail(VFD_E_INVALID, "bad slab (tile columns)");
+    if (info.ParticleCount) return fail(VFD_E_INVALID, "set_slab must precede set_particles");
+    dist->colLo = colLo; dist->colHi = colHi;
+    return VFD_OK;
+}
+
+// local grid of this rank: its owned tile columns plus one ghost column towards each existing neighbour
+void Solver::dist_apply_grid(DevState& s) {
+    const Dist& D = *dist;
+    const bool hasL = D.rank > 0, hasR = D.rank + 1 < D.nranks;
+    const uint32_t c0 = D.colLo - (hasL ? 1u : 0u), c1 = D.colHi + (hasR ? 1u : 0u);
+    s.gridOrigin[0] = D.origin[0]; s.gridOrigin[1] = D.origin[1]; s.gridOrigin[2] = D.origin[2];
+    s.cellOffset[0] = (int32_t)(c0 * 4u); s.cellOffset[1] = 0; s.cellOffset[2] = 0;
+    s.gridDim[0] = (c1 - c0) * 4u; s.gridDim[1] = D.gdim[1]; s.gridDim[2] = D.gdim[2];
+    s.tileDim[0] = c1 - c0; s.tileDim[1] = D.gtiles[1]; s.tileDim[2] = D.gtiles[2];
+    s.nTiles = s.tileDim[0] * s.tileDim[1] * s.tileDim[2];
+    s.nCells = s.nTiles * 64u;
+    s.gridMinCell[0] = s.gridMinCell[1] = s.gridMinCell[2] = 0;
+}
+
+void Solver::dist_params(Params& P) const {
+    const Dist& D = *dist;
+    const uint32_t T = D.gtiles[1] * D.gtiles[2];
+    P.nRanks = (uint32_t)D.nranks; P.rank = (uint32_t)D.rank;
+    P.nGlobal = D.nGlobal;
+    P.n = D.nLocal;
+    P.tile0 = (D.rank > 0 ? 1u : 0u) * T;
+    P.tile1 = P.tile0 + (D.colHi - D.colLo) * T;
+}
+
+// migration + ghost refresh (see the header of this file)
+int Solver::dist_exchange_state() {
+    Dist& D = *dist;
+    const bool hasL = D.rank > 0, hasR = D.rank + 1 < D.nranks;
+    Params P = params;
+    const float invCell = (1.0f / info.SupportRadius) * (1.0f - 1.0f / 1024.0f);
+    CK(cudaMemsetAsync(D.dCounters, 0, 16 * sizeof(uint32_t), stream));
+    const uint32_t nOwned = D.ownE - D.ownB;
+    if (nOwned) {
+        k_migrate<<<(nOwned + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, stream>>>(P, arrays, D.ownB, D.ownE, D.origin[0], invCell, (int)D.gdim[0],
+            (int)D.colLo, (int)D.colHi, hasL ? 1 : 0, hasR ? 1 : 0, (Record*)D.sendL, (Record*)D.sendR, D.haloCap, D.dCounters);
+        launches += 1;
+    }
+    // counts: mine to the host, and to the neighbours
+    NK(D.api.GroupStart());
+    if (hasL) { NK(D.api.Send(D.dCounters + 1, 1, ncclUint32, D.rank - 1, D.comm, stream)); NK(D.api.Recv(D.dCounters + 4, 1, ncclUint32, D.rank - 1, D.comm, stream)); }
+    if (hasR) { NK(D.api.Send(D.dCounters + 2, 1, ncclUint32, D.rank + 1, D.comm, stream)); NK(D.api.Recv(D.dCounters + 5, 1, ncclUint32, D.rank + 1, D.comm, stream)); }
+    NK(D.api.GroupEnd());
+    CK(cudaMemcpyAsync(D.hCounters, D.dCounters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const uint32_t nKeep = D.hCounters[0], nSendL = D.hCounters[1], nSendR = D.hCounters[2];
+    const uint32_t nRecvL = hasL ? D.hCounters[4] : 0u, nRecvR = hasR ? D.hCounters[5] : 0u;
+    if (nSendL > D.haloCap || nSendR > D.haloCap || nRecvL > D.haloCap || nRecvR > D.haloCap)
+        return fail(VFD_E_CAPACITY, "halo buffer too small for one tile column of particles (raise the capacity passed to set_particles)");
+    if ((uint64_t)nKeep + nRecvL + nRecvR > D.capacity) return fail(VFD_E_CAPACITY, "slab outgrew its particle capacity (rebalance the slabs or raise the capacity)");
+    NK(D.api.GroupStart());
+    if (hasL) {
+        if (nSendL) NK(D.api.Send(D.sendL, (size_t)nSendL * 20, ncclFloat32, D.rank - 1, D.comm, stream));
+        if (nRecvL) NK(D.api.Recv(D.recvL, (size_t)nRecvL * 20, ncclFloat32, D.rank - 1, D.comm, stream));
+    }
+    if (hasR) {
+        if (nSendR) NK(D.api.Send(D.sendR, (size_t)nSendR * 20, ncclFloat32, D.rank + 1, D.comm, stream));
+        if (nRecvR) NK(D.api.Recv(D.recvR, (size_t)nRecvR * 20, ncclFloat32, D.rank + 1, D.comm, stream));
+    }
+    NK(D.api.GroupEnd());
+    if (nRecvL) { k_unpack<<<(nRecvL + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, stream>>>(arrays, (const Record*)D.recvL, nRecvL, D.origin[0], invCell, (int)D.gdim[0], (int)D.colLo, (int)D.colHi, D.capacity, D.dCounters); launches += 1; }
+    if (nRecvR) { k_unpack<<<(nRecvR + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, stream>>>(arrays, (const Record*)D.recvR, nRecvR, D.origin[0], invCell, (int)D.gdim[0], (int)D.colLo, (int)D.colHi, D.capacity, D.dCounters); launches += 1; }
+    CK(cudaMemcpyAsync(D.hCounters, D.dCounters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    Arrays& A = arrays;
+    std::swap(A.pos, A.pos2); std::swap(A.vel, A.vel2); std::swap(A.dv, A.dv2); std::swap(A.nbar, A.nbar2);
+    std::swap(A.curv, A.curv2); std::swap(A.curvS, A.curvS2); std::swap(A.curvD, A.curvD2); std::swap(A.id, A.id2);
+    D.nLocal = D.hCounters[0];
+    D.bytesState += (uint64_t)(nSendL + nSendR) * sizeof(Record);
+    params.n = D.nLocal;
+    return VFD_OK;
+}
+
+// after the sort: where the ghost / edge / owned ranges of the local arrays lie; cross-checked with the neighbours
+int Solver::dist_read_ranges() {
+    Dist& D = *dist;
+    const bool hasL = D.rank > 0, hasR = D.rank + 1 < D.nranks;
+    const uint32_t T = D.gtiles[1] * D.gtiles[2];
+    const uint32_t t0 = params.tile0, t1 = params.tile1;
+    const uint32_t* cb = arrays.cellBegin;
+    uint32_t* h = D.hCounters + 8;
+    CK(cudaMemcpyAsync(h + 0, cb + (size_t)t0 * 64, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h + 1, cb + (size_t)(t0 + T) * 64, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h + 2, cb + (size_t)(t1 - T) * 64, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h + 3, cb + (size_t)t1 * 64, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    D.ownB = h[0]; D.edgeLEnd = h[1]; D.edgeRBegin = h[2]; D.ownE = h[3];
+    // my ghost ranges must be exactly my neighbours' edge columns: verify before the first halo message of the step
+    uint32_t* d = D.dCounters + 8;
+    const uint32_t mine[2] = { D.edgeLEnd - D.ownB, D.ownE - D.edgeRBegin };
+    CK(cudaMemcpyAsync(d, mine, 8, cudaMemcpyHostToDevice, stream));
+    NK(D.api.GroupStart());
+    if (hasL) { NK(D.api.Send(d + 0, 1, ncclUint32, D.rank - 1, D.comm, stream)); NK(D.api.Recv(d + 2, 1, ncclUint32, D.rank - 1, D.comm, stream)); }
+    if (hasR) { NK(D.api.Send(d + 1, 1, ncclUint32, D.rank + 1, D.comm, stream)); NK(D.api.Recv(d + 3, 1, ncclUint32, D.rank + 1, D.comm, stream)); }
+    NK(D.api.GroupEnd());
+    CK(cudaMemcpyAsync(h + 4, d + 2, 8, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const uint32_t ghostL = D.ownB, ghostR = D.nLocal - D.ownE;
+    if ((hasL && h[4] != ghostL) || (hasR && h[5] != ghostR) || (!hasL && ghostL) || (!hasR && ghostR)) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "rank %d: ghost ranges (%u, %u) do not match the neighbours' edge columns (%u, %u)", D.rank, ghostL, ghostR, hasL ? h[4] : 0u, hasR ? h[5] : 0u);
+        return fail(VFD_E_NCCL, buf);
+    }
+    return VFD_OK;
+}
+
+// halo of one per-particle array (elemFloats floats per particle)
+int Solver::dist_halo(void* base, uint32_t elemFloats) {
+    Dist& D = *dist;
+    const bool hasL = D.rank > 0, hasR = D.rank + 1 < D.nranks;
+    float* f = (float*)base;
+    const size_t e = elemFloats;
+    NK(D.api.GroupStart());
+    if (hasL) {
+        if (D.edgeLEnd > D.ownB) NK(D.api.Send(f + D.ownB * e, (D.edgeLEnd - D.ownB) * e, ncclFloat32, D.rank - 1, D.comm, stream));
+        if (D.ownB) NK(D.api.Recv(f, D.ownB * e, ncclFloat32, D.rank - 1, D.comm, stream));
+    }
+    if (hasR) {
+        if (D.ownE > D.edgeRBegin) NK(D.api.Send(f + D.edgeRBegin * e, (D.ownE - D.edgeRBegin) * e, ncclFloat32, D.rank + 1, D.comm, stream));
+        if (D.nLocal > D.ownE) NK(D.api.Recv(f + D.ownE * e, (D.nLocal - D.ownE) * e, ncclFloat32, D.rank + 1, D.comm, stream));
+    }
+    NK(D.api.GroupEnd());
+    D.halos += 1;
+    D.bytesHalo += (uint64_t)((D.edgeLEnd - D.ownB) * (hasL ? 1 : 0) + (D.ownE - D.edgeRBegin) * (hasR ? 1 : 0)) * e * 4;
+    return VFD_OK;
+}
+
+// combine the ranks' partial reduction results of one site and take the control decision on every rank
+int Solver::dist_reduce(int site, bool isMax) {
+    Dist& D = *dist;
+    NK(D.api.AllReduce(&dState->red[site * 2], &dState->red[site * 2], 2, ncclFloat64, isMax ? ncclMax : ncclSum, D.comm, stream));
+    k_control<<<1, 32, 0, stream>>>(params, dState, site);
+    launches += 1;
+    D.reductions += 1;
+    return VFD_OK;
+}
+
+int Solver::dist_get_owned(uint32_t capacity, uint32_t* count, uint32_t* ids, VfdParticle* out) {
+    CK(cudaSetDevice(device));
+    if (!dist) return fail(VFD_E_INVALID, "not distributed");
+    Dist& D = *dist;
+    const uint32_t n = D.ownE - D.ownB;
+    if (count) *count = n;
+    if (!ids || !out) return VFD_OK;
+    if (capacity < n) return fail(VFD_E_INVALID, "get_owned: capacity too small");
+    if (!n) return VFD_OK;
+    uint32_t* dIds = nullptr; VfdParticle* dOut = nullptr;
+    CK(cudaMalloc(&dIds, (size_t)n * 4)); CK(cudaMalloc(&dOut, (size_t)n * sizeof(VfdParticle)));
+    k_export_owned<<<(n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, stream>>>(params, arrays, D.ownB, D.ownE, dIds, dOut);
+    launches += 1;
+    cudaError_t e = cudaMemcpyAsync(ids, dIds, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dOut, (size_t)n * sizeof(VfdParticle), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(dIds); cudaFree(dOut);
+    if (e != cudaSuccess) return fail_cuda(e, "get_owned", __LINE__);
+    return VFD_OK;
+}
+
+Dist::~Dist() {
+    if (comm && api.CommDestroy) api.CommDestroy(comm);
+    cudaFree(sendL); cudaFree(sendR); cudaFree(recvL); cudaFree(recvR); cudaFree(dCounters);
+    if (hCounters) cudaFreeHost(hCounters);
+}
+
+} // namespace vfd

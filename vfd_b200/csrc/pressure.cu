@@ -325,12 +325,17 @@ void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays&
     LaunchScope ls(L, KID_DIV_SOURCE);
     k_source<true><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
 }
-void launch_divergence_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s1 = tile_smem_bytes<1, 1>(STAGE_CAP), s2 = tile_smem_bytes<1, 2>(STAGE_CAP);
+void launch_divergence_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const size_t s1 = tile_smem_bytes<1, 1>(STAGE_CAP);
     const uint32_t g1 = tile_grid(k_pressure_accel<ACC_DIV_ITER>, s1, L, TT_LUT);
-    { LaunchScope ls(L, KID_DIV_ACCEL); k_pressure_accel<ACC_DIV_ITER><<<g1, TT_LUT, s1, L.stream>>>(P, A, S, lutG); }
+    LaunchScope ls(L, KID_DIV_ACCEL);
+    k_pressure_accel<ACC_DIV_ITER><<<g1, TT_LUT, s1, L.stream>>>(P, A, S, lutG);
+}
+void launch_divergence_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const size_t s2 = tile_smem_bytes<1, 2>(STAGE_CAP);
     const uint32_t g2 = tile_grid(k_solve_iteration<true>, s2, L, TT_LUT);
-    { LaunchScope ls(L, KID_DIV_SOLVE); k_solve_iteration<true><<<g2, TT_LUT, s2, L.stream>>>(P, A, S, lutG); }
+    LaunchScope ls(L, KID_DIV_SOLVE);
+    k_solve_iteration<true><<<g2, TT_LUT, s2, L.stream>>>(P, A, S, lutG);
 }
 void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
     const size_t smem = tile_smem_bytes<1, 1>(STAGE_CAP);
@@ -344,12 +349,17 @@ void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A
     LaunchScope ls(L, KID_PRESS_SOURCE);
     k_source<false><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
 }
-void launch_pressure_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s1 = tile_smem_bytes<1, 1>(STAGE_CAP), s2 = tile_smem_bytes<1, 2>(STAGE_CAP);
+void launch_pressure_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const size_t s1 = tile_smem_bytes<1, 1>(STAGE_CAP);
     const uint32_t g1 = tile_grid(k_pressure_accel<ACC_PRESS_ITER>, s1, L, TT_LUT);
-    { LaunchScope ls(L, KID_PRESS_ACCEL); k_pressure_accel<ACC_PRESS_ITER><<<g1, TT_LUT, s1, L.stream>>>(P, A, S, lutG); }
+    LaunchScope ls(L, KID_PRESS_ACCEL);
+    k_pressure_accel<ACC_PRESS_ITER><<<g1, TT_LUT, s1, L.stream>>>(P, A, S, lutG);
+}
+void launch_pressure_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
+    const size_t s2 = tile_smem_bytes<1, 2>(STAGE_CAP);
     const uint32_t g2 = tile_grid(k_solve_iteration<false>, s2, L, TT_LUT);
-    { LaunchScope ls(L, KID_PRESS_SOLVE); k_solve_iteration<false><<<g2, TT_LUT, s2, L.stream>>>(P, A, S, lutG); }
+    LaunchScope ls(L, KID_PRESS_SOLVE);
+    k_solve_iteration<false><<<g2, TT_LUT, s2, L.stream>>>(P, A, S, lutG);
 }
 void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
     const size_t smem = tile_smem_bytes<1, 1>(STAGE_CAP);
@@ -359,16 +369,20 @@ void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A
 }
 void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A) {
     LaunchScope ls(L, KID_CLEAR_ACC);
-    k_clear_acc<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A);
+    k_clear_acc<<<std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB), VFD_TPB, 0, L.stream>>>(P, A);
 }
-void launch_cfl_and_velocity(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
-    const uint32_t tiles = (P.n + VFD_TPB - 1) / VFD_TPB;
-    { LaunchScope ls(L, KID_CFL); k_cfl<<<std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 8u)), VFD_TPB, 0, L.stream>>>(P, A, S); }
-    { LaunchScope ls(L, KID_VELOCITY); k_velocity<<<tiles, VFD_TPB, 0, L.stream>>>(P, A, S); }
+void launch_cfl(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    const uint32_t tiles = std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB);
+    LaunchScope ls(L, KID_CFL);
+    k_cfl<<<std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 8u)), VFD_TPB, 0, L.stream>>>(P, A, S);
+}
+void launch_velocity(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    LaunchScope ls(L, KID_VELOCITY);
+    k_velocity<<<std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB), VFD_TPB, 0, L.stream>>>(P, A, S);
 }
 void launch_positions(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     LaunchScope ls(L, KID_POSITION);
-    k_position<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, S);
+    k_position<<<std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB), VFD_TPB, 0, L.stream>>>(P, A, S);
 }
 
 } // namespace vfd

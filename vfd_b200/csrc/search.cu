@@ -260,9 +260,10 @@ __global__ void __launch_bounds__(TT_PLAIN) k_build_list(const __grid_constant__
 static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, uint32_t cellCapacity, uint32_t cellEstimate) {
-    const uint32_t nb = div_up(P.n, VFD_TPB);
-    const uint32_t gb = std::min<uint32_t>(nb, (uint32_t)L.numSMs * 8u);
-    { LaunchScope ls(L, KID_BOUNDS); k_bounds<<<gb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, cellCapacity); }
+    const uint32_t nb = std::max(1u, div_up(P.n, VFD_TPB));
+    const uint32_t gb = std::max(1u, std::min<uint32_t>(nb, (uint32_t)L.numSMs * 8u));
+    // several ranks: the grid is the fixed global one (distributed.cu); one GPU: derived from the particles' extent
+    if (P.nRanks == 1) { LaunchScope ls(L, KID_BOUNDS); k_bounds<<<gb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, cellCapacity); }
     { LaunchScope ls(L, KID_HIST); k_hist<<<nb, VFD_TPB, 0, L.stream>>>(P, A.pos, S, A.key, A.rank, A.cellCount); }
     const uint32_t est = std::min<uint64_t>((uint64_t)cellCapacity, std::max<uint64_t>(4ull * cellEstimate, 1u << 16));
     const uint32_t st = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(est, SCAN_TILE), (uint32_t)L.numSMs * 8u));

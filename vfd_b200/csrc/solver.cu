@@ -5,6 +5,7 @@
 // continue flag is polled with one batch of look-ahead).  Solver::simulate() is Simulate() (:33-61).
 #include "solver_impl.h"
 #include "tile.cuh"
+#include "control.cuh"
 #include <algorithm>
 #include <cstring>
 #include <limits.h>
@@ -54,7 +55,7 @@ __global__ void k_import_aos(Params P, Arrays A, const VfdParticle* __restrict__
 }
 
 // initial state: SetFluidObjects zero-fills everything but position and velocity (DFSPHImplementation.cu:198-220)
-__global__ void k_reset_state(Params P, Arrays A, const float4* __restrict__ pos0, const float4* __restrict__ vel0) {
+__global__ void k_reset_state(Params P, Arrays A, const float4* __restrict__ pos0, const float4* __restrict__ vel0, const uint32_t* __restrict__ ids0) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n) return;
     const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -62,7 +63,7 @@ __global__ void k_reset_state(Params P, Arrays A, const float4* __restrict__ pos
     A.acc[p] = z; A.pacc[p] = z; A.dv[p] = z; A.nrm[p] = z; A.nbar[p] = z;
     A.res[p] = 0.0f; A.rho[p] = 0.0f; A.rhoAdv[p] = 0.0f; A.kappa[p] = 0.0f; A.kappaV[p] = 0.0f; A.alpha[p] = 0.0f;
     A.curv[p] = 0.0f; A.curvS[p] = 0.0f; A.curvD[p] = 0.0f;
-    A.id[p] = p; A.cnt[p] = 0;
+    A.id[p] = ids0 ? ids0[p] : p; A.cnt[p] = 0;
     for (uint32_t b = 0; b < P.nBodies; b++) A.bx[b][p] = z;
 }
 
@@ -275,6 +276,7 @@ void Solver::refresh_params() {
     P.minDivIt = desc.MinDivergenceSolverIterations; P.maxDivIt = desc.MaxDivergenceSolverIterations;
     P.minViscIt = desc.MinViscositySolverIterations; P.maxViscIt = desc.MaxViscositySolverIterations;
     P.searchFma = optSearchFma;
+    if (dist) dist_params(P);
 }
 
 template<typename T> static cudaError_t dalloc(T*& p, size_t count) { return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
@@ -285,6 +287,7 @@ void Solver::free_particles() {
                      A.posRho, A.acc, A.pacc, A.nrm, A.res, A.rho, A.rhoAdv, A.kappa, A.kappaV, A.alpha, A.cgG, A.cgR, A.cgP, A.cgQ, A.cgZ, A.minv,
                      A.cnt, A.list16, A.coef, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.partials, dPos0, dVel0 };
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (dIds0) { cudaFree(dIds0); dIds0 = nullptr; }
     for (int b = 0; b < VFD_MAX_BODIES; b++) { if (A.bx[b]) cudaFree(A.bx[b]); if (A.bcoef[b]) cudaFree(A.bcoef[b]); }
     memset(&A, 0, sizeof A);
     dPos0 = dVel0 = nullptr;
@@ -294,9 +297,10 @@ void Solver::free_particles() {
 int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxMax) {
     free_particles();
     Arrays& A = arrays;
-    const size_t np = ((size_t)n + 31) / 32 * 32;
+    const size_t np = ((size_t)(dist ? std::max(dist->capacity, n) : n) + 31) / 32 * 32;
     float4** f4s[] = { &A.pos, &A.vel, &A.dv, &A.nbar, &A.pos2, &A.vel2, &A.dv2, &A.nbar2, &A.posRho, &A.acc, &A.pacc, &A.nrm,
                        &A.cgG, &A.cgR, &A.cgP, &A.cgQ, &A.cgZ, &dPos0, &dVel0 };
+    CK(dalloc(dIds0, np));
     for (float4** p : f4s) { CK(dalloc(*p, np)); allocBytes += np * 16; }
     float** f1s[] = { &A.curv, &A.curvS, &A.curvD, &A.curv2, &A.curvS2, &A.curvD2, &A.res, &A.rho, &A.rhoAdv, &A.kappa, &A.kappaV, &A.alpha };
     for (float** p : f1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
@@ -311,6 +315,12 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
     for (int k = 0; k < 3; k++) cells0 *= std::ceil((double)(bboxMax[k] - bboxMin[k]) / info.SupportRadius) + 9.0;
     cellEstimate = (uint32_t)std::min<double>(cells0, (double)optMaxCells);
     cellCapacity = (uint32_t)std::min<double>(std::max<double>(64.0 * cells0, (double)(1u << 20)), (double)optMaxCells);
+    if (dist) {
+        // fixed local grid: owned tile columns + ghost columns
+        DevState g; memset(&g, 0, sizeof g);
+        dist_apply_grid(g);
+        cellEstimate = g.nCells; cellCapacity = g.nCells + 64;
+    }
     CK(dalloc(A.cellCount, (size_t)cellCapacity + 4)); CK(dalloc(A.cellBegin, (size_t)cellCapacity + 4));
     CK(cudaMemset(A.cellCount, 0, ((size_t)cellCapacity + 4) * 4));
     CK(cudaMemset(A.cellBegin, 0, ((size_t)cellCapacity + 4) * 4));
@@ -357,6 +367,44 @@ int Solver::set_particles(const float* pos, const float* vel, uint32_t n, bool o
     return begin();
 }
 
+// Distributed variant: this rank's particles (those inside its slab), their global ids, the global particle count and
+// the number of particle slots to allocate (owned + ghosts + head room for migration).
+int Solver::dist_set_particles(const float* pos, const float* vel, const uint32_t* ids, uint32_t n, uint32_t nGlobal, uint32_t capacity) {
+    CK(cudaSetDevice(device));
+    if (!dist) return fail(VFD_E_INVALID, "set_particles_distributed needs init_distributed first");
+    if ((!pos || !ids) && n) return fail(VFD_E_INVALID, "set_particles_distributed: null positions / ids");
+    Dist& D = *dist;
+    D.nGlobal = nGlobal;
+    D.capacity = std::max<uint32_t>(capacity, n + 1024u);
+    // one tile column of ghosts per side + the migrants of a step
+    const uint64_t column = (uint64_t)D.gtiles[1] * D.gtiles[2] * 64ull * 24ull;      // 24 particles per cell is twice the rest density
+    D.haloCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(column, 1u << 16), (uint64_t)D.capacity);
+    cudaFree(D.sendL); cudaFree(D.sendR); cudaFree(D.recvL); cudaFree(D.recvR);
+    D.sendL = D.sendR = D.recvL = D.recvR = nullptr;
+    CK(cudaMalloc(&D.sendL, (size_t)D.haloCap * 80)); CK(cudaMalloc(&D.sendR, (size_t)D.haloCap * 80));
+    CK(cudaMalloc(&D.recvL, (size_t)D.haloCap * 80)); CK(cudaMalloc(&D.recvR, (size_t)D.haloCap * 80));
+    state = VFD_STATE_NONE;
+    info.ParticleCount = n;
+    frames.clear();
+    began = false;
+    float bmin[3] = { 0, 0, 0 }, bmax[3] = { 1, 1, 1 };
+    int rc = alloc_particles(n, bmin, bmax);
+    if (rc) return rc;
+    // rigid-body sample arrays are sized with the particle arrays
+    if (n) {
+        float *dPos = nullptr, *dVel = nullptr;
+        CK(cudaMalloc(&dPos, (size_t)12 * n));
+        CK(cudaMemcpyAsync(dPos, pos, (size_t)12 * n, cudaMemcpyHostToDevice, stream));
+        if (vel) { CK(cudaMalloc(&dVel, (size_t)12 * n)); CK(cudaMemcpyAsync(dVel, vel, (size_t)12 * n, cudaMemcpyHostToDevice, stream)); }
+        CK(cudaMemcpyAsync(dIds0, ids, (size_t)4 * n, cudaMemcpyHostToDevice, stream));
+        k_pack_posvel<<<nblk(n), VFD_TPB, 0, stream>>>(n, dPos, dVel, dPos0, dVel0);
+        launches += 1;
+        CK(cudaStreamSynchronize(stream));
+        cudaFree(dPos); if (dVel) cudaFree(dVel);
+    }
+    return begin();
+}
+
 void Solver::free_bodies() {
     for (auto& p : bodyAllocs) cudaFree(p);
     bodyAllocs.clear();
@@ -387,12 +435,12 @@ int Solver::set_rigid_bodies(uint32_t count, const VfdVolumeMap* maps) {
         d.nodes = dn; d.cells = dc; d.cellMap = dm;
     }
     // per-body boundary sample arrays are sized by the particle count (RigidBody.cu:13-16): particles first
-    const size_t np = ((size_t)info.ParticleCount + 31) / 32 * 32;
+    const size_t np = ((size_t)(dist ? std::max(dist->capacity, info.ParticleCount) : info.ParticleCount) + 31) / 32 * 32;
     for (int b = 0; b < VFD_MAX_BODIES; b++) {
         if (arrays.bx[b]) { cudaFree(arrays.bx[b]); arrays.bx[b] = nullptr; }
         if (arrays.bcoef[b]) { cudaFree(arrays.bcoef[b]); arrays.bcoef[b] = nullptr; }
     }
-    for (uint32_t b = 0; b < count && info.ParticleCount; b++) {
+    for (uint32_t b = 0; b < count && (info.ParticleCount || dist); b++) {
         CK(dalloc(arrays.bx[b], np)); CK(cudaMemset(arrays.bx[b], 0, np * 16));
         CK(dalloc(arrays.bcoef[b], np)); CK(cudaMemset(arrays.bcoef[b], 0, np * 16));
     }
@@ -404,9 +452,10 @@ int Solver::set_rigid_bodies(uint32_t count, const VfdVolumeMap* maps) {
 // What Simulate() does before its loop (DFSPHImplementation.cu:36-51)
 int Solver::begin() {
     CK(cudaSetDevice(device));
-    if (info.ParticleCount == 0) { began = true; return VFD_OK; }
+    if (info.ParticleCount == 0 && !dist) { began = true; return VFD_OK; }
+    if (dist) { dist->nLocal = info.ParticleCount; dist->ownB = 0; dist->ownE = info.ParticleCount; dist->edgeLEnd = 0; dist->edgeRBegin = info.ParticleCount; }
     refresh_params();
-    k_reset_state<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dPos0, dVel0);
+    k_reset_state<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dPos0, dVel0, dist ? dIds0 : nullptr);
     launches += 1;
     DevState s;
     memset(&s, 0, sizeof s);
@@ -415,6 +464,7 @@ int Solver::begin() {
     s.sampleCount = info.SurfaceTensionSampleCount; s.mcFactor = info.MonteCarloFactor;
     for (int k = 0; k < 3; k++) { s.boundsMin[k] = INT_MAX; s.boundsMax[k] = INT_MIN; s.gridDim[k] = 4; s.tileDim[k] = 1; }
     s.nCells = 64; s.nTiles = 1;
+    if (dist) dist_apply_grid(s);
     hState[0] = s;
     CK(cudaMemcpyAsync(dState, &hState[0], sizeof(DevState), cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
@@ -441,11 +491,11 @@ int Solver::read_state(DevState& out) {
 }
 
 // polls a device flag with one batch of look-ahead; returns true if the loop may stop
-int Solver::run_polled_loop(uint32_t maxIt, uint32_t already, int batch, uint32_t* dFlag, const std::function<void()>& enqueueIteration, uint32_t continueValue) {
+int Solver::run_polled_loop(uint32_t maxIt, uint32_t already, int batch, uint32_t* dFlag, const std::function<int()>& enqueueIteration, uint32_t continueValue) {
     uint32_t issued = already;
     int slot = 0, pending = -1;
     while (issued < maxIt) {
-        for (int b = 0; b < batch && issued < maxIt; b++, issued++) enqueueIteration();
+        for (int b = 0; b < batch && issued < maxIt; b++, issued++) { int rc = enqueueIteration(); if (rc) return rc; }
         CK(cudaMemcpyAsync(&hFlags[slot], dFlag, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CK(cudaEventRecord(pollEvent[slot], stream));
         if (pending >= 0) {
@@ -470,10 +520,14 @@ int Solver::search_only() {
     return VFD_OK;
 }
 
+#define RC(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
+
 int Solver::step() {
     CK(cudaSetDevice(device));
     if (!began) { int rc = begin(); if (rc) return rc; }
-    if (info.ParticleCount == 0) return VFD_OK;        // DFSPHImplementation.cu:65-67
+    if (info.ParticleCount == 0 && !dist) return VFD_OK;        // DFSPHImplementation.cu:65-67
+    // several ranks: particles that left the slab migrate, the ghost copies of the neighbours' edge columns are renewed
+    if (dist) RC(dist_exchange_state());
     refresh_params();
     const Params& P = params;
     Arrays& A = arrays;
@@ -484,53 +538,86 @@ int Solver::step() {
     // 1. neighbourhood search (:71)
     launch_search(L, P, A, dState, cellCapacity, cellEstimate);
     searched = true;
+    if (dist) RC(dist_read_ranges());
     if (T) cudaEventRecord(phaseEvent[1], stream);
 
     // 2. boundary samples, density, factor (:79-104); a = g (:112) is fused into the density pass
     launch_boundary(L, P, A, bodies);
     launch_density_factor(L, P, A, dState, dLutW, dLutG);
+    RC(halo4(A.posRho));
     if (T) cudaEventRecord(phaseEvent[2], stream);
 
     // 3. divergence-free solve (:108, :506-575)
     if (desc.EnableDivergenceSolverError) {
         launch_divergence_source(L, P, A, dState, dLutG);
+        RC(halo1(A.kappaV));
+        auto iteration = [&]() -> int {
+            launch_divergence_accel(L, P, A, dState, dLutG);
+            RC(halo4(A.pacc));
+            launch_divergence_solve(L, P, A, dState, dLutG);
+            RC(reduce(SITE_DIV));
+            RC(halo1(A.kappaV));
+            return VFD_OK;
+        };
         const uint32_t fixed = std::min(P.minDivIt, P.maxDivIt);
-        for (uint32_t i = 0; i < fixed; i++) launch_divergence_iteration(L, P, A, dState, dLutG);
-        if (fixed > 0 && fixed < P.maxDivIt) {
-            int rc = run_polled_loop(P.maxDivIt, fixed, 2, &dState->divActive, [&] { launch_divergence_iteration(L, P, A, dState, dLutG); }, 1u);
-            if (rc) return rc;
-        }
+        for (uint32_t i = 0; i < fixed; i++) RC(iteration());
+        if (fixed > 0 && fixed < P.maxDivIt) RC(run_polled_loop(P.maxDivIt, fixed, 2, &dState->divActive, iteration, 1u));
         launch_divergence_finish(L, P, A, dState, dLutG);
     }
     if (T) cudaEventRecord(phaseEvent[3], stream);
 
     // 5. surface tension (:119, :810-839)
-    if (desc.EnableSurfaceTensionSolver) launch_surface_tension(L, P, A, dState, dHalton, desc.SurfaceTensionSmoothPassCount);
+    if (desc.EnableSurfaceTensionSolver) {
+        launch_st_classify(L, P, A, dState, dHalton);
+        RC(halo4(A.nrm));
+        launch_st_smooth(L, P, A, dState);
+        for (uint32_t i = 0; i < desc.SurfaceTensionSmoothPassCount; i++) launch_st_apply(L, P, A);
+    }
     if (T) cudaEventRecord(phaseEvent[4], stream);
 
     // 6. implicit viscosity (:123, :577-808)
     if (desc.EnableViscositySolver) {
         launch_viscosity_setup(L, P, A, dState, dLutG);
-        if (P.minViscIt == 0 && P.maxViscIt > 0) {
-            int rc = run_polled_loop(P.maxViscIt, 0, 4, &dState->viscActive, [&] { launch_viscosity_iteration(L, P, A, dState, dLutG); }, 1u);
-            if (rc) return rc;
-        }
+        RC(reduce(SITE_VISC_BB));
+        RC(halo4(A.cgG));
+        launch_viscosity_matvec(L, P, A, dState, true);
+        RC(reduce(SITE_VISC_INIT));
+        RC(halo4(A.cgP));
+        auto iteration = [&]() -> int {
+            launch_viscosity_matvec(L, P, A, dState, false);
+            RC(reduce(SITE_VISC_PQ));
+            launch_viscosity_update(L, P, A, dState);
+            RC(reduce(SITE_VISC_UPDATE));
+            launch_viscosity_direction(L, P, A, dState);
+            RC(halo4(A.cgP));
+            return VFD_OK;
+        };
+        if (P.minViscIt == 0 && P.maxViscIt > 0) RC(run_polled_loop(P.maxViscIt, 0, 4, &dState->viscActive, iteration, 1u));
         launch_viscosity_apply(L, P, A, dState);
     }
     if (T) cudaEventRecord(phaseEvent[5], stream);
 
     // 7.-8. CFL time step, v += dt a (:127-130)
-    launch_cfl_and_velocity(L, P, A, dState);
+    launch_cfl(L, P, A, dState);
+    RC(reduce(SITE_CFL, true));
+    launch_velocity(L, P, A, dState);
+    RC(halo4(A.vel));
 
     // 9. constant-density solve (:137, :443-504)
     launch_pressure_source(L, P, A, dState, dLutG);
+    RC(halo1(A.kappa));
     {
+        auto iteration = [&]() -> int {
+            launch_pressure_accel(L, P, A, dState, dLutG);
+            RC(halo4(A.pacc));
+            launch_pressure_solve(L, P, A, dState, dLutG);
+            RC(reduce(SITE_PRESS));
+            RC(halo1(A.kappa));
+            return VFD_OK;
+        };
         const uint32_t fixed = std::min(P.minPressIt, P.maxPressIt);
-        for (uint32_t i = 0; i < fixed; i++) launch_pressure_iteration(L, P, A, dState, dLutG);
-        if (fixed > 0 && fixed < P.maxPressIt) {
-            int rc = run_polled_loop(P.maxPressIt, fixed, 2, &dState->pressActive, [&] { launch_pressure_iteration(L, P, A, dState, dLutG); }, 1u);
-            if (rc) return rc;
-        }
+        for (uint32_t i = 0; i < fixed; i++) RC(iteration());
+        if (fixed > 0 && fixed < P.maxPressIt) RC(run_polled_loop(P.maxPressIt, fixed, 2, &dState->pressActive, iteration, 1u));
         launch_pressure_finish(L, P, A, dState, dLutG);
     }
     if (T) cudaEventRecord(phaseEvent[6], stream);
@@ -632,6 +719,7 @@ int Solver::sync_debug() {
 
 int Solver::get_particles(VfdParticle* out) {
     CK(cudaSetDevice(device));
+    if (dist) return fail(VFD_E_INVALID, "original-order dumps are single-GPU calls: use get_owned on each rank");
     if (!out) return fail(VFD_E_INVALID, "null output");
     if (info.ParticleCount == 0) return VFD_OK;
     VfdParticle* d = nullptr;
@@ -648,6 +736,7 @@ int Solver::get_particles(VfdParticle* out) {
 
 int Solver::set_particles_full(const VfdParticle* in) {
     CK(cudaSetDevice(device));
+    if (dist) return fail(VFD_E_INVALID, "original-order dumps are single-GPU calls: use get_owned on each rank");
     if (!in) return fail(VFD_E_INVALID, "null input");
     if (!began) { int rc = begin(); if (rc) return rc; }
     if (info.ParticleCount == 0) return VFD_OK;
@@ -684,6 +773,7 @@ int Solver::set_st_state(uint32_t sampleCount, float mcFactor) {
 
 int Solver::get_current_frame(VfdParticleSimple* out) {
     CK(cudaSetDevice(device));
+    if (dist) return fail(VFD_E_INVALID, "original-order dumps are single-GPU calls: use get_owned on each rank");
     if (!out) return fail(VFD_E_INVALID, "null output");
     if (info.ParticleCount == 0) return VFD_OK;
     if (!dFrame) CK(cudaMalloc(&dFrame, (size_t)info.ParticleCount * sizeof(VfdParticleSimple)));
@@ -697,6 +787,7 @@ int Solver::get_current_frame(VfdParticleSimple* out) {
 
 int Solver::get_neighbors(uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t capacity, uint64_t* total) {
     CK(cudaSetDevice(device));
+    if (dist) return fail(VFD_E_INVALID, "original-order dumps are single-GPU calls: use get_owned on each rank");
     const uint32_t n = info.ParticleCount;
     if (!searched) return fail(VFD_E_INVALID, "get_neighbors: no neighbour search has run on the current state");
     uint32_t *dC = nullptr, *dI = nullptr;
@@ -729,6 +820,7 @@ int Solver::get_neighbors(uint32_t* counts, uint32_t* offsets, uint32_t* ids, ui
 
 int Solver::get_boundary(uint32_t body, float* xj, float* vol) {
     CK(cudaSetDevice(device));
+    if (dist) return fail(VFD_E_INVALID, "original-order dumps are single-GPU calls: use get_owned on each rank");
     if (body >= info.RigidBodyCount) return fail(VFD_E_INVALID, "body index out of range");
     const uint32_t n = info.ParticleCount;
     float *dX = nullptr, *dV = nullptr;

@@ -102,19 +102,25 @@ void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, 
 void launch_boundary(const LaunchCfg& L, const Params& P, const Arrays& A, const BodySet& B);
 void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutW, const float* lutG);
 void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
-void launch_divergence_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_divergence_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_divergence_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
 void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
 void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
-void launch_pressure_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_pressure_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_pressure_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
 void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
 void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A);
-void launch_cfl_and_velocity(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
+void launch_cfl(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
+void launch_velocity(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
 void launch_positions(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
-void launch_surface_tension(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* halton, uint32_t passes);
+void launch_st_classify(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* halton);
+void launch_st_smooth(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
+void launch_st_apply(const LaunchCfg& L, const Params& P, const Arrays& A);
 void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
-void launch_viscosity_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
+void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init);
+void launch_viscosity_update(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
+void launch_viscosity_direction(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
 void launch_viscosity_apply(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
-void launch_reset_solver_state(const LaunchCfg& L, DevState* S, int which);   // 0 div, 1 press, 2 visc
 
 // dump / restore helpers (original particle order <-> sorted SoA)
 void launch_export_aos(const LaunchCfg& L, const Params& P, const Arrays& A, VfdParticle* dOut);

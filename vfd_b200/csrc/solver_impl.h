@@ -2,8 +2,45 @@
 #pragma once
 #include "solver.h"
 #include <functional>
+#include <memory>
+
+#include <nccl.h>     // types only: the entry points are resolved at run time (no link-time dependency)
 
 namespace vfd {
+
+// NCCL entry points resolved with dlopen/dlsym (distributed.cu)
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    bool load(std::string& err);
+};
+
+// state of the slab decomposition (distributed.cu)
+struct Dist {
+    int rank = 0, nranks = 1;
+    NcclApi api;
+    ncclComm_t comm = nullptr;
+    float origin[3] = {};                 // global grid
+    uint32_t gdim[3] = {}, gtiles[3] = {};
+    uint32_t colLo = 0, colHi = 0;        // owned tile columns (global)
+    uint32_t capacity = 0, haloCap = 0;   // particle slots, records per exchange buffer
+    uint32_t nGlobal = 0, nLocal = 0;
+    uint32_t ownB = 0, edgeLEnd = 0, edgeRBegin = 0, ownE = 0;   // [ghost L | first col | ... | last col | ghost R] boundaries
+    void *sendL = nullptr, *sendR = nullptr, *recvL = nullptr, *recvR = nullptr;
+    uint32_t* dCounters = nullptr; uint32_t* hCounters = nullptr;
+    uint64_t halos = 0, reductions = 0, bytesHalo = 0, bytesState = 0;
+    ~Dist();
+};
+
+int dist_unique_id(char* out128, std::string& err);
 
 struct Frame { std::vector<VfdParticleSimple> data; float maxVel2; float dt; };
 
@@ -28,6 +65,13 @@ public:
     int get_neighbors(uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t capacity, uint64_t* total);
     int get_boundary(uint32_t body, float* xj, float* vol);
     int get_bounds(float* bmin, float* bmax);
+    // slab decomposition over several ranks (distributed.cu)
+    int dist_init(int rank, int nranks, const char* id128, const float* dmin, const float* dmax);
+    int dist_get_grid(float* origin3, float* cellSize, uint32_t* tiles3);
+    int dist_set_slab(uint32_t colLo, uint32_t colHi);
+    int dist_set_particles(const float* pos, const float* vel, const uint32_t* ids, uint32_t n, uint32_t nGlobal, uint32_t capacity);
+    int dist_get_owned(uint32_t capacity, uint32_t* count, uint32_t* ids, VfdParticle* out);
+    std::unique_ptr<Dist> dist;
     int record_event(uint32_t slot);
     int elapsed_ms(uint32_t from, uint32_t to, float* ms);
     int fail(int code, const std::string& msg);
@@ -61,7 +105,16 @@ private:
     int read_state(DevState& out);
     void update_debug(const DevState& s, bool timers);
     int capture_frame(const DevState& s);
-    int run_polled_loop(uint32_t maxIt, uint32_t already, int batch, uint32_t* dFlag, const std::function<void()>& enqueueIteration, uint32_t continueValue);
+    void dist_apply_grid(DevState& s);
+    void dist_params(Params& P) const;
+    int dist_exchange_state();
+    int dist_read_ranges();
+    int dist_halo(void* base, uint32_t elemFloats);
+    int dist_reduce(int site, bool isMax);
+    int halo4(float4* a) { return dist ? dist_halo(a, 4) : VFD_OK; }
+    int halo1(float* a) { return dist ? dist_halo(a, 1) : VFD_OK; }
+    int reduce(int site, bool isMax = false) { return dist ? dist_reduce(site, isMax) : VFD_OK; }
+    int run_polled_loop(uint32_t maxIt, uint32_t already, int batch, uint32_t* dFlag, const std::function<int()>& enqueueIteration, uint32_t continueValue);
 
     int numSMs = 148;
     cudaStream_t stream = nullptr;
@@ -76,6 +129,7 @@ private:
     BodySet bodies{};
     std::vector<void*> bodyAllocs;
     float4 *dPos0 = nullptr, *dVel0 = nullptr;
+    uint32_t* dIds0 = nullptr;
     VfdParticleSimple* dFrame = nullptr;
     uint32_t cellEstimate = 27, cellCapacity = 0;
     bool began = false, searched = false;

@@ -142,20 +142,31 @@ __global__ void __launch_bounds__(VFD_TPB) k_st_apply(Params P, Arrays A) {
     }
 }
 
-void launch_surface_tension(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* halton, uint32_t passes) {
-    const uint32_t tiles = (P.n + VFD_TPB - 1) / VFD_TPB;
-    const size_t s1 = tile_smem_bytes<0, 1>(STAGE_CAP), s2 = tile_smem_bytes<0, 2>(STAGE_CAP);
-    static thread_local int per1 = 0, per2 = 0;
-    if (!per1) {
+static void st_config(int& per1, int& per2, size_t& s1, size_t& s2) {
+    s1 = tile_smem_bytes<0, 1>(STAGE_CAP); s2 = tile_smem_bytes<0, 2>(STAGE_CAP);
+    static thread_local int p1 = 0, p2 = 0;
+    if (!p1) {
         cudaFuncSetAttribute(k_st_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
         cudaFuncSetAttribute(k_st_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per1, k_st_classify, TT_PLAIN, s1);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_st_smooth, TT_PLAIN, s2);
-        per1 = std::max(per1, 1); per2 = std::max(per2, 1);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, k_st_classify, TT_PLAIN, s1);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, k_st_smooth, TT_PLAIN, s2);
+        p1 = std::max(p1, 1); p2 = std::max(p2, 1);
     }
-    { LaunchScope ls(L, KID_ST_CLASSIFY); k_st_classify<<<per1 * L.numSMs, TT_PLAIN, s1, L.stream>>>(P, A, S, halton); }
-    { LaunchScope ls(L, KID_ST_SMOOTH); k_st_smooth<<<per2 * L.numSMs, TT_PLAIN, s2, L.stream>>>(P, A, S); }
-    for (uint32_t i = 0; i < passes; i++) { LaunchScope ls(L, KID_ST_APPLY); k_st_apply<<<tiles, VFD_TPB, 0, L.stream>>>(P, A); }
+    per1 = p1; per2 = p2;
+}
+void launch_st_classify(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* halton) {
+    int per1, per2; size_t s1, s2; st_config(per1, per2, s1, s2);
+    LaunchScope ls(L, KID_ST_CLASSIFY);
+    k_st_classify<<<per1 * L.numSMs, TT_PLAIN, s1, L.stream>>>(P, A, S, halton);
+}
+void launch_st_smooth(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    int per1, per2; size_t s1, s2; st_config(per1, per2, s1, s2);
+    LaunchScope ls(L, KID_ST_SMOOTH);
+    k_st_smooth<<<per2 * L.numSMs, TT_PLAIN, s2, L.stream>>>(P, A, S);
+}
+void launch_st_apply(const LaunchCfg& L, const Params& P, const Arrays& A) {
+    LaunchScope ls(L, KID_ST_APPLY);
+    k_st_apply<<<std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB), VFD_TPB, 0, L.stream>>>(P, A);
 }
 
 } // namespace vfd

@@ -40,14 +40,15 @@ namespace vfd {
 __device__ __forceinline__ float cell_inv(float h) { return (1.0f / h) * (1.0f - 1.0f / 1024.0f); }
 
 __device__ __forceinline__ uint3 cell_of(float4 x, const DevState* S, float invCell) {
-    uint3 c;
-    c.x = (uint32_t)((x.x - S->gridOrigin[0]) * invCell);
-    c.y = (uint32_t)((x.y - S->gridOrigin[1]) * invCell);
-    c.z = (uint32_t)((x.z - S->gridOrigin[2]) * invCell);
+    // global cell (identical on every rank that holds a copy of the particle), then the local grid's offset
+    int cx = (int)((x.x - S->gridOrigin[0]) * invCell) - S->cellOffset[0];
+    int cy = (int)((x.y - S->gridOrigin[1]) * invCell) - S->cellOffset[1];
+    int cz = (int)((x.z - S->gridOrigin[2]) * invCell) - S->cellOffset[2];
     // robustness against NaN / escaped particles: clamp into the padded interior
-    c.x = min(max(c.x, 1u), S->gridDim[0] - 2u);
-    c.y = min(max(c.y, 1u), S->gridDim[1] - 2u);
-    c.z = min(max(c.z, 1u), S->gridDim[2] - 2u);
+    uint3 c;
+    c.x = (uint32_t)min(max(cx, 1), (int)S->gridDim[0] - 2);
+    c.y = (uint32_t)min(max(cy, 1), (int)S->gridDim[1] - 2);
+    c.z = (uint32_t)min(max(cz, 1), (int)S->gridDim[2] - 2);
     return c;
 }
 

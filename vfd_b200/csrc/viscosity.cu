@@ -310,24 +310,36 @@ static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L, int thread
 }
 
 void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s0 = tile_smem_bytes<1, 1>(STAGE_CAP), s1 = tile_smem_bytes<0, 2>(STAGE_CAP);
+    const size_t s0 = tile_smem_bytes<1, 1>(STAGE_CAP);
     const uint32_t g0 = tile_grid(k_visc_setup, s0, L, TT_LUT);
-    { LaunchScope ls(L, KID_VISC_SETUP); k_visc_setup<<<g0, TT_LUT, s0, L.stream>>>(P, A, S, lutG); }
-    const uint32_t g1 = tile_grid(k_visc_matvec<true>, s1, L, TT_MATVEC);
-    { LaunchScope ls(L, KID_VISC_MATVEC0); k_visc_matvec<true><<<g1, TT_MATVEC, s1, L.stream>>>(P, A, S); }
+    LaunchScope ls(L, KID_VISC_SETUP);
+    k_visc_setup<<<g0, TT_LUT, s0, L.stream>>>(P, A, S, lutG);
 }
-void launch_viscosity_iteration(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
+void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init) {
     const size_t s1 = tile_smem_bytes<0, 2>(STAGE_CAP);
-    const uint32_t g1 = tile_grid(k_visc_matvec<false>, s1, L, TT_MATVEC);
-    { LaunchScope ls(L, KID_VISC_MATVEC); k_visc_matvec<false><<<g1, TT_MATVEC, s1, L.stream>>>(P, A, S); }
-    const uint32_t tiles = (P.n + VFD_TPB - 1) / VFD_TPB;
+    if (init) {
+        const uint32_t g1 = tile_grid(k_visc_matvec<true>, s1, L, TT_MATVEC);
+        LaunchScope ls(L, KID_VISC_MATVEC0);
+        k_visc_matvec<true><<<g1, TT_MATVEC, s1, L.stream>>>(P, A, S);
+    } else {
+        const uint32_t g1 = tile_grid(k_visc_matvec<false>, s1, L, TT_MATVEC);
+        LaunchScope ls(L, KID_VISC_MATVEC);
+        k_visc_matvec<false><<<g1, TT_MATVEC, s1, L.stream>>>(P, A, S);
+    }
+}
+void launch_viscosity_update(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    const uint32_t tiles = std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB);
     const uint32_t g2 = std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 8u));
-    { LaunchScope ls(L, KID_VISC_UPDATE); k_visc_update<<<g2, VFD_TPB, 0, L.stream>>>(P, A, S); }
-    { LaunchScope ls(L, KID_VISC_DIRECTION); k_visc_direction<<<tiles, VFD_TPB, 0, L.stream>>>(P, A, S); }
+    LaunchScope ls(L, KID_VISC_UPDATE);
+    k_visc_update<<<g2, VFD_TPB, 0, L.stream>>>(P, A, S);
+}
+void launch_viscosity_direction(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    LaunchScope ls(L, KID_VISC_DIRECTION);
+    k_visc_direction<<<std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB), VFD_TPB, 0, L.stream>>>(P, A, S);
 }
 void launch_viscosity_apply(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     LaunchScope ls(L, KID_VISC_APPLY);
-    k_visc_apply<<<(P.n + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, L.stream>>>(P, A, S);
+    k_visc_apply<<<std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB), VFD_TPB, 0, L.stream>>>(P, A, S);
 }
 
 } // namespace vfd
