@@ -92,7 +92,12 @@ __global__ void __launch_bounds__(VFD_TPB) k_unpack(Arrays A, const Record* __re
 }
 
 __global__ void k_control(Params P, DevState* S, int site) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) control_site(site, P, S, &S->red[site * 2]);
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // iterations enqueued beyond convergence are no-ops in the kernels; their (stale) reduction must not be acted upon
+    if ((site == SITE_VISC_PQ || site == SITE_VISC_UPDATE) && S->viscActive != 1u) return;
+    if (site == SITE_DIV && !S->divActive) return;
+    if (site == SITE_PRESS && !S->pressActive) return;
+    control_site(site, P, S, &S->red[site * 2]);
 }
 
 // owned particles in local order, with their persistent ids (frame / dump gathering on the host)
