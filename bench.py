@@ -109,22 +109,58 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def settled_state_on_gpu(args, local):
+    """Scene preparation shared by both arms: the settled dam-break state (BASELINE.json config 3 after `--settle`
+    steps).  200 steps of a 1M-particle scene take minutes on host cores (the PCG runs 100 iterations per step while
+    the block is at rest on the floor), so the state the reference arm is TIMED on is prepared, untimed, on the GPU."""
+    from vfd_b200 import api, build
+    build.build()
+    pos, box, res = scene(args.side)
+    vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R, device=local)
+    sim = api.DFSPHSimulation(description(api.DFSPHSimulationDescription), device=local)
+    sim.SetFluidObjects([api.FluidObject(pos)])
+    sim.SetRigidBodies([vm])
+    sim.steps(args.settle)
+    sim.synchronize()
+    state = sim.particles()
+    info = sim.GetInfo()
+    out = (state, info.TimeStepSize, (info.SurfaceTensionSampleCount, info.MonteCarloFactor), pos, box, res)
+    sim.close()
+    return out
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own solver sources on the host cores (oracle/_ref/libvfd_ref_cpu.so)."""
+    """--impl reference: the reference's own solver sources (oracle/_ref/libvfd_ref_cpu.so, built by oracle/build_ref.py
+    from /root/reference) on all host cores, timed on the arm's workload: K steps of the settled 1M-particle state.
+    Nothing of vfd_b200 runs inside the timed region."""
     if rank != 0:
         return 0
     from oracle import refsim
-    side = args.ref_side
-    from vfd_b200 import api
-    pos, box, res = scene(side)
     threads = os.cpu_count() or 1
     desc = description(refsim.Desc)
+    prepared = None
+    try:
+        prepared = settled_state_on_gpu(args, int(os.environ.get("LOCAL_RANK", "0")))
+    except Exception as ex:          # no GPU / no library: settle a smaller scene on the host cores instead
+        print("reference arm: GPU scene preparation unavailable (%r); settling %d^3 on the CPU" % (ex, args.ref_side), file=sys.stderr)
     with refsim.quiet_stdout():
         sim = refsim.RefSim(desc, threads=threads)
+        if prepared is not None:
+            state, dt0, st0, pos, box, res = prepared
+            side, how = args.side, "state after %d settle steps prepared untimed by vfd_b200 on cuda (CPU settling takes minutes)" % args.settle
+        else:
+            side = args.ref_side
+            pos, box, res = scene(side)
+            how = "%d settle steps on the CPU" % args.ref_settle
         sim.set_particles(pos)
         sim.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
         sim.commit_bodies()
-        sim.step(args.ref_settle)
+        if prepared is not None:
+            sim.set_particles_full(state)
+            sim.set_time_step(dt0)
+            sim.set_st_state(*st0)
+        else:
+            sim.step(args.ref_settle)
         sim.step(args.warmup)
         t0 = time.perf_counter()
         its = []
@@ -134,20 +170,22 @@ def run_reference(args, rank, world):
         dt = time.perf_counter() - t0
     n = len(pos)
     v = n * args.steps / dt
-    sample = "%d^3 = %d-particle dam break (same scene generator and solver settings), %d settle + %d warm-up steps, %d timed; mean PCG it %.1f" % (
-        side, n, args.ref_settle, args.warmup, args.steps, float(np.mean(its)))
+    sample = "%d^3 = %d-particle dam break, same scene generator and solver settings as the GPU arm; %s; %d warm-up + %d timed steps; mean PCG it %.1f" % (
+        side, n, how, args.warmup, args.steps, float(np.mean(its)))
     print(json.dumps({
         "impl": "reference", "metric": "DFSPH particle-steps/s", "value": v, "unit": "particle-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "dam break, DFSPH + viscosity + surface tension, reference CPU build; " + sample},
+        "config": {"workload": "dam break %d^3 = %d particles, DFSPH (2 divergence + 2 pressure Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; "
+                               "reference solver sources on %d host threads" % (side, n, threads), "particles": n,
+                   "pcg_iterations_mean": float(np.mean(its))},
         "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
     return 0
 
 
-def cpu_baseline(state, dt, st, pos0, box, res, steps=2):
+def cpu_baseline(state, dt, st, pos0, box, res, steps=10):
     """The reference's solver sources on this box's host cores, from the GPU run's settled state."""
     from oracle import refsim
     if not refsim.available("cpu"):
@@ -183,6 +221,8 @@ def main():
     ap.add_argument("--ref-settle", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ncu-visc-it", type=int, default=0, help="with --ncu: cap the PCG at this many iterations for the profiled steps "
+                                                                  "(keeps an `ncu --set full` capture of one step short)")
     ap.add_argument("--ncu", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop (run under ncu --profile-from-start off); "
                                                         "skips the event-bracketed pass, e2e and cpu_baseline; numbers printed under a profiler are not bench values")
     args = ap.parse_args()
@@ -217,6 +257,10 @@ def main():
     if args.ncu:
         import torch
         args.no_e2e = args.no_cpu_baseline = True
+        if args.ncu_visc_it:
+            dt_now = sim.GetCurrentTimeStepSize()
+            sim.SetDescription(description(api.DFSPHSimulationDescription, MaxViscositySolverIterations=args.ncu_visc_it))
+            sim.set_time_step(dt_now)
         torch.cuda.cudart().cudaProfilerStart()
     with ClockSampler(local) as clk:
         sim.record_event(0)
@@ -232,6 +276,7 @@ def main():
     dbg = sim.GetDebugInfo()
     counts, _, _ = sim.neighbors()
     mbar = float(counts.mean())
+    tstats = sim.tile_stats()
 
     # second pass over the next K steps with every launch bracketed by CUDA events on the solver's stream:
     # per-kernel device time -> roofline of the dominant kernel (the event pairs cost a few us per launch, so
@@ -268,6 +313,7 @@ def main():
         "config": {"workload": "dam break %d^3 = %d particles, DFSPH (2 divergence + 2 pressure Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; "
                                "%d settle steps; working set > L2 (neighbour list alone %.0f MB), no flush" % (args.side, n, args.settle, n * 70 * 4 / 1e6),
                    "particles": n, "mean_neighbours": mbar, "pcg_iterations_last_step": int(dbg.ViscositySolverIterationCount),
+                   "grid_tiles": tstats["tiles"], "tile_passes_on_slow_path": tstats["fallback_tile_passes"],
                    "kernels": table},
         "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,
     }

@@ -203,6 +203,10 @@ int vfd_dfsph_set_option(VfdDfsph* h, int option, int64_t value);
 
 /* per-kernel accounting for bench.py: number of kernels launched since the last reset */
 int vfd_dfsph_get_launch_count(VfdDfsph* h, uint64_t* launches, int reset);
+/* search-grid statistics of the last step (inspector only, like ParticleSearch::GetByteSize, ParticleSearch.cu:11):
+ * stats[0] tiles (4x4x4 cells) of the grid, [1] cells, [2] tile passes since the last begin() whose 6x6x6-cell
+ * neighbourhood did not fit the shared-memory stage and took the slow global-memory path, [3] frame bytes copied D2H */
+int vfd_dfsph_get_tile_stats(VfdDfsph* h, uint64_t stats[4]);
 
 /* ---- several GPUs: one process (rank) per GPU, the domain cut into slabs of tile columns along x ----------------
  * No reference equivalent (the reference drives device 0 only: VFD/Source/Debug/SystemInfo.cpp:34-35).

@@ -152,6 +152,7 @@ SYMBOLS = [
     ("vfd_halton_table_build", _i, [_vp]),
     ("vfd_dfsph_set_option", _i, [_vp, _i, C.c_int64]),
     ("vfd_dfsph_get_launch_count", _i, [_vp, C.POINTER(_u64), _i]),
+    ("vfd_dfsph_get_tile_stats", _i, [_vp, _vp]),
     ("vfd_dist_unique_id", _i, [_vp]),
     ("vfd_dfsph_init_distributed", _i, [_vp, _i, _i, _vp, _vp, _vp]),
     ("vfd_dfsph_get_grid", _i, [_vp, _vp, C.POINTER(_f32), _vp]),
@@ -438,6 +439,11 @@ class DFSPHSimulation:
         v = C.c_uint64()
         self._ck(self.L.vfd_dfsph_get_launch_count(self.h, C.byref(v), 1 if reset else 0))
         return v.value
+
+    def tile_stats(self):
+        st = np.zeros(4, np.uint64)
+        self._ck(self.L.vfd_dfsph_get_tile_stats(self.h, _p(st)))
+        return dict(tiles=int(st[0]), cells=int(st[1]), fallback_tile_passes=int(st[2]), frame_bytes=int(st[3]))
 
     def kernel_times(self, reset=False):
         """{kernel class: (ms of launches that did work, number of such launches, ms of all launches, all launches)}"""

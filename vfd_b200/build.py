@@ -16,7 +16,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libvfd_dfsph.so")
 OBJDIR = os.path.join(HERE, "build")
 
-CU = ["search.cu", "boundary.cu", "pressure.cu", "viscosity.cu", "surface_tension.cu", "solver.cu", "distributed.cu", "api.cu", "volume_map.cu"]
+CU = ["search.cu", "boundary.cu", "pressure.cu", "viscosity.cu", "surface_tension.cu", "solver.cu", "distributed.cu", "api.cu", "volume_map.cu", "frame_pipe.cu"]
 CPP = ["tables.cpp"]
 
 # -fmad=false: no implicit FMA contraction.  The reference's lookup-table kernel is piecewise constant in r

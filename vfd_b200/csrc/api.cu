@@ -88,16 +88,16 @@ uint32_t vfd_dfsph_get_particle_count(const VfdDfsph* h) { return h ? h->s.info.
 float vfd_dfsph_get_particle_radius(const VfdDfsph* h) { return h ? h->s.info.ParticleRadius : 0.0f; }
 uint32_t vfd_dfsph_get_rigid_body_count(const VfdDfsph* h) { return h ? h->s.info.RigidBodyCount : 0u; }
 
-int vfd_dfsph_get_frame_count(const VfdDfsph* h, uint32_t* baked) { GUARD(h); if (!baked) return VFD_E_INVALID; *baked = (uint32_t)h->s.frames.size(); return VFD_OK; }
+int vfd_dfsph_get_frame_count(const VfdDfsph* h, uint32_t* baked) { GUARD(h); if (!baked) return VFD_E_INVALID; *baked = (uint32_t)const_cast<VfdDfsph*>(h)->s.pipe.published(); return VFD_OK; }
 int vfd_dfsph_get_frame(VfdDfsph* h, uint32_t index, VfdParticleSimple* out, float* maxVel, float* dt) {
     GUARD(h);
-    std::lock_guard<std::mutex> g(h->s.frameMutex);
-    if (index >= h->s.frames.size()) return h->s.fail(VFD_E_INVALID, "frame index out of range");
-    const vfd::Frame& f = h->s.frames[index];
-    if (out) memcpy(out, f.data.data(), f.data.size() * sizeof(VfdParticleSimple));
-    if (maxVel) *maxVel = f.maxVel2;
-    if (dt) *dt = f.dt;
-    return VFD_OK;
+    if (h->s.pipe.read(index, out, maxVel, dt)) return VFD_OK;
+    // captured but still in flight (only possible outside Simulate(), which drains before it returns)
+    if (index < h->s.frameIndexHost && h->s.state != VFD_STATE_SIMULATING) {
+        if (h->s.pipe.drain() != cudaSuccess) return h->s.fail(VFD_E_CUDA, "asynchronous frame copy failed");
+        if (h->s.pipe.read(index, out, maxVel, dt)) return VFD_OK;
+    }
+    return h->s.fail(VFD_E_INVALID, "frame index out of range");
 }
 int vfd_dfsph_get_current_frame(VfdDfsph* h, VfdParticleSimple* out) { GUARD(h); TRY(h->s.get_current_frame(out)); }
 
@@ -151,6 +151,11 @@ int vfd_dfsph_set_option(VfdDfsph* h, int option, int64_t value) {
     }
 }
 int vfd_dfsph_get_launch_count(VfdDfsph* h, uint64_t* launches, int reset) { GUARD(h); if (launches) *launches = h->s.launches; if (reset) h->s.launches = 0; return VFD_OK; }
+
+int vfd_dfsph_get_tile_stats(VfdDfsph* h, uint64_t stats[4]) {
+    GUARD(h); if (!stats) return h->s.fail(VFD_E_INVALID, "null output");
+    return h->s.tile_stats(stats);
+}
 
 int vfd_dist_unique_id(char out[128]) {
     if (!out) return VFD_E_INVALID;

@@ -5,10 +5,10 @@
 //   float4 arrays : gathered per neighbour with one 16-B load (pos, vel, pressure acceleration,
 //                   PCG direction ...);  .w is a per-array payload or unused.
 //   float  arrays : per-particle scalars, streamed coalesced.
-//   neighbour list: "warp-blocked ELL" of 16-bit TILE-LOCAL indices (tile.cuh): the k-th neighbour
-//                   of the particle in lane l of 32-group w sits at
-//                   list16[(w*VFD_MAX_NEIGHBORS + k)*32 + l]  — a warp reads one 64-B line per k,
-//                   only rows k < max-count-in-warp are ever touched.
+//   neighbour list: "warp-blocked ELL" of 16-bit TILE-LOCAL indices in groups of four (tile.cuh): neighbours
+//                   4g..4g+3 of the particle in lane l of 32-group w are the 8-byte word
+//                   list16[(w*18 + g)*32 + l]  — a warp reads one 256-B block per four neighbours,
+//                   only groups below the largest count in the warp are ever touched.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -85,7 +85,7 @@ struct DevState {
     double red[16];
     // multi-GPU: global cell coordinates of the local grid's cell (0,0,0)
     int32_t cellOffset[3];
-    uint32_t pad_;
+    uint32_t fallbackTiles;     // tile passes whose halo box exceeded the shared-memory stage (slow, exact path); cumulative
 };
 
 struct float3x3 { float m[9]; };   // column-major like glm::mat3x3: m[3*c + r]

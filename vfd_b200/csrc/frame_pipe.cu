@@ -1,0 +1,144 @@
+// frame_pipe.cu — see frame_pipe.h.
+#include "frame_pipe.h"
+#include <cstring>
+
+namespace vfd {
+
+FramePipe::~FramePipe() {
+    stop_worker();
+    if (device >= 0) cudaSetDevice(device);
+    for (int s = 0; s < SLOTS; s++) {
+        if (dBuf[s]) cudaFree(dBuf[s]);
+        if (hBuf[s]) cudaFreeHost(hBuf[s]);
+        if (exported[s]) cudaEventDestroy(exported[s]);
+        if (copied[s]) cudaEventDestroy(copied[s]);
+    }
+    if (copyStream) cudaStreamDestroy(copyStream);
+}
+
+void FramePipe::stop_worker() {
+    if (!worker.joinable()) return;
+    {
+        std::lock_guard<std::mutex> g(m);
+        quit = true;
+    }
+    cvJob.notify_all();
+    worker.join();
+    quit = false;
+}
+
+cudaError_t FramePipe::configure(int dev, uint32_t count) {
+    cudaError_t e = drain();
+    if (e != cudaSuccess) return e;
+    if (dev == device && count == n && copyStream) return cudaSuccess;
+    stop_worker();
+    device = dev;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return e;
+    for (int s = 0; s < SLOTS; s++) {
+        if (dBuf[s]) { cudaFree(dBuf[s]); dBuf[s] = nullptr; }
+        if (hBuf[s]) { cudaFreeHost(hBuf[s]); hBuf[s] = nullptr; }
+    }
+    n = count;
+    if (!copyStream && (e = cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (int s = 0; s < SLOTS; s++) {
+        if (!exported[s] && (e = cudaEventCreateWithFlags(&exported[s], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if (!copied[s] && (e = cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming)) != cudaSuccess) return e;
+        busy[s] = false;
+    }
+    next = 0; acquired = -1;
+    // buffers are allocated lazily by acquire(): a solver that never bakes a frame pays nothing
+    worker = std::thread(&FramePipe::worker_main, this);
+    return cudaSuccess;
+}
+
+VfdParticleSimple* FramePipe::acquire() {
+    const int s = next;
+    {
+        std::unique_lock<std::mutex> g(m);
+        cvDone.wait(g, [&] { return !busy[s]; });
+    }
+    const size_t bytes = (size_t)(n ? n : 1u) * sizeof(VfdParticleSimple);
+    if (!dBuf[s] && cudaMalloc((void**)&dBuf[s], bytes) != cudaSuccess) return nullptr;
+    if (!hBuf[s] && cudaMallocHost((void**)&hBuf[s], bytes) != cudaSuccess) return nullptr;
+    acquired = s;
+    return dBuf[s];
+}
+
+cudaError_t FramePipe::submit(cudaStream_t solverStream, float maxVel2, float dt) {
+    if (acquired < 0) return cudaErrorInvalidValue;
+    const int s = acquired;
+    acquired = -1;
+    cudaError_t e;
+    if ((e = cudaEventRecord(exported[s], solverStream)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(copyStream, exported[s], 0)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(hBuf[s], dBuf[s], (size_t)n * sizeof(VfdParticleSimple), cudaMemcpyDeviceToHost, copyStream)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(copied[s], copyStream)) != cudaSuccess) return e;
+    bytesCopied += (uint64_t)n * sizeof(VfdParticleSimple);
+    {
+        std::lock_guard<std::mutex> g(m);
+        busy[s] = true;
+        jobs.push_back(Job{ s, maxVel2, dt });
+        inFlight++;
+    }
+    cvJob.notify_one();
+    next = (s + 1) % SLOTS;
+    return cudaSuccess;
+}
+
+void FramePipe::worker_main() {
+    cudaSetDevice(device);
+    for (;;) {
+        Job j;
+        {
+            std::unique_lock<std::mutex> g(m);
+            cvJob.wait(g, [&] { return quit || !jobs.empty(); });
+            if (jobs.empty()) return;          // quit
+            j = jobs.front();
+            jobs.pop_front();
+        }
+        Frame f;
+        f.count = n; f.maxVel2 = j.maxVel2; f.dt = j.dt;
+        f.data.reset(new VfdParticleSimple[n ? n : 1u]);          // uninitialised: written once, below
+        const cudaError_t e = cudaEventSynchronize(copied[j.slot]);
+        if (e == cudaSuccess) memcpy(f.data.get(), hBuf[j.slot], (size_t)n * sizeof(VfdParticleSimple));
+        {
+            std::lock_guard<std::mutex> g(m);
+            if (e != cudaSuccess && asyncError == cudaSuccess) asyncError = e;
+            frames.push_back(std::move(f));
+            busy[j.slot] = false;
+            inFlight--;
+        }
+        cvDone.notify_all();
+    }
+}
+
+cudaError_t FramePipe::drain() {
+    std::unique_lock<std::mutex> g(m);
+    cvDone.wait(g, [&] { return inFlight == 0; });
+    const cudaError_t e = asyncError;
+    asyncError = cudaSuccess;
+    return e;
+}
+
+void FramePipe::clear() {
+    drain();
+    std::lock_guard<std::mutex> g(m);
+    frames.clear();
+}
+
+size_t FramePipe::published() {
+    std::lock_guard<std::mutex> g(m);
+    return frames.size();
+}
+
+bool FramePipe::read(uint32_t index, VfdParticleSimple* out, float* maxVel2, float* dt) {
+    std::lock_guard<std::mutex> g(m);
+    if (index >= frames.size()) return false;
+    const Frame& f = frames[index];
+    if (out) memcpy(out, f.data.get(), f.count * sizeof(VfdParticleSimple));
+    if (maxVel2) *maxVel2 = f.maxVel2;
+    if (dt) *dt = f.dt;
+    return true;
+}
+
+} // namespace vfd

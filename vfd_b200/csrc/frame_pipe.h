@@ -1,0 +1,74 @@
+// frame_pipe.h — asynchronous capture of baked frames.
+//
+// Replaces the frame capture at the end of DFSPHImplementation::OnUpdate (reference:
+// DFSPHImplementation.cu:148-167: a new std::vector per frame, filled by a synchronous cudaMemcpy on the
+// default stream, so the solver idles for every frame) and the host cache of DFSPHParticleBuffer
+// (ParticleBuffer/DFSPHParticleBuffer.cu:26-33, format DFSPHParticleSimple, 36 B/particle, original
+// particle order).
+//
+// Here a captured frame flows through a ring of SLOTS (device buffer, pinned host buffer) pairs:
+//   solver stream : k_export_frame -> dBuf[slot]                           (record `exported`)
+//   copy stream   : wait `exported`; D2H dBuf[slot] -> hBuf[slot] (pinned)  (record `copied`)
+//   host worker   : wait `copied`; copy hBuf[slot] into the frame's own storage; publish; free the slot
+// so the solver stream never waits for PCIe or for the host: the next step's kernels run while the
+// previous frame drains.  Back-pressure: capture() blocks only when all SLOTS are still in flight.
+#pragma once
+#include "../../include/vfd_dfsph.h"
+#include <cuda_runtime.h>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace vfd {
+
+struct Frame {
+    std::unique_ptr<VfdParticleSimple[]> data;
+    size_t count = 0;
+    float maxVel2 = 0.0f, dt = 0.0f;
+};
+
+class FramePipe {
+public:
+    static constexpr int SLOTS = 3;
+    ~FramePipe();
+    // (re)size the ring for n particles on `device`; drains first
+    cudaError_t configure(int device, uint32_t n);
+    // device buffer the next frame must be exported into (blocks while every slot is in flight)
+    VfdParticleSimple* acquire();
+    // the export kernel has been enqueued on `solverStream` into the buffer returned by acquire()
+    cudaError_t submit(cudaStream_t solverStream, float maxVel2, float dt);
+    // wait until every submitted frame is published; returns the first asynchronous error, if any
+    cudaError_t drain();
+    void clear();                       // drain + drop all published frames
+    size_t published();
+    // copy a published frame out (false: index not published)
+    bool read(uint32_t index, VfdParticleSimple* out, float* maxVel2, float* dt);
+    uint64_t bytesCopied = 0;
+
+private:
+    struct Job { int slot; float maxVel2, dt; };
+    void worker_main();
+    void stop_worker();
+    int device = -1;
+    uint32_t n = 0;
+    VfdParticleSimple* dBuf[SLOTS] = {};
+    VfdParticleSimple* hBuf[SLOTS] = {};
+    cudaEvent_t exported[SLOTS] = {}, copied[SLOTS] = {};
+    cudaStream_t copyStream = nullptr;
+    bool busy[SLOTS] = {};
+    int next = 0, acquired = -1;
+    std::deque<Job> jobs;
+    size_t inFlight = 0;
+    bool quit = false;
+    cudaError_t asyncError = cudaSuccess;
+    std::thread worker;
+    std::mutex m;                       // guards busy, jobs, inFlight, quit, frames
+    std::condition_variable cvJob, cvDone;
+    std::vector<Frame> frames;
+};
+
+} // namespace vfd

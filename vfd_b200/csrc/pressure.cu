@@ -71,7 +71,7 @@ struct DensityFactorOp {
     }
 };
 
-__global__ void __launch_bounds__(TT_LUT) k_density_factor(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S,
+__global__ void __launch_bounds__(TT_LUT2) k_density_factor(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S,
                                                                  const float* __restrict__ lutW, const float* __restrict__ lutG) {
     float* sW = smem_lut<2>(smemRaw);
     float* sG = sW + VFD_LUT_RES;
@@ -123,7 +123,7 @@ struct SourceOp {
 };
 
 template<bool DIV>
-__global__ void __launch_bounds__(TT_LUT) k_source(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+__global__ void __launch_bounds__(TT_LUT, 2) k_source(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
     float* sG = smem_lut<1>(smemRaw);
     load_lut_tile(sG, lutG);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(TT_LUT) k_source(const __grid_constant__ Param
         else     { S->pressIt = 0; S->pressErr = 0.0f; S->pressActive = (0u < P.minPressIt && 0u < P.maxPressIt) ? 1u : 0u; }
     }
     SourceOp<DIV> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, S->dtInv, S->dt2Inv };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP), STAGE_CAP, op, P.tile0, P.tile1);
+    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP_LUT), STAGE_CAP_LUT, op, P.tile0, P.tile1);
 }
 
 // ---- K5 / K7 / K11 / K13: pressure acceleration from kappa ---------------------------------
@@ -182,7 +182,7 @@ struct AccelOp {
 };
 
 template<int MODE>
-__global__ void __launch_bounds__(TT_LUT) k_pressure_accel(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+__global__ void __launch_bounds__(TT_LUT, 2) k_pressure_accel(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
     if (MODE == ACC_DIV_ITER && !S->divActive) return;
     if (MODE == ACC_PRESS_ITER && !S->pressActive) return;
     float* sG = smem_lut<1>(smemRaw);
@@ -231,13 +231,13 @@ struct SolveOp {
 };
 
 template<bool DIV>
-__global__ void __launch_bounds__(TT_LUT) k_solve_iteration(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+__global__ void __launch_bounds__(TT_LUT, 2) k_solve_iteration(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
     if (DIV ? !S->divActive : !S->pressActive) return;
     TileShared& sh = smem_header(smemRaw);
     float* sG = smem_lut<1>(smemRaw);
     load_lut_tile(sG, lutG);
     SolveOp<DIV> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, DIV ? S->dt : S->dt2, 0.0f };
-    tile_pass(S, A, sh, smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP), STAGE_CAP, op, P.tile0, P.tile1);
+    tile_pass(S, A, sh, smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP_LUT), STAGE_CAP_LUT, op, P.tile0, P.tile1);
     __syncthreads();
     double v[1] = { (double)op.errSum };
     uint32_t* ticket = &S->ticket[DIV ? 1 : 2];
@@ -315,12 +315,12 @@ static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L, int thread
 
 void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutW, const float* lutG) {
     const size_t smem = tile_smem_bytes<2, 1>(STAGE_CAP);
-    const uint32_t g = tile_grid(k_density_factor, smem, L, TT_LUT);
+    const uint32_t g = tile_grid(k_density_factor, smem, L, TT_LUT2);
     LaunchScope ls(L, KID_DENSITY_FACTOR);
-    k_density_factor<<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutW, lutG);
+    k_density_factor<<<g, TT_LUT2, smem, L.stream>>>(P, A, S, lutW, lutG);
 }
 void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t smem = tile_smem_bytes<1, 2>(STAGE_CAP);
+    const size_t smem = tile_smem_bytes<1, 2>(STAGE_CAP_LUT);
     const uint32_t g = tile_grid(k_source<true>, smem, L, TT_LUT);
     LaunchScope ls(L, KID_DIV_SOURCE);
     k_source<true><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
@@ -332,7 +332,7 @@ void launch_divergence_accel(const LaunchCfg& L, const Params& P, const Arrays& 
     k_pressure_accel<ACC_DIV_ITER><<<g1, TT_LUT, s1, L.stream>>>(P, A, S, lutG);
 }
 void launch_divergence_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s2 = tile_smem_bytes<1, 2>(STAGE_CAP);
+    const size_t s2 = tile_smem_bytes<1, 2>(STAGE_CAP_LUT);
     const uint32_t g2 = tile_grid(k_solve_iteration<true>, s2, L, TT_LUT);
     LaunchScope ls(L, KID_DIV_SOLVE);
     k_solve_iteration<true><<<g2, TT_LUT, s2, L.stream>>>(P, A, S, lutG);
@@ -344,7 +344,7 @@ void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays&
     k_pressure_accel<ACC_DIV_FINISH><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
 }
 void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t smem = tile_smem_bytes<1, 2>(STAGE_CAP);
+    const size_t smem = tile_smem_bytes<1, 2>(STAGE_CAP_LUT);
     const uint32_t g = tile_grid(k_source<false>, smem, L, TT_LUT);
     LaunchScope ls(L, KID_PRESS_SOURCE);
     k_source<false><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
@@ -356,7 +356,7 @@ void launch_pressure_accel(const LaunchCfg& L, const Params& P, const Arrays& A,
     k_pressure_accel<ACC_PRESS_ITER><<<g1, TT_LUT, s1, L.stream>>>(P, A, S, lutG);
 }
 void launch_pressure_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s2 = tile_smem_bytes<1, 2>(STAGE_CAP);
+    const size_t s2 = tile_smem_bytes<1, 2>(STAGE_CAP_LUT);
     const uint32_t g2 = tile_grid(k_solve_iteration<false>, s2, L, TT_LUT);
     LaunchScope ls(L, KID_PRESS_SOLVE);
     k_solve_iteration<false><<<g2, TT_LUT, s2, L.stream>>>(P, A, S, lutG);

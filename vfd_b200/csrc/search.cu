@@ -222,12 +222,14 @@ struct SearchOp {
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return pos[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
     template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, size_t ell, const Acc& acc) {
+    __device__ __forceinline__ void particle(uint32_t p, bool valid, const Acc& acc) {
+        if (!valid) return;
         const float4 xi = pos[p];
         const uint3 c = cell_of(xi, S, invCell);
         const uint32_t hx = (c.x & 3u) + 1u, hy = (c.y & 3u) + 1u, hz = (c.z & 3u) + 1u;   // box coordinates of the own cell
-        uint16_t* col = list + ell;
+        uint2* col = reinterpret_cast<uint2*>(list) + ell_base(p);
         uint32_t m = 0;
+        uint32_t L[4] = { 0u, 0u, 0u, 0u };                  // the group being filled: written as one 8-byte word
         for (int dz = -1; dz <= 1 && m < VFD_MAX_NEIGHBORS; dz++) {
             for (int dy = -1; dy <= 1 && m < VFD_MAX_NEIGHBORS; dy++) {
                 const uint32_t c0 = ((hz + dz) * 6u + (hy + dy)) * 6u + hx - 1u;
@@ -239,12 +241,16 @@ struct SearchOp {
                     if (FMA) d2 = __fmaf_rn(dzz, dzz, __fmaf_rn(dx, dx, __fmul_rn(dyy, dyy)));   // how nvcc compiles ParticleSearchKernels.cu:124
                     else     d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dyy, dyy)), __fmul_rn(dzz, dzz));
                     if (d2 < h2 && d2 > 0.0f) {
-                        col[(size_t)m * 32] = (uint16_t)j;
+                        // static register indexing: select the slot without a local-memory array
+                        const uint32_t q = m & 3u;
+                        L[0] = q == 0u ? j : L[0]; L[1] = q == 1u ? j : L[1]; L[2] = q == 2u ? j : L[2]; L[3] = q == 3u ? j : L[3];
+                        if (q == 3u) { col[(size_t)(m >> 2) * 32] = ell_pack(L); L[0] = L[1] = L[2] = L[3] = 0u; }
                         if (++m == VFD_MAX_NEIGHBORS) break;
                     }
                 }
             }
         }
+        if (m & 3u) col[(size_t)(m >> 2) * 32] = ell_pack(L);
         cnt[p] = m;
     }
 };

@@ -99,8 +99,12 @@ __global__ void __launch_bounds__(512) k_export_neighbors(const __grid_constant_
         for (uint32_t p = t.begin + threadIdx.x; p < t.end; p += blockDim.x) {
             const uint32_t o = A.id[p], m = A.cnt[p];
             counts[o] = m;
-            const uint16_t* col = A.list16 + ell_base(p);
-            for (uint32_t k = 0; k < m; k++) idsPadded[(size_t)o * VFD_MAX_NEIGHBORS + k] = A.id[tile_local_to_global(sh, col[(size_t)k * 32])];
+            const uint2* col = ell_list(A.list16, p);
+            for (uint32_t k = 0; k < m; k++) {
+                uint32_t L[4];
+                ell_unpack(col[(size_t)(k >> 2) * 32], L);
+                idsPadded[(size_t)o * VFD_MAX_NEIGHBORS + k] = A.id[tile_local_to_global(sh, L[k & 3u])];
+            }
         }
     }
 }
@@ -203,6 +207,7 @@ int Solver::init(const VfdDfsphDescription& d, int dev) {
 
 Solver::~Solver() {
     if (device >= 0) cudaSetDevice(device);
+    pipe.drain();
     free_particles();
     free_bodies();
     cudaFree(dState); cudaFreeHost(hState); cudaFreeHost(hFlags);
@@ -292,12 +297,26 @@ void Solver::free_particles() {
     memset(&A, 0, sizeof A);
     dPos0 = dVel0 = nullptr;
     allocBytes = 0;
+    allocParticles = 0;
 }
 
 int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxMax) {
-    free_particles();
     Arrays& A = arrays;
     const size_t np = ((size_t)(dist ? std::max(dist->capacity, n) : n) + 31) / 32 * 32;
+    // Re-baking the same scene (the editor's "Simulate" button: Simulate() restarts from the stored initial state,
+    // DFSPHImplementation.cu:36-51) keeps every buffer: same particle capacity, same bodies, grid capacity still enough.
+    {
+        double cells0 = 1.0;
+        for (int k = 0; k < 3; k++) cells0 *= std::ceil((double)(bboxMax[k] - bboxMin[k]) / info.SupportRadius) + 9.0;
+        bool bodiesOk = true;
+        for (uint32_t b = 0; b < VFD_MAX_BODIES; b++) bodiesOk = bodiesOk && ((A.bx[b] != nullptr) == (b < info.RigidBodyCount));
+        if (!dist && A.pos && allocParticles == np && bodiesOk && 8.0 * cells0 <= (double)cellCapacity) {
+            cellEstimate = (uint32_t)std::min<double>(cells0, (double)optMaxCells);
+            return VFD_OK;
+        }
+    }
+    free_particles();
+    allocParticles = np;
     float4** f4s[] = { &A.pos, &A.vel, &A.dv, &A.nbar, &A.pos2, &A.vel2, &A.dv2, &A.nbar2, &A.posRho, &A.acc, &A.pacc, &A.nrm,
                        &A.cgG, &A.cgR, &A.cgP, &A.cgQ, &A.cgZ, &dPos0, &dVel0 };
     CK(dalloc(dIds0, np));
@@ -307,9 +326,9 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
     CK(dalloc(A.minv, np * 9)); allocBytes += np * 36;
     uint32_t** u1s[] = { &A.id, &A.id2, &A.cnt, &A.key, &A.rank, &A.tmpIdx };
     for (uint32_t** p : u1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
-    CK(dalloc(A.list16, np * VFD_MAX_NEIGHBORS)); searchBytes = np * VFD_MAX_NEIGHBORS * 2 + np * 4 * 4;
-    CK(dalloc(A.coef, np * VFD_MAX_NEIGHBORS));
-    allocBytes += np * VFD_MAX_NEIGHBORS * 6;
+    CK(dalloc(A.list16, np * ELL_SLOTS)); searchBytes = np * ELL_SLOTS * 2 + np * 4 * 4;
+    CK(dalloc(A.coef, np * ELL_SLOTS));
+    allocBytes += np * ELL_SLOTS * 6;
     // search grid capacity: 64x the cells of the initial bounding box (4x per axis of head room)
     double cells0 = 1.0;
     for (int k = 0; k < 3; k++) cells0 *= std::ceil((double)(bboxMax[k] - bboxMin[k]) / info.SupportRadius) + 9.0;
@@ -338,7 +357,7 @@ int Solver::set_particles(const float* pos, const float* vel, uint32_t n, bool o
     state = VFD_STATE_NONE;
     info.ParticleCount = n;
     refresh_params();
-    frames.clear();
+    pipe.clear();
     began = false;
     if (n == 0) { free_particles(); return VFD_OK; }
     float *dPos = nullptr, *dVel = nullptr;
@@ -354,6 +373,7 @@ int Solver::set_particles(const float* pos, const float* vel, uint32_t n, bool o
     for (size_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) { const float v = hp[3 * i + k]; bmin[k] = std::min(bmin[k], v); bmax[k] = std::max(bmax[k], v); }
     int rc = alloc_particles(n, bmin, bmax);
     if (rc) return rc;
+    CK(pipe.configure(device, n));
     if (onDevice) { dPos = const_cast<float*>(pos); dVel = const_cast<float*>(vel); }
     else {
         CK(cudaMalloc(&dPos, (size_t)12 * n));
@@ -385,11 +405,12 @@ int Solver::dist_set_particles(const float* pos, const float* vel, const uint32_
     CK(cudaMalloc(&D.recvL, (size_t)D.haloCap * 80)); CK(cudaMalloc(&D.recvR, (size_t)D.haloCap * 80));
     state = VFD_STATE_NONE;
     info.ParticleCount = n;
-    frames.clear();
+    pipe.clear();
     began = false;
     float bmin[3] = { 0, 0, 0 }, bmax[3] = { 1, 1, 1 };
     int rc = alloc_particles(n, bmin, bmax);
     if (rc) return rc;
+    CK(pipe.configure(device, n));
     // rigid-body sample arrays are sized with the particle arrays
     if (n) {
         float *dPos = nullptr, *dVel = nullptr;
@@ -473,7 +494,7 @@ int Solver::begin() {
         std::lock_guard<std::mutex> g(dbgMutex);
         memset(&debug, 0, sizeof debug);
     }
-    frames.clear();
+    pipe.clear();
     frameTimeHost = 0.0f; frameIndexHost = 0; stepsIssued = 0;
     began = true;
     searched = false;
@@ -666,21 +687,13 @@ void Solver::update_debug(const DevState& s, bool timers) {
 }
 
 int Solver::capture_frame(const DevState& s) {
-    Frame f;
-    f.maxVel2 = s.vmax2; f.dt = s.dt;
-    f.data.resize(info.ParticleCount);
-    VfdParticleSimple* d = nullptr;
-    CK(cudaMalloc(&d, (size_t)info.ParticleCount * sizeof(VfdParticleSimple)));
+    // K15 + the frame cache: export in original particle order on the solver's stream, then hand the buffer to the
+    // asynchronous pipe (copy stream + host worker): the next step does not wait for PCIe or for the host copy.
+    VfdParticleSimple* d = pipe.acquire();
+    if (!d) { cudaGetLastError(); return fail(VFD_E_CUDA, "frame capture: cannot allocate the frame ring buffers"); }
     k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d);
     launches += 1;
-    cudaError_t e = cudaMemcpyAsync(f.data.data(), d, (size_t)info.ParticleCount * sizeof(VfdParticleSimple), cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    cudaFree(d);
-    if (e != cudaSuccess) return fail_cuda(e, "frame capture", __LINE__);
-    {
-        std::lock_guard<std::mutex> g(frameMutex);
-        frames.push_back(std::move(f));
-    }
+    CK(pipe.submit(stream, s.vmax2, s.dt));
     frameTimeHost = 0.0f;              // FrameTime = 0 (:164)
     frameIndexHost++;
     std::lock_guard<std::mutex> g(dbgMutex);
@@ -697,6 +710,7 @@ int Solver::simulate() {
         rc = step();
         if (rc) { state = VFD_STATE_NONE; return rc; }
     }
+    CK(pipe.drain());                  // every baked frame is in the host cache when Simulate() returns
     state = VFD_STATE_READY;
     return VFD_OK;
 }
@@ -704,6 +718,7 @@ int Solver::simulate() {
 int Solver::synchronize() {
     CK(cudaSetDevice(device));
     CK(cudaStreamSynchronize(stream));
+    CK(pipe.drain());
     return VFD_OK;
 }
 
@@ -849,6 +864,17 @@ int Solver::elapsed_ms(uint32_t from, uint32_t to, float* ms) {
     if (from >= 16 || to >= 16 || !userEvent[from] || !userEvent[to]) return fail(VFD_E_INVALID, "event slot not recorded");
     CK(cudaEventSynchronize(userEvent[to]));
     CK(cudaEventElapsedTime(ms, userEvent[from], userEvent[to]));
+    return VFD_OK;
+}
+
+int Solver::tile_stats(uint64_t* st) {
+    st[0] = st[1] = st[2] = 0; st[3] = pipe.bytesCopied;
+    if (!began || info.ParticleCount == 0) return VFD_OK;
+    DevState s;
+    CK(cudaSetDevice(device));
+    int rc = read_state(s);
+    if (rc) return rc;
+    st[0] = s.nTiles; st[1] = s.nCells; st[2] = s.fallbackTiles;
     return VFD_OK;
 }
 

@@ -1,6 +1,7 @@
 // solver_impl.h — the object behind a VfdDfsph handle.
 #pragma once
 #include "solver.h"
+#include "frame_pipe.h"
 #include <functional>
 #include <memory>
 
@@ -42,8 +43,6 @@ struct Dist {
 
 int dist_unique_id(char* out128, std::string& err);
 
-struct Frame { std::vector<VfdParticleSimple> data; float maxVel2; float dt; };
-
 class Solver {
 public:
     ~Solver();
@@ -65,6 +64,7 @@ public:
     int get_neighbors(uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t capacity, uint64_t* total);
     int get_boundary(uint32_t body, float* xj, float* vol);
     int get_bounds(float* bmin, float* bmax);
+    int tile_stats(uint64_t* stats4);
     // slab decomposition over several ranks (distributed.cu)
     int dist_init(int rank, int nranks, const char* id128, const float* dmin, const float* dmax);
     int dist_get_grid(float* origin3, float* cellSize, uint32_t* tiles3);
@@ -90,8 +90,8 @@ public:
     int state = VFD_STATE_NONE;
     VfdDfsphDebugInfo debug{};
     float maxVel2 = 0.0f;
-    std::vector<Frame> frames;
-    std::mutex frameMutex, dbgMutex, errMutex;
+    FramePipe pipe;                   // baked frames: async D2H ring + host cache (frame_pipe.h)
+    std::mutex dbgMutex, errMutex;
     std::string lastError;
     uint32_t frameIndexHost = 0;
     int device = -1;
@@ -132,6 +132,7 @@ private:
     uint32_t* dIds0 = nullptr;
     VfdParticleSimple* dFrame = nullptr;
     uint32_t cellEstimate = 27, cellCapacity = 0;
+    size_t allocParticles = 0;        // particle slots the arrays are currently sized for
     bool began = false, searched = false;
     float frameTimeHost = 0.0f;
     uint64_t stepsIssued = 0;

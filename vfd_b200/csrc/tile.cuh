@@ -29,10 +29,14 @@ namespace vfd {
 #define TILE_WARPS (blockDim.x >> 5)
 #define HALO_CELLS 216
 #define TILE_CELLS 64
-#define TT_LUT 768             // kernels holding the 40-kB lookup table: one CTA per SM
-#define TT_MATVEC 512          // PCG mat-vec (no table): two CTAs per SM
+// A tile holds ~512 particles at rest density (64 cells x 8), so 512 threads give one particle per thread and pass.
+// Shared memory per SM is 228 KB; two resident CTAs (one staging while the other computes) need <= 113 KB each.
+#define TT_LUT 512             // kernels holding one 40-kB lookup table
+#define TT_LUT2 768            // density pass: two tables (80 kB), one CTA per SM
+#define TT_MATVEC 512          // PCG mat-vec (no table)
 #define TT_PLAIN 512
-#define STAGE_CAP 2432        // staged halo particles per tile (one or two float4 arrays: 38 / 76 KB)
+#define STAGE_CAP 2432         // staged halo particles per tile, kernels without a table (one or two float4 arrays: 38 / 76 KB)
+#define STAGE_CAP_LUT 2240     // ... kernels with one table and two payload arrays: 40 + 70 + 3 KB, two CTAs per SM
 
 // ---- grid / key helpers ---------------------------------------------------------------------------
 // cell slightly larger than h so that two particles closer than h can never be two cells apart
@@ -111,34 +115,46 @@ __device__ __forceinline__ TileInfo tile_setup(const DevState* __restrict__ S, c
     return t;
 }
 
-// Step 2: stage the payload of every halo particle; half a warp per cell (cells hold ~8 particles).
-// The payload is kept as one or two float4 arrays (SoA): a gather of consecutive local indices by the 8 lanes
-// of a group then touches 8 different 16-B bank groups.
-template<int NPAY, class Op>
-__device__ __forceinline__ void tile_stage(const TileShared& sh, float4* __restrict__ sA, float4* __restrict__ sB, const Op& op) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int half = lane >> 4, l16 = lane & 15;
-    for (int c = warp * 2 + half; c < HALO_CELLS; c += TILE_WARPS * 2) {
-        const uint32_t l0 = sh.local[c], cnt = sh.local[c + 1] - l0, g0 = sh.cellG[c];
-        for (uint32_t k = l16; k < cnt; k += 16) {
-            sA[l0 + k] = op.loadA(g0 + k);
-            if (NPAY > 1) sB[l0 + k] = op.loadB(g0 + k);
-        }
-    }
-}
-
-// local -> global index (fallback path and list export): binary search in the prefix table
+// local -> global index: binary search in the prefix table
 __device__ __forceinline__ uint32_t tile_local_to_global(const TileShared& sh, uint32_t L) {
     int lo = 0, hi = HALO_CELLS;          // find c with local[c] <= L < local[c+1]
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh.local[mid] <= L) lo = mid; else hi = mid; }
+    #pragma unroll
+    for (int it = 0; it < 8; it++) { const int mid = (lo + hi) >> 1; if (hi - lo > 1) { if (sh.local[mid] <= L) lo = mid; else hi = mid; } }
     return sh.cellG[lo] + (L - sh.local[lo]);
 }
 
+// Step 2: stage the payload of every halo particle.  Flat over the local index space (consecutive threads read
+// consecutive particles of a cell: coalesced), four items per thread with all global loads issued before the first
+// shared-memory store, so a tile pays one round of L2 latency instead of one per cell.
+// The payload is kept as one or two float4 arrays (SoA).
+template<int NPAY, class Op>
+__device__ __forceinline__ void tile_stage(const TileShared& sh, uint32_t total, float4* __restrict__ sA, float4* __restrict__ sB, const Op& op) {
+    constexpr int U = 4;
+    for (uint32_t base = threadIdx.x; base < total; base += blockDim.x * U) {
+        // items past the end are clamped to the last one (a duplicate store of the same value): no predicates, so the
+        // payload registers stay registers
+        uint32_t l[U], g[U];
+        float4 a[U], b[U];
+        #pragma unroll
+        for (int u = 0; u < U; u++) { l[u] = min(base + u * blockDim.x, total - 1u); g[u] = tile_local_to_global(sh, l[u]); }
+        #pragma unroll
+        for (int u = 0; u < U; u++) { a[u] = op.loadA(g[u]); if (NPAY > 1) b[u] = op.loadB(g[u]); }
+        #pragma unroll
+        for (int u = 0; u < U; u++) { sA[l[u]] = a[u]; if (NPAY > 1) sB[l[u]] = b[u]; }
+    }
+}
+
 // ---- neighbour list layout ------------------------------------------------------------------------
-// u16 tile-local indices, warp-blocked ELL: the k-th neighbour of particle p sits at
-// list16[((p>>5)*VFD_MAX_NEIGHBORS + k)*32 + (p&31)]; the per-pair viscosity coefficient uses the same layout.
-// One thread per particle: a warp reads 64 B (list) / 128 B (coefficients) per neighbour slot.
-__device__ __forceinline__ size_t ell_base(uint32_t p) { return (size_t)(p >> 5) * (VFD_MAX_NEIGHBORS * 32) + (p & 31); }
+// u16 tile-local indices in a warp-blocked ELL of 4-slot groups: slots 4g..4g+3 of particle p are the four u16 of the
+// 8-byte word  list16[((p>>5)*ELL_GROUPS + g)*32 + (p&31)]  (unused slots of the last group hold 0); the per-pair
+// viscosity coefficient uses the same layout with 16-byte words.  One thread per particle: a warp reads one 256-B
+// (list) / 512-B (coefficients) contiguous block per four neighbours with a single LDG.64 / LDG.128 per lane.
+#define ELL_GROUPS ((VFD_MAX_NEIGHBORS + 3) / 4)        // 18
+#define ELL_SLOTS (ELL_GROUPS * 4)                      // 72 slots allocated per particle
+__device__ __forceinline__ size_t ell_base(uint32_t p) { return (size_t)(p >> 5) * (ELL_GROUPS * 32) + (p & 31); }   // in groups; group g at + g*32
+__device__ __forceinline__ const uint2* ell_list(const uint16_t* list16, uint32_t p) { return reinterpret_cast<const uint2*>(list16) + ell_base(p); }
+__device__ __forceinline__ void ell_unpack(uint2 w, uint32_t (&L)[4]) { L[0] = w.x & 0xffffu; L[1] = w.x >> 16; L[2] = w.y & 0xffffu; L[3] = w.y >> 16; }
+__device__ __forceinline__ uint2 ell_pack(const uint32_t (&L)[4]) { return make_uint2(L[0] | (L[1] << 16), L[2] | (L[3] << 16)); }
 
 // staged / fallback gather of payload array A (for ops that run their own loops: search, classifier)
 template<bool STAGED, class Op> struct TileAcc {
@@ -148,16 +164,16 @@ template<bool STAGED, class Op> struct TileAcc {
 
 // ---- the pass driver --------------------------------------------------------------------------------
 // One thread per particle of the tile.  Two kinds of Op:
-//  * pair ops (Op::CUSTOM == false): the driver owns the neighbour loop, software-pipelined 4 deep — list
-//    entries (and pair coefficients) of the next 4 neighbours are in flight while the current 4 are gathered
-//    from shared memory and accumulated:
+//  * pair ops (Op::CUSTOM == false): the driver owns the neighbour loop.  Neighbours are consumed in groups of four:
+//    the next group's list word (and coefficient word) is in flight while the current group's four payloads are
+//    gathered from shared memory back to back (no branch between them: the loads overlap) and accumulated in
+//    list order.  Only the last, partial group of a particle takes the slot-by-slot path.
 //       NPAY (1|2), NOWN, NSUM, COEF (0 none, 1 read, 2 write)
 //       float4 loadA(g), loadB(g)                      staged payload of particle g
 //       void load_own(p, float (&own)[NOWN])
 //       void pair(const float (&own)[NOWN], float4 a, float4 b, float& coef, float (&acc)[NSUM])
 //       void finish(p, m, const float (&own)[NOWN], const float (&sum)[NSUM])
-//  * custom ops (Op::CUSTOM == true): NPAY == 1, void particle(p, m, ell, acc) with acc(L) -> float4.
-#define PIPE 4
+//  * custom ops (Op::CUSTOM == true): NPAY == 1, void particle(p, valid, acc) with acc(L) -> float4; warp-convergent call.
 template<class Op, bool STAGED>
 __device__ __forceinline__ void tile_particles(const TileInfo& t, const TileShared& sh, const Arrays& A,
                                                const float4* __restrict__ sA, const float4* __restrict__ sB, Op& op) {
@@ -165,45 +181,55 @@ __device__ __forceinline__ void tile_particles(const TileInfo& t, const TileShar
     const uint32_t nBatch = (t.end - t.begin + 31u) >> 5;
     for (uint32_t b = warp; b < nBatch; b += TILE_WARPS) {
         const uint32_t p = t.begin + (b << 5) + lane;
-        if (p >= t.end) continue;
         if constexpr (Op::CUSTOM) {
+            // called by all 32 lanes (custom ops may cooperate across the warp); lanes past the tile's end pass valid = false
             const TileAcc<STAGED, Op> acc{ sh, sA, op };
-            op.particle(p, ell_base(p), acc);
+            op.particle(p, p < t.end, acc);
         } else {
+            if (p >= t.end) continue;
             const uint32_t m = __ldg(A.cnt + p);
             float own[Op::NOWN];
             op.load_own(p, own);
             float acc[Op::NSUM];
             #pragma unroll
             for (int s = 0; s < Op::NSUM; s++) acc[s] = 0.0f;
-            const uint16_t* __restrict__ col = A.list16 + ell_base(p);
-            float* __restrict__ ccol = A.coef + ell_base(p);
-            uint32_t Lq[PIPE]; float cq[PIPE];
-            #pragma unroll
-            for (int u = 0; u < PIPE; u++) {
-                Lq[u] = 0u; cq[u] = 0.0f;
-                if ((uint32_t)u < m) { Lq[u] = col[(size_t)u * 32]; if (Op::COEF == 1) cq[u] = ccol[(size_t)u * 32]; }
-            }
-            for (uint32_t k = 0; k < m; k += PIPE) {
-                uint32_t Ln[PIPE]; float cn[PIPE];
-                #pragma unroll
-                for (int u = 0; u < PIPE; u++) {
-                    Ln[u] = 0u; cn[u] = 0.0f;
-                    const uint32_t kk = k + PIPE + u;
-                    if (kk < m) { Ln[u] = col[(size_t)kk * 32]; if (Op::COEF == 1) cn[u] = ccol[(size_t)kk * 32]; }
-                }
-                #pragma unroll
-                for (int u = 0; u < PIPE; u++) {
-                    if (k + u < m) {
-                        float4 a, bb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        if (STAGED) { a = sA[Lq[u]]; if (Op::NPAY > 1) bb = sB[Lq[u]]; }
-                        else { const uint32_t g = tile_local_to_global(sh, Lq[u]); a = op.loadA(g); if (Op::NPAY > 1) bb = op.loadB(g); }
-                        op.pair(own, a, bb, cq[u], acc);
-                        if (Op::COEF == 2) ccol[(size_t)(k + u) * 32] = cq[u];
+            const uint2* __restrict__ col = ell_list(A.list16, p);
+            float4* __restrict__ ccol = reinterpret_cast<float4*>(A.coef) + ell_base(p);
+            const uint32_t nG = (m + 3u) >> 2;
+            uint2 wq = make_uint2(0u, 0u);
+            float4 cq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (nG) { wq = col[0]; if (Op::COEF == 1) cq = ccol[0]; }
+            for (uint32_t g = 0; g < nG; g++) {
+                uint2 wn = make_uint2(0u, 0u);
+                float4 cn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (g + 1u < nG) { wn = col[(size_t)(g + 1u) * 32]; if (Op::COEF == 1) cn = ccol[(size_t)(g + 1u) * 32]; }
+                uint32_t L[4];
+                ell_unpack(wq, L);
+                float c[4] = { cq.x, cq.y, cq.z, cq.w };
+                if (g * 4u + 4u <= m) {
+                    float4 pa[4], pb[4];
+                    #pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        pb[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (STAGED) { pa[u] = sA[L[u]]; if (Op::NPAY > 1) pb[u] = sB[L[u]]; }
+                        else { const uint32_t gi = tile_local_to_global(sh, L[u]); pa[u] = op.loadA(gi); if (Op::NPAY > 1) pb[u] = op.loadB(gi); }
                     }
+                    #pragma unroll
+                    for (int u = 0; u < 4; u++) op.pair(own, pa[u], pb[u], c[u], acc);
+                } else {
+                    #pragma unroll
+                    for (int u = 0; u < 3; u++) {                    // a partial group holds one to three neighbours
+                        if (g * 4u + (uint32_t)u < m) {
+                            float4 xa, xb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            if (STAGED) { xa = sA[L[u]]; if (Op::NPAY > 1) xb = sB[L[u]]; }
+                            else { const uint32_t gi = tile_local_to_global(sh, L[u]); xa = op.loadA(gi); if (Op::NPAY > 1) xb = op.loadB(gi); }
+                            op.pair(own, xa, xb, c[u], acc);
+                        } else c[u] = 0.0f;
+                    }
+                    c[3] = 0.0f;
                 }
-                #pragma unroll
-                for (int u = 0; u < PIPE; u++) { Lq[u] = Ln[u]; cq[u] = cn[u]; }
+                if (Op::COEF == 2) ccol[(size_t)g * 32] = make_float4(c[0], c[1], c[2], c[3]);
+                wq = wn; cq = cn;
             }
             op.finish(p, m, own, acc);
         }
@@ -223,8 +249,9 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
         const TileInfo t = tile_setup(S, cellBegin, tile, sh, cap);
         // local indices are 16-bit: a halo box beyond 65535 particles cannot be encoded (flagged, caught by the host)
         if (checkIndexRange && t.total > 65535u && threadIdx.x == 0) atomicOr(&S->errorFlags, 2u);
+        if (!t.staged && threadIdx.x == 0) atomicAdd(&S->fallbackTiles, 1u);
         if (t.staged) {
-            tile_stage<Op::NPAY>(sh, sA, sB, op);
+            tile_stage<Op::NPAY>(sh, t.total, sA, sB, op);
             __syncthreads();
             tile_particles<Op, true>(t, sh, A, sA, sB, op);
         } else {

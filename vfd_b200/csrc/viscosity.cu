@@ -141,7 +141,7 @@ struct ViscSetupOp {
     }
 };
 
-__global__ void __launch_bounds__(TT_LUT) k_visc_setup(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+__global__ void __launch_bounds__(TT_LUT, 2) k_visc_setup(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
     TileShared& sh = smem_header(smemRaw);
     float* sG = smem_lut<1>(smemRaw);
     load_lut_tile(sG, lutG);
@@ -222,7 +222,7 @@ struct ViscMatvecOp {
 };
 
 template<bool INIT>
-__global__ void __launch_bounds__(TT_MATVEC) k_visc_matvec(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+__global__ void __launch_bounds__(TT_MATVEC, 2) k_visc_matvec(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (!INIT && S->viscActive != 1u) return;
     TileShared& sh = smem_header(smemRaw);
     ViscMatvecOp<INIT> op{ P, A, INIT ? A.cgG : A.cgP, S->dt, 0.0f, 0.0f };
