@@ -260,6 +260,288 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
     }
 }
 
+// =====================================================================================================
+// The asynchronous tile pipeline (pipe_pass): the same tile pass without a CTA-wide barrier in the loop.
+//
+// tile_pass above runs  setup | stage | compute  as phases separated by __syncthreads; ncu shows the price
+// (profiles/r01_ncu_matvec_before_pipeline.txt: 36 % of the warp-stall samples at barriers, the pair loop only a third of the
+// kernel).  pipe_pass splits the CTA into roles that meet only at shared-memory mbarriers:
+//   * PIPE_PRODUCER_WARPS warps build the halo cell table of the CTA's NEXT tile and copy its payload
+//     HBM/L2 -> shared memory with cp.async (LDGSTS: no registers, no binary search — a halo row of six
+//     x-adjacent cells is three contiguous global segments), tracked by the stage's `full` mbarrier
+//     (cp.async.mbarrier.arrive.noinc);
+//   * PIPE_CONSUMER_WARPS warps own one 32-particle batch of the current tile each, gather from the
+//     stage's shared memory, and release the stage through its `empty` mbarrier.
+// A warp that finishes its batch early starts on the next tile (already resident) instead of waiting for
+// the slowest warp; the copy of tile k+2 overlaps the pair loop of tile k+1.  One CTA per SM.
+// Work assignment is static (tile -> CTA round robin, batch -> warp rotating with the running batch count), so every
+// per-thread partial sum is accumulated in the same order run after run: reductions stay bit-reproducible.
+#define PIPE_STAGES 2
+#define PIPE_CONSUMER_WARPS 16
+#define PIPE_PRODUCER_WARPS 2
+#define PIPE_PRODUCER_THREADS (PIPE_PRODUCER_WARPS * 32)
+#define PIPE_THREADS ((PIPE_CONSUMER_WARPS + PIPE_PRODUCER_WARPS) * 32)     // 576
+#define PIPE_CAP 2816          // staged halo particles per stage
+
+struct StageHeader {
+    uint32_t cellG[HALO_CELLS];       // as TileShared
+    uint32_t local[HALO_CELLS + 8];
+    uint32_t begin, end, total, staged;      // begin == 0xffffffff: no more tiles for this CTA
+    uint32_t scan[4];
+};
+struct PipeShared {
+    unsigned long long full[PIPE_STAGES], empty[PIPE_STAGES];
+    double red[4 * 32];
+    StageHeader hdr[PIPE_STAGES];
+};
+__host__ __device__ constexpr size_t pipe_header_bytes() { return (sizeof(PipeShared) + 127) / 128 * 128; }
+// dynamic shared memory: [PipeShared][NLUT tables][stage 0: A, B][stage 1: A, B]; B is 16 or 4 bytes per particle
+template<int NLUT, int ABYTES, int BBYTES> static inline size_t pipe_smem_bytes() {
+    return pipe_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float) + (size_t)PIPE_STAGES * PIPE_CAP * (ABYTES + BBYTES);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival when all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive(unsigned long long* b) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(PIPE_PRODUCER_THREADS) : "memory"); }
+
+__device__ __forceinline__ uint32_t hdr_local_to_global(const StageHeader& H, uint32_t L) {
+    int lo = 0, hi = HALO_CELLS;
+    #pragma unroll
+    for (int it = 0; it < 8; it++) { const int mid = (lo + hi) >> 1; if (hi - lo > 1) { if (H.local[mid] <= L) lo = mid; else hi = mid; } }
+    return H.cellG[lo] + (L - H.local[lo]);
+}
+
+// ---- producer: the two producer warps of a CTA, all 64 threads ------------------------------------
+// Op supplies the global source arrays:  const float4* srcA();  const void* srcB()  (BBYTES 16: float4 array, 4: float array)
+template<class Op>
+__device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Arrays& A, PipeShared& ps, unsigned char* pay, const Op& op,
+                                              uint32_t tile0, uint32_t tile1, bool checkIndexRange) {
+    constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
+    constexpr size_t STAGE_BYTES = (size_t)PIPE_CAP * (16 + BBYTES);
+    const uint32_t pt = threadIdx.x - PIPE_CONSUMER_WARPS * 32, lane = pt & 31u, pw = pt >> 5;
+    const uint32_t nTiles = min(S->nTiles, tile1);
+    const uint32_t* __restrict__ cellBegin = A.cellBegin;
+    const uint32_t tdy = S->tileDim[1], tdz = S->tileDim[2];
+    const int gdx = (int)S->gridDim[0], gdy = (int)S->gridDim[1], gdz = (int)S->gridDim[2];
+    const unsigned char* __restrict__ gA = reinterpret_cast<const unsigned char*>(op.srcA());
+    const unsigned char* __restrict__ gB = reinterpret_cast<const unsigned char*>(op.srcB());
+    uint32_t tile = tile0 + blockIdx.x;
+    for (uint32_t k = 0;; k++, tile += gridDim.x) {
+        uint32_t b0 = 0, e0 = 0;
+        while (tile < nTiles) {
+            b0 = __ldg(cellBegin + tile * TILE_CELLS); e0 = __ldg(cellBegin + tile * TILE_CELLS + TILE_CELLS);
+            if (b0 != e0) break;
+            tile += gridDim.x;
+        }
+        const uint32_t s = k % PIPE_STAGES, u = k / PIPE_STAGES;
+        StageHeader& H = ps.hdr[s];
+        if (tile >= nTiles) {
+            mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);
+            if (pt == 0) { H.begin = 0xffffffffu; H.end = 0xffffffffu; H.total = 0; H.staged = 0; }
+            mbar_arrive(&ps.full[s]);
+            if (pt == 0) mbar_arrive(&ps.full[s]);
+            break;
+        }
+        // halo cell table: thread pt owns cells 4pt .. 4pt+3 of the 6x6x6 box (box order hz, hy, hx); the loads are
+        // issued before the stage is known to be free, so their latency overlaps the consumers' work
+        const uint32_t tz = tile % tdz, ty = (tile / tdz) % tdy, tx = tile / (tdz * tdy);
+        uint32_t beg[4], cnt[4];
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int c = (int)pt * 4 + i;
+            beg[i] = 0; cnt[i] = 0;
+            if (c < HALO_CELLS) {
+                const int hx = c % 6, hy = (c / 6) % 6, hz = c / 36;
+                const int cx = (int)(tx << 2) + hx - 1, cy = (int)(ty << 2) + hy - 1, cz = (int)(tz << 2) + hz - 1;
+                if (cx >= 0 && cy >= 0 && cz >= 0 && cx < gdx && cy < gdy && cz < gdz) {
+                    const uint32_t key = cell_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, S);
+                    beg[i] = __ldg(cellBegin + key);
+                    cnt[i] = __ldg(cellBegin + key + 1) - beg[i];
+                }
+            }
+        }
+        const uint32_t mine = (cnt[0] + cnt[1]) + (cnt[2] + cnt[3]);
+        uint32_t inc = mine;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += y; }
+        mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);          // every consumer warp has released the stage's previous tile
+        if (lane == 31) H.scan[pw] = inc;
+        producer_sync();
+        uint32_t run = (pw ? H.scan[0] : 0u) + inc - mine;
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int c = (int)pt * 4 + i;
+            if (c < HALO_CELLS) { H.cellG[c] = beg[i]; H.local[c] = run; }
+            run += cnt[i];
+        }
+        const uint32_t total = H.scan[0] + H.scan[1];
+        const bool staged = total <= PIPE_CAP;
+        if (pt == 0) {
+            H.local[HALO_CELLS] = total;
+            H.begin = b0; H.end = e0; H.total = total; H.staged = staged ? 1u : 0u;
+            if (checkIndexRange && total > 65535u) atomicOr(&S->errorFlags, 2u);
+            if (!staged) atomicAdd(&S->fallbackTiles, 1u);
+        }
+        producer_sync();                                  // the table is complete for both producer warps
+        if (staged) {
+            unsigned char* sA = pay + s * STAGE_BYTES;
+            unsigned char* sB = sA + (size_t)PIPE_CAP * 16;
+            // one halo row (six x-adjacent cells, contiguous in the local index space) per warp and turn: the first cell
+            // belongs to the tile on the left, the next four are contiguous in the sorted arrays, the last to the tile on the right
+            for (uint32_t r = pw; r < 36u; r += PIPE_PRODUCER_WARPS) {
+                const uint32_t c0 = r * 6u;
+                const uint32_t lA = H.local[c0], lB = H.local[c0 + 1], lC = H.local[c0 + 5], lE = (c0 + 6 < HALO_CELLS) ? H.local[c0 + 6] : total;
+                const uint32_t g0 = H.cellG[c0], g1 = H.cellG[c0 + 1], g5 = H.cellG[c0 + 5];
+                for (uint32_t l = lA + lane; l < lE; l += 32u) {
+                    const uint32_t g = l < lB ? g0 + (l - lA) : (l < lC ? g1 + (l - lB) : g5 + (l - lC));
+                    cp_async16(sA + (size_t)l * 16, gA + (size_t)g * 16);
+                    if (BBYTES == 16) cp_async16(sB + (size_t)l * 16, gB + (size_t)g * 16);
+                    if (BBYTES == 4) cp_async4(sB + (size_t)l * 4, gB + (size_t)g * 4);
+                }
+            }
+        }
+        cp_async_arrive(&ps.full[s]);                     // 64 arrivals: each thread's copies have landed
+        if (pt == 0) mbar_arrive(&ps.full[s]);            // + 1: the header (release)
+    }
+}
+
+template<class Op> struct PipeAcc {
+    const StageHeader& H; const float4* sA; const Op& op; bool staged;
+    __device__ __forceinline__ float4 operator()(uint32_t L) const { return staged ? sA[L] : op.loadA(hdr_local_to_global(H, L)); }
+};
+
+// ---- consumer: one batch of 32 particles (one per lane) -------------------------------------------
+template<class Op, bool STAGED>
+__device__ __forceinline__ void pipe_batch(uint32_t p, bool valid, const StageHeader& H, const Arrays& A,
+                                           const float4* __restrict__ sA, const void* __restrict__ sBv, Op& op) {
+    constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
+    const float4* __restrict__ sB = reinterpret_cast<const float4*>(sBv);
+    const float* __restrict__ sB1 = reinterpret_cast<const float*>(sBv);
+    auto gatherB = [&](uint32_t L) -> float4 {
+        if (BBYTES == 16) return sB[L];
+        if (BBYTES == 4) return make_float4(sB1[L], 0.0f, 0.0f, 0.0f);
+        return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    };
+    if (!valid) return;
+    const uint32_t m = __ldg(A.cnt + p);
+    float own[Op::NOWN];
+    op.load_own(p, own);
+    float acc[Op::NSUM];
+    #pragma unroll
+    for (int s = 0; s < Op::NSUM; s++) acc[s] = 0.0f;
+    const uint2* __restrict__ col = ell_list(A.list16, p);
+    float4* __restrict__ ccol = reinterpret_cast<float4*>(A.coef) + ell_base(p);
+    const uint32_t nG = (m + 3u) >> 2;
+    uint2 wq = make_uint2(0u, 0u);
+    float4 cq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (nG) { wq = col[0]; if (Op::COEF == 1) cq = ccol[0]; }
+    for (uint32_t g = 0; g < nG; g++) {
+        uint2 wn = make_uint2(0u, 0u);
+        float4 cn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (g + 1u < nG) { wn = col[(size_t)(g + 1u) * 32]; if (Op::COEF == 1) cn = ccol[(size_t)(g + 1u) * 32]; }
+        uint32_t L[4];
+        ell_unpack(wq, L);
+        float c[4] = { cq.x, cq.y, cq.z, cq.w };
+        if (g * 4u + 4u <= m) {
+            float4 pa[4], pb[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (STAGED) { pa[u] = sA[L[u]]; pb[u] = gatherB(L[u]); }
+                else { const uint32_t gi = hdr_local_to_global(H, L[u]); pa[u] = op.loadA(gi); pb[u] = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) op.pair(own, pa[u], pb[u], c[u], acc);
+        } else {
+            #pragma unroll
+            for (int u = 0; u < 3; u++) {                    // a partial group holds one to three neighbours
+                if (g * 4u + (uint32_t)u < m) {
+                    float4 xa, xb;
+                    if (STAGED) { xa = sA[L[u]]; xb = gatherB(L[u]); }
+                    else { const uint32_t gi = hdr_local_to_global(H, L[u]); xa = op.loadA(gi); xb = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+                    op.pair(own, xa, xb, c[u], acc);
+                } else c[u] = 0.0f;
+            }
+            c[3] = 0.0f;
+        }
+        if (Op::COEF == 2) ccol[(size_t)g * 32] = make_float4(c[0], c[1], c[2], c[3]);
+        wq = wn; cq = cn;
+    }
+    op.finish(p, m, own, acc);
+}
+
+template<class Op>
+__device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, const unsigned char* pay, Op& op) {
+    constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
+    constexpr size_t STAGE_BYTES = (size_t)PIPE_CAP * (16 + BBYTES);
+    const uint32_t lane = threadIdx.x & 31u, cw = threadIdx.x >> 5;
+    uint32_t rot = 0;                                     // running batch count of this CTA (mod the consumer warps)
+    for (uint32_t k = 0;; k++) {
+        const uint32_t s = k % PIPE_STAGES, u = k / PIPE_STAGES;
+        mbar_wait(&ps.full[s], u & 1u);
+        const StageHeader& H = ps.hdr[s];
+        const uint32_t begin = H.begin, end = H.end;
+        if (begin == 0xffffffffu) break;
+        const bool staged = H.staged != 0u;
+        const float4* sA = reinterpret_cast<const float4*>(pay + s * STAGE_BYTES);
+        const void* sB = pay + s * STAGE_BYTES + (size_t)PIPE_CAP * 16;
+        const uint32_t nBatch = (end - begin + 31u) >> 5;
+        // batch b of this tile goes to warp (rot + b) mod W: consecutive batches of consecutive tiles visit the warps in turn
+        for (uint32_t b = (cw + PIPE_CONSUMER_WARPS - rot) % PIPE_CONSUMER_WARPS; b < nBatch; b += PIPE_CONSUMER_WARPS) {
+            const uint32_t p = begin + (b << 5) + lane;
+            if constexpr (Op::CUSTOM) {
+                const PipeAcc<Op> acc{ H, sA, op, staged };
+                op.particle(p, p < end, acc, H);
+            } else {
+                if (staged) pipe_batch<Op, true>(p, p < end, H, A, sA, sB, op);
+                else        pipe_batch<Op, false>(p, p < end, H, A, sA, sB, op);
+            }
+        }
+        rot = (rot + nBatch) % PIPE_CONSUMER_WARPS;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ps.empty[s]);
+    }
+}
+
+// Called by all PIPE_THREADS threads of the CTA (after any lookup table has been loaded; contains __syncthreads).
+template<class Op>
+__device__ __forceinline__ void pipe_pass(DevState* __restrict__ S, const Arrays& A, PipeShared& ps, unsigned char* pay, Op& op,
+                                          uint32_t tile0, uint32_t tile1, bool checkIndexRange = false) {
+    if (threadIdx.x == 0) {
+        #pragma unroll
+        for (int s = 0; s < PIPE_STAGES; s++) { mbar_init(&ps.full[s], PIPE_PRODUCER_THREADS + 1); mbar_init(&ps.empty[s], PIPE_CONSUMER_WARPS); }
+    }
+    __syncthreads();
+    if (threadIdx.x >= PIPE_CONSUMER_WARPS * 32) pipe_producer(S, A, ps, pay, op, tile0, tile1, checkIndexRange);
+    else pipe_consumer(A, ps, pay, op);
+    __syncthreads();
+}
+
+__device__ __forceinline__ PipeShared& pipe_header(unsigned char* raw) { return *reinterpret_cast<PipeShared*>(raw); }
+template<int NLUT> __device__ __forceinline__ float* pipe_lut(unsigned char* raw) { return reinterpret_cast<float*>(raw + pipe_header_bytes()); }
+template<int NLUT> __device__ __forceinline__ unsigned char* pipe_pay(unsigned char* raw) { return raw + pipe_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float); }
+
 // The particles this rank owns (multi-GPU: the tiles [tile0, tile1) of the local grid; the tile columns before and
 // after hold ghost copies of the neighbour slabs' edge particles): a contiguous range because tiles are x-slowest.
 __device__ __forceinline__ void owned_range(const Params& P, const uint32_t* __restrict__ cellBegin, uint32_t& b, uint32_t& e) {

@@ -21,6 +21,7 @@
 #include "tile.cuh"
 #include "control.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace vfd {
 
@@ -176,6 +177,9 @@ struct ViscMatvecOp {
     const float4* __restrict__ x;    // the vector the operator is applied to: g (INIT) or the search direction p
     float dt;
     float s0, s1;
+    static constexpr int BBYTES = 16;
+    __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
+    __device__ __forceinline__ const void* srcB() const { return x; }
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t g) const { return x[g]; }
     __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
@@ -233,6 +237,26 @@ __global__ void __launch_bounds__(TT_MATVEC, 2) k_visc_matvec(const __grid_const
     if (block_reduce_publish<2>(v, A.partials, ticket, sh.red)) {
         double tot[2];
         last_block_fold<2>(tot, A.partials, sh.red);
+        if (threadIdx.x == 0) {
+            if (INIT) finish_reduction<2>(SITE_VISC_INIT, P, S, tot);
+            else { const double t1[1] = { tot[0] }; finish_reduction<1>(SITE_VISC_PQ, P, S, t1); }
+            *ticket = 0;
+        }
+    }
+}
+
+// the same product on the asynchronous tile pipeline (tile.cuh: pipe_pass)
+template<bool INIT>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_visc_matvec_pipe(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+    if (!INIT && S->viscActive != 1u) return;
+    PipeShared& ps = pipe_header(smemRaw);
+    ViscMatvecOp<INIT> op{ P, A, INIT ? A.cgG : A.cgP, S->dt, 0.0f, 0.0f };
+    pipe_pass(S, A, ps, pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
+    double v[2] = { (double)op.s0, (double)op.s1 };
+    uint32_t* ticket = &S->ticket[5];
+    if (block_reduce_publish<2>(v, A.partials, ticket, ps.red)) {
+        double tot[2];
+        last_block_fold<2>(tot, A.partials, ps.red);
         if (threadIdx.x == 0) {
             if (INIT) finish_reduction<2>(SITE_VISC_INIT, P, S, tot);
             else { const double t1[1] = { tot[0] }; finish_reduction<1>(SITE_VISC_PQ, P, S, t1); }
@@ -315,7 +339,26 @@ void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A
     LaunchScope ls(L, KID_VISC_SETUP);
     k_visc_setup<<<g0, TT_LUT, s0, L.stream>>>(P, A, S, lutG);
 }
+static int pipe_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("VFD_TILE_PIPELINE"); mode = e ? atoi(e) : 1; }
+    return mode;
+}
+
 void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init) {
+    if (pipe_mode()) {
+        const size_t sp = pipe_smem_bytes<0, 16, 16>();
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(k_visc_matvec_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
+            cudaFuncSetAttribute(k_visc_matvec_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
+            attr = true;
+        }
+        LaunchScope ls(L, init ? KID_VISC_MATVEC0 : KID_VISC_MATVEC);
+        if (init) k_visc_matvec_pipe<true><<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S);
+        else      k_visc_matvec_pipe<false><<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S);
+        return;
+    }
     const size_t s1 = tile_smem_bytes<0, 2>(STAGE_CAP);
     if (init) {
         const uint32_t g1 = tile_grid(k_visc_matvec<true>, s1, L, TT_MATVEC);
