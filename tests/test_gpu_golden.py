@@ -68,7 +68,7 @@ def test_one_step_from_golden_state(name, lib_built):
     assert dbg.PressureSolverIterationCount == g["its_out"][1]
     assert abs(int(dbg.ViscositySolverIterationCount) - int(g["its_out"][2])) <= 1
     tol = field_tolerances(g)
-    bad = {k: v for k, v in errs.items() if v[0] > tol[k]}
+    bad = parity.beyond_tolerance(errs, tol, out, g["state_out"])
     assert not bad, "fields beyond tolerance %s:\n%s" % ({k: "%.1e" % tol[k] for k in bad}, parity.format_errors(bad))
 
 

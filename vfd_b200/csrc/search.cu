@@ -177,6 +177,57 @@ __global__ void __launch_bounds__(VFD_TPB) k_scan_apply(Params P, const DevState
     if (blockIdx.x == 0 && threadIdx.x == 0) cellBegin[nCells] = P.n;
 }
 
+// S3b: static, cost-balanced partition of the owned tiles over the G CTAs of a pipelined tile pass (tile.cuh):
+// CTA c gets the contiguous tile range [ctaTile[c], ctaTile[c+1]) holding ~1/G of the total weight, a non-empty
+// tile weighing its particle count plus a constant for staging its halo box (a surface tile with 30 particles still
+// stages ~1700).  A fixed partition keeps every reduction's summation order fixed (bit-reproducible), which a dynamic
+// tile queue would not.  One block; thread i owns a contiguous chunk of tiles.
+#define PARTITION_THREADS 1024
+__global__ void __launch_bounds__(PARTITION_THREADS) k_partition_tiles(Params P, const DevState* __restrict__ S, const uint32_t* __restrict__ cellBegin,
+                                                                       uint32_t* __restrict__ ctaTile, uint32_t G, uint32_t tileWeight) {
+    __shared__ unsigned long long shScan[PARTITION_THREADS / 32 + 1];
+    const uint32_t t0 = P.tile0, t1 = min(S->nTiles, P.tile1);
+    const uint32_t nT = t1 > t0 ? t1 - t0 : 0u;
+    const uint32_t chunk = (nT + PARTITION_THREADS - 1) / PARTITION_THREADS;
+    const uint32_t a = min(t0 + threadIdx.x * chunk, t1), b = min(a + chunk, t1);
+    auto weight = [&](uint32_t t) -> uint32_t {
+        const uint32_t n = cellBegin[(size_t)(t + 1) * TILE_CELLS] - cellBegin[(size_t)t * TILE_CELLS];
+        return n ? n + tileWeight : 0u;
+    };
+    unsigned long long mine = 0;
+    for (uint32_t t = a; t < b; t++) mine += weight(t);
+    // block-wide exclusive scan of the chunk sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = mine;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) shScan[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int w = 0; w < PARTITION_THREADS / 32; w++) { const unsigned long long v = shScan[w]; shScan[w] = run; run += v; }
+        shScan[PARTITION_THREADS / 32] = run;
+    }
+    __syncthreads();
+    const unsigned long long total = shScan[PARTITION_THREADS / 32];
+    unsigned long long run = shScan[warp] + inc - mine;          // weight of all tiles before this chunk
+    // boundary c sits at the first tile where the cumulative weight reaches c * total / G
+    if (threadIdx.x == 0) { ctaTile[0] = t0; ctaTile[G] = t1; }
+    if (total == 0) { for (uint32_t c = 1 + threadIdx.x; c < G; c += blockDim.x) ctaTile[c] = t1; return; }
+    uint32_t c = (uint32_t)((run * G + total - 1) / total);       // smallest c with c * total / G >= run  (ceil(run * G / total))
+    if (c == 0) c = 1;
+    for (uint32_t t = a; t < b; t++) {
+        const unsigned long long next = run + weight(t);
+        while (c < G && (unsigned long long)c * total / G < next) {
+            if ((unsigned long long)c * total / G >= run) ctaTile[c] = t;
+            c++;
+        }
+        run = next;
+    }
+    // boundaries that fall exactly at the total weight (only possible for trailing empty ranges)
+    if (threadIdx.x == blockDim.x - 1) while (c < G) { ctaTile[c] = t1; c++; }
+}
+
 // S4: scatter slot indices into cell order (arbitrary order inside a cell)
 __global__ void __launch_bounds__(VFD_TPB) k_scatter(Params P, const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank,
                                                      const uint32_t* __restrict__ cellBegin, uint32_t* __restrict__ tmpIdx) {
@@ -227,13 +278,23 @@ struct SearchOp {
         const float4 xi = pos[p];
         const uint3 c = cell_of(xi, S, invCell);
         const uint32_t hx = (c.x & 3u) + 1u, hy = (c.y & 3u) + 1u, hz = (c.z & 3u) + 1u;   // box coordinates of the own cell
+        const TileShared& tab = *sh;
         uint2* col = reinterpret_cast<uint2*>(list) + ell_base(p);
         uint32_t m = 0;
-        uint32_t L[4] = { 0u, 0u, 0u, 0u };                  // the group being filled: written as one 8-byte word
+        // Slot order.  Every later pass has lane l of a warp gather, at slot s, its s-th neighbour's 16-byte payload from
+        // shared memory; an LDS.128 is served eight lanes at a time and is conflict-free when those eight local indices are
+        // distinct mod 8 (profiles/r01_ncu_*: in candidate order 8.9 wavefronts per LDS.128 against an ideal 4).  The set is
+        // what parity fixes, the order is free: neighbours are bucketed by index mod 8 as they are found, and slot s then
+        // takes one of residue (lane + s) mod 8 while that bucket lasts (else from the fullest one), so the lanes of a
+        // quarter-warp walk the eight bank groups in step: ~5.6 wavefronts per LDS.128 on a settled fluid.
+        // Buckets: 8 x SLOT_BUCKET entries of thread-local scratch; the eight fill counts are the bytes of one 64-bit register.
+        constexpr uint32_t SLOT_BUCKET = 12;                 // 96 entries >= 70; a full bucket spills into the next one
+        uint16_t bucket[8 * SLOT_BUCKET];
+        unsigned long long fill = 0ull;
         for (int dz = -1; dz <= 1 && m < VFD_MAX_NEIGHBORS; dz++) {
             for (int dy = -1; dy <= 1 && m < VFD_MAX_NEIGHBORS; dy++) {
                 const uint32_t c0 = ((hz + dz) * 6u + (hy + dy)) * 6u + hx - 1u;
-                const uint32_t jb = sh->local[c0], je = sh->local[c0 + 3u];
+                const uint32_t jb = tab.local[c0], je = tab.local[c0 + 3u];
                 for (uint32_t j = jb; j < je; j++) {
                     const float4 xj = acc(j);
                     const float dx = xj.x - xi.x, dyy = xj.y - xi.y, dzz = xj.z - xi.z;
@@ -241,16 +302,34 @@ struct SearchOp {
                     if (FMA) d2 = __fmaf_rn(dzz, dzz, __fmaf_rn(dx, dx, __fmul_rn(dyy, dyy)));   // how nvcc compiles ParticleSearchKernels.cu:124
                     else     d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dyy, dyy)), __fmul_rn(dzz, dzz));
                     if (d2 < h2 && d2 > 0.0f) {
-                        // static register indexing: select the slot without a local-memory array
-                        const uint32_t q = m & 3u;
-                        L[0] = q == 0u ? j : L[0]; L[1] = q == 1u ? j : L[1]; L[2] = q == 2u ? j : L[2]; L[3] = q == 3u ? j : L[3];
-                        if (q == 3u) { col[(size_t)(m >> 2) * 32] = ell_pack(L); L[0] = L[1] = L[2] = L[3] = 0u; }
+                        uint32_t r = j & 7u;
+                        uint32_t f = (uint32_t)(fill >> (8u * r)) & 0xffu;
+                        while (f == SLOT_BUCKET) { r = (r + 1u) & 7u; f = (uint32_t)(fill >> (8u * r)) & 0xffu; }
+                        bucket[r * SLOT_BUCKET + f] = (uint16_t)j;
+                        fill += 1ull << (8u * r);
                         if (++m == VFD_MAX_NEIGHBORS) break;
                     }
                 }
             }
         }
-        if (m & 3u) col[(size_t)(m >> 2) * 32] = ell_pack(L);
+        {
+            const uint32_t lane = threadIdx.x & 31u;
+            uint32_t L[4] = { 0u, 0u, 0u, 0u };
+            for (uint32_t sidx = 0; sidx < m; sidx++) {
+                uint32_t r = (lane + sidx) & 7u;
+                uint32_t f = (uint32_t)(fill >> (8u * r)) & 0xffu;
+                if (f == 0u) {                                 // that bucket is used up: take from the fullest
+                    #pragma unroll
+                    for (uint32_t q = 0; q < 8u; q++) { const uint32_t fq = (uint32_t)(fill >> (8u * q)) & 0xffu; if (fq > f) { f = fq; r = q; } }
+                }
+                fill -= 1ull << (8u * r);
+                const uint32_t j = bucket[r * SLOT_BUCKET + f - 1u];
+                const uint32_t q = sidx & 3u;
+                L[0] = q == 0u ? j : L[0]; L[1] = q == 1u ? j : L[1]; L[2] = q == 2u ? j : L[2]; L[3] = q == 3u ? j : L[3];
+                if (q == 3u) { col[(size_t)(sidx >> 2) * 32] = ell_pack(L); L[0] = L[1] = L[2] = L[3] = 0u; }
+            }
+            if (m & 3u) col[(size_t)(m >> 2) * 32] = ell_pack(L);
+        }
         cnt[p] = m;
     }
 };
@@ -276,6 +355,7 @@ void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, 
     { LaunchScope ls(L, KID_SCAN); k_scan_tiles<<<st, VFD_TPB, 0, L.stream>>>(S, A.cellCount, A.tileSums); }
     { LaunchScope ls(L, KID_SCAN); k_scan_tile_sums<<<1, 1024, 0, L.stream>>>(S, A.tileSums); }
     { LaunchScope ls(L, KID_SCAN); k_scan_apply<<<st, VFD_TPB, 0, L.stream>>>(P, S, A.cellCount, A.tileSums, A.cellBegin); }
+    { LaunchScope ls(L, KID_SCAN); k_partition_tiles<<<1, PARTITION_THREADS, 0, L.stream>>>(P, S, A.cellBegin, A.ctaTile, (uint32_t)L.numSMs, P.tune[2] ? (uint32_t)P.tune[2] : 256u); }
     { LaunchScope ls(L, KID_SCATTER); k_scatter<<<nb, VFD_TPB, 0, L.stream>>>(P, A.key, A.rank, A.cellBegin, A.tmpIdx); }
     { LaunchScope ls(L, KID_REORDER); k_reorder<<<nb, VFD_TPB, 0, L.stream>>>(P, A); }
     std::swap(A.pos, A.pos2); std::swap(A.vel, A.vel2); std::swap(A.dv, A.dv2); std::swap(A.nbar, A.nbar2);

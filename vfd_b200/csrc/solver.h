@@ -33,6 +33,7 @@ struct Arrays {
     float    *coef;                         // per-pair viscosity coefficient, same ELL layout (frozen during the PCG)
     float4   *bcoef[VFD_MAX_BODIES];        // per-particle boundary-friction coefficients of the 4 tangential samples
     uint32_t *key, *rank, *tmpIdx, *cellCount, *cellBegin, *tileSums;
+    uint32_t *ctaTile;                      // balanced static partition of the tiles over the CTAs of a pipelined pass (search.cu)
     // reductions
     double* partials;
 };

@@ -276,17 +276,24 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 // the slowest warp; the copy of tile k+2 overlaps the pair loop of tile k+1.  One CTA per SM.
 // Work assignment is static (tile -> CTA round robin, batch -> warp rotating with the running batch count), so every
 // per-thread partial sum is accumulated in the same order run after run: reductions stay bit-reproducible.
-#define PIPE_STAGES 2
+#define PIPE_STAGES 4          // tiles in flight per CTA (header slots); their payloads share one ring of PIPE_RING particle slots
 #define PIPE_CONSUMER_WARPS 16
-#define PIPE_PRODUCER_WARPS 2
+#define PIPE_PRODUCER_WARPS 4
 #define PIPE_PRODUCER_THREADS (PIPE_PRODUCER_WARPS * 32)
+#define PIPE_CELLS_PER_THREAD ((HALO_CELLS + PIPE_PRODUCER_THREADS - 1) / PIPE_PRODUCER_THREADS)
 #define PIPE_THREADS ((PIPE_CONSUMER_WARPS + PIPE_PRODUCER_WARPS) * 32)     // 576
-#define PIPE_CAP 2816          // staged halo particles per stage
+#define PIPE_CAP 2816          // largest halo box that is staged (larger ones take the exact global-memory path)
+#define PIPE_RING (2 * PIPE_CAP) // payload ring, in particles: two worst-case boxes, three to four typical ones (~1700)
+#define PIPE_LOOKAHEAD 3       // neighbour groups (of four) in flight per lane
+
+__device__ __forceinline__ uint2 ldg_stream(const uint2* p) { return __ldg(p); }
+__device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldg(p); }
 
 struct StageHeader {
     uint32_t cellG[HALO_CELLS];       // as TileShared
     uint32_t local[HALO_CELLS + 8];
     uint32_t begin, end, total, staged;      // begin == 0xffffffff: no more tiles for this CTA
+    uint32_t base, pad[3];                   // first ring slot of this tile's payload
     uint32_t scan[4];
 };
 struct PipeShared {
@@ -297,7 +304,7 @@ struct PipeShared {
 __host__ __device__ constexpr size_t pipe_header_bytes() { return (sizeof(PipeShared) + 127) / 128 * 128; }
 // dynamic shared memory: [PipeShared][NLUT tables][stage 0: A, B][stage 1: A, B]; B is 16 or 4 bytes per particle
 template<int NLUT, int ABYTES, int BBYTES> static inline size_t pipe_smem_bytes() {
-    return pipe_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float) + (size_t)PIPE_STAGES * PIPE_CAP * (ABYTES + BBYTES);
+    return pipe_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float) + (size_t)PIPE_RING * (ABYTES + BBYTES);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -324,6 +331,11 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_arrive(unsigned long long* b) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(b)) : "memory");
 }
+// fire-and-forget prefetch of a contiguous byte range into L2 (16-byte granularity; the range is widened to it)
+__device__ __forceinline__ void l2_prefetch(const void* base, size_t byteBegin, size_t byteEnd) {
+    const size_t a = byteBegin & ~(size_t)15, e = (byteEnd + 15) & ~(size_t)15;
+    if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(reinterpret_cast<const unsigned char*>(base) + a), "r"((uint32_t)(e - a)) : "memory");
+}
 __device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(PIPE_PRODUCER_THREADS) : "memory"); }
 
 __device__ __forceinline__ uint32_t hdr_local_to_global(const StageHeader& H, uint32_t L) {
@@ -339,38 +351,38 @@ template<class Op>
 __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Arrays& A, PipeShared& ps, unsigned char* pay, const Op& op,
                                               uint32_t tile0, uint32_t tile1, bool checkIndexRange) {
     constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
-    constexpr size_t STAGE_BYTES = (size_t)PIPE_CAP * (16 + BBYTES);
     const uint32_t pt = threadIdx.x - PIPE_CONSUMER_WARPS * 32, lane = pt & 31u, pw = pt >> 5;
-    const uint32_t nTiles = min(S->nTiles, tile1);
+    // ring bookkeeping (identical in every producer thread): region of the tiles k-1, k-2, k-3 and the next free slot
+    uint32_t regB[PIPE_STAGES - 1], regE[PIPE_STAGES - 1];
+    #pragma unroll
+    for (int j = 0; j < PIPE_STAGES - 1; j++) { regB[j] = 0; regE[j] = 0; }
+    uint32_t ringNext = 0;
     const uint32_t* __restrict__ cellBegin = A.cellBegin;
     const uint32_t tdy = S->tileDim[1], tdz = S->tileDim[2];
     const int gdx = (int)S->gridDim[0], gdy = (int)S->gridDim[1], gdz = (int)S->gridDim[2];
     const unsigned char* __restrict__ gA = reinterpret_cast<const unsigned char*>(op.srcA());
     const unsigned char* __restrict__ gB = reinterpret_cast<const unsigned char*>(op.srcB());
-    uint32_t tile = tile0 + blockIdx.x;
-    for (uint32_t k = 0;; k++, tile += gridDim.x) {
-        uint32_t b0 = 0, e0 = 0;
+    // this CTA's tiles: a contiguous, particle-balanced range (search.cu: k_partition_tiles); tile0/tile1 are folded into it
+    const bool roundRobin = op.P.tune[3] == 0;      // default: tile t -> CTA t mod G (neighbouring CTAs share halo boxes in L2 at the same time)
+    uint32_t tile = roundRobin ? tile0 + blockIdx.x : __ldg(A.ctaTile + blockIdx.x);
+    const uint32_t nTiles = roundRobin ? min(S->nTiles, tile1) : min(min(S->nTiles, tile1), __ldg(A.ctaTile + blockIdx.x + 1));
+    const uint32_t tileStep = roundRobin ? gridDim.x : 1u;
+    // Thread pt owns PIPE_CELLS_PER_THREAD consecutive cells of the 6x6x6 box (box order hz, hy, hx).  The lookup of the
+    // CTA's next non-empty tile and the loads of its cell table are issued one tile ahead (right after the previous
+    // tile's copies), so their latency overlaps the copies and the wait for a free header slot.
+    uint32_t b0 = 0, e0 = 0;
+    uint32_t beg[PIPE_CELLS_PER_THREAD], cnt[PIPE_CELLS_PER_THREAD];
+    auto next_tile = [&]() {
         while (tile < nTiles) {
             b0 = __ldg(cellBegin + tile * TILE_CELLS); e0 = __ldg(cellBegin + tile * TILE_CELLS + TILE_CELLS);
             if (b0 != e0) break;
-            tile += gridDim.x;
+            tile += tileStep;
         }
-        const uint32_t s = k % PIPE_STAGES, u = k / PIPE_STAGES;
-        StageHeader& H = ps.hdr[s];
-        if (tile >= nTiles) {
-            mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);
-            if (pt == 0) { H.begin = 0xffffffffu; H.end = 0xffffffffu; H.total = 0; H.staged = 0; }
-            mbar_arrive(&ps.full[s]);
-            if (pt == 0) mbar_arrive(&ps.full[s]);
-            break;
-        }
-        // halo cell table: thread pt owns cells 4pt .. 4pt+3 of the 6x6x6 box (box order hz, hy, hx); the loads are
-        // issued before the stage is known to be free, so their latency overlaps the consumers' work
+        if (tile >= nTiles) return;
         const uint32_t tz = tile % tdz, ty = (tile / tdz) % tdy, tx = tile / (tdz * tdy);
-        uint32_t beg[4], cnt[4];
         #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int c = (int)pt * 4 + i;
+        for (int i = 0; i < PIPE_CELLS_PER_THREAD; i++) {
+            const int c = (int)pt * PIPE_CELLS_PER_THREAD + i;
             beg[i] = 0; cnt[i] = 0;
             if (c < HALO_CELLS) {
                 const int hx = c % 6, hy = (c / 6) % 6, hz = c / 36;
@@ -382,44 +394,106 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
                 }
             }
         }
-        const uint32_t mine = (cnt[0] + cnt[1]) + (cnt[2] + cnt[3]);
+    };
+    next_tile();
+    for (uint32_t k = 0;; k++) {
+        const uint32_t s = k % PIPE_STAGES, u = k / PIPE_STAGES;
+        StageHeader& H = ps.hdr[s];
+        if (tile >= nTiles) {
+            mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);
+            if (pt == 0) { H.begin = 0xffffffffu; H.end = 0xffffffffu; H.total = 0; H.staged = 0; }
+            mbar_arrive(&ps.full[s]);
+            if (pt == 0) mbar_arrive(&ps.full[s]);
+            break;
+        }
+        const uint32_t tb = b0, te = e0;
+        uint32_t mine = 0;
+        #pragma unroll
+        for (int i = 0; i < PIPE_CELLS_PER_THREAD; i++) mine += cnt[i];
         uint32_t inc = mine;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += y; }
-        mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);          // every consumer warp has released the stage's previous tile
+        mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);          // every consumer warp has released the slot's previous tile
         if (lane == 31) H.scan[pw] = inc;
         producer_sync();
-        uint32_t run = (pw ? H.scan[0] : 0u) + inc - mine;
+        uint32_t run = inc - mine, total = 0;
         #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int c = (int)pt * 4 + i;
+        for (int w = 0; w < PIPE_PRODUCER_WARPS; w++) { const uint32_t v = H.scan[w]; if ((uint32_t)w < pw) run += v; total += v; }
+        #pragma unroll
+        for (int i = 0; i < PIPE_CELLS_PER_THREAD; i++) {
+            const int c = (int)pt * PIPE_CELLS_PER_THREAD + i;
             if (c < HALO_CELLS) { H.cellG[c] = beg[i]; H.local[c] = run; }
             run += cnt[i];
         }
-        const uint32_t total = H.scan[0] + H.scan[1];
         const bool staged = total <= PIPE_CAP;
+        // ring space: the tile's payload takes `total` contiguous slots; tiles still in flight whose region it would
+        // overlap are waited for, oldest first (consumers release tiles in order)
+        uint32_t base = 0;
+        if (staged) {
+            base = ringNext + total <= PIPE_RING ? ringNext : 0u;
+            #pragma unroll
+            for (int j = PIPE_STAGES - 2; j >= 0; j--) {            // j = 2: tile k-3 ... j = 0: tile k-1
+                const uint32_t kk = k - 1u - (uint32_t)j;
+                if (k >= 1u + (uint32_t)j && regE[j] > regB[j] && base < regE[j] && regB[j] < base + total)
+                    mbar_wait(&ps.empty[kk % PIPE_STAGES], (kk / PIPE_STAGES) & 1u);
+            }
+            ringNext = base + total;
+        }
+        #pragma unroll
+        for (int j = PIPE_STAGES - 2; j > 0; j--) { regB[j] = regB[j - 1]; regE[j] = regE[j - 1]; }
+        regB[0] = base; regE[0] = staged ? base + total : base;
         if (pt == 0) {
             H.local[HALO_CELLS] = total;
-            H.begin = b0; H.end = e0; H.total = total; H.staged = staged ? 1u : 0u;
+            H.begin = tb; H.end = te; H.total = total; H.staged = staged ? 1u : 0u; H.base = base;
             if (checkIndexRange && total > 65535u) atomicOr(&S->errorFlags, 2u);
             if (!staged) atomicAdd(&S->fallbackTiles, 1u);
         }
-        producer_sync();                                  // the table is complete for both producer warps
+        producer_sync();                                  // the table is complete for every producer warp
         if (staged) {
-            unsigned char* sA = pay + s * STAGE_BYTES;
-            unsigned char* sB = sA + (size_t)PIPE_CAP * 16;
-            // one halo row (six x-adjacent cells, contiguous in the local index space) per warp and turn: the first cell
-            // belongs to the tile on the left, the next four are contiguous in the sorted arrays, the last to the tile on the right
-            for (uint32_t r = pw; r < 36u; r += PIPE_PRODUCER_WARPS) {
-                const uint32_t c0 = r * 6u;
-                const uint32_t lA = H.local[c0], lB = H.local[c0 + 1], lC = H.local[c0 + 5], lE = (c0 + 6 < HALO_CELLS) ? H.local[c0 + 6] : total;
-                const uint32_t g0 = H.cellG[c0], g1 = H.cellG[c0 + 1], g5 = H.cellG[c0 + 5];
+            unsigned char* sA = pay + (size_t)base * 16;
+            unsigned char* sB = pay + (size_t)PIPE_RING * 16 + (size_t)base * BBYTES;
+            // One halo row (six x-adjacent cells, contiguous in the local index space) per warp and turn: the first cell
+            // belongs to the tile on the left, the next four are contiguous in the sorted arrays, the last to the tile on
+            // the right.  Lane j first fetches the seven table entries of the warp's j-th row (one shared-memory round
+            // for all rows), the loop then gets them by shuffle: no dependent shared-memory load per row.
+            constexpr int ROWS = 36 / PIPE_PRODUCER_WARPS;
+            uint32_t rl[4] = { 0u, 0u, 0u, 0u }, rg[3] = { 0u, 0u, 0u };
+            if (lane < (uint32_t)ROWS) {
+                const uint32_t c0 = (pw + lane * PIPE_PRODUCER_WARPS) * 6u;
+                rl[0] = H.local[c0]; rl[1] = H.local[c0 + 1]; rl[2] = H.local[c0 + 5]; rl[3] = (c0 + 6 < HALO_CELLS) ? H.local[c0 + 6] : total;
+                rg[0] = H.cellG[c0]; rg[1] = H.cellG[c0 + 1]; rg[2] = H.cellG[c0 + 5];
+            }
+            #pragma unroll
+            for (int j = 0; j < ROWS; j++) {
+                const uint32_t lA = __shfl_sync(0xffffffffu, rl[0], j), lB = __shfl_sync(0xffffffffu, rl[1], j);
+                const uint32_t lC = __shfl_sync(0xffffffffu, rl[2], j), lE = __shfl_sync(0xffffffffu, rl[3], j);
+                const uint32_t g0 = __shfl_sync(0xffffffffu, rg[0], j), g1 = __shfl_sync(0xffffffffu, rg[1], j), g5 = __shfl_sync(0xffffffffu, rg[2], j);
                 for (uint32_t l = lA + lane; l < lE; l += 32u) {
                     const uint32_t g = l < lB ? g0 + (l - lA) : (l < lC ? g1 + (l - lB) : g5 + (l - lC));
                     cp_async16(sA + (size_t)l * 16, gA + (size_t)g * 16);
                     if (BBYTES == 16) cp_async16(sB + (size_t)l * 16, gB + (size_t)g * 16);
                     if (BBYTES == 4) cp_async4(sB + (size_t)l * 4, gB + (size_t)g * 4);
                 }
+            }
+        }
+        // look up the CTA's next tile and start loading its cell table
+        tile += tileStep;
+        next_tile();
+        const uint32_t b0_ = tb, e0_ = te;
+        // What the consumers stream per particle of this tile — neighbour counts, the first PIPE_PREFETCH_GROUPS list (and
+        // coefficient) groups of every 32-particle block, the op's own per-particle arrays — is pulled into L2 a tile
+        // ahead, so the consumers' loads find it there instead of paying HBM latency with 16 warps
+        {
+            const uint32_t pfGroups = (uint32_t)op.P.tune[0];
+            const uint32_t blk0 = b0_ >> 5, blk1 = (e0_ - 1u) >> 5;
+            if (pfGroups) for (uint32_t blk = blk0 + pt; blk <= blk1; blk += PIPE_PRODUCER_THREADS) {
+                const size_t g0 = (size_t)blk * (ELL_GROUPS * 32);
+                l2_prefetch(A.list16, g0 * 8, (g0 + pfGroups * 32) * 8);
+                if (Op::COEF == 1) l2_prefetch(A.coef, g0 * 16, (g0 + pfGroups * 32) * 16);
+            }
+            if (op.P.tune[1]) {
+                if (pt == PIPE_PRODUCER_THREADS - 1) l2_prefetch(A.cnt, (size_t)b0_ * 4, (size_t)e0_ * 4);
+                op.prefetch_own(pt, b0_, e0_);
             }
         }
         cp_async_arrive(&ps.full[s]);                     // 64 arrivals: each thread's copies have landed
@@ -454,13 +528,20 @@ __device__ __forceinline__ void pipe_batch(uint32_t p, bool valid, const StageHe
     const uint2* __restrict__ col = ell_list(A.list16, p);
     float4* __restrict__ ccol = reinterpret_cast<float4*>(A.coef) + ell_base(p);
     const uint32_t nG = (m + 3u) >> 2;
-    uint2 wq = make_uint2(0u, 0u);
-    float4 cq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (nG) { wq = col[0]; if (Op::COEF == 1) cq = ccol[0]; }
-    for (uint32_t g = 0; g < nG; g++) {
-        uint2 wn = make_uint2(0u, 0u);
-        float4 cn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (g + 1u < nG) { wn = col[(size_t)(g + 1u) * 32]; if (Op::COEF == 1) cn = ccol[(size_t)(g + 1u) * 32]; }
+    // the list (and coefficient) words stream from HBM: PIPE_LOOKAHEAD groups (16 neighbours) are in flight per lane,
+    // held in a register ring that the fully unrolled inner loop indexes statically
+    constexpr int D = PIPE_LOOKAHEAD;
+    const uint32_t gLast = nG ? nG - 1u : 0u;             // past the end a lane re-reads its last group (an L2 hit)
+    uint2 wr[D]; float4 cr[D];
+    #pragma unroll
+    for (int i = 0; i < D; i++) {
+        // the first D groups are loaded whether or not the particle has that many neighbours (the slots exist): the
+        // addresses do not depend on the count, so these loads go out together with it
+        wr[i] = __ldg(col + (size_t)i * 32);
+        cr[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (Op::COEF == 1) cr[i] = __ldg(reinterpret_cast<const float4*>(ccol) + (size_t)i * 32);
+    }
+    auto group = [&](const uint2 wq, const float4 cq, const uint32_t g) {
         uint32_t L[4];
         ell_unpack(wq, L);
         float c[4] = { cq.x, cq.y, cq.z, cq.w };
@@ -486,15 +567,28 @@ __device__ __forceinline__ void pipe_batch(uint32_t p, bool valid, const StageHe
             c[3] = 0.0f;
         }
         if (Op::COEF == 2) ccol[(size_t)g * 32] = make_float4(c[0], c[1], c[2], c[3]);
-        wq = wn; cq = cn;
+    };
+    // main loop: every ring slot is consumed and reloaded unconditionally (no merge of an old and a new value, so the
+    // load targets the ring register itself); the last 0..D-1 groups drain the ring
+    uint32_t g0 = 0;
+    for (; g0 + D <= nG; g0 += D) {
+        #pragma unroll
+        for (int i = 0; i < D; i++) {
+            group(wr[i], cr[i], g0 + (uint32_t)i);
+            // reloaded once its old value is dead, so the load can target the ring registers directly
+            const uint32_t gn = min(g0 + (uint32_t)i + D, gLast);
+            wr[i] = __ldg(col + (size_t)gn * 32);
+            if (Op::COEF == 1) cr[i] = __ldg(reinterpret_cast<const float4*>(ccol) + (size_t)gn * 32);
+        }
     }
+    #pragma unroll
+    for (int i = 0; i < D - 1; i++) if (g0 + (uint32_t)i < nG) group(wr[i], cr[i], g0 + (uint32_t)i);
     op.finish(p, m, own, acc);
 }
 
 template<class Op>
 __device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, const unsigned char* pay, Op& op) {
     constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
-    constexpr size_t STAGE_BYTES = (size_t)PIPE_CAP * (16 + BBYTES);
     const uint32_t lane = threadIdx.x & 31u, cw = threadIdx.x >> 5;
     uint32_t rot = 0;                                     // running batch count of this CTA (mod the consumer warps)
     for (uint32_t k = 0;; k++) {
@@ -504,8 +598,9 @@ __device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, c
         const uint32_t begin = H.begin, end = H.end;
         if (begin == 0xffffffffu) break;
         const bool staged = H.staged != 0u;
-        const float4* sA = reinterpret_cast<const float4*>(pay + s * STAGE_BYTES);
-        const void* sB = pay + s * STAGE_BYTES + (size_t)PIPE_CAP * 16;
+        const uint32_t base = H.base;
+        const float4* sA = reinterpret_cast<const float4*>(pay + (size_t)base * 16);
+        const void* sB = pay + (size_t)PIPE_RING * 16 + (size_t)base * BBYTES;
         const uint32_t nBatch = (end - begin + 31u) >> 5;
         // batch b of this tile goes to warp (rot + b) mod W: consecutive batches of consecutive tiles visit the warps in turn
         for (uint32_t b = (cw + PIPE_CONSUMER_WARPS - rot) % PIPE_CONSUMER_WARPS; b < nBatch; b += PIPE_CONSUMER_WARPS) {

@@ -180,6 +180,13 @@ struct ViscMatvecOp {
     static constexpr int BBYTES = 16;
     __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
     __device__ __forceinline__ const void* srcB() const { return x; }
+    __device__ __forceinline__ void prefetch_own(uint32_t pt, uint32_t b0, uint32_t e0) const {
+        if (P.muB != 0.0f && pt < P.nBodies) {
+            l2_prefetch(A.bx[pt], (size_t)b0 * 16, (size_t)e0 * 16);
+            l2_prefetch(A.bcoef[pt], (size_t)b0 * 16, (size_t)e0 * 16);
+        }
+        if (INIT && pt == 8) l2_prefetch(A.vel, (size_t)b0 * 16, (size_t)e0 * 16);
+    }
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t g) const { return x[g]; }
     __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
