@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libvfd_dfsph.so")
+LIB_PATH = os.environ.get("VFD_LIB") or os.path.join(HERE, "lib", "libvfd_dfsph.so")   # VFD_LIB: a tuning variant built by build.py --out
 
 
 class VfdError(RuntimeError):

@@ -44,18 +44,21 @@ def needs_build():
     return _newest(deps) > os.path.getmtime(LIB)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defs=(), out=None):
+    """defs/out: tuning variants (extra -D flags, written to another file; selected at run time with VFD_LIB)."""
+    if out is None and not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    objdir = OBJDIR if out is None else OBJDIR + "_" + os.path.basename(out)
+    os.makedirs(objdir, exist_ok=True)
     srcs = sources()
-    objs = [os.path.join(OBJDIR, os.path.basename(s) + ".o") for s in srcs]
+    objs = [os.path.join(objdir, os.path.basename(s) + ".o") for s in srcs]
+    lib = LIB if out is None else out
 
     def cc(i):
         s, o = srcs[i], objs[i]
         if s.endswith(".cu"):
-            cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = ["nvcc"] + NVCC_FLAGS + list(defs) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         else:
             cmd = ["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-I/usr/local/cuda/include", "-c", s, "-o", o]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -67,16 +70,18 @@ def build(force=False, verbose=False):
         outs = list(ex.map(cc, range(len(srcs))))
     if verbose:
         print("\n".join(outs))
-    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
+    cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout[-8000:]))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--defs", default="", help="extra nvcc -D flags (tuning variant)")
+    ap.add_argument("--out", default=None, help="write the variant to this file instead of lib/libvfd_dfsph.so")
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build(a.force, a.verbose, a.defs.split(), a.out))

@@ -50,7 +50,7 @@ struct Params {
     float viscErr2;             // MaxViscositySolverError^2 * 0.0001       (:663)
     uint32_t minPressIt, maxPressIt, minDivIt, maxDivIt, minViscIt, maxViscIt;
     int   searchFma;
-    int   tune[4];              // experiment knobs (env VFD_TUNE0..3; 0 = default behaviour)
+    int   tune[8];              // experiment knobs (env VFD_TUNE0..7; 0 = default behaviour)
 };
 
 // Device-resident mutable scalars: the time step and all solver control state.  Kernels read dt

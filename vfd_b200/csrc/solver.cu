@@ -281,7 +281,7 @@ void Solver::refresh_params() {
     P.minDivIt = desc.MinDivergenceSolverIterations; P.maxDivIt = desc.MaxDivergenceSolverIterations;
     P.minViscIt = desc.MinViscositySolverIterations; P.maxViscIt = desc.MaxViscositySolverIterations;
     P.searchFma = optSearchFma;
-    for (int k = 0; k < 4; k++) { char nm[16]; snprintf(nm, sizeof nm, "VFD_TUNE%d", k); const char* e = getenv(nm); P.tune[k] = e ? atoi(e) : 0; }
+    for (int k = 0; k < 8; k++) { char nm[16]; snprintf(nm, sizeof nm, "VFD_TUNE%d", k); const char* e = getenv(nm); P.tune[k] = e ? atoi(e) : 0; }
     if (dist) dist_params(P);
 }
 

@@ -277,14 +277,18 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 // Work assignment is static (tile -> CTA round robin, batch -> warp rotating with the running batch count), so every
 // per-thread partial sum is accumulated in the same order run after run: reductions stay bit-reproducible.
 #define PIPE_STAGES 4          // tiles in flight per CTA (header slots); their payloads share one ring of PIPE_RING particle slots
+#ifndef PIPE_CONSUMER_WARPS
 #define PIPE_CONSUMER_WARPS 16
+#endif
 #define PIPE_PRODUCER_WARPS 4
 #define PIPE_PRODUCER_THREADS (PIPE_PRODUCER_WARPS * 32)
 #define PIPE_CELLS_PER_THREAD ((HALO_CELLS + PIPE_PRODUCER_THREADS - 1) / PIPE_PRODUCER_THREADS)
 #define PIPE_THREADS ((PIPE_CONSUMER_WARPS + PIPE_PRODUCER_WARPS) * 32)     // 576
 #define PIPE_CAP 2816          // largest halo box that is staged (larger ones take the exact global-memory path)
 #define PIPE_RING (2 * PIPE_CAP) // payload ring, in particles: two worst-case boxes, three to four typical ones (~1700)
-#define PIPE_LOOKAHEAD 3       // neighbour groups (of four) in flight per lane
+#ifndef PIPE_LOOKAHEAD
+#define PIPE_LOOKAHEAD 3
+#endif                         // neighbour groups (of four) in flight per lane
 
 __device__ __forceinline__ uint2 ldg_stream(const uint2* p) { return __ldg(p); }
 __device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldg(p); }
@@ -619,6 +623,162 @@ __device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, c
     }
 }
 
+// ---- consumer of pair ops, software-pipelined ACROSS batches -------------------------------------------
+// A tile of ~512 particles is 16 batches and the CTA has 16 consumer warps: every warp gets one batch per tile, and in
+// the plain loop above all of them sit in the batch's start-up at the same time — neighbour count, own fields, first list
+// and coefficient words, one L2/HBM latency with nothing to overlap it (ncu, profiles/r01_ncu_matvec_pipeline.txt: 40 %
+// of the warp-stall samples at the top of the batch).  Here a warp issues the start-up loads of its NEXT batch (which
+// may belong to a later tile: the producers are tiles ahead) right after the gather loop of the current one, before the
+// current batch's epilogue (Op::finish: boundary terms, preconditioner, stores), so they are in flight during it.
+// The order of batches per warp, and therefore every per-thread sum, is the plain loop's.
+template<class Op> struct BatchHead {
+    uint32_t p, m;
+    float own[Op::NOWN];
+    uint2 wr[PIPE_LOOKAHEAD]; float4 cr[PIPE_LOOKAHEAD];
+};
+struct BatchCursor {
+    uint32_t k, b, rot;                    // tile counter of this CTA, batch inside the tile, rotation (see above)
+    uint32_t begin, end, nBatch;
+    bool done;
+};
+
+template<class Op>
+__device__ __forceinline__ void pipe_head_load(BatchHead<Op>& h, const BatchCursor& c, uint32_t lane, const Arrays& A, const Op& op) {
+    constexpr int D = PIPE_LOOKAHEAD;
+    h.p = c.begin + (c.b << 5) + lane;
+    h.m = 0u;
+    #pragma unroll
+    for (int i = 0; i < D; i++) { h.wr[i] = make_uint2(0u, 0u); h.cr[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+    #pragma unroll
+    for (int i = 0; i < Op::NOWN; i++) h.own[i] = 0.0f;
+    if (h.p >= c.end) { h.p = 0xffffffffu; return; }
+    h.m = __ldg(A.cnt + h.p);
+    op.load_own(h.p, h.own);
+    const uint2* __restrict__ col = ell_list(A.list16, h.p);
+    const float4* __restrict__ ccol = reinterpret_cast<const float4*>(A.coef) + ell_base(h.p);
+    #pragma unroll
+    for (int i = 0; i < D; i++) {
+        // the first D groups are loaded whether or not the particle has that many neighbours (the slots exist)
+        h.wr[i] = __ldg(col + (size_t)i * 32);
+        if (Op::COEF == 1) h.cr[i] = __ldg(ccol + (size_t)i * 32);
+    }
+}
+
+template<class Op, bool STAGED>
+__device__ __forceinline__ void pipe_gather(BatchHead<Op>& h, float (&acc)[Op::NSUM], const StageHeader& H, const Arrays& A,
+                                            const float4* __restrict__ sA, const void* __restrict__ sBv, Op& op) {
+    constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
+    constexpr int D = PIPE_LOOKAHEAD;
+    const float4* __restrict__ sB = reinterpret_cast<const float4*>(sBv);
+    const float* __restrict__ sB1 = reinterpret_cast<const float*>(sBv);
+    auto gatherB = [&](uint32_t L) -> float4 {
+        if (BBYTES == 16) return sB[L];
+        if (BBYTES == 4) return make_float4(sB1[L], 0.0f, 0.0f, 0.0f);
+        return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    };
+    const uint32_t m = h.m;
+    if (m == 0u) return;
+    const uint2* __restrict__ col = ell_list(A.list16, h.p);
+    float4* __restrict__ ccol = reinterpret_cast<float4*>(A.coef) + ell_base(h.p);
+    const uint32_t nG = (m + 3u) >> 2;
+    const uint32_t gLast = nG - 1u;                       // past the end a lane re-reads its last group (an L2 hit)
+    auto group = [&](const uint2 wq, const float4 cq, const uint32_t g) {
+        uint32_t L[4];
+        ell_unpack(wq, L);
+        float c[4] = { cq.x, cq.y, cq.z, cq.w };
+        if (g * 4u + 4u <= m) {
+            float4 pa[4], pb[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (STAGED) { pa[u] = sA[L[u]]; pb[u] = gatherB(L[u]); }
+                else { const uint32_t gi = hdr_local_to_global(H, L[u]); pa[u] = op.loadA(gi); pb[u] = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) op.pair(h.own, pa[u], pb[u], c[u], acc);
+        } else {
+            #pragma unroll
+            for (int u = 0; u < 3; u++) {                    // a partial group holds one to three neighbours
+                if (g * 4u + (uint32_t)u < m) {
+                    float4 xa, xb;
+                    if (STAGED) { xa = sA[L[u]]; xb = gatherB(L[u]); }
+                    else { const uint32_t gi = hdr_local_to_global(H, L[u]); xa = op.loadA(gi); xb = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+                    op.pair(h.own, xa, xb, c[u], acc);
+                } else c[u] = 0.0f;
+            }
+            c[3] = 0.0f;
+        }
+        if (Op::COEF == 2) ccol[(size_t)g * 32] = make_float4(c[0], c[1], c[2], c[3]);
+    };
+    uint32_t g0 = 0;
+    for (; g0 + D <= nG; g0 += D) {
+        #pragma unroll
+        for (int i = 0; i < D; i++) {
+            group(h.wr[i], h.cr[i], g0 + (uint32_t)i);
+            const uint32_t gn = min(g0 + (uint32_t)i + D, gLast);
+            h.wr[i] = __ldg(col + (size_t)gn * 32);
+            if (Op::COEF == 1) h.cr[i] = __ldg(reinterpret_cast<const float4*>(ccol) + (size_t)gn * 32);
+        }
+    }
+    #pragma unroll
+    for (int i = 0; i < D - 1; i++) if (g0 + (uint32_t)i < nG) group(h.wr[i], h.cr[i], g0 + (uint32_t)i);
+}
+
+template<class Op>
+__device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared& ps, const unsigned char* pay, Op& op) {
+    static_assert(!Op::CUSTOM, "pair ops only");
+    constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
+    const uint32_t lane = threadIdx.x & 31u, cw = threadIdx.x >> 5;
+    BatchCursor c;
+    c.k = 0; c.rot = 0; c.b = 0; c.begin = 0; c.end = 0; c.nBatch = 0; c.done = false;
+    // enter tile c.k: wait until the producers have filled its slot, read its range
+    auto enter = [&]() {
+        const uint32_t s = c.k % PIPE_STAGES;
+        mbar_wait(&ps.full[s], (c.k / PIPE_STAGES) & 1u);
+        const StageHeader& H = ps.hdr[s];
+        c.begin = H.begin; c.end = H.end;
+        if (c.begin == 0xffffffffu) { c.done = true; c.nBatch = 0; return; }
+        c.nBatch = (c.end - c.begin + 31u) >> 5;
+        c.b = (cw + PIPE_CONSUMER_WARPS - c.rot) % PIPE_CONSUMER_WARPS;
+    };
+    // move to this warp's next batch, releasing every tile it leaves behind (their gathers are complete)
+    auto seek = [&]() {
+        while (!c.done && c.b >= c.nBatch) {
+            c.rot = (c.rot + c.nBatch) % PIPE_CONSUMER_WARPS;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ps.empty[c.k % PIPE_STAGES]);
+            c.k++;
+            enter();
+        }
+    };
+    enter();
+    seek();
+    BatchHead<Op> h;
+    if (!c.done) pipe_head_load(h, c, lane, A, op);
+    while (!c.done) {
+        float acc[Op::NSUM];
+        #pragma unroll
+        for (int s = 0; s < Op::NSUM; s++) acc[s] = 0.0f;
+        {
+            const StageHeader& H = ps.hdr[c.k % PIPE_STAGES];
+            const uint32_t base = H.base;
+            const float4* sA = reinterpret_cast<const float4*>(pay + (size_t)base * 16);
+            const void* sB = pay + (size_t)PIPE_RING * 16 + (size_t)base * BBYTES;
+            if (H.staged != 0u) pipe_gather<Op, true>(h, acc, H, A, sA, sB, op);
+            else                pipe_gather<Op, false>(h, acc, H, A, sA, sB, op);
+        }
+        // what the epilogue needs of the current batch
+        const uint32_t p = h.p, m = h.m;
+        float own[Op::NOWN];
+        #pragma unroll
+        for (int i = 0; i < Op::NOWN; i++) own[i] = h.own[i];
+        // next batch: its start-up loads go out now and land during the epilogue
+        c.b += PIPE_CONSUMER_WARPS;
+        seek();
+        if (!c.done) pipe_head_load(h, c, lane, A, op);
+        if (p != 0xffffffffu) op.finish(p, m, own, acc);
+    }
+}
+
 // Called by all PIPE_THREADS threads of the CTA (after any lookup table has been loaded; contains __syncthreads).
 template<class Op>
 __device__ __forceinline__ void pipe_pass(DevState* __restrict__ S, const Arrays& A, PipeShared& ps, unsigned char* pay, Op& op,
@@ -629,7 +789,11 @@ __device__ __forceinline__ void pipe_pass(DevState* __restrict__ S, const Arrays
     }
     __syncthreads();
     if (threadIdx.x >= PIPE_CONSUMER_WARPS * 32) pipe_producer(S, A, ps, pay, op, tile0, tile1, checkIndexRange);
-    else pipe_consumer(A, ps, pay, op);
+    else if constexpr (Op::CUSTOM) pipe_consumer(A, ps, pay, op);
+    else {
+        if (op.P.tune[4] == 0) pipe_consumer_pairs(A, ps, pay, op);      // default; tune[4] = 1: the plain loop (A/B runs)
+        else pipe_consumer(A, ps, pay, op);
+    }
     __syncthreads();
 }
 
