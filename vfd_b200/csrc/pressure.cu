@@ -10,10 +10,10 @@
 // (DFSPHImplementation.cu: ComputeDivergence :506-575, ComputePressure :443-504,
 // ComputeTimeStepSize :395-428, ComputeMaxVelocityMagnitude :430-441).
 //
-// The neighbour-sum kernels are tile passes (tile.cuh): persistent CTAs, the 40-kB kernel lookup table
-// staged into shared memory once per CTA, the neighbour payload of a tile's 6x6x6-cell halo box staged
-// once per tile, groups of 8 lanes per particle streaming 16-bit local neighbour indices and reducing
-// the kernel-weighted sums with warp shuffles.  Solver control
+// The neighbour-sum kernels are pipelined tile passes (tile.cuh: pipe_pass): one persistent CTA per SM, producer
+// warps copying the neighbour payload of a tile's 6x6x6-cell halo box into a shared-memory ring with cp.async,
+// consumer warps (one particle per lane) streaming 16-bit local neighbour indices and the per-pair kernel-gradient
+// factor and gathering the payload from shared memory.  Solver control
 // (iteration counters, residual means, continue flags) lives in DevState: the loop-carried decision
 // of the reference's host loops is taken by the last block of the iteration kernel.
 #include "solver.h"
@@ -31,20 +31,37 @@ extern __shared__ __align__(128) unsigned char smemRaw[];
     const uint32_t p = ownB_ + blockIdx.x * blockDim.x + threadIdx.x; if (p >= ownE_) return
 #define NO_B __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
 
-// ---- K2 + K3 + K8 fused: density, DFSPH factor, a = g --------------------------------------
+// Positions and neighbour lists are frozen between two searches, so the kernel-gradient factor of a pair,
+//   g_ij  with  gradW(x_ij) = g_ij x_ij      (the table lookup of PrecomputedDFSPHCubicKernel::GetGradientW,
+//   Kernel/DFSPHKernels.h:67-80: one square root, one index conversion, two dependent table loads),
+// is evaluated ONCE per step — by the density pass, which needs it anyway — and streamed next to the neighbour list
+// (A.gcoef, same ELL layout, 4 B per pair) by the ~14 later neighbour passes of the step, bit-identical to evaluating
+// it again.  The same holds for the boundary term: gradW(x_i - x_b) per particle and body is stored as A.bgrad
+// (w = V_b; zero when the body is out of range).  Only the density pass keeps the lookup tables in shared memory.
+#define NO_PREFETCH __device__ __forceinline__ void prefetch_own(uint32_t, uint32_t, uint32_t) const {}
+#define COEF_IN_G __device__ __forceinline__ const float* coef_in() const { return A.gcoef; } \
+                  __device__ __forceinline__ float* coef_out() const { return nullptr; }
+
+// ---- K2 + K3 + K8 fused: density, DFSPH factor, a = g; writes the pair factors g_ij and the boundary gradients ----
 struct DensityFactorOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 1, NOWN = 3, NSUM = 5, COEF = 0;
+    static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 5, COEF = 2;
     const Params& P; const Arrays& A; Lut K;
+    __device__ __forceinline__ const float4* srcA() const { return A.pos; }
+    __device__ __forceinline__ const void* srcB() const { return nullptr; }
+    __device__ __forceinline__ const float* coef_in() const { return nullptr; }
+    __device__ __forceinline__ float* coef_out() const { return A.gcoef; }
+    NO_PREFETCH
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.pos[g]; }
     NO_B
     __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
         const float4 x = A.pos[p]; own[0] = x.x; own[1] = x.y; own[2] = x.z;
     }
-    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4, float&, float (&acc)[NSUM]) const {
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4, float& c, float (&acc)[NSUM]) const {
         const float3 xij = f3(o[0], o[1], o[2]) - f3(a);
         acc[0] += P.volume * K.w(xij);
-        const float3 gj = -P.volume * K.gradW(xij);
+        c = K.gradWScalar(xij);
+        const float3 gj = -P.volume * (c * xij);
         acc[1] += dot3(gj, gj);
         acc[2] -= gj.x; acc[3] -= gj.y; acc[4] -= gj.z;
     }
@@ -55,12 +72,16 @@ struct DensityFactorOp {
         float3 gradI = f3(sum[2], sum[3], sum[4]);
         for (uint32_t b = 0; b < P.nBodies; b++) {
             const float4 bx = A.bx[b][p];
+            float4 bg = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (bx.w > 0.0f) {
                 const float3 xib = xi - f3(bx);
                 rho += bx.w * K.w(xib);
-                const float3 gj = -bx.w * K.gradW(xib);
+                const float3 gw = K.gradW(xib);
+                const float3 gj = -bx.w * gw;
                 gradI -= gj;
+                bg = make_float4(gw.x, gw.y, gw.z, bx.w);
             }
+            A.bgrad[b][p] = bg;
         }
         rho *= P.rho0;
         sumK += dot3(gradI, gradI);
@@ -71,14 +92,14 @@ struct DensityFactorOp {
     }
 };
 
-__global__ void __launch_bounds__(TT_LUT2) k_density_factor(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S,
-                                                                 const float* __restrict__ lutW, const float* __restrict__ lutG) {
-    float* sW = smem_lut<2>(smemRaw);
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_density_factor(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S,
+                                                                    const float* __restrict__ lutW, const float* __restrict__ lutG) {
+    float* sW = pipe_lut<2>(smemRaw);
     float* sG = sW + VFD_LUT_RES;
     load_lut_tile(sW, lutW);
     load_lut_tile(sG, lutG);
     DensityFactorOp op{ P, A, Lut{ sW, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 } };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<2>(smemRaw), nullptr, STAGE_CAP, op, P.tile0, P.tile1);
+    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<2>(smemRaw), op, P.tile0, P.tile1);
 }
 
 // ---- K4 / K10: solver source terms ----------------------------------------------------------
@@ -86,24 +107,28 @@ __global__ void __launch_bounds__(TT_LUT2) k_density_factor(const __grid_constan
 template<bool DIV>
 struct SourceOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 2, NOWN = 6, NSUM = 1, COEF = 0;
-    const Params& P; const Arrays& A; Lut K;
+    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1;
+    const Params& P; const Arrays& A;
     float dt, dtInv, dt2Inv;
+    __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
+    __device__ __forceinline__ const void* srcB() const { return A.vel; }
+    COEF_IN_G
+    NO_PREFETCH
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t g) const { return A.vel[g]; }
     __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
         const float4 x = A.posRho[p], v = A.vel[p];
         own[0] = x.x; own[1] = x.y; own[2] = x.z; own[3] = v.x; own[4] = v.y; own[5] = v.z;
     }
-    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float&, float (&acc)[NSUM]) const {
-        acc[0] += dot3(f3(o[3], o[4], o[5]) - f3(b), K.gradW(f3(o[0], o[1], o[2]) - f3(a)));
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
+        acc[0] += dot3(f3(o[3], o[4], o[5]) - f3(b), c * (f3(o[0], o[1], o[2]) - f3(a)));
     }
     __device__ __forceinline__ void finish(uint32_t p, uint32_t m, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
-        const float3 xi = f3(o[0], o[1], o[2]), vi = f3(o[3], o[4], o[5]);
+        const float3 vi = f3(o[3], o[4], o[5]);
         float s = sum[0] * P.volume;
         for (uint32_t b = 0; b < P.nBodies; b++) {
-            const float4 bx = A.bx[b][p];
-            if (bx.w > 0.0f) s += bx.w * dot3(vi, K.gradW(xi - f3(bx)));
+            const float4 bg = A.bgrad[b][p];
+            if (bg.w > 0.0f) s += bg.w * dot3(vi, f3(bg));
         }
         if (DIV) {
             const float adv = m < 20u ? 0.0f : fmaxf(s, 0.0f);
@@ -123,17 +148,15 @@ struct SourceOp {
 };
 
 template<bool DIV>
-__global__ void __launch_bounds__(TT_LUT, 2) k_source(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
-    float* sG = smem_lut<1>(smemRaw);
-    load_lut_tile(sG, lutG);
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_source(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // loop entry of ComputeDivergence / ComputePressure (DFSPHImplementation.cu:526-532, 455-461): error 0, so the
         // loop is entered only through the minimum iteration count
         if (DIV) { S->divIt = 0; S->divErr = 0.0f; S->divActive = (0u < P.minDivIt && 0u < P.maxDivIt) ? 1u : 0u; }
         else     { S->pressIt = 0; S->pressErr = 0.0f; S->pressActive = (0u < P.minPressIt && 0u < P.maxPressIt) ? 1u : 0u; }
     }
-    SourceOp<DIV> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, S->dtInv, S->dt2Inv };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP_LUT), STAGE_CAP_LUT, op, P.tile0, P.tile1);
+    SourceOp<DIV> op{ P, A, S->dt, S->dtInv, S->dt2Inv };
+    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
 }
 
 // ---- K5 / K7 / K11 / K13: pressure acceleration from kappa ---------------------------------
@@ -142,31 +165,34 @@ enum { ACC_DIV_ITER = 0, ACC_DIV_FINISH = 1, ACC_PRESS_ITER = 2, ACC_PRESS_FINIS
 template<int MODE>
 struct AccelOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 1, NOWN = 4, NSUM = 3, COEF = 0;       // payload (x, y, z, kappa)
-    const Params& P; const Arrays& A; Lut K;
+    static constexpr int NPAY = 2, BBYTES = 4, NOWN = 4, NSUM = 3, COEF = 1;       // payload: (x, y, z, rho) and kappa
+    const Params& P; const Arrays& A;
     const float* __restrict__ kap;
     float dt;
-    __device__ __forceinline__ float4 loadA(uint32_t g) const { float4 x = A.posRho[g]; x.w = kap[g]; return x; }
-    NO_B
+    __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
+    __device__ __forceinline__ const void* srcB() const { return kap; }
+    COEF_IN_G
+    NO_PREFETCH
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
+    __device__ __forceinline__ float4 loadB(uint32_t g) const { return make_float4(kap[g], 0.0f, 0.0f, 0.0f); }
     __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
         const float4 x = A.posRho[p]; own[0] = x.x; own[1] = x.y; own[2] = x.z; own[3] = kap[p];
     }
-    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4, float&, float (&acc)[NSUM]) const {
-        const float ks = o[3] + a.w;
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
+        const float ks = o[3] + b.x;
         if (fabsf(ks) > VFD_EPS_F) {
-            const float3 gj = -P.volume * K.gradW(f3(o[0], o[1], o[2]) - f3(a));
+            const float3 gj = -P.volume * (c * (f3(o[0], o[1], o[2]) - f3(a)));
             acc[0] += ks * gj.x; acc[1] += ks * gj.y; acc[2] += ks * gj.z;
         }
     }
     __device__ __forceinline__ void finish(uint32_t p, uint32_t, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
-        const float3 xi = f3(o[0], o[1], o[2]);
         const float ki = o[3];
         float3 a = f3(sum[0], sum[1], sum[2]);
         if (fabsf(ki) > VFD_EPS_F) {
             for (uint32_t b = 0; b < P.nBodies; b++) {
-                const float4 bx = A.bx[b][p];
-                if (bx.w > 0.0f) {
-                    const float3 gj = -bx.w * K.gradW(xi - f3(bx));
+                const float4 bg = A.bgrad[b][p];
+                if (bg.w > 0.0f) {
+                    const float3 gj = -bg.w * f3(bg);
                     a += ki * gj;
                 }
             }
@@ -182,39 +208,40 @@ struct AccelOp {
 };
 
 template<int MODE>
-__global__ void __launch_bounds__(TT_LUT, 2) k_pressure_accel(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_pressure_accel(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (MODE == ACC_DIV_ITER && !S->divActive) return;
     if (MODE == ACC_PRESS_ITER && !S->pressActive) return;
-    float* sG = smem_lut<1>(smemRaw);
-    load_lut_tile(sG, lutG);
-    AccelOp<MODE> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 },
-                      (MODE == ACC_DIV_ITER || MODE == ACC_DIV_FINISH) ? A.kappaV : A.kappa, S->dt };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<1>(smemRaw), nullptr, STAGE_CAP, op, P.tile0, P.tile1);
+    AccelOp<MODE> op{ P, A, (MODE == ACC_DIV_ITER || MODE == ACC_DIV_FINISH) ? A.kappaV : A.kappa, S->dt };
+    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
 }
 
 // ---- K6 / K12 (+ R1 / R3): one Jacobi update and the fused residual reduction ----------------
 template<bool DIV>
 struct SolveOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 2, NOWN = 6, NSUM = 1, COEF = 0;       // payload: position, pressure acceleration
-    const Params& P; const Arrays& A; Lut K;
+    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1;       // payload: position, pressure acceleration
+    const Params& P; const Arrays& A;
     float scale;
     float errSum;
+    __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
+    __device__ __forceinline__ const void* srcB() const { return A.pacc; }
+    COEF_IN_G
+    NO_PREFETCH
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t g) const { return A.pacc[g]; }
     __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
         const float4 x = A.posRho[p], a = A.pacc[p];
         own[0] = x.x; own[1] = x.y; own[2] = x.z; own[3] = a.x; own[4] = a.y; own[5] = a.z;
     }
-    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float&, float (&acc)[NSUM]) const {
-        acc[0] += dot3(f3(o[3], o[4], o[5]) - f3(b), K.gradW(f3(o[0], o[1], o[2]) - f3(a)));
+    __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
+        acc[0] += dot3(f3(o[3], o[4], o[5]) - f3(b), c * (f3(o[0], o[1], o[2]) - f3(a)));
     }
     __device__ __forceinline__ void finish(uint32_t p, uint32_t m, const float (&o)[NOWN], const float (&sum)[NSUM]) {
-        const float3 xi = f3(o[0], o[1], o[2]), ai = f3(o[3], o[4], o[5]);
+        const float3 ai = f3(o[3], o[4], o[5]);
         float s = sum[0] * P.volume;
         for (uint32_t b = 0; b < P.nBodies; b++) {
-            const float4 bx = A.bx[b][p];
-            if (bx.w > 0.0f) s += bx.w * dot3(ai, K.gradW(xi - f3(bx)));
+            const float4 bg = A.bgrad[b][p];
+            if (bg.w > 0.0f) s += bg.w * dot3(ai, f3(bg));
         }
         s *= scale;
         float residuum;
@@ -231,19 +258,16 @@ struct SolveOp {
 };
 
 template<bool DIV>
-__global__ void __launch_bounds__(TT_LUT, 2) k_solve_iteration(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_iteration(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (DIV ? !S->divActive : !S->pressActive) return;
-    TileShared& sh = smem_header(smemRaw);
-    float* sG = smem_lut<1>(smemRaw);
-    load_lut_tile(sG, lutG);
-    SolveOp<DIV> op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, DIV ? S->dt : S->dt2, 0.0f };
-    tile_pass(S, A, sh, smem_pay_a<1>(smemRaw), smem_pay_b<1>(smemRaw, STAGE_CAP_LUT), STAGE_CAP_LUT, op, P.tile0, P.tile1);
-    __syncthreads();
+    PipeShared& ps = pipe_header(smemRaw);
+    SolveOp<DIV> op{ P, A, DIV ? S->dt : S->dt2, 0.0f };
+    pipe_pass(S, A, ps, pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
     double v[1] = { (double)op.errSum };
     uint32_t* ticket = &S->ticket[DIV ? 1 : 2];
-    if (block_reduce_publish<1>(v, A.partials, ticket, sh.red)) {
+    if (block_reduce_publish<1>(v, A.partials, ticket, ps.red)) {
         double tot[1];
-        last_block_fold<1>(tot, A.partials, sh.red);
+        last_block_fold<1>(tot, A.partials, ps.red);
         if (threadIdx.x == 0) {
             finish_reduction<1>(DIV ? SITE_DIV : SITE_PRESS, P, S, tot);
             *ticket = 0;
@@ -298,74 +322,43 @@ __global__ void k_clear_acc(Params P, Arrays A) {
 }
 
 // ---- launchers -------------------------------------------------------------------------------
-// persistent grid: resident CTAs per SM (from the occupancy calculator) x SMs
+// pipelined tile passes: one persistent CTA per SM
 template<typename Kern>
-static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L, int threads) {
-    static thread_local const void* cachedK[32]; static thread_local int cachedV[32]; static thread_local int nc = 0;
-    int perSM = 0;
-    for (int i = 0; i < nc; i++) if (cachedK[i] == (const void*)kern) perSM = cachedV[i];
-    if (!perSM) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, threads, smem);
-        if (perSM < 1) perSM = 1;
-        if (nc < 32) { cachedK[nc] = (const void*)kern; cachedV[nc] = perSM; nc++; }
-    }
-    return (uint32_t)(perSM * L.numSMs);
+static void pipe_attr(Kern kern, size_t smem) {
+    static thread_local const void* done[32]; static thread_local int nd = 0;
+    for (int i = 0; i < nd; i++) if (done[i] == (const void*)kern) return;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (nd < 32) done[nd++] = (const void*)kern;
 }
+#define PIPE_LAUNCH(kid, kern, smem, ...) do { const size_t sm_ = (smem); pipe_attr(kern, sm_); LaunchScope ls(L, kid); \
+    kern<<<L.numSMs, PIPE_THREADS, sm_, L.stream>>>(__VA_ARGS__); } while (0)
 
 void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutW, const float* lutG) {
-    const size_t smem = tile_smem_bytes<2, 1>(STAGE_CAP);
-    const uint32_t g = tile_grid(k_density_factor, smem, L, TT_LUT2);
-    LaunchScope ls(L, KID_DENSITY_FACTOR);
-    k_density_factor<<<g, TT_LUT2, smem, L.stream>>>(P, A, S, lutW, lutG);
+    PIPE_LAUNCH(KID_DENSITY_FACTOR, k_density_factor, (pipe_smem_bytes<2, 16, 0>()), P, A, S, lutW, lutG);
 }
-void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t smem = tile_smem_bytes<1, 2>(STAGE_CAP_LUT);
-    const uint32_t g = tile_grid(k_source<true>, smem, L, TT_LUT);
-    LaunchScope ls(L, KID_DIV_SOURCE);
-    k_source<true><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
+void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
+    PIPE_LAUNCH(KID_DIV_SOURCE, k_source<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
 }
-void launch_divergence_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s1 = tile_smem_bytes<1, 1>(STAGE_CAP);
-    const uint32_t g1 = tile_grid(k_pressure_accel<ACC_DIV_ITER>, s1, L, TT_LUT);
-    LaunchScope ls(L, KID_DIV_ACCEL);
-    k_pressure_accel<ACC_DIV_ITER><<<g1, TT_LUT, s1, L.stream>>>(P, A, S, lutG);
+void launch_divergence_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
+    PIPE_LAUNCH(KID_DIV_ACCEL, k_pressure_accel<ACC_DIV_ITER>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
 }
-void launch_divergence_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s2 = tile_smem_bytes<1, 2>(STAGE_CAP_LUT);
-    const uint32_t g2 = tile_grid(k_solve_iteration<true>, s2, L, TT_LUT);
-    LaunchScope ls(L, KID_DIV_SOLVE);
-    k_solve_iteration<true><<<g2, TT_LUT, s2, L.stream>>>(P, A, S, lutG);
+void launch_divergence_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
+    PIPE_LAUNCH(KID_DIV_SOLVE, k_solve_iteration<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
 }
-void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t smem = tile_smem_bytes<1, 1>(STAGE_CAP);
-    const uint32_t g = tile_grid(k_pressure_accel<ACC_DIV_FINISH>, smem, L, TT_LUT);
-    LaunchScope ls(L, KID_DIV_FINISH);
-    k_pressure_accel<ACC_DIV_FINISH><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
+void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
+    PIPE_LAUNCH(KID_DIV_FINISH, k_pressure_accel<ACC_DIV_FINISH>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
 }
-void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t smem = tile_smem_bytes<1, 2>(STAGE_CAP_LUT);
-    const uint32_t g = tile_grid(k_source<false>, smem, L, TT_LUT);
-    LaunchScope ls(L, KID_PRESS_SOURCE);
-    k_source<false><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
+void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
+    PIPE_LAUNCH(KID_PRESS_SOURCE, k_source<false>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
 }
-void launch_pressure_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s1 = tile_smem_bytes<1, 1>(STAGE_CAP);
-    const uint32_t g1 = tile_grid(k_pressure_accel<ACC_PRESS_ITER>, s1, L, TT_LUT);
-    LaunchScope ls(L, KID_PRESS_ACCEL);
-    k_pressure_accel<ACC_PRESS_ITER><<<g1, TT_LUT, s1, L.stream>>>(P, A, S, lutG);
+void launch_pressure_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
+    PIPE_LAUNCH(KID_PRESS_ACCEL, k_pressure_accel<ACC_PRESS_ITER>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
 }
-void launch_pressure_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s2 = tile_smem_bytes<1, 2>(STAGE_CAP_LUT);
-    const uint32_t g2 = tile_grid(k_solve_iteration<false>, s2, L, TT_LUT);
-    LaunchScope ls(L, KID_PRESS_SOLVE);
-    k_solve_iteration<false><<<g2, TT_LUT, s2, L.stream>>>(P, A, S, lutG);
+void launch_pressure_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
+    PIPE_LAUNCH(KID_PRESS_SOLVE, k_solve_iteration<false>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
 }
-void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t smem = tile_smem_bytes<1, 1>(STAGE_CAP);
-    const uint32_t g = tile_grid(k_pressure_accel<ACC_PRESS_FINISH>, smem, L, TT_LUT);
-    LaunchScope ls(L, KID_PRESS_FINISH);
-    k_pressure_accel<ACC_PRESS_FINISH><<<g, TT_LUT, smem, L.stream>>>(P, A, S, lutG);
+void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
+    PIPE_LAUNCH(KID_PRESS_FINISH, k_pressure_accel<ACC_PRESS_FINISH>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
 }
 void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A) {
     LaunchScope ls(L, KID_CLEAR_ACC);

@@ -291,10 +291,10 @@ void Solver::free_particles() {
     Arrays& A = arrays;
     void* ptrs[] = { A.pos, A.vel, A.dv, A.nbar, A.curv, A.curvS, A.curvD, A.id, A.pos2, A.vel2, A.dv2, A.nbar2, A.curv2, A.curvS2, A.curvD2, A.id2,
                      A.posRho, A.acc, A.pacc, A.nrm, A.res, A.rho, A.rhoAdv, A.kappa, A.kappaV, A.alpha, A.cgG, A.cgR, A.cgP, A.cgQ, A.cgZ, A.minv,
-                     A.cnt, A.list16, A.coef, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.ctaTile, A.partials, dPos0, dVel0 };
+                     A.cnt, A.list16, A.coef, A.gcoef, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.ctaTile, A.partials, dPos0, dVel0 };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (dIds0) { cudaFree(dIds0); dIds0 = nullptr; }
-    for (int b = 0; b < VFD_MAX_BODIES; b++) { if (A.bx[b]) cudaFree(A.bx[b]); if (A.bcoef[b]) cudaFree(A.bcoef[b]); }
+    for (int b = 0; b < VFD_MAX_BODIES; b++) { if (A.bx[b]) cudaFree(A.bx[b]); if (A.bcoef[b]) cudaFree(A.bcoef[b]); if (A.bgrad[b]) cudaFree(A.bgrad[b]); }
     memset(&A, 0, sizeof A);
     dPos0 = dVel0 = nullptr;
     allocBytes = 0;
@@ -329,7 +329,8 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
     for (uint32_t** p : u1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
     CK(dalloc(A.list16, np * ELL_SLOTS)); searchBytes = np * ELL_SLOTS * 2 + np * 4 * 4;
     CK(dalloc(A.coef, np * ELL_SLOTS));
-    allocBytes += np * ELL_SLOTS * 6;
+    CK(dalloc(A.gcoef, np * ELL_SLOTS));
+    allocBytes += np * ELL_SLOTS * 10;
     // search grid capacity: 64x the cells of the initial bounding box (4x per axis of head room)
     double cells0 = 1.0;
     for (int k = 0; k < 3; k++) cells0 *= std::ceil((double)(bboxMax[k] - bboxMin[k]) / info.SupportRadius) + 9.0;
@@ -349,7 +350,7 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
     searchBytes += ((size_t)cellCapacity * 2 + 8) * 4;
     allocBytes += ((size_t)cellCapacity * 2 + 8) * 4;
     CK(dalloc(A.partials, (size_t)4 * 65536));
-    for (uint32_t b = 0; b < info.RigidBodyCount; b++) { CK(dalloc(A.bx[b], np)); CK(dalloc(A.bcoef[b], np)); allocBytes += np * 32; }
+    for (uint32_t b = 0; b < info.RigidBodyCount; b++) { CK(dalloc(A.bx[b], np)); CK(dalloc(A.bcoef[b], np)); CK(dalloc(A.bgrad[b], np)); allocBytes += np * 48; }
     return VFD_OK;
 }
 
@@ -462,10 +463,12 @@ int Solver::set_rigid_bodies(uint32_t count, const VfdVolumeMap* maps) {
     for (int b = 0; b < VFD_MAX_BODIES; b++) {
         if (arrays.bx[b]) { cudaFree(arrays.bx[b]); arrays.bx[b] = nullptr; }
         if (arrays.bcoef[b]) { cudaFree(arrays.bcoef[b]); arrays.bcoef[b] = nullptr; }
+        if (arrays.bgrad[b]) { cudaFree(arrays.bgrad[b]); arrays.bgrad[b] = nullptr; }
     }
     for (uint32_t b = 0; b < count && (info.ParticleCount || dist); b++) {
         CK(dalloc(arrays.bx[b], np)); CK(cudaMemset(arrays.bx[b], 0, np * 16));
         CK(dalloc(arrays.bcoef[b], np)); CK(cudaMemset(arrays.bcoef[b], 0, np * 16));
+        CK(dalloc(arrays.bgrad[b], np)); CK(cudaMemset(arrays.bgrad[b], 0, np * 16));
     }
     info.RigidBodyCount = count;
     refresh_params();

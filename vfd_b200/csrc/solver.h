@@ -32,6 +32,8 @@ struct Arrays {
     uint16_t *list16;                       // neighbour lists: tile-local indices, warp-blocked ELL (tile.cuh)
     float    *coef;                         // per-pair viscosity coefficient, same ELL layout (frozen during the PCG)
     float4   *bcoef[VFD_MAX_BODIES];        // per-particle boundary-friction coefficients of the 4 tangential samples
+    float    *gcoef;                        // per-pair kernel-gradient factor g_ij (gradW = g x_ij), same ELL layout; written by the density pass
+    float4   *bgrad[VFD_MAX_BODIES];        // per particle and body: (gradW(x_i - x_b), V_b), zero when out of range; written by the density pass
     uint32_t *key, *rank, *tmpIdx, *cellCount, *cellBegin, *tileSums;
     uint32_t *ctaTile;                      // balanced static partition of the tiles over the CTAs of a pipelined pass (search.cu)
     // reductions

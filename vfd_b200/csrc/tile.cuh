@@ -276,6 +276,14 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 // the slowest warp; the copy of tile k+2 overlaps the pair loop of tile k+1.  One CTA per SM.
 // Work assignment is static (tile -> CTA round robin, batch -> warp rotating with the running batch count), so every
 // per-thread partial sum is accumulated in the same order run after run: reductions stay bit-reproducible.
+//
+// Op interface of a pipelined pass.  All ops:  NPAY (1|2), BBYTES (16: payload B is a float4 array, 4: a float array),
+//   const float4* srcA(), const void* srcB()      global payload arrays the producers copy from
+//   float4 loadA(g), loadB(g)                     the same payload for the exact fallback path
+//   void prefetch_own(pt, b0, e0)                 optional L2 prefetch of the op's per-particle arrays (producer thread pt)
+// Pair ops (CUSTOM == false): NOWN, NSUM, COEF (bit 0: a per-pair coefficient stream is read, bit 1: one is written;
+//   both in the list's ELL layout), const float* coef_in(), float* coef_out(), load_own, pair(own, a, b, coef&, acc),
+//   finish(p, m, own, sum) — as for tile_pass.  Custom ops: particle(p, valid, acc, H), called by all 32 lanes.
 #define PIPE_STAGES 4          // tiles in flight per CTA (header slots); their payloads share one ring of PIPE_RING particle slots
 #ifndef PIPE_CONSUMER_WARPS
 #define PIPE_CONSUMER_WARPS 16
@@ -493,7 +501,7 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
             if (pfGroups) for (uint32_t blk = blk0 + pt; blk <= blk1; blk += PIPE_PRODUCER_THREADS) {
                 const size_t g0 = (size_t)blk * (ELL_GROUPS * 32);
                 l2_prefetch(A.list16, g0 * 8, (g0 + pfGroups * 32) * 8);
-                if (Op::COEF == 1) l2_prefetch(A.coef, g0 * 16, (g0 + pfGroups * 32) * 16);
+                if constexpr ((Op::COEF & 1) != 0) l2_prefetch(op.coef_in(), g0 * 16, (g0 + pfGroups * 32) * 16);
             }
             if (op.P.tune[1]) {
                 if (pt == PIPE_PRODUCER_THREADS - 1) l2_prefetch(A.cnt, (size_t)b0_ * 4, (size_t)e0_ * 4);
@@ -509,86 +517,6 @@ template<class Op> struct PipeAcc {
     const StageHeader& H; const float4* sA; const Op& op; bool staged;
     __device__ __forceinline__ float4 operator()(uint32_t L) const { return staged ? sA[L] : op.loadA(hdr_local_to_global(H, L)); }
 };
-
-// ---- consumer: one batch of 32 particles (one per lane) -------------------------------------------
-template<class Op, bool STAGED>
-__device__ __forceinline__ void pipe_batch(uint32_t p, bool valid, const StageHeader& H, const Arrays& A,
-                                           const float4* __restrict__ sA, const void* __restrict__ sBv, Op& op) {
-    constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
-    const float4* __restrict__ sB = reinterpret_cast<const float4*>(sBv);
-    const float* __restrict__ sB1 = reinterpret_cast<const float*>(sBv);
-    auto gatherB = [&](uint32_t L) -> float4 {
-        if (BBYTES == 16) return sB[L];
-        if (BBYTES == 4) return make_float4(sB1[L], 0.0f, 0.0f, 0.0f);
-        return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    };
-    if (!valid) return;
-    const uint32_t m = __ldg(A.cnt + p);
-    float own[Op::NOWN];
-    op.load_own(p, own);
-    float acc[Op::NSUM];
-    #pragma unroll
-    for (int s = 0; s < Op::NSUM; s++) acc[s] = 0.0f;
-    const uint2* __restrict__ col = ell_list(A.list16, p);
-    float4* __restrict__ ccol = reinterpret_cast<float4*>(A.coef) + ell_base(p);
-    const uint32_t nG = (m + 3u) >> 2;
-    // the list (and coefficient) words stream from HBM: PIPE_LOOKAHEAD groups (16 neighbours) are in flight per lane,
-    // held in a register ring that the fully unrolled inner loop indexes statically
-    constexpr int D = PIPE_LOOKAHEAD;
-    const uint32_t gLast = nG ? nG - 1u : 0u;             // past the end a lane re-reads its last group (an L2 hit)
-    uint2 wr[D]; float4 cr[D];
-    #pragma unroll
-    for (int i = 0; i < D; i++) {
-        // the first D groups are loaded whether or not the particle has that many neighbours (the slots exist): the
-        // addresses do not depend on the count, so these loads go out together with it
-        wr[i] = __ldg(col + (size_t)i * 32);
-        cr[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (Op::COEF == 1) cr[i] = __ldg(reinterpret_cast<const float4*>(ccol) + (size_t)i * 32);
-    }
-    auto group = [&](const uint2 wq, const float4 cq, const uint32_t g) {
-        uint32_t L[4];
-        ell_unpack(wq, L);
-        float c[4] = { cq.x, cq.y, cq.z, cq.w };
-        if (g * 4u + 4u <= m) {
-            float4 pa[4], pb[4];
-            #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (STAGED) { pa[u] = sA[L[u]]; pb[u] = gatherB(L[u]); }
-                else { const uint32_t gi = hdr_local_to_global(H, L[u]); pa[u] = op.loadA(gi); pb[u] = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
-            }
-            #pragma unroll
-            for (int u = 0; u < 4; u++) op.pair(own, pa[u], pb[u], c[u], acc);
-        } else {
-            #pragma unroll
-            for (int u = 0; u < 3; u++) {                    // a partial group holds one to three neighbours
-                if (g * 4u + (uint32_t)u < m) {
-                    float4 xa, xb;
-                    if (STAGED) { xa = sA[L[u]]; xb = gatherB(L[u]); }
-                    else { const uint32_t gi = hdr_local_to_global(H, L[u]); xa = op.loadA(gi); xb = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
-                    op.pair(own, xa, xb, c[u], acc);
-                } else c[u] = 0.0f;
-            }
-            c[3] = 0.0f;
-        }
-        if (Op::COEF == 2) ccol[(size_t)g * 32] = make_float4(c[0], c[1], c[2], c[3]);
-    };
-    // main loop: every ring slot is consumed and reloaded unconditionally (no merge of an old and a new value, so the
-    // load targets the ring register itself); the last 0..D-1 groups drain the ring
-    uint32_t g0 = 0;
-    for (; g0 + D <= nG; g0 += D) {
-        #pragma unroll
-        for (int i = 0; i < D; i++) {
-            group(wr[i], cr[i], g0 + (uint32_t)i);
-            // reloaded once its old value is dead, so the load can target the ring registers directly
-            const uint32_t gn = min(g0 + (uint32_t)i + D, gLast);
-            wr[i] = __ldg(col + (size_t)gn * 32);
-            if (Op::COEF == 1) cr[i] = __ldg(reinterpret_cast<const float4*>(ccol) + (size_t)gn * 32);
-        }
-    }
-    #pragma unroll
-    for (int i = 0; i < D - 1; i++) if (g0 + (uint32_t)i < nG) group(wr[i], cr[i], g0 + (uint32_t)i);
-    op.finish(p, m, own, acc);
-}
 
 template<class Op>
 __device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, const unsigned char* pay, Op& op) {
@@ -609,13 +537,8 @@ __device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, c
         // batch b of this tile goes to warp (rot + b) mod W: consecutive batches of consecutive tiles visit the warps in turn
         for (uint32_t b = (cw + PIPE_CONSUMER_WARPS - rot) % PIPE_CONSUMER_WARPS; b < nBatch; b += PIPE_CONSUMER_WARPS) {
             const uint32_t p = begin + (b << 5) + lane;
-            if constexpr (Op::CUSTOM) {
-                const PipeAcc<Op> acc{ H, sA, op, staged };
-                op.particle(p, p < end, acc, H);
-            } else {
-                if (staged) pipe_batch<Op, true>(p, p < end, H, A, sA, sB, op);
-                else        pipe_batch<Op, false>(p, p < end, H, A, sA, sB, op);
-            }
+            const PipeAcc<Op> acc{ H, sA, op, staged };
+            op.particle(p, p < end, acc, H);
         }
         rot = (rot + nBatch) % PIPE_CONSUMER_WARPS;
         __syncwarp();
@@ -655,12 +578,12 @@ __device__ __forceinline__ void pipe_head_load(BatchHead<Op>& h, const BatchCurs
     h.m = __ldg(A.cnt + h.p);
     op.load_own(h.p, h.own);
     const uint2* __restrict__ col = ell_list(A.list16, h.p);
-    const float4* __restrict__ ccol = reinterpret_cast<const float4*>(A.coef) + ell_base(h.p);
+    const float4* __restrict__ cin = reinterpret_cast<const float4*>(op.coef_in()) + ell_base(h.p);
     #pragma unroll
     for (int i = 0; i < D; i++) {
         // the first D groups are loaded whether or not the particle has that many neighbours (the slots exist)
         h.wr[i] = __ldg(col + (size_t)i * 32);
-        if (Op::COEF == 1) h.cr[i] = __ldg(ccol + (size_t)i * 32);
+        if (Op::COEF & 1) h.cr[i] = __ldg(cin + (size_t)i * 32);
     }
 }
 
@@ -679,7 +602,8 @@ __device__ __forceinline__ void pipe_gather(BatchHead<Op>& h, float (&acc)[Op::N
     const uint32_t m = h.m;
     if (m == 0u) return;
     const uint2* __restrict__ col = ell_list(A.list16, h.p);
-    float4* __restrict__ ccol = reinterpret_cast<float4*>(A.coef) + ell_base(h.p);
+    const float4* __restrict__ cin = reinterpret_cast<const float4*>(op.coef_in()) + ell_base(h.p);
+    float4* __restrict__ cout = reinterpret_cast<float4*>(op.coef_out()) + ell_base(h.p);
     const uint32_t nG = (m + 3u) >> 2;
     const uint32_t gLast = nG - 1u;                       // past the end a lane re-reads its last group (an L2 hit)
     auto group = [&](const uint2 wq, const float4 cq, const uint32_t g) {
@@ -707,7 +631,7 @@ __device__ __forceinline__ void pipe_gather(BatchHead<Op>& h, float (&acc)[Op::N
             }
             c[3] = 0.0f;
         }
-        if (Op::COEF == 2) ccol[(size_t)g * 32] = make_float4(c[0], c[1], c[2], c[3]);
+        if (Op::COEF & 2) cout[(size_t)g * 32] = make_float4(c[0], c[1], c[2], c[3]);
     };
     uint32_t g0 = 0;
     for (; g0 + D <= nG; g0 += D) {
@@ -716,7 +640,7 @@ __device__ __forceinline__ void pipe_gather(BatchHead<Op>& h, float (&acc)[Op::N
             group(h.wr[i], h.cr[i], g0 + (uint32_t)i);
             const uint32_t gn = min(g0 + (uint32_t)i + D, gLast);
             h.wr[i] = __ldg(col + (size_t)gn * 32);
-            if (Op::COEF == 1) h.cr[i] = __ldg(reinterpret_cast<const float4*>(ccol) + (size_t)gn * 32);
+            if (Op::COEF & 1) h.cr[i] = __ldg(cin + (size_t)gn * 32);
         }
     }
     #pragma unroll
@@ -790,10 +714,7 @@ __device__ __forceinline__ void pipe_pass(DevState* __restrict__ S, const Arrays
     __syncthreads();
     if (threadIdx.x >= PIPE_CONSUMER_WARPS * 32) pipe_producer(S, A, ps, pay, op, tile0, tile1, checkIndexRange);
     else if constexpr (Op::CUSTOM) pipe_consumer(A, ps, pay, op);
-    else {
-        if (op.P.tune[4] == 0) pipe_consumer_pairs(A, ps, pay, op);      // default; tune[4] = 1: the plain loop (A/B runs)
-        else pipe_consumer(A, ps, pay, op);
-    }
+    else pipe_consumer_pairs(A, ps, pay, op);
     __syncthreads();
 }
 

@@ -61,10 +61,15 @@ __device__ __forceinline__ bool boundary_samples(const Params& P, float3 xi, flo
 // ---- V1 + V2 fused: preconditioner blocks, per-pair coefficients, warm start, |b|^2 ----------
 struct ViscSetupOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 1, NOWN = 3, NSUM = 9, COEF = 2;       // payload (x, y, z, rho); writes the pair coefficients
-    const Params& P; const Arrays& A; Lut K;
+    static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 9, COEF = 3;   // payload (x, y, z, rho); reads the pair's kernel-gradient
+    const Params& P; const Arrays& A; Lut K;                                   // factor g_ij (pressure.cu), writes the pair coefficients
     float dt, eps2;
     float bb;
+    __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
+    __device__ __forceinline__ const void* srcB() const { return nullptr; }
+    __device__ __forceinline__ const float* coef_in() const { return A.gcoef; }
+    __device__ __forceinline__ float* coef_out() const { return A.coef; }
+    __device__ __forceinline__ void prefetch_own(uint32_t, uint32_t, uint32_t) const {}
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
     __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
@@ -72,7 +77,7 @@ struct ViscSetupOp {
     }
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 xj, float4, float& coef, float (&M)[NSUM]) const {
         const float3 d = f3(o[0], o[1], o[2]) - f3(xj);
-        const float g = K.gradWScalar(d);
+        const float g = coef;                             // gradW(d) = g d
         const float3 gw = g * d;
         const float s = 10.0f * P.mu * (P.mass / xj.w) / (dot3(d, d) + eps2);
         coef = s * g;
@@ -142,17 +147,16 @@ struct ViscSetupOp {
     }
 };
 
-__global__ void __launch_bounds__(TT_LUT, 2) k_visc_setup(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
-    TileShared& sh = smem_header(smemRaw);
-    float* sG = smem_lut<1>(smemRaw);
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_visc_setup(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+    PipeShared& ps = pipe_header(smemRaw);
+    float* sG = pipe_lut<1>(smemRaw);                     // the boundary-friction samples still need the table
     load_lut_tile(sG, lutG);
     ViscSetupOp op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, 0.01f * P.h2, 0.0f };
-    tile_pass(S, A, sh, smem_pay_a<1>(smemRaw), nullptr, STAGE_CAP, op, P.tile0, P.tile1);
-    __syncthreads();
+    pipe_pass(S, A, ps, pipe_pay<1>(smemRaw), op, P.tile0, P.tile1);
     double v[1] = { (double)op.bb };
-    if (block_reduce_publish<1>(v, A.partials, &S->ticket[4], sh.red)) {
+    if (block_reduce_publish<1>(v, A.partials, &S->ticket[4], ps.red)) {
         double tot[1];
-        last_block_fold<1>(tot, A.partials, sh.red);
+        last_block_fold<1>(tot, A.partials, ps.red);
         if (threadIdx.x == 0) {
             finish_reduction<1>(SITE_VISC_BB, P, S, tot);
             S->ticket[4] = 0;
@@ -180,6 +184,8 @@ struct ViscMatvecOp {
     static constexpr int BBYTES = 16;
     __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
     __device__ __forceinline__ const void* srcB() const { return x; }
+    __device__ __forceinline__ const float* coef_in() const { return A.coef; }
+    __device__ __forceinline__ float* coef_out() const { return nullptr; }
     __device__ __forceinline__ void prefetch_own(uint32_t pt, uint32_t b0, uint32_t e0) const {
         if (P.muB != 0.0f && pt < P.nBodies) {
             l2_prefetch(A.bx[pt], (size_t)b0 * 16, (size_t)e0 * 16);
@@ -232,27 +238,6 @@ struct ViscMatvecOp {
     }
 };
 
-template<bool INIT>
-__global__ void __launch_bounds__(TT_MATVEC, 2) k_visc_matvec(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
-    if (!INIT && S->viscActive != 1u) return;
-    TileShared& sh = smem_header(smemRaw);
-    ViscMatvecOp<INIT> op{ P, A, INIT ? A.cgG : A.cgP, S->dt, 0.0f, 0.0f };
-    tile_pass(S, A, sh, smem_pay_a<0>(smemRaw), smem_pay_b<0>(smemRaw, STAGE_CAP), STAGE_CAP, op, P.tile0, P.tile1);
-    __syncthreads();
-    double v[2] = { (double)op.s0, (double)op.s1 };
-    uint32_t* ticket = &S->ticket[5];
-    if (block_reduce_publish<2>(v, A.partials, ticket, sh.red)) {
-        double tot[2];
-        last_block_fold<2>(tot, A.partials, sh.red);
-        if (threadIdx.x == 0) {
-            if (INIT) finish_reduction<2>(SITE_VISC_INIT, P, S, tot);
-            else { const double t1[1] = { tot[0] }; finish_reduction<1>(SITE_VISC_PQ, P, S, t1); }
-            *ticket = 0;
-        }
-    }
-}
-
-// the same product on the asynchronous tile pipeline (tile.cuh: pipe_pass)
 template<bool INIT>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) k_visc_matvec_pipe(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (!INIT && S->viscActive != 1u) return;
@@ -327,55 +312,25 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_apply(Params P, Arrays A, DevS
 }
 
 template<typename Kern>
-static uint32_t tile_grid(Kern kern, size_t smem, const LaunchCfg& L, int threads) {
-    static thread_local const void* cachedK[16]; static thread_local int cachedV[16]; static thread_local int nc = 0;
-    int perSM = 0;
-    for (int i = 0; i < nc; i++) if (cachedK[i] == (const void*)kern) perSM = cachedV[i];
-    if (!perSM) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, threads, smem);
-        if (perSM < 1) perSM = 1;
-        if (nc < 16) { cachedK[nc] = (const void*)kern; cachedV[nc] = perSM; nc++; }
-    }
-    return (uint32_t)(perSM * L.numSMs);
+static void pipe_attr(Kern kern, size_t smem) {
+    static thread_local const void* done[16]; static thread_local int nd = 0;
+    for (int i = 0; i < nd; i++) if (done[i] == (const void*)kern) return;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (nd < 16) done[nd++] = (const void*)kern;
 }
 
 void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t s0 = tile_smem_bytes<1, 1>(STAGE_CAP);
-    const uint32_t g0 = tile_grid(k_visc_setup, s0, L, TT_LUT);
+    const size_t sp = pipe_smem_bytes<1, 16, 0>();
+    pipe_attr(k_visc_setup, sp);
     LaunchScope ls(L, KID_VISC_SETUP);
-    k_visc_setup<<<g0, TT_LUT, s0, L.stream>>>(P, A, S, lutG);
-}
-static int pipe_mode() {
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("VFD_TILE_PIPELINE"); mode = e ? atoi(e) : 1; }
-    return mode;
+    k_visc_setup<<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S, lutG);
 }
 
 void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init) {
-    if (pipe_mode()) {
-        const size_t sp = pipe_smem_bytes<0, 16, 16>();
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(k_visc_matvec_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
-            cudaFuncSetAttribute(k_visc_matvec_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
-            attr = true;
-        }
-        LaunchScope ls(L, init ? KID_VISC_MATVEC0 : KID_VISC_MATVEC);
-        if (init) k_visc_matvec_pipe<true><<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S);
-        else      k_visc_matvec_pipe<false><<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S);
-        return;
-    }
-    const size_t s1 = tile_smem_bytes<0, 2>(STAGE_CAP);
-    if (init) {
-        const uint32_t g1 = tile_grid(k_visc_matvec<true>, s1, L, TT_MATVEC);
-        LaunchScope ls(L, KID_VISC_MATVEC0);
-        k_visc_matvec<true><<<g1, TT_MATVEC, s1, L.stream>>>(P, A, S);
-    } else {
-        const uint32_t g1 = tile_grid(k_visc_matvec<false>, s1, L, TT_MATVEC);
-        LaunchScope ls(L, KID_VISC_MATVEC);
-        k_visc_matvec<false><<<g1, TT_MATVEC, s1, L.stream>>>(P, A, S);
-    }
+    const size_t sp = pipe_smem_bytes<0, 16, 16>();
+    LaunchScope ls(L, init ? KID_VISC_MATVEC0 : KID_VISC_MATVEC);
+    if (init) { pipe_attr(k_visc_matvec_pipe<true>, sp); k_visc_matvec_pipe<true><<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S); }
+    else      { pipe_attr(k_visc_matvec_pipe<false>, sp); k_visc_matvec_pipe<false><<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S); }
 }
 void launch_viscosity_update(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     const uint32_t tiles = std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB);
