@@ -87,6 +87,9 @@ struct DevState {
     // multi-GPU: global cell coordinates of the local grid's cell (0,0,0)
     int32_t cellOffset[3];
     uint32_t fallbackTiles;     // tile passes whose halo box exceeded the shared-memory stage (slow, exact path); cumulative
+    // dynamic tile queue of the pipelined passes (tile.cuh): next entry of the tile list, CTAs that have finished the
+    // running pass (the last one resets both)
+    uint32_t tileCursor, doneCtas;
 };
 
 struct float3x3 { float m[9]; };   // column-major like glm::mat3x3: m[3*c + r]
@@ -215,6 +218,38 @@ __device__ __forceinline__ void last_block_fold(double (&out)[NV], const double*
     for (int q = 0; q < NV; q++) {
         double x = isMax ? -DBL_MAX : 0.0;
         for (int w = 0; w < nwarps; w++) { const double y = sh[q * 32 + w]; x = isMax ? fmax(x, y) : x + y; }
+        out[q] = x;
+    }
+}
+
+// Reductions of the dynamically scheduled tile passes: which CTA processes a tile is decided at run time, so partial
+// sums are kept per TILE, in the slot of the tile's entry in the tile list (tile.cuh: RedRecord); the last CTA to
+// finish folds the slots in list order — bit-reproducible run to run whatever the schedule was.  Result valid in every thread.
+template<int NV>
+__device__ __forceinline__ void fold_slots(double (&out)[NV], const double* __restrict__ slots, uint32_t nSlots, size_t stride, double* sh) {
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    #pragma unroll
+    for (int q = 0; q < NV; q++) {
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+        uint32_t b = threadIdx.x;
+        for (; b + 3u * blockDim.x < nSlots; b += 4u * blockDim.x) {
+            const double* p = slots + (size_t)q * stride + b;
+            const double y0 = __ldcg(p), y1 = __ldcg(p + blockDim.x), y2 = __ldcg(p + 2u * blockDim.x), y3 = __ldcg(p + 3u * blockDim.x);
+            x0 += y0; x1 += y1; x2 += y2; x3 += y3;
+        }
+        for (; b < nSlots; b += blockDim.x) x0 += __ldcg(slots + (size_t)q * stride + b);
+        double x = (x0 + x1) + (x2 + x3);
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        __syncthreads();
+        if (lane == 0) sh[q * 32 + warp] = x;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int q = 0; q < NV; q++) {
+        double x = 0.0;
+        for (int w = 0; w < nwarps; w++) x += sh[q * 32 + w];
         out[q] = x;
     }
 }

@@ -45,7 +45,7 @@ extern __shared__ __align__(128) unsigned char smemRaw[];
 // ---- K2 + K3 + K8 fused: density, DFSPH factor, a = g; writes the pair factors g_ij and the boundary gradients ----
 struct DensityFactorOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 5, COEF = 2;
+    static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 5, COEF = 2, NRED = 0;
     const Params& P; const Arrays& A; Lut K;
     __device__ __forceinline__ const float4* srcA() const { return A.pos; }
     __device__ __forceinline__ const void* srcB() const { return nullptr; }
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_density_factor(const __grid
 template<bool DIV>
 struct SourceOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1;
+    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1, NRED = 0;
     const Params& P; const Arrays& A;
     float dt, dtInv, dt2Inv;
     __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
@@ -165,7 +165,7 @@ enum { ACC_DIV_ITER = 0, ACC_DIV_FINISH = 1, ACC_PRESS_ITER = 2, ACC_PRESS_FINIS
 template<int MODE>
 struct AccelOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 2, BBYTES = 4, NOWN = 4, NSUM = 3, COEF = 1;       // payload: (x, y, z, rho) and kappa
+    static constexpr int NPAY = 2, BBYTES = 4, NOWN = 4, NSUM = 3, COEF = 1, NRED = 0;     // payload: (x, y, z, rho) and kappa
     const Params& P; const Arrays& A;
     const float* __restrict__ kap;
     float dt;
@@ -219,10 +219,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pressure_accel(const __grid
 template<bool DIV>
 struct SolveOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1;       // payload: position, pressure acceleration
+    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1, NRED = 1;   // payload: position, pressure acceleration
     const Params& P; const Arrays& A;
     float scale;
-    float errSum;
+    float red[1];                                          // rho0 * residuum of the lane's particle (summed grid-wide: tile.cuh RedRecord)
     __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
     __device__ __forceinline__ const void* srcB() const { return A.pacc; }
     COEF_IN_G
@@ -253,7 +253,7 @@ struct SolveOp {
             A.kappa[p] -= residuum * A.alpha[p];
         }
         A.res[p] = residuum;
-        errSum += P.rho0 * residuum;
+        red[0] = P.rho0 * residuum;
     }
 };
 
@@ -261,17 +261,11 @@ template<bool DIV>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_iteration(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (DIV ? !S->divActive : !S->pressActive) return;
     PipeShared& ps = pipe_header(smemRaw);
-    SolveOp<DIV> op{ P, A, DIV ? S->dt : S->dt2, 0.0f };
-    pipe_pass(S, A, ps, pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
-    double v[1] = { (double)op.errSum };
-    uint32_t* ticket = &S->ticket[DIV ? 1 : 2];
-    if (block_reduce_publish<1>(v, A.partials, ticket, ps.red)) {
+    SolveOp<DIV> op{ P, A, DIV ? S->dt : S->dt2, { 0.0f } };
+    if (pipe_pass(S, A, ps, pipe_pay<0>(smemRaw), op, P.tile0, P.tile1)) {
         double tot[1];
-        last_block_fold<1>(tot, A.partials, ps.red);
-        if (threadIdx.x == 0) {
-            finish_reduction<1>(DIV ? SITE_DIV : SITE_PRESS, P, S, tot);
-            *ticket = 0;
-        }
+        fold_slots<1>(tot, A.slotSums, __ldg(A.tileList), A.slotStride, ps.red);
+        if (threadIdx.x == 0) finish_reduction<1>(DIV ? SITE_DIV : SITE_PRESS, P, S, tot);
     }
 }
 

@@ -177,55 +177,39 @@ __global__ void __launch_bounds__(VFD_TPB) k_scan_apply(Params P, const DevState
     if (blockIdx.x == 0 && threadIdx.x == 0) cellBegin[nCells] = P.n;
 }
 
-// S3b: static, cost-balanced partition of the owned tiles over the G CTAs of a pipelined tile pass (tile.cuh):
-// CTA c gets the contiguous tile range [ctaTile[c], ctaTile[c+1]) holding ~1/G of the total weight, a non-empty
-// tile weighing its particle count plus a constant for staging its halo box (a surface tile with 30 particles still
-// stages ~1700).  A fixed partition keeps every reduction's summation order fixed (bit-reproducible), which a dynamic
-// tile queue would not.  One block; thread i owns a contiguous chunk of tiles.
+// S3b: the non-empty owned tiles, compacted in tile order: tileList[0] = their number K, tileList[1..K] = tile indices.
+// A pipelined tile pass (tile.cuh) hands entry i to CTA i mod G: every CTA gets the same number of non-empty tiles
+// (+-1) — about a quarter of the grid's tiles are empty in a settled dam break, and a round robin over ALL tiles left
+// some CTAs with a third more work than the mean — while CTAs that run side by side still work on neighbouring tiles
+// and share their halo boxes in L2 (a contiguous range per CTA was measured 60 % slower for that reason).  The
+// assignment is static, so every reduction's summation order is fixed (bit-reproducible), which a dynamic tile queue
+// would not give.  One block; thread i owns a contiguous chunk of tiles.
 #define PARTITION_THREADS 1024
-__global__ void __launch_bounds__(PARTITION_THREADS) k_partition_tiles(Params P, const DevState* __restrict__ S, const uint32_t* __restrict__ cellBegin,
-                                                                       uint32_t* __restrict__ ctaTile, uint32_t G, uint32_t tileWeight) {
-    __shared__ unsigned long long shScan[PARTITION_THREADS / 32 + 1];
+__global__ void __launch_bounds__(PARTITION_THREADS) k_compact_tiles(Params P, DevState* __restrict__ S, const uint32_t* __restrict__ cellBegin,
+                                                                     uint32_t* __restrict__ tileList) {
+    __shared__ uint32_t shScan[PARTITION_THREADS / 32 + 1];
     const uint32_t t0 = P.tile0, t1 = min(S->nTiles, P.tile1);
     const uint32_t nT = t1 > t0 ? t1 - t0 : 0u;
     const uint32_t chunk = (nT + PARTITION_THREADS - 1) / PARTITION_THREADS;
     const uint32_t a = min(t0 + threadIdx.x * chunk, t1), b = min(a + chunk, t1);
-    auto weight = [&](uint32_t t) -> uint32_t {
-        const uint32_t n = cellBegin[(size_t)(t + 1) * TILE_CELLS] - cellBegin[(size_t)t * TILE_CELLS];
-        return n ? n + tileWeight : 0u;
-    };
-    unsigned long long mine = 0;
-    for (uint32_t t = a; t < b; t++) mine += weight(t);
-    // block-wide exclusive scan of the chunk sums
+    auto nonempty = [&](uint32_t t) -> bool { return cellBegin[(size_t)(t + 1) * TILE_CELLS] != cellBegin[(size_t)t * TILE_CELLS]; };
+    uint32_t mine = 0;
+    for (uint32_t t = a; t < b; t++) mine += nonempty(t) ? 1u : 0u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long inc = mine;
+    uint32_t inc = mine;
     #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
     if (lane == 31) shScan[warp] = inc;
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long run = 0;
-        for (int w = 0; w < PARTITION_THREADS / 32; w++) { const unsigned long long v = shScan[w]; shScan[w] = run; run += v; }
-        shScan[PARTITION_THREADS / 32] = run;
+        uint32_t run = 0;
+        for (int w = 0; w < PARTITION_THREADS / 32; w++) { const uint32_t v = shScan[w]; shScan[w] = run; run += v; }
+        tileList[0] = run;
+        S->tileCursor = 0u; S->doneCtas = 0u;
     }
     __syncthreads();
-    const unsigned long long total = shScan[PARTITION_THREADS / 32];
-    unsigned long long run = shScan[warp] + inc - mine;          // weight of all tiles before this chunk
-    // boundary c sits at the first tile where the cumulative weight reaches c * total / G
-    if (threadIdx.x == 0) { ctaTile[0] = t0; ctaTile[G] = t1; }
-    if (total == 0) { for (uint32_t c = 1 + threadIdx.x; c < G; c += blockDim.x) ctaTile[c] = t1; return; }
-    uint32_t c = (uint32_t)((run * G + total - 1) / total);       // smallest c with c * total / G >= run  (ceil(run * G / total))
-    if (c == 0) c = 1;
-    for (uint32_t t = a; t < b; t++) {
-        const unsigned long long next = run + weight(t);
-        while (c < G && (unsigned long long)c * total / G < next) {
-            if ((unsigned long long)c * total / G >= run) ctaTile[c] = t;
-            c++;
-        }
-        run = next;
-    }
-    // boundaries that fall exactly at the total weight (only possible for trailing empty ranges)
-    if (threadIdx.x == blockDim.x - 1) while (c < G) { ctaTile[c] = t1; c++; }
+    uint32_t run = shScan[warp] + inc - mine;
+    for (uint32_t t = a; t < b; t++) if (nonempty(t)) tileList[1u + run++] = t;
 }
 
 // S4: scatter slot indices into cell order (arbitrary order inside a cell)
@@ -355,7 +339,7 @@ void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, 
     { LaunchScope ls(L, KID_SCAN); k_scan_tiles<<<st, VFD_TPB, 0, L.stream>>>(S, A.cellCount, A.tileSums); }
     { LaunchScope ls(L, KID_SCAN); k_scan_tile_sums<<<1, 1024, 0, L.stream>>>(S, A.tileSums); }
     { LaunchScope ls(L, KID_SCAN); k_scan_apply<<<st, VFD_TPB, 0, L.stream>>>(P, S, A.cellCount, A.tileSums, A.cellBegin); }
-    { LaunchScope ls(L, KID_SCAN); k_partition_tiles<<<1, PARTITION_THREADS, 0, L.stream>>>(P, S, A.cellBegin, A.ctaTile, (uint32_t)L.numSMs, P.tune[2] ? (uint32_t)P.tune[2] : 256u); }
+    { LaunchScope ls(L, KID_SCAN); k_compact_tiles<<<1, PARTITION_THREADS, 0, L.stream>>>(P, S, A.cellBegin, A.tileList); }
     { LaunchScope ls(L, KID_SCATTER); k_scatter<<<nb, VFD_TPB, 0, L.stream>>>(P, A.key, A.rank, A.cellBegin, A.tmpIdx); }
     { LaunchScope ls(L, KID_REORDER); k_reorder<<<nb, VFD_TPB, 0, L.stream>>>(P, A); }
     std::swap(A.pos, A.pos2); std::swap(A.vel, A.vel2); std::swap(A.dv, A.dv2); std::swap(A.nbar, A.nbar2);

@@ -291,7 +291,7 @@ void Solver::free_particles() {
     Arrays& A = arrays;
     void* ptrs[] = { A.pos, A.vel, A.dv, A.nbar, A.curv, A.curvS, A.curvD, A.id, A.pos2, A.vel2, A.dv2, A.nbar2, A.curv2, A.curvS2, A.curvD2, A.id2,
                      A.posRho, A.acc, A.pacc, A.nrm, A.res, A.rho, A.rhoAdv, A.kappa, A.kappaV, A.alpha, A.cgG, A.cgR, A.cgP, A.cgQ, A.cgZ, A.minv,
-                     A.cnt, A.list16, A.coef, A.gcoef, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.ctaTile, A.partials, dPos0, dVel0 };
+                     A.cnt, A.list16, A.coef, A.gcoef, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.tileList, A.partials, A.slotSums, dPos0, dVel0 };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (dIds0) { cudaFree(dIds0); dIds0 = nullptr; }
     for (int b = 0; b < VFD_MAX_BODIES; b++) { if (A.bx[b]) cudaFree(A.bx[b]); if (A.bcoef[b]) cudaFree(A.bcoef[b]); if (A.bgrad[b]) cudaFree(A.bgrad[b]); }
@@ -346,10 +346,13 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
     CK(cudaMemset(A.cellCount, 0, ((size_t)cellCapacity + 4) * 4));
     CK(cudaMemset(A.cellBegin, 0, ((size_t)cellCapacity + 4) * 4));
     CK(dalloc(A.tileSums, (size_t)cellCapacity / 4096 + 8));
-    CK(dalloc(A.ctaTile, (size_t)1024));
+    CK(dalloc(A.tileList, (size_t)cellCapacity / TILE_CELLS + 8));
     searchBytes += ((size_t)cellCapacity * 2 + 8) * 4;
     allocBytes += ((size_t)cellCapacity * 2 + 8) * 4;
     CK(dalloc(A.partials, (size_t)4 * 65536));
+    A.slotStride = (uint32_t)((size_t)cellCapacity / TILE_CELLS + 8);      // one reduction slot per listed tile
+    CK(dalloc(A.slotSums, (size_t)2 * A.slotStride));
+    CK(cudaMemset(A.slotSums, 0, (size_t)2 * A.slotStride * sizeof(double)));
     for (uint32_t b = 0; b < info.RigidBodyCount; b++) { CK(dalloc(A.bx[b], np)); CK(dalloc(A.bcoef[b], np)); CK(dalloc(A.bgrad[b], np)); allocBytes += np * 48; }
     return VFD_OK;
 }

@@ -35,9 +35,11 @@ struct Arrays {
     float    *gcoef;                        // per-pair kernel-gradient factor g_ij (gradW = g x_ij), same ELL layout; written by the density pass
     float4   *bgrad[VFD_MAX_BODIES];        // per particle and body: (gradW(x_i - x_b), V_b), zero when out of range; written by the density pass
     uint32_t *key, *rank, *tmpIdx, *cellCount, *cellBegin, *tileSums;
-    uint32_t *ctaTile;                      // balanced static partition of the tiles over the CTAs of a pipelined pass (search.cu)
+    uint32_t *tileList;                     // [0] = number of non-empty owned tiles, [1..] their indices (search.cu: k_compact_tiles)
     // reductions
     double* partials;
+    double* slotSums;                       // per-batch partial sums of the pipelined passes: slotSums[q * slotStride + slot] (common.cuh: fold_slots)
+    uint32_t slotStride;
 };
 
 // Flattened volume map on the device (reference: SDFDeviceData, Utility/SDF/SDFDeviceData.cuh:552-566)

@@ -239,12 +239,11 @@ __device__ __forceinline__ void tile_particles(const TileInfo& t, const TileShar
 template<class Op>
 __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays& A, TileShared& sh,
                                           float4* sA, float4* sB, uint32_t cap, Op& op, uint32_t tile0, uint32_t tile1, bool checkIndexRange = false) {
-    const uint32_t nTiles = min(S->nTiles, tile1);
     const uint32_t* __restrict__ cellBegin = A.cellBegin;
-    for (uint32_t tile = tile0 + blockIdx.x; tile < nTiles; tile += gridDim.x) {
-        // cheap emptiness test before the full setup
-        const uint32_t b0 = __ldg(cellBegin + tile * TILE_CELLS), e0 = __ldg(cellBegin + tile * TILE_CELLS + TILE_CELLS);
-        if (b0 == e0) continue;
+    // the non-empty owned tiles (search.cu: k_compact_tiles), entry i to CTA i mod G
+    const uint32_t nList = __ldg(A.tileList);
+    for (uint32_t li = blockIdx.x; li < nList; li += gridDim.x) {
+        const uint32_t tile = __ldg(A.tileList + 1u + li);
         __syncthreads();                                   // previous tile's readers are done with shared memory
         const TileInfo t = tile_setup(S, cellBegin, tile, sh, cap);
         // local indices are 16-bit: a halo box beyond 65535 particles cannot be encoded (flagged, caught by the host)
@@ -305,12 +304,26 @@ struct StageHeader {
     uint32_t cellG[HALO_CELLS];       // as TileShared
     uint32_t local[HALO_CELLS + 8];
     uint32_t begin, end, total, staged;      // begin == 0xffffffff: no more tiles for this CTA
-    uint32_t base, pad[3];                   // first ring slot of this tile's payload
+    uint32_t base, li, pad[2];               // first ring slot of this tile's payload; the tile's entry in the tile list
     uint32_t scan[4];
+};
+// Grid-wide sums of a dynamically scheduled pass.  Every batch's warp-level sum goes into the record of its tile
+// (bsum[.][batch]); the warp that completes a tile's record folds it in batch order and stores ONE value per tile in
+// the global slot of the tile's list entry; the CTA that finishes the pass last folds the tile slots in list order
+// (common.cuh: fold_slots).  Every order is fixed, so the result does not depend on which CTA or warp did what.
+// Records are reused every PIPE_RED_RECORDS tiles of the CTA: by the time tile k + PIPE_STAGES can be entered every warp
+// has finished the epilogues of its batches up to tile k - 1, so 2 * PIPE_STAGES records are plenty.
+#define PIPE_MAX_BATCH 64      // a tile holds ~16 batches; beyond 63 (4x rest density) the surplus shares the last entry atomically
+#define PIPE_RED_RECORDS (2 * PIPE_STAGES)
+struct RedRecord {
+    double bsum[2][PIPE_MAX_BATCH];
+    uint32_t count, pad[3];
 };
 struct PipeShared {
     unsigned long long full[PIPE_STAGES], empty[PIPE_STAGES];
+    uint32_t nextLi[2], lastCta, pad_;       // tile queue hand-over between the producer threads (two slots, used in turn); "this CTA finished last"
     double red[4 * 32];
+    RedRecord rec[PIPE_RED_RECORDS];
     StageHeader hdr[PIPE_STAGES];
 };
 __host__ __device__ constexpr size_t pipe_header_bytes() { return (sizeof(PipeShared) + 127) / 128 * 128; }
@@ -374,23 +387,29 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
     const int gdx = (int)S->gridDim[0], gdy = (int)S->gridDim[1], gdz = (int)S->gridDim[2];
     const unsigned char* __restrict__ gA = reinterpret_cast<const unsigned char*>(op.srcA());
     const unsigned char* __restrict__ gB = reinterpret_cast<const unsigned char*>(op.srcB());
-    // this CTA's tiles: a contiguous, particle-balanced range (search.cu: k_partition_tiles); tile0/tile1 are folded into it
-    const bool roundRobin = op.P.tune[3] == 0;      // default: tile t -> CTA t mod G (neighbouring CTAs share halo boxes in L2 at the same time)
-    uint32_t tile = roundRobin ? tile0 + blockIdx.x : __ldg(A.ctaTile + blockIdx.x);
-    const uint32_t nTiles = roundRobin ? min(S->nTiles, tile1) : min(min(S->nTiles, tile1), __ldg(A.ctaTile + blockIdx.x + 1));
-    const uint32_t tileStep = roundRobin ? gridDim.x : 1u;
+    // Tiles come from a queue: the list of non-empty owned tiles (search.cu: k_compact_tiles) is handed out entry by entry
+    // through an atomic cursor, so a CTA that drew cheap tiles (surface, boundary) simply draws more of them, and CTAs
+    // that run side by side still work on neighbouring tiles and share their halo boxes in L2.  (A static round robin
+    // left the average CTA idle for 20 % of a pass: ncu smsp__cycles_active 80 % of elapsed.)  Reductions do not depend
+    // on the schedule (common.cuh: fold_slots).  Thread 0 draws one entry ahead, so the atomic's round trip overlaps the copies.
+    const uint32_t* __restrict__ tileList = A.tileList;
+    const uint32_t nList = __ldg(tileList);
+    uint32_t li = 0xffffffffu, liCur = 0xffffffffu, tile = 0xffffffffu, drawn = 0xffffffffu;
+    const bool staticQueue = op.P.tune[6] == 1;          // A/B knob: entry i to CTA i mod G instead of the atomic cursor
+    if (pt == 0) ps.nextLi[0] = staticQueue ? blockIdx.x : atomicAdd(&S->tileCursor, 1u);
+    producer_sync();
+    li = ps.nextLi[0];
+    if (pt == 0) drawn = staticQueue ? li + gridDim.x : atomicAdd(&S->tileCursor, 1u);
     // Thread pt owns PIPE_CELLS_PER_THREAD consecutive cells of the 6x6x6 box (box order hz, hy, hx).  The lookup of the
     // CTA's next non-empty tile and the loads of its cell table are issued one tile ahead (right after the previous
     // tile's copies), so their latency overlaps the copies and the wait for a free header slot.
     uint32_t b0 = 0, e0 = 0;
     uint32_t beg[PIPE_CELLS_PER_THREAD], cnt[PIPE_CELLS_PER_THREAD];
     auto next_tile = [&]() {
-        while (tile < nTiles) {
-            b0 = __ldg(cellBegin + tile * TILE_CELLS); e0 = __ldg(cellBegin + tile * TILE_CELLS + TILE_CELLS);
-            if (b0 != e0) break;
-            tile += tileStep;
-        }
-        if (tile >= nTiles) return;
+        if (li >= nList) { tile = 0xffffffffu; return; }
+        tile = __ldg(tileList + 1u + li);
+        liCur = li;
+        b0 = __ldg(cellBegin + tile * TILE_CELLS); e0 = __ldg(cellBegin + tile * TILE_CELLS + TILE_CELLS);
         const uint32_t tz = tile % tdz, ty = (tile / tdz) % tdy, tx = tile / (tdz * tdy);
         #pragma unroll
         for (int i = 0; i < PIPE_CELLS_PER_THREAD; i++) {
@@ -411,14 +430,14 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
     for (uint32_t k = 0;; k++) {
         const uint32_t s = k % PIPE_STAGES, u = k / PIPE_STAGES;
         StageHeader& H = ps.hdr[s];
-        if (tile >= nTiles) {
+        if (tile == 0xffffffffu) {
             mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);
             if (pt == 0) { H.begin = 0xffffffffu; H.end = 0xffffffffu; H.total = 0; H.staged = 0; }
             mbar_arrive(&ps.full[s]);
             if (pt == 0) mbar_arrive(&ps.full[s]);
             break;
         }
-        const uint32_t tb = b0, te = e0;
+        const uint32_t tb = b0, te = e0, tli = liCur;
         uint32_t mine = 0;
         #pragma unroll
         for (int i = 0; i < PIPE_CELLS_PER_THREAD; i++) mine += cnt[i];
@@ -427,7 +446,10 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += y; }
         mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);          // every consumer warp has released the slot's previous tile
         if (lane == 31) H.scan[pw] = inc;
+        if (pt == 0) ps.nextLi[(k + 1u) & 1u] = drawn;    // the entry drawn during the previous tile
         producer_sync();
+        li = ps.nextLi[(k + 1u) & 1u];
+        if (pt == 0 && li < nList) drawn = staticQueue ? li + gridDim.x : atomicAdd(&S->tileCursor, 1u);
         uint32_t run = inc - mine, total = 0;
         #pragma unroll
         for (int w = 0; w < PIPE_PRODUCER_WARPS; w++) { const uint32_t v = H.scan[w]; if ((uint32_t)w < pw) run += v; total += v; }
@@ -456,7 +478,7 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
         regB[0] = base; regE[0] = staged ? base + total : base;
         if (pt == 0) {
             H.local[HALO_CELLS] = total;
-            H.begin = tb; H.end = te; H.total = total; H.staged = staged ? 1u : 0u; H.base = base;
+            H.begin = tb; H.end = te; H.total = total; H.staged = staged ? 1u : 0u; H.base = base; H.li = tli;
             if (checkIndexRange && total > 65535u) atomicOr(&S->errorFlags, 2u);
             if (!staged) atomicAdd(&S->fallbackTiles, 1u);
         }
@@ -489,7 +511,6 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
             }
         }
         // look up the CTA's next tile and start loading its cell table
-        tile += tileStep;
         next_tile();
         const uint32_t b0_ = tb, e0_ = te;
         // What the consumers stream per particle of this tile — neighbour counts, the first PIPE_PREFETCH_GROUPS list (and
@@ -561,7 +582,7 @@ template<class Op> struct BatchHead {
 };
 struct BatchCursor {
     uint32_t k, b, rot;                    // tile counter of this CTA, batch inside the tile, rotation (see above)
-    uint32_t begin, end, nBatch;
+    uint32_t begin, end, nBatch, li;
     bool done;
 };
 
@@ -653,13 +674,13 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
     constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
     const uint32_t lane = threadIdx.x & 31u, cw = threadIdx.x >> 5;
     BatchCursor c;
-    c.k = 0; c.rot = 0; c.b = 0; c.begin = 0; c.end = 0; c.nBatch = 0; c.done = false;
+    c.k = 0; c.rot = 0; c.b = 0; c.begin = 0; c.end = 0; c.nBatch = 0; c.li = 0; c.done = false;
     // enter tile c.k: wait until the producers have filled its slot, read its range
     auto enter = [&]() {
         const uint32_t s = c.k % PIPE_STAGES;
         mbar_wait(&ps.full[s], (c.k / PIPE_STAGES) & 1u);
         const StageHeader& H = ps.hdr[s];
-        c.begin = H.begin; c.end = H.end;
+        c.begin = H.begin; c.end = H.end; c.li = H.li;
         if (c.begin == 0xffffffffu) { c.done = true; c.nBatch = 0; return; }
         c.nBatch = (c.end - c.begin + 31u) >> 5;
         c.b = (cw + PIPE_CONSUMER_WARPS - c.rot) % PIPE_CONSUMER_WARPS;
@@ -691,7 +712,7 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
             else                pipe_gather<Op, false>(h, acc, H, A, sA, sB, op);
         }
         // what the epilogue needs of the current batch
-        const uint32_t p = h.p, m = h.m;
+        const uint32_t p = h.p, m = h.m, curK = c.k, curB = c.b, curN = c.nBatch, curLi = c.li;
         float own[Op::NOWN];
         #pragma unroll
         for (int i = 0; i < Op::NOWN; i++) own[i] = h.own[i];
@@ -700,22 +721,67 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
         seek();
         if (!c.done) pipe_head_load(h, c, lane, A, op);
         if (p != 0xffffffffu) op.finish(p, m, own, acc);
+        if constexpr (Op::NRED > 0) {
+            __syncwarp();
+            RedRecord& R = ps.rec[curK % PIPE_RED_RECORDS];
+            #pragma unroll
+            for (int q = 0; q < Op::NRED; q++) {
+                double x = p != 0xffffffffu ? (double)op.red[q] : 0.0;
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+                if (lane == 0) {
+                    if (curB < PIPE_MAX_BATCH - 1) R.bsum[q][curB] = x;
+                    else atomicAdd(&R.bsum[q][PIPE_MAX_BATCH - 1], x);
+                }
+            }
+            uint32_t old = 0;
+            if (lane == 0) { __threadfence_block(); old = atomicAdd(&R.count, 1u); }
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old + 1u == curN) {                       // this warp completed the tile: fold its batches in order
+                __threadfence_block();
+                const uint32_t nb = min(curN, (uint32_t)PIPE_MAX_BATCH);
+                #pragma unroll
+                for (int q = 0; q < Op::NRED; q++) {
+                    const volatile double* bs = R.bsum[q];
+                    double x = (lane < nb ? bs[lane] : 0.0) + (lane + 32u < nb ? bs[lane + 32u] : 0.0);
+                    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+                    if (lane == 0) A.slotSums[(size_t)q * A.slotStride + curLi] = x;
+                }
+                __syncwarp();
+                if (lane == 0) { R.bsum[0][PIPE_MAX_BATCH - 1] = 0.0; R.bsum[1][PIPE_MAX_BATCH - 1] = 0.0; R.count = 0u; }
+            }
+        }
     }
 }
 
 // Called by all PIPE_THREADS threads of the CTA (after any lookup table has been loaded; contains __syncthreads).
+// Returns true in every thread of the CTA that finished last (it has reset the tile queue; kernels with a grid-wide
+// sum fold the batch slots there).
 template<class Op>
-__device__ __forceinline__ void pipe_pass(DevState* __restrict__ S, const Arrays& A, PipeShared& ps, unsigned char* pay, Op& op,
+__device__ __forceinline__ bool pipe_pass(DevState* __restrict__ S, const Arrays& A, PipeShared& ps, unsigned char* pay, Op& op,
                                           uint32_t tile0, uint32_t tile1, bool checkIndexRange = false) {
     if (threadIdx.x == 0) {
         #pragma unroll
         for (int s = 0; s < PIPE_STAGES; s++) { mbar_init(&ps.full[s], PIPE_PRODUCER_THREADS + 1); mbar_init(&ps.empty[s], PIPE_CONSUMER_WARPS); }
+    }
+    if (threadIdx.x < PIPE_RED_RECORDS) {
+        RedRecord& R = ps.rec[threadIdx.x];
+        R.count = 0u; R.bsum[0][PIPE_MAX_BATCH - 1] = 0.0; R.bsum[1][PIPE_MAX_BATCH - 1] = 0.0;
     }
     __syncthreads();
     if (threadIdx.x >= PIPE_CONSUMER_WARPS * 32) pipe_producer(S, A, ps, pay, op, tile0, tile1, checkIndexRange);
     else if constexpr (Op::CUSTOM) pipe_consumer(A, ps, pay, op);
     else pipe_consumer_pairs(A, ps, pay, op);
     __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                  // this CTA's slot and field stores before its ticket
+        const bool last = atomicAdd(&S->doneCtas, 1u) == gridDim.x - 1u;
+        if (last) { S->tileCursor = 0u; S->doneCtas = 0u; }
+        ps.lastCta = last ? 1u : 0u;
+    }
+    __syncthreads();
+    return ps.lastCta != 0u;
 }
 
 __device__ __forceinline__ PipeShared& pipe_header(unsigned char* raw) { return *reinterpret_cast<PipeShared*>(raw); }

@@ -61,10 +61,10 @@ __device__ __forceinline__ bool boundary_samples(const Params& P, float3 xi, flo
 // ---- V1 + V2 fused: preconditioner blocks, per-pair coefficients, warm start, |b|^2 ----------
 struct ViscSetupOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 9, COEF = 3;   // payload (x, y, z, rho); reads the pair's kernel-gradient
+    static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 9, COEF = 3, NRED = 1; // payload (x, y, z, rho); reads the pair's kernel-gradient
     const Params& P; const Arrays& A; Lut K;                                   // factor g_ij (pressure.cu), writes the pair coefficients
     float dt, eps2;
-    float bb;
+    float red[1];                                          // |b_i|^2 of the lane's particle
     __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
     __device__ __forceinline__ const void* srcB() const { return nullptr; }
     __device__ __forceinline__ const float* coef_in() const { return A.gcoef; }
@@ -143,7 +143,7 @@ struct ViscSetupOp {
         // V2: b = v (the boundary term multiplies a zero vector: DFSPHKernels.cu:744-754), g = v + dv_prev
         const float4 v = A.vel[p], dv = A.dv[p];
         A.cgG[p] = make_float4(v.x + dv.x, v.y + dv.y, v.z + dv.z, 0.0f);
-        bb += (v.x * v.x + v.y * v.y) + v.z * v.z;
+        red[0] = (v.x * v.x + v.y * v.y) + v.z * v.z;
     }
 };
 
@@ -151,16 +151,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_visc_setup(const __grid_con
     PipeShared& ps = pipe_header(smemRaw);
     float* sG = pipe_lut<1>(smemRaw);                     // the boundary-friction samples still need the table
     load_lut_tile(sG, lutG);
-    ViscSetupOp op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, 0.01f * P.h2, 0.0f };
-    pipe_pass(S, A, ps, pipe_pay<1>(smemRaw), op, P.tile0, P.tile1);
-    double v[1] = { (double)op.bb };
-    if (block_reduce_publish<1>(v, A.partials, &S->ticket[4], ps.red)) {
+    ViscSetupOp op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, 0.01f * P.h2, { 0.0f } };
+    if (pipe_pass(S, A, ps, pipe_pay<1>(smemRaw), op, P.tile0, P.tile1)) {
         double tot[1];
-        last_block_fold<1>(tot, A.partials, ps.red);
-        if (threadIdx.x == 0) {
-            finish_reduction<1>(SITE_VISC_BB, P, S, tot);
-            S->ticket[4] = 0;
-        }
+        fold_slots<1>(tot, A.slotSums, __ldg(A.tileList), A.slotStride, ps.red);
+        if (threadIdx.x == 0) finish_reduction<1>(SITE_VISC_BB, P, S, tot);
     }
 }
 
@@ -176,11 +171,11 @@ __device__ __forceinline__ float3 mat_vec(const float* __restrict__ minv, uint32
 template<bool INIT>
 struct ViscMatvecOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 2, NOWN = 6, NSUM = 3, COEF = 1;       // payload: (x, y, z, rho), the vector's (x, y, z); reads the pair coefficients
+    static constexpr int NPAY = 2, NOWN = 6, NSUM = 3, COEF = 1, NRED = INIT ? 2 : 1;     // payload: (x, y, z, rho), the vector's (x, y, z); reads the pair coefficients
     const Params& P; const Arrays& A;
     const float4* __restrict__ x;    // the vector the operator is applied to: g (INIT) or the search direction p
     float dt;
-    float s0, s1;
+    float red[2];                    // INIT: |r_i|^2, r_i.z_i; else p_i.q_i
     static constexpr int BBYTES = 16;
     __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
     __device__ __forceinline__ const void* srcB() const { return x; }
@@ -229,11 +224,11 @@ struct ViscMatvecOp {
             const float3 z = mat_vec(A.minv, P.n, p, r);
             A.cgR[p] = make_float4(r.x, r.y, r.z, 0.0f);
             A.cgP[p] = make_float4(z.x, z.y, z.z, 0.0f);
-            s0 += (r.x * r.x + r.y * r.y) + r.z * r.z;
-            s1 += (r.x * z.x + r.y * z.y) + r.z * z.z;
+            red[0] = (r.x * r.x + r.y * r.y) + r.z * r.z;
+            red[1] = (r.x * z.x + r.y * z.y) + r.z * z.z;
         } else {
             A.cgQ[p] = make_float4(q.x, q.y, q.z, 0.0f);
-            s0 += (vi.x * q.x + vi.y * q.y) + vi.z * q.z;
+            red[0] = (vi.x * q.x + vi.y * q.y) + vi.z * q.z;
         }
     }
 };
@@ -242,17 +237,16 @@ template<bool INIT>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) k_visc_matvec_pipe(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (!INIT && S->viscActive != 1u) return;
     PipeShared& ps = pipe_header(smemRaw);
-    ViscMatvecOp<INIT> op{ P, A, INIT ? A.cgG : A.cgP, S->dt, 0.0f, 0.0f };
-    pipe_pass(S, A, ps, pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
-    double v[2] = { (double)op.s0, (double)op.s1 };
-    uint32_t* ticket = &S->ticket[5];
-    if (block_reduce_publish<2>(v, A.partials, ticket, ps.red)) {
-        double tot[2];
-        last_block_fold<2>(tot, A.partials, ps.red);
-        if (threadIdx.x == 0) {
-            if (INIT) finish_reduction<2>(SITE_VISC_INIT, P, S, tot);
-            else { const double t1[1] = { tot[0] }; finish_reduction<1>(SITE_VISC_PQ, P, S, t1); }
-            *ticket = 0;
+    ViscMatvecOp<INIT> op{ P, A, INIT ? A.cgG : A.cgP, S->dt, { 0.0f, 0.0f } };
+    if (pipe_pass(S, A, ps, pipe_pay<0>(smemRaw), op, P.tile0, P.tile1)) {
+        double tot[2] = { 0.0, 0.0 };
+        if (INIT) {
+            fold_slots<2>(tot, A.slotSums, __ldg(A.tileList), A.slotStride, ps.red);
+            if (threadIdx.x == 0) finish_reduction<2>(SITE_VISC_INIT, P, S, tot);
+        } else {
+            double t1[1];
+            fold_slots<1>(t1, A.slotSums, __ldg(A.tileList), A.slotStride, ps.red);
+            if (threadIdx.x == 0) finish_reduction<1>(SITE_VISC_PQ, P, S, t1);
         }
     }
 }
