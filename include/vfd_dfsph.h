@@ -207,6 +207,9 @@ int vfd_dfsph_get_launch_count(VfdDfsph* h, uint64_t* launches, int reset);
  * stats[0] tiles (4x4x4 cells) of the grid, [1] cells, [2] tile passes since the last begin() whose 6x6x6-cell
  * neighbourhood did not fit the shared-memory stage and took the slow global-memory path, [3] frame bytes copied D2H */
 int vfd_dfsph_get_tile_stats(VfdDfsph* h, uint64_t stats[4]);
+/* tuning aid (no reference equivalent): milliseconds of `reps` back-to-back launches of the initial PCG mat-vec on the
+ * state of the last step; the PCG work arrays it overwrites are rebuilt by the next step */
+int vfd_dfsph_time_matvec(VfdDfsph* h, uint32_t reps, float* ms);
 
 /* ---- several GPUs: one process (rank) per GPU, the domain cut into slabs of tile columns along x ----------------
  * No reference equivalent (the reference drives device 0 only: VFD/Source/Debug/SystemInfo.cpp:34-35).

@@ -153,6 +153,7 @@ SYMBOLS = [
     ("vfd_dfsph_set_option", _i, [_vp, _i, C.c_int64]),
     ("vfd_dfsph_get_launch_count", _i, [_vp, C.POINTER(_u64), _i]),
     ("vfd_dfsph_get_tile_stats", _i, [_vp, _vp]),
+    ("vfd_dfsph_time_matvec", _i, [_vp, C.c_uint32, C.POINTER(C.c_float)]),
     ("vfd_dist_unique_id", _i, [_vp]),
     ("vfd_dfsph_init_distributed", _i, [_vp, _i, _i, _vp, _vp, _vp]),
     ("vfd_dfsph_get_grid", _i, [_vp, _vp, C.POINTER(_f32), _vp]),
@@ -444,6 +445,12 @@ class DFSPHSimulation:
         st = np.zeros(4, np.uint64)
         self._ck(self.L.vfd_dfsph_get_tile_stats(self.h, _p(st)))
         return dict(tiles=int(st[0]), cells=int(st[1]), fallback_tile_passes=int(st[2]), frame_bytes=int(st[3]))
+
+    def time_matvec(self, reps=20):
+        """ms per launch of the initial PCG mat-vec on the current state (tuning aid)"""
+        ms = C.c_float()
+        self._ck(self.L.vfd_dfsph_time_matvec(self.h, int(reps), C.byref(ms)))
+        return ms.value / reps
 
     def kernel_times(self, reset=False):
         """{kernel class: (ms of launches that did work, number of such launches, ms of all launches, all launches)}"""

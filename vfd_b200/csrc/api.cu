@@ -157,6 +157,11 @@ int vfd_dfsph_get_tile_stats(VfdDfsph* h, uint64_t stats[4]) {
     return h->s.tile_stats(stats);
 }
 
+int vfd_dfsph_time_matvec(VfdDfsph* h, uint32_t reps, float* ms) {
+    GUARD(h); if (!ms) return h->s.fail(VFD_E_INVALID, "null output");
+    return h->s.time_matvec(reps, ms);
+}
+
 int vfd_dist_unique_id(char out[128]) {
     if (!out) return VFD_E_INVALID;
     std::string err;

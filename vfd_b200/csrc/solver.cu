@@ -886,6 +886,26 @@ int Solver::tile_stats(uint64_t* st) {
     return VFD_OK;
 }
 
+// Tuning aid: `reps` back-to-back launches of the initial PCG mat-vec (r = b - A g: the pipelined pair pass with the
+// heaviest payload) on the state the last step left behind, timed with events on the solver's stream.  The PCG work
+// arrays it overwrites are rebuilt by the next step.
+int Solver::time_matvec(uint32_t reps, float* ms) {
+    CK(cudaSetDevice(device));
+    if (!began || !searched || info.ParticleCount == 0) return fail(VFD_E_INVALID, "time_matvec: step the simulation first");
+    LaunchCfg L{ stream, numSMs, &launches, &prof };
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    launch_viscosity_matvec(L, params, arrays, dState, true);
+    CK(cudaEventRecord(a, stream));
+    for (uint32_t i = 0; i < reps; i++) launch_viscosity_matvec(L, params, arrays, dState, true);
+    CK(cudaEventRecord(b, stream));
+    CK(cudaEventSynchronize(b));
+    CK(cudaEventElapsedTime(ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    CK(cudaGetLastError());
+    return VFD_OK;
+}
+
 int Solver::get_bounds(float* bmin, float* bmax) {
     DevState s;
     CK(cudaSetDevice(device));

@@ -65,6 +65,7 @@ public:
     int get_boundary(uint32_t body, float* xj, float* vol);
     int get_bounds(float* bmin, float* bmax);
     int tile_stats(uint64_t* stats4);
+    int time_matvec(uint32_t reps, float* ms);
     // slab decomposition over several ranks (distributed.cu)
     int dist_init(int rank, int nranks, const char* id128, const float* dmin, const float* dmax);
     int dist_get_grid(float* origin3, float* cellSize, uint32_t* tiles3);

@@ -31,15 +31,18 @@ __device__ __forceinline__ float3 normalize_if_nonzero(float3 v) {   // DFSPHKer
 // summed in sample order, as the reference's sequential loop does, so the result is bit-identical to it.
 struct StClassifyOp {
     static constexpr bool CUSTOM = true;
-    static constexpr int NPAY = 1;
+    static constexpr int NPAY = 1, BBYTES = 0, COEF = 0, NRED = 0;
     const Params& P; const Arrays& A;
     const float* __restrict__ halton;
     uint32_t sampleCount;
     float mcFactor, cover2;
+    __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
+    __device__ __forceinline__ const void* srcB() const { return nullptr; }
+    __device__ __forceinline__ void prefetch_own(uint32_t, uint32_t, uint32_t) const {}
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
     template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, bool valid, const Acc& acc) {
+    __device__ __forceinline__ void particle(uint32_t p, bool valid, const Acc& acc, const StageHeader&) {
         const int lane = threadIdx.x & 31;
         uint32_t m = 0u;
         float3 xi = f3(0.0f, 0.0f, 0.0f);
@@ -121,17 +124,25 @@ struct StClassifyOp {
     }
 };
 
-__global__ void __launch_bounds__(TT_PLAIN) k_st_classify(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ halton) {
+// On the asynchronous tile pipeline: the few warps of a tile that hold surface particles (and run the sample tests) no
+// longer keep the rest of the CTA waiting at a tile barrier (57 % of the warp-stall samples of the barrier version,
+// profiles/r01_ncu_full_step_before_pipeline.txt) — the other warps move on to the next tiles.
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_st_classify(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ halton) {
     const float radiusRatio = P.nbrRadius / P.r;
     StClassifyOp op{ P, A, halton, S->sampleCount, S->mcFactor, radiusRatio * radiusRatio * P.h2 };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<0>(smemRaw), nullptr, STAGE_CAP, op, P.tile0, P.tile1);
+    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
 }
 
 // T2: neighbour-weighted smoothing of normal and curvature among surface particles
 struct StSmoothOp {
     static constexpr bool CUSTOM = false;
-    static constexpr int NPAY = 2, NOWN = 4, NSUM = 5, COEF = 0;       // payload: position, (normal, curvature)
+    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 4, NSUM = 5, COEF = 0, NRED = 0;       // payload: position, (normal, curvature)
     const Params& P; const Arrays& A;
+    __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
+    __device__ __forceinline__ const void* srcB() const { return A.nrm; }
+    __device__ __forceinline__ const float* coef_in() const { return nullptr; }
+    __device__ __forceinline__ float* coef_out() const { return nullptr; }
+    __device__ __forceinline__ void prefetch_own(uint32_t, uint32_t, uint32_t) const {}
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t g) const { return A.nrm[g]; }
     __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
@@ -161,9 +172,9 @@ struct StSmoothOp {
     }
 };
 
-__global__ void __launch_bounds__(TT_PLAIN) k_st_smooth(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_st_smooth(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     StSmoothOp op{ P, A };
-    tile_pass(S, A, smem_header(smemRaw), smem_pay_a<0>(smemRaw), smem_pay_b<0>(smemRaw, STAGE_CAP), STAGE_CAP, op, P.tile0, P.tile1);
+    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
 }
 
 // T3: apply the force (once per smoothing pass: SURVEY.md Q18)
@@ -186,27 +197,19 @@ __global__ void __launch_bounds__(VFD_TPB) k_st_apply(Params P, Arrays A) {
     }
 }
 
-static void st_config(int& per1, int& per2, size_t& s1, size_t& s2) {
-    s1 = tile_smem_bytes<0, 1>(STAGE_CAP); s2 = tile_smem_bytes<0, 2>(STAGE_CAP);
-    static thread_local int p1 = 0, p2 = 0;
-    if (!p1) {
-        cudaFuncSetAttribute(k_st_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
-        cudaFuncSetAttribute(k_st_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, k_st_classify, TT_PLAIN, s1);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, k_st_smooth, TT_PLAIN, s2);
-        p1 = std::max(p1, 1); p2 = std::max(p2, 1);
-    }
-    per1 = p1; per2 = p2;
-}
 void launch_st_classify(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* halton) {
-    int per1, per2; size_t s1, s2; st_config(per1, per2, s1, s2);
+    const size_t sp = pipe_smem_bytes<0, 16, 0>();
+    static thread_local bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_st_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp); attr = true; }
     LaunchScope ls(L, KID_ST_CLASSIFY);
-    k_st_classify<<<per1 * L.numSMs, TT_PLAIN, s1, L.stream>>>(P, A, S, halton);
+    k_st_classify<<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S, halton);
 }
 void launch_st_smooth(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
-    int per1, per2; size_t s1, s2; st_config(per1, per2, s1, s2);
+    const size_t sp = pipe_smem_bytes<0, 16, 16>();
+    static thread_local bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_st_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp); attr = true; }
     LaunchScope ls(L, KID_ST_SMOOTH);
-    k_st_smooth<<<per2 * L.numSMs, TT_PLAIN, s2, L.stream>>>(P, A, S);
+    k_st_smooth<<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S);
 }
 void launch_st_apply(const LaunchCfg& L, const Params& P, const Arrays& A) {
     LaunchScope ls(L, KID_ST_APPLY);

@@ -283,6 +283,11 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 // Pair ops (CUSTOM == false): NOWN, NSUM, COEF (bit 0: a per-pair coefficient stream is read, bit 1: one is written;
 //   both in the list's ELL layout), const float* coef_in(), float* coef_out(), load_own, pair(own, a, b, coef&, acc),
 //   finish(p, m, own, sum) — as for tile_pass.  Custom ops: particle(p, valid, acc, H), called by all 32 lanes.
+// PIPE_ABLATE (tuning builds only, results are wrong): bit 0: the list/coefficient stream re-reads its first group (no
+// HBM streaming), bit 1: no shared-memory gather, bit 2: the producers copy nothing, bit 3: no epilogue
+#ifndef PIPE_ABLATE
+#define PIPE_ABLATE 0
+#endif
 #define PIPE_STAGES 4          // tiles in flight per CTA (header slots); their payloads share one ring of PIPE_RING particle slots
 #ifndef PIPE_CONSUMER_WARPS
 #define PIPE_CONSUMER_WARPS 16
@@ -293,6 +298,9 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 #define PIPE_THREADS ((PIPE_CONSUMER_WARPS + PIPE_PRODUCER_WARPS) * 32)     // 576
 #define PIPE_CAP 2816          // largest halo box that is staged (larger ones take the exact global-memory path)
 #define PIPE_RING (2 * PIPE_CAP) // payload ring, in particles: two worst-case boxes, three to four typical ones (~1700)
+#ifndef PIPE_GATHER_WIDTH
+#define PIPE_GATHER_WIDTH 4    // payload gathers in flight per lane (1, 2 or 4)
+#endif
 #ifndef PIPE_LOOKAHEAD
 #define PIPE_LOOKAHEAD 3
 #endif                         // neighbour groups (of four) in flight per lane
@@ -502,7 +510,7 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
                 const uint32_t lA = __shfl_sync(0xffffffffu, rl[0], j), lB = __shfl_sync(0xffffffffu, rl[1], j);
                 const uint32_t lC = __shfl_sync(0xffffffffu, rl[2], j), lE = __shfl_sync(0xffffffffu, rl[3], j);
                 const uint32_t g0 = __shfl_sync(0xffffffffu, rg[0], j), g1 = __shfl_sync(0xffffffffu, rg[1], j), g5 = __shfl_sync(0xffffffffu, rg[2], j);
-                for (uint32_t l = lA + lane; l < lE; l += 32u) {
+                if (!(PIPE_ABLATE & 4)) for (uint32_t l = lA + lane; l < lE; l += 32u) {
                     const uint32_t g = l < lB ? g0 + (l - lA) : (l < lC ? g1 + (l - lB) : g5 + (l - lC));
                     cp_async16(sA + (size_t)l * 16, gA + (size_t)g * 16);
                     if (BBYTES == 16) cp_async16(sB + (size_t)l * 16, gB + (size_t)g * 16);
@@ -553,7 +561,6 @@ __device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, c
         const bool staged = H.staged != 0u;
         const uint32_t base = H.base;
         const float4* sA = reinterpret_cast<const float4*>(pay + (size_t)base * 16);
-        const void* sB = pay + (size_t)PIPE_RING * 16 + (size_t)base * BBYTES;
         const uint32_t nBatch = (end - begin + 31u) >> 5;
         // batch b of this tile goes to warp (rot + b) mod W: consecutive batches of consecutive tiles visit the warps in turn
         for (uint32_t b = (cw + PIPE_CONSUMER_WARPS - rot) % PIPE_CONSUMER_WARPS; b < nBatch; b += PIPE_CONSUMER_WARPS) {
@@ -632,14 +639,20 @@ __device__ __forceinline__ void pipe_gather(BatchHead<Op>& h, float (&acc)[Op::N
         ell_unpack(wq, L);
         float c[4] = { cq.x, cq.y, cq.z, cq.w };
         if (g * 4u + 4u <= m) {
-            float4 pa[4], pb[4];
+            // PIPE_GATHER_WIDTH payloads are gathered back to back before their pair terms are accumulated (in list order)
             #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (STAGED) { pa[u] = sA[L[u]]; pb[u] = gatherB(L[u]); }
-                else { const uint32_t gi = hdr_local_to_global(H, L[u]); pa[u] = op.loadA(gi); pb[u] = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+            for (int u0 = 0; u0 < 4; u0 += PIPE_GATHER_WIDTH) {
+                float4 pa[PIPE_GATHER_WIDTH], pb[PIPE_GATHER_WIDTH];
+                #pragma unroll
+                for (int u = 0; u < PIPE_GATHER_WIDTH; u++) {
+                    const uint32_t Lu = L[u0 + u];
+                    if (PIPE_ABLATE & 2) { pa[u] = make_float4(h.own[0] + (float)Lu, h.own[1], h.own[2], 1.0f); pb[u] = pa[u]; }
+                    else if (STAGED) { pa[u] = sA[Lu]; pb[u] = gatherB(Lu); }
+                    else { const uint32_t gi = hdr_local_to_global(H, Lu); pa[u] = op.loadA(gi); pb[u] = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+                }
+                #pragma unroll
+                for (int u = 0; u < PIPE_GATHER_WIDTH; u++) op.pair(h.own, pa[u], pb[u], c[u0 + u], acc);
             }
-            #pragma unroll
-            for (int u = 0; u < 4; u++) op.pair(h.own, pa[u], pb[u], c[u], acc);
         } else {
             #pragma unroll
             for (int u = 0; u < 3; u++) {                    // a partial group holds one to three neighbours
@@ -659,7 +672,7 @@ __device__ __forceinline__ void pipe_gather(BatchHead<Op>& h, float (&acc)[Op::N
         #pragma unroll
         for (int i = 0; i < D; i++) {
             group(h.wr[i], h.cr[i], g0 + (uint32_t)i);
-            const uint32_t gn = min(g0 + (uint32_t)i + D, gLast);
+            const uint32_t gn = (PIPE_ABLATE & 1) ? 0u : min(g0 + (uint32_t)i + D, gLast);
             h.wr[i] = __ldg(col + (size_t)gn * 32);
             if (Op::COEF & 1) h.cr[i] = __ldg(cin + (size_t)gn * 32);
         }
@@ -720,7 +733,7 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
         c.b += PIPE_CONSUMER_WARPS;
         seek();
         if (!c.done) pipe_head_load(h, c, lane, A, op);
-        if (p != 0xffffffffu) op.finish(p, m, own, acc);
+        if (p != 0xffffffffu && !((PIPE_ABLATE & 8) && acc[0] != 12345.0f)) op.finish(p, m, own, acc);
         if constexpr (Op::NRED > 0) {
             __syncwarp();
             RedRecord& R = ps.rec[curK % PIPE_RED_RECORDS];
