@@ -45,6 +45,7 @@ extern __shared__ __align__(128) unsigned char smemRaw[];
 // ---- K2 + K3 + K8 fused: density, DFSPH factor, a = g; writes the pair factors g_ij and the boundary gradients ----
 struct DensityFactorOp {
     static constexpr bool CUSTOM = false;
+    using Cfg = PipeCfgMany;
     static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 5, COEF = 2, NRED = 0;
     const Params& P; const Arrays& A; Lut K;
     __device__ __forceinline__ const float4* srcA() const { return A.pos; }
@@ -92,7 +93,7 @@ struct DensityFactorOp {
     }
 };
 
-__global__ void __launch_bounds__(PIPE_THREADS, 1) k_density_factor(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S,
+__global__ void __launch_bounds__(DensityFactorOp::Cfg::THREADS, 1) k_density_factor(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S,
                                                                     const float* __restrict__ lutW, const float* __restrict__ lutG) {
     float* sW = pipe_lut<2>(smemRaw);
     float* sG = sW + VFD_LUT_RES;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_density_factor(const __grid
 template<bool DIV>
 struct SourceOp {
     static constexpr bool CUSTOM = false;
+    using Cfg = PipeCfgWide;
     static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1, NRED = 0;
     const Params& P; const Arrays& A;
     float dt, dtInv, dt2Inv;
@@ -148,7 +150,7 @@ struct SourceOp {
 };
 
 template<bool DIV>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) k_source(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+__global__ void __launch_bounds__(SourceOp<DIV>::Cfg::THREADS, 1) k_source(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // loop entry of ComputeDivergence / ComputePressure (DFSPHImplementation.cu:526-532, 455-461): error 0, so the
         // loop is entered only through the minimum iteration count
@@ -165,6 +167,7 @@ enum { ACC_DIV_ITER = 0, ACC_DIV_FINISH = 1, ACC_PRESS_ITER = 2, ACC_PRESS_FINIS
 template<int MODE>
 struct AccelOp {
     static constexpr bool CUSTOM = false;
+    using Cfg = PipeCfgMany;
     static constexpr int NPAY = 2, BBYTES = 4, NOWN = 4, NSUM = 3, COEF = 1, NRED = 0;     // payload: (x, y, z, rho) and kappa
     const Params& P; const Arrays& A;
     const float* __restrict__ kap;
@@ -208,7 +211,7 @@ struct AccelOp {
 };
 
 template<int MODE>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) k_pressure_accel(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+__global__ void __launch_bounds__(AccelOp<MODE>::Cfg::THREADS, 1) k_pressure_accel(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (MODE == ACC_DIV_ITER && !S->divActive) return;
     if (MODE == ACC_PRESS_ITER && !S->pressActive) return;
     AccelOp<MODE> op{ P, A, (MODE == ACC_DIV_ITER || MODE == ACC_DIV_FINISH) ? A.kappaV : A.kappa, S->dt };
@@ -219,6 +222,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_pressure_accel(const __grid
 template<bool DIV>
 struct SolveOp {
     static constexpr bool CUSTOM = false;
+    using Cfg = PipeCfgWide;
     static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1, NRED = 1;   // payload: position, pressure acceleration
     const Params& P; const Arrays& A;
     float scale;
@@ -258,7 +262,7 @@ struct SolveOp {
 };
 
 template<bool DIV>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_iteration(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+__global__ void __launch_bounds__(SolveOp<DIV>::Cfg::THREADS, 1) k_solve_iteration(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (DIV ? !S->divActive : !S->pressActive) return;
     PipeShared& ps = pipe_header(smemRaw);
     SolveOp<DIV> op{ P, A, DIV ? S->dt : S->dt2, { 0.0f } };
@@ -324,35 +328,35 @@ static void pipe_attr(Kern kern, size_t smem) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (nd < 32) done[nd++] = (const void*)kern;
 }
-#define PIPE_LAUNCH(kid, kern, smem, ...) do { const size_t sm_ = (smem); pipe_attr(kern, sm_); LaunchScope ls(L, kid); \
-    kern<<<L.numSMs, PIPE_THREADS, sm_, L.stream>>>(__VA_ARGS__); } while (0)
+#define PIPE_LAUNCH(kid, kern, OpT, smem, ...) do { const size_t sm_ = (smem); pipe_attr(kern, sm_); LaunchScope ls(L, kid); \
+    kern<<<L.numSMs, OpT::Cfg::THREADS, sm_, L.stream>>>(__VA_ARGS__); } while (0)
 
 void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutW, const float* lutG) {
-    PIPE_LAUNCH(KID_DENSITY_FACTOR, k_density_factor, (pipe_smem_bytes<2, 16, 0>()), P, A, S, lutW, lutG);
+    PIPE_LAUNCH(KID_DENSITY_FACTOR, k_density_factor, DensityFactorOp, (pipe_smem_bytes<2, 16, 0>()), P, A, S, lutW, lutG);
 }
 void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_DIV_SOURCE, k_source<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
+    PIPE_LAUNCH(KID_DIV_SOURCE, k_source<true>, SourceOp<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
 }
 void launch_divergence_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_DIV_ACCEL, k_pressure_accel<ACC_DIV_ITER>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
+    PIPE_LAUNCH(KID_DIV_ACCEL, k_pressure_accel<ACC_DIV_ITER>, AccelOp<0>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
 }
 void launch_divergence_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_DIV_SOLVE, k_solve_iteration<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
+    PIPE_LAUNCH(KID_DIV_SOLVE, k_solve_iteration<true>, SolveOp<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
 }
 void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_DIV_FINISH, k_pressure_accel<ACC_DIV_FINISH>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
+    PIPE_LAUNCH(KID_DIV_FINISH, k_pressure_accel<ACC_DIV_FINISH>, AccelOp<0>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
 }
 void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_PRESS_SOURCE, k_source<false>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
+    PIPE_LAUNCH(KID_PRESS_SOURCE, k_source<false>, SourceOp<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
 }
 void launch_pressure_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_PRESS_ACCEL, k_pressure_accel<ACC_PRESS_ITER>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
+    PIPE_LAUNCH(KID_PRESS_ACCEL, k_pressure_accel<ACC_PRESS_ITER>, AccelOp<0>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
 }
 void launch_pressure_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_PRESS_SOLVE, k_solve_iteration<false>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
+    PIPE_LAUNCH(KID_PRESS_SOLVE, k_solve_iteration<false>, SolveOp<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
 }
 void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_PRESS_FINISH, k_pressure_accel<ACC_PRESS_FINISH>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
+    PIPE_LAUNCH(KID_PRESS_FINISH, k_pressure_accel<ACC_PRESS_FINISH>, AccelOp<0>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
 }
 void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A) {
     LaunchScope ls(L, KID_CLEAR_ACC);

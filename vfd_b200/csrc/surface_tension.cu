@@ -31,6 +31,7 @@ __device__ __forceinline__ float3 normalize_if_nonzero(float3 v) {   // DFSPHKer
 // summed in sample order, as the reference's sequential loop does, so the result is bit-identical to it.
 struct StClassifyOp {
     static constexpr bool CUSTOM = true;
+    using Cfg = PipeCfg<24, 2, 2>;
     static constexpr int NPAY = 1, BBYTES = 0, COEF = 0, NRED = 0;
     const Params& P; const Arrays& A;
     const float* __restrict__ halton;
@@ -127,7 +128,7 @@ struct StClassifyOp {
 // On the asynchronous tile pipeline: the few warps of a tile that hold surface particles (and run the sample tests) no
 // longer keep the rest of the CTA waiting at a tile barrier (57 % of the warp-stall samples of the barrier version,
 // profiles/r01_ncu_full_step_before_pipeline.txt) — the other warps move on to the next tiles.
-__global__ void __launch_bounds__(PIPE_THREADS, 1) k_st_classify(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ halton) {
+__global__ void __launch_bounds__(StClassifyOp::Cfg::THREADS, 1) k_st_classify(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ halton) {
     const float radiusRatio = P.nbrRadius / P.r;
     StClassifyOp op{ P, A, halton, S->sampleCount, S->mcFactor, radiusRatio * radiusRatio * P.h2 };
     pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_st_classify(const __grid_co
 // T2: neighbour-weighted smoothing of normal and curvature among surface particles
 struct StSmoothOp {
     static constexpr bool CUSTOM = false;
+    using Cfg = PipeCfgMany;
     static constexpr int NPAY = 2, BBYTES = 16, NOWN = 4, NSUM = 5, COEF = 0, NRED = 0;       // payload: position, (normal, curvature)
     const Params& P; const Arrays& A;
     __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
@@ -172,7 +174,7 @@ struct StSmoothOp {
     }
 };
 
-__global__ void __launch_bounds__(PIPE_THREADS, 1) k_st_smooth(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+__global__ void __launch_bounds__(StSmoothOp::Cfg::THREADS, 1) k_st_smooth(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     StSmoothOp op{ P, A };
     pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
 }
@@ -202,14 +204,14 @@ void launch_st_classify(const LaunchCfg& L, const Params& P, const Arrays& A, De
     static thread_local bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_st_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp); attr = true; }
     LaunchScope ls(L, KID_ST_CLASSIFY);
-    k_st_classify<<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S, halton);
+    k_st_classify<<<L.numSMs, StClassifyOp::Cfg::THREADS, sp, L.stream>>>(P, A, S, halton);
 }
 void launch_st_smooth(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     const size_t sp = pipe_smem_bytes<0, 16, 16>();
     static thread_local bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_st_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp); attr = true; }
     LaunchScope ls(L, KID_ST_SMOOTH);
-    k_st_smooth<<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S);
+    k_st_smooth<<<L.numSMs, StSmoothOp::Cfg::THREADS, sp, L.stream>>>(P, A, S);
 }
 void launch_st_apply(const LaunchCfg& L, const Params& P, const Arrays& A) {
     LaunchScope ls(L, KID_ST_APPLY);

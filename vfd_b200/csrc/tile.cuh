@@ -295,7 +295,6 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 #define PIPE_PRODUCER_WARPS 4
 #define PIPE_PRODUCER_THREADS (PIPE_PRODUCER_WARPS * 32)
 #define PIPE_CELLS_PER_THREAD ((HALO_CELLS + PIPE_PRODUCER_THREADS - 1) / PIPE_PRODUCER_THREADS)
-#define PIPE_THREADS ((PIPE_CONSUMER_WARPS + PIPE_PRODUCER_WARPS) * 32)     // 576
 #define PIPE_CAP 2816          // largest halo box that is staged (larger ones take the exact global-memory path)
 #define PIPE_RING (2 * PIPE_CAP) // payload ring, in particles: two worst-case boxes, three to four typical ones (~1700)
 #ifndef PIPE_GATHER_WIDTH
@@ -304,6 +303,16 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 #ifndef PIPE_LOOKAHEAD
 #define PIPE_LOOKAHEAD 3
 #endif                         // neighbour groups (of four) in flight per lane
+
+// Shape of a pass, chosen per kernel (every Op names one as Op::Cfg): consumer warps per CTA, neighbour groups in flight
+// per lane (register ring), payload gathers in flight per lane.  Passes that are heavy on arithmetic or gather one
+// payload array want many warps with a narrow register footprint (28 warps at 64 registers); the passes that stream two
+// 16-byte payloads and a coefficient word per pair are better off with 16 warps at 96 registers and a deeper ring.
+template<int CW_, int D_, int GW_> struct PipeCfg {
+    static constexpr int CW = CW_, D = D_, GW = GW_, THREADS = (CW_ + PIPE_PRODUCER_WARPS) * 32;
+};
+using PipeCfgWide = PipeCfg<PIPE_CONSUMER_WARPS, PIPE_LOOKAHEAD, PIPE_GATHER_WIDTH>;   // 16 warps, 3 groups ahead, 4 gathers
+using PipeCfgMany = PipeCfg<28, 2, 2>;
 
 __device__ __forceinline__ uint2 ldg_stream(const uint2* p) { return __ldg(p); }
 __device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldg(p); }
@@ -384,7 +393,7 @@ template<class Op>
 __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Arrays& A, PipeShared& ps, unsigned char* pay, const Op& op,
                                               uint32_t tile0, uint32_t tile1, bool checkIndexRange) {
     constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
-    const uint32_t pt = threadIdx.x - PIPE_CONSUMER_WARPS * 32, lane = pt & 31u, pw = pt >> 5;
+    const uint32_t pt = threadIdx.x - Op::Cfg::CW * 32, lane = pt & 31u, pw = pt >> 5;
     // ring bookkeeping (identical in every producer thread): region of the tiles k-1, k-2, k-3 and the next free slot
     uint32_t regB[PIPE_STAGES - 1], regE[PIPE_STAGES - 1];
     #pragma unroll
@@ -563,12 +572,12 @@ __device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, c
         const float4* sA = reinterpret_cast<const float4*>(pay + (size_t)base * 16);
         const uint32_t nBatch = (end - begin + 31u) >> 5;
         // batch b of this tile goes to warp (rot + b) mod W: consecutive batches of consecutive tiles visit the warps in turn
-        for (uint32_t b = (cw + PIPE_CONSUMER_WARPS - rot) % PIPE_CONSUMER_WARPS; b < nBatch; b += PIPE_CONSUMER_WARPS) {
+        for (uint32_t b = (cw + Op::Cfg::CW - rot) % Op::Cfg::CW; b < nBatch; b += Op::Cfg::CW) {
             const uint32_t p = begin + (b << 5) + lane;
             const PipeAcc<Op> acc{ H, sA, op, staged };
             op.particle(p, p < end, acc, H);
         }
-        rot = (rot + nBatch) % PIPE_CONSUMER_WARPS;
+        rot = (rot + nBatch) % Op::Cfg::CW;
         __syncwarp();
         if (lane == 0) mbar_arrive(&ps.empty[s]);
     }
@@ -585,7 +594,7 @@ __device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, c
 template<class Op> struct BatchHead {
     uint32_t p, m;
     float own[Op::NOWN];
-    uint2 wr[PIPE_LOOKAHEAD]; float4 cr[PIPE_LOOKAHEAD];
+    uint2 wr[Op::Cfg::D]; float4 cr[Op::Cfg::D];
 };
 struct BatchCursor {
     uint32_t k, b, rot;                    // tile counter of this CTA, batch inside the tile, rotation (see above)
@@ -595,7 +604,7 @@ struct BatchCursor {
 
 template<class Op>
 __device__ __forceinline__ void pipe_head_load(BatchHead<Op>& h, const BatchCursor& c, uint32_t lane, const Arrays& A, const Op& op) {
-    constexpr int D = PIPE_LOOKAHEAD;
+    constexpr int D = Op::Cfg::D;
     h.p = c.begin + (c.b << 5) + lane;
     h.m = 0u;
     #pragma unroll
@@ -619,7 +628,7 @@ template<class Op, bool STAGED>
 __device__ __forceinline__ void pipe_gather(BatchHead<Op>& h, float (&acc)[Op::NSUM], const StageHeader& H, const Arrays& A,
                                             const float4* __restrict__ sA, const void* __restrict__ sBv, Op& op) {
     constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
-    constexpr int D = PIPE_LOOKAHEAD;
+    constexpr int D = Op::Cfg::D;
     const float4* __restrict__ sB = reinterpret_cast<const float4*>(sBv);
     const float* __restrict__ sB1 = reinterpret_cast<const float*>(sBv);
     auto gatherB = [&](uint32_t L) -> float4 {
@@ -639,19 +648,19 @@ __device__ __forceinline__ void pipe_gather(BatchHead<Op>& h, float (&acc)[Op::N
         ell_unpack(wq, L);
         float c[4] = { cq.x, cq.y, cq.z, cq.w };
         if (g * 4u + 4u <= m) {
-            // PIPE_GATHER_WIDTH payloads are gathered back to back before their pair terms are accumulated (in list order)
+            // Cfg::GW payloads are gathered back to back before their pair terms are accumulated (in list order)
             #pragma unroll
-            for (int u0 = 0; u0 < 4; u0 += PIPE_GATHER_WIDTH) {
-                float4 pa[PIPE_GATHER_WIDTH], pb[PIPE_GATHER_WIDTH];
+            for (int u0 = 0; u0 < 4; u0 += Op::Cfg::GW) {
+                float4 pa[Op::Cfg::GW], pb[Op::Cfg::GW];
                 #pragma unroll
-                for (int u = 0; u < PIPE_GATHER_WIDTH; u++) {
+                for (int u = 0; u < Op::Cfg::GW; u++) {
                     const uint32_t Lu = L[u0 + u];
                     if (PIPE_ABLATE & 2) { pa[u] = make_float4(h.own[0] + (float)Lu, h.own[1], h.own[2], 1.0f); pb[u] = pa[u]; }
                     else if (STAGED) { pa[u] = sA[Lu]; pb[u] = gatherB(Lu); }
                     else { const uint32_t gi = hdr_local_to_global(H, Lu); pa[u] = op.loadA(gi); pb[u] = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
                 }
                 #pragma unroll
-                for (int u = 0; u < PIPE_GATHER_WIDTH; u++) op.pair(h.own, pa[u], pb[u], c[u0 + u], acc);
+                for (int u = 0; u < Op::Cfg::GW; u++) op.pair(h.own, pa[u], pb[u], c[u0 + u], acc);
             }
         } else {
             #pragma unroll
@@ -696,12 +705,12 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
         c.begin = H.begin; c.end = H.end; c.li = H.li;
         if (c.begin == 0xffffffffu) { c.done = true; c.nBatch = 0; return; }
         c.nBatch = (c.end - c.begin + 31u) >> 5;
-        c.b = (cw + PIPE_CONSUMER_WARPS - c.rot) % PIPE_CONSUMER_WARPS;
+        c.b = (cw + Op::Cfg::CW - c.rot) % Op::Cfg::CW;
     };
     // move to this warp's next batch, releasing every tile it leaves behind (their gathers are complete)
     auto seek = [&]() {
         while (!c.done && c.b >= c.nBatch) {
-            c.rot = (c.rot + c.nBatch) % PIPE_CONSUMER_WARPS;
+            c.rot = (c.rot + c.nBatch) % Op::Cfg::CW;
             __syncwarp();
             if (lane == 0) mbar_arrive(&ps.empty[c.k % PIPE_STAGES]);
             c.k++;
@@ -730,7 +739,7 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
         #pragma unroll
         for (int i = 0; i < Op::NOWN; i++) own[i] = h.own[i];
         // next batch: its start-up loads go out now and land during the epilogue
-        c.b += PIPE_CONSUMER_WARPS;
+        c.b += Op::Cfg::CW;
         seek();
         if (!c.done) pipe_head_load(h, c, lane, A, op);
         if (p != 0xffffffffu && !((PIPE_ABLATE & 8) && acc[0] != 12345.0f)) op.finish(p, m, own, acc);
@@ -768,7 +777,7 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
     }
 }
 
-// Called by all PIPE_THREADS threads of the CTA (after any lookup table has been loaded; contains __syncthreads).
+// Called by all Op::Cfg::THREADS threads of the CTA (after any lookup table has been loaded; contains __syncthreads).
 // Returns true in every thread of the CTA that finished last (it has reset the tile queue; kernels with a grid-wide
 // sum fold the batch slots there).
 template<class Op>
@@ -776,14 +785,14 @@ __device__ __forceinline__ bool pipe_pass(DevState* __restrict__ S, const Arrays
                                           uint32_t tile0, uint32_t tile1, bool checkIndexRange = false) {
     if (threadIdx.x == 0) {
         #pragma unroll
-        for (int s = 0; s < PIPE_STAGES; s++) { mbar_init(&ps.full[s], PIPE_PRODUCER_THREADS + 1); mbar_init(&ps.empty[s], PIPE_CONSUMER_WARPS); }
+        for (int s = 0; s < PIPE_STAGES; s++) { mbar_init(&ps.full[s], PIPE_PRODUCER_THREADS + 1); mbar_init(&ps.empty[s], Op::Cfg::CW); }
     }
     if (threadIdx.x < PIPE_RED_RECORDS) {
         RedRecord& R = ps.rec[threadIdx.x];
         R.count = 0u; R.bsum[0][PIPE_MAX_BATCH - 1] = 0.0; R.bsum[1][PIPE_MAX_BATCH - 1] = 0.0;
     }
     __syncthreads();
-    if (threadIdx.x >= PIPE_CONSUMER_WARPS * 32) pipe_producer(S, A, ps, pay, op, tile0, tile1, checkIndexRange);
+    if (threadIdx.x >= Op::Cfg::CW * 32) pipe_producer(S, A, ps, pay, op, tile0, tile1, checkIndexRange);
     else if constexpr (Op::CUSTOM) pipe_consumer(A, ps, pay, op);
     else pipe_consumer_pairs(A, ps, pay, op);
     __syncthreads();

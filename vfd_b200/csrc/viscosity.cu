@@ -61,6 +61,7 @@ __device__ __forceinline__ bool boundary_samples(const Params& P, float3 xi, flo
 // ---- V1 + V2 fused: preconditioner blocks, per-pair coefficients, warm start, |b|^2 ----------
 struct ViscSetupOp {
     static constexpr bool CUSTOM = false;
+    using Cfg = PipeCfgMany;
     static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 9, COEF = 3, NRED = 1; // payload (x, y, z, rho); reads the pair's kernel-gradient
     const Params& P; const Arrays& A; Lut K;                                   // factor g_ij (pressure.cu), writes the pair coefficients
     float dt, eps2;
@@ -147,7 +148,7 @@ struct ViscSetupOp {
     }
 };
 
-__global__ void __launch_bounds__(PIPE_THREADS, 1) k_visc_setup(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
+__global__ void __launch_bounds__(ViscSetupOp::Cfg::THREADS, 1) k_visc_setup(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
     PipeShared& ps = pipe_header(smemRaw);
     float* sG = pipe_lut<1>(smemRaw);                     // the boundary-friction samples still need the table
     load_lut_tile(sG, lutG);
@@ -171,6 +172,7 @@ __device__ __forceinline__ float3 mat_vec(const float* __restrict__ minv, uint32
 template<bool INIT>
 struct ViscMatvecOp {
     static constexpr bool CUSTOM = false;
+    using Cfg = PipeCfgWide;
     static constexpr int NPAY = 2, NOWN = 6, NSUM = 3, COEF = 1, NRED = INIT ? 2 : 1;     // payload: (x, y, z, rho), the vector's (x, y, z); reads the pair coefficients
     const Params& P; const Arrays& A;
     const float4* __restrict__ x;    // the vector the operator is applied to: g (INIT) or the search direction p
@@ -234,7 +236,7 @@ struct ViscMatvecOp {
 };
 
 template<bool INIT>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) k_visc_matvec_pipe(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+__global__ void __launch_bounds__(ViscMatvecOp<INIT>::Cfg::THREADS, 1) k_visc_matvec_pipe(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (!INIT && S->viscActive != 1u) return;
     PipeShared& ps = pipe_header(smemRaw);
     ViscMatvecOp<INIT> op{ P, A, INIT ? A.cgG : A.cgP, S->dt, { 0.0f, 0.0f } };
@@ -317,14 +319,14 @@ void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A
     const size_t sp = pipe_smem_bytes<1, 16, 0>();
     pipe_attr(k_visc_setup, sp);
     LaunchScope ls(L, KID_VISC_SETUP);
-    k_visc_setup<<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S, lutG);
+    k_visc_setup<<<L.numSMs, ViscSetupOp::Cfg::THREADS, sp, L.stream>>>(P, A, S, lutG);
 }
 
 void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init) {
     const size_t sp = pipe_smem_bytes<0, 16, 16>();
     LaunchScope ls(L, init ? KID_VISC_MATVEC0 : KID_VISC_MATVEC);
-    if (init) { pipe_attr(k_visc_matvec_pipe<true>, sp); k_visc_matvec_pipe<true><<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S); }
-    else      { pipe_attr(k_visc_matvec_pipe<false>, sp); k_visc_matvec_pipe<false><<<L.numSMs, PIPE_THREADS, sp, L.stream>>>(P, A, S); }
+    if (init) { pipe_attr(k_visc_matvec_pipe<true>, sp); k_visc_matvec_pipe<true><<<L.numSMs, ViscMatvecOp<true>::Cfg::THREADS, sp, L.stream>>>(P, A, S); }
+    else      { pipe_attr(k_visc_matvec_pipe<false>, sp); k_visc_matvec_pipe<false><<<L.numSMs, ViscMatvecOp<false>::Cfg::THREADS, sp, L.stream>>>(P, A, S); }
 }
 void launch_viscosity_update(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     const uint32_t tiles = std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB);
