@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_boundary(Params P, Arrays A, BodySe
     if (p >= P.n) return;
     const float4 x4 = A.pos[p];
     float3 x = f3(x4);
-    bool moved = false;
+    bool moved = false, nearBody = false;
     for (uint32_t b = 0; b < P.nBodies; b++) {
         float3 xb = f3(0.0f, 0.0f, 0.0f);
         float vb = 0.0f;
@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(VFD_TPB) k_boundary(Params P, Arrays A, BodySe
             }
         }
         A.bx[b][p] = make_float4(xb.x, xb.y, xb.z, vb);
+        nearBody = nearBody || vb > 0.0f;
     }
+    if (nearBody) A.cnt[p] |= VFD_NEAR_BODY;             // the search has just written the plain count
     if (moved) A.pos[p] = make_float4(x.x, x.y, x.z, x4.w);
 }
 

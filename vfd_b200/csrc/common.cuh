@@ -25,6 +25,10 @@
 #define VFD_EPS_F 1.0e-5f
 #define VFD_TPB 256                   // reference launch shape: DFSPHKernels.cuh:11
 #define VFD_MAX_BODIES 8
+// cnt[p] = neighbour count | VFD_NEAR_BODY when at least one rigid body has a boundary sample for the particle (set by
+// the boundary kernel): the epilogues of the neighbour passes read the per-body arrays only then
+#define VFD_NEAR_BODY 0x80000000u
+#define VFD_COUNT_MASK 0x7fffffffu
 
 namespace vfd {
 

@@ -66,12 +66,12 @@ struct DensityFactorOp {
         acc[1] += dot3(gj, gj);
         acc[2] -= gj.x; acc[3] -= gj.y; acc[4] -= gj.z;
     }
-    __device__ __forceinline__ void finish(uint32_t p, uint32_t, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t mf, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
         const float3 xi = f3(o[0], o[1], o[2]);
         float rho = P.volume * P.wZero + sum[0];
         float sumK = sum[1];
         float3 gradI = f3(sum[2], sum[3], sum[4]);
-        for (uint32_t b = 0; b < P.nBodies; b++) {
+        if (mf & VFD_NEAR_BODY) for (uint32_t b = 0; b < P.nBodies; b++) {
             const float4 bx = A.bx[b][p];
             float4 bg = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (bx.w > 0.0f) {
@@ -125,10 +125,11 @@ struct SourceOp {
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
         acc[0] += dot3(f3(o[3], o[4], o[5]) - f3(b), c * (f3(o[0], o[1], o[2]) - f3(a)));
     }
-    __device__ __forceinline__ void finish(uint32_t p, uint32_t m, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t mf, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
+        const uint32_t m = mf & VFD_COUNT_MASK;
         const float3 vi = f3(o[3], o[4], o[5]);
         float s = sum[0] * P.volume;
-        for (uint32_t b = 0; b < P.nBodies; b++) {
+        if (mf & VFD_NEAR_BODY) for (uint32_t b = 0; b < P.nBodies; b++) {
             const float4 bg = A.bgrad[b][p];
             if (bg.w > 0.0f) s += bg.w * dot3(vi, f3(bg));
         }
@@ -188,10 +189,10 @@ struct AccelOp {
             acc[0] += ks * gj.x; acc[1] += ks * gj.y; acc[2] += ks * gj.z;
         }
     }
-    __device__ __forceinline__ void finish(uint32_t p, uint32_t, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t mf, const float (&o)[NOWN], const float (&sum)[NSUM]) const {
         const float ki = o[3];
         float3 a = f3(sum[0], sum[1], sum[2]);
-        if (fabsf(ki) > VFD_EPS_F) {
+        if ((mf & VFD_NEAR_BODY) && fabsf(ki) > VFD_EPS_F) {
             for (uint32_t b = 0; b < P.nBodies; b++) {
                 const float4 bg = A.bgrad[b][p];
                 if (bg.w > 0.0f) {
@@ -240,10 +241,11 @@ struct SolveOp {
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
         acc[0] += dot3(f3(o[3], o[4], o[5]) - f3(b), c * (f3(o[0], o[1], o[2]) - f3(a)));
     }
-    __device__ __forceinline__ void finish(uint32_t p, uint32_t m, const float (&o)[NOWN], const float (&sum)[NSUM]) {
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t mf, const float (&o)[NOWN], const float (&sum)[NSUM]) {
+        const uint32_t m = mf & VFD_COUNT_MASK;
         const float3 ai = f3(o[3], o[4], o[5]);
         float s = sum[0] * P.volume;
-        for (uint32_t b = 0; b < P.nBodies; b++) {
+        if (mf & VFD_NEAR_BODY) for (uint32_t b = 0; b < P.nBodies; b++) {
             const float4 bg = A.bgrad[b][p];
             if (bg.w > 0.0f) s += bg.w * dot3(ai, f3(bg));
         }

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(512) k_export_neighbors(const __grid_constant_
         const TileInfo t = tile_setup(S, A.cellBegin, tile, sh, 0u);
         (void)t.staged;
         for (uint32_t p = t.begin + threadIdx.x; p < t.end; p += blockDim.x) {
-            const uint32_t o = A.id[p], m = A.cnt[p];
+            const uint32_t o = A.id[p], m = A.cnt[p] & VFD_COUNT_MASK;
             counts[o] = m;
             const uint2* col = ell_list(A.list16, p);
             for (uint32_t k = 0; k < m; k++) {

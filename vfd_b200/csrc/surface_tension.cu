@@ -52,7 +52,7 @@ struct StClassifyOp {
         float curv = 0.0f;
         bool surface = false;
         if (valid) {
-            m = A.cnt[p];
+            m = A.cnt[p] & VFD_COUNT_MASK;
             xi = f3(A.posRho[p]);
             curv = A.curv[p];             // left untouched for interior particles
             if (m == 0u) {

@@ -187,7 +187,7 @@ __device__ __forceinline__ void tile_particles(const TileInfo& t, const TileShar
             op.particle(p, p < t.end, acc);
         } else {
             if (p >= t.end) continue;
-            const uint32_t m = __ldg(A.cnt + p);
+            const uint32_t m = __ldg(A.cnt + p) & VFD_COUNT_MASK;
             float own[Op::NOWN];
             op.load_own(p, own);
             float acc[Op::NSUM];
@@ -612,7 +612,7 @@ __device__ __forceinline__ void pipe_head_load(BatchHead<Op>& h, const BatchCurs
     #pragma unroll
     for (int i = 0; i < Op::NOWN; i++) h.own[i] = 0.0f;
     if (h.p >= c.end) { h.p = 0xffffffffu; return; }
-    h.m = __ldg(A.cnt + h.p);
+    h.m = __ldg(A.cnt + h.p);                             // with the VFD_NEAR_BODY flag, which the epilogue wants
     op.load_own(h.p, h.own);
     const uint2* __restrict__ col = ell_list(A.list16, h.p);
     const float4* __restrict__ cin = reinterpret_cast<const float4*>(op.coef_in()) + ell_base(h.p);
@@ -636,7 +636,7 @@ __device__ __forceinline__ void pipe_gather(BatchHead<Op>& h, float (&acc)[Op::N
         if (BBYTES == 4) return make_float4(sB1[L], 0.0f, 0.0f, 0.0f);
         return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     };
-    const uint32_t m = h.m;
+    const uint32_t m = h.m & VFD_COUNT_MASK;
     if (m == 0u) return;
     const uint2* __restrict__ col = ell_list(A.list16, h.p);
     const float4* __restrict__ cin = reinterpret_cast<const float4*>(op.coef_in()) + ell_base(h.p);

@@ -87,13 +87,13 @@ struct ViscSetupOp {
         M[3] += s * (d.x * gw.y); M[4] += s * (d.y * gw.y); M[5] += s * (d.z * gw.y);
         M[6] += s * (d.x * gw.z); M[7] += s * (d.y * gw.z); M[8] += s * (d.z * gw.z);
     }
-    __device__ __forceinline__ void finish(uint32_t p, uint32_t, const float (&o)[NOWN], const float (&sum)[NSUM]) {
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t mf, const float (&o)[NOWN], const float (&sum)[NSUM]) {
         const float3 xi = f3(o[0], o[1], o[2]);
         const float rhoI = A.posRho[p].w;
         float M[9];
         #pragma unroll
         for (int q = 0; q < 9; q++) M[q] = sum[q];
-        if (P.muB != 0.0f) {
+        if (P.muB != 0.0f && (mf & VFD_NEAR_BODY)) {
             for (uint32_t b = 0; b < P.nBodies; b++) {
                 const float4 bx = A.bx[b][p];
                 float4 cb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -173,7 +173,7 @@ template<bool INIT>
 struct ViscMatvecOp {
     static constexpr bool CUSTOM = false;
     using Cfg = PipeCfgWide;
-    static constexpr int NPAY = 2, NOWN = 6, NSUM = 3, COEF = 1, NRED = INIT ? 2 : 1;     // payload: (x, y, z, rho), the vector's (x, y, z); reads the pair coefficients
+    static constexpr int NPAY = 2, NOWN = 7, NSUM = 3, COEF = 1, NRED = INIT ? 2 : 1;     // payload: (x, y, z, rho), the vector's (x, y, z); reads the pair coefficients
     const Params& P; const Arrays& A;
     const float4* __restrict__ x;    // the vector the operator is applied to: g (INIT) or the search direction p
     float dt;
@@ -194,18 +194,18 @@ struct ViscMatvecOp {
     __device__ __forceinline__ float4 loadB(uint32_t g) const { return x[g]; }
     __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
         const float4 xr = A.posRho[p], v = x[p];
-        own[0] = xr.x; own[1] = xr.y; own[2] = xr.z; own[3] = v.x; own[4] = v.y; own[5] = v.z;
+        own[0] = xr.x; own[1] = xr.y; own[2] = xr.z; own[3] = v.x; own[4] = v.y; own[5] = v.z; own[6] = xr.w;
     }
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
         const float dx = o[0] - a.x, dy = o[1] - a.y, dz = o[2] - a.z;
         const float w = c * __fmaf_rn(o[5] - b.z, dz, __fmaf_rn(o[4] - b.y, dy, (o[3] - b.x) * dx));
         acc[0] = __fmaf_rn(w, dx, acc[0]); acc[1] = __fmaf_rn(w, dy, acc[1]); acc[2] = __fmaf_rn(w, dz, acc[2]);
     }
-    __device__ __forceinline__ void finish(uint32_t p, uint32_t, const float (&o)[NOWN], const float (&acc)[NSUM]) {
+    __device__ __forceinline__ void finish(uint32_t p, uint32_t mf, const float (&o)[NOWN], const float (&acc)[NSUM]) {
         const float3 xi = f3(o[0], o[1], o[2]), vi = f3(o[3], o[4], o[5]);
-        const float rhoI = A.posRho[p].w;
+        const float rhoI = o[6];
         float3 sum = f3(acc[0], acc[1], acc[2]);
-        if (P.muB != 0.0f) {
+        if (P.muB != 0.0f && (mf & VFD_NEAR_BODY)) {
             for (uint32_t b = 0; b < P.nBodies; b++) {
                 const float4 bx = A.bx[b][p];
                 if (bx.w > 0.0f) {
