@@ -24,13 +24,14 @@ __device__ __forceinline__ float3 normalize_if_nonzero(float3 v) {   // DFSPHKer
 // T1: classify surface particles by the centre of mass of their neighbourhood; for those, estimate
 // the normal and curvature from the Halton samples on the support sphere not covered by a neighbour.
 //
-// Two phases per warp.  A: every lane classifies its own particle (one pass over its neighbours).  B: the few
-// surface particles of the warp (a thin shell of the fluid) are then processed ONE AT A TIME BY THE WHOLE WARP —
-// lane l tests samples l, l+32, ... against the particle's neighbours (warp-uniform shared-memory reads: broadcasts)
-// — instead of one lane running SampleCount x m distance tests while 31 lanes idle.  The uncovered samples are
+// Two phases per tile.  A: every lane classifies its own particle (one pass over its neighbours); surface particles go into
+// the tile's work queue (tile.cuh: TileQueue).  B: the consumer warps of the CTA take surface particles from the queue one at
+// a time and process each WITH THE WHOLE WARP — lane l tests samples l, l+32, ... against the particle's neighbours
+// (warp-uniform shared-memory reads: broadcasts) — instead of one lane running SampleCount x m distance tests while 31 lanes
+// idle, and instead of the few warps whose batches lie in the surface shell doing all of it.  The uncovered samples are
 // summed in sample order, as the reference's sequential loop does, so the result is bit-identical to it.
 struct StClassifyOp {
-    static constexpr bool CUSTOM = true;
+    static constexpr bool CUSTOM = true, TILE_QUEUE = true;
     using Cfg = PipeCfg<24, 2, 2>;
     static constexpr int NPAY = 1, BBYTES = 0, COEF = 0, NRED = 0;
     const Params& P; const Arrays& A;
@@ -42,85 +43,104 @@ struct StClassifyOp {
     __device__ __forceinline__ void prefetch_own(uint32_t, uint32_t, uint32_t) const {}
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+    // phase A; returns true when the particle is a surface particle (to be queued)
     template<class Acc>
-    __device__ __forceinline__ void particle(uint32_t p, bool valid, const Acc& acc, const StageHeader&) {
-        const int lane = threadIdx.x & 31;
-        uint32_t m = 0u;
-        float3 xi = f3(0.0f, 0.0f, 0.0f);
-        const uint16_t* col = A.list16 + ell_base(valid ? p : 0u) * 4;          // slot k: col[(k >> 2) * 128 + (k & 3)]
-        float3 n = f3(0.0f, 0.0f, 0.0f);
-        float curv = 0.0f;
+    __device__ __forceinline__ bool particle(uint32_t p, bool valid, const Acc& acc, const StageHeader&) {
+        if (!valid) return false;
+        const uint32_t m = A.cnt[p] & VFD_COUNT_MASK;
+        const float3 xi = f3(A.posRho[p]);
+        float curv = A.curv[p];           // left untouched for interior particles
         bool surface = false;
-        if (valid) {
-            m = A.cnt[p] & VFD_COUNT_MASK;
-            xi = f3(A.posRho[p]);
-            curv = A.curv[p];             // left untouched for interior particles
-            if (m == 0u) {
-                curv = 1.0f / P.h;
-            } else {
-                float3 com = f3(0.0f, 0.0f, 0.0f);
-                for (uint32_t k = 0; k < m; k++) com += f3(acc(col[(size_t)(k >> 2) * 128 + (k & 3u)])) - xi;
-                com = com / P.h;
-                const float clsIn = sqrtf(dot3(com, com)) / (float)m;
-                const float onLine = P.clsSlope * clsIn + P.clsConst + 0.0f;
-                surface = (float)m <= onLine;
+        if (m == 0u) {
+            curv = 1.0f / P.h;
+        } else {
+            const uint2* col = ell_list(A.list16, p);                  // group g (slots 4g..4g+3): col[g * 32]
+            float3 com = f3(0.0f, 0.0f, 0.0f);
+            const uint32_t nG = (m + 3u) >> 2;
+            uint2 w = __ldg(col);
+            for (uint32_t g = 0; g < nG; g++) {
+                const uint2 wn = __ldg(col + (size_t)min(g + 1u, nG - 1u) * 32);      // next group in flight
+                uint32_t L[4];
+                ell_unpack(w, L);
+                float4 x[4];
+                #pragma unroll
+                for (int u = 0; u < 4; u++) x[u] = acc(L[u]);           // unused slots of the last group hold index 0: a valid read
+                #pragma unroll
+                for (int u = 0; u < 4; u++) if (g * 4u + (uint32_t)u < m) com += f3(x[u]) - xi;      // in list order
+                w = wn;
             }
+            com = com / P.h;
+            const float clsIn = sqrtf(dot3(com, com)) / (float)m;
+            const float onLine = P.clsSlope * clsIn + P.clsConst + 0.0f;
+            surface = (float)m <= onLine;
         }
-        // phase B: the warp's surface particles, one at a time
-        uint32_t todo = __ballot_sync(0xffffffffu, surface);
-        // the sample window depends on the particle's *original* index (DFSPHKernels.cu:911)
-        const uint32_t sOwn = surface ? A.id[p] * sampleCount / 3u * 3u : 0u;
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const uint32_t mS = __shfl_sync(0xffffffffu, m, src);
-            const uint32_t sS = __shfl_sync(0xffffffffu, sOwn, src);
-            const float3 xS = f3(__shfl_sync(0xffffffffu, xi.x, src), __shfl_sync(0xffffffffu, xi.y, src), __shfl_sync(0xffffffffu, xi.z, src));
-            const uint32_t pS = __shfl_sync(0xffffffffu, p, src);
-            const uint16_t* colS = A.list16 + ell_base(pS) * 4;
-            float3 nS = f3(0.0f, 0.0f, 0.0f);
-            uint32_t kept = 0u;
-            for (uint32_t q0 = 0; q0 < sampleCount; q0 += 32u) {
-                const uint32_t q = q0 + (uint32_t)lane;
-                float3 pt = f3(0.0f, 0.0f, 0.0f);
-                bool open = false;
-                if (q < sampleCount) {
-                    const uint32_t i3 = sS + 3u * q;
-                    pt = P.h * f3(__ldg(halton + i3 % VFD_HALTON_N), __ldg(halton + (i3 + 1u) % VFD_HALTON_N), __ldg(halton + (i3 + 2u) % VFD_HALTON_N));
-                    open = true;
-                }
-                // every lane walks the same neighbour list (uniform addresses); a lane's sample drops out once covered
-                for (uint32_t k = 0; k < mS; k++) {
-                    const float3 dir = f3(acc(colS[(size_t)(k >> 2) * 128 + (k & 3u)])) - xS;
-                    const float3 v = pt - dir;
-                    if (dot3(v, v) <= cover2) open = false;
-                    if (!__any_sync(0xffffffffu, open)) break;
-                }
-                uint32_t keep = __ballot_sync(0xffffffffu, open);
-                kept += __popc(keep);
-                // n += pt in sample order (the reference's sequential sum)
-                while (keep) {
-                    const int l = __ffs(keep) - 1;
-                    keep &= keep - 1u;
-                    nS.x += __shfl_sync(0xffffffffu, pt.x, l);
-                    nS.y += __shfl_sync(0xffffffffu, pt.y, l);
-                    nS.z += __shfl_sync(0xffffffffu, pt.z, l);
-                }
-            }
-            if (lane == src) {
-                if (kept > 0u) {
-                    n = normalize_if_nonzero(nS);
-                    curv = 1.0f / P.h * -2.0f * sqrtf(1.0f - P.nbrRadius * P.nbrRadius / (P.r * P.r)) *
-                           cosf(acosf(1.0f - 2.0f * ((float)kept / (float)sampleCount)) + mcFactor);
-                } else {
-                    n = f3(0.0f, 0.0f, 0.0f);
-                    curv = 0.0f;
-                }
-            }
-        }
-        if (valid) {
+        if (!surface) {
             A.curv[p] = curv;
-            A.nrm[p] = make_float4(n.x, n.y, n.z, curv);
+            A.nrm[p] = make_float4(0.0f, 0.0f, 0.0f, curv);
+        }
+        return surface;
+    }
+    // phase B: one surface particle, by all 32 lanes
+    template<class Acc>
+    __device__ __forceinline__ void item(uint32_t pS, const Acc& acc, const StageHeader&) {
+        const int lane = threadIdx.x & 31;
+        const uint32_t mS = __ldg(A.cnt + pS) & VFD_COUNT_MASK;
+        const float3 xS = f3(A.posRho[pS]);
+        // the sample window depends on the particle's *original* index (DFSPHKernels.cu:911)
+        const uint32_t sS = A.id[pS] * sampleCount / 3u * 3u;
+        // the particle's whole list in registers: lane g holds group g (18 groups), handed round by shuffle
+        const uint32_t nG = (mS + 3u) >> 2;
+        uint2 myW = make_uint2(0u, 0u);
+        if ((uint32_t)lane < nG) myW = __ldg(ell_list(A.list16, pS) + (size_t)lane * 32);
+        float3 nS = f3(0.0f, 0.0f, 0.0f);
+        uint32_t kept = 0u;
+        for (uint32_t q0 = 0; q0 < sampleCount; q0 += 32u) {
+            const uint32_t q = q0 + (uint32_t)lane;
+            float3 pt = f3(0.0f, 0.0f, 0.0f);
+            bool open = false;
+            if (q < sampleCount) {
+                const uint32_t i3 = sS + 3u * q;
+                pt = P.h * f3(__ldg(halton + i3 % VFD_HALTON_N), __ldg(halton + (i3 + 1u) % VFD_HALTON_N), __ldg(halton + (i3 + 2u) % VFD_HALTON_N));
+                open = true;
+            }
+            // every lane walks the same neighbour list (uniform addresses); a lane's sample drops out once covered
+            for (uint32_t g = 0; g < nG; g++) {
+                uint32_t L[4];
+                ell_unpack(make_uint2(__shfl_sync(0xffffffffu, myW.x, g), __shfl_sync(0xffffffffu, myW.y, g)), L);
+                float4 x[4];
+                #pragma unroll
+                for (int u = 0; u < 4; u++) x[u] = acc(L[u]);
+                #pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (g * 4u + (uint32_t)u < mS) {
+                        const float3 dir = f3(x[u]) - xS;
+                        const float3 v = pt - dir;
+                        if (dot3(v, v) <= cover2) open = false;
+                    }
+                }
+                if (!__any_sync(0xffffffffu, open)) break;
+            }
+            uint32_t keep = __ballot_sync(0xffffffffu, open);
+            kept += __popc(keep);
+            // n += pt in sample order (the reference's sequential sum)
+            while (keep) {
+                const int l = __ffs(keep) - 1;
+                keep &= keep - 1u;
+                nS.x += __shfl_sync(0xffffffffu, pt.x, l);
+                nS.y += __shfl_sync(0xffffffffu, pt.y, l);
+                nS.z += __shfl_sync(0xffffffffu, pt.z, l);
+            }
+        }
+        if (lane == 0) {
+            float3 n = f3(0.0f, 0.0f, 0.0f);
+            float curv = 0.0f;
+            if (kept > 0u) {
+                n = normalize_if_nonzero(nS);
+                curv = 1.0f / P.h * -2.0f * sqrtf(1.0f - P.nbrRadius * P.nbrRadius / (P.r * P.r)) *
+                       cosf(acosf(1.0f - 2.0f * ((float)kept / (float)sampleCount)) + mcFactor);
+            }
+            A.curv[pS] = curv;
+            A.nrm[pS] = make_float4(n.x, n.y, n.z, curv);
         }
     }
 };

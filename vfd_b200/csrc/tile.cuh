@@ -336,6 +336,18 @@ struct RedRecord {
     double bsum[2][PIPE_MAX_BATCH];
     uint32_t count, pad[3];
 };
+// Custom ops with Op::TILE_QUEUE: the same storage, seen as the tile's work queue — items one warp found (for the surface
+// classifier: the tile's surface particles) that ANY consumer warp of the CTA may take, so the warps whose batches hold no
+// such item help the ones whose batches are full of them instead of running ahead and stalling on the ring.
+// Entries are 16-bit offsets from the tile's first particle; PIPE_QUEUE_NONE marks a slot that is not written yet.
+#define PIPE_QUEUE_CAP 504
+#define PIPE_QUEUE_NONE 0xffffu
+struct TileQueue {
+    uint32_t head, tail, left, pad;
+    unsigned short e[PIPE_QUEUE_CAP];
+};
+static_assert(sizeof(TileQueue) <= sizeof(RedRecord), "the queue overlays a reduction record");
+
 struct PipeShared {
     unsigned long long full[PIPE_STAGES], empty[PIPE_STAGES];
     uint32_t nextLi[2], lastCta, pad_;       // tile queue hand-over between the producer threads (two slots, used in turn); "this CTA finished last"
@@ -572,10 +584,58 @@ __device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, c
         const float4* sA = reinterpret_cast<const float4*>(pay + (size_t)base * 16);
         const uint32_t nBatch = (end - begin + 31u) >> 5;
         // batch b of this tile goes to warp (rot + b) mod W: consecutive batches of consecutive tiles visit the warps in turn
-        for (uint32_t b = (cw + Op::Cfg::CW - rot) % Op::Cfg::CW; b < nBatch; b += Op::Cfg::CW) {
-            const uint32_t p = begin + (b << 5) + lane;
-            const PipeAcc<Op> acc{ H, sA, op, staged };
-            op.particle(p, p < end, acc, H);
+        const PipeAcc<Op> acc{ H, sA, op, staged };
+        if constexpr (Op::TILE_QUEUE) {
+            TileQueue& Q = *reinterpret_cast<TileQueue*>(&ps.rec[k % PIPE_RED_RECORDS]);
+            for (uint32_t b = (cw + Op::Cfg::CW - rot) % Op::Cfg::CW; b < nBatch; b += Op::Cfg::CW) {
+                const uint32_t p = begin + (b << 5) + lane;
+                // phase A: the op handles the particle or asks for it to be queued
+                const bool want = op.particle(p, p < end, acc, H);
+                const uint32_t mask = __ballot_sync(0xffffffffu, want);
+                if (mask) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&Q.tail, (uint32_t)__popc(mask));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const uint32_t slot = base + __popc(mask & ((1u << lane) - 1u));
+                    if (want && slot < PIPE_QUEUE_CAP) *reinterpret_cast<volatile unsigned short*>(&Q.e[slot]) = (unsigned short)(p - begin);
+                    // a tile with more items than the queue holds (never at fluid densities): the finder does the surplus itself
+                    uint32_t over = __ballot_sync(0xffffffffu, want && slot >= PIPE_QUEUE_CAP);
+                    while (over) { const int src = __ffs(over) - 1; over &= over - 1u; op.item(__shfl_sync(0xffffffffu, p, src), acc, H); }
+                }
+            }
+            // phase B: take items until the queue is empty (whoever queued them)
+            for (;;) {
+                uint32_t h = 0, got = 0;
+                if (lane == 0) {
+                    for (;;) {
+                        h = *reinterpret_cast<volatile uint32_t*>(&Q.head);
+                        const uint32_t t = min(*reinterpret_cast<volatile uint32_t*>(&Q.tail), (uint32_t)PIPE_QUEUE_CAP);
+                        if (h >= t) break;
+                        if (atomicCAS(&Q.head, h, h + 1u) == h) { got = 1; break; }
+                    }
+                }
+                got = __shfl_sync(0xffffffffu, got, 0);
+                if (!got) break;
+                h = __shfl_sync(0xffffffffu, h, 0);
+                uint32_t off = PIPE_QUEUE_NONE;
+                if (lane == 0) {
+                    volatile unsigned short* e = reinterpret_cast<volatile unsigned short*>(&Q.e[h]);
+                    do { off = *e; } while (off == PIPE_QUEUE_NONE);     // reserved before it is written: a few cycles at most
+                    *e = PIPE_QUEUE_NONE;
+                }
+                off = __shfl_sync(0xffffffffu, off, 0);
+                op.item(begin + off, acc, H);
+            }
+            // the last warp to leave resets the counters for the record's next tile (the slots are PIPE_QUEUE_NONE again)
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&Q.left, 1u) == Op::Cfg::CW - 1u) { Q.head = 0u; Q.tail = 0u; Q.left = 0u; }
+            }
+        } else {
+            for (uint32_t b = (cw + Op::Cfg::CW - rot) % Op::Cfg::CW; b < nBatch; b += Op::Cfg::CW) {
+                const uint32_t p = begin + (b << 5) + lane;
+                op.particle(p, p < end, acc, H);
+            }
         }
         rot = (rot + nBatch) % Op::Cfg::CW;
         __syncwarp();
@@ -787,7 +847,15 @@ __device__ __forceinline__ bool pipe_pass(DevState* __restrict__ S, const Arrays
         #pragma unroll
         for (int s = 0; s < PIPE_STAGES; s++) { mbar_init(&ps.full[s], PIPE_PRODUCER_THREADS + 1); mbar_init(&ps.empty[s], Op::Cfg::CW); }
     }
-    if (threadIdx.x < PIPE_RED_RECORDS) {
+    if constexpr (Op::CUSTOM) {
+        if constexpr (Op::TILE_QUEUE) {
+            for (uint32_t i = threadIdx.x; i < PIPE_RED_RECORDS * PIPE_QUEUE_CAP; i += blockDim.x) {
+                TileQueue& Q = *reinterpret_cast<TileQueue*>(&ps.rec[i / PIPE_QUEUE_CAP]);
+                Q.e[i % PIPE_QUEUE_CAP] = PIPE_QUEUE_NONE;
+                if (i % PIPE_QUEUE_CAP == 0) { Q.head = 0u; Q.tail = 0u; Q.left = 0u; }
+            }
+        }
+    } else if (threadIdx.x < PIPE_RED_RECORDS) {
         RedRecord& R = ps.rec[threadIdx.x];
         R.count = 0u; R.bsum[0][PIPE_MAX_BATCH - 1] = 0.0; R.bsum[1][PIPE_MAX_BATCH - 1] = 0.0;
     }
