@@ -185,6 +185,54 @@ def run_reference(args, rank, world):
     return 0
 
 
+def ncu_traffic(kernel, n):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel class from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json, written from the round's capture by
+    tools_ncu_summary.py); None when the capture does not cover this kernel or particle count."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if int(t.get("particles", 0)) != int(n):
+            return None
+        v = t.get("dram_bytes_per_launch", {}).get(kernel)
+        return None if v is None else float(v)
+    except Exception:
+        return None
+
+
+def roofline_pass(sim, api, n, mbar, steps, skip=False):
+    """Second pass over the next K steps with every launch bracketed by CUDA events on the solver's stream: per-kernel
+    device time -> roofline of the dominant kernel class (the event pairs cost a few us per launch, so this pass is not
+    the one `value` is taken from).  Returns (roofline, per-kernel table, ms of the pass)."""
+    sim.set_option(api.VFD_OPT_KERNEL_TIMERS, 0 if skip else 1)
+    sim.kernel_times(reset=True)
+    sim.record_event(2)
+    for _ in range(0 if skip else steps):
+        sim.OnUpdate()
+    sim.record_event(3)
+    ms_prof = sim.elapsed_ms(2, 3)
+    ktimes = sim.kernel_times()
+    sim.set_option(api.VFD_OPT_KERNEL_TIMERS, 0)
+    peak, peak_src = peaks()
+    roof, table = None, {}
+    total_kernel_ms = sum(v[2] for v in ktimes.values())
+    for name, (msa, lna, msall, lnall) in sorted(ktimes.items(), key=lambda kv: -kv[1][2]):
+        fixed, per = ALGO_BYTES.get(name, (0, 0))
+        b = (fixed + per * mbar) * n
+        avg = msa / lna if lna else 0.0
+        gbs = b / (avg * 1e-3) / 1e9 if avg > 0 and b > 0 else None
+        table[name] = {"ms_per_step": round(msall / steps, 4), "launches_per_step": round(lnall / steps, 2),
+                       "avg_ms_active": round(avg, 5), "algo_GBps": None if gbs is None else round(gbs, 1),
+                       "frac_of_peak": None if gbs is None else round(gbs / peak, 3), "share": round(msall / total_kernel_ms, 4)}
+        if roof is None:
+            roof = {"bound": "hbm", "kernel": name, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak if gbs else None,
+                    "traffic": ncu_traffic(name, n), "peak_source": peak_src, "avg_launch_ms": avg, "active_launches": lna,
+                    "share_of_step": msall / total_kernel_ms, "algorithmic_bytes_per_launch": b,
+                    "note": "event-bracketed pass over the %d steps following the timed region (%.3f ms/step with brackets); traffic = DRAM bytes per launch "
+                            "from the committed ncu capture (profiles/)" % (steps, ms_prof / steps)}
+    return roof, table, ms_prof
+
+
 def cpu_baseline(state, dt, st, pos0, box, res, steps=10):
     """The reference's solver sources on this box's host cores, from the GPU run's settled state."""
     from oracle import refsim
@@ -278,34 +326,7 @@ def main():
     mbar = float(counts.mean())
     tstats = sim.tile_stats()
 
-    # second pass over the next K steps with every launch bracketed by CUDA events on the solver's stream:
-    # per-kernel device time -> roofline of the dominant kernel (the event pairs cost a few us per launch, so
-    # this pass is not the one `value` is taken from)
-    sim.set_option(api.VFD_OPT_KERNEL_TIMERS, 0 if args.ncu else 1)
-    sim.kernel_times(reset=True)
-    sim.record_event(2)
-    for _ in range(0 if args.ncu else args.steps):
-        sim.OnUpdate()
-    sim.record_event(3)
-    ms_prof = sim.elapsed_ms(2, 3)
-    ktimes = sim.kernel_times()
-    sim.set_option(api.VFD_OPT_KERNEL_TIMERS, 0)
-    peak, peak_src = peaks()
-    roof, table = None, {}
-    total_kernel_ms = sum(v[2] for v in ktimes.values())
-    for name, (msa, lna, msall, lnall) in sorted(ktimes.items(), key=lambda kv: -kv[1][2]):
-        fixed, per = ALGO_BYTES.get(name, (0, 0))
-        b = (fixed + per * mbar) * n
-        avg = msa / lna if lna else 0.0
-        gbs = b / (avg * 1e-3) / 1e9 if avg > 0 and b > 0 else None
-        table[name] = {"ms_per_step": round(msall / args.steps, 4), "launches_per_step": round(lnall / args.steps, 2),
-                       "avg_ms_active": round(avg, 5), "algo_GBps": None if gbs is None else round(gbs, 1),
-                       "frac_of_peak": None if gbs is None else round(gbs / peak, 3), "share": round(msall / total_kernel_ms, 4)}
-        if roof is None:
-            roof = {"bound": "hbm", "kernel": name, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak if gbs else None,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg, "active_launches": lna,
-                    "share_of_step": msall / total_kernel_ms, "algorithmic_bytes_per_launch": b,
-                    "note": "event-bracketed pass over the %d steps following the timed region (%.3f ms/step with brackets)" % (args.steps, ms_prof / args.steps)}
+    roof, table, ms_prof = roofline_pass(sim, api, n, mbar, args.steps, skip=args.ncu)
 
     out = {
         "metric": "DFSPH particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,

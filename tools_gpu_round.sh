@@ -14,7 +14,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
     -k regex:"k_visc_matvec|k_visc_setup|k_density_factor|k_source|k_pressure_accel|k_solve_iteration|k_build_list|k_st_classify|k_st_smooth|k_visc_update" \
     -c 14 -f -o gpurun_out/full_step python bench.py --steps 1 --warmup 3 --ncu --ncu-visc-it 1 > gpurun_out/ncu_full.log 2>&1; echo "ncu-full rc=$?" >> gpurun_out/ncu_full.log
-python tools_ncu_summary.py gpurun_out/full_step.ncu-rep gpurun_out/ncu_full_summary.txt > /dev/null 2>&1
+python tools_ncu_summary.py gpurun_out/full_step.ncu-rep gpurun_out/ncu_full_summary.txt gpurun_out/ncu_traffic.json 1000000 > /dev/null 2>&1
 [ "$(du -sm gpurun_out | cut -f1)" -gt 55 ] && rm -f gpurun_out/full_step.ncu-rep
 tail -n 5 gpurun_out/pytest.log gpurun_out/smoke.log gpurun_out/bench.err gpurun_out/ncu_launches.log gpurun_out/ncu_full.log
 cat gpurun_out/bench.json | cut -c1-1500

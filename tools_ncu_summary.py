@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""tools_ncu_summary.py REPORT.ncu-rep OUT.txt — condenses an `ncu --set full` report into the text summary kept under
+"""tools_ncu_summary.py REPORT.ncu-rep OUT.txt [TRAFFIC.json PARTICLES] — condenses an `ncu --set full` report into the text summary kept under
 profiles/: per launch the duration, DRAM bytes, L2/L1/SM throughput, shared-memory wavefronts and bank conflicts,
 occupancy, registers, and the warp-stall sample breakdown of each distinct kernel."""
 import csv
@@ -59,3 +59,27 @@ with open(out, "w") as f:
         tot = sum(v for v, _ in st) or 1.0
         f.write("%-44s " % short[:44] + "  ".join("%s %.0f%%" % (n, 100 * v / tot) for v, n in sorted(st, reverse=True)[:7]) + "\n")
 print(open(out).read())
+
+# optional: DRAM bytes per launch per bench.py kernel class (mean over the captured launches) -> profiles/ncu_traffic.json
+if len(sys.argv) > 4:
+    import json
+    CLASS = [("k_visc_matvec_pipe<(bool)0>", "visc_matvec"), ("k_visc_matvec_pipe<(bool)1>", "visc_matvec0"), ("k_visc_update", "visc_update"),
+             ("k_visc_direction", "visc_direction"), ("k_visc_setup", "visc_setup"), ("k_density_factor", "density_factor"),
+             ("k_solve_iteration<(bool)1>", "div_solve"), ("k_solve_iteration<(bool)0>", "press_solve"),
+             ("k_source<(bool)1>", "div_source"), ("k_source<(bool)0>", "press_source"),
+             ("k_pressure_accel<(int)0>", "div_accel"), ("k_pressure_accel<(int)1>", "div_finish"),
+             ("k_pressure_accel<(int)2>", "press_accel"), ("k_pressure_accel<(int)3>", "press_finish"),
+             ("k_st_classify", "st_classify"), ("k_st_smooth", "st_smooth"), ("k_build_list", "search_build_list")]
+    acc = {}
+    for r in data:
+        name = r[ix["Kernel Name"]]
+        rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
+        if rd is None or wr is None:
+            continue
+        for pat, cls in CLASS:
+            if pat in name:
+                acc.setdefault(cls, []).append(rd + wr)
+                break
+    with open(sys.argv[3], "w") as f:
+        json.dump({"source": rep.split("/")[-1] + " (ncu --set full --clock-control none; dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the captured launches)",
+                   "particles": int(sys.argv[4]), "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in acc.items()}}, f, indent=1)
