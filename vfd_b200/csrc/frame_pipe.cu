@@ -1,5 +1,6 @@
 // frame_pipe.cu — see frame_pipe.h.
 #include "frame_pipe.h"
+#include <cstdlib>
 #include <cstring>
 
 namespace vfd {
@@ -14,6 +15,38 @@ FramePipe::~FramePipe() {
         if (copied[s]) cudaEventDestroy(copied[s]);
     }
     if (copyStream) cudaStreamDestroy(copyStream);
+    for (Frame& f : frames) pool.push_back(f.data);
+    frames.clear();
+    release_pool();
+    if (dMeta) cudaFree(dMeta);
+    if (hMeta) cudaFreeHost(hMeta);
+}
+
+void FramePipe::release_pool() {
+    for (HostBuf& b : pool) {
+        if (!b.p) continue;
+        if (b.pinned) cudaFreeHost(b.p); else delete[] b.p;
+    }
+    pool.clear();
+    pinnedBytes = 0;
+}
+
+HostBuf FramePipe::take_buffer() {
+    {
+        std::lock_guard<std::mutex> g(m);
+        if (!pool.empty()) { HostBuf b = pool.back(); pool.pop_back(); return b; }
+    }
+    HostBuf b;
+    const size_t bytes = (size_t)(n ? n : 1u) * sizeof(VfdParticleSimple);
+    if (pinnedBytes + bytes <= pinnedBudget && cudaMallocHost((void**)&b.p, bytes) == cudaSuccess) {
+        b.pinned = true;
+        pinnedBytes += bytes;
+    } else {
+        cudaGetLastError();
+        b.p = new VfdParticleSimple[n ? n : 1u];
+        b.pinned = false;
+    }
+    return b;
 }
 
 void FramePipe::stop_worker() {
@@ -32,6 +65,15 @@ cudaError_t FramePipe::configure(int dev, uint32_t count) {
     if (e != cudaSuccess) return e;
     if (dev == device && count == n && copyStream) return cudaSuccess;
     stop_worker();
+    {
+        std::lock_guard<std::mutex> g(m);
+        for (Frame& f : frames) pool.push_back(f.data);
+        frames.clear();
+    }
+    if (device >= 0) cudaSetDevice(device);
+    release_pool();                                    // buffers of the old particle count
+    const char* mb = getenv("VFD_FRAME_PINNED_MB");
+    pinnedBudget = (size_t)(mb ? atoll(mb) : 8192) << 20;
     device = dev;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return e;
     for (int s = 0; s < SLOTS; s++) {
@@ -46,6 +88,8 @@ cudaError_t FramePipe::configure(int dev, uint32_t count) {
         busy[s] = false;
     }
     next = 0; acquired = -1;
+    if (!dMeta && (e = cudaMalloc((void**)&dMeta, SLOTS * 2 * sizeof(float))) != cudaSuccess) return e;
+    if (!hMeta && (e = cudaMallocHost((void**)&hMeta, SLOTS * 2 * sizeof(float))) != cudaSuccess) return e;
     // buffers are allocated lazily by acquire(): a solver that never bakes a frame pays nothing
     worker = std::thread(&FramePipe::worker_main, this);
     return cudaSuccess;
@@ -59,25 +103,30 @@ VfdParticleSimple* FramePipe::acquire() {
     }
     const size_t bytes = (size_t)(n ? n : 1u) * sizeof(VfdParticleSimple);
     if (!dBuf[s] && cudaMalloc((void**)&dBuf[s], bytes) != cudaSuccess) return nullptr;
-    if (!hBuf[s] && cudaMallocHost((void**)&hBuf[s], bytes) != cudaSuccess) return nullptr;
     acquired = s;
     return dBuf[s];
 }
 
-cudaError_t FramePipe::submit(cudaStream_t solverStream, float maxVel2, float dt) {
+float* FramePipe::meta_slot() { return acquired >= 0 ? dMeta + 2 * acquired : nullptr; }
+
+cudaError_t FramePipe::submit(cudaStream_t solverStream, float maxVel2, float dt, bool fromDevice) {
     if (acquired < 0) return cudaErrorInvalidValue;
     const int s = acquired;
     acquired = -1;
+    const size_t bytes = (size_t)n * sizeof(VfdParticleSimple);
+    HostBuf dst = take_buffer();
     cudaError_t e;
+    if (!dst.pinned && !hBuf[s] && (e = cudaMallocHost((void**)&hBuf[s], bytes ? bytes : 1)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(exported[s], solverStream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(copyStream, exported[s], 0)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(hBuf[s], dBuf[s], (size_t)n * sizeof(VfdParticleSimple), cudaMemcpyDeviceToHost, copyStream)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(dst.pinned ? dst.p : hBuf[s], dBuf[s], bytes, cudaMemcpyDeviceToHost, copyStream)) != cudaSuccess) return e;
+    if (fromDevice && (e = cudaMemcpyAsync(hMeta + 2 * s, dMeta + 2 * s, 2 * sizeof(float), cudaMemcpyDeviceToHost, copyStream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(copied[s], copyStream)) != cudaSuccess) return e;
-    bytesCopied += (uint64_t)n * sizeof(VfdParticleSimple);
+    bytesCopied += (uint64_t)bytes;
     {
         std::lock_guard<std::mutex> g(m);
         busy[s] = true;
-        jobs.push_back(Job{ s, maxVel2, dt });
+        jobs.push_back(Job{ s, dst, fromDevice, maxVel2, dt });
         inFlight++;
     }
     cvJob.notify_one();
@@ -98,9 +147,10 @@ void FramePipe::worker_main() {
         }
         Frame f;
         f.count = n; f.maxVel2 = j.maxVel2; f.dt = j.dt;
-        f.data.reset(new VfdParticleSimple[n ? n : 1u]);          // uninitialised: written once, below
+        f.data = j.dst;
         const cudaError_t e = cudaEventSynchronize(copied[j.slot]);
-        if (e == cudaSuccess) memcpy(f.data.get(), hBuf[j.slot], (size_t)n * sizeof(VfdParticleSimple));
+        if (e == cudaSuccess && !j.dst.pinned) memcpy(f.data.p, hBuf[j.slot], (size_t)n * sizeof(VfdParticleSimple));
+        if (e == cudaSuccess && j.metaFromDevice) { f.maxVel2 = hMeta[2 * j.slot]; f.dt = hMeta[2 * j.slot + 1]; }
         {
             std::lock_guard<std::mutex> g(m);
             if (e != cudaSuccess && asyncError == cudaSuccess) asyncError = e;
@@ -123,6 +173,7 @@ cudaError_t FramePipe::drain() {
 void FramePipe::clear() {
     drain();
     std::lock_guard<std::mutex> g(m);
+    for (Frame& f : frames) pool.push_back(f.data);     // the storage is kept for the next bake
     frames.clear();
 }
 
@@ -135,7 +186,7 @@ bool FramePipe::read(uint32_t index, VfdParticleSimple* out, float* maxVel2, flo
     std::lock_guard<std::mutex> g(m);
     if (index >= frames.size()) return false;
     const Frame& f = frames[index];
-    if (out) memcpy(out, f.data.get(), f.count * sizeof(VfdParticleSimple));
+    if (out) memcpy(out, f.data.p, f.count * sizeof(VfdParticleSimple));
     if (maxVel2) *maxVel2 = f.maxVel2;
     if (dt) *dt = f.dt;
     return true;

@@ -6,12 +6,15 @@
 // (ParticleBuffer/DFSPHParticleBuffer.cu:26-33, format DFSPHParticleSimple, 36 B/particle, original
 // particle order).
 //
-// Here a captured frame flows through a ring of SLOTS (device buffer, pinned host buffer) pairs:
-//   solver stream : k_export_frame -> dBuf[slot]                           (record `exported`)
-//   copy stream   : wait `exported`; D2H dBuf[slot] -> hBuf[slot] (pinned)  (record `copied`)
-//   host worker   : wait `copied`; copy hBuf[slot] into the frame's own storage; publish; free the slot
-// so the solver stream never waits for PCIe or for the host: the next step's kernels run while the
-// previous frame drains.  Back-pressure: capture() blocks only when all SLOTS are still in flight.
+// Here a captured frame flows through a ring of SLOTS device buffers into the frame's own host storage:
+//   solver stream : k_export_frame -> dBuf[slot] (+ the frame's (MaxVelocityMagnitude, dt) -> dMeta[slot])   (record `exported`)
+//   copy stream   : wait `exported`; D2H dBuf[slot] -> the frame's storage                                    (record `copied`)
+//   host worker   : wait `copied`; publish the frame; free the slot
+// so the solver stream never waits for PCIe or for the host: the next step's kernels run while the previous frame
+// drains.  Frame storage is PINNED host memory taken from a pool that survives clear() — re-baking (the editor's
+// "Bake" after a parameter change) allocates nothing and the D2H copy lands where the frame will live, with no
+// host-side copy.  Beyond a pinned budget (VFD_FRAME_PINNED_MB, default 8192) frames fall back to pageable storage
+// filled by the worker from a pinned staging buffer.  Back-pressure: acquire() blocks only when all SLOTS are in flight.
 #pragma once
 #include "../../include/vfd_dfsph.h"
 #include <cuda_runtime.h>
@@ -25,8 +28,12 @@
 
 namespace vfd {
 
+struct HostBuf {
+    VfdParticleSimple* p = nullptr;
+    bool pinned = false;
+};
 struct Frame {
-    std::unique_ptr<VfdParticleSimple[]> data;
+    HostBuf data;
     size_t count = 0;
     float maxVel2 = 0.0f, dt = 0.0f;
 };
@@ -39,8 +46,11 @@ public:
     cudaError_t configure(int device, uint32_t n);
     // device buffer the next frame must be exported into (blocks while every slot is in flight)
     VfdParticleSimple* acquire();
-    // the export kernel has been enqueued on `solverStream` into the buffer returned by acquire()
-    cudaError_t submit(cudaStream_t solverStream, float maxVel2, float dt);
+    // device slot for the frame's two scalars (float[2]: MaxVelocityMagnitude, dt) of the buffer returned by acquire()
+    float* meta_slot();
+    // the export kernel has been enqueued on `solverStream` into the buffer returned by acquire(); fromDevice: the
+    // frame's scalars are read from meta_slot() (written by the export kernel), else the host values are used
+    cudaError_t submit(cudaStream_t solverStream, float maxVel2, float dt, bool fromDevice = false);
     // wait until every submitted frame is published; returns the first asynchronous error, if any
     cudaError_t drain();
     void clear();                       // drain + drop all published frames
@@ -50,13 +60,19 @@ public:
     uint64_t bytesCopied = 0;
 
 private:
-    struct Job { int slot; float maxVel2, dt; };
+    struct Job { int slot; HostBuf dst; bool metaFromDevice; float maxVel2, dt; };
+    HostBuf take_buffer();
+    void release_pool();
     void worker_main();
     void stop_worker();
     int device = -1;
     uint32_t n = 0;
     VfdParticleSimple* dBuf[SLOTS] = {};
-    VfdParticleSimple* hBuf[SLOTS] = {};
+    VfdParticleSimple* hBuf[SLOTS] = {};          // pinned staging, only for frames in pageable storage
+    float* dMeta = nullptr;                         // SLOTS x float[2]
+    float* hMeta = nullptr;                         // pinned mirror
+    std::vector<HostBuf> pool;                      // free frame buffers (n particles each)
+    size_t pinnedBytes = 0, pinnedBudget = 0;
     cudaEvent_t exported[SLOTS] = {}, copied[SLOTS] = {};
     cudaStream_t copyStream = nullptr;
     bool busy[SLOTS] = {};

@@ -75,8 +75,9 @@ __global__ void k_pack_posvel(uint32_t n, const float* __restrict__ pos, const f
 }
 
 // K15: ConvertParticlesToBuffer (DFSPHKernels.cu:6-22), written in original particle order
-__global__ void k_export_frame(Params P, Arrays A, VfdParticleSimple* __restrict__ out) {
+__global__ void k_export_frame(Params P, Arrays A, VfdParticleSimple* __restrict__ out, const DevState* __restrict__ S, float* __restrict__ meta) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0 && meta) { meta[0] = S->vmax2; meta[1] = S->dt; }     // DFSPHParticleFrame::MaxVelocityMagnitude, CurrentTimeStep
     if (p >= P.n) return;
     const float4 x = A.pos[p], v = A.vel[p], a = A.acc[p];
     VfdParticleSimple q;
@@ -657,8 +658,18 @@ int Solver::step() {
     stepsIssued++;
     if (prof.enabled) { CK(cudaStreamSynchronize(stream)); prof.drain(); }
 
-    // 11. frame capture (:148-167) — needs the accumulated frame time on the host
-    if (frameIndexHost < desc.FrameCount || T) {
+    // 11. frame capture (:148-167).  FrameLength <= 0: every step is a frame, so there is nothing to ask the device —
+    // the frame's scalars travel with it and the host keeps queueing the next step (debug info is refreshed when the
+    // bake ends).  Otherwise the accumulated frame time is needed on the host.
+    if (frameIndexHost < desc.FrameCount && desc.FrameLength <= 0.0f && !T && state == VFD_STATE_SIMULATING) {
+        VfdParticleSimple* d = pipe.acquire();
+        if (!d) { cudaGetLastError(); return fail(VFD_E_CUDA, "frame capture: cannot allocate the frame ring buffers"); }
+        k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d, dState, pipe.meta_slot());
+        launches += 1;
+        CK(pipe.submit(stream, 0.0f, 0.0f, true));
+        frameTimeHost = 0.0f;
+        frameIndexHost++;
+    } else if (frameIndexHost < desc.FrameCount || T) {
         DevState s;
         int rc = read_state(s);
         if (rc) return rc;
@@ -699,7 +710,7 @@ int Solver::capture_frame(const DevState& s) {
     // asynchronous pipe (copy stream + host worker): the next step does not wait for PCIe or for the host copy.
     VfdParticleSimple* d = pipe.acquire();
     if (!d) { cudaGetLastError(); return fail(VFD_E_CUDA, "frame capture: cannot allocate the frame ring buffers"); }
-    k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d);
+    k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d, dState, nullptr);
     launches += 1;
     CK(pipe.submit(stream, s.vmax2, s.dt));
     frameTimeHost = 0.0f;              // FrameTime = 0 (:164)
@@ -719,6 +730,12 @@ int Solver::simulate() {
         if (rc) { state = VFD_STATE_NONE; return rc; }
     }
     CK(pipe.drain());                  // every baked frame is in the host cache when Simulate() returns
+    rc = sync_debug();                 // also surfaces device-side error flags of the steps that ran unobserved
+    if (rc) { state = VFD_STATE_NONE; return rc; }
+    {
+        std::lock_guard<std::mutex> g(dbgMutex);
+        debug.FrameIndex = frameIndexHost;
+    }
     state = VFD_STATE_READY;
     return VFD_OK;
 }
@@ -801,7 +818,7 @@ int Solver::get_current_frame(VfdParticleSimple* out) {
     if (info.ParticleCount == 0) return VFD_OK;
     if (!dFrame) CK(cudaMalloc(&dFrame, (size_t)info.ParticleCount * sizeof(VfdParticleSimple)));
     refresh_params();
-    k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dFrame);
+    k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dFrame, dState, nullptr);
     launches += 1;
     CK(cudaMemcpyAsync(out, dFrame, (size_t)info.ParticleCount * sizeof(VfdParticleSimple), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
