@@ -385,6 +385,14 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_arrive(unsigned long long* b) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(b)) : "memory");
 }
+// bulk (TMA) copy global -> shared of `bytes` (a multiple of 16, both addresses 16-byte aligned), completing on the mbarrier
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
 // fire-and-forget prefetch of a contiguous byte range into L2 (16-byte granularity; the range is widened to it)
 __device__ __forceinline__ void l2_prefetch(const void* base, size_t byteBegin, size_t byteEnd) {
     const size_t a = byteBegin & ~(size_t)15, e = (byteEnd + 15) & ~(size_t)15;
@@ -520,22 +528,45 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
             // the right.  Lane j first fetches the seven table entries of the warp's j-th row (one shared-memory round
             // for all rows), the loop then gets them by shuffle: no dependent shared-memory load per row.
             constexpr int ROWS = 36 / PIPE_PRODUCER_WARPS;
+            // bulk (TMA) copies measured equal to LDGSTS for the two-payload passes and 2-4 % faster for the one-payload ones;
+            // VFD_TUNE7=1 flips the choice (A/B runs)
+            const bool bulk = (Op::NPAY == 1) != (op.P.tune[7] == 1);
+            if (bulk) {
+                // 16-byte payload arrays by bulk copy: lane 3r + q takes segment q of the warp's r-th row (one instruction per
+                // contiguous segment instead of one LDGSTS per particle, and full-width shared-memory writes)
+                if (lane < 3u * ROWS && !(PIPE_ABLATE & 4)) {
+                    const uint32_t r = lane / 3u, q = lane - 3u * r;
+                    const uint32_t c0 = (pw + r * PIPE_PRODUCER_WARPS) * 6u;
+                    const uint32_t cb = q == 0u ? c0 : (q == 1u ? c0 + 1u : c0 + 5u), ce = q == 0u ? c0 + 1u : (q == 1u ? c0 + 5u : c0 + 6u);
+                    const uint32_t lb = H.local[cb], le = ce < HALO_CELLS ? H.local[ce] : total, g = H.cellG[cb];
+                    const uint32_t bytes = (le - lb) * 16u;
+                    if (bytes) {
+                        mbar_expect_tx(&ps.full[s], BBYTES == 16 ? 2u * bytes : bytes);
+                        bulk_copy(sA + (size_t)lb * 16, gA + (size_t)g * 16, bytes, &ps.full[s]);
+                        if (BBYTES == 16) bulk_copy(sB + (size_t)lb * 16, gB + (size_t)g * 16, bytes, &ps.full[s]);
+                    }
+                }
+            }
             uint32_t rl[4] = { 0u, 0u, 0u, 0u }, rg[3] = { 0u, 0u, 0u };
-            if (lane < (uint32_t)ROWS) {
+            if ((!bulk || BBYTES == 4) && lane < (uint32_t)ROWS) {
                 const uint32_t c0 = (pw + lane * PIPE_PRODUCER_WARPS) * 6u;
                 rl[0] = H.local[c0]; rl[1] = H.local[c0 + 1]; rl[2] = H.local[c0 + 5]; rl[3] = (c0 + 6 < HALO_CELLS) ? H.local[c0 + 6] : total;
                 rg[0] = H.cellG[c0]; rg[1] = H.cellG[c0 + 1]; rg[2] = H.cellG[c0 + 5];
             }
-            #pragma unroll
-            for (int j = 0; j < ROWS; j++) {
-                const uint32_t lA = __shfl_sync(0xffffffffu, rl[0], j), lB = __shfl_sync(0xffffffffu, rl[1], j);
-                const uint32_t lC = __shfl_sync(0xffffffffu, rl[2], j), lE = __shfl_sync(0xffffffffu, rl[3], j);
-                const uint32_t g0 = __shfl_sync(0xffffffffu, rg[0], j), g1 = __shfl_sync(0xffffffffu, rg[1], j), g5 = __shfl_sync(0xffffffffu, rg[2], j);
-                if (!(PIPE_ABLATE & 4)) for (uint32_t l = lA + lane; l < lE; l += 32u) {
-                    const uint32_t g = l < lB ? g0 + (l - lA) : (l < lC ? g1 + (l - lB) : g5 + (l - lC));
-                    cp_async16(sA + (size_t)l * 16, gA + (size_t)g * 16);
-                    if (BBYTES == 16) cp_async16(sB + (size_t)l * 16, gB + (size_t)g * 16);
-                    if (BBYTES == 4) cp_async4(sB + (size_t)l * 4, gB + (size_t)g * 4);
+            if (!bulk || BBYTES == 4) {
+                #pragma unroll
+                for (int j = 0; j < ROWS; j++) {
+                    const uint32_t lA = __shfl_sync(0xffffffffu, rl[0], j), lB = __shfl_sync(0xffffffffu, rl[1], j);
+                    const uint32_t lC = __shfl_sync(0xffffffffu, rl[2], j), lE = __shfl_sync(0xffffffffu, rl[3], j);
+                    const uint32_t g0 = __shfl_sync(0xffffffffu, rg[0], j), g1 = __shfl_sync(0xffffffffu, rg[1], j), g5 = __shfl_sync(0xffffffffu, rg[2], j);
+                    if (!(PIPE_ABLATE & 4)) for (uint32_t l = lA + lane; l < lE; l += 32u) {
+                        const uint32_t g = l < lB ? g0 + (l - lA) : (l < lC ? g1 + (l - lB) : g5 + (l - lC));
+                        if (!bulk) {
+                            cp_async16(sA + (size_t)l * 16, gA + (size_t)g * 16);
+                            if (BBYTES == 16) cp_async16(sB + (size_t)l * 16, gB + (size_t)g * 16);
+                        }
+                        if (BBYTES == 4) cp_async4(sB + (size_t)l * 4, gB + (size_t)g * 4);
+                    }
                 }
             }
         }
