@@ -63,16 +63,16 @@ print(open(out).read())
 # optional: DRAM bytes per launch per bench.py kernel class (mean over the captured launches) -> profiles/ncu_traffic.json
 if len(sys.argv) > 4:
     import json
-    CLASS = [("k_visc_matvec_pipe<(bool)0>", "visc_matvec"), ("k_visc_matvec_pipe<(bool)1>", "visc_matvec0"), ("k_visc_update", "visc_update"),
+    CLASS = [("k_visc_matvec_pipe<0>", "visc_matvec"), ("k_visc_matvec_pipe<1>", "visc_matvec0"), ("k_visc_update", "visc_update"),
              ("k_visc_direction", "visc_direction"), ("k_visc_setup", "visc_setup"), ("k_density_factor", "density_factor"),
-             ("k_solve_iteration<(bool)1>", "div_solve"), ("k_solve_iteration<(bool)0>", "press_solve"),
-             ("k_source<(bool)1>", "div_source"), ("k_source<(bool)0>", "press_source"),
-             ("k_pressure_accel<(int)0>", "div_accel"), ("k_pressure_accel<(int)1>", "div_finish"),
-             ("k_pressure_accel<(int)2>", "press_accel"), ("k_pressure_accel<(int)3>", "press_finish"),
+             ("k_solve_iteration<1>", "div_solve"), ("k_solve_iteration<0>", "press_solve"),
+             ("k_source<1>", "div_source"), ("k_source<0>", "press_source"),
+             ("k_pressure_accel<0>", "div_accel"), ("k_pressure_accel<1>", "div_finish"),
+             ("k_pressure_accel<2>", "press_accel"), ("k_pressure_accel<3>", "press_finish"),
              ("k_st_classify", "st_classify"), ("k_st_smooth", "st_smooth"), ("k_build_list", "search_build_list")]
     acc = {}
     for r in data:
-        name = r[ix["Kernel Name"]]
+        name = r[ix["Kernel Name"]].replace("(bool)", "").replace("(int)", "")
         rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
         if rd is None or wr is None:
             continue
