@@ -1,0 +1,199 @@
+"""GPU parity and invariants beyond the 1 000-particle fixtures: scenes large enough to span many tiles, CTAs and
+pipeline stages (the dynamic tile queue, the payload ring's wrap-around, the per-tile reduction records), checked
+
+* against the LIVE oracle (oracle/_ref/libvfd_ref_cpu.so: the reference's own solver sources on the host cores; it
+  travels to the GPU box) on 27 000 particles (BASELINE.json config 1's size): one step from an evolved state, and a
+  100-step trajectory;
+* through properties that do not need the oracle at sizes it would take minutes for: bit-reproducibility, neighbour
+  symmetry, frames in original particle order.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+R, D, H = 0.025, 0.05, 0.1
+
+
+def scene(side, clearance=4):
+    from vfd_b200 import api
+    pos = api.block_positions(side, side, side, R, origin=(clearance * D, clearance * D, clearance * D))
+    rng = np.random.RandomState(11)
+    pos = (pos + rng.uniform(-0.2 * R, 0.2 * R, pos.shape)).astype(np.float32)      # no pair exactly at the support radius
+    box = ((0.0, 0.0, 0.0), ((side + 2 * clearance + 8) * D, (side + 2 * clearance + 4) * D, (side + 2 * clearance) * D))
+    ext = [b - a + 2 * (8 * H - R) for a, b in zip(*box)]
+    res = tuple(min(64, max(8, int(np.ceil(e / (4 * H))))) for e in ext)
+    return pos, box, res
+
+
+PINNED = dict(MinPressureSolverIterations=2, MaxPressureSolverIterations=2, MinDivergenceSolverIterations=2, MaxDivergenceSolverIterations=2)
+CONFIGS = {
+    "dfsph": dict(EnableViscositySolver=0, EnableSurfaceTensionSolver=0, **PINNED),
+    "full": dict(CSDFix=24, **PINNED),
+}
+
+
+def make_pair(cfg, side):
+    """Our solver and the reference on the same scene (the reference computes the volume map; ours takes it flattened)."""
+    from oracle import refsim
+    from vfd_b200 import api
+    if not refsim.available("cpu"):
+        pytest.skip("oracle/_ref/libvfd_ref_cpu.so not built")
+    pos, box, res = scene(side)
+    with refsim.quiet_stdout():
+        ref = refsim.RefSim(refsim.Desc(**CONFIGS[cfg]))
+        ref.set_particles(pos)
+        ref.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
+        ref.commit_bodies()
+        m = ref.volume_map(0)
+    sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(FrameCount=0, **CONFIGS[cfg]))
+    sim.set_option(api.VFD_OPT_SEARCH_FMA, 0)
+    sim.SetFluidObjects([api.FluidObject(pos)])
+    sim.SetRigidBodies([api.VolumeMap(m["domain_min"], m["domain_max"], m["resolution"], m["cell_size"], m["cell_size_inv"], m["field_count"],
+                                      m["node_count"], m["cell_count"], m["cell_map_count"], m["nodes"], m["cells"], m["cell_map"])])
+    return sim, ref, pos
+
+
+@pytest.mark.parametrize("cfg", ["dfsph", "full"])
+def test_one_step_vs_live_oracle_27k(cfg, lib_built):
+    from oracle import refsim
+    sim, ref, pos = make_pair(cfg, 30)
+    sim.steps(40)                                   # evolve on the GPU: contact with the floor, non-trivial neighbourhoods
+    sim.synchronize()
+    state = sim.particles()
+    info = sim.GetInfo()
+    with refsim.quiet_stdout():
+        ref.set_particles_full(state)
+        ref.set_time_step(info.TimeStepSize)
+        ref.set_st_state(int(info.SurfaceTensionSampleCount), float(info.MonteCarloFactor))
+        ref.step(1)
+        # the reference's own reproducibility on this very step: its neighbour order and reduction order are not fixed
+        # (thrust on OpenMP threads vs one thread here; atomics and thrust reductions on a GPU): SURVEY.md Appendix E
+        ref2 = ref.particles()
+        ref.L.ref_set_serial(1)
+        ref.set_particles_full(state)
+        ref.set_time_step(info.TimeStepSize)
+        ref.set_st_state(int(info.SurfaceTensionSampleCount), float(info.MonteCarloFactor))
+        ref.step(1)
+        ref3 = ref.particles()
+        ref.L.ref_set_serial(0)
+    noise = parity.field_errors(ref3, ref2)
+    print("\n[%s] the reference against itself (threads vs serial)\n%s" % (cfg, parity.format_errors(noise)))
+    sim.OnUpdate()
+    out = sim.particles()
+    mism = parity.neighbor_mismatches(sim.neighbors(), ref.neighbors())
+    assert not mism, "neighbour sets differ for %d of %d particles, e.g. %s" % (len(mism), len(out), mism[:5])
+    errs = parity.field_errors(out, ref3)
+    tol = {f: max(1.0e-5, 3.0 * float(noise[f][0])) for f in errs}
+    print("\n[%s, %d particles] one step vs the live oracle\n%s" % (cfg, len(out), parity.format_errors(errs)))
+    bad = parity.beyond_tolerance(errs, tol, out, ref3)
+    assert not bad, "fields beyond tolerance %s:\n%s" % ({k: "%.1e" % tol[k] for k in bad}, parity.format_errors(bad))
+
+
+def test_trajectory_100_steps_vs_live_oracle(lib_built):
+    """100 steps from the same initial lattice (DFSPH, pinned iteration counts, 8 000 particles dropped onto the floor).
+    A particle system amplifies rounding differences exponentially, and the reference's own arithmetic is not
+    reproducible (reduction and neighbour order): the yardstick is therefore the reference against itself (OpenMP threads
+    vs one thread).  Stated tolerance: the mean displacement between our trajectory and the reference's stays within 3x
+    the reference's own mean self-displacement (or 1 % of the particle diameter if that is larger), and the bulk
+    quantities — centre of mass and the extent of the fluid — within 3x the reference's own deviation (floors: 5 % and
+    25 % of the particle diameter)."""
+    from oracle import refsim
+    sim, ref, pos = make_pair("dfsph", 20)
+    with refsim.quiet_stdout():
+        ref.step(100)
+        a = ref.particles()["Position"].astype(np.float64)
+        ref2 = refsim.RefSim(refsim.Desc(**CONFIGS["dfsph"]), serial=True)
+        p0, box, res = scene(20)
+        ref2.set_particles(p0)
+        ref2.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
+        ref2.commit_bodies()
+        ref2.step(100)
+        a2 = ref2.particles()["Position"].astype(np.float64)
+        ref2.L.ref_set_serial(0)
+    sim.steps(100)
+    sim.synchronize()
+    b = sim.particles()["Position"].astype(np.float64)
+    d = np.sqrt(((a - b) ** 2).sum(axis=1)) / D
+    dself = np.sqrt(((a - a2) ** 2).sum(axis=1)) / D
+    print("\n100-step trajectory, %d particles: displacement vs the oracle mean %.3e d, 99%% %.3e d, max %.3e d; the oracle against itself "
+          "mean %.3e d, 99%% %.3e d, max %.3e d" % (len(d), d.mean(), np.percentile(d, 99), d.max(), dself.mean(), np.percentile(dself, 99), dself.max()))
+    com, com_self = np.abs(a.mean(axis=0) - b.mean(axis=0)).max() / D, np.abs(a.mean(axis=0) - a2.mean(axis=0)).max() / D
+    ext, ext_self = np.abs(a.max(axis=0) - b.max(axis=0)).max() / D, np.abs(a.max(axis=0) - a2.max(axis=0)).max() / D
+    print("centre of mass %.3e d (oracle vs itself %.3e d), extent %.3e d (%.3e d)" % (com, com_self, ext, ext_self))
+    assert d.mean() <= max(3.0 * dself.mean(), 0.01)
+    assert com <= max(3.0 * com_self, 0.05), (com, com_self)
+    assert ext <= max(3.0 * ext_self, 0.25), (ext, ext_self)
+
+
+def test_runs_are_bit_reproducible_and_neighbours_symmetric_200k(lib_built):
+    from vfd_b200 import api
+    pos, box, res = scene(58)
+    vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R)
+    states = []
+    for _ in range(2):
+        sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(FrameCount=0, **CONFIGS["full"]))
+        sim.SetFluidObjects([api.FluidObject(pos)])
+        sim.SetRigidBodies([vm])
+        sim.steps(30)
+        sim.synchronize()
+        states.append(sim.particles())
+        if len(states) == 2:
+            counts, offsets, ids = sim.neighbors()
+        else:
+            sim.close()
+    for f in parity.ALL_FIELDS:
+        assert np.array_equal(states[0][f].view(np.uint32), states[1][f].view(np.uint32)), "field %s differs between two identical runs" % f
+    # neighbour relation: symmetric, irreflexive, within the support radius, capped at 70
+    n = len(pos)
+    assert counts.max() <= 70
+    i = np.repeat(np.arange(n, dtype=np.int64), counts)
+    j = ids.astype(np.int64)
+    assert not np.any(i == j)
+    x = states[1]["Position"].astype(np.float32)
+    # positions moved after the list was built; the pairs were within h at search time: allow one CFL step (0.4 d)
+    dist = np.sqrt(((x[i] - x[j]) ** 2).sum(axis=1))
+    assert dist.max() < H + 0.8 * D
+    if counts.max() < 70:                              # the cap breaks symmetry by construction
+        fwd = np.unique(i * n + j)
+        bwd = np.unique(j * n + i)
+        assert np.array_equal(fwd, bwd), "the neighbour relation is not symmetric"
+    sim.close()
+
+
+def test_frames_come_back_in_original_particle_order(lib_built):
+    from vfd_b200 import api
+    pos, box, res = scene(30)
+    vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R)
+    sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(FrameCount=5, FrameLength=0.0, **CONFIGS["dfsph"]))
+    sim.SetFluidObjects([api.FluidObject(pos)])
+    sim.SetRigidBodies([vm])
+    sim.Simulate()
+    assert sim.GetFrameCount() == 5
+    last, vmax, dt = sim.GetFrame(4)
+    state = sim.particles()                            # original order as well
+    assert np.array_equal(np.asarray(last["Position"], np.float32), np.asarray(state["Position"], np.float32))
+    first, _, _ = sim.GetFrame(0)
+    # after one step of free fall every particle is still next to where it started: the order is the caller's
+    assert np.abs(np.asarray(first["Position"], np.float32) - pos).max() < 0.5 * D
+    assert dt > 0.0 and vmax >= 0.0
+    sim.close()
+
+
+def test_empty_and_tiny_scenes(lib_built):
+    from vfd_b200 import api
+    sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(FrameCount=0, **CONFIGS["full"]))
+    sim.SetFluidObjects([api.FluidObject(np.zeros((0, 3), np.float32))])
+    sim.OnUpdate()                                     # the reference returns at once (DFSPHImplementation.cu:65-67)
+    assert sim.GetParticleCount() == 0
+    sim.SetFluidObjects([api.FluidObject(np.array([[0.5, 0.5, 0.5]], np.float32))])
+    sim.steps(3)
+    sim.synchronize()
+    p = sim.particles()
+    counts, _, _ = sim.neighbors()
+    assert len(p) == 1 and counts[0] == 0 and np.isfinite(p["Position"]).all()
+    assert p["Position"][0][1] < 0.5                   # it falls
+    sim.close()
