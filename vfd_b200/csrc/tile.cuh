@@ -292,16 +292,18 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 #ifndef PIPE_CONSUMER_WARPS
 #define PIPE_CONSUMER_WARPS 16
 #endif
+#ifndef PIPE_PRODUCER_WARPS
 #define PIPE_PRODUCER_WARPS 4
+#endif
 #define PIPE_PRODUCER_THREADS (PIPE_PRODUCER_WARPS * 32)
 #define PIPE_CELLS_PER_THREAD ((HALO_CELLS + PIPE_PRODUCER_THREADS - 1) / PIPE_PRODUCER_THREADS)
 #define PIPE_CAP 2816          // largest halo box that is staged (larger ones take the exact global-memory path)
 #define PIPE_RING (2 * PIPE_CAP) // payload ring, in particles: two worst-case boxes, three to four typical ones (~1700)
 #ifndef PIPE_GATHER_WIDTH
-#define PIPE_GATHER_WIDTH 4    // payload gathers in flight per lane (1, 2 or 4)
+#define PIPE_GATHER_WIDTH 2    // payload gathers in flight per lane (1, 2 or 4)
 #endif
 #ifndef PIPE_LOOKAHEAD
-#define PIPE_LOOKAHEAD 3
+#define PIPE_LOOKAHEAD 4
 #endif                         // neighbour groups (of four) in flight per lane
 
 // Shape of a pass, chosen per kernel (every Op names one as Op::Cfg): consumer warps per CTA, neighbour groups in flight
@@ -311,7 +313,7 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 template<int CW_, int D_, int GW_> struct PipeCfg {
     static constexpr int CW = CW_, D = D_, GW = GW_, THREADS = (CW_ + PIPE_PRODUCER_WARPS) * 32;
 };
-using PipeCfgWide = PipeCfg<PIPE_CONSUMER_WARPS, PIPE_LOOKAHEAD, PIPE_GATHER_WIDTH>;   // 16 warps, 3 groups ahead, 4 gathers
+using PipeCfgWide = PipeCfg<PIPE_CONSUMER_WARPS, PIPE_LOOKAHEAD, PIPE_GATHER_WIDTH>;   // 16 warps, 4 groups ahead, 2 gathers (measured best of 3..6 x 1..4)
 using PipeCfgMany = PipeCfg<28, 2, 2>;
 
 __device__ __forceinline__ uint2 ldg_stream(const uint2* p) { return __ldg(p); }
