@@ -288,7 +288,9 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 #ifndef PIPE_ABLATE
 #define PIPE_ABLATE 0
 #endif
-#define PIPE_STAGES 4          // tiles in flight per CTA (header slots); their payloads share one ring of PIPE_RING particle slots
+#ifndef PIPE_STAGES
+#define PIPE_STAGES 4            // tiles in flight per CTA (header slots); their payloads share one ring of PIPE_RING particle slots
+#endif
 #ifndef PIPE_CONSUMER_WARPS
 #define PIPE_CONSUMER_WARPS 16
 #endif
@@ -314,7 +316,12 @@ template<int CW_, int D_, int GW_> struct PipeCfg {
     static constexpr int CW = CW_, D = D_, GW = GW_, THREADS = (CW_ + PIPE_PRODUCER_WARPS) * 32;
 };
 using PipeCfgWide = PipeCfg<PIPE_CONSUMER_WARPS, PIPE_LOOKAHEAD, PIPE_GATHER_WIDTH>;   // 16 warps, 4 groups ahead, 2 gathers (measured best of 3..6 x 1..4)
-using PipeCfgMany = PipeCfg<28, 2, 2>;
+#ifndef PIPE_MANY_CW
+#define PIPE_MANY_CW 28
+#define PIPE_MANY_D 2
+#define PIPE_MANY_GW 2
+#endif
+using PipeCfgMany = PipeCfg<PIPE_MANY_CW, PIPE_MANY_D, PIPE_MANY_GW>;
 
 __device__ __forceinline__ uint2 ldg_stream(const uint2* p) { return __ldg(p); }
 __device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldg(p); }
