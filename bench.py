@@ -68,9 +68,13 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
-    def __enter__(self):
+    def start(self):
+        """nvidia-smi takes ~0.1 s to deliver its first line: started before the warm-up so that it is streaming (one line per
+        100 ms) when the timed region begins."""
+        if self.proc is not None:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -80,26 +84,44 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def __enter__(self):
+        self.start()
+        self.t0 = time.perf_counter()
+        return self
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
         if self.proc:
             self.proc.terminate()
             self.t.join(timeout=2)
+            self.proc = None
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        """Samples taken inside the timed region; a region shorter than the sampling period borrows the samples of the half
+        second on either side (warm-up before, the event-bracketed pass after: the same kernels under the same load)."""
+        self.stop()
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        window = "timed region"
+        if not rows:
+            rows = [r for t, r in self.rows if t0 - 0.5 <= t <= t1 + 0.5]
+            window = "timed region +- 0.5 s (region shorter than the 100 ms sampling period)"
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def peaks():
@@ -299,6 +321,7 @@ def main():
     info = sim.GetInfo()
     settled_dt, settled_st = info.TimeStepSize, (info.SurfaceTensionSampleCount, info.MonteCarloFactor)
 
+    clk = ClockSampler(local).start()
     sim.steps(args.warmup)
     sim.synchronize()
     sim.launch_count(reset=True)
@@ -310,7 +333,7 @@ def main():
             sim.SetDescription(description(api.DFSPHSimulationDescription, MaxViscositySolverIterations=args.ncu_visc_it))
             sim.set_time_step(dt_now)
         torch.cuda.cudart().cudaProfilerStart()
-    with ClockSampler(local) as clk:
+    with clk:
         sim.record_event(0)
         for _ in range(args.steps):
             sim.OnUpdate()

@@ -86,13 +86,14 @@ def main(args, rank, local, world):
     dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     sim, n_global, bounds, hist = setup(args, rank, local, world, bench.description)
     sim.steps(args.settle)
+    clk = bench.ClockSampler(local).start()
     sim.steps(args.warmup)
     sim.synchronize()
     sim.launch_count(reset=True)
     stats0 = sim.comm_stats()
     dist.barrier()
     torch.cuda.synchronize()
-    with bench.ClockSampler(local) as clk:
+    with clk:
         sim.record_event(0)
         for _ in range(args.steps):
             sim.OnUpdate()
@@ -143,6 +144,7 @@ def main(args, rank, local, world):
             "e2e": None,                                   # end to end through host buffers is measured at N = 1 (bench.py)
         }
         print(json.dumps(out))
+    clk.stop()
     dist.barrier()
     dist.destroy_process_group()
     return 0
