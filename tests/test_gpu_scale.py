@@ -197,3 +197,33 @@ def test_empty_and_tiny_scenes(lib_built):
     assert len(p) == 1 and counts[0] == 0 and np.isfinite(p["Position"]).all()
     assert p["Position"][0][1] < 0.5                   # it falls
     sim.close()
+
+
+def test_box_volume_map_built_on_the_gpu_matches_the_reference(lib_built):
+    """SURVEY.md §8(f) N2 for the scenes this repo generates: the two-field volume map of an (inverted) box, integrated on the
+    GPU (csrc/volume_map.cu), against the reference's host precompute (RigidBody.cu:10-73 over SDF.cu and GaussQuadrature.cpp)
+    for the same box — same node numbering and cell table, distance field within 5e-5 (absolute, distances of order 1), volume field
+    within 1e-4 of its scale."""
+    from oracle import refsim
+    from vfd_b200 import api
+    if not refsim.available("cpu"):
+        pytest.skip("oracle/_ref/libvfd_ref_cpu.so not built")
+    box, res = ((0.0, 0.0, 0.0), (1.2, 0.9, 0.8)), (10, 8, 8)
+    with refsim.quiet_stdout():
+        ref = refsim.RefSim(refsim.Desc())
+        ref.set_particles(np.array([[0.5, 0.5, 0.4]], np.float32))
+        ref.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
+        ref.commit_bodies()
+        m = ref.volume_map(0)
+    g = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R)
+    assert (int(g.field_count), int(g.node_count), int(g.cell_count)) == (int(m["field_count"]), int(m["node_count"]), int(m["cell_count"]))
+    assert np.array_equal(np.asarray(g.resolution, np.uint32), np.asarray(m["resolution"], np.uint32))
+    assert np.allclose(np.asarray(g.domain_min), m["domain_min"], rtol=0, atol=1e-6) and np.allclose(np.asarray(g.domain_max), m["domain_max"], rtol=0, atol=1e-6)
+    assert np.array_equal(np.asarray(g.cells), m["cells"]) and np.array_equal(np.asarray(g.cell_map), m["cell_map"])
+    n = int(m["node_count"])
+    ours, theirs = np.asarray(g.nodes, np.float64).reshape(2, n), np.asarray(m["nodes"], np.float64).reshape(2, n)
+    finite = np.abs(theirs[0]) < 1e30
+    e0 = np.abs(ours[0] - theirs[0])[finite].max()
+    e1 = np.abs(ours[1] - theirs[1]).max() / max(np.abs(theirs[1]).max(), 1e-30)
+    print("\nbox volume map %s nodes: distance field max abs err %.2e, volume field max err %.2e of scale %.3g" % (n, e0, e1, np.abs(theirs[1]).max()))
+    assert e0 < 5e-5 and e1 < 1e-4          # distances of order 1: the reference goes through a triangle mesh and fp32 point-triangle distances
