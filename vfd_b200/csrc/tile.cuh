@@ -5,21 +5,20 @@
 // inside the tile).  A tile's particles therefore form ONE contiguous range of every SoA array,
 // and every neighbour of a tile's particle lies in the 6x6x6-cell "halo box" around it.
 //
-// A tile pass is executed by one CTA per tile:
-//   1. the 216 halo cells' particle ranges are read from the cell table and prefix-summed in
-//      shared memory, which defines a tile-LOCAL index space (box order: hz, hy, hx; the three
-//      x-adjacent cells of a stencil row are contiguous in it);
-//   2. the payload the pass gathers per neighbour (position, plus kappa / velocity / pressure
-//      acceleration / PCG direction ...) is staged ONCE for all halo particles from HBM/L2 into
-//      shared memory with coalesced loads;
-//   3. each thread owns one particle of the tile and streams its neighbour list — 16-bit tile-local
-//      indices in a warp-blocked ELL layout, so a warp reads one 64-B line per neighbour slot, four slots
-//      ahead of their use — gathering payloads from shared memory instead of through L1/L2.
-// Per pass and particle HBM sees: own fields once + 2 B per neighbour; neighbour fields never.
+// A tile pass is executed by persistent CTAs (one per SM) as an asynchronous pipeline (pipe_pass below):
+//   1. producer warps draw tiles from a queue, read the 216 halo cells' particle ranges from the cell table and prefix-sum
+//      them, which defines a tile-LOCAL index space (box order: hz, hy, hx; the x-adjacent cells of a stencil row are
+//      contiguous in it);
+//   2. they copy the payload the pass gathers per neighbour (position, plus kappa / velocity / pressure acceleration / PCG
+//      direction ...) ONCE for all halo particles from HBM/L2 into a shared-memory ring (cp.async or bulk copies), several
+//      tiles ahead of the consumers;
+//   3. each consumer thread owns one particle of the tile and streams its neighbour list — 16-bit tile-local indices in a
+//      warp-blocked ELL layout, so a warp reads one 256-B block per four neighbour slots, several groups ahead of their
+//      use — and the per-pair coefficient stream next to it, gathering payloads from shared memory instead of through L1/L2.
+// Per pass and particle HBM sees: own fields once + 2 B (index) + 4 B (coefficient) per neighbour; neighbour fields never.
 //
-// If a halo box holds more particles than the staging buffer (pathological clumping), the pass
-// falls back to translating local indices to global ones (binary search in the 217-entry table)
-// and gathers from global memory: slow, but exact.
+// If a halo box holds more particles than PIPE_CAP (pathological clumping), the pass falls back to translating local
+// indices to global ones (binary search in the 217-entry table) and gathers from global memory: slow, but exact.
 #pragma once
 #include "solver.h"
 
@@ -162,77 +161,22 @@ template<bool STAGED, class Op> struct TileAcc {
     __device__ __forceinline__ float4 operator()(uint32_t L) const { return STAGED ? sA[L] : op.loadA(tile_local_to_global(sh, L)); }
 };
 
-// ---- the pass driver --------------------------------------------------------------------------------
-// One thread per particle of the tile.  Two kinds of Op:
-//  * pair ops (Op::CUSTOM == false): the driver owns the neighbour loop.  Neighbours are consumed in groups of four:
-//    the next group's list word (and coefficient word) is in flight while the current group's four payloads are
-//    gathered from shared memory back to back (no branch between them: the loads overlap) and accumulated in
-//    list order.  Only the last, partial group of a particle takes the slot-by-slot path.
-//       NPAY (1|2), NOWN, NSUM, COEF (0 none, 1 read, 2 write)
-//       float4 loadA(g), loadB(g)                      staged payload of particle g
-//       void load_own(p, float (&own)[NOWN])
-//       void pair(const float (&own)[NOWN], float4 a, float4 b, float& coef, float (&acc)[NSUM])
-//       void finish(p, m, const float (&own)[NOWN], const float (&sum)[NSUM])
-//  * custom ops (Op::CUSTOM == true): NPAY == 1, void particle(p, valid, acc) with acc(L) -> float4; warp-convergent call.
+// ---- the barrier-phased pass driver ------------------------------------------------------------------
+// setup | stage | compute as phases of one CTA separated by __syncthreads: what every neighbour pass used before the
+// asynchronous pipeline below (profiles/r01_ncu_full_step_before_pipeline.txt).  The neighbour-list build still runs on
+// it — that kernel is bound by instruction issue, not by latency, and wants the 48 warps per SM it gets here.
+// Ops are custom: NPAY == 1, float4 loadA(g), void particle(p, valid, acc) with acc(L) -> float4, called by all 32 lanes.
 template<class Op, bool STAGED>
 __device__ __forceinline__ void tile_particles(const TileInfo& t, const TileShared& sh, const Arrays& A,
                                                const float4* __restrict__ sA, const float4* __restrict__ sB, Op& op) {
+    static_assert(Op::CUSTOM, "pair ops run on the pipeline (pipe_pass)");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nBatch = (t.end - t.begin + 31u) >> 5;
     for (uint32_t b = warp; b < nBatch; b += TILE_WARPS) {
         const uint32_t p = t.begin + (b << 5) + lane;
-        if constexpr (Op::CUSTOM) {
-            // called by all 32 lanes (custom ops may cooperate across the warp); lanes past the tile's end pass valid = false
-            const TileAcc<STAGED, Op> acc{ sh, sA, op };
-            op.particle(p, p < t.end, acc);
-        } else {
-            if (p >= t.end) continue;
-            const uint32_t m = __ldg(A.cnt + p) & VFD_COUNT_MASK;
-            float own[Op::NOWN];
-            op.load_own(p, own);
-            float acc[Op::NSUM];
-            #pragma unroll
-            for (int s = 0; s < Op::NSUM; s++) acc[s] = 0.0f;
-            const uint2* __restrict__ col = ell_list(A.list16, p);
-            float4* __restrict__ ccol = reinterpret_cast<float4*>(A.coef) + ell_base(p);
-            const uint32_t nG = (m + 3u) >> 2;
-            uint2 wq = make_uint2(0u, 0u);
-            float4 cq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (nG) { wq = col[0]; if (Op::COEF == 1) cq = ccol[0]; }
-            for (uint32_t g = 0; g < nG; g++) {
-                uint2 wn = make_uint2(0u, 0u);
-                float4 cn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (g + 1u < nG) { wn = col[(size_t)(g + 1u) * 32]; if (Op::COEF == 1) cn = ccol[(size_t)(g + 1u) * 32]; }
-                uint32_t L[4];
-                ell_unpack(wq, L);
-                float c[4] = { cq.x, cq.y, cq.z, cq.w };
-                if (g * 4u + 4u <= m) {
-                    float4 pa[4], pb[4];
-                    #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        pb[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        if (STAGED) { pa[u] = sA[L[u]]; if (Op::NPAY > 1) pb[u] = sB[L[u]]; }
-                        else { const uint32_t gi = tile_local_to_global(sh, L[u]); pa[u] = op.loadA(gi); if (Op::NPAY > 1) pb[u] = op.loadB(gi); }
-                    }
-                    #pragma unroll
-                    for (int u = 0; u < 4; u++) op.pair(own, pa[u], pb[u], c[u], acc);
-                } else {
-                    #pragma unroll
-                    for (int u = 0; u < 3; u++) {                    // a partial group holds one to three neighbours
-                        if (g * 4u + (uint32_t)u < m) {
-                            float4 xa, xb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                            if (STAGED) { xa = sA[L[u]]; if (Op::NPAY > 1) xb = sB[L[u]]; }
-                            else { const uint32_t gi = tile_local_to_global(sh, L[u]); xa = op.loadA(gi); if (Op::NPAY > 1) xb = op.loadB(gi); }
-                            op.pair(own, xa, xb, c[u], acc);
-                        } else c[u] = 0.0f;
-                    }
-                    c[3] = 0.0f;
-                }
-                if (Op::COEF == 2) ccol[(size_t)g * 32] = make_float4(c[0], c[1], c[2], c[3]);
-                wq = wn; cq = cn;
-            }
-            op.finish(p, m, own, acc);
-        }
+        // lanes past the tile's end pass valid = false
+        const TileAcc<STAGED, Op> acc{ sh, sA, op };
+        op.particle(p, p < t.end, acc);
     }
 }
 
