@@ -28,7 +28,7 @@ GLM = os.path.join(REF, "VFD", "VFD", "ThirdParty", "glm")
 TINYOBJ = os.path.join(REF, "VFD", "ThirdParty", "tinyobjloader")
 OUT = os.path.join(HERE, "_ref")
 
-# the solver path; FluidObject/ParticleSampler are replaced by oracle/shim
+# the solver path; FluidObject is replaced by oracle/shim (raw positions)
 FILES = [
     "Simulation/DFSPH/DFSPHImplementation.cu",
     "Simulation/DFSPH/DFSPHKernels.cu",
@@ -38,6 +38,7 @@ FILES = [
     "Simulation/DFSPH/ParticleBuffer/DFSPHParticleBuffer.cu",
     "Utility/SDF/SDF.cu",
     "Utility/SDF/MeshDistance.cpp",
+    "Utility/Sampler/ParticleSampler.cpp",       # scene preparation next to the path: oracle of vfd_b200/scene_io.py
     "Renderer/Mesh/EdgeMesh.cpp",
     "Core/Structures/BoundingSphere.cpp",
     "Core/Structures/AxisAlignedBoundingBox.cpp",

@@ -25,6 +25,7 @@
 #define protected public
 #include "Simulation/DFSPH/DFSPHImplementation.h"
 #include "Utility/SDF/SDF.cuh"
+#include "Utility/Sampler/ParticleSampler.h"
 #undef private
 #undef protected
 
@@ -152,6 +153,24 @@ void ref_add_box_body(RefSim* s, const float* bmin, const float* bmax, int inver
 }
 
 void ref_commit_bodies(RefSim* s) { s->impl->SetRigidBodies(s->bodies); }
+
+// The reference's own fluid sampling (FluidObject::FluidObject, FluidObject.cpp:6-26: transform the mesh, then
+// ParticleSampler::SampleMeshVolume, ParticleSampler.cpp:7-91) on a raw triangle mesh.  Returns the number of samples;
+// writes at most `capacity` positions.
+uint32_t ref_sample_mesh_volume(const float* verts, uint32_t nv, const uint32_t* tris, uint32_t nt, const float* transform16,
+                                float radius, const uint32_t* res, int inverted, int mode, float* out, uint32_t capacity) {
+    std::vector<glm::vec3> v(nv);
+    std::vector<glm::uvec3> t(nt);
+    glm::mat4 T(1.0f);
+    if (transform16) memcpy(&T[0][0], transform16, 16 * sizeof(float));      // column-major like glm
+    for (uint32_t i = 0; i < nv; i++) v[i] = T * glm::vec4(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2], 1.0f);
+    for (uint32_t i = 0; i < nt; i++) t[i] = { tris[3 * i], tris[3 * i + 1], tris[3 * i + 2] };
+    const Ref<EdgeMesh> mesh = Ref<EdgeMesh>::Create(v, t);
+    const std::vector<glm::vec3> p = ParticleSampler::SampleMeshVolume(mesh, radius, glm::uvec3(res[0], res[1], res[2]), inverted != 0, (SampleMode)mode);
+    const uint32_t n = (uint32_t)p.size();
+    for (uint32_t i = 0; i < n && i < capacity; i++) { out[3 * i] = p[i].x; out[3 * i + 1] = p[i].y; out[3 * i + 2] = p[i].z; }
+    return n;
+}
 
 // Volume-map extraction = exactly what SDF::GetDeviceData flattens (SDF.cu:227-306).
 // sizes: [fieldCount, nodeCount, cellCount, cellMapCount, res.x, res.y, res.z]

@@ -104,6 +104,9 @@ def _load(kind):
     L.ref_get_neighbors.restype = u32
     L.ref_find_neighbors.argtypes = [vp]
     L.ref_get_boundary.argtypes = [vp, u32, vp, vp]
+    if hasattr(L, "ref_sample_mesh_volume"):
+        L.ref_sample_mesh_volume.restype = u32
+        L.ref_sample_mesh_volume.argtypes = [vp, u32, vp, u32, vp, f32, vp, C.c_int, C.c_int, vp, u32]
     L.ref_set_serial.argtypes = [C.c_int]
     L.ref_set_threads.argtypes = [C.c_int]
     L.ref_get_max_threads.restype = C.c_int
@@ -114,6 +117,24 @@ def _load(kind):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+BOX_VERTS = lambda a, b: np.array([[a[0], a[1], a[2]], [b[0], a[1], a[2]], [b[0], a[1], b[2]], [a[0], a[1], b[2]],
+                                    [a[0], b[1], a[2]], [b[0], b[1], a[2]], [b[0], b[1], b[2]], [a[0], b[1], b[2]]], np.float32)
+BOX_TRIS = np.array([[0, 1, 2], [0, 2, 3], [4, 7, 6], [4, 6, 5], [0, 3, 7], [0, 7, 4], [1, 5, 6], [1, 6, 2], [0, 4, 5], [0, 5, 1], [3, 2, 6], [3, 6, 7]], np.uint32)
+
+
+def sample_mesh_volume(verts, tris, radius, resolution=(20, 20, 20), inverted=False, mode=0, transform=None, kind="cpu"):
+    """The reference's FluidObject sampling (FluidObject.cpp:6-26 + ParticleSampler.cpp:7-91) of a raw triangle mesh."""
+    L = _load(kind)
+    v = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(tris, np.uint32).reshape(-1, 3)
+    r = np.ascontiguousarray(resolution, np.uint32)
+    T = None if transform is None else np.ascontiguousarray(np.asarray(transform, np.float32).T).reshape(16)   # row-major matrix -> glm columns
+    n = L.ref_sample_mesh_volume(_p(v), len(v), _p(t), len(t), None if T is None else _p(T), float(radius), _p(r), int(inverted), int(mode), None, 0)
+    out = np.zeros((max(n, 1), 3), np.float32)
+    L.ref_sample_mesh_volume(_p(v), len(v), _p(t), len(t), None if T is None else _p(T), float(radius), _p(r), int(inverted), int(mode), _p(out), n)
+    return out[:n]
 
 
 class quiet_stdout:

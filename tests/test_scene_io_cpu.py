@@ -1,0 +1,104 @@
+"""Host-side data formats next to the solver path: the scene reader against the reference's shipped
+scene, the box sampler against the reference's own `ParticleSampler` (through the oracle)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SCENE = "/root/reference/VFD/Resources/Scenes/New/DFSPH/default.json"
+
+
+def oracle():
+    sys.path.insert(0, ROOT)
+    from oracle import refsim
+    if not refsim.available("cpu"):
+        pytest.skip("oracle/_ref/libvfd_ref_cpu.so not built")
+    try:
+        refsim._load("cpu").ref_sample_mesh_volume
+    except AttributeError:
+        pytest.skip("oracle/_ref predates the sampler hook: rebuild with oracle/build_ref.py --force")
+    return refsim
+
+
+BOXES = [((0.1, 0.2, 0.3), (0.62, 0.71, 0.93)), ((-1.0, -0.1, -1.0), (1.0, 0.1, 1.0)), ((0.0, 0.0, 0.0), (0.33, 0.47, 0.21)),
+         ((0.13, 0.21, 0.34), (0.61, 0.72, 0.9))]
+
+
+@pytest.mark.parametrize("box", BOXES)
+def test_min_density_box_sampling_is_the_references(box):
+    from vfd_b200 import scene_io
+    refsim = oracle()
+    with refsim.quiet_stdout():
+        theirs = refsim.sample_mesh_volume(refsim.BOX_VERTS(*box), refsim.BOX_TRIS, 0.025, (20, 20, 20), False, scene_io.MIN_DENSITY)
+    ours = scene_io.sample_box_volume(box[0], box[1], 0.025, scene_io.MIN_DENSITY)
+    assert ours.shape == theirs.shape
+    assert np.array_equal(ours.view(np.uint32), theirs.view(np.uint32))          # same samples, same order, bit for bit
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("box", BOXES + [((0.13, 0.21, 0.34), (0.62, 0.71, 0.93))])
+def test_denser_modes_differ_only_on_the_surface(mode, box):
+    """In the denser modes lattice points lie ON the faces of the box, where the reference's answer is the sign of its
+    interpolated SDF (a 20^3 grid spanning the box AND the origin: errors up to ~2e-3 at edges).  Stated tolerance: the two
+    sample sets differ only in points within 2.5e-3 (a tenth of a particle radius) of the surface, and the common
+    samples come in the same order."""
+    from vfd_b200 import scene_io
+    refsim = oracle()
+    with refsim.quiet_stdout():
+        theirs = refsim.sample_mesh_volume(refsim.BOX_VERTS(*box), refsim.BOX_TRIS, 0.025, (20, 20, 20), False, mode)
+    ours = scene_io.sample_box_volume(box[0], box[1], 0.025, mode)
+    a = {tuple(p) for p in ours.view(np.uint32).tolist()}
+    b = {tuple(p) for p in theirs.view(np.uint32).tolist()}
+    diff = np.array(sorted(a ^ b), np.uint32).view(np.float32).reshape(-1, 3)
+    lo, hi = np.asarray(box[0], np.float32), np.asarray(box[1], np.float32)
+    if len(diff):
+        depth = np.minimum(diff - lo, hi - diff).min(axis=1)            # > 0 inside
+        assert np.abs(depth).max() <= 2.5e-3, "samples well inside/outside the box differ"
+    common = a & b
+    assert len(common) > 0.9 * len(b)
+    # the common samples come in the same order
+    ka = np.array([tuple(p) in common for p in ours.view(np.uint32).tolist()])
+    kb = np.array([tuple(p) in common for p in theirs.view(np.uint32).tolist()])
+    assert np.array_equal(ours[ka].view(np.uint32), theirs[kb].view(np.uint32))
+
+
+def test_reader_on_the_references_default_scene():
+    from vfd_b200 import scene_io
+    if not os.path.exists(REF_SCENE):
+        pytest.skip("reference not mounted")
+    s = scene_io.read_scene(REF_SCENE)
+    d = s["description"]
+    assert abs(d["TimeStepSize"] - 1e-3) < 1e-9 and d["FrameCount"] == 200 and abs(d["Viscosity"] - 10.0) < 1e-6
+    assert abs(d["ParticleRadius"] - 0.025) < 1e-8 and abs(d["Gravity"][1] + 9.81) < 1e-5 and d["CSD"] == 10000
+    assert len(s["rigid_bodies"]) == 1 and len(s["fluid_objects"]) == 1
+    rb, fo = s["rigid_bodies"][0], s["fluid_objects"][0]
+    assert rb["mesh"].endswith("Cube.obj") and rb["resolution"] == (20, 20, 20) and not rb["inverted"]
+    assert np.allclose(np.diag(rb["transform"]), [2.0, 0.2, 2.0, 1.0])
+    assert fo["mesh"].endswith("Cone.obj") and fo["sample_mode"] == 1 and abs(fo["transform"][1, 3] - 3.0) < 1e-6
+    lo, hi = scene_io.unit_cube_box(rb["transform"])
+    assert np.allclose(lo, [-2.0, -0.2, -2.0]) and np.allclose(hi, [2.0, 0.2, 2.0])
+    assert scene_io.unit_cube_box(fo["transform"]) is not None          # a rotation by 180 degrees keeps the box axis-aligned
+
+
+def test_scene_round_trip(tmp_path):
+    from vfd_b200 import scene_io
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = np.diag([0.5, 0.25, 0.5]); T[:3, 3] = [0.0, 1.0, 0.0]
+    F = np.eye(4, dtype=np.float32)
+    F[:3, :3] = np.diag([2.0, 0.1, 2.0])
+    desc = {"TimeStepSize": 0.001, "FrameCount": 10, "FrameLength": 0.0, "Viscosity": 5.0, "EnableSurfaceTensionSolver": True,
+            "ParticleRadius": 0.025, "Gravity": (0.0, -9.81, 0.0), "CSDFix": 16}
+    p = str(tmp_path / "scene.json")
+    scene_io.write_scene(p, desc,
+                         fluid_objects=[dict(mesh="Resources/Models/Cube.obj", transform=T, inverted=False, resolution=(20, 20, 20), sample_mode=0, velocity=(0.0, -1.0, 0.0))],
+                         rigid_bodies=[dict(mesh="Resources/Models/Cube.obj", transform=F, inverted=False, padding=0.0, resolution=(16, 8, 16))])
+    s = scene_io.read_scene(p)
+    assert s["description"]["FrameCount"] == 10 and abs(s["description"]["Viscosity"] - 5.0) < 1e-6 and s["description"]["Gravity"][1] == pytest.approx(-9.81)
+    assert len(s["fluid_objects"]) == 1 and len(s["rigid_bodies"]) == 1
+    assert np.allclose(s["fluid_objects"][0]["transform"], T) and s["fluid_objects"][0]["velocity"] == (0.0, -1.0, 0.0)
+    assert s["rigid_bodies"][0]["resolution"] == (16, 8, 16)
+    lo, hi = scene_io.unit_cube_box(s["fluid_objects"][0]["transform"])
+    pts = scene_io.sample_box_volume(lo, hi, 0.025)
+    assert len(pts) == 20 * 10 * 20 and pts.min() > -0.5 and np.all(pts[:, 1] > 0.75)
