@@ -1,9 +1,9 @@
-"""tools_ref_gpu.py — the reference's own CUDA solver (its sources compiled by `oracle/build_ref.py --gpu` for sm_100a, as
+"""tests/ref_gpu_timing.py — TEST INFRASTRUCTURE (a script, not collected by pytest): the reference's own CUDA solver (its sources compiled by `oracle/build_ref.py --gpu` for sm_100a, as
 shipped with --use_fast_math and in the IEEE variant) timed on the B200 on bench.py's workload: K steps of the settled
 1M-particle dam break.  It is the only pre-existing GPU implementation of the path: a reported number,
-recorded under profiles/, not part of bench.py.  Usage (GPU box): python tools_ref_gpu.py [steps] [side]"""
+recorded under profiles/, not part of bench.py.  Usage (GPU box): python tests/ref_gpu_timing.py [steps] [side]"""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import bench
