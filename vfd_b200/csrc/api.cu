@@ -6,7 +6,16 @@
 #include <new>
 
 using vfd::Solver;
-struct VfdDfsph { Solver s; };
+// Threading contract (include/vfd_dfsph.h): one mutating thread plus concurrent read-only getters, as the reference's editor
+// uses DFSPHSimulation (worker thread bakes, UI thread polls).  `call` is held by every mutating entry point for its whole
+// duration; a getter refreshes its snapshot from the device only if it can take the lock (no mutating call in flight),
+// otherwise it returns the last snapshot (kept under Solver::dbgMutex) and never touches the solver's stream.
+struct VfdDfsph { Solver s; std::mutex call; };
+#define LOCKED(h) std::lock_guard<std::mutex> callLock_((h)->call)
+static void refresh_if_idle(VfdDfsph* h) {
+    std::unique_lock<std::mutex> lk(h->call, std::try_to_lock);
+    if (lk.owns_lock() && h->s.state != VFD_STATE_SIMULATING) h->s.sync_debug();
+}
 
 static std::string g_createError;
 static std::mutex g_createMutex;
@@ -49,41 +58,47 @@ int vfd_dfsph_create(const VfdDfsphDescription* desc, int device, VfdDfsph** out
 void vfd_dfsph_destroy(VfdDfsph* h) { delete h; }
 
 const char* vfd_dfsph_last_error(const VfdDfsph* h) {
-    if (!h) return g_createError.c_str();
-    return h->s.lastError.c_str();
+    // a copy taken under the error mutex: the pointer stays valid (per calling thread) while another thread fails again
+    static thread_local std::string copy;
+    if (!h) { std::lock_guard<std::mutex> g(g_createMutex); copy = g_createError; return copy.c_str(); }
+    Solver& s = const_cast<VfdDfsph*>(h)->s;
+    std::lock_guard<std::mutex> g(s.errMutex);
+    copy = s.lastError;
+    return copy.c_str();
 }
 
-int vfd_dfsph_set_description(VfdDfsph* h, const VfdDfsphDescription* d) { GUARD(h); if (!d) return h->s.fail(VFD_E_INVALID, "null description"); TRY(h->s.set_description(*d)); }
+int vfd_dfsph_set_description(VfdDfsph* h, const VfdDfsphDescription* d) { GUARD(h); LOCKED(h); if (!d) return h->s.fail(VFD_E_INVALID, "null description"); TRY(h->s.set_description(*d)); }
 int vfd_dfsph_get_description(const VfdDfsph* h, VfdDfsphDescription* out) { GUARD(h); if (!out) return VFD_E_INVALID; *out = h->s.desc; return VFD_OK; }
 int vfd_dfsph_get_info(VfdDfsph* h, VfdDfsphInfo* out) {
     GUARD(h); if (!out) return h->s.fail(VFD_E_INVALID, "null output");
-    int rc = h->s.sync_debug(); if (rc) return rc;
+    refresh_if_idle(h);
+    std::lock_guard<std::mutex> g(h->s.dbgMutex);
     *out = h->s.info; return VFD_OK;
 }
 
-int vfd_dfsph_set_particles(VfdDfsph* h, const float* pos, const float* vel, uint32_t n) { GUARD(h); TRY(h->s.set_particles(pos, vel, n, false)); }
-int vfd_dfsph_set_particles_device(VfdDfsph* h, const float* pos, const float* vel, uint32_t n) { GUARD(h); TRY(h->s.set_particles(pos, vel, n, true)); }
-int vfd_dfsph_set_rigid_bodies(VfdDfsph* h, uint32_t count, const VfdVolumeMap* maps) { GUARD(h); TRY(h->s.set_rigid_bodies(count, maps)); }
+int vfd_dfsph_set_particles(VfdDfsph* h, const float* pos, const float* vel, uint32_t n) { GUARD(h); LOCKED(h); TRY(h->s.set_particles(pos, vel, n, false)); }
+int vfd_dfsph_set_particles_device(VfdDfsph* h, const float* pos, const float* vel, uint32_t n) { GUARD(h); LOCKED(h); TRY(h->s.set_particles(pos, vel, n, true)); }
+int vfd_dfsph_set_rigid_bodies(VfdDfsph* h, uint32_t count, const VfdVolumeMap* maps) { GUARD(h); LOCKED(h); TRY(h->s.set_rigid_bodies(count, maps)); }
 
-int vfd_dfsph_simulate(VfdDfsph* h) { GUARD(h); TRY(h->s.simulate()); }
-int vfd_dfsph_begin(VfdDfsph* h) { GUARD(h); TRY(h->s.begin()); }
-int vfd_dfsph_step(VfdDfsph* h) { GUARD(h); TRY(h->s.step()); }
+int vfd_dfsph_simulate(VfdDfsph* h) { GUARD(h); LOCKED(h); TRY(h->s.simulate()); }
+int vfd_dfsph_begin(VfdDfsph* h) { GUARD(h); LOCKED(h); TRY(h->s.begin()); }
+int vfd_dfsph_step(VfdDfsph* h) { GUARD(h); LOCKED(h); TRY(h->s.step()); }
 int vfd_dfsph_steps(VfdDfsph* h, uint32_t count) {
-    GUARD(h);
+    GUARD(h); LOCKED(h);
     try { for (uint32_t i = 0; i < count; i++) { int rc = h->s.step(); if (rc) return rc; } return VFD_OK; }
     catch (const std::exception& e) { return h->s.fail(VFD_E_INVALID, e.what()); }
 }
-int vfd_dfsph_synchronize(VfdDfsph* h) { GUARD(h); TRY(h->s.synchronize()); }
+int vfd_dfsph_synchronize(VfdDfsph* h) { GUARD(h); LOCKED(h); TRY(h->s.synchronize()); }
 
 int vfd_dfsph_get_state(const VfdDfsph* h) { return h ? h->s.state : VFD_STATE_NONE; }
 int vfd_dfsph_get_debug_info(VfdDfsph* h, VfdDfsphDebugInfo* out) {
     GUARD(h); if (!out) return h->s.fail(VFD_E_INVALID, "null output");
-    if (h->s.state != VFD_STATE_SIMULATING) { int rc = h->s.sync_debug(); if (rc) return rc; }   // while baking: last snapshot, as the reference's UI thread sees it
+    refresh_if_idle(h);                            // while a mutating call runs: the last snapshot, as the reference's UI thread sees it
     std::lock_guard<std::mutex> g(h->s.dbgMutex);
     *out = h->s.debug; return VFD_OK;
 }
-float vfd_dfsph_get_max_velocity_magnitude(VfdDfsph* h) { if (!h) return 0.0f; if (h->s.state != VFD_STATE_SIMULATING) h->s.sync_debug(); return h->s.maxVel2; }
-float vfd_dfsph_get_current_time_step_size(VfdDfsph* h) { if (!h) return 0.0f; if (h->s.state != VFD_STATE_SIMULATING) h->s.sync_debug(); return h->s.info.TimeStepSize; }
+float vfd_dfsph_get_max_velocity_magnitude(VfdDfsph* h) { if (!h) return 0.0f; refresh_if_idle(h); std::lock_guard<std::mutex> g(h->s.dbgMutex); return h->s.maxVel2; }
+float vfd_dfsph_get_current_time_step_size(VfdDfsph* h) { if (!h) return 0.0f; refresh_if_idle(h); std::lock_guard<std::mutex> g(h->s.dbgMutex); return h->s.info.TimeStepSize; }
 uint32_t vfd_dfsph_get_particle_count(const VfdDfsph* h) { return h ? h->s.info.ParticleCount : 0u; }
 float vfd_dfsph_get_particle_radius(const VfdDfsph* h) { return h ? h->s.info.ParticleRadius : 0.0f; }
 uint32_t vfd_dfsph_get_rigid_body_count(const VfdDfsph* h) { return h ? h->s.info.RigidBodyCount : 0u; }
@@ -99,20 +114,20 @@ int vfd_dfsph_get_frame(VfdDfsph* h, uint32_t index, VfdParticleSimple* out, flo
     }
     return h->s.fail(VFD_E_INVALID, "frame index out of range");
 }
-int vfd_dfsph_get_current_frame(VfdDfsph* h, VfdParticleSimple* out) { GUARD(h); TRY(h->s.get_current_frame(out)); }
+int vfd_dfsph_get_current_frame(VfdDfsph* h, VfdParticleSimple* out) { GUARD(h); LOCKED(h); TRY(h->s.get_current_frame(out)); }
 
 int vfd_dfsph_get_search_bytes(const VfdDfsph* h, uint64_t* bytes) { GUARD(h); if (!bytes) return VFD_E_INVALID; *bytes = h->s.searchBytes; return VFD_OK; }
-int vfd_dfsph_get_bounds(VfdDfsph* h, float bmin[3], float bmax[3]) { GUARD(h); TRY(h->s.get_bounds(bmin, bmax)); }
+int vfd_dfsph_get_bounds(VfdDfsph* h, float bmin[3], float bmax[3]) { GUARD(h); LOCKED(h); TRY(h->s.get_bounds(bmin, bmax)); }
 
-int vfd_dfsph_get_particles(VfdDfsph* h, VfdParticle* out) { GUARD(h); TRY(h->s.get_particles(out)); }
-int vfd_dfsph_set_particles_full(VfdDfsph* h, const VfdParticle* in) { GUARD(h); TRY(h->s.set_particles_full(in)); }
-int vfd_dfsph_set_time_step(VfdDfsph* h, float dt) { GUARD(h); if (!(dt > 0.0f)) return h->s.fail(VFD_E_INVALID, "time step must be positive"); TRY(h->s.set_time_step(dt)); }
-int vfd_dfsph_set_surface_tension_state(VfdDfsph* h, uint32_t sc, float mc) { GUARD(h); TRY(h->s.set_st_state(sc, mc)); }
-int vfd_dfsph_find_neighbors(VfdDfsph* h) { GUARD(h); TRY(h->s.search_only()); }
+int vfd_dfsph_get_particles(VfdDfsph* h, VfdParticle* out) { GUARD(h); LOCKED(h); TRY(h->s.get_particles(out)); }
+int vfd_dfsph_set_particles_full(VfdDfsph* h, const VfdParticle* in) { GUARD(h); LOCKED(h); TRY(h->s.set_particles_full(in)); }
+int vfd_dfsph_set_time_step(VfdDfsph* h, float dt) { GUARD(h); LOCKED(h); if (!(dt > 0.0f)) return h->s.fail(VFD_E_INVALID, "time step must be positive"); TRY(h->s.set_time_step(dt)); }
+int vfd_dfsph_set_surface_tension_state(VfdDfsph* h, uint32_t sc, float mc) { GUARD(h); LOCKED(h); TRY(h->s.set_st_state(sc, mc)); }
+int vfd_dfsph_find_neighbors(VfdDfsph* h) { GUARD(h); LOCKED(h); TRY(h->s.search_only()); }
 int vfd_dfsph_get_neighbors(VfdDfsph* h, uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t capacity, uint64_t* total) {
-    GUARD(h); TRY(h->s.get_neighbors(counts, offsets, ids, capacity, total));
+    GUARD(h); LOCKED(h); TRY(h->s.get_neighbors(counts, offsets, ids, capacity, total));
 }
-int vfd_dfsph_get_boundary(VfdDfsph* h, uint32_t body, float* xj, float* vol) { GUARD(h); if (!xj || !vol) return h->s.fail(VFD_E_INVALID, "null output"); TRY(h->s.get_boundary(body, xj, vol)); }
+int vfd_dfsph_get_boundary(VfdDfsph* h, uint32_t body, float* xj, float* vol) { GUARD(h); LOCKED(h); if (!xj || !vol) return h->s.fail(VFD_E_INVALID, "null output"); TRY(h->s.get_boundary(body, xj, vol)); }
 int vfd_dfsph_get_kernel_tables(VfdDfsph* h, float* W, float* gradW, float* sc) {
     GUARD(h);
     const vfd::KernelTables& t = h->s.tables;
@@ -141,7 +156,7 @@ int vfd_halton_table_build(float* out) {
 }
 
 int vfd_dfsph_set_option(VfdDfsph* h, int option, int64_t value) {
-    GUARD(h);
+    GUARD(h); LOCKED(h);
     switch (option) {
     case VFD_OPT_SEARCH_FMA: h->s.optSearchFma = value ? 1 : 0; return VFD_OK;
     case VFD_OPT_TIMERS: h->s.optTimers = value ? 1 : 0; return VFD_OK;
@@ -153,12 +168,12 @@ int vfd_dfsph_set_option(VfdDfsph* h, int option, int64_t value) {
 int vfd_dfsph_get_launch_count(VfdDfsph* h, uint64_t* launches, int reset) { GUARD(h); if (launches) *launches = h->s.launches; if (reset) h->s.launches = 0; return VFD_OK; }
 
 int vfd_dfsph_get_tile_stats(VfdDfsph* h, uint64_t stats[4]) {
-    GUARD(h); if (!stats) return h->s.fail(VFD_E_INVALID, "null output");
+    GUARD(h); LOCKED(h); if (!stats) return h->s.fail(VFD_E_INVALID, "null output");
     return h->s.tile_stats(stats);
 }
 
 int vfd_dfsph_time_matvec(VfdDfsph* h, uint32_t reps, float* ms) {
-    GUARD(h); if (!ms) return h->s.fail(VFD_E_INVALID, "null output");
+    GUARD(h); LOCKED(h); if (!ms) return h->s.fail(VFD_E_INVALID, "null output");
     return h->s.time_matvec(reps, ms);
 }
 
@@ -170,14 +185,14 @@ int vfd_dist_unique_id(char out[128]) {
     return rc;
 }
 int vfd_dfsph_init_distributed(VfdDfsph* h, int rank, int nranks, const char id[128], const float dmin[3], const float dmax[3]) {
-    GUARD(h); if (!id || !dmin || !dmax) return h->s.fail(VFD_E_INVALID, "null argument"); TRY(h->s.dist_init(rank, nranks, id, dmin, dmax));
+    GUARD(h); LOCKED(h); if (!id || !dmin || !dmax) return h->s.fail(VFD_E_INVALID, "null argument"); TRY(h->s.dist_init(rank, nranks, id, dmin, dmax));
 }
 int vfd_dfsph_get_grid(VfdDfsph* h, float origin[3], float* cellSize, uint32_t tiles[3]) { GUARD(h); if (!origin || !cellSize || !tiles) return h->s.fail(VFD_E_INVALID, "null argument"); TRY(h->s.dist_get_grid(origin, cellSize, tiles)); }
-int vfd_dfsph_set_slab(VfdDfsph* h, uint32_t lo, uint32_t hi) { GUARD(h); TRY(h->s.dist_set_slab(lo, hi)); }
+int vfd_dfsph_set_slab(VfdDfsph* h, uint32_t lo, uint32_t hi) { GUARD(h); LOCKED(h); TRY(h->s.dist_set_slab(lo, hi)); }
 int vfd_dfsph_set_particles_distributed(VfdDfsph* h, const float* pos, const float* vel, const uint32_t* ids, uint32_t n, uint32_t nGlobal, uint32_t capacity) {
-    GUARD(h); TRY(h->s.dist_set_particles(pos, vel, ids, n, nGlobal, capacity));
+    GUARD(h); LOCKED(h); TRY(h->s.dist_set_particles(pos, vel, ids, n, nGlobal, capacity));
 }
-int vfd_dfsph_get_owned(VfdDfsph* h, uint32_t capacity, uint32_t* count, uint32_t* ids, VfdParticle* out) { GUARD(h); TRY(h->s.dist_get_owned(capacity, count, ids, out)); }
+int vfd_dfsph_get_owned(VfdDfsph* h, uint32_t capacity, uint32_t* count, uint32_t* ids, VfdParticle* out) { GUARD(h); LOCKED(h); TRY(h->s.dist_get_owned(capacity, count, ids, out)); }
 int vfd_dfsph_get_comm_stats(VfdDfsph* h, uint64_t stats[4]) {
     GUARD(h); if (!stats) return VFD_E_INVALID;
     stats[0] = stats[1] = stats[2] = stats[3] = 0;
@@ -200,7 +215,7 @@ int vfd_dfsph_get_kernel_times(VfdDfsph* h, uint32_t capacity, uint32_t* count, 
     if (reset) p.reset();
     return VFD_OK;
 }
-int vfd_dfsph_record_event(VfdDfsph* h, uint32_t slot) { GUARD(h); TRY(h->s.record_event(slot)); }
-int vfd_dfsph_elapsed_ms(VfdDfsph* h, uint32_t from, uint32_t to, float* ms) { GUARD(h); if (!ms) return h->s.fail(VFD_E_INVALID, "null output"); TRY(h->s.elapsed_ms(from, to, ms)); }
+int vfd_dfsph_record_event(VfdDfsph* h, uint32_t slot) { GUARD(h); LOCKED(h); TRY(h->s.record_event(slot)); }
+int vfd_dfsph_elapsed_ms(VfdDfsph* h, uint32_t from, uint32_t to, float* ms) { GUARD(h); LOCKED(h); if (!ms) return h->s.fail(VFD_E_INVALID, "null output"); TRY(h->s.elapsed_ms(from, to, ms)); }
 
 } // extern "C"

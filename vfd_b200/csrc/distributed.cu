@@ -311,6 +311,15 @@ int Solver::dist_reduce(int site, bool isMax) {
     return VFD_OK;
 }
 
+// Frame capture of a decomposed run (DFSPHImplementation.cu:148-167 across ranks).  Not gathered yet: a distributed handle
+// bakes no frames (FrameCount must be 0; the state is read with get_owned), and says so instead of exporting its slab with
+// global ids into a buffer sized for the local count.
+int Solver::dist_frame_step() {
+    if (desc.FrameCount > 0 && frameIndexHost < desc.FrameCount)
+        return fail(VFD_E_INVALID, "a distributed handle does not bake frames: set FrameCount = 0 and read the slabs with vfd_dfsph_get_owned");
+    return VFD_OK;
+}
+
 int Solver::dist_get_owned(uint32_t capacity, uint32_t* count, uint32_t* ids, VfdParticle* out) {
     CK(cudaSetDevice(device));
     if (!dist) return fail(VFD_E_INVALID, "not distributed");

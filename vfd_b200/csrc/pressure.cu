@@ -46,7 +46,7 @@ extern __shared__ __align__(128) unsigned char smemRaw[];
 struct DensityFactorOp {
     static constexpr bool CUSTOM = false;
     using Cfg = PipeCfgMany;
-    static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 5, COEF = 2, NRED = 0;
+    static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 5, COEF = 2, NRED = 0, NLUT = 2;
     const Params& P; const Arrays& A; Lut K;
     __device__ __forceinline__ const float4* srcA() const { return A.pos; }
     __device__ __forceinline__ const void* srcB() const { return nullptr; }
@@ -55,9 +55,8 @@ struct DensityFactorOp {
     NO_PREFETCH
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.pos[g]; }
     NO_B
-    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
-        const float4 x = A.pos[p]; own[0] = x.x; own[1] = x.y; own[2] = x.z;
-    }
+    static constexpr bool PAD_SAFE = false;
+    __device__ __forceinline__ void own_from(uint32_t, float4 x, float4, float (&own)[NOWN]) const { own[0] = x.x; own[1] = x.y; own[2] = x.z; }
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4, float& c, float (&acc)[NSUM]) const {
         const float3 xij = f3(o[0], o[1], o[2]) - f3(a);
         acc[0] += P.volume * K.w(xij);
@@ -95,12 +94,12 @@ struct DensityFactorOp {
 
 __global__ void __launch_bounds__(DensityFactorOp::Cfg::THREADS, 1) k_density_factor(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S,
                                                                     const float* __restrict__ lutW, const float* __restrict__ lutG) {
-    float* sW = pipe_lut<2>(smemRaw);
+    float* sW = pipe_lut<DensityFactorOp>(smemRaw);
     float* sG = sW + VFD_LUT_RES;
     load_lut_tile(sW, lutW);
     load_lut_tile(sG, lutG);
     DensityFactorOp op{ P, A, Lut{ sW, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 } };
-    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<2>(smemRaw), op, P.tile0, P.tile1);
+    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<DensityFactorOp>(smemRaw), op, P.tile0, P.tile1);
 }
 
 // ---- K4 / K10: solver source terms ----------------------------------------------------------
@@ -109,7 +108,7 @@ template<bool DIV>
 struct SourceOp {
     static constexpr bool CUSTOM = false;
     using Cfg = PipeCfgWide;
-    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1, NRED = 0;
+    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1, NRED = 0, NLUT = 0;
     const Params& P; const Arrays& A;
     float dt, dtInv, dt2Inv;
     __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
@@ -118,8 +117,8 @@ struct SourceOp {
     NO_PREFETCH
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t g) const { return A.vel[g]; }
-    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
-        const float4 x = A.posRho[p], v = A.vel[p];
+    static constexpr bool PAD_SAFE = true;                 // the pair term is linear in the kernel-gradient factor
+    __device__ __forceinline__ void own_from(uint32_t, float4 x, float4 v, float (&own)[NOWN]) const {
         own[0] = x.x; own[1] = x.y; own[2] = x.z; own[3] = v.x; own[4] = v.y; own[5] = v.z;
     }
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
@@ -159,7 +158,7 @@ __global__ void __launch_bounds__(SourceOp<DIV>::Cfg::THREADS, 1) k_source(const
         else     { S->pressIt = 0; S->pressErr = 0.0f; S->pressActive = (0u < P.minPressIt && 0u < P.maxPressIt) ? 1u : 0u; }
     }
     SourceOp<DIV> op{ P, A, S->dt, S->dtInv, S->dt2Inv };
-    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
+    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<SourceOp<DIV>>(smemRaw), op, P.tile0, P.tile1);
 }
 
 // ---- K5 / K7 / K11 / K13: pressure acceleration from kappa ---------------------------------
@@ -169,7 +168,7 @@ template<int MODE>
 struct AccelOp {
     static constexpr bool CUSTOM = false;
     using Cfg = PipeCfgMany;
-    static constexpr int NPAY = 2, BBYTES = 4, NOWN = 4, NSUM = 3, COEF = 1, NRED = 0;     // payload: (x, y, z, rho) and kappa
+    static constexpr int NPAY = 2, BBYTES = 4, NOWN = 4, NSUM = 3, COEF = 1, NRED = 0, NLUT = 0;     // payload: (x, y, z, rho) and kappa
     const Params& P; const Arrays& A;
     const float* __restrict__ kap;
     float dt;
@@ -179,9 +178,8 @@ struct AccelOp {
     NO_PREFETCH
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t g) const { return make_float4(kap[g], 0.0f, 0.0f, 0.0f); }
-    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
-        const float4 x = A.posRho[p]; own[0] = x.x; own[1] = x.y; own[2] = x.z; own[3] = kap[p];
-    }
+    static constexpr bool PAD_SAFE = true;
+    __device__ __forceinline__ void own_from(uint32_t, float4 x, float4 k, float (&own)[NOWN]) const { own[0] = x.x; own[1] = x.y; own[2] = x.z; own[3] = k.x; }
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
         const float ks = o[3] + b.x;
         if (fabsf(ks) > VFD_EPS_F) {
@@ -216,7 +214,7 @@ __global__ void __launch_bounds__(AccelOp<MODE>::Cfg::THREADS, 1) k_pressure_acc
     if (MODE == ACC_DIV_ITER && !S->divActive) return;
     if (MODE == ACC_PRESS_ITER && !S->pressActive) return;
     AccelOp<MODE> op{ P, A, (MODE == ACC_DIV_ITER || MODE == ACC_DIV_FINISH) ? A.kappaV : A.kappa, S->dt };
-    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
+    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<AccelOp<MODE>>(smemRaw), op, P.tile0, P.tile1);
 }
 
 // ---- K6 / K12 (+ R1 / R3): one Jacobi update and the fused residual reduction ----------------
@@ -224,7 +222,7 @@ template<bool DIV>
 struct SolveOp {
     static constexpr bool CUSTOM = false;
     using Cfg = PipeCfgWide;
-    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1, NRED = 1;   // payload: position, pressure acceleration
+    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 6, NSUM = 1, COEF = 1, NRED = 1, NLUT = 0;   // payload: position, pressure acceleration
     const Params& P; const Arrays& A;
     float scale;
     float red[1];                                          // rho0 * residuum of the lane's particle (summed grid-wide: tile.cuh RedRecord)
@@ -234,8 +232,8 @@ struct SolveOp {
     NO_PREFETCH
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t g) const { return A.pacc[g]; }
-    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
-        const float4 x = A.posRho[p], a = A.pacc[p];
+    static constexpr bool PAD_SAFE = true;
+    __device__ __forceinline__ void own_from(uint32_t, float4 x, float4 a, float (&own)[NOWN]) const {
         own[0] = x.x; own[1] = x.y; own[2] = x.z; own[3] = a.x; own[4] = a.y; own[5] = a.z;
     }
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
@@ -268,7 +266,7 @@ __global__ void __launch_bounds__(SolveOp<DIV>::Cfg::THREADS, 1) k_solve_iterati
     if (DIV ? !S->divActive : !S->pressActive) return;
     PipeShared& ps = pipe_header(smemRaw);
     SolveOp<DIV> op{ P, A, DIV ? S->dt : S->dt2, { 0.0f } };
-    if (pipe_pass(S, A, ps, pipe_pay<0>(smemRaw), op, P.tile0, P.tile1)) {
+    if (pipe_pass(S, A, ps, pipe_pay<SolveOp<DIV>>(smemRaw), op, P.tile0, P.tile1)) {
         double tot[1];
         fold_slots<1>(tot, A.slotSums, __ldg(A.tileList), A.slotStride, ps.red);
         if (threadIdx.x == 0) finish_reduction<1>(DIV ? SITE_DIV : SITE_PRESS, P, S, tot);
@@ -330,35 +328,35 @@ static void pipe_attr(Kern kern, size_t smem) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (nd < 32) done[nd++] = (const void*)kern;
 }
-#define PIPE_LAUNCH(kid, kern, OpT, smem, ...) do { const size_t sm_ = (smem); pipe_attr(kern, sm_); LaunchScope ls(L, kid); \
+#define PIPE_LAUNCH(kid, kern, OpT, smem, ...) do { using OPT_ = OpT; const size_t sm_ = (smem); pipe_attr(kern, sm_); LaunchScope ls(L, kid); \
     kern<<<L.numSMs, OpT::Cfg::THREADS, sm_, L.stream>>>(__VA_ARGS__); } while (0)
 
 void launch_density_factor(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutW, const float* lutG) {
-    PIPE_LAUNCH(KID_DENSITY_FACTOR, k_density_factor, DensityFactorOp, (pipe_smem_bytes<2, 16, 0>()), P, A, S, lutW, lutG);
+    PIPE_LAUNCH(KID_DENSITY_FACTOR, k_density_factor, DensityFactorOp, (pipe_smem_bytes<OPT_>()), P, A, S, lutW, lutG);
 }
 void launch_divergence_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_DIV_SOURCE, k_source<true>, SourceOp<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
+    PIPE_LAUNCH(KID_DIV_SOURCE, k_source<true>, SourceOp<true>, (pipe_smem_bytes<OPT_>()), P, A, S);
 }
 void launch_divergence_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_DIV_ACCEL, k_pressure_accel<ACC_DIV_ITER>, AccelOp<0>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
+    PIPE_LAUNCH(KID_DIV_ACCEL, k_pressure_accel<ACC_DIV_ITER>, AccelOp<0>, (pipe_smem_bytes<OPT_>()), P, A, S);
 }
 void launch_divergence_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_DIV_SOLVE, k_solve_iteration<true>, SolveOp<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
+    PIPE_LAUNCH(KID_DIV_SOLVE, k_solve_iteration<true>, SolveOp<true>, (pipe_smem_bytes<OPT_>()), P, A, S);
 }
 void launch_divergence_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_DIV_FINISH, k_pressure_accel<ACC_DIV_FINISH>, AccelOp<0>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
+    PIPE_LAUNCH(KID_DIV_FINISH, k_pressure_accel<ACC_DIV_FINISH>, AccelOp<0>, (pipe_smem_bytes<OPT_>()), P, A, S);
 }
 void launch_pressure_source(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_PRESS_SOURCE, k_source<false>, SourceOp<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
+    PIPE_LAUNCH(KID_PRESS_SOURCE, k_source<false>, SourceOp<true>, (pipe_smem_bytes<OPT_>()), P, A, S);
 }
 void launch_pressure_accel(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_PRESS_ACCEL, k_pressure_accel<ACC_PRESS_ITER>, AccelOp<0>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
+    PIPE_LAUNCH(KID_PRESS_ACCEL, k_pressure_accel<ACC_PRESS_ITER>, AccelOp<0>, (pipe_smem_bytes<OPT_>()), P, A, S);
 }
 void launch_pressure_solve(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_PRESS_SOLVE, k_solve_iteration<false>, SolveOp<true>, (pipe_smem_bytes<0, 16, 16>()), P, A, S);
+    PIPE_LAUNCH(KID_PRESS_SOLVE, k_solve_iteration<false>, SolveOp<true>, (pipe_smem_bytes<OPT_>()), P, A, S);
 }
 void launch_pressure_finish(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float*) {
-    PIPE_LAUNCH(KID_PRESS_FINISH, k_pressure_accel<ACC_PRESS_FINISH>, AccelOp<0>, (pipe_smem_bytes<0, 16, 4>()), P, A, S);
+    PIPE_LAUNCH(KID_PRESS_FINISH, k_pressure_accel<ACC_PRESS_FINISH>, AccelOp<0>, (pipe_smem_bytes<OPT_>()), P, A, S);
 }
 void launch_clear_acceleration(const LaunchCfg& L, const Params& P, const Arrays& A) {
     LaunchScope ls(L, KID_CLEAR_ACC);

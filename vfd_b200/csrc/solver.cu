@@ -291,10 +291,11 @@ template<typename T> static cudaError_t dalloc(T*& p, size_t count) { return cud
 void Solver::free_particles() {
     Arrays& A = arrays;
     void* ptrs[] = { A.pos, A.vel, A.dv, A.nbar, A.curv, A.curvS, A.curvD, A.id, A.pos2, A.vel2, A.dv2, A.nbar2, A.curv2, A.curvS2, A.curvD2, A.id2,
-                     A.posRho, A.acc, A.pacc, A.nrm, A.res, A.rho, A.rhoAdv, A.kappa, A.kappaV, A.alpha, A.cgG, A.cgR, A.cgP, A.cgQ, A.cgZ, A.minv,
+                     A.posRho, A.acc, A.pacc, A.nrm, A.res, A.rho, A.rhoAdv, A.kappa, A.kappaV, A.alpha, A.cgG, A.cgR, A.cgQ, A.cgZ, A.cgXG, A.cgXP, A.cgGyz, A.cgPyz, A.minv,
                      A.cnt, A.list16, A.coef, A.gcoef, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.tileList, A.partials, A.slotSums, dPos0, dVel0 };
     for (void* p : ptrs) if (p) cudaFree(p);
     if (dIds0) { cudaFree(dIds0); dIds0 = nullptr; }
+    if (dFrame) { cudaFree(dFrame); dFrame = nullptr; dFrameCapacity = 0; }
     for (int b = 0; b < VFD_MAX_BODIES; b++) { if (A.bx[b]) cudaFree(A.bx[b]); if (A.bcoef[b]) cudaFree(A.bcoef[b]); if (A.bgrad[b]) cudaFree(A.bgrad[b]); }
     memset(&A, 0, sizeof A);
     dPos0 = dVel0 = nullptr;
@@ -320,12 +321,13 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
     free_particles();
     allocParticles = np;
     float4** f4s[] = { &A.pos, &A.vel, &A.dv, &A.nbar, &A.pos2, &A.vel2, &A.dv2, &A.nbar2, &A.posRho, &A.acc, &A.pacc, &A.nrm,
-                       &A.cgG, &A.cgR, &A.cgP, &A.cgQ, &A.cgZ, &dPos0, &dVel0 };
+                       &A.cgG, &A.cgR, &A.cgQ, &A.cgZ, &A.cgXG, &A.cgXP, &dPos0, &dVel0 };
     CK(dalloc(dIds0, np));
     for (float4** p : f4s) { CK(dalloc(*p, np)); allocBytes += np * 16; }
     float** f1s[] = { &A.curv, &A.curvS, &A.curvD, &A.curv2, &A.curvS2, &A.curvD2, &A.res, &A.rho, &A.rhoAdv, &A.kappa, &A.kappaV, &A.alpha };
     for (float** p : f1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
     CK(dalloc(A.minv, np * 9)); allocBytes += np * 36;
+    CK(dalloc(A.cgGyz, np)); CK(dalloc(A.cgPyz, np)); allocBytes += np * 16;
     uint32_t** u1s[] = { &A.id, &A.id2, &A.cnt, &A.key, &A.rank, &A.tmpIdx };
     for (uint32_t** p : u1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
     CK(dalloc(A.list16, np * ELL_SLOTS)); searchBytes = np * ELL_SLOTS * 2 + np * 4 * 4;
@@ -485,8 +487,10 @@ int Solver::begin() {
     if (info.ParticleCount == 0 && !dist) { began = true; return VFD_OK; }
     if (dist) { dist->nLocal = info.ParticleCount; dist->ownB = 0; dist->ownE = info.ParticleCount; dist->edgeLEnd = 0; dist->edgeRBegin = info.ParticleCount; }
     refresh_params();
-    k_reset_state<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dPos0, dVel0, dist ? dIds0 : nullptr);
-    launches += 1;
+    if (params.n) {                                      // a rank of a decomposition may own nothing at start-up
+        k_reset_state<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dPos0, dVel0, dist ? dIds0 : nullptr);
+        launches += 1;
+    }
     DevState s;
     memset(&s, 0, sizeof s);
     s.dt = desc.TimeStepSize; s.dt2 = desc.TimeStepSize * desc.TimeStepSize;
@@ -609,17 +613,17 @@ int Solver::step() {
     if (desc.EnableViscositySolver) {
         launch_viscosity_setup(L, P, A, dState, dLutG);
         RC(reduce(SITE_VISC_BB));
-        RC(halo4(A.cgG));
+        RC(halo4(A.cgXG)); RC(halo2(A.cgGyz));
         launch_viscosity_matvec(L, P, A, dState, true);
         RC(reduce(SITE_VISC_INIT));
-        RC(halo4(A.cgP));
+        RC(halo4(A.cgXP)); RC(halo2(A.cgPyz));
         auto iteration = [&]() -> int {
             launch_viscosity_matvec(L, P, A, dState, false);
             RC(reduce(SITE_VISC_PQ));
             launch_viscosity_update(L, P, A, dState);
             RC(reduce(SITE_VISC_UPDATE));
             launch_viscosity_direction(L, P, A, dState);
-            RC(halo4(A.cgP));
+            RC(halo4(A.cgXP)); RC(halo2(A.cgPyz));
             return VFD_OK;
         };
         if (P.minViscIt == 0 && P.maxViscIt > 0) RC(run_polled_loop(P.maxViscIt, 0, 4, &dState->viscActive, iteration, 1u));
@@ -661,6 +665,9 @@ int Solver::step() {
     // 11. frame capture (:148-167).  FrameLength <= 0: every step is a frame, so there is nothing to ask the device —
     // the frame's scalars travel with it and the host keeps queueing the next step (debug info is refreshed when the
     // bake ends).  Otherwise the accumulated frame time is needed on the host.
+    // A rank of a decomposition holds a slab in local order: its frames go through dist_capture_frame (owned particles with
+    // their persistent ids, gathered on rank 0), never through the original-order export of the whole scene.
+    if (dist) return dist_frame_step();
     if (frameIndexHost < desc.FrameCount && desc.FrameLength <= 0.0f && !T && state == VFD_STATE_SIMULATING) {
         VfdParticleSimple* d = pipe.acquire();
         if (!d) { cudaGetLastError(); return fail(VFD_E_CUDA, "frame capture: cannot allocate the frame ring buffers"); }
@@ -816,7 +823,11 @@ int Solver::get_current_frame(VfdParticleSimple* out) {
     if (dist) return fail(VFD_E_INVALID, "original-order dumps are single-GPU calls: use get_owned on each rank");
     if (!out) return fail(VFD_E_INVALID, "null output");
     if (info.ParticleCount == 0) return VFD_OK;
-    if (!dFrame) CK(cudaMalloc(&dFrame, (size_t)info.ParticleCount * sizeof(VfdParticleSimple)));
+    if (dFrameCapacity < info.ParticleCount) {           // the handle may have been given more particles since the last call
+        if (dFrame) { cudaFree(dFrame); dFrame = nullptr; dFrameCapacity = 0; }
+        CK(cudaMalloc(&dFrame, (size_t)info.ParticleCount * sizeof(VfdParticleSimple)));
+        dFrameCapacity = info.ParticleCount;
+    }
     refresh_params();
     k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dFrame, dState, nullptr);
     launches += 1;

@@ -23,7 +23,9 @@ struct Arrays {
     float4 *acc, *pacc, *nrm;               // Acceleration, PressureAcceleration, (MonteCarloSurfaceNormal, MonteCarloSurfaceCurvature)
     float  *res, *rho, *rhoAdv, *kappa, *kappaV, *alpha;   // PressureResiduum, Density, DensityAdvection, PressureRho2, PressureRho2V, Factor
     // implicit viscosity (matrix-free PCG)
-    float4 *cgG, *cgR, *cgP, *cgQ, *cgZ;
+    float4 *cgG, *cgR, *cgQ, *cgZ;
+    float4 *cgXG, *cgXP;                    // (x, y, z, v.x) with v = g at start-up / the search direction p: what the mat-vec gathers (viscosity.cu)
+    float2 *cgGyz, *cgPyz;                  // (v.y, v.z)
     float  *minv;                           // 9 x n, SoA: minv[k*n + p], column-major 3x3 like glm
     // boundary samples per rigid body: (x_b.xyz, V_b)
     float4* bx[VFD_MAX_BODIES];

@@ -112,7 +112,9 @@ private:
     int dist_read_ranges();
     int dist_halo(void* base, uint32_t elemFloats);
     int dist_reduce(int site, bool isMax);
+    int dist_frame_step();
     int halo4(float4* a) { return dist ? dist_halo(a, 4) : VFD_OK; }
+    int halo2(float2* a) { return dist ? dist_halo(a, 2) : VFD_OK; }
     int halo1(float* a) { return dist ? dist_halo(a, 1) : VFD_OK; }
     int reduce(int site, bool isMax = false) { return dist ? dist_reduce(site, isMax) : VFD_OK; }
     int run_polled_loop(uint32_t maxIt, uint32_t already, int batch, uint32_t* dFlag, const std::function<int()>& enqueueIteration, uint32_t continueValue);
@@ -132,6 +134,7 @@ private:
     float4 *dPos0 = nullptr, *dVel0 = nullptr;
     uint32_t* dIds0 = nullptr;
     VfdParticleSimple* dFrame = nullptr;
+    uint32_t dFrameCapacity = 0;
     uint32_t cellEstimate = 27, cellCapacity = 0;
     size_t allocParticles = 0;        // particle slots the arrays are currently sized for
     bool began = false, searched = false;

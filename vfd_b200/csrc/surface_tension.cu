@@ -33,7 +33,7 @@ __device__ __forceinline__ float3 normalize_if_nonzero(float3 v) {   // DFSPHKer
 struct StClassifyOp {
     static constexpr bool CUSTOM = true, TILE_QUEUE = true;
     using Cfg = PipeCfg<24, 2, 2>;
-    static constexpr int NPAY = 1, BBYTES = 0, COEF = 0, NRED = 0;
+    static constexpr int NPAY = 1, BBYTES = 0, COEF = 0, NRED = 0, NLUT = 0;
     const Params& P; const Arrays& A;
     const float* __restrict__ halton;
     uint32_t sampleCount;
@@ -151,14 +151,14 @@ struct StClassifyOp {
 __global__ void __launch_bounds__(StClassifyOp::Cfg::THREADS, 1) k_st_classify(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ halton) {
     const float radiusRatio = P.nbrRadius / P.r;
     StClassifyOp op{ P, A, halton, S->sampleCount, S->mcFactor, radiusRatio * radiusRatio * P.h2 };
-    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
+    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<StClassifyOp>(smemRaw), op, P.tile0, P.tile1);
 }
 
 // T2: neighbour-weighted smoothing of normal and curvature among surface particles
 struct StSmoothOp {
     static constexpr bool CUSTOM = false;
     using Cfg = PipeCfgMany;
-    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 4, NSUM = 5, COEF = 0, NRED = 0;       // payload: position, (normal, curvature)
+    static constexpr int NPAY = 2, BBYTES = 16, NOWN = 4, NSUM = 5, COEF = 0, NRED = 0, NLUT = 0;       // payload: position, (normal, curvature)
     const Params& P; const Arrays& A;
     __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
     __device__ __forceinline__ const void* srcB() const { return A.nrm; }
@@ -167,8 +167,8 @@ struct StSmoothOp {
     __device__ __forceinline__ void prefetch_own(uint32_t, uint32_t, uint32_t) const {}
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t g) const { return A.nrm[g]; }
-    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
-        const float4 x = A.posRho[p], n = A.nrm[p];
+    static constexpr bool PAD_SAFE = false;
+    __device__ __forceinline__ void own_from(uint32_t, float4 x, float4 n, float (&own)[NOWN]) const {
         own[0] = x.x; own[1] = x.y; own[2] = x.z;
         own[3] = (n.x != 0.0f || n.y != 0.0f || n.z != 0.0f) ? 1.0f : 0.0f;
     }
@@ -196,7 +196,7 @@ struct StSmoothOp {
 
 __global__ void __launch_bounds__(StSmoothOp::Cfg::THREADS, 1) k_st_smooth(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     StSmoothOp op{ P, A };
-    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<0>(smemRaw), op, P.tile0, P.tile1);
+    pipe_pass(S, A, pipe_header(smemRaw), pipe_pay<StSmoothOp>(smemRaw), op, P.tile0, P.tile1);
 }
 
 // T3: apply the force (once per smoothing pass: SURVEY.md Q18)
@@ -220,14 +220,14 @@ __global__ void __launch_bounds__(VFD_TPB) k_st_apply(Params P, Arrays A) {
 }
 
 void launch_st_classify(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* halton) {
-    const size_t sp = pipe_smem_bytes<0, 16, 0>();
+    const size_t sp = pipe_smem_bytes<StClassifyOp>();
     static thread_local bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_st_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp); attr = true; }
     LaunchScope ls(L, KID_ST_CLASSIFY);
     k_st_classify<<<L.numSMs, StClassifyOp::Cfg::THREADS, sp, L.stream>>>(P, A, S, halton);
 }
 void launch_st_smooth(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
-    const size_t sp = pipe_smem_bytes<0, 16, 16>();
+    const size_t sp = pipe_smem_bytes<StSmoothOp>();
     static thread_local bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_st_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp); attr = true; }
     LaunchScope ls(L, KID_ST_SMOOTH);

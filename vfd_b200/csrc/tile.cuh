@@ -233,10 +233,10 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 #define PIPE_ABLATE 0
 #endif
 #ifndef PIPE_STAGES
-#define PIPE_STAGES 4            // tiles in flight per CTA (header slots); their payloads share one ring of PIPE_RING particle slots
+#define PIPE_STAGES 6            // tiles in flight per CTA (header slots); their payloads share one ring of particle slots
 #endif
 #ifndef PIPE_CONSUMER_WARPS
-#define PIPE_CONSUMER_WARPS 16
+#define PIPE_CONSUMER_WARPS 28
 #endif
 #ifndef PIPE_PRODUCER_WARPS
 #define PIPE_PRODUCER_WARPS 4
@@ -244,28 +244,39 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 #define PIPE_PRODUCER_THREADS (PIPE_PRODUCER_WARPS * 32)
 #define PIPE_CELLS_PER_THREAD ((HALO_CELLS + PIPE_PRODUCER_THREADS - 1) / PIPE_PRODUCER_THREADS)
 #define PIPE_CAP 2816          // largest halo box that is staged (larger ones take the exact global-memory path)
-#define PIPE_RING (2 * PIPE_CAP) // payload ring, in particles: two worst-case boxes, three to four typical ones (~1700)
+// The payload ring takes whatever shared memory the pass has left (pipe_ring_slots below): how many tiles a CTA has in
+// flight — staged or being gathered — is what bounds its throughput once the consumers no longer wait for memory (a batch
+// lives ~10 us in a warp, a tile is released when its slowest batch is done): 6700 particle slots for the 32-byte payloads,
+// 8900 for the mat-vec's 24 bytes, ~13000 for one 16-byte array; a typical halo box holds 1700 - 2000 particles.
+#define PIPE_SMEM_MAX 232448u  // 227 KB of dynamic shared memory per CTA on sm_100
 #ifndef PIPE_GATHER_WIDTH
 #define PIPE_GATHER_WIDTH 2    // payload gathers in flight per lane (1, 2 or 4)
 #endif
 #ifndef PIPE_LOOKAHEAD
-#define PIPE_LOOKAHEAD 4
-#endif                         // neighbour groups (of four) in flight per lane
+#define PIPE_LOOKAHEAD 2
+#endif                         // neighbour groups (of four) in flight per warp
 
 // Shape of a pass, chosen per kernel (every Op names one as Op::Cfg): consumer warps per CTA, neighbour groups in flight
-// per lane (register ring), payload gathers in flight per lane.  Passes that are heavy on arithmetic or gather one
-// payload array want many warps with a narrow register footprint (28 warps at 64 registers); the passes that stream two
-// 16-byte payloads and a coefficient word per pair are better off with 16 warps at 96 registers and a deeper ring.
+// per warp (slots of its shared-memory stream ring), payload gathers in flight per lane.  Measured on the settled 1M scene
+// (round 2): with the list/coefficient stream in shared memory every pair pass fits 64 registers, and 28 consumer warps
+// with a two-slot ring do best — deeper rings take shared memory from the payload ring (tiles in flight), which costs more
+// than the extra look-ahead gains (ring 2/3/4/6: 0.116/0.120/0.122/0.144 ms per mat-vec).
 template<int CW_, int D_, int GW_> struct PipeCfg {
     static constexpr int CW = CW_, D = D_, GW = GW_, THREADS = (CW_ + PIPE_PRODUCER_WARPS) * 32;
 };
-using PipeCfgWide = PipeCfg<PIPE_CONSUMER_WARPS, PIPE_LOOKAHEAD, PIPE_GATHER_WIDTH>;   // 16 warps, 4 groups ahead, 2 gathers (measured best of 3..6 x 1..4)
+using PipeCfgWide = PipeCfg<PIPE_CONSUMER_WARPS, PIPE_LOOKAHEAD, PIPE_GATHER_WIDTH>;   // two 16-byte payloads (source terms, Jacobi updates)
 #ifndef PIPE_MANY_CW
 #define PIPE_MANY_CW 28
 #define PIPE_MANY_D 2
 #define PIPE_MANY_GW 2
 #endif
 using PipeCfgMany = PipeCfg<PIPE_MANY_CW, PIPE_MANY_D, PIPE_MANY_GW>;
+#ifndef PIPE_MV_CW
+#define PIPE_MV_CW 28
+#define PIPE_MV_D 2
+#define PIPE_MV_GW 2
+#endif
+using PipeCfgMatvec = PipeCfg<PIPE_MV_CW, PIPE_MV_D, PIPE_MV_GW>;    // the PCG mat-vec (payload 16 + 8 bytes)
 
 __device__ __forceinline__ uint2 ldg_stream(const uint2* p) { return __ldg(p); }
 __device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldg(p); }
@@ -309,10 +320,25 @@ struct PipeShared {
     StageHeader hdr[PIPE_STAGES];
 };
 __host__ __device__ constexpr size_t pipe_header_bytes() { return (sizeof(PipeShared) + 127) / 128 * 128; }
-// dynamic shared memory: [PipeShared][NLUT tables][stage 0: A, B][stage 1: A, B]; B is 16 or 4 bytes per particle
-template<int NLUT, int ABYTES, int BBYTES> static inline size_t pipe_smem_bytes() {
-    return pipe_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float) + (size_t)PIPE_RING * (ABYTES + BBYTES);
-}
+// dynamic shared memory: [PipeShared][per-warp neighbour-stream rings (pair ops)][NLUT tables][payload A ring][payload B ring]
+// The stream ring of a consumer warp: Cfg::D slots of one neighbour group each — the 32 lanes' list words (256 B) and, for ops
+// that read a per-pair coefficient stream, their coefficient words (512 B) — filled with cp.async by the lanes themselves.
+template<class Op> struct PipeLayout {
+    static constexpr bool STREAM = !Op::CUSTOM;
+    static constexpr uint32_t SLOT = STREAM ? 256u + ((Op::COEF & 1) ? 512u : 0u) : 0u;           // bytes per group
+    static constexpr uint32_t STREAM_BYTES = STREAM ? (uint32_t)Op::Cfg::CW * (uint32_t)Op::Cfg::D * SLOT : 0u;
+    static constexpr uint32_t BB = Op::NPAY > 1 ? (uint32_t)Op::BBYTES : 0u;
+    static constexpr uint32_t LUT_BYTES = (uint32_t)Op::NLUT * (uint32_t)(VFD_LUT_RES * sizeof(float));
+    static constexpr uint32_t OFF_STREAM = (uint32_t)pipe_header_bytes();
+    static constexpr uint32_t OFF_LUT = OFF_STREAM + STREAM_BYTES;
+    static constexpr uint32_t OFF_PAY = OFF_LUT + LUT_BYTES;
+    // particle slots of the payload ring: whatever shared memory is left
+    static constexpr uint32_t SLOTS = ((PIPE_SMEM_MAX - OFF_PAY) / (16u + BB)) & ~63u;
+    static constexpr size_t BYTES = (size_t)OFF_PAY + (size_t)SLOTS * (16u + BB);
+    static_assert(SLOTS >= PIPE_CAP, "the payload ring must hold the largest staged halo box");
+};
+template<class Op> struct PipeRing { static constexpr uint32_t SLOTS = PipeLayout<Op>::SLOTS; };
+template<class Op> static inline size_t pipe_smem_bytes() { return PipeLayout<Op>::BYTES; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count) {
@@ -328,9 +354,29 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
                      : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ bool mbar_test(unsigned long long* b, uint32_t parity) {     // non-blocking
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return done != 0u;
+}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// cp.async of the lane's own word with zero fill: srcBytes = 0 writes zeros without touching global memory
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dstShared, const void* src, uint32_t srcBytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dstShared), "l"(src), "r"(srcBytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dstShared, const void* src, uint32_t srcBytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dstShared), "l"(src), "r"(srcBytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float4 lds128(uint32_t a) { float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -454,9 +500,9 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
         // overlap are waited for, oldest first (consumers release tiles in order)
         uint32_t base = 0;
         if (staged) {
-            base = ringNext + total <= PIPE_RING ? ringNext : 0u;
+            base = ringNext + total <= PipeRing<Op>::SLOTS ? ringNext : 0u;
             #pragma unroll
-            for (int j = PIPE_STAGES - 2; j >= 0; j--) {            // j = 2: tile k-3 ... j = 0: tile k-1
+            for (int j = PIPE_STAGES - 2; j >= 0; j--) {            // oldest first: j = 0 is tile k-1
                 const uint32_t kk = k - 1u - (uint32_t)j;
                 if (k >= 1u + (uint32_t)j && regE[j] > regB[j] && base < regE[j] && regB[j] < base + total)
                     mbar_wait(&ps.empty[kk % PIPE_STAGES], (kk / PIPE_STAGES) & 1u);
@@ -475,7 +521,7 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
         producer_sync();                                  // the table is complete for every producer warp
         if (staged) {
             unsigned char* sA = pay + (size_t)base * 16;
-            unsigned char* sB = pay + (size_t)PIPE_RING * 16 + (size_t)base * BBYTES;
+            unsigned char* sB = pay + (size_t)PipeRing<Op>::SLOTS * 16 + (size_t)base * BBYTES;
             // One halo row (six x-adjacent cells, contiguous in the local index space) per warp and turn: the first cell
             // belongs to the tile on the left, the next four are contiguous in the sorted arrays, the last to the tile on
             // the right.  Lane j first fetches the seven table entries of the warp's j-th row (one shared-memory round
@@ -483,7 +529,7 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
             constexpr int ROWS = 36 / PIPE_PRODUCER_WARPS;
             // bulk (TMA) copies measured equal to LDGSTS for the two-payload passes and 2-4 % faster for the one-payload ones;
             // VFD_TUNE7=1 flips the choice (A/B runs)
-            const bool bulk = (Op::NPAY == 1) != (op.P.tune[7] == 1);
+            const bool bulk = (Op::NPAY == 1 || BBYTES == 16) != (op.P.tune[7] == 1);
             if (bulk) {
                 // 16-byte payload arrays by bulk copy: lane 3r + q takes segment q of the warp's r-th row (one instruction per
                 // contiguous segment instead of one LDGSTS per particle, and full-width shared-memory writes)
@@ -501,12 +547,12 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
                 }
             }
             uint32_t rl[4] = { 0u, 0u, 0u, 0u }, rg[3] = { 0u, 0u, 0u };
-            if ((!bulk || BBYTES == 4) && lane < (uint32_t)ROWS) {
+            if ((!bulk || BBYTES == 4 || BBYTES == 8) && lane < (uint32_t)ROWS) {
                 const uint32_t c0 = (pw + lane * PIPE_PRODUCER_WARPS) * 6u;
                 rl[0] = H.local[c0]; rl[1] = H.local[c0 + 1]; rl[2] = H.local[c0 + 5]; rl[3] = (c0 + 6 < HALO_CELLS) ? H.local[c0 + 6] : total;
                 rg[0] = H.cellG[c0]; rg[1] = H.cellG[c0 + 1]; rg[2] = H.cellG[c0 + 5];
             }
-            if (!bulk || BBYTES == 4) {
+            if (!bulk || BBYTES == 4 || BBYTES == 8) {
                 #pragma unroll
                 for (int j = 0; j < ROWS; j++) {
                     const uint32_t lA = __shfl_sync(0xffffffffu, rl[0], j), lB = __shfl_sync(0xffffffffu, rl[1], j);
@@ -518,6 +564,7 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
                             cp_async16(sA + (size_t)l * 16, gA + (size_t)g * 16);
                             if (BBYTES == 16) cp_async16(sB + (size_t)l * 16, gB + (size_t)g * 16);
                         }
+                        if (BBYTES == 8) cp_async8(sB + (size_t)l * 8, gB + (size_t)g * 8);
                         if (BBYTES == 4) cp_async4(sB + (size_t)l * 4, gB + (size_t)g * 4);
                     }
                 }
@@ -627,198 +674,269 @@ __device__ __forceinline__ void pipe_consumer(const Arrays& A, PipeShared& ps, c
     }
 }
 
-// ---- consumer of pair ops, software-pipelined ACROSS batches -------------------------------------------
-// A tile of ~512 particles is 16 batches and the CTA has 16 consumer warps: every warp gets one batch per tile, and in
-// the plain loop above all of them sit in the batch's start-up at the same time — neighbour count, own fields, first list
-// and coefficient words, one L2/HBM latency with nothing to overlap it (ncu, profiles/r01_ncu_matvec_pipeline.txt: 40 %
-// of the warp-stall samples at the top of the batch).  Here a warp issues the start-up loads of its NEXT batch (which
-// may belong to a later tile: the producers are tiles ahead) right after the gather loop of the current one, before the
-// current batch's epilogue (Op::finish: boundary terms, preconditioner, stores), so they are in flight during it.
-// The order of batches per warp, and therefore every per-thread sum, is the plain loop's.
-template<class Op> struct BatchHead {
-    uint32_t p, m;
-    float own[Op::NOWN];
-    uint2 wr[Op::Cfg::D]; float4 cr[Op::Cfg::D];
-};
-struct BatchCursor {
-    uint32_t k, b, rot;                    // tile counter of this CTA, batch inside the tile, rotation (see above)
-    uint32_t begin, end, nBatch, li;
-    bool done;
-};
+// ---- consumer of pair ops: one continuous neighbour stream per warp ---------------------------------------
+// A warp owns a sequence of 32-particle batches (one particle per lane), possibly spread over several tiles.  ncu of
+// the round-1 consumer (profiles/r01_ncu_full_step.txt, source page) put 42 % of the consumer warps' stall samples OUTSIDE
+// the gather loop: every batch started cold (neighbour count, own fields, first list and coefficient words: one exposed
+// L2/HBM latency per batch, only partly hidden behind the previous epilogue at the price of a second register set and
+// spills), and a warp that had finished a tile waited for the next one.  Here
+//   * the list/coefficient register ring runs ACROSS batch boundaries: the last round of a batch refills the ring with the
+//     first groups of the warp's next batch, whose particle index and neighbour count were fetched a whole batch earlier
+//     (the batch cursor walks one batch ahead of the gather, without blocking: a tile that is not staged yet is not waited
+//     for while the warp still holds an older one);
+//   * a particle's own fields are read from the shared-memory stage (the tile's own cells are part of its halo box), not
+//     from global memory: no long-latency load sits between two gather loops;
+//   * the group loop has a warp-uniform trip count (lanes past their last group are predicated off) and, for ops whose pair
+//     term vanishes with the coefficient (Op::PAD_SAFE: the unused slots of a particle's last group hold index 0 and
+//     coefficient 0), no separate code path for partial groups.
+// The order of a lane's pair terms is the list order, as before: results are bit-identical to the round-1 consumer up to
+// the sign of a zero.
+//
+// Op interface (pair ops): NOWN, NSUM, NRED, COEF, PAD_SAFE; own_from(p, a, b, own) fills the lane's own fields from its
+// own payload entry (a, b) — it may add plain global loads of fields the epilogue wants; pair(own, a, b, coef&, acc);
+// finish(p, countWord, own, acc).
 
-template<class Op>
-__device__ __forceinline__ void pipe_head_load(BatchHead<Op>& h, const BatchCursor& c, uint32_t lane, const Arrays& A, const Op& op) {
-    constexpr int D = Op::Cfg::D;
-    h.p = c.begin + (c.b << 5) + lane;
-    h.m = 0u;
+// local index of one of the tile's OWN particles: the tile's 16 rows of four x-adjacent cells (row r = 4 z + y, box cell
+// 36 z + 6 y + 43) are contiguous runs of both the global and the local index space
+__device__ __forceinline__ uint32_t hdr_own_local(const StageHeader& H, uint32_t p) {
+    uint32_t r = 0;
     #pragma unroll
-    for (int i = 0; i < D; i++) { h.wr[i] = make_uint2(0u, 0u); h.cr[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
-    #pragma unroll
-    for (int i = 0; i < Op::NOWN; i++) h.own[i] = 0.0f;
-    if (h.p >= c.end) { h.p = 0xffffffffu; return; }
-    h.m = __ldg(A.cnt + h.p);                             // with the VFD_NEAR_BODY flag, which the epilogue wants
-    op.load_own(h.p, h.own);
-    const uint2* __restrict__ col = ell_list(A.list16, h.p);
-    const float4* __restrict__ cin = reinterpret_cast<const float4*>(op.coef_in()) + ell_base(h.p);
-    #pragma unroll
-    for (int i = 0; i < D; i++) {
-        // the first D groups are loaded whether or not the particle has that many neighbours (the slots exist)
-        h.wr[i] = __ldg(col + (size_t)i * 32);
-        if (Op::COEF & 1) h.cr[i] = __ldg(cin + (size_t)i * 32);
+    for (uint32_t step = 8u; step >= 1u; step >>= 1) {
+        const uint32_t t = r + step;
+        if (H.cellG[43u + 6u * (t & 3u) + 36u * (t >> 2)] <= p) r = t;
     }
+    const uint32_t c = 43u + 6u * (r & 3u) + 36u * (r >> 2);
+    return H.local[c] + (p - H.cellG[c]);
 }
 
-template<class Op, bool STAGED>
-__device__ __forceinline__ void pipe_gather(BatchHead<Op>& h, float (&acc)[Op::NSUM], const StageHeader& H, const Arrays& A,
-                                            const float4* __restrict__ sA, const void* __restrict__ sBv, Op& op) {
-    constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
-    constexpr int D = Op::Cfg::D;
-    const float4* __restrict__ sB = reinterpret_cast<const float4*>(sBv);
-    const float* __restrict__ sB1 = reinterpret_cast<const float*>(sBv);
-    auto gatherB = [&](uint32_t L) -> float4 {
-        if (BBYTES == 16) return sB[L];
-        if (BBYTES == 4) return make_float4(sB1[L], 0.0f, 0.0f, 0.0f);
-        return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    };
-    const uint32_t m = h.m & VFD_COUNT_MASK;
-    if (m == 0u) return;
-    const uint2* __restrict__ col = ell_list(A.list16, h.p);
-    const float4* __restrict__ cin = reinterpret_cast<const float4*>(op.coef_in()) + ell_base(h.p);
-    float4* __restrict__ cout = reinterpret_cast<float4*>(op.coef_out()) + ell_base(h.p);
-    const uint32_t nG = (m + 3u) >> 2;
-    const uint32_t gLast = nG - 1u;                       // past the end a lane re-reads its last group (an L2 hit)
-    auto group = [&](const uint2 wq, const float4 cq, const uint32_t g) {
-        uint32_t L[4];
-        ell_unpack(wq, L);
-        float c[4] = { cq.x, cq.y, cq.z, cq.w };
-        if (g * 4u + 4u <= m) {
-            // Cfg::GW payloads are gathered back to back before their pair terms are accumulated (in list order)
-            #pragma unroll
-            for (int u0 = 0; u0 < 4; u0 += Op::Cfg::GW) {
-                float4 pa[Op::Cfg::GW], pb[Op::Cfg::GW];
-                #pragma unroll
-                for (int u = 0; u < Op::Cfg::GW; u++) {
-                    const uint32_t Lu = L[u0 + u];
-                    if (PIPE_ABLATE & 2) { pa[u] = make_float4(h.own[0] + (float)Lu, h.own[1], h.own[2], 1.0f); pb[u] = pa[u]; }
-                    else if (STAGED) { pa[u] = sA[Lu]; pb[u] = gatherB(Lu); }
-                    else { const uint32_t gi = hdr_local_to_global(H, Lu); pa[u] = op.loadA(gi); pb[u] = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
-                }
-                #pragma unroll
-                for (int u = 0; u < Op::Cfg::GW; u++) op.pair(h.own, pa[u], pb[u], c[u0 + u], acc);
-            }
-        } else {
-            #pragma unroll
-            for (int u = 0; u < 3; u++) {                    // a partial group holds one to three neighbours
-                if (g * 4u + (uint32_t)u < m) {
-                    float4 xa, xb;
-                    if (STAGED) { xa = sA[L[u]]; xb = gatherB(L[u]); }
-                    else { const uint32_t gi = hdr_local_to_global(H, L[u]); xa = op.loadA(gi); xb = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
-                    op.pair(h.own, xa, xb, c[u], acc);
-                } else c[u] = 0.0f;
-            }
-            c[3] = 0.0f;
-        }
-        if (Op::COEF & 2) cout[(size_t)g * 32] = make_float4(c[0], c[1], c[2], c[3]);
-    };
-    uint32_t g0 = 0;
-    for (; g0 + D <= nG; g0 += D) {
-        #pragma unroll
-        for (int i = 0; i < D; i++) {
-            group(h.wr[i], h.cr[i], g0 + (uint32_t)i);
-            const uint32_t gn = (PIPE_ABLATE & 1) ? 0u : min(g0 + (uint32_t)i + D, gLast);
-            h.wr[i] = __ldg(col + (size_t)gn * 32);
-            if (Op::COEF & 1) h.cr[i] = __ldg(cin + (size_t)gn * 32);
-        }
-    }
-    #pragma unroll
-    for (int i = 0; i < D - 1; i++) if (g0 + (uint32_t)i < nG) group(h.wr[i], h.cr[i], g0 + (uint32_t)i);
+template<int BBYTES>
+__device__ __forceinline__ float4 pipe_payload_b(const void* __restrict__ sB, uint32_t L) {
+    if (BBYTES == 16) return reinterpret_cast<const float4*>(sB)[L];
+    if (BBYTES == 8) { const float2 t = reinterpret_cast<const float2*>(sB)[L]; return make_float4(t.x, t.y, 0.0f, 0.0f); }
+    if (BBYTES == 4) return make_float4(reinterpret_cast<const float*>(sB)[L], 0.0f, 0.0f, 0.0f);
+    return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 template<class Op>
-__device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared& ps, const unsigned char* pay, Op& op) {
+__device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared& ps, const unsigned char* pay, unsigned char* streams, Op& op) {
     static_assert(!Op::CUSTOM, "pair ops only");
     constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
+    constexpr int R = Op::Cfg::D, GW = Op::Cfg::GW;
+    constexpr uint32_t CW = Op::Cfg::CW, NONE = 0xffffffffu, SLOT = PipeLayout<Op>::SLOT;
     const uint32_t lane = threadIdx.x & 31u, cw = threadIdx.x >> 5;
-    BatchCursor c;
-    c.k = 0; c.rot = 0; c.b = 0; c.begin = 0; c.end = 0; c.nBatch = 0; c.li = 0; c.done = false;
-    // enter tile c.k: wait until the producers have filled its slot, read its range
+    const uint2* __restrict__ listBase = reinterpret_cast<const uint2*>(A.list16);
+    const float4* __restrict__ cinBase = reinterpret_cast<const float4*>(op.coef_in());
+    float4* __restrict__ coutBase = reinterpret_cast<float4*>(op.coef_out());
+    const unsigned char* payB = pay + (size_t)PipeRing<Op>::SLOTS * 16;
+    // this lane's words in slot 0 of the warp's stream ring
+    const uint32_t ringL = smem_u32(streams) + cw * (uint32_t)R * SLOT + lane * 8u, ringC = ringL - lane * 8u + 256u + lane * 16u;
+
+    // the batch cursor: tile counter of this CTA, batch inside the tile, rotation (batch b of a tile goes to warp
+    // (rot + b) mod CW: consecutive batches of consecutive tiles visit the warps in turn), batches of the tile
+    uint32_t wK = 0, wB = 0, wRot = 0, wN = 0;
+    uint32_t heldK = NONE;                      // tile of the batch being gathered: released after its gather, not by the cursor
+    bool wDone = false;
     auto enter = [&]() {
-        const uint32_t s = c.k % PIPE_STAGES;
-        mbar_wait(&ps.full[s], (c.k / PIPE_STAGES) & 1u);
+        const uint32_t s = wK % PIPE_STAGES;
+        mbar_wait(&ps.full[s], (wK / PIPE_STAGES) & 1u);
         const StageHeader& H = ps.hdr[s];
-        c.begin = H.begin; c.end = H.end; c.li = H.li;
-        if (c.begin == 0xffffffffu) { c.done = true; c.nBatch = 0; return; }
-        c.nBatch = (c.end - c.begin + 31u) >> 5;
-        c.b = (cw + Op::Cfg::CW - c.rot) % Op::Cfg::CW;
+        const uint32_t begin = H.begin;
+        if (begin == NONE) { wDone = true; wN = 0; wB = 0; return; }
+        wN = (H.end - begin + 31u) >> 5;
+        wB = (cw + CW - wRot) % CW;
     };
-    // move to this warp's next batch, releasing every tile it leaves behind (their gathers are complete)
-    auto seek = [&]() {
-        while (!c.done && c.b >= c.nBatch) {
-            c.rot = (c.rot + c.nBatch) % Op::Cfg::CW;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ps.empty[c.k % PIPE_STAGES]);
-            c.k++;
+    // moves the cursor to this warp's next batch, releasing the tiles it leaves behind.  Non-blocking: stops (false) in front
+    // of a tile the producers have not staged yet — the caller still holds a tile the producers may be waiting for.
+    auto seek = [&](bool blocking) -> bool {
+        while (!wDone && wB >= wN) {
+            const uint32_t kn = wK + 1u;
+            if (!blocking && !__any_sync(0xffffffffu, mbar_test(&ps.full[kn % PIPE_STAGES], (kn / PIPE_STAGES) & 1u))) return false;
+            if (wK != heldK) { __syncwarp(); if (lane == 0) mbar_arrive(&ps.empty[wK % PIPE_STAGES]); }
+            wRot = (wRot + wN) % CW;
+            wK = kn;
             enter();
         }
+        return true;
     };
+    auto batch_particle = [&]() -> uint32_t {   // the lane's particle of the cursor's batch
+        const StageHeader& H = ps.hdr[wK % PIPE_STAGES];
+        const uint32_t q = H.begin + (wB << 5) + lane;
+        return q < H.end ? q : NONE;
+    };
+    auto ell_off = [](uint32_t p) -> uint32_t { return (p >> 5) * (uint32_t)(ELL_GROUPS * 32) + (p & 31u); };
+    // one neighbour group of one particle into a ring slot (zeros when `valid` is false: nothing is read from global memory)
+    auto issue = [&](uint32_t slot, uint32_t off, bool valid, bool cold = false) {
+        if ((PIPE_ABLATE & 128) && !cold) return;
+        cp_async8_zfill(ringL + slot * SLOT, listBase + off, valid ? 8u : 0u);
+        if (Op::COEF & 1) cp_async16_zfill(ringC + slot * SLOT, cinBase + off, valid ? 16u : 0u);
+    };
+
     enter();
-    seek();
-    BatchHead<Op> h;
-    if (!c.done) pipe_head_load(h, c, lane, A, op);
-    while (!c.done) {
+    seek(true);
+    if (wDone) return;
+    uint32_t pN = batch_particle(), mN = 0u;
+    if (pN != NONE) mN = __ldg(A.cnt + pN);
+    uint32_t q = 0;                             // ring slot of the next group to be consumed
+    uint32_t issued = 0;                        // groups of the coming batch that are already in the ring (or on their way)
+    for (;;) {
+        // ---- the batch the cursor points at; then the cursor moves on, one batch ahead of the gather -----------------
+        const uint32_t curK = wK, curB = wB, curN = wN;
+        const StageHeader& H = ps.hdr[curK % PIPE_STAGES];
+        const uint32_t p = pN, mf = mN;
+        const uint32_t curLi = H.li;
+        const bool staged = H.staged != 0u;
+        const float4* __restrict__ sA = reinterpret_cast<const float4*>(pay + (size_t)H.base * 16);
+        const void* __restrict__ sB = payB + (size_t)H.base * BBYTES;
+        const uint32_t m = mf & VFD_COUNT_MASK, nG = (m + 3u) >> 2;
+        const uint32_t cOff = p != NONE ? ell_off(p) : 0u;
+        const uint32_t nGw = __reduce_max_sync(0xffffffffu, nG);
+        // the first groups of this batch: normally prefetched during the previous batch; otherwise (first batch, the next tile
+        // was not staged in time, a predecessor with fewer than R groups) they are fetched now
+        if (issued < (uint32_t)R) {
+            cp_async_wait<0>();                 // nothing older may still be on its way into the slots written next
+            #pragma unroll
+            for (int j = 0; j < R; j++) if ((uint32_t)j >= issued) issue((q + (uint32_t)j) % (uint32_t)R, cOff + (uint32_t)j * 32u, (uint32_t)j < nG, true);
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
+        heldK = curK;
+        wB += CW;
+        const bool ahead = seek(false);
+        const bool haveNext = ahead && !wDone;
+        pN = NONE; mN = 0u;
+        if (haveNext) { pN = batch_particle(); if (pN != NONE) mN = __ldg(A.cnt + pN); }
+        const uint32_t nOff = pN != NONE ? ell_off(pN) : 0u;
+        issued = 0;
+
+        float own[Op::NOWN];
+        #pragma unroll
+        for (int i = 0; i < Op::NOWN; i++) own[i] = 0.0f;
+        if (p != NONE) {
+            float4 a, b;
+            if (staged) { const uint32_t L = hdr_own_local(H, p); a = sA[L]; b = pipe_payload_b<BBYTES>(sB, L); }
+            else { a = op.loadA(p); b = Op::NPAY > 1 ? op.loadB(p) : make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+            op.own_from(p, a, b, own);
+        }
         float acc[Op::NSUM];
         #pragma unroll
         for (int s = 0; s < Op::NSUM; s++) acc[s] = 0.0f;
-        {
-            const StageHeader& H = ps.hdr[c.k % PIPE_STAGES];
-            const uint32_t base = H.base;
-            const float4* sA = reinterpret_cast<const float4*>(pay + (size_t)base * 16);
-            const void* sB = pay + (size_t)PIPE_RING * 16 + (size_t)base * BBYTES;
-            if (H.staged != 0u) pipe_gather<Op, true>(h, acc, H, A, sA, sB, op);
-            else                pipe_gather<Op, false>(h, acc, H, A, sA, sB, op);
+
+        // one group of four neighbour slots: GW payloads are gathered back to back before their pair terms are accumulated
+        auto group = [&](const uint2 wq, const float4 cq, const uint32_t g, auto fetch) {
+            uint32_t L[4];
+            ell_unpack(wq, L);
+            float c[4] = { cq.x, cq.y, cq.z, cq.w };
+            if (Op::PAD_SAFE || g * 4u + 4u <= m) {
+                #pragma unroll
+                for (int u0 = 0; u0 < 4; u0 += GW) {
+                    float4 pa[GW], pb[GW];
+                    #pragma unroll
+                    for (int u = 0; u < GW; u++) fetch(L[u0 + u], pa[u], pb[u]);
+                    #pragma unroll
+                    for (int u = 0; u < GW; u++) op.pair(own, pa[u], pb[u], c[u0 + u], acc);
+                }
+            } else {
+                #pragma unroll
+                for (int u = 0; u < 3; u++) {                    // a partial group holds one to three neighbours
+                    if (g * 4u + (uint32_t)u < m) { float4 xa, xb; fetch(L[u], xa, xb); op.pair(own, xa, xb, c[u], acc); }
+                    else c[u] = 0.0f;
+                }
+                c[3] = 0.0f;
+            }
+            if (Op::COEF & 2) coutBase[cOff + g * 32u] = make_float4(c[0], c[1], c[2], c[3]);
+        };
+        if (staged) {
+            // PIPE_ABLATE (tuning builds, wrong results): 32: no gathers, 128: no list/coefficient stream
+            auto fetch = [&](uint32_t L, float4& a, float4& b) {
+                if (PIPE_ABLATE & 32) { a = make_float4(__uint_as_float(L | 0x3f800000u), own[1], own[2], 1.0f); b = a; return; }
+                if (PIPE_ABLATE & 128) L = min(L, 1023u);
+                a = sA[L]; b = pipe_payload_b<BBYTES>(sB, L);
+            };
+            // Every consumed group frees its ring slot, which is refilled at once — R groups ahead in this batch, or with the
+            // next group of the warp's NEXT batch once this one's are all on their way — so R groups per warp are in flight
+            // whatever the consumer is doing: the copy is issued before the group's gathers and arithmetic, and unlike a load
+            // into registers it cannot be moved down to its use by the instruction scheduler.
+            const uint32_t nGnext = ((mN & VFD_COUNT_MASK) + 3u) >> 2;
+            const bool chain = haveNext && nGw >= (uint32_t)R;   // a batch with fewer groups than ring slots hands nothing over
+            #pragma unroll 2
+            for (uint32_t g = 0; g < nGw; g++) {
+                cp_async_wait<R - 1>();         // this lane's words of group g have landed
+                const uint2 wq = lds64(ringL + q * SLOT);
+                float4 cq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (Op::COEF & 1) cq = lds128(ringC + q * SLOT);
+                const uint32_t gn = g + (uint32_t)R;
+                if (gn < nGw) issue(q, cOff + gn * 32u, gn < nG);
+                else if (chain) { issue(q, nOff + issued * 32u, issued < nGnext); issued++; }
+                cp_async_commit();
+                q = q + 1u == (uint32_t)R ? 0u : q + 1u;
+                if (Op::PAD_SAFE) group(wq, cq, g, fetch);      // lanes past their last group hold index 0 / coefficient 0: a pair term of exactly zero
+                else if (g < nG) group(wq, cq, g, fetch);
+            }
+            if (nGw < (uint32_t)R) {
+                // fewer groups than ring slots: the slots behind them hold this batch's unused groups, not the next batch's
+                issued = 0;
+                q = (q + (uint32_t)R - nGw) % (uint32_t)R;       // q back to where this batch started: the next batch refills from there
+            }
+        } else {
+            // a halo box beyond PIPE_CAP: exact path through global memory (rare); the ring is refilled by the next batch
+            auto fetch = [&](uint32_t L, float4& a, float4& b) {
+                const uint32_t gi = hdr_local_to_global(H, L);
+                a = op.loadA(gi); b = Op::NPAY > 1 ? op.loadB(gi) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            };
+            for (uint32_t g = 0; g < nG; g++) {
+                const uint2 wq = __ldg(listBase + cOff + g * 32u);
+                float4 cq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (Op::COEF & 1) cq = __ldg(cinBase + cOff + g * 32u);
+                group(wq, cq, g, fetch);
+            }
+            issued = 0;
         }
-        // what the epilogue needs of the current batch
-        const uint32_t p = h.p, m = h.m, curK = c.k, curB = c.b, curN = c.nBatch, curLi = c.li;
-        float own[Op::NOWN];
-        #pragma unroll
-        for (int i = 0; i < Op::NOWN; i++) own[i] = h.own[i];
-        // next batch: its start-up loads go out now and land during the epilogue
-        c.b += Op::Cfg::CW;
-        seek();
-        if (!c.done) pipe_head_load(h, c, lane, A, op);
-        if (p != 0xffffffffu && !((PIPE_ABLATE & 8) && acc[0] != 12345.0f)) op.finish(p, m, own, acc);
+        // the gathers of this batch are complete: release its tile if the cursor has left it
+        __syncwarp();
+        if (wK != curK && lane == 0) mbar_arrive(&ps.empty[curK % PIPE_STAGES]);
+        heldK = NONE;
+
+        if (p != NONE && !((PIPE_ABLATE & 8) && acc[0] != 12345.0f)) op.finish(p, mf, own, acc);
         if constexpr (Op::NRED > 0) {
             __syncwarp();
-            RedRecord& R = ps.rec[curK % PIPE_RED_RECORDS];
+            RedRecord& R_ = ps.rec[curK % PIPE_RED_RECORDS];
             #pragma unroll
-            for (int q = 0; q < Op::NRED; q++) {
-                double x = p != 0xffffffffu ? (double)op.red[q] : 0.0;
+            for (int k = 0; k < Op::NRED; k++) {
+                double x = p != NONE ? (double)op.red[k] : 0.0;
                 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
                 if (lane == 0) {
-                    if (curB < PIPE_MAX_BATCH - 1) R.bsum[q][curB] = x;
-                    else atomicAdd(&R.bsum[q][PIPE_MAX_BATCH - 1], x);
+                    if (curB < PIPE_MAX_BATCH - 1) R_.bsum[k][curB] = x;
+                    else atomicAdd(&R_.bsum[k][PIPE_MAX_BATCH - 1], x);
                 }
             }
             uint32_t old = 0;
-            if (lane == 0) { __threadfence_block(); old = atomicAdd(&R.count, 1u); }
+            if (lane == 0) { __threadfence_block(); old = atomicAdd(&R_.count, 1u); }
             old = __shfl_sync(0xffffffffu, old, 0);
             if (old + 1u == curN) {                       // this warp completed the tile: fold its batches in order
                 __threadfence_block();
                 const uint32_t nb = min(curN, (uint32_t)PIPE_MAX_BATCH);
                 #pragma unroll
-                for (int q = 0; q < Op::NRED; q++) {
-                    const volatile double* bs = R.bsum[q];
+                for (int k = 0; k < Op::NRED; k++) {
+                    const volatile double* bs = R_.bsum[k];
                     double x = (lane < nb ? bs[lane] : 0.0) + (lane + 32u < nb ? bs[lane + 32u] : 0.0);
                     #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-                    if (lane == 0) A.slotSums[(size_t)q * A.slotStride + curLi] = x;
+                    if (lane == 0) A.slotSums[(size_t)k * A.slotStride + curLi] = x;
                 }
                 __syncwarp();
-                if (lane == 0) { R.bsum[0][PIPE_MAX_BATCH - 1] = 0.0; R.bsum[1][PIPE_MAX_BATCH - 1] = 0.0; R.count = 0u; }
+                if (lane == 0) { R_.bsum[0][PIPE_MAX_BATCH - 1] = 0.0; R_.bsum[1][PIPE_MAX_BATCH - 1] = 0.0; R_.count = 0u; }
             }
         }
+        if (!ahead) {
+            // the next tile was not staged when this batch began: wait for it now (this warp holds no tile any more)
+            seek(true);
+            if (!wDone) { pN = batch_particle(); if (pN != NONE) mN = __ldg(A.cnt + pN); }
+            issued = 0;
+        }
+        if (wDone) break;
     }
+    cp_async_wait<0>();
 }
 
 // Called by all Op::Cfg::THREADS threads of the CTA (after any lookup table has been loaded; contains __syncthreads).
@@ -846,7 +964,7 @@ __device__ __forceinline__ bool pipe_pass(DevState* __restrict__ S, const Arrays
     __syncthreads();
     if (threadIdx.x >= Op::Cfg::CW * 32) pipe_producer(S, A, ps, pay, op, tile0, tile1, checkIndexRange);
     else if constexpr (Op::CUSTOM) pipe_consumer(A, ps, pay, op);
-    else pipe_consumer_pairs(A, ps, pay, op);
+    else pipe_consumer_pairs(A, ps, pay, pay - PipeLayout<Op>::OFF_PAY + PipeLayout<Op>::OFF_STREAM, op);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();                                  // this CTA's slot and field stores before its ticket
@@ -859,8 +977,9 @@ __device__ __forceinline__ bool pipe_pass(DevState* __restrict__ S, const Arrays
 }
 
 __device__ __forceinline__ PipeShared& pipe_header(unsigned char* raw) { return *reinterpret_cast<PipeShared*>(raw); }
-template<int NLUT> __device__ __forceinline__ float* pipe_lut(unsigned char* raw) { return reinterpret_cast<float*>(raw + pipe_header_bytes()); }
-template<int NLUT> __device__ __forceinline__ unsigned char* pipe_pay(unsigned char* raw) { return raw + pipe_header_bytes() + (size_t)NLUT * VFD_LUT_RES * sizeof(float); }
+template<class Op> __device__ __forceinline__ float* pipe_lut(unsigned char* raw) { return reinterpret_cast<float*>(raw + PipeLayout<Op>::OFF_LUT); }
+template<class Op> __device__ __forceinline__ unsigned char* pipe_pay(unsigned char* raw) { return raw + PipeLayout<Op>::OFF_PAY; }
+template<class Op> __device__ __forceinline__ unsigned char* pipe_stream(unsigned char* raw) { return raw + PipeLayout<Op>::OFF_STREAM; }
 
 // The particles this rank owns (multi-GPU: the tiles [tile0, tile1) of the local grid; the tile columns before and
 // after hold ghost copies of the neighbour slabs' edge particles): a contiguous range because tiles are x-slowest.

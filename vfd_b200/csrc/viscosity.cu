@@ -62,7 +62,7 @@ __device__ __forceinline__ bool boundary_samples(const Params& P, float3 xi, flo
 struct ViscSetupOp {
     static constexpr bool CUSTOM = false;
     using Cfg = PipeCfgMany;
-    static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 9, COEF = 3, NRED = 1; // payload (x, y, z, rho); reads the pair's kernel-gradient
+    static constexpr int NPAY = 1, BBYTES = 0, NOWN = 3, NSUM = 9, COEF = 3, NRED = 1, NLUT = 1; // payload (x, y, z, rho); reads the pair's kernel-gradient
     const Params& P; const Arrays& A; Lut K;                                   // factor g_ij (pressure.cu), writes the pair coefficients
     float dt, eps2;
     float red[1];                                          // |b_i|^2 of the lane's particle
@@ -73,9 +73,8 @@ struct ViscSetupOp {
     __device__ __forceinline__ void prefetch_own(uint32_t, uint32_t, uint32_t) const {}
     __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
     __device__ __forceinline__ float4 loadB(uint32_t) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
-    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
-        const float4 x = A.posRho[p]; own[0] = x.x; own[1] = x.y; own[2] = x.z;
-    }
+    static constexpr bool PAD_SAFE = false;
+    __device__ __forceinline__ void own_from(uint32_t, float4 x, float4, float (&own)[NOWN]) const { own[0] = x.x; own[1] = x.y; own[2] = x.z; }
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 xj, float4, float& coef, float (&M)[NSUM]) const {
         const float3 d = f3(o[0], o[1], o[2]) - f3(xj);
         const float g = coef;                             // gradW(d) = g d
@@ -143,17 +142,20 @@ struct ViscSetupOp {
         for (int q = 0; q < 9; q++) A.minv[(size_t)q * P.n + p] = inv[q];
         // V2: b = v (the boundary term multiplies a zero vector: DFSPHKernels.cu:744-754), g = v + dv_prev
         const float4 v = A.vel[p], dv = A.dv[p];
-        A.cgG[p] = make_float4(v.x + dv.x, v.y + dv.y, v.z + dv.z, 0.0f);
+        const float3 g0 = f3(v.x + dv.x, v.y + dv.y, v.z + dv.z);
+        A.cgG[p] = make_float4(g0.x, g0.y, g0.z, 0.0f);
+        A.cgXG[p] = make_float4(xi.x, xi.y, xi.z, g0.x);     // what the first mat-vec gathers per neighbour (see ViscMatvecOp)
+        A.cgGyz[p] = make_float2(g0.y, g0.z);
         red[0] = (v.x * v.x + v.y * v.y) + v.z * v.z;
     }
 };
 
 __global__ void __launch_bounds__(ViscSetupOp::Cfg::THREADS, 1) k_visc_setup(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, const float* __restrict__ lutG) {
     PipeShared& ps = pipe_header(smemRaw);
-    float* sG = pipe_lut<1>(smemRaw);                     // the boundary-friction samples still need the table
+    float* sG = pipe_lut<ViscSetupOp>(smemRaw);                     // the boundary-friction samples still need the table
     load_lut_tile(sG, lutG);
     ViscSetupOp op{ P, A, Lut{ nullptr, sG, P.lutInvStep, P.lutRadius, P.lutRadius2 }, S->dt, 0.01f * P.h2, { 0.0f } };
-    if (pipe_pass(S, A, ps, pipe_pay<1>(smemRaw), op, P.tile0, P.tile1)) {
+    if (pipe_pass(S, A, ps, pipe_pay<ViscSetupOp>(smemRaw), op, P.tile0, P.tile1)) {
         double tot[1];
         fold_slots<1>(tot, A.slotSums, __ldg(A.tileList), A.slotStride, ps.red);
         if (threadIdx.x == 0) finish_reduction<1>(SITE_VISC_BB, P, S, tot);
@@ -169,18 +171,23 @@ __device__ __forceinline__ float3 mat_vec(const float* __restrict__ minv, uint32
     return f3(M[0] * r.x + M[3] * r.y + M[6] * r.z, M[1] * r.x + M[4] * r.y + M[7] * r.z, M[2] * r.x + M[5] * r.y + M[8] * r.z);
 }
 
+// What a pair needs of the neighbour is its position and the vector's value there: six floats.  They are kept as ONE
+// 16-byte word (x, y, z, v.x) and one 8-byte word (v.y, v.z) per particle — A.cgXG/cgGyz for the start-up product with g,
+// A.cgXP/cgPyz for the search direction p — so a neighbour costs an LDS.128 and an LDS.64 from the shared-memory stage
+// (six wavefronts per warp and slot at best) instead of two LDS.128 on (x, y, z, rho) and (v, 0): the pass is bound by
+// the shared-memory/L1 data path (profiles/r01_ncu_full_step.txt: 17.2 M wavefronts = 59 us of a 117-us launch).
+// The position part never changes during a solve; whoever rewrites p rewrites the whole 16-byte word.
 template<bool INIT>
 struct ViscMatvecOp {
-    static constexpr bool CUSTOM = false;
-    using Cfg = PipeCfgWide;
-    static constexpr int NPAY = 2, NOWN = 7, NSUM = 3, COEF = 1, NRED = INIT ? 2 : 1;     // payload: (x, y, z, rho), the vector's (x, y, z); reads the pair coefficients
+    static constexpr bool CUSTOM = false, PAD_SAFE = true;      // the pair term is linear in the pair coefficient
+    using Cfg = PipeCfgMatvec;
+    static constexpr int NPAY = 2, NOWN = 7, NSUM = 3, COEF = 1, NRED = INIT ? 2 : 1, NLUT = 0;
     const Params& P; const Arrays& A;
-    const float4* __restrict__ x;    // the vector the operator is applied to: g (INIT) or the search direction p
     float dt;
     float red[2];                    // INIT: |r_i|^2, r_i.z_i; else p_i.q_i
-    static constexpr int BBYTES = 16;
-    __device__ __forceinline__ const float4* srcA() const { return A.posRho; }
-    __device__ __forceinline__ const void* srcB() const { return x; }
+    static constexpr int BBYTES = 8;
+    __device__ __forceinline__ const float4* srcA() const { return INIT ? A.cgXG : A.cgXP; }
+    __device__ __forceinline__ const void* srcB() const { return INIT ? A.cgGyz : A.cgPyz; }
     __device__ __forceinline__ const float* coef_in() const { return A.coef; }
     __device__ __forceinline__ float* coef_out() const { return nullptr; }
     __device__ __forceinline__ void prefetch_own(uint32_t pt, uint32_t b0, uint32_t e0) const {
@@ -190,15 +197,15 @@ struct ViscMatvecOp {
         }
         if (INIT && pt == 8) l2_prefetch(A.vel, (size_t)b0 * 16, (size_t)e0 * 16);
     }
-    __device__ __forceinline__ float4 loadA(uint32_t g) const { return A.posRho[g]; }
-    __device__ __forceinline__ float4 loadB(uint32_t g) const { return x[g]; }
-    __device__ __forceinline__ void load_own(uint32_t p, float (&own)[NOWN]) const {
-        const float4 xr = A.posRho[p], v = x[p];
-        own[0] = xr.x; own[1] = xr.y; own[2] = xr.z; own[3] = v.x; own[4] = v.y; own[5] = v.z; own[6] = xr.w;
+    __device__ __forceinline__ float4 loadA(uint32_t g) const { return srcA()[g]; }
+    __device__ __forceinline__ float4 loadB(uint32_t g) const { const float2 t = reinterpret_cast<const float2*>(srcB())[g]; return make_float4(t.x, t.y, 0.0f, 0.0f); }
+    __device__ __forceinline__ void own_from(uint32_t p, float4 a, float4 b, float (&own)[NOWN]) const {
+        own[0] = a.x; own[1] = a.y; own[2] = a.z; own[3] = a.w; own[4] = b.x; own[5] = b.y;
+        own[6] = __ldg(A.rho + p);                          // for the epilogue; in flight during the gather
     }
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
         const float dx = o[0] - a.x, dy = o[1] - a.y, dz = o[2] - a.z;
-        const float w = c * __fmaf_rn(o[5] - b.z, dz, __fmaf_rn(o[4] - b.y, dy, (o[3] - b.x) * dx));
+        const float w = c * __fmaf_rn(o[5] - b.y, dz, __fmaf_rn(o[4] - b.x, dy, (o[3] - a.w) * dx));
         acc[0] = __fmaf_rn(w, dx, acc[0]); acc[1] = __fmaf_rn(w, dy, acc[1]); acc[2] = __fmaf_rn(w, dz, acc[2]);
     }
     __device__ __forceinline__ void finish(uint32_t p, uint32_t mf, const float (&o)[NOWN], const float (&acc)[NSUM]) {
@@ -225,7 +232,8 @@ struct ViscMatvecOp {
             const float3 r = f3(A.vel[p]) - q;
             const float3 z = mat_vec(A.minv, P.n, p, r);
             A.cgR[p] = make_float4(r.x, r.y, r.z, 0.0f);
-            A.cgP[p] = make_float4(z.x, z.y, z.z, 0.0f);
+            A.cgXP[p] = make_float4(xi.x, xi.y, xi.z, z.x);
+            A.cgPyz[p] = make_float2(z.y, z.z);
             red[0] = (r.x * r.x + r.y * r.y) + r.z * r.z;
             red[1] = (r.x * z.x + r.y * z.y) + r.z * z.z;
         } else {
@@ -239,8 +247,8 @@ template<bool INIT>
 __global__ void __launch_bounds__(ViscMatvecOp<INIT>::Cfg::THREADS, 1) k_visc_matvec_pipe(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
     if (!INIT && S->viscActive != 1u) return;
     PipeShared& ps = pipe_header(smemRaw);
-    ViscMatvecOp<INIT> op{ P, A, INIT ? A.cgG : A.cgP, S->dt, { 0.0f, 0.0f } };
-    if (pipe_pass(S, A, ps, pipe_pay<0>(smemRaw), op, P.tile0, P.tile1)) {
+    ViscMatvecOp<INIT> op{ P, A, S->dt, { 0.0f, 0.0f } };
+    if (pipe_pass(S, A, ps, pipe_pay<ViscMatvecOp<INIT>>(smemRaw), op, P.tile0, P.tile1)) {
         double tot[2] = { 0.0, 0.0 };
         if (INIT) {
             fold_slots<2>(tot, A.slotSums, __ldg(A.tileList), A.slotStride, ps.red);
@@ -260,7 +268,9 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_update(Params P, Arrays A, Dev
     const float alpha = S->alpha;
     float s0 = 0.0f, s1 = 0.0f;
     FOR_EACH_OWNED(p) {
-        const float4 pp = A.cgP[p], qq = A.cgQ[p];
+        const float4 xp = A.cgXP[p], qq = A.cgQ[p];
+        const float2 pyz = A.cgPyz[p];
+        const float3 pp = f3(xp.w, pyz.x, pyz.y);
         float4 g = A.cgG[p], r = A.cgR[p];
         g.x = g.x + pp.x * alpha; g.y = g.y + pp.y * alpha; g.z = g.z + pp.z * alpha;
         r.x = r.x - qq.x * alpha; r.y = r.y - qq.y * alpha; r.z = r.z - qq.z * alpha;
@@ -287,9 +297,10 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_direction(Params P, Arrays A, 
     OWNED_INDEX(p);
     const float beta = S->beta;
     const float4 z = A.cgZ[p];
-    float4 d = A.cgP[p];
-    d.x = d.x * beta + z.x; d.y = d.y * beta + z.y; d.z = d.z * beta + z.z;
-    A.cgP[p] = d;
+    float4 xp = A.cgXP[p];
+    float2 pyz = A.cgPyz[p];
+    xp.w = xp.w * beta + z.x; pyz.x = pyz.x * beta + z.y; pyz.y = pyz.y * beta + z.z;
+    A.cgXP[p] = xp; A.cgPyz[p] = pyz;
 }
 
 // V5: a += (g - v)/dt ; dv = g - v
@@ -316,14 +327,14 @@ static void pipe_attr(Kern kern, size_t smem) {
 }
 
 void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG) {
-    const size_t sp = pipe_smem_bytes<1, 16, 0>();
+    const size_t sp = pipe_smem_bytes<ViscSetupOp>();
     pipe_attr(k_visc_setup, sp);
     LaunchScope ls(L, KID_VISC_SETUP);
     k_visc_setup<<<L.numSMs, ViscSetupOp::Cfg::THREADS, sp, L.stream>>>(P, A, S, lutG);
 }
 
 void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init) {
-    const size_t sp = pipe_smem_bytes<0, 16, 16>();
+    const size_t sp = pipe_smem_bytes<ViscMatvecOp<false>>();
     LaunchScope ls(L, init ? KID_VISC_MATVEC0 : KID_VISC_MATVEC);
     if (init) { pipe_attr(k_visc_matvec_pipe<true>, sp); k_visc_matvec_pipe<true><<<L.numSMs, ViscMatvecOp<true>::Cfg::THREADS, sp, L.stream>>>(P, A, S); }
     else      { pipe_attr(k_visc_matvec_pipe<false>, sp); k_visc_matvec_pipe<false><<<L.numSMs, ViscMatvecOp<false>::Cfg::THREADS, sp, L.stream>>>(P, A, S); }
