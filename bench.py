@@ -37,7 +37,7 @@ ALGO_BYTES = {
     "div_source": (68, 4), "div_accel": (56, 4), "div_solve": (72, 4), "div_finish": (96, 4),
     "press_source": (68, 4), "press_accel": (56, 4), "press_solve": (72, 4), "press_finish": (88, 4),
     "st_classify": (48, 4), "st_smooth": (56, 4), "st_apply": (76, 0),
-    "visc_setup": (120, 4), "visc_matvec0": (136, 4), "visc_matvec": (68, 4), "visc_update": (148, 0), "visc_direction": (48, 0), "visc_apply": (80, 0),
+    "visc_setup": (120, 4), "visc_matvec0": (136, 4), "visc_matvec": (68, 4), "visc_update": (156, 0), "visc_direction": (64, 0), "visc_step": (164, 0), "visc_apply": (80, 0),
     "cfl": (32, 0), "velocity": (48, 0), "position": (48, 0),
 }
 

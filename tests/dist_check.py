@@ -1,9 +1,10 @@
-"""N-rank vs 1-rank consistency of the slab decomposition (run under torch.distributed.run on a multi-GPU box):
+"""tests/dist_check.py — a script run by tests/test_gpu_dist.py (and by hand) under torch.distributed.run, not collected by pytest.
+N-rank vs 1-rank consistency of the slab decomposition (run under torch.distributed.run on a multi-GPU box):
 the same scene is stepped K times by the distributed solver and, on rank 0, by a plain single-GPU solver; the
 gathered distributed state must agree with the single-GPU state to rounding (summation orders differ)."""
 import os, sys, json
 import numpy as np
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import torch.distributed as dist

@@ -57,10 +57,11 @@ def make_pair(cfg, side):
     return sim, ref, pos
 
 
-@pytest.mark.parametrize("cfg", ["dfsph", "full"])
-def test_one_step_vs_live_oracle_27k(cfg, lib_built):
+@pytest.mark.parametrize("cfg,side", [("dfsph", 30), ("full", 30), ("full", 58)])
+def test_one_step_vs_live_oracle(cfg, side, lib_built):
+    """27 000 particles (BASELINE.json config 1's size) and 195 112 (twice config 2's) with viscosity and surface tension."""
     from oracle import refsim
-    sim, ref, pos = make_pair(cfg, 30)
+    sim, ref, pos = make_pair(cfg, side)
     sim.steps(40)                                   # evolve on the GPU: contact with the floor, non-trivial neighbourhoods
     sim.synchronize()
     state = sim.particles()
@@ -97,19 +98,21 @@ def test_one_step_vs_live_oracle_27k(cfg, lib_built):
     assert not bad, "fields beyond tolerance %s:\n%s" % ({k: "%.1e" % tol[k] for k in bad}, parity.format_errors(bad))
 
 
-def test_trajectory_100_steps_vs_live_oracle(lib_built):
-    """100 steps from the same initial lattice (DFSPH, pinned iteration counts, 8 000 particles dropped onto the floor).
+@pytest.mark.parametrize("cfg", ["dfsph", "full"])
+def test_trajectory_100_steps_vs_live_oracle(cfg, lib_built):
+    """100 steps from the same initial lattice (pinned Jacobi iteration counts, 8 000 particles dropped onto the floor; "full"
+    adds the implicit viscosity PCG and surface tension).
     A particle system amplifies rounding differences exponentially, and the reference's own arithmetic is not
     reproducible (reduction and neighbour order): the yardstick is therefore the reference against itself (OpenMP threads
     vs one thread).  Stated tolerance: the mean displacement between our trajectory and the reference's stays within 3x
     the reference's own mean self-displacement (floor: half a particle diameter), and the bulk quantities — centre of
     mass and the 99.9 % extent of the fluid — within 3x the reference's own deviation (floors: 0.1 and 0.5 diameters)."""
     from oracle import refsim
-    sim, ref, pos = make_pair("dfsph", 20)
+    sim, ref, pos = make_pair(cfg, 20)
     with refsim.quiet_stdout():
         ref.step(100)
         a = ref.particles()["Position"].astype(np.float64)
-        ref2 = refsim.RefSim(refsim.Desc(**CONFIGS["dfsph"]), serial=True)
+        ref2 = refsim.RefSim(refsim.Desc(**CONFIGS[cfg]), serial=True)
         p0, box, res = scene(20)
         ref2.set_particles(p0)
         ref2.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
@@ -122,8 +125,8 @@ def test_trajectory_100_steps_vs_live_oracle(lib_built):
     b = sim.particles()["Position"].astype(np.float64)
     d = np.sqrt(((a - b) ** 2).sum(axis=1)) / D
     dself = np.sqrt(((a - a2) ** 2).sum(axis=1)) / D
-    print("\n100-step trajectory, %d particles: displacement vs the oracle mean %.3e d, 99%% %.3e d, max %.3e d; the oracle against itself "
-          "mean %.3e d, 99%% %.3e d, max %.3e d" % (len(d), d.mean(), np.percentile(d, 99), d.max(), dself.mean(), np.percentile(dself, 99), dself.max()))
+    print("\n[%s] 100-step trajectory, %d particles: displacement vs the oracle mean %.3e d, 99%% %.3e d, max %.3e d; the oracle against itself "
+          "mean %.3e d, 99%% %.3e d, max %.3e d" % (cfg, len(d), d.mean(), np.percentile(d, 99), d.max(), dself.mean(), np.percentile(dself, 99), dself.max()))
     com, com_self = np.abs(a.mean(axis=0) - b.mean(axis=0)).max() / D, np.abs(a.mean(axis=0) - a2.mean(axis=0)).max() / D
     q = lambda x: np.percentile(x, 99.9, axis=0)           # the splash front, without the single farthest droplet
     ext, ext_self = np.abs(q(a) - q(b)).max() / D, np.abs(q(a) - q(a2)).max() / D
@@ -133,6 +136,66 @@ def test_trajectory_100_steps_vs_live_oracle(lib_built):
     assert d.mean() <= max(3.0 * dself.mean(), 0.5), (d.mean(), dself.mean())
     assert com <= max(3.0 * com_self, 0.1), (com, com_self)
     assert ext <= max(3.0 * ext_self, 0.5), (ext, ext_self)
+
+
+@pytest.mark.parametrize("lattice", ["plain", "jittered", "evolved"])
+def test_default_search_matches_the_reference_cuda_build(lattice, lib_built):
+    """The search as benchmarked (VFD_OPT_SEARCH_FMA = 1, the default: d^2 contracted the way nvcc compiles
+    ParticleSearchKernels.cu:123-126) against the reference's own search compiled by nvcc for this GPU
+    (oracle/_ref/libvfd_ref_gpu.so): neighbour sets bit-exact — also on the plain lattice, where six pairs per particle lie at
+    exactly the support radius and membership hangs on the last bit of d^2."""
+    from oracle import refsim
+    from vfd_b200 import api
+    if not refsim.available("gpu"):
+        pytest.skip("oracle/_ref/libvfd_ref_gpu.so not built (oracle/build_ref.py --gpu)")
+    side = 30
+    pos, box, res = scene(side)
+    if lattice == "plain":
+        pos = api.block_positions(side, side, side, R, origin=(4 * D, 4 * D, 4 * D))
+    if lattice == "evolved":
+        vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R)
+        s0 = api.DFSPHSimulation(api.DFSPHSimulationDescription(FrameCount=0, **CONFIGS["dfsph"]))
+        s0.SetFluidObjects([api.FluidObject(pos)])
+        s0.SetRigidBodies([vm])
+        s0.steps(60)
+        s0.synchronize()
+        pos = np.ascontiguousarray(s0.particles()["Position"], np.float32)
+        s0.close()
+    sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(FrameCount=0, **CONFIGS["dfsph"]))      # options untouched: FMA search
+    sim.SetFluidObjects([api.FluidObject(pos)])
+    sim.find_neighbors()
+    with refsim.quiet_stdout():
+        ref = refsim.RefSim(refsim.Desc(**CONFIGS["dfsph"]), kind="gpu")
+        ref.set_particles(pos)
+        ref.find_neighbors()
+        theirs = ref.neighbors()
+    ours = sim.neighbors()
+    mism = parity.neighbor_mismatches(ours, theirs)
+    print("\n[%s] %d particles, mean neighbours %.2f (reference %.2f)" % (lattice, len(pos), ours[0].mean(), theirs[0].mean()))
+    assert not mism, "neighbour sets differ for %d of %d particles, e.g. %s" % (len(mism), len(pos), mism[:5])
+    sim.close()
+
+
+def test_fused_pcg_vector_kernel_matches_the_two_kernel_path(lib_built, monkeypatch):
+    """The cooperative update+direction kernel of the PCG (viscosity.cu: k_visc_step) against the two separate kernels it
+    replaces (VFD_TUNE5 = 1 selects them; the path every multi-rank run takes): bit-identical states."""
+    from vfd_b200 import api
+    pos, box, res = scene(40)
+    vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R)
+    states, its = [], []
+    for knob in ("0", "1"):
+        monkeypatch.setenv("VFD_TUNE5", knob)
+        sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(FrameCount=0, **CONFIGS["full"]))
+        sim.SetFluidObjects([api.FluidObject(pos)])
+        sim.SetRigidBodies([vm])
+        sim.steps(45)
+        sim.synchronize()
+        states.append(sim.particles())
+        its.append(int(sim.GetDebugInfo().ViscositySolverIterationCount))
+        sim.close()
+    assert its[0] == its[1] and its[0] > 0, its
+    for f in parity.ALL_FIELDS:
+        assert np.array_equal(states[0][f].view(np.uint32), states[1][f].view(np.uint32)), "field %s differs between the fused and the two-kernel PCG" % f
 
 
 def test_runs_are_bit_reproducible_and_neighbours_symmetric_200k(lib_built):

@@ -94,6 +94,7 @@ struct DevState {
     // dynamic tile queue of the pipelined passes (tile.cuh): next entry of the tile list, CTAs that have finished the
     // running pass (the last one resets both)
     uint32_t tileCursor, doneCtas;
+    uint32_t stepGen;           // generation counter of the grid barrier of the fused PCG vector kernel (viscosity.cu: k_visc_step)
 };
 
 struct float3x3 { float m[9]; };   // column-major like glm::mat3x3: m[3*c + r]

@@ -129,7 +129,7 @@ const char* const kKernelNames[KID_COUNT] = {
     "boundary", "density_factor",
     "div_source", "div_accel", "div_solve", "div_finish",
     "st_classify", "st_smooth", "st_apply",
-    "visc_setup", "visc_matvec0", "visc_matvec", "visc_update", "visc_direction", "visc_apply",
+    "visc_setup", "visc_matvec0", "visc_matvec", "visc_update", "visc_direction", "visc_step", "visc_apply",
     "cfl", "velocity",
     "press_source", "press_accel", "press_solve", "press_finish",
     "position", "clear_acc", "io" };
@@ -617,9 +617,11 @@ int Solver::step() {
         launch_viscosity_matvec(L, P, A, dState, true);
         RC(reduce(SITE_VISC_INIT));
         RC(halo4(A.cgXP)); RC(halo2(A.cgPyz));
+        const bool fusedStep = viscosity_step_fits(L, P);
         auto iteration = [&]() -> int {
             launch_viscosity_matvec(L, P, A, dState, false);
             RC(reduce(SITE_VISC_PQ));
+            if (fusedStep) { CK((cudaError_t)launch_viscosity_step(L, P, A, dState)); return VFD_OK; }
             launch_viscosity_update(L, P, A, dState);
             RC(reduce(SITE_VISC_UPDATE));
             launch_viscosity_direction(L, P, A, dState);

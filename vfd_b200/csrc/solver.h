@@ -60,7 +60,7 @@ enum KernelId {
     KID_BOUNDARY, KID_DENSITY_FACTOR,
     KID_DIV_SOURCE, KID_DIV_ACCEL, KID_DIV_SOLVE, KID_DIV_FINISH,
     KID_ST_CLASSIFY, KID_ST_SMOOTH, KID_ST_APPLY,
-    KID_VISC_SETUP, KID_VISC_MATVEC0, KID_VISC_MATVEC, KID_VISC_UPDATE, KID_VISC_DIRECTION, KID_VISC_APPLY,
+    KID_VISC_SETUP, KID_VISC_MATVEC0, KID_VISC_MATVEC, KID_VISC_UPDATE, KID_VISC_DIRECTION, KID_VISC_STEP, KID_VISC_APPLY,
     KID_CFL, KID_VELOCITY,
     KID_PRESS_SOURCE, KID_PRESS_ACCEL, KID_PRESS_SOLVE, KID_PRESS_FINISH,
     KID_POSITION, KID_CLEAR_ACC, KID_IO, KID_COUNT
@@ -127,6 +127,8 @@ void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A
 void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init);
 void launch_viscosity_update(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
 void launch_viscosity_direction(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
+bool viscosity_step_fits(const LaunchCfg& L, const Params& P);
+int launch_viscosity_step(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);   // update + direction fused (cudaError_t as int)
 void launch_viscosity_apply(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
 
 // dump / restore helpers (original particle order <-> sorted SoA)

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_update(Params P, Arrays A, Dev
     if (S->viscActive != 1u) return;
     __shared__ double shRed[64];
     const float alpha = S->alpha;
-    float s0 = 0.0f, s1 = 0.0f;
+    double s0 = 0.0, s1 = 0.0;                  // sums of fp32 terms in fp64: the same value whatever the order (and the kernel)
     FOR_EACH_OWNED(p) {
         const float4 xp = A.cgXP[p], qq = A.cgQ[p];
         const float2 pyz = A.cgPyz[p];
@@ -277,10 +277,10 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_update(Params P, Arrays A, Dev
         A.cgG[p] = g; A.cgR[p] = r;
         const float3 z = mat_vec(A.minv, P.n, p, f3(r));
         A.cgZ[p] = make_float4(z.x, z.y, z.z, 0.0f);
-        s0 += (r.x * r.x + r.y * r.y) + r.z * r.z;
-        s1 += (r.x * z.x + r.y * z.y) + r.z * z.z;
+        s0 += (double)((r.x * r.x + r.y * r.y) + r.z * r.z);
+        s1 += (double)((r.x * z.x + r.y * z.y) + r.z * z.z);
     }
-    double v[2] = { (double)s0, (double)s1 };
+    double v[2] = { s0, s1 };
     if (block_reduce_publish<2>(v, A.partials, &S->ticket[6], shRed)) {
         double tot[2];
         last_block_fold<2>(tot, A.partials, shRed);
@@ -301,6 +301,79 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_direction(Params P, Arrays A, 
     float2 pyz = A.cgPyz[p];
     xp.w = xp.w * beta + z.x; pyz.x = pyz.x * beta + z.y; pyz.y = pyz.y * beta + z.z;
     A.cgXP[p] = xp; A.cgPyz[p] = pyz;
+}
+
+// ---- the vector work of one PCG iteration in ONE launch -------------------------------------------------------------
+// k_visc_update and k_visc_direction are separated by a grid-wide decision (|r|^2 against the threshold, beta) and nothing
+// else: the direction update needs z and p of the SAME particle only.  On one GPU, with a scene that fits (<= STEP_MAXK x 1024
+// particles per SM), both run as one cooperative launch of one CTA per SM: each CTA keeps the (x, y, z, p) words of its
+// particles in shared memory and z in registers across a grid barrier (last block folds the partial sums, takes the solver's
+// decision — control.cuh — and releases the others), then writes p = z + beta p.  Per iteration this saves a launch, the write
+// and re-read of z and the re-read of p: 164 B per particle instead of 220.  Same expressions, same values as the two kernels.
+#define STEP_THREADS 1024
+#define STEP_MAXK 8
+__global__ void __launch_bounds__(STEP_THREADS, 1) k_visc_step(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+    if (*(volatile uint32_t*)&S->viscActive != 1u) return;       // every block reads this before the last one can change it
+    __shared__ double shRed[64];
+    __shared__ uint32_t shGo;
+    float4* sXP = reinterpret_cast<float4*>(smemRaw);
+    float2* sPyz = reinterpret_cast<float2*>(smemRaw + (size_t)STEP_MAXK * STEP_THREADS * sizeof(float4));
+    const uint32_t gen0 = *(volatile uint32_t*)&S->stepGen;
+    uint32_t ownB, ownE;
+    owned_range(P, A.cellBegin, ownB, ownE);
+    const uint32_t chunk = ((ownE - ownB + gridDim.x - 1u) / gridDim.x + 31u) & ~31u;
+    const uint32_t lo = min(ownB + blockIdx.x * chunk, ownE), hi = min(lo + chunk, ownE);
+    const float alpha = S->alpha;
+    float z[STEP_MAXK][3];
+    double s0 = 0.0, s1 = 0.0;
+    #pragma unroll
+    for (int k = 0; k < STEP_MAXK; k++) {
+        const uint32_t i = (uint32_t)k * STEP_THREADS + threadIdx.x, p = lo + i;
+        z[k][0] = z[k][1] = z[k][2] = 0.0f;
+        if (p < hi) {
+            const float4 xp = A.cgXP[p], qq = A.cgQ[p];
+            const float2 pyz = A.cgPyz[p];
+            const float3 pp = f3(xp.w, pyz.x, pyz.y);
+            float4 g = A.cgG[p], r = A.cgR[p];
+            g.x = g.x + pp.x * alpha; g.y = g.y + pp.y * alpha; g.z = g.z + pp.z * alpha;
+            r.x = r.x - qq.x * alpha; r.y = r.y - qq.y * alpha; r.z = r.z - qq.z * alpha;
+            A.cgG[p] = g; A.cgR[p] = r;
+            const float3 zz = mat_vec(A.minv, P.n, p, f3(r));
+            z[k][0] = zz.x; z[k][1] = zz.y; z[k][2] = zz.z;
+            sXP[i] = xp; sPyz[i] = pyz;
+            s0 += (double)((r.x * r.x + r.y * r.y) + r.z * r.z);
+            s1 += (double)((r.x * zz.x + r.y * zz.y) + r.z * zz.z);
+        }
+    }
+    double v[2] = { s0, s1 };
+    if (block_reduce_publish<2>(v, A.partials, &S->ticket[6], shRed)) {
+        double tot[2];
+        last_block_fold<2>(tot, A.partials, shRed);
+        if (threadIdx.x == 0) {
+            finish_reduction<2>(SITE_VISC_UPDATE, P, S, tot);
+            S->ticket[6] = 0;
+            __threadfence();
+            atomicAdd(&S->stepGen, 1u);                         // release: the decision and beta are visible
+        }
+    }
+    if (threadIdx.x == 0) {
+        while (*(volatile uint32_t*)&S->stepGen == gen0) { }
+        __threadfence();
+        shGo = *(volatile uint32_t*)&S->viscActive;
+    }
+    __syncthreads();
+    if (shGo != 1u) return;                                      // converged (or the iteration cap): no next direction
+    const float beta = *(volatile float*)&S->beta;
+    #pragma unroll
+    for (int k = 0; k < STEP_MAXK; k++) {
+        const uint32_t i = (uint32_t)k * STEP_THREADS + threadIdx.x, p = lo + i;
+        if (p < hi) {
+            float4 xp = sXP[i];
+            float2 pyz = sPyz[i];
+            xp.w = xp.w * beta + z[k][0]; pyz.x = pyz.x * beta + z[k][1]; pyz.y = pyz.y * beta + z[k][2];
+            A.cgXP[p] = xp; A.cgPyz[p] = pyz;
+        }
+    }
 }
 
 // V5: a += (g - v)/dt ; dv = g - v
@@ -344,6 +417,18 @@ void launch_viscosity_update(const LaunchCfg& L, const Params& P, const Arrays& 
     const uint32_t g2 = std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 8u));
     LaunchScope ls(L, KID_VISC_UPDATE);
     k_visc_update<<<g2, VFD_TPB, 0, L.stream>>>(P, A, S);
+}
+// true when the fused kernel can carry this scene: one rank (the decision needs no exchange) and <= STEP_MAXK x 1024 particles per SM
+bool viscosity_step_fits(const LaunchCfg& L, const Params& P) {
+    return P.nRanks == 1 && P.tune[5] != 1 && (uint64_t)P.n <= (uint64_t)L.numSMs * STEP_MAXK * STEP_THREADS - 32ull * (uint64_t)L.numSMs;
+}
+int launch_viscosity_step(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
+    const size_t sm = (size_t)STEP_MAXK * STEP_THREADS * (sizeof(float4) + sizeof(float2));
+    pipe_attr(k_visc_step, sm);
+    LaunchScope ls(L, KID_VISC_STEP);
+    void* args[] = { (void*)&P, (void*)&A, (void*)&S };
+    // cooperative: the grid barrier needs every CTA resident (one per SM; the launch fails rather than deadlock)
+    return (int)cudaLaunchCooperativeKernel((const void*)k_visc_step, dim3((unsigned)L.numSMs), dim3(STEP_THREADS), args, sm, L.stream);
 }
 void launch_viscosity_direction(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     LaunchScope ls(L, KID_VISC_DIRECTION);
