@@ -393,4 +393,12 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner, the reference's banners)
+    # are routed to stderr while the bench runs; print() keeps writing to the real stdout
+    sys.stdout.flush()
+    _real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real, "w")
+    rc = main()
+    sys.stdout.flush()
+    sys.exit(rc)

@@ -55,6 +55,9 @@ struct Params {
     uint32_t minPressIt, maxPressIt, minDivIt, maxDivIt, minViscIt, maxViscIt;
     int   searchFma;
     int   tune[8];              // experiment knobs (env VFD_TUNE0..7; 0 = default behaviour)
+    // several ranks: every rank's control block (control.cuh: PeerCtl) mapped into this process over NVLink (CUDA IPC), own one
+    // included; null when the ranks talk through NCCL only
+    void* peerCtl[8];
 };
 
 // Device-resident mutable scalars: the time step and all solver control state.  Kernels read dt

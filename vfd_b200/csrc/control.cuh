@@ -10,6 +10,19 @@
 
 namespace vfd {
 
+// Per-rank control block in peer-mapped memory: what the ranks of a decomposition write into EACH OTHER over NVLink.
+//   red / redFlag   all-reduce of a solver decision's two doubles: rank r stores its partial result into slot [seq & 3][r] of
+//                   every rank's block, then the sequence number into redFlag; every rank sums the eight entries in rank order
+//                   (the same value everywhere) as soon as all flags show the number — no collective launch, no host;
+//   haloReady/Data  hand-shake of a halo exchange with the left [0] / right [1] neighbour (distributed.cu: k_halo_exchange).
+struct PeerCtl {
+    double red[4][8][2];
+    uint32_t redFlag[4][8];
+    uint32_t haloReady[2], haloData[2];
+    uint32_t redSeq, haloSeq;             // the owner's own sequence numbers (never reset while the slab lives: a restarted bake goes on counting)
+    uint32_t pad[26];
+};
+
 enum ReductionSite { SITE_DIV = 0, SITE_PRESS, SITE_CFL, SITE_VISC_BB, SITE_VISC_INIT, SITE_VISC_PQ, SITE_VISC_UPDATE, SITE_COUNT };
 
 #ifdef __CUDACC__
@@ -85,10 +98,38 @@ __device__ __forceinline__ void control_site(int site, const Params& P, DevState
     }
 }
 
+// All-reduce (sum or max) of two doubles over the ranks through peer memory; called by ONE thread per rank, in the same
+// sequence on every rank (the solver's control flow is identical everywhere).  A rank can be at most one reduction ahead of
+// another (it needs the other's contribution to finish), so four slots used in turn never collide.
+__device__ __forceinline__ void peer_allreduce(const Params& P, DevState* S, double (&v)[2], bool isMax) {
+    PeerCtl* me = reinterpret_cast<PeerCtl*>(P.peerCtl[P.rank]);
+    const uint32_t seq = me->redSeq + 1u, slot = seq & 3u;
+    me->redSeq = seq;
+    for (uint32_t r = 0; r < P.nRanks; r++) {
+        volatile double* d = reinterpret_cast<PeerCtl*>(P.peerCtl[r])->red[slot][P.rank];
+        d[0] = v[0]; d[1] = v[1];
+    }
+    __threadfence_system();
+    for (uint32_t r = 0; r < P.nRanks; r++) *(volatile uint32_t*)&reinterpret_cast<PeerCtl*>(P.peerCtl[r])->redFlag[slot][P.rank] = seq;
+    for (uint32_t r = 0; r < P.nRanks; r++) while (*(volatile uint32_t*)&me->redFlag[slot][r] != seq) { }
+    __threadfence_system();
+    double a = isMax ? -DBL_MAX : 0.0, b = a;
+    for (uint32_t r = 0; r < P.nRanks; r++) {
+        const volatile double* d = me->red[slot][r];
+        a = isMax ? fmax(a, d[0]) : a + d[0];
+        b = isMax ? fmax(b, d[1]) : b + d[1];
+    }
+    v[0] = a; v[1] = b;
+}
+
 // called by thread 0 of the last block with the folded result
 template<int NV>
-__device__ __forceinline__ void finish_reduction(int site, const Params& P, DevState* S, const double (&tot)[NV]) {
-    if (P.nRanks > 1) {
+__device__ __forceinline__ void finish_reduction(int site, const Params& P, DevState* S, const double (&tot)[NV], bool isMax = false) {
+    if (P.nRanks > 1 && P.peerCtl[0]) {
+        double v[2] = { tot[0], NV > 1 ? tot[NV - 1] : 0.0 };
+        peer_allreduce(P, S, v, isMax);
+        control_site(site, P, S, v);
+    } else if (P.nRanks > 1) {
         #pragma unroll
         for (int q = 0; q < NV; q++) S->red[site * 2 + q] = tot[q];
         if (NV < 2) S->red[site * 2 + 1] = 0.0;

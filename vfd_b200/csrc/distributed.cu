@@ -42,7 +42,7 @@ bool NcclApi::load(std::string& err) {
     if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!handle) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
 #define SYM(name) *(void**)(&name) = dlsym(handle, "nccl" #name); if (!name) { err = "libnccl lacks nccl" #name; return false; }
-    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(GetErrorString) SYM(GroupStart) SYM(GroupEnd) SYM(Send) SYM(Recv) SYM(AllReduce)
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(GetErrorString) SYM(GroupStart) SYM(GroupEnd) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(AllGather)
 #undef SYM
     return true;
 }
@@ -89,6 +89,68 @@ __global__ void __launch_bounds__(VFD_TPB) k_unpack(Arrays A, const Record* __re
     if (q >= capacity) return;
     A.pos2[q] = r.pos; A.vel2[q] = r.vel; A.dv2[q] = r.dv; A.nbar2[q] = r.nbar;
     A.curv2[q] = r.curv; A.curvS2[q] = r.curvS; A.curvD2[q] = r.curvD; A.id2[q] = r.id;
+}
+
+// ---- peer-memory slab --------------------------------------------------------------------------------------
+// [ PeerCtl (4 KB) | seven float4 arrays | two float2 arrays | two float arrays ], each array np particle slots long
+enum SlabRegion { SR_POSRHO = 0, SR_VEL_A, SR_VEL_B, SR_PACC, SR_NRM, SR_CGXG, SR_CGXP, SR_CGGYZ, SR_CGPYZ, SR_KAPPA, SR_KAPPAV, SR_COUNT };
+static const uint32_t kRegionBytes[SR_COUNT] = { 16, 16, 16, 16, 16, 16, 16, 8, 8, 4, 4 };
+static size_t slab_offset(int region, uint64_t np) {
+    size_t off = 4096;
+    for (int r = 0; r < region; r++) off += (size_t)np * kRegionBytes[r];
+    return off;
+}
+static size_t slab_bytes(uint64_t np) { return slab_offset(SR_COUNT, np); }
+
+// One halo exchange of one array: this rank's first / last owned tile column straight into the ghost range of the left /
+// right neighbour's copy of the array (peer stores over NVLink), and theirs into ours.
+//   1. "ready": every earlier kernel of this rank has finished with its ghost ranges (stream order) — told to both neighbours;
+//   2. wait for the neighbours' ready, copy, fence;
+//   3. the last block tells both neighbours that the data has landed and waits for theirs: when the kernel ends the ghost
+//      ranges of this rank are current.  One launch per exchange; nothing on the host.
+struct HaloArray { const unsigned char* mine; unsigned char* dstL; unsigned char* dstR; uint32_t eb, pad; };
+struct HaloJob { HaloArray a[2]; uint32_t count; };          // arrays exchanged by one launch (the PCG direction travels as two)
+__global__ void __launch_bounds__(VFD_TPB) k_halo_exchange(const __grid_constant__ HaloJob J, uint32_t ownB, uint32_t edgeLEnd, uint32_t edgeRBegin, uint32_t ownE,
+                                                           PeerCtl* me, PeerCtl* ctlL, PeerCtl* ctlR, DevState* S) {
+    __shared__ uint32_t shSeq;
+    if (threadIdx.x == 0) {
+        const uint32_t seq = *(volatile uint32_t*)&me->haloSeq + 1u;          // the last block advances it once every block has read it
+        if (blockIdx.x == 0) {
+            if (ctlL) *(volatile uint32_t*)&ctlL->haloReady[1] = seq;           // I am my left neighbour's right neighbour
+            if (ctlR) *(volatile uint32_t*)&ctlR->haloReady[0] = seq;
+        }
+        if (ctlL) while (*(volatile uint32_t*)&me->haloReady[0] != seq) { }
+        if (ctlR) while (*(volatile uint32_t*)&me->haloReady[1] != seq) { }
+        __threadfence_system();
+        shSeq = seq;
+    }
+    __syncthreads();
+    const uint32_t nL = ctlL ? edgeLEnd - ownB : 0u, nR = ctlR ? ownE - edgeRBegin : 0u;
+    for (uint32_t k = 0; k < J.count; k++) {
+        const HaloArray& H = J.a[k];
+        const uint32_t eb = H.eb;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nL + nR; i += gridDim.x * blockDim.x) {
+            const bool left = i < nL;
+            const size_t so = (size_t)(left ? ownB + i : edgeRBegin + (i - nL)) * eb, dof = (size_t)(left ? i : i - nL) * eb;
+            unsigned char* dst = (left ? H.dstL : H.dstR) + dof;
+            if (eb == 16) *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(H.mine + so);
+            else if (eb == 8) *reinterpret_cast<float2*>(dst) = *reinterpret_cast<const float2*>(H.mine + so);
+            else *reinterpret_cast<float*>(dst) = *reinterpret_cast<const float*>(H.mine + so);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&S->ticket[7], 1u) == gridDim.x - 1u) {
+        const uint32_t seq = shSeq;
+        S->ticket[7] = 0u;
+        __threadfence_system();
+        if (ctlL) *(volatile uint32_t*)&ctlL->haloData[1] = seq;
+        if (ctlR) *(volatile uint32_t*)&ctlR->haloData[0] = seq;
+        if (ctlL) while (*(volatile uint32_t*)&me->haloData[0] != seq) { }
+        if (ctlR) while (*(volatile uint32_t*)&me->haloData[1] != seq) { }
+        __threadfence_system();
+        *(volatile uint32_t*)&me->haloSeq = seq;
+    }
 }
 
 __global__ void k_control(Params P, DevState* S, int site) {
@@ -197,6 +259,77 @@ void Solver::dist_params(Params& P) const {
     P.n = D.nLocal;
     P.tile0 = (D.rank > 0 ? 1u : 0u) * T;
     P.tile1 = P.tile0 + (D.colHi - D.colLo) * T;
+    for (int r = 0; r < 8; r++) P.peerCtl[r] = (D.p2p && r < D.nranks) ? (void*)D.peerSlab[r] : nullptr;
+}
+
+// The slab of this rank (control block + the arrays halo exchanges touch) and its mapping into every other rank: called by
+// alloc_particles on every rank at the same point (set_particles_distributed is collective).
+int Solver::dist_alloc_slab(size_t np) {
+    Dist& D = *dist;
+    Arrays& A = arrays;
+    dist_free_slab();
+    const char* off = getenv("VFD_DIST_P2P");
+    const bool want = !(off && atoi(off) == 0) && D.nranks <= 8;
+    D.slabBytes = slab_bytes(np);
+    CK(cudaMalloc(&D.slab, D.slabBytes));
+    CK(cudaMemset(D.slab, 0, 4096));
+    unsigned char* b = D.slab;
+    A.posRho = (float4*)(b + slab_offset(SR_POSRHO, np)); A.vel = (float4*)(b + slab_offset(SR_VEL_A, np)); A.vel2 = (float4*)(b + slab_offset(SR_VEL_B, np));
+    A.pacc = (float4*)(b + slab_offset(SR_PACC, np)); A.nrm = (float4*)(b + slab_offset(SR_NRM, np));
+    A.cgXG = (float4*)(b + slab_offset(SR_CGXG, np)); A.cgXP = (float4*)(b + slab_offset(SR_CGXP, np));
+    A.cgGyz = (float2*)(b + slab_offset(SR_CGGYZ, np)); A.cgPyz = (float2*)(b + slab_offset(SR_CGPYZ, np));
+    A.kappa = (float*)(b + slab_offset(SR_KAPPA, np)); A.kappaV = (float*)(b + slab_offset(SR_KAPPAV, np));
+    D.p2p = false;
+    for (int r = 0; r < 8; r++) { D.peerSlab[r] = nullptr; D.slabNp[r] = 0; }
+    // every rank's IPC handle and slot count, gathered through the communicator that exists anyway
+    struct Info { cudaIpcMemHandle_t h; uint64_t np; uint64_t ok; };
+    Info mine; memset(&mine, 0, sizeof mine);
+    mine.np = np;
+    mine.ok = want && cudaIpcGetMemHandle(&mine.h, D.slab) == cudaSuccess ? 1u : 0u;
+    cudaGetLastError();
+    Info* dInfo = nullptr;
+    CK(cudaMalloc(&dInfo, sizeof(Info) * (size_t)(D.nranks + 1)));
+    CK(cudaMemcpyAsync(dInfo + D.nranks, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));
+    NK(D.api.AllGather(dInfo + D.nranks, dInfo, sizeof(Info), ncclChar, D.comm, stream));
+    std::vector<Info> all((size_t)D.nranks);
+    CK(cudaMemcpyAsync(all.data(), dInfo, sizeof(Info) * (size_t)D.nranks, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    cudaFree(dInfo);
+    bool ok = true;
+    for (int r = 0; r < D.nranks; r++) ok = ok && all[(size_t)r].ok;
+    if (ok) {
+        for (int r = 0; r < D.nranks && ok; r++) {
+            D.slabNp[r] = all[(size_t)r].np;
+            if (r == D.rank) { D.peerSlab[r] = D.slab; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+            D.peerSlab[r] = (unsigned char*)ptr;
+        }
+    }
+    // all ranks take the same path: agree on the outcome
+    int* dOk = nullptr;
+    CK(cudaMalloc(&dOk, sizeof(int)));
+    int hOk = ok ? 1 : 0;
+    CK(cudaMemcpyAsync(dOk, &hOk, sizeof(int), cudaMemcpyHostToDevice, stream));
+    NK(D.api.AllReduce(dOk, dOk, 1, ncclInt32, ncclMin, D.comm, stream));
+    CK(cudaMemcpyAsync(&hOk, dOk, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    cudaFree(dOk);
+    D.p2p = hOk == 1;
+    if (!D.p2p) for (int r = 0; r < D.nranks; r++) if (r != D.rank && D.peerSlab[r]) { cudaIpcCloseMemHandle(D.peerSlab[r]); D.peerSlab[r] = nullptr; }
+    return VFD_OK;
+}
+
+void Solver::dist_free_slab() {
+    if (!dist) return;
+    Dist& D = *dist;
+    Arrays& A = arrays;
+    if (!D.slab) return;
+    for (int r = 0; r < 8; r++) { if (r != D.rank && D.peerSlab[r]) cudaIpcCloseMemHandle(D.peerSlab[r]); D.peerSlab[r] = nullptr; }
+    A.posRho = A.vel = A.vel2 = A.pacc = A.nrm = A.cgXG = A.cgXP = nullptr;
+    A.cgGyz = A.cgPyz = nullptr; A.kappa = A.kappaV = nullptr;
+    cudaFree(D.slab);
+    D.slab = nullptr; D.slabBytes = 0; D.p2p = false;
 }
 
 // migration + ghost refresh (see the header of this file)
@@ -263,14 +396,19 @@ int Solver::dist_read_ranges() {
     D.ownB = h[0]; D.edgeLEnd = h[1]; D.edgeRBegin = h[2]; D.ownE = h[3];
     // my ghost ranges must be exactly my neighbours' edge columns: verify before the first halo message of the step
     uint32_t* d = D.dCounters + 8;
-    const uint32_t mine[2] = { D.edgeLEnd - D.ownB, D.ownE - D.edgeRBegin };
-    CK(cudaMemcpyAsync(d, mine, 8, cudaMemcpyHostToDevice, stream));
+    // to each neighbour: the size of the edge column it mirrors, and where my own range ends (= where my ghost-R range begins:
+    // the right neighbour writes its halos there)
+    const uint32_t mine[4] = { D.edgeLEnd - D.ownB, D.ownE, D.ownE - D.edgeRBegin, D.ownE };
+    CK(cudaMemcpyAsync(d, mine, 16, cudaMemcpyHostToDevice, stream));
     NK(D.api.GroupStart());
-    if (hasL) { NK(D.api.Send(d + 0, 1, ncclUint32, D.rank - 1, D.comm, stream)); NK(D.api.Recv(d + 2, 1, ncclUint32, D.rank - 1, D.comm, stream)); }
-    if (hasR) { NK(D.api.Send(d + 1, 1, ncclUint32, D.rank + 1, D.comm, stream)); NK(D.api.Recv(d + 3, 1, ncclUint32, D.rank + 1, D.comm, stream)); }
+    if (hasL) { NK(D.api.Send(d + 0, 2, ncclUint32, D.rank - 1, D.comm, stream)); NK(D.api.Recv(d + 4, 2, ncclUint32, D.rank - 1, D.comm, stream)); }
+    if (hasR) { NK(D.api.Send(d + 2, 2, ncclUint32, D.rank + 1, D.comm, stream)); NK(D.api.Recv(d + 6, 2, ncclUint32, D.rank + 1, D.comm, stream)); }
     NK(D.api.GroupEnd());
-    CK(cudaMemcpyAsync(h + 4, d + 2, 8, cudaMemcpyDeviceToHost, stream));
+    uint32_t got[4] = { 0, 0, 0, 0 };
+    CK(cudaMemcpyAsync(got, d + 4, 16, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    h[4] = got[0]; h[5] = got[2];
+    D.leftOwnE = got[1];
     const uint32_t ghostL = D.ownB, ghostR = D.nLocal - D.ownE;
     if ((hasL && h[4] != ghostL) || (hasR && h[5] != ghostR) || (!hasL && ghostL) || (!hasR && ghostR)) {
         char buf[256];
@@ -280,30 +418,60 @@ int Solver::dist_read_ranges() {
     return VFD_OK;
 }
 
-// halo of one per-particle array (elemFloats floats per particle)
-int Solver::dist_halo(void* base, uint32_t elemFloats) {
+// halo of one or two per-particle arrays (elemFloats floats per particle each)
+int Solver::dist_halo(void* base, uint32_t elemFloats, void* base2, uint32_t elemFloats2) {
     Dist& D = *dist;
     const bool hasL = D.rank > 0, hasR = D.rank + 1 < D.nranks;
-    float* f = (float*)base;
-    const size_t e = elemFloats;
-    NK(D.api.GroupStart());
-    if (hasL) {
-        if (D.edgeLEnd > D.ownB) NK(D.api.Send(f + D.ownB * e, (D.edgeLEnd - D.ownB) * e, ncclFloat32, D.rank - 1, D.comm, stream));
-        if (D.ownB) NK(D.api.Recv(f, D.ownB * e, ncclFloat32, D.rank - 1, D.comm, stream));
+    if (D.p2p) {
+        HaloJob J; memset(&J, 0, sizeof J);
+        void* bases[2] = { base, base2 }; const uint32_t efs[2] = { elemFloats, elemFloats2 };
+        uint64_t bytes = 0;
+        const uint32_t items = (hasL ? D.edgeLEnd - D.ownB : 0u) + (hasR ? D.ownE - D.edgeRBegin : 0u);
+        for (int k = 0; k < 2 && bases[k]; k++) {
+            // which array of the slab this is (velocity changes sides with every sort, on every rank alike)
+            const size_t myOff = (size_t)((unsigned char*)bases[k] - D.slab);
+            int region = -1;
+            for (int r = 0; r < SR_COUNT; r++) if (slab_offset(r, D.slabNp[D.rank]) == myOff) region = r;
+            if (region < 0 || kRegionBytes[region] != efs[k] * 4u) return fail(VFD_E_INVALID, "halo exchange of an array outside the peer-memory slab");
+            HaloArray& H = J.a[J.count++];
+            H.eb = kRegionBytes[region];
+            H.mine = (const unsigned char*)bases[k];
+            H.dstL = hasL ? D.peerSlab[D.rank - 1] + slab_offset(region, D.slabNp[D.rank - 1]) + (size_t)D.leftOwnE * H.eb : nullptr;
+            H.dstR = hasR ? D.peerSlab[D.rank + 1] + slab_offset(region, D.slabNp[D.rank + 1]) : nullptr;
+            bytes += (uint64_t)items * H.eb;
+        }
+        const uint32_t blocks = std::max(1u, std::min<uint32_t>((items + VFD_TPB - 1) / VFD_TPB, (uint32_t)numSMs * 4u));
+        k_halo_exchange<<<blocks, VFD_TPB, 0, stream>>>(J, D.ownB, D.edgeLEnd, D.edgeRBegin, D.ownE,
+            (PeerCtl*)D.slab, hasL ? (PeerCtl*)D.peerSlab[D.rank - 1] : nullptr, hasR ? (PeerCtl*)D.peerSlab[D.rank + 1] : nullptr, dState);
+        launches += 1;
+        D.halos += 1;
+        D.bytesHalo += bytes;
+        return VFD_OK;
     }
-    if (hasR) {
-        if (D.ownE > D.edgeRBegin) NK(D.api.Send(f + D.edgeRBegin * e, (D.ownE - D.edgeRBegin) * e, ncclFloat32, D.rank + 1, D.comm, stream));
-        if (D.nLocal > D.ownE) NK(D.api.Recv(f + D.ownE * e, (D.nLocal - D.ownE) * e, ncclFloat32, D.rank + 1, D.comm, stream));
+    void* bases[2] = { base, base2 }; const uint32_t efs[2] = { elemFloats, elemFloats2 };
+    NK(D.api.GroupStart());
+    for (int k = 0; k < 2 && bases[k]; k++) {
+        float* f = (float*)bases[k];
+        const size_t e = efs[k];
+        if (hasL) {
+            if (D.edgeLEnd > D.ownB) NK(D.api.Send(f + D.ownB * e, (D.edgeLEnd - D.ownB) * e, ncclFloat32, D.rank - 1, D.comm, stream));
+            if (D.ownB) NK(D.api.Recv(f, D.ownB * e, ncclFloat32, D.rank - 1, D.comm, stream));
+        }
+        if (hasR) {
+            if (D.ownE > D.edgeRBegin) NK(D.api.Send(f + D.edgeRBegin * e, (D.ownE - D.edgeRBegin) * e, ncclFloat32, D.rank + 1, D.comm, stream));
+            if (D.nLocal > D.ownE) NK(D.api.Recv(f + D.ownE * e, (D.nLocal - D.ownE) * e, ncclFloat32, D.rank + 1, D.comm, stream));
+        }
+        D.bytesHalo += (uint64_t)((D.edgeLEnd - D.ownB) * (hasL ? 1 : 0) + (D.ownE - D.edgeRBegin) * (hasR ? 1 : 0)) * e * 4;
     }
     NK(D.api.GroupEnd());
     D.halos += 1;
-    D.bytesHalo += (uint64_t)((D.edgeLEnd - D.ownB) * (hasL ? 1 : 0) + (D.ownE - D.edgeRBegin) * (hasR ? 1 : 0)) * e * 4;
     return VFD_OK;
 }
 
 // combine the ranks' partial reduction results of one site and take the control decision on every rank
 int Solver::dist_reduce(int site, bool isMax) {
     Dist& D = *dist;
+    if (D.p2p) { D.reductions += 1; return VFD_OK; }        // all-reduced by the reducing kernel itself (control.cuh: peer_allreduce)
     NK(D.api.AllReduce(&dState->red[site * 2], &dState->red[site * 2], 2, ncclFloat64, isMax ? ncclMax : ncclSum, D.comm, stream));
     k_control<<<1, 32, 0, stream>>>(params, dState, site);
     launches += 1;
@@ -342,6 +510,8 @@ int Solver::dist_get_owned(uint32_t capacity, uint32_t* count, uint32_t* ids, Vf
 }
 
 Dist::~Dist() {
+    for (int r = 0; r < 8; r++) if (r != rank && peerSlab[r]) cudaIpcCloseMemHandle(peerSlab[r]);
+    if (slab) cudaFree(slab);
     if (comm && api.CommDestroy) api.CommDestroy(comm);
     cudaFree(sendL); cudaFree(sendR); cudaFree(recvL); cudaFree(recvR); cudaFree(dCounters);
     if (hCounters) cudaFreeHost(hCounters);

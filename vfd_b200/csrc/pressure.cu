@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(VFD_TPB) k_cfl(Params P, Arrays A, DevState* S
         double tot[1];
         last_block_fold<1>(tot, A.partials, shRed, true);
         if (threadIdx.x == 0) {
-            finish_reduction<1>(SITE_CFL, P, S, tot);
+            finish_reduction<1>(SITE_CFL, P, S, tot, true);
             S->ticket[3] = 0;
         }
     }

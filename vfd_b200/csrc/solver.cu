@@ -290,6 +290,7 @@ template<typename T> static cudaError_t dalloc(T*& p, size_t count) { return cud
 
 void Solver::free_particles() {
     Arrays& A = arrays;
+    dist_free_slab();                        // the arrays that live in the peer-memory slab (several ranks) are not freed one by one
     void* ptrs[] = { A.pos, A.vel, A.dv, A.nbar, A.curv, A.curvS, A.curvD, A.id, A.pos2, A.vel2, A.dv2, A.nbar2, A.curv2, A.curvS2, A.curvD2, A.id2,
                      A.posRho, A.acc, A.pacc, A.nrm, A.res, A.rho, A.rhoAdv, A.kappa, A.kappaV, A.alpha, A.cgG, A.cgR, A.cgQ, A.cgZ, A.cgXG, A.cgXP, A.cgGyz, A.cgPyz, A.minv,
                      A.cnt, A.list16, A.coef, A.gcoef, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.tileList, A.partials, A.slotSums, dPos0, dVel0 };
@@ -320,14 +321,16 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
     }
     free_particles();
     allocParticles = np;
+    // several ranks: the arrays that halo exchanges touch come from one slab that the other ranks map (distributed.cu)
+    if (dist) { int rc = dist_alloc_slab(np); if (rc) return rc; allocBytes += dist->slabBytes; }
     float4** f4s[] = { &A.pos, &A.vel, &A.dv, &A.nbar, &A.pos2, &A.vel2, &A.dv2, &A.nbar2, &A.posRho, &A.acc, &A.pacc, &A.nrm,
                        &A.cgG, &A.cgR, &A.cgQ, &A.cgZ, &A.cgXG, &A.cgXP, &dPos0, &dVel0 };
     CK(dalloc(dIds0, np));
-    for (float4** p : f4s) { CK(dalloc(*p, np)); allocBytes += np * 16; }
+    for (float4** p : f4s) if (!*p) { CK(dalloc(*p, np)); allocBytes += np * 16; }
     float** f1s[] = { &A.curv, &A.curvS, &A.curvD, &A.curv2, &A.curvS2, &A.curvD2, &A.res, &A.rho, &A.rhoAdv, &A.kappa, &A.kappaV, &A.alpha };
-    for (float** p : f1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
+    for (float** p : f1s) if (!*p) { CK(dalloc(*p, np)); allocBytes += np * 4; }
     CK(dalloc(A.minv, np * 9)); allocBytes += np * 36;
-    CK(dalloc(A.cgGyz, np)); CK(dalloc(A.cgPyz, np)); allocBytes += np * 16;
+    if (!A.cgGyz) { CK(dalloc(A.cgGyz, np)); CK(dalloc(A.cgPyz, np)); allocBytes += np * 16; }
     uint32_t** u1s[] = { &A.id, &A.id2, &A.cnt, &A.key, &A.rank, &A.tmpIdx };
     for (uint32_t** p : u1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
     CK(dalloc(A.list16, np * ELL_SLOTS)); searchBytes = np * ELL_SLOTS * 2 + np * 4 * 4;
@@ -613,19 +616,22 @@ int Solver::step() {
     if (desc.EnableViscositySolver) {
         launch_viscosity_setup(L, P, A, dState, dLutG);
         RC(reduce(SITE_VISC_BB));
-        RC(halo4(A.cgXG)); RC(halo2(A.cgGyz));
+        RC(halo42(A.cgXG, A.cgGyz));
         launch_viscosity_matvec(L, P, A, dState, true);
         RC(reduce(SITE_VISC_INIT));
-        RC(halo4(A.cgXP)); RC(halo2(A.cgPyz));
+        RC(halo42(A.cgXP, A.cgPyz));
         const bool fusedStep = viscosity_step_fits(L, P);
         auto iteration = [&]() -> int {
             launch_viscosity_matvec(L, P, A, dState, false);
             RC(reduce(SITE_VISC_PQ));
-            if (fusedStep) { CK((cudaError_t)launch_viscosity_step(L, P, A, dState)); return VFD_OK; }
-            launch_viscosity_update(L, P, A, dState);
-            RC(reduce(SITE_VISC_UPDATE));
-            launch_viscosity_direction(L, P, A, dState);
-            RC(halo4(A.cgXP)); RC(halo2(A.cgPyz));
+            if (fusedStep) {
+                CK((cudaError_t)launch_viscosity_step(L, P, A, dState));
+            } else {
+                launch_viscosity_update(L, P, A, dState);
+                RC(reduce(SITE_VISC_UPDATE));
+                launch_viscosity_direction(L, P, A, dState);
+            }
+            RC(halo42(A.cgXP, A.cgPyz));
             return VFD_OK;
         };
         if (P.minViscIt == 0 && P.maxViscIt > 0) RC(run_polled_loop(P.maxViscIt, 0, 4, &dState->viscActive, iteration, 1u));

@@ -21,6 +21,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     bool load(std::string& err);
 };
 
@@ -38,6 +39,14 @@ struct Dist {
     void *sendL = nullptr, *sendR = nullptr, *recvL = nullptr, *recvR = nullptr;
     uint32_t* dCounters = nullptr; uint32_t* hCounters = nullptr;
     uint64_t halos = 0, reductions = 0, bytesHalo = 0, bytesState = 0;
+    // peer memory (CUDA IPC over NVLink): one slab per rank = its control block + every array a halo exchange touches, mapped
+    // into every other rank of the box; halos are written straight into the neighbour's ghost ranges, solver decisions are
+    // all-reduced through the control blocks (control.cuh: PeerCtl) — no NCCL call per solver iteration
+    bool p2p = false;
+    unsigned char* slab = nullptr; size_t slabBytes = 0;
+    uint64_t slabNp[8] = {};                  // particle slots of every rank's arrays (region offsets follow from it)
+    unsigned char* peerSlab[8] = {};          // every rank's slab in this process' address space (own: slab)
+    uint32_t leftOwnE = 0;                    // where the left neighbour's ghost-R range begins (its ownE), renewed every step
     ~Dist();
 };
 
@@ -110,11 +119,13 @@ private:
     void dist_params(Params& P) const;
     int dist_exchange_state();
     int dist_read_ranges();
-    int dist_halo(void* base, uint32_t elemFloats);
+    int dist_halo(void* base, uint32_t elemFloats, void* base2 = nullptr, uint32_t elemFloats2 = 0);
     int dist_reduce(int site, bool isMax);
     int dist_frame_step();
+    int dist_alloc_slab(size_t np);
+    void dist_free_slab();
     int halo4(float4* a) { return dist ? dist_halo(a, 4) : VFD_OK; }
-    int halo2(float2* a) { return dist ? dist_halo(a, 2) : VFD_OK; }
+    int halo42(float4* a, float2* b) { return dist ? dist_halo(a, 4, b, 2) : VFD_OK; }
     int halo1(float* a) { return dist ? dist_halo(a, 1) : VFD_OK; }
     int reduce(int site, bool isMax = false) { return dist ? dist_reduce(site, isMax) : VFD_OK; }
     int run_polled_loop(uint32_t maxIt, uint32_t already, int batch, uint32_t* dFlag, const std::function<int()>& enqueueIteration, uint32_t continueValue);

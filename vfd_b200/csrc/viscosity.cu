@@ -418,9 +418,10 @@ void launch_viscosity_update(const LaunchCfg& L, const Params& P, const Arrays& 
     LaunchScope ls(L, KID_VISC_UPDATE);
     k_visc_update<<<g2, VFD_TPB, 0, L.stream>>>(P, A, S);
 }
-// true when the fused kernel can carry this scene: one rank (the decision needs no exchange) and <= STEP_MAXK x 1024 particles per SM
+// true when the fused kernel can carry this scene: the decision is taken inside the kernel (one rank, or ranks that all-reduce
+// through peer memory) and the rank holds <= STEP_MAXK x 1024 particles per SM
 bool viscosity_step_fits(const LaunchCfg& L, const Params& P) {
-    return P.nRanks == 1 && P.tune[5] != 1 && (uint64_t)P.n <= (uint64_t)L.numSMs * STEP_MAXK * STEP_THREADS - 32ull * (uint64_t)L.numSMs;
+    return (P.nRanks == 1 || P.peerCtl[0] != nullptr) && P.tune[5] != 1 && (uint64_t)P.n <= (uint64_t)L.numSMs * STEP_MAXK * STEP_THREADS - 32ull * (uint64_t)L.numSMs;
 }
 int launch_viscosity_step(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     const size_t sm = (size_t)STEP_MAXK * STEP_THREADS * (sizeof(float4) + sizeof(float2));
