@@ -37,15 +37,33 @@ ALGO_BYTES = {
     "div_source": (68, 4), "div_accel": (56, 4), "div_solve": (72, 4), "div_finish": (96, 4),
     "press_source": (68, 4), "press_accel": (56, 4), "press_solve": (72, 4), "press_finish": (88, 4),
     "st_classify": (48, 4), "st_smooth": (56, 4), "st_apply": (76, 0),
-    "visc_setup": (120, 4), "visc_matvec0": (136, 4), "visc_matvec": (68, 4), "visc_update": (156, 0), "visc_direction": (64, 0), "visc_step": (164, 0), "visc_apply": (80, 0),
+    "visc_setup": (120, 4), "visc_matvec0": (136, 4), "visc_matvec": (56, 4), "visc_update": (156, 0), "visc_direction": (64, 0), "visc_step": (164, 0), "visc_apply": (80, 0),
     "cfl": (32, 0), "velocity": (48, 0), "position": (48, 0),
+}
+
+
+def block_positions(nx, ny, nz, origin):
+    """Lattice at spacing 2r, (i + 1/2) d + origin: what the reference's SampleMode::MinDensity yields (ParticleSampler.cpp:39-43)."""
+    d = np.float32(D)
+    ax = [(np.arange(n, dtype=np.float32) + np.float32(0.5)) * d + np.float32(o) for n, o in zip((nx, ny, nz), origin)]
+    Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+    return np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1).astype(np.float32)
+
+
+# BASELINE.json configs that fit one GPU (SURVEY.md section 8d): block edge, solver switches, settle steps
+CONFIGS = {
+    1: dict(side=30, settle=200, name="dam break %d^3 = %d particles, DFSPH (2 divergence + 2 pressure Jacobi iterations), viscosity and surface tension off",
+            desc=dict(EnableViscositySolver=0, EnableSurfaceTensionSolver=0)),
+    2: dict(side=46, settle=200, name="viscous block drop %d^3 = %d particles, DFSPH (2+2 Jacobi iterations) + implicit viscosity PCG (nu 10, honey-like), surface tension off",
+            desc=dict(EnableSurfaceTensionSolver=0)),
+    3: dict(side=100, settle=200, name="dam break %d^3 = %d particles, DFSPH (2 divergence + 2 pressure Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension",
+            desc=dict()),
 }
 
 
 def scene(side):
     """Dam break: side^3 lattice block in the corner of an inverted box twice as long."""
-    from vfd_b200 import api
-    pos = api.block_positions(side, side, side, R, origin=(2 * D, 2 * D, 2 * D))
+    pos = block_positions(side, side, side, (2 * D, 2 * D, 2 * D))
     L = side * D
     box = ((0.0, 0.0, 0.0), (2 * L + 4 * D, 1.4 * L + 4 * D, L + 4 * D))
     ext = [b - a + 2 * (8 * H - R) for a, b in zip(*box)]
@@ -53,12 +71,17 @@ def scene(side):
     return pos, box, res
 
 
+CONFIG_DESC = {}          # solver switches of the selected --config (set by main)
+CONFIG_NAME = CONFIGS[3]["name"]
+
+
 def description(api_mod, frames=0, **kw):
-    """Config 3: defaults of the reference (viscosity 10, boundary viscosity 10, surface tension 1) with the
-    Jacobi iteration counts pinned to 2 (the reference's loops run exactly `Min` iterations: SURVEY.md F4/F5)."""
+    """Defaults of the reference (viscosity 10, boundary viscosity 10, surface tension 1) with the Jacobi iteration
+    counts pinned to 2 (the reference's loops run exactly `Min` iterations: SURVEY.md F4/F5), plus the --config's switches."""
     d = dict(FrameCount=frames, FrameLength=0.0,
              MinPressureSolverIterations=2, MaxPressureSolverIterations=2,
              MinDivergenceSolverIterations=2, MaxDivergenceSolverIterations=2)
+    d.update(CONFIG_DESC)
     d.update(kw)
     return api_mod(**d)
 
@@ -131,75 +154,72 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def settled_state_on_gpu(args, local):
-    """Scene preparation shared by both arms: the settled dam-break state (BASELINE.json config 3 after `--settle`
-    steps).  200 steps of a 1M-particle scene take minutes on host cores (the PCG runs 100 iterations per step while
-    the block is at rest on the floor), so the state the reference arm is TIMED on is prepared, untimed, on the GPU."""
-    from vfd_b200 import api, build
-    build.build()
-    pos, box, res = scene(args.side)
-    vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R, device=local)
-    sim = api.DFSPHSimulation(description(api.DFSPHSimulationDescription), device=local)
-    sim.SetFluidObjects([api.FluidObject(pos)])
-    sim.SetRigidBodies([vm])
-    sim.steps(args.settle)
-    sim.synchronize()
-    state = sim.particles()
-    info = sim.GetInfo()
-    out = (state, info.TimeStepSize, (info.SurfaceTensionSampleCount, info.MonteCarloFactor), pos, box, res)
-    sim.close()
-    return out
+def reference_settled_state(args, refsim, desc):
+    """Scene preparation of the reference arm WITHOUT the product: the workload's settled state (`--settle` steps from the
+    lattice) computed by the reference itself — its CUDA build for this GPU (oracle/_ref/libvfd_ref_gpu.so, the IEEE
+    variant: SURVEY.md F6) when the box has a GPU and the build travelled, which takes seconds; else on the host cores on a
+    smaller scene (`--ref-side`).  Returns (state, dt, (sample count, Monte-Carlo factor), positions, box, map resolution, how)."""
+    def settle(kind, side, steps):
+        pos, box, res = scene(side)
+        sim = refsim.RefSim(desc, kind=kind, threads=os.cpu_count() or 1)
+        sim.set_particles(pos)
+        sim.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
+        sim.commit_bodies()
+        sim.step(steps)
+        info = sim.info_bytes().tobytes()             # DFSPHSimulationInfo: SurfaceTensionSampleCount @84, MonteCarloFactor @112 (SURVEY.md section 8a)
+        st = (int(np.frombuffer(info[84:88], np.uint32)[0]), float(np.frombuffer(info[112:116], np.float32)[0]))
+        return sim.particles(), float(sim.debug()["dt"]), st, pos, box, res
+    gpu = False
+    try:
+        import torch
+        gpu = torch.cuda.is_available()
+    except Exception:
+        pass
+    if gpu and refsim.available("gpu"):
+        try:
+            out = settle("gpu", args.side, args.settle)
+            return out + ("%d settle steps by the reference's own CUDA build on this GPU (untimed)" % args.settle, args.side)
+        except Exception as ex:
+            print("reference arm: settling on the reference's CUDA build failed (%r); settling %d^3 on the CPU" % (ex, args.ref_side), file=sys.stderr)
+    out = settle("cpu", args.ref_side, args.ref_settle)
+    return out + ("%d settle steps on the host cores (untimed)" % args.ref_settle, args.ref_side)
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own solver sources (oracle/_ref/libvfd_ref_cpu.so, built by oracle/build_ref.py
-    from /root/reference) on all host cores, timed on the arm's workload: K steps of the settled 1M-particle state.
-    Nothing of vfd_b200 runs inside the timed region."""
+    from /root/reference) on all host cores, timed on the arm's workload: K steps from the workload's settled state.
+    Nothing of vfd_b200 is imported, loaded or run by this arm — the settled state comes from the reference too."""
     if rank != 0:
         return 0
     from oracle import refsim
     threads = os.cpu_count() or 1
     desc = description(refsim.Desc)
-    prepared = None
-    try:
-        prepared = settled_state_on_gpu(args, int(os.environ.get("LOCAL_RANK", "0")))
-    except Exception as ex:          # no GPU / no library: settle a smaller scene on the host cores instead
-        print("reference arm: GPU scene preparation unavailable (%r); settling %d^3 on the CPU" % (ex, args.ref_side), file=sys.stderr)
+    steps = min(args.steps, args.ref_steps)            # each step is ~1 s of 16 cores at 1M particles: a bounded sample
     with refsim.quiet_stdout():
+        state, dt0, st0, pos, box, res, how, side = reference_settled_state(args, refsim, desc)
         sim = refsim.RefSim(desc, threads=threads)
-        if prepared is not None:
-            state, dt0, st0, pos, box, res = prepared
-            side, how = args.side, "state after %d settle steps prepared untimed by vfd_b200 on cuda (CPU settling takes minutes)" % args.settle
-        else:
-            side = args.ref_side
-            pos, box, res = scene(side)
-            how = "%d settle steps on the CPU" % args.ref_settle
         sim.set_particles(pos)
         sim.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
         sim.commit_bodies()
-        if prepared is not None:
-            sim.set_particles_full(state)
-            sim.set_time_step(dt0)
-            sim.set_st_state(*st0)
-        else:
-            sim.step(args.ref_settle)
-        sim.step(args.warmup)
+        sim.set_particles_full(state)
+        sim.set_time_step(dt0)
+        sim.set_st_state(*st0)
+        sim.step(min(args.warmup, 3))
         t0 = time.perf_counter()
         its = []
-        for _ in range(args.steps):
+        for _ in range(steps):
             sim.step(1)
             its.append(sim.debug()["visc_it"])
         dt = time.perf_counter() - t0
     n = len(pos)
-    v = n * args.steps / dt
-    sample = "%d^3 = %d-particle dam break, same scene generator and solver settings as the GPU arm; %s; %d warm-up + %d timed steps; mean PCG it %.1f" % (
-        side, n, how, args.warmup, args.steps, float(np.mean(its)))
+    v = n * steps / dt
+    sample = "%s; %s; %d warm-up + %d timed steps (a bounded sample of the arm's %d); mean PCG it %.1f" % (
+        CONFIG_NAME % (side, n), how, min(args.warmup, 3), steps, args.steps, float(np.mean(its)))
     print(json.dumps({
         "impl": "reference", "metric": "DFSPH particle-steps/s", "value": v, "unit": "particle-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "dam break %d^3 = %d particles, DFSPH (2 divergence + 2 pressure Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; "
-                               "reference solver sources on %d host threads" % (side, n, threads), "particles": n,
+        "config": {"workload": CONFIG_NAME % (side, n) + "; reference solver sources on %d host threads" % threads, "particles": n,
                    "pcg_iterations_mean": float(np.mean(its))},
         "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -250,16 +270,24 @@ def roofline_pass(sim, api, n, mbar, steps, skip=False):
             roof = {"bound": "hbm", "kernel": name, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak if gbs else None,
                     "traffic": ncu_traffic(name, n), "peak_source": peak_src, "avg_launch_ms": avg, "active_launches": lna,
                     "share_of_step": msall / total_kernel_ms, "algorithmic_bytes_per_launch": b,
-                    "note": "event-bracketed pass over the %d steps following the timed region (%.3f ms/step with brackets); traffic = DRAM bytes per launch "
-                            "from the committed ncu capture (profiles/)" % (steps, ms_prof / steps)}
+                    "note": "event-bracketed pass over the %d steps following the timed region (%.3f ms/step with brackets); algorithmic bytes per particle = "
+                            "%d + %d x mean neighbours (SURVEY.md section 8d); traffic = DRAM bytes per launch from the round's committed ncu capture "
+                            "(profiles/ncu_traffic.json), not measured in this run" % (steps, ms_prof / steps, fixed, per)}
     return roof, table, ms_prof
 
 
-def cpu_baseline(state, dt, st, pos0, box, res, steps=10):
-    """The reference's solver sources on this box's host cores, from the GPU run's settled state."""
+PARITY_FIELDS = ["Position", "Velocity", "Acceleration", "PressureAcceleration", "VelocityDifference", "MonteCarloSurfaceNormal",
+                 "MonteCarloSurfaceNormalSmooth", "Density", "DensityAdvection", "PressureRho2", "PressureRho2V", "Factor",
+                 "MonteCarloSurfaceCurvature", "MonteCarloSurfaceCurvatureSmooth", "DeltaFinalCurvature"]
+
+
+def cpu_baseline(state, dt, st, pos0, box, res, steps=10, gpu_step=None):
+    """The reference's solver sources on this box's host cores, from the GPU run's settled state; its FIRST step is also the
+    checker of the GPU's step from the same state (`gpu_step`: the 120-B particle state after one vfd_b200 step): error of
+    every field relative to the field's scale, as the parity tests measure it."""
     from oracle import refsim
     if not refsim.available("cpu"):
-        return None
+        return None, None
     threads = os.cpu_count() or 1
     with refsim.quiet_stdout():
         sim = refsim.RefSim(description(refsim.Desc), threads=threads)
@@ -269,24 +297,80 @@ def cpu_baseline(state, dt, st, pos0, box, res, steps=10):
         sim.set_particles_full(state)
         sim.set_time_step(dt)
         sim.set_st_state(*st)
-        sim.step(1)                       # untimed: first-touch of the reference's buffers
+        sim.step(1)                       # untimed: first-touch of the reference's buffers; the parity reference
+        first = sim.particles()
         t0 = time.perf_counter()
         sim.step(steps)
         el = time.perf_counter() - t0
     n = len(pos0)
+    par = None
+    if gpu_step is not None:
+        worst = ("", 0.0)
+        for f in PARITY_FIELDS:
+            x, y = np.asarray(gpu_step[f], np.float64), np.asarray(first[f], np.float64)
+            scale = np.abs(y).max()
+            e = 0.0 if scale == 0.0 else float(np.abs(x - y).max() / scale)
+            if e > worst[1]:
+                worst = (f, e)
+        par = {"worst_field": worst[0], "value": worst[1], "tol": 2.0e-5, "ok": bool(worst[1] <= 2.0e-5), "particles": n,
+               "note": "one step from the timed run's settled state: vfd_b200 (search without FMA contraction, as the host-compiled oracle) vs the "
+                       "reference's sources on the host cores; max |error| / max |field| over the fields of the 120-B particle state; tolerance as in "
+                       "tests/test_gpu_scale.py (the reference moves by ~1e-5 against itself between two runs)"}
     return {"value": n * steps / el, "unit": "particle-steps/s", "cores": threads, "kind": "reference",
             "sample": "%d steps of the same %d-particle settled state (after 1 untimed step), %.1f s; PCG it of last step %d" % (
-                steps, n, el, sim.debug()["visc_it"])}
+                steps, n, el, sim.debug()["visc_it"])}, par
+
+
+def reference_cuda(state, dt, st, pos0, box, res, steps=5):
+    """The reference's own CUDA solver (its sources compiled by oracle/build_ref.py --gpu for sm_100a) on this GPU and this
+    state: the only pre-existing GPU implementation of the path.  `ieee`: without fast-math and with the
+    preconditioner's accumulator zero-initialised; `fast_math`: as shipped."""
+    from oracle import refsim
+    out = {}
+    for key, kind, k in (("ieee", "gpu", steps), ("fast_math", "gpu_fast", 2)):
+        if not refsim.available(kind):
+            out[key] = None
+            continue
+        try:
+            with refsim.quiet_stdout():
+                sim = refsim.RefSim(description(refsim.Desc), kind=kind)
+                sim.set_particles(pos0)
+                sim.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
+                sim.commit_bodies()
+                sim.set_particles_full(state)
+                sim.set_time_step(dt)
+                sim.set_st_state(*st)
+                sim.step(1)
+                t0 = time.perf_counter()
+                its, tm = [], {}
+                for _ in range(k):
+                    sim.step(1)
+                    dbg = sim.debug()
+                    its.append(dbg["visc_it"])
+                    for name, us in dbg["timers_us"].items():
+                        tm[name] = tm.get(name, 0.0) + us / 1e3 / k
+                fin = np.isfinite(sim.particles()["Position"]).all()       # device -> host read: the steps have completed
+                el = time.perf_counter() - t0
+            out[key] = {"ms_per_step": 1e3 * el / k, "pcg_it_mean": float(np.mean(its)), "steps": k, "phase_ms": {a: round(b, 2) for a, b in tm.items()},
+                        "positions_finite": bool(fin)}
+        except Exception as ex:
+            out[key] = {"error": repr(ex)}
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3], help="BASELINE.json config: 1 = 27k dam break, DFSPH only; 2 = 100k viscous block; "
+                                                                             "3 = 1M dam break, DFSPH + viscosity + surface tension (the metric's config, default)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--side", type=int, default=100, help="block edge in particles (100 -> 1M)")
-    ap.add_argument("--settle", type=int, default=200, help="scene-preparation steps before warm-up (SURVEY.md §8d)")
+    ap.add_argument("--side", type=int, default=None, help="block edge in particles (default: the config's; 100 -> 1M)")
+    ap.add_argument("--settle", type=int, default=None, help="scene-preparation steps before warm-up (SURVEY.md §8d; default 200)")
+    ap.add_argument("--ref-steps", type=int, default=12, help="--impl reference: timed steps (a bounded sample: ~1 s each at 1M on 16 cores)")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA build on this GPU")
+    ap.add_argument("--scene", default="dam", choices=["dam", "tank"], help="N > 1: the dam break stretched along x (default; the N = 1 scene at N = 1) or a closed tank")
     ap.add_argument("--ref-side", type=int, default=50)
     ap.add_argument("--ref-settle", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -300,6 +384,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     args.warmup = max(args.warmup, 3)
+    global CONFIG_NAME
+    cfg = CONFIGS[args.config]
+    args.side = args.side or cfg["side"]
+    args.settle = cfg["settle"] if args.settle is None else args.settle
+    CONFIG_DESC.clear(); CONFIG_DESC.update(cfg["desc"])
+    CONFIG_NAME = cfg["name"]
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -354,8 +444,10 @@ def main():
     out = {
         "metric": "DFSPH particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "dam break %d^3 = %d particles, DFSPH (2 divergence + 2 pressure Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; "
-                               "%d settle steps; working set > L2 (neighbour list alone %.0f MB), no flush" % (args.side, n, args.settle, n * 70 * 4 / 1e6),
+        "config": {"workload": CONFIG_NAME % (args.side, n) + "; %d settle steps; %s" % (args.settle,
+                               "working set > L2 (neighbour list and pair coefficients alone %.0f MB), no flush" % (n * 72 * 6 / 1e6) if n * 72 * 6 > 126e6 else
+                               "working set %.0f MB of list and coefficients: L2-resident, flushed between steps by nothing (stated: NOT flushed)" % (n * 72 * 6 / 1e6)),
+                   "baseline_config": args.config,
                    "particles": n, "mean_neighbours": mbar, "pcg_iterations_last_step": int(dbg.ViscositySolverIterationCount),
                    "grid_tiles": tstats["tiles"], "tile_passes_on_slow_path": tstats["fallback_tile_passes"],
                    "kernels": table},
@@ -385,9 +477,29 @@ def main():
 
     if not args.no_cpu_baseline:
         try:
-            out["cpu_baseline"] = cpu_baseline(settled, settled_dt, settled_st, pos, box, res)
+            # the GPU's step from the settled state, for the parity block (host-order search: the oracle is host-compiled)
+            g = api.DFSPHSimulation(description(api.DFSPHSimulationDescription), device=local)
+            g.set_option(api.VFD_OPT_SEARCH_FMA, 0)
+            g.SetFluidObjects([api.FluidObject(pos)])
+            g.SetRigidBodies([vm])
+            g.set_particles_full(settled)
+            g.set_time_step(settled_dt)
+            g.set_surface_tension_state(*settled_st)
+            g.OnUpdate()
+            gpu_step = g.particles()
+            g.close()
+            out["cpu_baseline"], out["parity"] = cpu_baseline(settled, settled_dt, settled_st, pos, box, res, gpu_step=gpu_step)
         except Exception as ex:      # the baseline must not take the GPU number down with it
             out["cpu_baseline"] = {"error": repr(ex)}
+    if not args.no_ref_cuda and not args.no_cpu_baseline:
+        try:
+            sim.close()
+            out["reference_cuda"] = reference_cuda(settled, settled_dt, settled_st, pos, box, res)
+            ie = (out["reference_cuda"] or {}).get("ieee") or {}
+            if ie.get("ms_per_step"):
+                out["reference_cuda"]["speedup_over_ieee"] = ie["ms_per_step"] / (ms / args.steps)
+        except Exception as ex:
+            out["reference_cuda"] = {"error": repr(ex)}
     print(json.dumps(out))
     return 0
 

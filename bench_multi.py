@@ -16,11 +16,14 @@ import numpy as np
 R, D, H = 0.025, 0.05, 0.1
 
 
-def dist_scene(side, world):
-    """The global block of world*side x side x side particles in a tank with 2d clearance below/beside and free head room."""
+def dist_scene(side, world, kind="dam"):
+    """The global block of world*side x side x side particles: "dam" — at the left end of a box twice its length (bench.py's
+    1-GPU dam break stretched along x: at world = 1 the very same scene); "tank" — filling a closed tank along x (the slabs
+    never move)."""
     from vfd_b200 import api
     nx = side * world
-    box = ((0.0, 0.0, 0.0), (nx * D + 4 * D, 1.4 * side * D + 4 * D, side * D + 4 * D))
+    lx = 2 * nx * D if kind == "dam" else nx * D
+    box = ((0.0, 0.0, 0.0), (lx + 4 * D, 1.4 * side * D + 4 * D, side * D + 4 * D))
     ext = [b - a + 2 * (8 * H - R) for a, b in zip(*box)]
     res = tuple(min(256, max(8, int(np.ceil(e / (4 * H))))) for e in ext)
     return nx, box, res
@@ -39,7 +42,7 @@ def setup(args, rank, local, world, description, frames=0):
     import torch
     import torch.distributed as dist
     from vfd_b200 import api, partition
-    nx, box, res = dist_scene(args.side, world)
+    nx, box, res = dist_scene(args.side, world, getattr(args, "scene", "dam"))
     sim = api.DFSPHSimulation(description(api.DFSPHSimulationDescription, frames=frames), device=local)
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
@@ -57,7 +60,7 @@ def setup(args, rank, local, world, description, frames=0):
     sim.set_slab(int(bounds[rank]), int(bounds[rank + 1]))
     n_global = world * args.side ** 3
     ghost = int(tiles[1]) * int(tiles[2]) * 64 * 12 * 2
-    sim.set_particles_distributed(pos, None, ids, n_global, int(1.25 * len(pos)) + 2 * ghost)
+    sim.set_particles_distributed(pos, None, ids, n_global, int(1.5 * len(pos)) + 2 * ghost)
     vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R, device=local)
     sim.SetRigidBodies([vm])
     return sim, n_global, bounds, hist.cpu().numpy()
@@ -132,8 +135,11 @@ def main(args, rank, local, world):
         out = {
             "metric": "DFSPH particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "closed tank, %d x %d^3 = %d particles (%d^3 per GPU), DFSPH (2+2 Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; "
-                                   "%d settle steps; slabs of tile columns along x, NCCL halo exchange; working set > L2, no flush" % (world, args.side, n_global, args.side, args.settle),
+            "config": {"workload": "%s, %d x %d^3 = %d particles (%d^3 per GPU), DFSPH (2+2 Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; "
+                                   "%d settle steps; slabs of tile columns along x re-balanced while stepping, halos and all-reduces through peer memory (%s); working set > L2, no flush" % (
+                                       "dam break (the 1-GPU scene stretched along x)" if args.scene == "dam" else "closed tank", world, args.side, n_global, args.side, args.settle,
+                                       "CUDA IPC over NVLink" if sim.slab()["peer_memory"] else "off: NCCL only"),
+                       "slab_rank0_now": sim.slab(),
                        "particles": n_global, "slab_bounds_tile_columns": [int(b) for b in bounds], "owned_per_rank": [int(o.item()) for o in owns],
                        "pcg_iterations_last_step": int(dbg.ViscositySolverIterationCount),
                        "per_step_rank0": {"halo_exchanges": per_step["halos"], "all_reduces": per_step["reductions"],

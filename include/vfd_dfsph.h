@@ -215,7 +215,11 @@ int vfd_dfsph_time_matvec(VfdDfsph* h, uint32_t reps, float* ms);
  * No reference equivalent (the reference drives device 0 only: VFD/Source/Debug/SystemInfo.cpp:34-35).
  * Call order on every rank:  create -> init_distributed -> get_grid / set_slab -> set_particles_distributed ->
  * set_rigid_bodies -> step ...  Ranks own consecutive slabs in rank order; rank r exchanges with r-1 and r+1 only.
- * NCCL (libnccl.so.2) is loaded at run time by init_distributed; single-GPU use never needs it. */
+ * NCCL (libnccl.so.2) is loaded at run time by init_distributed; single-GPU use never needs it.
+ * Baked frames (simulate / step with FrameCount > 0) are whole-scene frames in original particle order — nGlobal entries of
+ * VfdParticleSimple, gathered by persistent id — and live on rank 0: vfd_dfsph_get_frame there, nothing on the other ranks.
+ * The original-order dumps (get_particles, get_current_frame, get_neighbors, get_boundary) are single-GPU calls; a rank's own
+ * particles are read with vfd_dfsph_get_owned. */
 int vfd_dist_unique_id(char out[128]);     /* on rank 0; hand the 128 bytes to every rank (ncclGetUniqueId) */
 int vfd_dfsph_init_distributed(VfdDfsph* h, int rank, int nranks, const char id[128], const float domainMin[3], const float domainMax[3]);
 /* the global search grid over the domain: origin, cell size, tiles (4x4x4 cells) per axis; identical on all ranks */
@@ -230,6 +234,10 @@ int vfd_dfsph_set_particles_distributed(VfdDfsph* h, const float* pos_xyz, const
 int vfd_dfsph_get_owned(VfdDfsph* h, uint32_t capacity, uint32_t* count, uint32_t* ids, VfdParticle* out);
 /* halo exchanges, all-reduces, halo bytes sent, state-exchange bytes sent since creation */
 int vfd_dfsph_get_comm_stats(VfdDfsph* h, uint64_t stats[4]);
+/* the slab now: set_slab gives the start; every VFD_DIST_REBALANCE steps (environment, default 4, 0 = never) a boundary moves by
+ * one tile column towards the heavier of the two ranks it separates.  info[0] lo, [1] hi, [2] boundary moves of
+ * this rank so far, [3] 1 when the ranks exchange through peer memory (CUDA IPC over NVLink), 0 when through NCCL only */
+int vfd_dfsph_get_slab(VfdDfsph* h, uint64_t info[4]);
 
 /* per-kernel device time accumulated while VFD_OPT_KERNEL_TIMERS is on.  *count receives the number of kernel
  * classes; names/ms/launches (each may be NULL) receive up to `capacity` entries.  msActive/launchesActive count only

@@ -161,6 +161,7 @@ SYMBOLS = [
     ("vfd_dfsph_set_particles_distributed", _i, [_vp, _vp, _vp, _vp, _u32, _u32, _u32]),
     ("vfd_dfsph_get_owned", _i, [_vp, _u32, C.POINTER(_u32), _vp, _vp]),
     ("vfd_dfsph_get_comm_stats", _i, [_vp, _vp]),
+    ("vfd_dfsph_get_slab", _i, [_vp, _vp]),
     ("vfd_dfsph_get_kernel_times", _i, [_vp, _u32, C.POINTER(_u32), _vp, _vp, _vp, _vp, _vp, _i]),
     ("vfd_dfsph_record_event", _i, [_vp, _u32]),
     ("vfd_dfsph_elapsed_ms", _i, [_vp, _u32, _u32, C.POINTER(_f32)]),
@@ -355,7 +356,7 @@ class DFSPHSimulation:
 
     def GetFrame(self, index):
         """One baked DFSPHParticleFrame: (ParticleData[n], MaxVelocityMagnitude, CurrentTimeStep)."""
-        out = np.zeros(self.n, PARTICLE_SIMPLE_DTYPE)
+        out = np.zeros(getattr(self, "n_global", None) or self.n, PARTICLE_SIMPLE_DTYPE)      # a decomposed run bakes whole-scene frames on rank 0
         mv, dt = C.c_float(), C.c_float()
         self._ck(self.L.vfd_dfsph_get_frame(self.h, index, _p(out), C.byref(mv), C.byref(dt)))
         return out, mv.value, dt.value
@@ -497,6 +498,7 @@ class DFSPHSimulation:
             vel = np.ascontiguousarray(vel, np.float32).reshape(-1, 3)
             velp = _p(vel)
         self.n = pos.shape[0]
+        self.n_global = int(n_global)
         self._ck(self.L.vfd_dfsph_set_particles_distributed(self.h, _p(pos), velp, _p(ids), self.n, int(n_global), int(capacity)))
 
     def owned(self):
@@ -507,6 +509,12 @@ class DFSPHSimulation:
         out = np.zeros(max(cnt.value, 1), PARTICLE_DTYPE)
         self._ck(self.L.vfd_dfsph_get_owned(self.h, cnt.value, C.byref(cnt), _p(ids), _p(out)))
         return ids[:cnt.value], out[:cnt.value]
+
+    def slab(self):
+        """Owned tile columns [lo, hi) now, boundary moves so far, whether the ranks talk through peer memory."""
+        st = np.zeros(4, np.uint64)
+        self._ck(self.L.vfd_dfsph_get_slab(self.h, _p(st)))
+        return {"lo": int(st[0]), "hi": int(st[1]), "shifts": int(st[2]), "peer_memory": bool(st[3])}
 
     def comm_stats(self):
         st = np.zeros(4, np.uint64)

@@ -200,6 +200,13 @@ int vfd_dfsph_get_comm_stats(VfdDfsph* h, uint64_t stats[4]) {
     return VFD_OK;
 }
 
+int vfd_dfsph_get_slab(VfdDfsph* h, uint64_t info[4]) {
+    GUARD(h); if (!info) return VFD_E_INVALID;
+    if (!h->s.dist) return h->s.fail(VFD_E_INVALID, "not distributed");
+    info[0] = h->s.dist->colLo; info[1] = h->s.dist->colHi; info[2] = h->s.dist->shifts; info[3] = h->s.dist->p2p ? 1u : 0u;
+    return VFD_OK;
+}
+
 int vfd_dfsph_get_kernel_times(VfdDfsph* h, uint32_t capacity, uint32_t* count, const char** names, double* ms, uint64_t* launches,
                                double* msActive, uint64_t* launchesActive, int reset) {
     GUARD(h);

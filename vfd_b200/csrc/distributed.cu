@@ -32,6 +32,7 @@
 namespace vfd {
 
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda(e__, #call, __LINE__); } while (0)
+#define RC_(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
 #define NK(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return fail(VFD_E_NCCL, std::string("NCCL error: ") + dist->api.GetErrorString(r__) + " in " #call); } while (0)
 
 // NCCL is resolved at run time (the library has no link-time dependency on it; a single-GPU user never loads it).
@@ -217,7 +218,8 @@ int Solver::dist_init(int rank, int nranks, const char* id128, const float* dmin
     dist_grid(dmin, dmax, info.SupportRadius, dist->origin, dist->gdim);
     for (int k = 0; k < 3; k++) dist->gtiles[k] = dist->gdim[k] / 4;
     dist->colLo = 0; dist->colHi = dist->gtiles[0];
-    CK(cudaMalloc(&dist->dCounters, 16 * sizeof(uint32_t)));
+    CK(cudaMalloc(&dist->dCounters, 64 * sizeof(uint32_t)));
+    { const char* e = getenv("VFD_DIST_REBALANCE"); if (e) dist->rebalanceEvery = atoi(e); }
     CK(cudaMallocHost(&dist->hCounters, 16 * sizeof(uint32_t)));
     return VFD_OK;
 }
@@ -333,9 +335,32 @@ void Solver::dist_free_slab() {
 }
 
 // migration + ghost refresh (see the header of this file)
+// the device's copy of the local grid (DevState: gridMinCell .. gridOrigin, cellOffset) after the slab's bounds have changed
+int Solver::dist_upload_grid() {
+    static_assert(offsetof(DevState, gridOrigin) > offsetof(DevState, gridMinCell), "grid fields are contiguous in DevState");
+    DevState& g = hState[2];
+    memset(&g, 0, sizeof g);
+    dist_apply_grid(g);
+    const size_t a = offsetof(DevState, gridMinCell), b = offsetof(DevState, gridOrigin) + sizeof(g.gridOrigin);
+    CK(cudaMemcpyAsync((char*)dState + a, (char*)&g + a, b - a, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync((char*)dState + offsetof(DevState, cellOffset), (char*)&g + offsetof(DevState, cellOffset), sizeof(g.cellOffset), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));        // hState[2] is reused
+    cellEstimate = g.nCells;
+    return VFD_OK;
+}
+
 int Solver::dist_exchange_state() {
     Dist& D = *dist;
     const bool hasL = D.rank > 0, hasR = D.rank + 1 < D.nranks;
+    if (D.pendL || D.pendR) {
+        // a tile column changes hands: the new bounds classify this step's particles, the column itself travels with the
+        // migrants below (what was an edge column becomes the neighbour's first owned one, and stays here as the ghost copy)
+        D.colLo = (uint32_t)((int)D.colLo + D.pendL);
+        D.colHi = (uint32_t)((int)D.colHi + D.pendR);
+        D.shifts += (D.pendL != 0) + (D.pendR != 0);
+        D.pendL = D.pendR = 0;
+        RC_(dist_upload_grid());
+    }
     Params P = params;
     const float invCell = (1.0f / info.SupportRadius) * (1.0f - 1.0f / 1024.0f);
     CK(cudaMemsetAsync(D.dCounters, 0, 16 * sizeof(uint32_t), stream));
@@ -398,17 +423,34 @@ int Solver::dist_read_ranges() {
     uint32_t* d = D.dCounters + 8;
     // to each neighbour: the size of the edge column it mirrors, and where my own range ends (= where my ghost-R range begins:
     // the right neighbour writes its halos there)
-    const uint32_t mine[4] = { D.edgeLEnd - D.ownB, D.ownE, D.ownE - D.edgeRBegin, D.ownE };
-    CK(cudaMemcpyAsync(d, mine, 16, cudaMemcpyHostToDevice, stream));
+    // to each neighbour: the size of the edge column it mirrors, where my own range ends (= where my ghost-R range begins: the
+    // right neighbour writes its halos there), how many particles and tile columns I own (slab re-balancing)
+    const uint32_t nOwn = D.ownE - D.ownB, cols = D.colHi - D.colLo;
+    const uint32_t mine[8] = { D.edgeLEnd - D.ownB, D.ownE, nOwn, cols, D.ownE - D.edgeRBegin, D.ownE, nOwn, cols };
+    uint32_t* d2 = D.dCounters + 16;            // [0..7] mine, [8..11] from the left, [12..15] from the right
+    CK(cudaMemcpyAsync(d2, mine, 32, cudaMemcpyHostToDevice, stream));
     NK(D.api.GroupStart());
-    if (hasL) { NK(D.api.Send(d + 0, 2, ncclUint32, D.rank - 1, D.comm, stream)); NK(D.api.Recv(d + 4, 2, ncclUint32, D.rank - 1, D.comm, stream)); }
-    if (hasR) { NK(D.api.Send(d + 2, 2, ncclUint32, D.rank + 1, D.comm, stream)); NK(D.api.Recv(d + 6, 2, ncclUint32, D.rank + 1, D.comm, stream)); }
+    if (hasL) { NK(D.api.Send(d2 + 0, 4, ncclUint32, D.rank - 1, D.comm, stream)); NK(D.api.Recv(d2 + 8, 4, ncclUint32, D.rank - 1, D.comm, stream)); }
+    if (hasR) { NK(D.api.Send(d2 + 4, 4, ncclUint32, D.rank + 1, D.comm, stream)); NK(D.api.Recv(d2 + 12, 4, ncclUint32, D.rank + 1, D.comm, stream)); }
     NK(D.api.GroupEnd());
-    uint32_t got[4] = { 0, 0, 0, 0 };
-    CK(cudaMemcpyAsync(got, d + 4, 16, cudaMemcpyDeviceToHost, stream));
+    uint32_t got[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    CK(cudaMemcpyAsync(got, d2 + 8, 32, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    h[4] = got[0]; h[5] = got[2];
+    h[4] = got[0]; h[5] = got[4];
     D.leftOwnE = got[1];
+    D.stepsDone++;
+    if (D.rebalanceEvery > 0 && D.stepsDone % (uint64_t)D.rebalanceEvery == 0) {
+        // boundary between ranks a (left) and b (right): a's last column goes to b when a is heavier by more than that column
+        // (the move then shrinks the difference), b's first column to a in the opposite case; only a slab of four or more columns gives one away (it may lose one on
+        // either side in the same step).  Same numbers, same decision on both sides.
+        auto decide = [](uint32_t nA, uint32_t nB, uint32_t edgeA, uint32_t edgeB, uint32_t colsA, uint32_t colsB) -> int {
+            if (nA > nB && (uint64_t)(nA - nB) > (uint64_t)edgeA && colsA > 3u) return -1;
+            if (nB > nA && (uint64_t)(nB - nA) > (uint64_t)edgeB && colsB > 3u) return +1;
+            return 0;
+        };
+        if (hasL) D.pendL = decide(got[2], nOwn, got[0], D.edgeLEnd - D.ownB, got[3], cols);
+        if (hasR) D.pendR = decide(nOwn, got[6], D.ownE - D.edgeRBegin, got[4], cols, got[7]);
+    }
     const uint32_t ghostL = D.ownB, ghostR = D.nLocal - D.ownE;
     if ((hasL && h[4] != ghostL) || (hasR && h[5] != ghostR) || (!hasL && ghostL) || (!hasR && ghostR)) {
         char buf[256];
@@ -479,12 +521,97 @@ int Solver::dist_reduce(int site, bool isMax) {
     return VFD_OK;
 }
 
-// Frame capture of a decomposed run (DFSPHImplementation.cu:148-167 across ranks).  Not gathered yet: a distributed handle
-// bakes no frames (FrameCount must be 0; the state is read with get_owned), and says so instead of exporting its slab with
-// global ids into a buffer sized for the local count.
+// ---- frame capture of a decomposed run (DFSPHImplementation.cu:148-167 across ranks) ------------------------------------
+// Every rank packs its owned particles as 40-byte records (persistent id + DFSPHParticleSimple); rank 0 receives them and
+// scatters them by id into the frame (original particle order, what the reference's renderer indexes across frames:
+// Scene.cpp:361-368), which then flows through rank 0's frame pipe like a single-GPU frame.  The other ranks bake nothing.
+struct FrameRec { uint32_t id; float v[9]; };
+static_assert(sizeof(FrameRec) == 40, "frame record");
+
+__global__ void k_export_owned_frame(Arrays A, uint32_t ownB, uint32_t ownE, FrameRec* __restrict__ out) {
+    const uint32_t p = ownB + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ownE) return;
+    const float4 x = A.pos[p], v = A.vel[p], a = A.acc[p];
+    FrameRec r;
+    r.id = A.id[p];
+    r.v[0] = x.x; r.v[1] = x.y; r.v[2] = x.z; r.v[3] = v.x; r.v[4] = v.y; r.v[5] = v.z; r.v[6] = a.x; r.v[7] = a.y; r.v[8] = a.z;
+    out[p - ownB] = r;
+}
+
+__global__ void k_scatter_frame(const FrameRec* __restrict__ in, uint32_t count, uint32_t nGlobal, VfdParticleSimple* __restrict__ out,
+                                const DevState* __restrict__ S, float* __restrict__ meta) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && meta) { meta[0] = S->vmax2; meta[1] = S->dt; }
+    if (i >= count) return;
+    const FrameRec r = in[i];
+    if (r.id >= nGlobal) return;
+    VfdParticleSimple q;
+    q.Position[0] = r.v[0]; q.Position[1] = r.v[1]; q.Position[2] = r.v[2];
+    q.Velocity[0] = r.v[3]; q.Velocity[1] = r.v[4]; q.Velocity[2] = r.v[5];
+    q.Acceleration[0] = r.v[6]; q.Acceleration[1] = r.v[7]; q.Acceleration[2] = r.v[8];
+    out[r.id] = q;
+}
+
+int Solver::dist_capture_frame(bool metaFromDevice, float vmax2, float dt) {
+    Dist& D = *dist;
+    const uint32_t nOwn = D.ownE - D.ownB;
+    if (!D.frameSend) CK(cudaMalloc(&D.frameSend, (size_t)std::max(D.capacity, 1u) * sizeof(FrameRec)));
+    if (nOwn) { k_export_owned_frame<<<(nOwn + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, stream>>>(arrays, D.ownB, D.ownE, (FrameRec*)D.frameSend); launches += 1; }
+    // every rank's record count, on every rank
+    uint32_t* d = D.dCounters + 32;             // [0] mine, [8..15] all
+    CK(cudaMemcpyAsync(d, &nOwn, 4, cudaMemcpyHostToDevice, stream));
+    NK(D.api.AllGather(d, d + 8, 1, ncclUint32, D.comm, stream));
+    uint32_t cnt[8] = {};
+    CK(cudaMemcpyAsync(cnt, d + 8, 4 * (size_t)D.nranks, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    uint64_t total = 0;
+    for (int r = 0; r < D.nranks; r++) total += cnt[r];
+    if (total != D.nGlobal) return fail(VFD_E_NCCL, "frame gather: the ranks' owned particles do not add up to the global count");
+    if (D.rank == 0 && D.frameRecvCap < D.nGlobal) {
+        if (D.frameRecv) cudaFree(D.frameRecv);
+        D.frameRecv = nullptr;
+        CK(cudaMalloc(&D.frameRecv, (size_t)D.nGlobal * sizeof(FrameRec)));
+        D.frameRecvCap = D.nGlobal;
+    }
+    NK(D.api.GroupStart());
+    if (D.rank == 0) {
+        size_t off = cnt[0];
+        for (int r = 1; r < D.nranks; r++) { if (cnt[r]) NK(D.api.Recv((FrameRec*)D.frameRecv + off, (size_t)cnt[r] * 10, ncclFloat32, r, D.comm, stream)); off += cnt[r]; }
+    } else if (nOwn) {
+        NK(D.api.Send(D.frameSend, (size_t)nOwn * 10, ncclFloat32, 0, D.comm, stream));
+    }
+    NK(D.api.GroupEnd());
+    if (D.rank == 0) {
+        if (nOwn) CK(cudaMemcpyAsync(D.frameRecv, D.frameSend, (size_t)nOwn * sizeof(FrameRec), cudaMemcpyDeviceToDevice, stream));
+        VfdParticleSimple* dst = pipe.acquire();
+        if (!dst) { cudaGetLastError(); return fail(VFD_E_CUDA, "frame capture: cannot allocate the frame ring buffers"); }
+        k_scatter_frame<<<(D.nGlobal + VFD_TPB - 1) / VFD_TPB, VFD_TPB, 0, stream>>>((const FrameRec*)D.frameRecv, D.nGlobal, D.nGlobal, dst, dState, metaFromDevice ? pipe.meta_slot() : nullptr);
+        launches += 1;
+        CK(pipe.submit(stream, vmax2, dt, metaFromDevice));
+    }
+    return VFD_OK;
+}
+
+// the frame section of Solver::step for a rank of a decomposition: the same decisions on every rank (the time step is global)
 int Solver::dist_frame_step() {
-    if (desc.FrameCount > 0 && frameIndexHost < desc.FrameCount)
-        return fail(VFD_E_INVALID, "a distributed handle does not bake frames: set FrameCount = 0 and read the slabs with vfd_dfsph_get_owned");
+    if (frameIndexHost >= desc.FrameCount) return VFD_OK;
+    if (desc.FrameLength <= 0.0f && state == VFD_STATE_SIMULATING) {
+        RC_(dist_capture_frame(true, 0.0f, 0.0f));
+        frameTimeHost = 0.0f;
+        frameIndexHost++;
+        return VFD_OK;
+    }
+    DevState s;
+    RC_(read_state(s));
+    frameTimeHost += s.dt;
+    update_debug(s, false);
+    if (frameTimeHost >= desc.FrameLength) {
+        RC_(dist_capture_frame(false, s.vmax2, s.dt));
+        frameTimeHost = 0.0f;
+        frameIndexHost++;
+        std::lock_guard<std::mutex> g(dbgMutex);
+        debug.FrameTime = 0.0f; debug.FrameIndex = frameIndexHost;
+    }
     return VFD_OK;
 }
 
@@ -513,7 +640,7 @@ Dist::~Dist() {
     for (int r = 0; r < 8; r++) if (r != rank && peerSlab[r]) cudaIpcCloseMemHandle(peerSlab[r]);
     if (slab) cudaFree(slab);
     if (comm && api.CommDestroy) api.CommDestroy(comm);
-    cudaFree(sendL); cudaFree(sendR); cudaFree(recvL); cudaFree(recvR); cudaFree(dCounters);
+    cudaFree(sendL); cudaFree(sendR); cudaFree(recvL); cudaFree(recvR); cudaFree(dCounters); cudaFree(frameSend); cudaFree(frameRecv);
     if (hCounters) cudaFreeHost(hCounters);
 }
 

@@ -346,7 +346,9 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
         // fixed local grid: owned tile columns + ghost columns
         DevState g; memset(&g, 0, sizeof g);
         dist_apply_grid(g);
-        cellEstimate = g.nCells; cellCapacity = g.nCells + 64;
+        cellEstimate = g.nCells;
+        // the slab's bounds move (re-balancing): room for the whole domain's tile columns plus the two ghost columns
+        cellCapacity = (dist->gtiles[0] + 2u) * dist->gtiles[1] * dist->gtiles[2] * 64u + 64u;
     }
     CK(dalloc(A.cellCount, (size_t)cellCapacity + 4)); CK(dalloc(A.cellBegin, (size_t)cellCapacity + 4));
     CK(cudaMemset(A.cellCount, 0, ((size_t)cellCapacity + 4) * 4));
@@ -422,7 +424,7 @@ int Solver::dist_set_particles(const float* pos, const float* vel, const uint32_
     float bmin[3] = { 0, 0, 0 }, bmax[3] = { 1, 1, 1 };
     int rc = alloc_particles(n, bmin, bmax);
     if (rc) return rc;
-    CK(pipe.configure(device, n));
+    CK(pipe.configure(device, D.rank == 0 ? nGlobal : 0u));          // frames are whole-scene frames, gathered on rank 0
     // rigid-body sample arrays are sized with the particle arrays
     if (n) {
         float *dPos = nullptr, *dVel = nullptr;

@@ -47,6 +47,14 @@ struct Dist {
     uint64_t slabNp[8] = {};                  // particle slots of every rank's arrays (region offsets follow from it)
     unsigned char* peerSlab[8] = {};          // every rank's slab in this process' address space (own: slab)
     uint32_t leftOwnE = 0;                    // where the left neighbour's ghost-R range begins (its ownE), renewed every step
+    // slab re-balancing: every `rebalanceEvery` steps a boundary moves by one tile column towards the heavier neighbour; both
+    // sides of a boundary take the decision from the same six numbers, the column changes hands in the next state exchange
+    int rebalanceEvery = 4;
+    int pendL = 0, pendR = 0;                 // pending move of my left / right boundary (-1: one column to the left, +1: to the right)
+    uint64_t stepsDone = 0, shifts = 0;
+    // baked frames of a decomposed run: owned particles as (id, position, velocity, acceleration) records, gathered on rank 0
+    void *frameSend = nullptr, *frameRecv = nullptr;
+    uint32_t frameRecvCap = 0;
     ~Dist();
 };
 
@@ -122,8 +130,10 @@ private:
     int dist_halo(void* base, uint32_t elemFloats, void* base2 = nullptr, uint32_t elemFloats2 = 0);
     int dist_reduce(int site, bool isMax);
     int dist_frame_step();
+    int dist_capture_frame(bool metaFromDevice, float vmax2, float dt);
     int dist_alloc_slab(size_t np);
     void dist_free_slab();
+    int dist_upload_grid();
     int halo4(float4* a) { return dist ? dist_halo(a, 4) : VFD_OK; }
     int halo42(float4* a, float2* b) { return dist ? dist_halo(a, 4, b, 2) : VFD_OK; }
     int halo1(float* a) { return dist ? dist_halo(a, 1) : VFD_OK; }
