@@ -297,6 +297,7 @@ def cpu_baseline(state, dt, st, pos0, box, res, steps=10, gpu_step=None):
         sim.set_particles_full(state)
         sim.set_time_step(dt)
         sim.set_st_state(*st)
+        ref_map = sim.volume_map(0)       # the reference's own host precompute of the box's volume map: the same input for both
         sim.step(1)                       # untimed: first-touch of the reference's buffers; the parity reference
         first = sim.particles()
         t0 = time.perf_counter()
@@ -305,6 +306,7 @@ def cpu_baseline(state, dt, st, pos0, box, res, steps=10, gpu_step=None):
     n = len(pos0)
     par = None
     if gpu_step is not None:
+        gpu_step = gpu_step(ref_map)
         worst = ("", 0.0)
         for f in PARITY_FIELDS:
             x, y = np.asarray(gpu_step[f], np.float64), np.asarray(first[f], np.float64)
@@ -313,8 +315,10 @@ def cpu_baseline(state, dt, st, pos0, box, res, steps=10, gpu_step=None):
             if e > worst[1]:
                 worst = (f, e)
         par = {"worst_field": worst[0], "value": worst[1], "tol": 2.0e-5, "ok": bool(worst[1] <= 2.0e-5), "particles": n,
-               "note": "one step from the timed run's settled state: vfd_b200 (search without FMA contraction, as the host-compiled oracle) vs the "
-                       "reference's sources on the host cores; max |error| / max |field| over the fields of the 120-B particle state; tolerance as in "
+               "note": "one step from the timed run's settled state, both sides fed the reference's own volume map (its mesh distance is evaluated in "
+                       "fp32 on a 10-m box, which moves wall distances by up to 1e-3 against the analytic box distance the timed run's GPU-built map "
+                       "uses: DESIGN.md section 2): vfd_b200 (search without FMA contraction, as the host-compiled oracle) vs the reference's sources "
+                       "on the host cores; max |error| / max |field| over the fields of the 120-B particle state; tolerance as in "
                        "tests/test_gpu_scale.py (the reference moves by ~1e-5 against itself between two runs)"}
     return {"value": n * steps / el, "unit": "particle-steps/s", "cores": threads, "kind": "reference",
             "sample": "%d steps of the same %d-particle settled state (after 1 untimed step), %.1f s; PCG it of last step %d" % (
@@ -478,16 +482,19 @@ def main():
     if not args.no_cpu_baseline:
         try:
             # the GPU's step from the settled state, for the parity block (host-order search: the oracle is host-compiled)
-            g = api.DFSPHSimulation(description(api.DFSPHSimulationDescription), device=local)
-            g.set_option(api.VFD_OPT_SEARCH_FMA, 0)
-            g.SetFluidObjects([api.FluidObject(pos)])
-            g.SetRigidBodies([vm])
-            g.set_particles_full(settled)
-            g.set_time_step(settled_dt)
-            g.set_surface_tension_state(*settled_st)
-            g.OnUpdate()
-            gpu_step = g.particles()
-            g.close()
+            def gpu_step(m):
+                g = api.DFSPHSimulation(description(api.DFSPHSimulationDescription), device=local)
+                g.set_option(api.VFD_OPT_SEARCH_FMA, 0)
+                g.SetFluidObjects([api.FluidObject(pos)])
+                g.SetRigidBodies([api.VolumeMap(m["domain_min"], m["domain_max"], m["resolution"], m["cell_size"], m["cell_size_inv"], m["field_count"],
+                                                m["node_count"], m["cell_count"], m["cell_map_count"], m["nodes"], m["cells"], m["cell_map"])])
+                g.set_particles_full(settled)
+                g.set_time_step(settled_dt)
+                g.set_surface_tension_state(*settled_st)
+                g.OnUpdate()
+                got = g.particles()
+                g.close()
+                return got
             out["cpu_baseline"], out["parity"] = cpu_baseline(settled, settled_dt, settled_st, pos, box, res, gpu_step=gpu_step)
         except Exception as ex:      # the baseline must not take the GPU number down with it
             out["cpu_baseline"] = {"error": repr(ex)}

@@ -101,7 +101,7 @@ static size_t slab_offset(int region, uint64_t np) {
     for (int r = 0; r < region; r++) off += (size_t)np * kRegionBytes[r];
     return off;
 }
-static size_t slab_bytes(uint64_t np) { return slab_offset(SR_COUNT, np); }
+static size_t slab_bytes(uint64_t np) { return slab_offset(SR_COUNT, np) + 256; }     // + slack: granule-aligned bulk copies read up to one element past a range (tile.cuh)
 
 // One halo exchange of one array: this rank's first / last owned tile column straight into the ghost range of the left /
 // right neighbour's copy of the array (peer stores over NVLink), and theirs into ours.

@@ -11,6 +11,9 @@
 #include <limits.h>
 
 namespace vfd {
+#ifdef PIPE_TRACE
+void trace_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const char* path);
+#endif
 
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda(e__, #call, __LINE__); } while (0)
 
@@ -286,7 +289,8 @@ void Solver::refresh_params() {
     if (dist) dist_params(P);
 }
 
-template<typename T> static cudaError_t dalloc(T*& p, size_t count) { return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
+// + 32 elements: the bulk copies of an 8-byte payload array read whole 16-byte granules, i.e. up to one element past a range's end (tile.cuh)
+template<typename T> static cudaError_t dalloc(T*& p, size_t count) { return cudaMalloc((void**)&p, (std::max<size_t>(count, 1) + 32) * sizeof(T)); }
 
 void Solver::free_particles() {
     Arrays& A = arrays;
@@ -940,6 +944,9 @@ int Solver::time_matvec(uint32_t reps, float* ms) {
     CK(cudaEventSynchronize(b));
     CK(cudaEventElapsedTime(ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
+#ifdef PIPE_TRACE
+    { const char* path = getenv("VFD_TRACE_FILE"); if (path) trace_viscosity_matvec(L, params, arrays, dState, path); }
+#endif
     CK(cudaGetLastError());
     return VFD_OK;
 }

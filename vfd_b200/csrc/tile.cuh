@@ -34,7 +34,7 @@ namespace vfd {
 #define TT_LUT2 768            // density pass: two tables (80 kB), one CTA per SM
 #define TT_MATVEC 512          // PCG mat-vec (no table)
 #define TT_PLAIN 512
-#define STAGE_CAP 2432         // staged halo particles per tile, kernels without a table (one or two float4 arrays: 38 / 76 KB)
+#define STAGE_CAP 2688         // staged halo particles per tile, kernels without a table (one or two float4 arrays: 38 / 76 KB)
 #define STAGE_CAP_LUT 2240     // ... kernels with one table and two payload arrays: 40 + 70 + 3 KB, two CTAs per SM
 
 // ---- grid / key helpers ---------------------------------------------------------------------------
@@ -62,9 +62,21 @@ __device__ __forceinline__ uint32_t cell_key(uint32_t cx, uint32_t cy, uint32_t 
 }
 
 // ---- shared-memory header of a tile pass ----------------------------------------------------------
+// ---- the tile-local index space ------------------------------------------------------------------
+// A halo row (six x-adjacent cells) is three contiguous runs of the sorted arrays: the cell of the tile on the left
+// (hx = 0), the tile's own four cells (hx = 1..4), the cell of the tile on the right (hx = 5) — 108 segments per box.
+// Local indices number the box's particles in box order (hz, hy, hx) with every segment placed so that its particles'
+// local index has the parity of their global index, and padded to an even length: a segment [g, g + n) occupies the
+// slots [l - (g & 1), l + n + ((g + n) & 1)) where l is its first particle's local index.  8-byte payload arrays can then
+// be copied segment by segment in aligned 16-byte granules (bulk copies need 16-byte alignment on both sides and in the
+// size) without touching a neighbouring segment's slots; the price is one spare slot per segment on average (~5 %).
+__device__ __forceinline__ uint32_t seg_pre(int hx, uint32_t beg) { return (hx == 0 || hx == 1 || hx == 5) ? (beg & 1u) : 0u; }
+__device__ __forceinline__ uint32_t seg_post(int hx, uint32_t end) { return (hx == 0 || hx == 4 || hx == 5) ? (end & 1u) : 0u; }
+
 struct TileShared {
     uint32_t cellG[HALO_CELLS];       // global index of the first particle of each halo cell
-    uint32_t local[HALO_CELLS + 8];   // exclusive prefix of the halo cells' particle counts (local index space)
+    uint32_t cellE[HALO_CELLS];       // ... one past its last particle
+    uint32_t local[HALO_CELLS + 8];   // local index of the first particle of each halo cell (see above); [HALO_CELLS] = size of the index space
     uint32_t scan[32];
     double   red[4 * 32];
     uint32_t flag;
@@ -82,16 +94,19 @@ __device__ __forceinline__ TileInfo tile_setup(const DevState* __restrict__ S, c
     const uint32_t tdy = S->tileDim[1], tdz = S->tileDim[2];
     const uint32_t tz = tile % tdz, ty = (tile / tdz) % tdy, tx = tile / (tdz * tdy);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t cnt = 0, beg = 0;
+    uint32_t cnt = 0, beg = 0, pre = 0;     // cnt: the cell's slots (its particles + the segment padding it carries)
     if (tid < HALO_CELLS) {
         const int hx = tid % 6, hy = (tid / 6) % 6, hz = tid / 36;
         const int cx = (int)(tx << 2) + hx - 1, cy = (int)(ty << 2) + hy - 1, cz = (int)(tz << 2) + hz - 1;
+        uint32_t end = 0;
         if (cx >= 0 && cy >= 0 && cz >= 0 && cx < (int)S->gridDim[0] && cy < (int)S->gridDim[1] && cz < (int)S->gridDim[2]) {
             const uint32_t key = cell_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, S);
             beg = __ldg(cellBegin + key);
-            cnt = __ldg(cellBegin + key + 1) - beg;
+            end = __ldg(cellBegin + key + 1);
         }
-        sh.cellG[tid] = beg;
+        pre = seg_pre(hx, beg);
+        cnt = (end - beg) + pre + seg_post(hx, end);
+        sh.cellG[tid] = beg; sh.cellE[tid] = end;
     }
     // exclusive scan of 216 counts held by the first 7 warps
     uint32_t inc = cnt;
@@ -102,7 +117,7 @@ __device__ __forceinline__ TileInfo tile_setup(const DevState* __restrict__ S, c
     if (tid < HALO_CELLS) {
         uint32_t base = 0;
         for (int w = 0; w < warp; w++) base += sh.scan[w];
-        sh.local[tid] = base + inc - cnt;
+        sh.local[tid] = base + inc - cnt + pre;
         if (tid == HALO_CELLS - 1) sh.local[HALO_CELLS] = base + inc;
     }
     __syncthreads();
@@ -122,6 +137,15 @@ __device__ __forceinline__ uint32_t tile_local_to_global(const TileShared& sh, u
     return sh.cellG[lo] + (L - sh.local[lo]);
 }
 
+// the same for a slot that may be segment padding: false (and no particle) for those
+__device__ __forceinline__ bool tile_slot_to_global(const TileShared& sh, uint32_t L, uint32_t& g) {
+    int lo = 0, hi = HALO_CELLS;
+    #pragma unroll
+    for (int it = 0; it < 8; it++) { const int mid = (lo + hi) >> 1; if (hi - lo > 1) { if (sh.local[mid] <= L) lo = mid; else hi = mid; } }
+    g = sh.cellG[lo] + (L - sh.local[lo]);
+    return L >= sh.local[lo] && g < sh.cellE[lo];
+}
+
 // Step 2: stage the payload of every halo particle.  Flat over the local index space (consecutive threads read
 // consecutive particles of a cell: coalesced), four items per thread with all global loads issued before the first
 // shared-memory store, so a tile pays one round of L2 latency instead of one per cell.
@@ -132,12 +156,17 @@ __device__ __forceinline__ void tile_stage(const TileShared& sh, uint32_t total,
     for (uint32_t base = threadIdx.x; base < total; base += blockDim.x * U) {
         // items past the end are clamped to the last one (a duplicate store of the same value): no predicates, so the
         // payload registers stay registers
+        // padding slots receive a position no particle is near (ops that walk whole local ranges: the neighbour search)
         uint32_t l[U], g[U];
+        bool real[U];
         float4 a[U], b[U];
         #pragma unroll
-        for (int u = 0; u < U; u++) { l[u] = min(base + u * blockDim.x, total - 1u); g[u] = tile_local_to_global(sh, l[u]); }
+        for (int u = 0; u < U; u++) { l[u] = min(base + u * blockDim.x, total - 1u); real[u] = tile_slot_to_global(sh, l[u], g[u]); }
         #pragma unroll
-        for (int u = 0; u < U; u++) { a[u] = op.loadA(g[u]); if (NPAY > 1) b[u] = op.loadB(g[u]); }
+        for (int u = 0; u < U; u++) {
+            a[u] = real[u] ? op.loadA(g[u]) : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.0f);
+            if (NPAY > 1) b[u] = real[u] ? op.loadB(g[u]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
         #pragma unroll
         for (int u = 0; u < U; u++) { sA[l[u]] = a[u]; if (NPAY > 1) sB[l[u]] = b[u]; }
     }
@@ -158,7 +187,11 @@ __device__ __forceinline__ uint2 ell_pack(const uint32_t (&L)[4]) { return make_
 // staged / fallback gather of payload array A (for ops that run their own loops: search, classifier)
 template<bool STAGED, class Op> struct TileAcc {
     const TileShared& sh; const float4* sA; const Op& op;
-    __device__ __forceinline__ float4 operator()(uint32_t L) const { return STAGED ? sA[L] : op.loadA(tile_local_to_global(sh, L)); }
+    __device__ __forceinline__ float4 operator()(uint32_t L) const {
+        if (STAGED) return sA[L];
+        uint32_t g;                              // a padding slot reads as a position no particle is near, as in the stage
+        return tile_slot_to_global(sh, L, g) ? op.loadA(g) : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.0f);
+    }
 };
 
 // ---- the barrier-phased pass driver ------------------------------------------------------------------
@@ -278,6 +311,22 @@ using PipeCfgMany = PipeCfg<PIPE_MANY_CW, PIPE_MANY_D, PIPE_MANY_GW>;
 #endif
 using PipeCfgMatvec = PipeCfg<PIPE_MV_CW, PIPE_MV_D, PIPE_MV_GW>;    // the PCG mat-vec (payload 16 + 8 bytes)
 
+// PIPE_TRACE (diagnostic builds): CTA 0 logs (SM clock, event) pairs of its warps' lane 0 into a per-translation-unit buffer
+#ifdef PIPE_TRACE
+#define PIPE_TRACE_CAP 65536u
+static __device__ unsigned long long g_pipeTrace[2 * PIPE_TRACE_CAP];
+static __device__ unsigned int g_pipeTraceN, g_pipeTraceOn;
+__device__ __forceinline__ void ptrace(uint32_t code, uint32_t a, uint32_t b) {
+    if (blockIdx.x != 0 || (threadIdx.x & 31u) != 0u || !g_pipeTraceOn) return;
+    const unsigned int i = atomicAdd(&g_pipeTraceN, 1u);
+    if (i >= PIPE_TRACE_CAP) return;
+    g_pipeTrace[2 * i] = (unsigned long long)clock64();
+    g_pipeTrace[2 * i + 1] = ((unsigned long long)code << 56) | ((unsigned long long)(threadIdx.x >> 5) << 48) | ((unsigned long long)(a & 0xffffffu) << 24) | (unsigned long long)(b & 0xffffffu);
+}
+#else
+#define ptrace(code, a, b) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint2 ldg_stream(const uint2* p) { return __ldg(p); }
 __device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldg(p); }
 
@@ -286,7 +335,7 @@ struct StageHeader {
     uint32_t local[HALO_CELLS + 8];
     uint32_t begin, end, total, staged;      // begin == 0xffffffff: no more tiles for this CTA
     uint32_t base, li, pad[2];               // first ring slot of this tile's payload; the tile's entry in the tile list
-    uint32_t scan[4];
+    uint32_t cellE[HALO_CELLS];              // one past the last particle of each halo cell in the sorted arrays (for the copy warps)
 };
 // Grid-wide sums of a dynamically scheduled pass.  Every batch's warp-level sum goes into the record of its tile
 // (bsum[.][batch]); the warp that completes a tile's record folds it in batch order and stores ONE value per tile in
@@ -314,7 +363,8 @@ static_assert(sizeof(TileQueue) <= sizeof(RedRecord), "the queue overlays a redu
 
 struct PipeShared {
     unsigned long long full[PIPE_STAGES], empty[PIPE_STAGES];
-    uint32_t nextLi[2], lastCta, pad_;       // tile queue hand-over between the producer threads (two slots, used in turn); "this CTA finished last"
+    unsigned long long table[PIPE_STAGES];   // "the cell table of this stage's tile is complete" (scout -> copy warps)
+    uint32_t lastCta, ticket, pad_[2];       // "this CTA finished last"; batches handed out so far (pair passes)
     double red[4 * 32];
     RedRecord rec[PIPE_RED_RECORDS];
     StageHeader hdr[PIPE_STAGES];
@@ -347,12 +397,19 @@ __device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count)
 __device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
 }
+// A waiting warp must not eat the issue slots of the working ones (ncu of round 1's mat-vec: a quarter of all executed warp
+// instructions were these polls): after a failed try it sleeps before the next one (PIPE_WAIT_NS, 0 = poll flat out).
+#ifndef PIPE_WAIT_NS
+#define PIPE_WAIT_NS 100
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
     uint32_t done;
-    do {
+    for (;;) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    } while (!done);
+        if (done) break;
+        if (PIPE_WAIT_NS) __nanosleep(PIPE_WAIT_NS);
+    }
 }
 __device__ __forceinline__ bool mbar_test(unsigned long long* b, uint32_t parity) {     // non-blocking
     uint32_t done;
@@ -406,95 +463,130 @@ __device__ __forceinline__ uint32_t hdr_local_to_global(const StageHeader& H, ui
     return H.cellG[lo] + (L - H.local[lo]);
 }
 
-// ---- producer: the two producer warps of a CTA, all 64 threads ------------------------------------
-// Op supplies the global source arrays:  const float4* srcA();  const void* srcB()  (BBYTES 16: float4 array, 4: float array)
+// ---- producers: one scout warp and PIPE_COPY_WARPS copy warps ---------------------------------------------------
+// Round 1 had all producer warps do everything for one tile at a time: queue draw -> tile id -> cell table (three dependent
+// trips to L2) -> prefix sum -> ring space -> copies -> next tile.  A trace of the PCG mat-vec (PIPE_TRACE build,
+// profiles/r02_pipeline_trace.md) showed that chain to be the whole kernel: 6.5 - 7.5 us per tile, one tile after the other,
+// never waiting for the consumers, while the consumers went through every tile the instant it arrived (20 % of their time
+// waiting for it, every batch started cold).  The chain is now split by role:
+//   * the SCOUT warp draws tiles from the queue and builds their tables, one tile ahead of the copy warps, and publishes
+//     each through the stage's `table` mbarrier;
+//   * the COPY warps take the tables in order, claim ring space (the same bookkeeping in every copy thread, no barrier
+//     between them), and issue the copies: their loop is nothing but address arithmetic and LDGSTS / bulk copies.
+// Op supplies the global source arrays:  const float4* srcA();  const void* srcB()  (BBYTES 16: float4 array, 8 / 4: float2 / float array)
+#define PIPE_COPY_WARPS (PIPE_PRODUCER_WARPS - 1)
+#define PIPE_COPY_THREADS (PIPE_COPY_WARPS * 32)
+#define PIPE_FULL_ARRIVALS (PIPE_COPY_THREADS + 1u)   // every copy thread's copies have landed (cp.async.mbarrier.arrive.noinc) + the header (release)
 template<class Op>
-__device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Arrays& A, PipeShared& ps, unsigned char* pay, const Op& op,
-                                              uint32_t tile0, uint32_t tile1, bool checkIndexRange) {
+__device__ __forceinline__ void pipe_scout(DevState* __restrict__ S, const Arrays& A, PipeShared& ps, bool checkIndexRange) {
+    constexpr int CPL = (HALO_CELLS + 31) / 32;          // cells per lane: lane l owns the box cells [7 l, 7 l + 7)
+    constexpr uint32_t NONE = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t* __restrict__ cellBegin = A.cellBegin;
+    const uint32_t* __restrict__ tileList = A.tileList;
+    const uint32_t tdy = S->tileDim[1], tdz = S->tileDim[2];
+    const int gdx = (int)S->gridDim[0], gdy = (int)S->gridDim[1], gdz = (int)S->gridDim[2];
+    const uint32_t nList = __ldg(tileList);
+    // Tiles come from a queue: the list of non-empty owned tiles (search.cu: k_compact_tiles) is handed out entry by entry
+    // through an atomic cursor, so a CTA that drew cheap tiles (surface, boundary) simply draws more of them, and CTAs
+    // that run side by side still work on neighbouring tiles and share their halo boxes in L2.  Reductions do not depend
+    // on the schedule (common.cuh: fold_slots).
+    auto draw = [&]() -> uint32_t {
+        uint32_t v = 0;
+        if (lane == 0) v = atomicAdd(&S->tileCursor, 1u);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+    uint32_t b0 = 0, e0 = 0, beg[CPL], fin[CPL];          // per cell: first particle, one past the last
+    for (uint32_t k = 0;; k++) {
+        const uint32_t s = k % PIPE_STAGES, u = k / PIPE_STAGES;
+        StageHeader& H = ps.hdr[s];
+        // A tile is drawn when the tile two before it has been staged: late enough that a CTA never sits on a queue of tiles
+        // while others run dry at the end of the pass (the draw, the tile id and the cell table are three dependent trips to
+        // L2, ~2 us — a fraction of what the consumers need for a tile), early enough that the consumers find the table of
+        // their next batch's tile when they look ahead.
+        if (k >= 2u) mbar_wait(&ps.full[(k - 2u) % PIPE_STAGES], ((k - 2u) / PIPE_STAGES) & 1u);
+        const uint32_t li = draw();
+        const uint32_t tile = li < nList ? __ldg(tileList + 1u + li) : NONE;
+        const bool end = tile == NONE;
+        #pragma unroll
+        for (int i = 0; i < CPL; i++) { beg[i] = 0; fin[i] = 0; }
+        if (!end) {
+            b0 = __ldg(cellBegin + tile * TILE_CELLS); e0 = __ldg(cellBegin + tile * TILE_CELLS + TILE_CELLS);
+            const uint32_t tz = tile % tdz, ty = (tile / tdz) % tdy, tx = tile / (tdz * tdy);
+            #pragma unroll
+            for (int i = 0; i < CPL; i++) {
+                const int c = (int)lane * CPL + i;
+                if (c < HALO_CELLS) {
+                    const int hx = c % 6, hy = (c / 6) % 6, hz = c / 36;
+                    const int cx = (int)(tx << 2) + hx - 1, cy = (int)(ty << 2) + hy - 1, cz = (int)(tz << 2) + hz - 1;
+                    if (cx >= 0 && cy >= 0 && cz >= 0 && cx < gdx && cy < gdy && cz < gdz) {
+                        const uint32_t key = cell_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, S);
+                        beg[i] = __ldg(cellBegin + key);
+                        fin[i] = __ldg(cellBegin + key + 1);
+                    }
+                }
+            }
+        }
+        const uint32_t tb = b0, te = e0, tli = li;
+        // slots of each cell: its particles plus the padding of the segment it begins / ends (see "the tile-local index space")
+        uint32_t pre[CPL], slots[CPL], mine = 0;
+        #pragma unroll
+        for (int i = 0; i < CPL; i++) {
+            const int hx = ((int)lane * CPL + i) % 6;
+            pre[i] = seg_pre(hx, beg[i]);
+            slots[i] = (fin[i] - beg[i]) + pre[i] + seg_post(hx, fin[i]);
+            mine += slots[i];
+        }
+        uint32_t inc = mine;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += y; }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        ptrace(1, k, total);
+        mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);          // every consumer warp has released the slot's previous tile
+        ptrace(2, k, 0);
+        uint32_t run = inc - mine;
+        #pragma unroll
+        for (int i = 0; i < CPL; i++) {
+            const int c = (int)lane * CPL + i;
+            if (c < HALO_CELLS) { H.cellG[c] = beg[i]; H.local[c] = run + pre[i]; H.cellE[c] = fin[i]; }
+            run += slots[i];
+        }
+        if (lane == 0) {
+            H.local[HALO_CELLS] = total;
+            H.begin = end ? NONE : tb; H.end = end ? NONE : te; H.total = end ? 0u : total; H.li = tli;
+            if (!end && checkIndexRange && total > 65535u) atomicOr(&S->errorFlags, 2u);
+            if (!end && total > PIPE_CAP) atomicAdd(&S->fallbackTiles, 1u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ps.table[s]);        // release: the table of the CTA's k-th tile is complete
+        ptrace(3, k, 0);
+        if (end) break;
+    }
+}
+
+template<class Op>
+__device__ __forceinline__ void pipe_copier(PipeShared& ps, unsigned char* pay, const Op& op) {
     constexpr int BBYTES = Op::NPAY > 1 ? Op::BBYTES : 0;
-    const uint32_t pt = threadIdx.x - Op::Cfg::CW * 32, lane = pt & 31u, pw = pt >> 5;
-    // ring bookkeeping (identical in every producer thread): region of the tiles k-1, k-2, k-3 and the next free slot
+    constexpr uint32_t NONE = 0xffffffffu;
+    const uint32_t ct = threadIdx.x - (Op::Cfg::CW + 1) * 32, lane = ct & 31u, cw = ct >> 5;     // copy thread, its warp
+    const unsigned char* __restrict__ gA = reinterpret_cast<const unsigned char*>(op.srcA());
+    const unsigned char* __restrict__ gB = reinterpret_cast<const unsigned char*>(op.srcB());
+    // ring bookkeeping (identical in every copy thread): regions of the tiles k-1 ... and the next free slot
     uint32_t regB[PIPE_STAGES - 1], regE[PIPE_STAGES - 1];
     #pragma unroll
     for (int j = 0; j < PIPE_STAGES - 1; j++) { regB[j] = 0; regE[j] = 0; }
     uint32_t ringNext = 0;
-    const uint32_t* __restrict__ cellBegin = A.cellBegin;
-    const uint32_t tdy = S->tileDim[1], tdz = S->tileDim[2];
-    const int gdx = (int)S->gridDim[0], gdy = (int)S->gridDim[1], gdz = (int)S->gridDim[2];
-    const unsigned char* __restrict__ gA = reinterpret_cast<const unsigned char*>(op.srcA());
-    const unsigned char* __restrict__ gB = reinterpret_cast<const unsigned char*>(op.srcB());
-    // Tiles come from a queue: the list of non-empty owned tiles (search.cu: k_compact_tiles) is handed out entry by entry
-    // through an atomic cursor, so a CTA that drew cheap tiles (surface, boundary) simply draws more of them, and CTAs
-    // that run side by side still work on neighbouring tiles and share their halo boxes in L2.  (A static round robin
-    // left the average CTA idle for 20 % of a pass: ncu smsp__cycles_active 80 % of elapsed.)  Reductions do not depend
-    // on the schedule (common.cuh: fold_slots).  Thread 0 draws one entry ahead, so the atomic's round trip overlaps the copies.
-    const uint32_t* __restrict__ tileList = A.tileList;
-    const uint32_t nList = __ldg(tileList);
-    uint32_t li = 0xffffffffu, liCur = 0xffffffffu, tile = 0xffffffffu, drawn = 0xffffffffu;
-    const bool staticQueue = op.P.tune[6] == 1;          // A/B knob: entry i to CTA i mod G instead of the atomic cursor
-    if (pt == 0) ps.nextLi[0] = staticQueue ? blockIdx.x : atomicAdd(&S->tileCursor, 1u);
-    producer_sync();
-    li = ps.nextLi[0];
-    if (pt == 0) drawn = staticQueue ? li + gridDim.x : atomicAdd(&S->tileCursor, 1u);
-    // Thread pt owns PIPE_CELLS_PER_THREAD consecutive cells of the 6x6x6 box (box order hz, hy, hx).  The lookup of the
-    // CTA's next non-empty tile and the loads of its cell table are issued one tile ahead (right after the previous
-    // tile's copies), so their latency overlaps the copies and the wait for a free header slot.
-    uint32_t b0 = 0, e0 = 0;
-    uint32_t beg[PIPE_CELLS_PER_THREAD], cnt[PIPE_CELLS_PER_THREAD];
-    auto next_tile = [&]() {
-        if (li >= nList) { tile = 0xffffffffu; return; }
-        tile = __ldg(tileList + 1u + li);
-        liCur = li;
-        b0 = __ldg(cellBegin + tile * TILE_CELLS); e0 = __ldg(cellBegin + tile * TILE_CELLS + TILE_CELLS);
-        const uint32_t tz = tile % tdz, ty = (tile / tdz) % tdy, tx = tile / (tdz * tdy);
-        #pragma unroll
-        for (int i = 0; i < PIPE_CELLS_PER_THREAD; i++) {
-            const int c = (int)pt * PIPE_CELLS_PER_THREAD + i;
-            beg[i] = 0; cnt[i] = 0;
-            if (c < HALO_CELLS) {
-                const int hx = c % 6, hy = (c / 6) % 6, hz = c / 36;
-                const int cx = (int)(tx << 2) + hx - 1, cy = (int)(ty << 2) + hy - 1, cz = (int)(tz << 2) + hz - 1;
-                if (cx >= 0 && cy >= 0 && cz >= 0 && cx < gdx && cy < gdy && cz < gdz) {
-                    const uint32_t key = cell_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz, S);
-                    beg[i] = __ldg(cellBegin + key);
-                    cnt[i] = __ldg(cellBegin + key + 1) - beg[i];
-                }
-            }
-        }
-    };
-    next_tile();
     for (uint32_t k = 0;; k++) {
         const uint32_t s = k % PIPE_STAGES, u = k / PIPE_STAGES;
         StageHeader& H = ps.hdr[s];
-        if (tile == 0xffffffffu) {
-            mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);
-            if (pt == 0) { H.begin = 0xffffffffu; H.end = 0xffffffffu; H.total = 0; H.staged = 0; }
+        mbar_wait(&ps.table[s], u & 1u);
+        if (H.begin == NONE) {                            // the end marker goes straight through
+            if (ct == 0) { H.staged = 0u; H.base = 0u; }
             mbar_arrive(&ps.full[s]);
-            if (pt == 0) mbar_arrive(&ps.full[s]);
+            if (ct == 0) mbar_arrive(&ps.full[s]);
             break;
         }
-        const uint32_t tb = b0, te = e0, tli = liCur;
-        uint32_t mine = 0;
-        #pragma unroll
-        for (int i = 0; i < PIPE_CELLS_PER_THREAD; i++) mine += cnt[i];
-        uint32_t inc = mine;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += y; }
-        mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);          // every consumer warp has released the slot's previous tile
-        if (lane == 31) H.scan[pw] = inc;
-        if (pt == 0) ps.nextLi[(k + 1u) & 1u] = drawn;    // the entry drawn during the previous tile
-        producer_sync();
-        li = ps.nextLi[(k + 1u) & 1u];
-        if (pt == 0 && li < nList) drawn = staticQueue ? li + gridDim.x : atomicAdd(&S->tileCursor, 1u);
-        uint32_t run = inc - mine, total = 0;
-        #pragma unroll
-        for (int w = 0; w < PIPE_PRODUCER_WARPS; w++) { const uint32_t v = H.scan[w]; if ((uint32_t)w < pw) run += v; total += v; }
-        #pragma unroll
-        for (int i = 0; i < PIPE_CELLS_PER_THREAD; i++) {
-            const int c = (int)pt * PIPE_CELLS_PER_THREAD + i;
-            if (c < HALO_CELLS) { H.cellG[c] = beg[i]; H.local[c] = run; }
-            run += cnt[i];
-        }
+        const uint32_t total = H.total;
         const bool staged = total <= PIPE_CAP;
         // ring space: the tile's payload takes `total` contiguous slots; tiles still in flight whose region it would
         // overlap are waited for, oldest first (consumers release tiles in order)
@@ -512,85 +604,50 @@ __device__ __forceinline__ void pipe_producer(DevState* __restrict__ S, const Ar
         #pragma unroll
         for (int j = PIPE_STAGES - 2; j > 0; j--) { regB[j] = regB[j - 1]; regE[j] = regE[j - 1]; }
         regB[0] = base; regE[0] = staged ? base + total : base;
-        if (pt == 0) {
-            H.local[HALO_CELLS] = total;
-            H.begin = tb; H.end = te; H.total = total; H.staged = staged ? 1u : 0u; H.base = base; H.li = tli;
-            if (checkIndexRange && total > 65535u) atomicOr(&S->errorFlags, 2u);
-            if (!staged) atomicAdd(&S->fallbackTiles, 1u);
-        }
-        producer_sync();                                  // the table is complete for every producer warp
-        if (staged) {
+        if (ct == 0) { H.staged = staged ? 1u : 0u; H.base = base; }
+        ptrace(4, k, base);
+        if (staged && !(PIPE_ABLATE & 4)) {
             unsigned char* sA = pay + (size_t)base * 16;
             unsigned char* sB = pay + (size_t)PipeRing<Op>::SLOTS * 16 + (size_t)base * BBYTES;
-            // One halo row (six x-adjacent cells, contiguous in the local index space) per warp and turn: the first cell
-            // belongs to the tile on the left, the next four are contiguous in the sorted arrays, the last to the tile on
-            // the right.  Lane j first fetches the seven table entries of the warp's j-th row (one shared-memory round
-            // for all rows), the loop then gets them by shuffle: no dependent shared-memory load per row.
-            constexpr int ROWS = 36 / PIPE_PRODUCER_WARPS;
-            // bulk (TMA) copies measured equal to LDGSTS for the two-payload passes and 2-4 % faster for the one-payload ones;
-            // VFD_TUNE7=1 flips the choice (A/B runs)
-            const bool bulk = (Op::NPAY == 1 || BBYTES == 16) != (op.P.tune[7] == 1);
-            if (bulk) {
-                // 16-byte payload arrays by bulk copy: lane 3r + q takes segment q of the warp's r-th row (one instruction per
-                // contiguous segment instead of one LDGSTS per particle, and full-width shared-memory writes)
-                if (lane < 3u * ROWS && !(PIPE_ABLATE & 4)) {
-                    const uint32_t r = lane / 3u, q = lane - 3u * r;
-                    const uint32_t c0 = (pw + r * PIPE_PRODUCER_WARPS) * 6u;
-                    const uint32_t cb = q == 0u ? c0 : (q == 1u ? c0 + 1u : c0 + 5u), ce = q == 0u ? c0 + 1u : (q == 1u ? c0 + 5u : c0 + 6u);
-                    const uint32_t lb = H.local[cb], le = ce < HALO_CELLS ? H.local[ce] : total, g = H.cellG[cb];
-                    const uint32_t bytes = (le - lb) * 16u;
-                    if (bytes) {
-                        mbar_expect_tx(&ps.full[s], BBYTES == 16 ? 2u * bytes : bytes);
-                        bulk_copy(sA + (size_t)lb * 16, gA + (size_t)g * 16, bytes, &ps.full[s]);
-                        if (BBYTES == 16) bulk_copy(sB + (size_t)lb * 16, gB + (size_t)g * 16, bytes, &ps.full[s]);
-                    }
+            // One bulk (TMA) copy per segment and payload array, 108 segments over the copy threads: no LSU instruction per
+            // particle, no per-sector shared-memory write.  16-byte arrays copy the exact range; the 8-byte array copies the
+            // enclosing aligned 16-byte granules into the segment's (even, padded) slots.
+            unsigned long long* fb = &ps.full[s];
+            for (uint32_t seg = ct; seg < 108u; seg += PIPE_COPY_THREADS) {
+                const uint32_t r = seg / 3u, q = seg - 3u * r, c0 = r * 6u;
+                const uint32_t cb = q == 0u ? c0 : (q == 1u ? c0 + 1u : c0 + 5u), cl = q == 0u ? c0 : (q == 1u ? c0 + 4u : c0 + 5u);
+                const uint32_t g = H.cellG[cb], n = H.cellE[cl] - g, lb = H.local[cb];
+                if (n) {
+                    const uint32_t pre_ = g & 1u, ext = n + pre_ + ((g + n) & 1u);
+                    mbar_expect_tx(fb, n * 16u + (BBYTES == 16 ? n * 16u : 0u) + (BBYTES == 8 ? ext * 8u : 0u));
+                    bulk_copy(sA + (size_t)lb * 16, gA + (size_t)g * 16, n * 16u, fb);
+                    if (BBYTES == 16) bulk_copy(sB + (size_t)lb * 16, gB + (size_t)g * 16, n * 16u, fb);
+                    if (BBYTES == 8) bulk_copy(sB + (size_t)(lb - pre_) * 8, gB + (size_t)(g - pre_) * 8, ext * 8u, fb);
                 }
             }
-            uint32_t rl[4] = { 0u, 0u, 0u, 0u }, rg[3] = { 0u, 0u, 0u };
-            if ((!bulk || BBYTES == 4 || BBYTES == 8) && lane < (uint32_t)ROWS) {
-                const uint32_t c0 = (pw + lane * PIPE_PRODUCER_WARPS) * 6u;
-                rl[0] = H.local[c0]; rl[1] = H.local[c0 + 1]; rl[2] = H.local[c0 + 5]; rl[3] = (c0 + 6 < HALO_CELLS) ? H.local[c0 + 6] : total;
-                rg[0] = H.cellG[c0]; rg[1] = H.cellG[c0 + 1]; rg[2] = H.cellG[c0 + 5];
-            }
-            if (!bulk || BBYTES == 4 || BBYTES == 8) {
-                #pragma unroll
-                for (int j = 0; j < ROWS; j++) {
-                    const uint32_t lA = __shfl_sync(0xffffffffu, rl[0], j), lB = __shfl_sync(0xffffffffu, rl[1], j);
-                    const uint32_t lC = __shfl_sync(0xffffffffu, rl[2], j), lE = __shfl_sync(0xffffffffu, rl[3], j);
-                    const uint32_t g0 = __shfl_sync(0xffffffffu, rg[0], j), g1 = __shfl_sync(0xffffffffu, rg[1], j), g5 = __shfl_sync(0xffffffffu, rg[2], j);
-                    if (!(PIPE_ABLATE & 4)) for (uint32_t l = lA + lane; l < lE; l += 32u) {
-                        const uint32_t g = l < lB ? g0 + (l - lA) : (l < lC ? g1 + (l - lB) : g5 + (l - lC));
-                        if (!bulk) {
-                            cp_async16(sA + (size_t)l * 16, gA + (size_t)g * 16);
-                            if (BBYTES == 16) cp_async16(sB + (size_t)l * 16, gB + (size_t)g * 16);
+            if (BBYTES == 4) {
+                // a 4-byte array (one pass: the pressure acceleration's kappa) goes particle by particle, a halo row (three
+                // segments, contiguous in the local index space up to their padding slots, which receive whatever follows the
+                // segment in the sorted array) per warp and turn
+                constexpr uint32_t ROWS = (36u + PIPE_COPY_WARPS - 1u) / PIPE_COPY_WARPS;
+                #pragma unroll 2
+                for (uint32_t j = 0; j < ROWS; j++) {
+                    const uint32_t r = cw + j * PIPE_COPY_WARPS;
+                    if (r < 36u) {
+                        const uint32_t c0 = r * 6u;
+                        const uint32_t lA = H.local[c0], lB = H.local[c0 + 1], lC = H.local[c0 + 5], lE = H.local[c0 + 6];
+                        const uint32_t g0 = H.cellG[c0], g1 = H.cellG[c0 + 1], g5 = H.cellG[c0 + 5];
+                        for (uint32_t l = lA + lane; l < lE; l += 32u) {
+                            const uint32_t g = l < lB ? g0 + (l - lA) : (l < lC ? g1 + (l - lB) : g5 + (l - lC));
+                            cp_async4(sB + (size_t)l * 4, gB + (size_t)g * 4);
                         }
-                        if (BBYTES == 8) cp_async8(sB + (size_t)l * 8, gB + (size_t)g * 8);
-                        if (BBYTES == 4) cp_async4(sB + (size_t)l * 4, gB + (size_t)g * 4);
                     }
                 }
             }
         }
-        // look up the CTA's next tile and start loading its cell table
-        next_tile();
-        const uint32_t b0_ = tb, e0_ = te;
-        // What the consumers stream per particle of this tile — neighbour counts, the first PIPE_PREFETCH_GROUPS list (and
-        // coefficient) groups of every 32-particle block, the op's own per-particle arrays — is pulled into L2 a tile
-        // ahead, so the consumers' loads find it there instead of paying HBM latency with 16 warps
-        {
-            const uint32_t pfGroups = (uint32_t)op.P.tune[0];
-            const uint32_t blk0 = b0_ >> 5, blk1 = (e0_ - 1u) >> 5;
-            if (pfGroups) for (uint32_t blk = blk0 + pt; blk <= blk1; blk += PIPE_PRODUCER_THREADS) {
-                const size_t g0 = (size_t)blk * (ELL_GROUPS * 32);
-                l2_prefetch(A.list16, g0 * 8, (g0 + pfGroups * 32) * 8);
-                if constexpr ((Op::COEF & 1) != 0) l2_prefetch(op.coef_in(), g0 * 16, (g0 + pfGroups * 32) * 16);
-            }
-            if (op.P.tune[1]) {
-                if (pt == PIPE_PRODUCER_THREADS - 1) l2_prefetch(A.cnt, (size_t)b0_ * 4, (size_t)e0_ * 4);
-                op.prefetch_own(pt, b0_, e0_);
-            }
-        }
-        cp_async_arrive(&ps.full[s]);                     // 64 arrivals: each thread's copies have landed
-        if (pt == 0) mbar_arrive(&ps.full[s]);            // + 1: the header (release)
+        cp_async_arrive(&ps.full[s]);                     // one arrival per copy thread: its copies have landed
+        if (ct == 0) mbar_arrive(&ps.full[s]);            // + 1: the header (release)
+        ptrace(5, k, 0);
     }
 }
 
@@ -731,28 +788,39 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
     // this lane's words in slot 0 of the warp's stream ring
     const uint32_t ringL = smem_u32(streams) + cw * (uint32_t)R * SLOT + lane * 8u, ringC = ringL - lane * 8u + 256u + lane * 16u;
 
-    // the batch cursor: tile counter of this CTA, batch inside the tile, rotation (batch b of a tile goes to warp
-    // (rot + b) mod CW: consecutive batches of consecutive tiles visit the warps in turn), batches of the tile
-    uint32_t wK = 0, wB = 0, wRot = 0, wN = 0;
+    // Batches are handed out by a CTA-wide ticket counter (ps.ticket): ticket t is the CTA's t-th batch, counting through its
+    // tiles in order, so the warps that are free always take the oldest batches not yet started — a tile's batches run side by
+    // side and its ring space comes back as early as possible (with a fixed warp <-> batch assignment a tile waited for
+    // whichever warps its batches were bound to; the payload ring holds only about three halo boxes: profiles/r02_pipeline_trace.md).
+    // Sums do not depend on who took what: every batch's partial goes to its own slot of the tile's record.
+    // The cursor: tile counter of this CTA, its batch count, the ticket of its first batch, the ticket the cursor is looking for
+    uint32_t wK = 0, wB = 0, wN = 0, wBase = 0, wTick = 0;
     uint32_t heldK = NONE;                      // tile of the batch being gathered: released after its gather, not by the cursor
     bool wDone = false;
+    auto claim = [&]() {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&ps.ticket, 1u);
+        wTick = __shfl_sync(0xffffffffu, t, 0);
+    };
     auto enter = [&]() {
         const uint32_t s = wK % PIPE_STAGES;
-        mbar_wait(&ps.full[s], (wK / PIPE_STAGES) & 1u);
+        ptrace(10, wK, 0);
+        mbar_wait(&ps.table[s], (wK / PIPE_STAGES) & 1u);   // the tile's table (which particles, how many batches): the scout is well ahead of the payload
+        ptrace(11, wK, 0);
         const StageHeader& H = ps.hdr[s];
         const uint32_t begin = H.begin;
         if (begin == NONE) { wDone = true; wN = 0; wB = 0; return; }
         wN = (H.end - begin + 31u) >> 5;
-        wB = (cw + CW - wRot) % CW;
+        wB = wTick - wBase;
     };
     // moves the cursor to this warp's next batch, releasing the tiles it leaves behind.  Non-blocking: stops (false) in front
     // of a tile the producers have not staged yet — the caller still holds a tile the producers may be waiting for.
     auto seek = [&](bool blocking) -> bool {
         while (!wDone && wB >= wN) {
             const uint32_t kn = wK + 1u;
-            if (!blocking && !__any_sync(0xffffffffu, mbar_test(&ps.full[kn % PIPE_STAGES], (kn / PIPE_STAGES) & 1u))) return false;
+            if (!blocking && !__any_sync(0xffffffffu, mbar_test(&ps.table[kn % PIPE_STAGES], (kn / PIPE_STAGES) & 1u))) return false;
             if (wK != heldK) { __syncwarp(); if (lane == 0) mbar_arrive(&ps.empty[wK % PIPE_STAGES]); }
-            wRot = (wRot + wN) % CW;
+            wBase += wN;
             wK = kn;
             enter();
         }
@@ -771,6 +839,7 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
         if (Op::COEF & 1) cp_async16_zfill(ringC + slot * SLOT, cinBase + off, valid ? 16u : 0u);
     };
 
+    claim();
     enter();
     seek(true);
     if (wDone) return;
@@ -784,12 +853,10 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
         const StageHeader& H = ps.hdr[curK % PIPE_STAGES];
         const uint32_t p = pN, mf = mN;
         const uint32_t curLi = H.li;
-        const bool staged = H.staged != 0u;
-        const float4* __restrict__ sA = reinterpret_cast<const float4*>(pay + (size_t)H.base * 16);
-        const void* __restrict__ sB = payB + (size_t)H.base * BBYTES;
         const uint32_t m = mf & VFD_COUNT_MASK, nG = (m + 3u) >> 2;
         const uint32_t cOff = p != NONE ? ell_off(p) : 0u;
         const uint32_t nGw = __reduce_max_sync(0xffffffffu, nG);
+        ptrace(12, curK, (curB << 8) | issued);
         // the first groups of this batch: normally prefetched during the previous batch; otherwise (first batch, the next tile
         // was not staged in time, a predecessor with fewer than R groups) they are fetched now
         if (issued < (uint32_t)R) {
@@ -799,8 +866,10 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
             cp_async_commit();
             cp_async_wait<0>();
         }
+        ptrace(13, curK, curB);
         heldK = curK;
-        wB += CW;
+        claim();                                // this warp's next batch
+        wB = wTick - wBase;
         const bool ahead = seek(false);
         const bool haveNext = ahead && !wDone;
         pN = NONE; mN = 0u;
@@ -808,6 +877,13 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
         const uint32_t nOff = pN != NONE ? ell_off(pN) : 0u;
         issued = 0;
 
+        // everything above needed only the tile's table; the gathers need its payload
+        ptrace(17, curK, curB);
+        mbar_wait(&ps.full[curK % PIPE_STAGES], (curK / PIPE_STAGES) & 1u);
+        ptrace(18, curK, curB);
+        const bool staged = H.staged != 0u;
+        const float4* __restrict__ sA = reinterpret_cast<const float4*>(pay + (size_t)H.base * 16);
+        const void* __restrict__ sB = payB + (size_t)H.base * BBYTES;
         float own[Op::NOWN];
         #pragma unroll
         for (int i = 0; i < Op::NOWN; i++) own[i] = 0.0f;
@@ -845,6 +921,7 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
             }
             if (Op::COEF & 2) coutBase[cOff + g * 32u] = make_float4(c[0], c[1], c[2], c[3]);
         };
+        ptrace(14, curK, (curB << 8) | (ahead ? 1u : 0u));
         if (staged) {
             // PIPE_ABLATE (tuning builds, wrong results): 32: no gathers, 128: no list/coefficient stream
             auto fetch = [&](uint32_t L, float4& a, float4& b) {
@@ -892,6 +969,7 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
             issued = 0;
         }
         // the gathers of this batch are complete: release its tile if the cursor has left it
+        ptrace(15, curK, (curB << 8) | nGw);
         __syncwarp();
         if (wK != curK && lane == 0) mbar_arrive(&ps.empty[curK % PIPE_STAGES]);
         heldK = NONE;
@@ -928,6 +1006,7 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
                 if (lane == 0) { R_.bsum[0][PIPE_MAX_BATCH - 1] = 0.0; R_.bsum[1][PIPE_MAX_BATCH - 1] = 0.0; R_.count = 0u; }
             }
         }
+        ptrace(16, curK, curB);
         if (!ahead) {
             // the next tile was not staged when this batch began: wait for it now (this warp holds no tile any more)
             seek(true);
@@ -946,8 +1025,9 @@ template<class Op>
 __device__ __forceinline__ bool pipe_pass(DevState* __restrict__ S, const Arrays& A, PipeShared& ps, unsigned char* pay, Op& op,
                                           uint32_t tile0, uint32_t tile1, bool checkIndexRange = false) {
     if (threadIdx.x == 0) {
+        ps.ticket = 0u;
         #pragma unroll
-        for (int s = 0; s < PIPE_STAGES; s++) { mbar_init(&ps.full[s], PIPE_PRODUCER_THREADS + 1); mbar_init(&ps.empty[s], Op::Cfg::CW); }
+        for (int s = 0; s < PIPE_STAGES; s++) { mbar_init(&ps.full[s], PIPE_FULL_ARRIVALS); mbar_init(&ps.empty[s], Op::Cfg::CW); mbar_init(&ps.table[s], 1u); }
     }
     if constexpr (Op::CUSTOM) {
         if constexpr (Op::TILE_QUEUE) {
@@ -962,7 +1042,8 @@ __device__ __forceinline__ bool pipe_pass(DevState* __restrict__ S, const Arrays
         R.count = 0u; R.bsum[0][PIPE_MAX_BATCH - 1] = 0.0; R.bsum[1][PIPE_MAX_BATCH - 1] = 0.0;
     }
     __syncthreads();
-    if (threadIdx.x >= Op::Cfg::CW * 32) pipe_producer(S, A, ps, pay, op, tile0, tile1, checkIndexRange);
+    if (threadIdx.x >= (Op::Cfg::CW + 1) * 32) pipe_copier(ps, pay, op);
+    else if (threadIdx.x >= Op::Cfg::CW * 32) pipe_scout<Op>(S, A, ps, checkIndexRange);
     else if constexpr (Op::CUSTOM) pipe_consumer(A, ps, pay, op);
     else pipe_consumer_pairs(A, ps, pay, pay - PipeLayout<Op>::OFF_PAY + PipeLayout<Op>::OFF_STREAM, op);
     __syncthreads();

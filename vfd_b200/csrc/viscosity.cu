@@ -22,6 +22,7 @@
 #include "control.cuh"
 #include <algorithm>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace vfd {
 
@@ -412,6 +413,38 @@ void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& 
     if (init) { pipe_attr(k_visc_matvec_pipe<true>, sp); k_visc_matvec_pipe<true><<<L.numSMs, ViscMatvecOp<true>::Cfg::THREADS, sp, L.stream>>>(P, A, S); }
     else      { pipe_attr(k_visc_matvec_pipe<false>, sp); k_visc_matvec_pipe<false><<<L.numSMs, ViscMatvecOp<false>::Cfg::THREADS, sp, L.stream>>>(P, A, S); }
 }
+#ifdef PIPE_TRACE
+// diagnostic builds: one traced launch of the initial mat-vec; the event log of CTA 0 goes to `path` (u64 pairs)
+void trace_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const char* path) {
+    unsigned int zero = 0, one = 1;
+    cudaMemcpyToSymbol(g_pipeTraceN, &zero, 4); cudaMemcpyToSymbol(g_pipeTraceOn, &one, 4);
+    // the PCG's own product (q = A p) unless VFD_TRACE_INIT is set; it only runs while the solver is active
+    const bool init = getenv("VFD_TRACE_INIT") != nullptr;
+    uint32_t active = 1u, saved = 0u;
+    cudaMemcpy(&saved, &S->viscActive, 4, cudaMemcpyDeviceToHost);
+    if (!init) cudaMemcpy(&S->viscActive, &active, 4, cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; i++) launch_viscosity_matvec(L, P, A, S, init);      // warm: the traced launch is a steady-state one
+    cudaStreamSynchronize(L.stream);
+    cudaMemcpyToSymbol(g_pipeTraceN, &zero, 4);
+    cudaEventRecord(e0, L.stream);
+    launch_viscosity_matvec(L, P, A, S, init);
+    cudaEventRecord(e1, L.stream);
+    cudaStreamSynchronize(L.stream);
+    float ms = 0.0f; cudaEventElapsedTime(&ms, e0, e1);
+    printf("traced launch (%s): %.4f ms\n", init ? "r = b - A g" : "q = A p", ms);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaMemcpy(&S->viscActive, &saved, 4, cudaMemcpyHostToDevice);
+    cudaMemcpyToSymbol(g_pipeTraceOn, &zero, 4);
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, g_pipeTraceN, 4);
+    if (n > PIPE_TRACE_CAP) n = PIPE_TRACE_CAP;
+    unsigned long long* h = (unsigned long long*)malloc((size_t)n * 16);
+    cudaMemcpyFromSymbol(h, g_pipeTrace, (size_t)n * 16);
+    if (FILE* f = fopen(path, "wb")) { fwrite(h, 16, n, f); fclose(f); }
+    free(h);
+}
+#endif
 void launch_viscosity_update(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     const uint32_t tiles = std::max(1u, (P.n + VFD_TPB - 1) / VFD_TPB);
     const uint32_t g2 = std::max(1u, std::min<uint32_t>(tiles, (uint32_t)L.numSMs * 8u));
