@@ -23,4 +23,4 @@ else:
         info = sim.GetInfo()
         np.savez(state, state=sim.particles(), dt=info.TimeStepSize, st=np.array([info.SurfaceTensionSampleCount, info.MonteCarloFactor]))
 sim.synchronize()
-print("[%s] matvec0 %.4f ms/launch" % (os.environ.get("VFD_LIB", "default"), sim.time_matvec(40)))
+print("[%s] matvec %.4f ms/launch" % (os.environ.get("VFD_LIB", "default"), sim.time_matvec(40)))

@@ -937,16 +937,24 @@ int Solver::time_matvec(uint32_t reps, float* ms) {
     LaunchCfg L{ stream, numSMs, &launches, &prof };
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-    launch_viscosity_matvec(L, params, arrays, dState, true);
+    // the PCG's own product q = A p (VFD_TIME_MATVEC_INIT: the start-up product r = b - A g); it only runs while the solver is active
+    const bool init = getenv("VFD_TIME_MATVEC_INIT") != nullptr;
+    uint32_t active = 1u, saved = 0u;
+    CK(cudaMemcpyAsync(&saved, &dState->viscActive, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (!init) CK(cudaMemcpyAsync(&dState->viscActive, &active, 4, cudaMemcpyHostToDevice, stream));
+    launch_viscosity_matvec(L, params, arrays, dState, init);
     CK(cudaEventRecord(a, stream));
-    for (uint32_t i = 0; i < reps; i++) launch_viscosity_matvec(L, params, arrays, dState, true);
+    for (uint32_t i = 0; i < reps; i++) launch_viscosity_matvec(L, params, arrays, dState, init);
     CK(cudaEventRecord(b, stream));
+    CK(cudaMemcpyAsync(&dState->viscActive, &saved, 4, cudaMemcpyHostToDevice, stream));
     CK(cudaEventSynchronize(b));
     CK(cudaEventElapsedTime(ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
 #ifdef PIPE_TRACE
     { const char* path = getenv("VFD_TRACE_FILE"); if (path) trace_viscosity_matvec(L, params, arrays, dState, path); }
 #endif
+    CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
     return VFD_OK;
 }

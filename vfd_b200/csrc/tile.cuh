@@ -305,7 +305,7 @@ using PipeCfgWide = PipeCfg<PIPE_CONSUMER_WARPS, PIPE_LOOKAHEAD, PIPE_GATHER_WID
 #endif
 using PipeCfgMany = PipeCfg<PIPE_MANY_CW, PIPE_MANY_D, PIPE_MANY_GW>;
 #ifndef PIPE_MV_CW
-#define PIPE_MV_CW 28
+#define PIPE_MV_CW 24
 #define PIPE_MV_D 2
 #define PIPE_MV_GW 2
 #endif
@@ -474,6 +474,9 @@ __device__ __forceinline__ uint32_t hdr_local_to_global(const StageHeader& H, ui
 //   * the COPY warps take the tables in order, claim ring space (the same bookkeeping in every copy thread, no barrier
 //     between them), and issue the copies: their loop is nothing but address arithmetic and LDGSTS / bulk copies.
 // Op supplies the global source arrays:  const float4* srcA();  const void* srcB()  (BBYTES 16: float4 array, 8 / 4: float2 / float array)
+#ifndef PIPE_SCOUT_LAG
+#define PIPE_SCOUT_LAG 2u         // the scout draws tile k once tile k - PIPE_SCOUT_LAG is staged
+#endif
 #define PIPE_COPY_WARPS (PIPE_PRODUCER_WARPS - 1)
 #define PIPE_COPY_THREADS (PIPE_COPY_WARPS * 32)
 #define PIPE_FULL_ARRIVALS (PIPE_COPY_THREADS + 1u)   // every copy thread's copies have landed (cp.async.mbarrier.arrive.noinc) + the header (release)
@@ -504,7 +507,7 @@ __device__ __forceinline__ void pipe_scout(DevState* __restrict__ S, const Array
         // while others run dry at the end of the pass (the draw, the tile id and the cell table are three dependent trips to
         // L2, ~2 us — a fraction of what the consumers need for a tile), early enough that the consumers find the table of
         // their next batch's tile when they look ahead.
-        if (k >= 2u) mbar_wait(&ps.full[(k - 2u) % PIPE_STAGES], ((k - 2u) / PIPE_STAGES) & 1u);
+        if (k >= PIPE_SCOUT_LAG) mbar_wait(&ps.full[(k - PIPE_SCOUT_LAG) % PIPE_STAGES], ((k - PIPE_SCOUT_LAG) / PIPE_STAGES) & 1u);
         const uint32_t li = draw();
         const uint32_t tile = li < nList ? __ldg(tileList + 1u + li) : NONE;
         const bool end = tile == NONE;
@@ -836,6 +839,8 @@ __device__ __forceinline__ void pipe_consumer_pairs(const Arrays& A, PipeShared&
     auto issue = [&](uint32_t slot, uint32_t off, bool valid, bool cold = false) {
         if ((PIPE_ABLATE & 128) && !cold) return;
         cp_async8_zfill(ringL + slot * SLOT, listBase + off, valid ? 8u : 0u);
+        // (the coefficient word as two 8-byte copies would halve its shared-memory write wavefronts — a 16-byte LDGSTS writes sector
+        // by sector, 10.6 wavefronts per warp instruction against 2 x 2 — but the L1-allocating 8-byte form measured 10 % slower)
         if (Op::COEF & 1) cp_async16_zfill(ringC + slot * SLOT, cinBase + off, valid ? 16u : 0u);
     };
 
