@@ -61,14 +61,25 @@ CONFIGS = {
 }
 
 
-def scene(side):
-    """Dam break: side^3 lattice block in the corner of an inverted box twice as long."""
-    pos = block_positions(side, side, side, (2 * D, 2 * D, 2 * D))
+def scene(side, world=1):
+    """Dam break for `world` GPUs: a lattice block of world*side x side x side particles standing against one long wall of an
+    inverted box of the same length and twice the block's depth, so that it collapses along z (config 5:
+    "slabs side by side along x").  Every x-slice of the scene is the 1-GPU scene (world = 1): the flow runs across the slabs'
+    normal, per-GPU physics, neighbour counts and PCG iteration counts do not depend on the number of GPUs."""
+    nx = side * world
+    pos = block_positions(nx, side, side, (2 * D, 2 * D, 2 * D))
     L = side * D
-    box = ((0.0, 0.0, 0.0), (2 * L + 4 * D, 1.4 * L + 4 * D, L + 4 * D))
+    box = ((0.0, 0.0, 0.0), (nx * D + 4 * D, 1.4 * L + 4 * D, 2 * L + 4 * D))
     ext = [b - a + 2 * (8 * H - R) for a, b in zip(*box)]
-    res = tuple(max(8, int(np.ceil(e / (4 * H)))) for e in ext)
+    res = tuple(min(256, max(8, int(np.ceil(e / (4 * H))))) for e in ext)
     return pos, box, res
+
+
+def workload(side, world, settle):
+    """The workload's name: the same string in both arms' `config.workload` (what differs between the arms goes to `config.notes`)."""
+    n = world * side ** 3
+    shape = "%d x %d^3" % (world, side) if world > 1 else "%d^3" % side
+    return (CONFIG_NAME % (side, side ** 3)).replace("%d^3 = %d" % (side, side ** 3), "%s = %d" % (shape, n)) + "; %d settle steps" % settle
 
 
 CONFIG_DESC = {}          # solver switches of the selected --config (set by main)
@@ -160,7 +171,7 @@ def reference_settled_state(args, refsim, desc):
     variant: SURVEY.md F6) when the box has a GPU and the build travelled, which takes seconds; else on the host cores on a
     smaller scene (`--ref-side`).  Returns (state, dt, (sample count, Monte-Carlo factor), positions, box, map resolution, how)."""
     def settle(kind, side, steps):
-        pos, box, res = scene(side)
+        pos, box, res = scene(side, max(1, args.gpus))
         sim = refsim.RefSim(desc, kind=kind, threads=os.cpu_count() or 1)
         sim.set_particles(pos)
         sim.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
@@ -194,7 +205,7 @@ def run_reference(args, rank, world):
     from oracle import refsim
     threads = os.cpu_count() or 1
     desc = description(refsim.Desc)
-    steps = min(args.steps, args.ref_steps)            # each step is ~1 s of 16 cores at 1M particles: a bounded sample
+    steps = min(args.steps, max(3, args.ref_steps // max(1, args.gpus)))     # each step is ~1 s of 16 cores per million particles: a bounded sample
     with refsim.quiet_stdout():
         state, dt0, st0, pos, box, res, how, side = reference_settled_state(args, refsim, desc)
         sim = refsim.RefSim(desc, threads=threads)
@@ -213,14 +224,16 @@ def run_reference(args, rank, world):
         dt = time.perf_counter() - t0
     n = len(pos)
     v = n * steps / dt
+    full = side == args.side
+    wl = workload(args.side, max(1, args.gpus), args.settle) if full else CONFIG_NAME % (side, n) + " (the box has no GPU for the reference's CUDA build to prepare the full scene)"
     sample = "%s; %s; %d warm-up + %d timed steps (a bounded sample of the arm's %d); mean PCG it %.1f" % (
-        CONFIG_NAME % (side, n), how, min(args.warmup, 3), steps, args.steps, float(np.mean(its)))
+        wl, how, min(args.warmup, 3), steps, args.steps, float(np.mean(its)))
     print(json.dumps({
         "impl": "reference", "metric": "DFSPH particle-steps/s", "value": v, "unit": "particle-steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": CONFIG_NAME % (side, n) + "; reference solver sources on %d host threads" % threads, "particles": n,
-                   "pcg_iterations_mean": float(np.mean(its))},
+        "config": {"workload": wl, "notes": "the reference's solver sources on %d host threads; %s" % (threads, how), "baseline_config": args.config,
+                   "particles": n, "pcg_iterations_mean": float(np.mean(its))},
         "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -448,9 +461,9 @@ def main():
     out = {
         "metric": "DFSPH particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": CONFIG_NAME % (args.side, n) + "; %d settle steps; %s" % (args.settle,
-                               "working set > L2 (neighbour list and pair coefficients alone %.0f MB), no flush" % (n * 72 * 6 / 1e6) if n * 72 * 6 > 126e6 else
-                               "working set %.0f MB of list and coefficients: L2-resident, flushed between steps by nothing (stated: NOT flushed)" % (n * 72 * 6 / 1e6)),
+        "config": {"workload": workload(args.side, 1, args.settle),
+                   "notes": ("working set > L2 (neighbour list and pair coefficients alone %.0f MB), no flush" % (n * 72 * 6 / 1e6) if n * 72 * 6 > 126e6 else
+                             "working set %.0f MB of list and coefficients: L2-resident, flushed between steps by nothing (stated: NOT flushed)" % (n * 72 * 6 / 1e6)),
                    "baseline_config": args.config,
                    "particles": n, "mean_neighbours": mbar, "pcg_iterations_last_step": int(dbg.ViscositySolverIterationCount),
                    "grid_tiles": tstats["tiles"], "tile_passes_on_slow_path": tstats["fallback_tile_passes"],

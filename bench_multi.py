@@ -17,13 +17,15 @@ R, D, H = 0.025, 0.05, 0.1
 
 
 def dist_scene(side, world, kind="dam"):
-    """The global block of world*side x side x side particles: "dam" — at the left end of a box twice its length (bench.py's
-    1-GPU dam break stretched along x: at world = 1 the very same scene); "tank" — filling a closed tank along x (the slabs
-    never move)."""
-    from vfd_b200 import api
+    """The global block of world*side x side x side particles: "dam" — bench.scene(side, world): the 1-GPU dam break repeated
+    along x (it collapses along z: at world = 1 the very same scene, at any world size the same per-GPU physics); "tank" —
+    filling a closed tank along x."""
     nx = side * world
-    lx = 2 * nx * D if kind == "dam" else nx * D
-    box = ((0.0, 0.0, 0.0), (lx + 4 * D, 1.4 * side * D + 4 * D, side * D + 4 * D))
+    if kind == "dam":
+        L = side * D
+        box = ((0.0, 0.0, 0.0), (nx * D + 4 * D, 1.4 * L + 4 * D, 2 * L + 4 * D))       # = bench.scene(side, world)'s box
+    else:
+        box = ((0.0, 0.0, 0.0), (nx * D + 4 * D, 1.4 * side * D + 4 * D, side * D + 4 * D))
     ext = [b - a + 2 * (8 * H - R) for a, b in zip(*box)]
     res = tuple(min(256, max(8, int(np.ceil(e / (4 * H))))) for e in ext)
     return nx, box, res
@@ -135,10 +137,11 @@ def main(args, rank, local, world):
         out = {
             "metric": "DFSPH particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s, %d x %d^3 = %d particles (%d^3 per GPU), DFSPH (2+2 Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; "
-                                   "%d settle steps; slabs of tile columns along x re-balanced while stepping, halos and all-reduces through peer memory (%s); working set > L2, no flush" % (
-                                       "dam break (the 1-GPU scene stretched along x)" if args.scene == "dam" else "closed tank", world, args.side, n_global, args.side, args.settle,
-                                       "CUDA IPC over NVLink" if sim.slab()["peer_memory"] else "off: NCCL only"),
+            "config": {"workload": bench.workload(args.side, world, args.settle) if args.scene == "dam" else
+                                   "closed tank, %d x %d^3 = %d particles, DFSPH (2+2 Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; %d settle steps" % (world, args.side, n_global, args.settle),
+                       "notes": "%d^3 particles per GPU, the 1-GPU scene repeated along x (it collapses along z); slabs of tile columns along x re-balanced while stepping, halos and "
+                                "all-reduces through peer memory (%s); working set > L2, no flush" % (args.side, "CUDA IPC over NVLink" if sim.slab()["peer_memory"] else "off: NCCL only"),
+                       "baseline_config": args.config,
                        "slab_rank0_now": sim.slab(),
                        "particles": n_global, "slab_bounds_tile_columns": [int(b) for b in bounds], "owned_per_rank": [int(o.item()) for o in owns],
                        "pcg_iterations_last_step": int(dbg.ViscositySolverIterationCount),

@@ -58,6 +58,11 @@ struct Params {
     // several ranks: every rank's control block (control.cuh: PeerCtl) mapped into this process over NVLink (CUDA IPC), own one
     // included; null when the ranks talk through NCCL only
     void* peerCtl[8];
+    // ... and where the PCG direction of this rank's first / last owned tile column lives in the left / right neighbour's ghost
+    // range ([neighbour][(x, y, z, p.x) | (p.y, p.z)]), with the particle ranges of those columns: ownB, edgeLEnd, edgeRBegin, ownE.
+    // The kernel that rewrites the direction stores these particles' words there as well (viscosity.cu: k_visc_step).
+    unsigned char* haloP[2][2];
+    uint32_t haloRange[4];
 };
 
 // Device-resident mutable scalars: the time step and all solver control state.  Kernels read dt

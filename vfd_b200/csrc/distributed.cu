@@ -262,6 +262,27 @@ void Solver::dist_params(Params& P) const {
     P.tile0 = (D.rank > 0 ? 1u : 0u) * T;
     P.tile1 = P.tile0 + (D.colHi - D.colLo) * T;
     for (int r = 0; r < 8; r++) P.peerCtl[r] = (D.p2p && r < D.nranks) ? (void*)D.peerSlab[r] : nullptr;
+    dist_halo_targets(P);
+}
+
+void Solver::dist_count_fused_halo(uint64_t bytesPerItem) {
+    Dist& D = *dist;
+    const bool hasL = D.rank > 0, hasR = D.rank + 1 < D.nranks;
+    D.halos += 1;
+    D.bytesHalo += (uint64_t)((hasL ? D.edgeLEnd - D.ownB : 0u) + (hasR ? D.ownE - D.edgeRBegin : 0u)) * bytesPerItem;
+}
+
+// where this step's edge columns go in the neighbours' copies of the PCG direction (the ranges move with every sort)
+void Solver::dist_halo_targets(Params& P) const {
+    const Dist& D = *dist;
+    const bool hasL = D.rank > 0, hasR = D.rank + 1 < D.nranks;
+    for (int k = 0; k < 2; k++) {
+        const int region = k == 0 ? SR_CGXP : SR_CGPYZ;
+        const size_t eb = kRegionBytes[region];
+        P.haloP[0][k] = (D.p2p && hasL) ? D.peerSlab[D.rank - 1] + slab_offset(region, D.slabNp[D.rank - 1]) + (size_t)D.leftOwnE * eb : nullptr;
+        P.haloP[1][k] = (D.p2p && hasR) ? D.peerSlab[D.rank + 1] + slab_offset(region, D.slabNp[D.rank + 1]) : nullptr;
+    }
+    P.haloRange[0] = D.ownB; P.haloRange[1] = D.edgeLEnd; P.haloRange[2] = D.edgeRBegin; P.haloRange[3] = D.ownE;
 }
 
 // The slab of this rank (control block + the arrays halo exchanges touch) and its mapping into every other rank: called by
@@ -438,6 +459,7 @@ int Solver::dist_read_ranges() {
     CK(cudaStreamSynchronize(stream));
     h[4] = got[0]; h[5] = got[4];
     D.leftOwnE = got[1];
+    dist_halo_targets(params);
     D.stepsDone++;
     if (D.rebalanceEvery > 0 && D.stepsDone % (uint64_t)D.rebalanceEvery == 0) {
         // boundary between ranks a (left) and b (right): a's last column goes to b when a is heavier by more than that column

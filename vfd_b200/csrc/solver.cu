@@ -627,8 +627,12 @@ int Solver::step() {
         RC(reduce(SITE_VISC_INIT));
         RC(halo42(A.cgXP, A.cgPyz));
         const bool fusedStep = viscosity_step_fits(L, P);
+        // several ranks over peer memory: the fused vector kernel writes the new direction of the edge columns straight into
+        // the neighbours' ghost ranges, and the next mat-vec waits for their "landed" flags: no exchange kernel per iteration
+        const bool fusedHalo = fusedStep && dist && P.nRanks > 1u && P.peerCtl[0] != nullptr;
+        bool haloPending = false;
         auto iteration = [&]() -> int {
-            launch_viscosity_matvec(L, P, A, dState, false);
+            launch_viscosity_matvec(L, P, A, dState, false, haloPending);
             RC(reduce(SITE_VISC_PQ));
             if (fusedStep) {
                 CK((cudaError_t)launch_viscosity_step(L, P, A, dState));
@@ -637,7 +641,8 @@ int Solver::step() {
                 RC(reduce(SITE_VISC_UPDATE));
                 launch_viscosity_direction(L, P, A, dState);
             }
-            RC(halo42(A.cgXP, A.cgPyz));
+            if (fusedHalo) { haloPending = true; dist_count_fused_halo(24); }
+            else RC(halo42(A.cgXP, A.cgPyz));
             return VFD_OK;
         };
         if (P.minViscIt == 0 && P.maxViscIt > 0) RC(run_polled_loop(P.maxViscIt, 0, 4, &dState->viscActive, iteration, 1u));

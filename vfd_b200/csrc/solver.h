@@ -124,7 +124,7 @@ void launch_st_classify(const LaunchCfg& L, const Params& P, const Arrays& A, De
 void launch_st_smooth(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
 void launch_st_apply(const LaunchCfg& L, const Params& P, const Arrays& A);
 void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* lutG);
-void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init);
+void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init, bool waitHalo = false);
 void launch_viscosity_update(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
 void launch_viscosity_direction(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S);
 bool viscosity_step_fits(const LaunchCfg& L, const Params& P);

@@ -134,6 +134,8 @@ private:
     int dist_alloc_slab(size_t np);
     void dist_free_slab();
     int dist_upload_grid();
+    void dist_halo_targets(Params& P) const;
+    void dist_count_fused_halo(uint64_t bytesPerItem);
     int halo4(float4* a) { return dist ? dist_halo(a, 4) : VFD_OK; }
     int halo42(float4* a, float2* b) { return dist ? dist_halo(a, 4, b, 2) : VFD_OK; }
     int halo1(float* a) { return dist ? dist_halo(a, 1) : VFD_OK; }

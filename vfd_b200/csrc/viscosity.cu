@@ -244,12 +244,26 @@ struct ViscMatvecOp {
     }
 };
 
+// waitHalo: the neighbours' edge columns of the direction are written into this rank's ghost ranges by THEIR k_visc_step (no
+// exchange kernel in between): wait for both "landed" flags first; the block that finishes last advances the exchange counter.
 template<bool INIT>
-__global__ void __launch_bounds__(ViscMatvecOp<INIT>::Cfg::THREADS, 1) k_visc_matvec_pipe(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S) {
+__global__ void __launch_bounds__(ViscMatvecOp<INIT>::Cfg::THREADS, 1) k_visc_matvec_pipe(const __grid_constant__ Params P, const __grid_constant__ Arrays A, DevState* S, uint32_t waitHalo) {
     if (!INIT && S->viscActive != 1u) return;
     PipeShared& ps = pipe_header(smemRaw);
+    uint32_t haloSeq = 0;
+    if (!INIT && waitHalo) {
+        if (threadIdx.x == 0) {
+            PeerCtl* me = reinterpret_cast<PeerCtl*>(P.peerCtl[P.rank]);
+            haloSeq = *(volatile uint32_t*)&me->haloSeq + 1u;
+            if (P.rank > 0u) while (*(volatile uint32_t*)&me->haloData[0] != haloSeq) { }
+            if (P.rank + 1u < P.nRanks) while (*(volatile uint32_t*)&me->haloData[1] != haloSeq) { }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     ViscMatvecOp<INIT> op{ P, A, S->dt, { 0.0f, 0.0f } };
     if (pipe_pass(S, A, ps, pipe_pay<ViscMatvecOp<INIT>>(smemRaw), op, P.tile0, P.tile1)) {
+        if (!INIT && waitHalo && threadIdx.x == 0) *(volatile uint32_t*)&reinterpret_cast<PeerCtl*>(P.peerCtl[P.rank])->haloSeq = haloSeq;
         double tot[2] = { 0.0, 0.0 };
         if (INIT) {
             fold_slots<2>(tot, A.slotSums, __ldg(A.tileList), A.slotStride, ps.red);
@@ -373,6 +387,29 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_visc_step(const __grid_cons
             float2 pyz = sPyz[i];
             xp.w = xp.w * beta + z[k][0]; pyz.x = pyz.x * beta + z[k][1]; pyz.y = pyz.y * beta + z[k][2];
             A.cgXP[p] = xp; A.cgPyz[p] = pyz;
+            // several ranks over peer memory: the edge columns' direction goes straight into the neighbours' ghost ranges.  They
+            // are done reading the previous direction: this rank's mat-vec ended with an all-reduce every rank's mat-vec fed
+            // after its last tile.
+            if (P.haloP[0][0] && p >= P.haloRange[0] && p < P.haloRange[1]) {
+                const uint32_t j = p - P.haloRange[0];
+                reinterpret_cast<float4*>(P.haloP[0][0])[j] = xp; reinterpret_cast<float2*>(P.haloP[0][1])[j] = pyz;
+            }
+            if (P.haloP[1][0] && p >= P.haloRange[2] && p < P.haloRange[3]) {
+                const uint32_t j = p - P.haloRange[2];
+                reinterpret_cast<float4*>(P.haloP[1][0])[j] = xp; reinterpret_cast<float2*>(P.haloP[1][1])[j] = pyz;
+            }
+        }
+    }
+    if (P.nRanks > 1u && P.peerCtl[0]) {
+        // "the direction has landed": told to both neighbours by the block that finishes last; their next mat-vec waits for it
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&S->ticket[7], 1u) == gridDim.x - 1u) {
+            S->ticket[7] = 0u;
+            __threadfence_system();
+            const uint32_t seq = *(volatile uint32_t*)&reinterpret_cast<PeerCtl*>(P.peerCtl[P.rank])->haloSeq + 1u;
+            if (P.rank > 0u) *(volatile uint32_t*)&reinterpret_cast<PeerCtl*>(P.peerCtl[P.rank - 1u])->haloData[1] = seq;
+            if (P.rank + 1u < P.nRanks) *(volatile uint32_t*)&reinterpret_cast<PeerCtl*>(P.peerCtl[P.rank + 1u])->haloData[0] = seq;
         }
     }
 }
@@ -407,11 +444,11 @@ void launch_viscosity_setup(const LaunchCfg& L, const Params& P, const Arrays& A
     k_visc_setup<<<L.numSMs, ViscSetupOp::Cfg::THREADS, sp, L.stream>>>(P, A, S, lutG);
 }
 
-void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init) {
+void launch_viscosity_matvec(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, bool init, bool waitHalo) {
     const size_t sp = pipe_smem_bytes<ViscMatvecOp<false>>();
     LaunchScope ls(L, init ? KID_VISC_MATVEC0 : KID_VISC_MATVEC);
-    if (init) { pipe_attr(k_visc_matvec_pipe<true>, sp); k_visc_matvec_pipe<true><<<L.numSMs, ViscMatvecOp<true>::Cfg::THREADS, sp, L.stream>>>(P, A, S); }
-    else      { pipe_attr(k_visc_matvec_pipe<false>, sp); k_visc_matvec_pipe<false><<<L.numSMs, ViscMatvecOp<false>::Cfg::THREADS, sp, L.stream>>>(P, A, S); }
+    if (init) { pipe_attr(k_visc_matvec_pipe<true>, sp); k_visc_matvec_pipe<true><<<L.numSMs, ViscMatvecOp<true>::Cfg::THREADS, sp, L.stream>>>(P, A, S, 0u); }
+    else      { pipe_attr(k_visc_matvec_pipe<false>, sp); k_visc_matvec_pipe<false><<<L.numSMs, ViscMatvecOp<false>::Cfg::THREADS, sp, L.stream>>>(P, A, S, waitHalo ? 1u : 0u); }
 }
 #ifdef PIPE_TRACE
 // diagnostic builds: one traced launch of the initial mat-vec; the event log of CTA 0 goes to `path` (u64 pairs)
