@@ -252,6 +252,59 @@ def test_frames_come_back_in_original_particle_order(lib_built):
     sim.close()
 
 
+def test_default_frame_length_bake_follows_the_reference_cadence(lib_built, monkeypatch):
+    """Simulate() with the reference's default FrameLength (0.0016 s): a step's state becomes a frame when the accumulated
+    time steps reach the frame length (DFSPHImplementation.cu:148-167, FrameTime accumulated in :427).  Here the device takes
+    that decision and the host never reads the time step back; the frames must be the ones the reference bakes — same
+    steps, same time steps, same particles — and the same as with the decision taken on the host after every step."""
+    from oracle import refsim
+    from vfd_b200 import api
+    if not refsim.available("cpu"):
+        pytest.skip("oracle/_ref/libvfd_ref_cpu.so not built")
+    frames, flen = 8, 0.0016
+    pos, box, res = scene(16)
+    cfg = dict(FrameCount=frames, FrameLength=flen, **CONFIGS["dfsph"])
+    with refsim.quiet_stdout():
+        ref = refsim.RefSim(refsim.Desc(**{k: v for k, v in cfg.items() if k not in ("FrameCount", "FrameLength")}))
+        ref.set_particles(pos)
+        ref.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
+        ref.commit_bodies()
+        m = ref.volume_map(0)
+        # the reference's rule, driven step by step: FrameTime += dt (float), frame when FrameTime >= FrameLength
+        want, t_frame, steps = [], np.float32(0.0), 0
+        while len(want) < frames and steps < 200:
+            ref.step(1)
+            steps += 1
+            dt = np.float32(ref.debug()["dt"])
+            t_frame = np.float32(t_frame + dt)
+            if t_frame >= np.float32(flen):
+                want.append((steps, float(dt), ref.particles()["Position"].copy()))
+                t_frame = np.float32(0.0)
+    assert len(want) == frames
+    vm = api.VolumeMap(m["domain_min"], m["domain_max"], m["resolution"], m["cell_size"], m["cell_size_inv"], m["field_count"],
+                       m["node_count"], m["cell_count"], m["cell_map_count"], m["nodes"], m["cells"], m["cell_map"])
+
+    def bake():
+        sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(**cfg))
+        sim.set_option(api.VFD_OPT_SEARCH_FMA, 0)
+        sim.SetFluidObjects([api.FluidObject(pos)])
+        sim.SetRigidBodies([vm])
+        sim.Simulate()
+        out = [sim.GetFrame(i) for i in range(sim.GetFrameCount())]
+        n_steps = sim.GetDebugInfo().IterationCount
+        sim.close()
+        return out, n_steps
+    got, n_steps = bake()
+    monkeypatch.setenv("VFD_SYNC_FRAMES", "1")
+    got_sync, n_sync = bake()
+    assert len(got) == frames and len(got_sync) == frames
+    assert n_steps == want[-1][0] == n_sync, (n_steps, n_sync, want[-1][0])          # the bake stops with the step that made the last frame
+    for (f, vmax, dt), (fs, vs, dts), (_, rdt, rpos) in zip(got, got_sync, want):
+        assert f.tobytes() == fs.tobytes() and vmax == vs and dt == dts
+        assert abs(dt - rdt) <= 1e-6 * rdt
+        assert np.abs(np.asarray(f["Position"], np.float64) - rpos).max() <= 2e-5 * np.abs(rpos).max()
+
+
 def test_empty_and_tiny_scenes(lib_built):
     from vfd_b200 import api
     sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(FrameCount=0, **CONFIGS["full"]))

@@ -295,7 +295,7 @@ int Solver::dist_alloc_slab(size_t np) {
     const bool want = !(off && atoi(off) == 0) && D.nranks <= 8;
     D.slabBytes = slab_bytes(np);
     CK(cudaMalloc(&D.slab, D.slabBytes));
-    CK(cudaMemset(D.slab, 0, 4096));
+    CK(cudaMemset(D.slab, 0, D.slabBytes));
     unsigned char* b = D.slab;
     A.posRho = (float4*)(b + slab_offset(SR_POSRHO, np)); A.vel = (float4*)(b + slab_offset(SR_VEL_A, np)); A.vel2 = (float4*)(b + slab_offset(SR_VEL_B, np));
     A.pacc = (float4*)(b + slab_offset(SR_PACC, np)); A.nrm = (float4*)(b + slab_offset(SR_NRM, np));

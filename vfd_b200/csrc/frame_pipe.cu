@@ -88,8 +88,8 @@ cudaError_t FramePipe::configure(int dev, uint32_t count) {
         busy[s] = false;
     }
     next = 0; acquired = -1;
-    if (!dMeta && (e = cudaMalloc((void**)&dMeta, SLOTS * 2 * sizeof(float))) != cudaSuccess) return e;
-    if (!hMeta && (e = cudaMallocHost((void**)&hMeta, SLOTS * 2 * sizeof(float))) != cudaSuccess) return e;
+    if (!dMeta && (e = cudaMalloc((void**)&dMeta, SLOTS * 4 * sizeof(float))) != cudaSuccess) return e;
+    if (!hMeta && (e = cudaMallocHost((void**)&hMeta, SLOTS * 4 * sizeof(float))) != cudaSuccess) return e;
     // buffers are allocated lazily by acquire(): a solver that never bakes a frame pays nothing
     worker = std::thread(&FramePipe::worker_main, this);
     return cudaSuccess;
@@ -107,9 +107,9 @@ VfdParticleSimple* FramePipe::acquire() {
     return dBuf[s];
 }
 
-float* FramePipe::meta_slot() { return acquired >= 0 ? dMeta + 2 * acquired : nullptr; }
+float* FramePipe::meta_slot() { return acquired >= 0 ? dMeta + 4 * acquired : nullptr; }
 
-cudaError_t FramePipe::submit(cudaStream_t solverStream, float maxVel2, float dt, bool fromDevice) {
+cudaError_t FramePipe::submit(cudaStream_t solverStream, float maxVel2, float dt, bool fromDevice, bool conditional) {
     if (acquired < 0) return cudaErrorInvalidValue;
     const int s = acquired;
     acquired = -1;
@@ -120,13 +120,13 @@ cudaError_t FramePipe::submit(cudaStream_t solverStream, float maxVel2, float dt
     if ((e = cudaEventRecord(exported[s], solverStream)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(copyStream, exported[s], 0)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(dst.pinned ? dst.p : hBuf[s], dBuf[s], bytes, cudaMemcpyDeviceToHost, copyStream)) != cudaSuccess) return e;
-    if (fromDevice && (e = cudaMemcpyAsync(hMeta + 2 * s, dMeta + 2 * s, 2 * sizeof(float), cudaMemcpyDeviceToHost, copyStream)) != cudaSuccess) return e;
+    if (fromDevice && (e = cudaMemcpyAsync(hMeta + 4 * s, dMeta + 4 * s, 4 * sizeof(float), cudaMemcpyDeviceToHost, copyStream)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(copied[s], copyStream)) != cudaSuccess) return e;
     bytesCopied += (uint64_t)bytes;
     {
         std::lock_guard<std::mutex> g(m);
         busy[s] = true;
-        jobs.push_back(Job{ s, dst, fromDevice, maxVel2, dt });
+        jobs.push_back(Job{ s, dst, fromDevice, conditional, maxVel2, dt });
         inFlight++;
     }
     cvJob.notify_one();
@@ -149,12 +149,13 @@ void FramePipe::worker_main() {
         f.count = n; f.maxVel2 = j.maxVel2; f.dt = j.dt;
         f.data = j.dst;
         const cudaError_t e = cudaEventSynchronize(copied[j.slot]);
-        if (e == cudaSuccess && !j.dst.pinned) memcpy(f.data.p, hBuf[j.slot], (size_t)n * sizeof(VfdParticleSimple));
-        if (e == cudaSuccess && j.metaFromDevice) { f.maxVel2 = hMeta[2 * j.slot]; f.dt = hMeta[2 * j.slot + 1]; }
+        const bool keep = !(e == cudaSuccess && j.conditional && hMeta[4 * j.slot + 2] == 0.0f);   // the device decided: no frame this step
+        if (e == cudaSuccess && keep && !j.dst.pinned) memcpy(f.data.p, hBuf[j.slot], (size_t)n * sizeof(VfdParticleSimple));
+        if (e == cudaSuccess && j.metaFromDevice) { f.maxVel2 = hMeta[4 * j.slot]; f.dt = hMeta[4 * j.slot + 1]; }
         {
             std::lock_guard<std::mutex> g(m);
             if (e != cudaSuccess && asyncError == cudaSuccess) asyncError = e;
-            frames.push_back(std::move(f));
+            if (keep) frames.push_back(std::move(f)); else pool.push_back(f.data);
             busy[j.slot] = false;
             inFlight--;
         }
@@ -175,6 +176,17 @@ void FramePipe::clear() {
     std::lock_guard<std::mutex> g(m);
     for (Frame& f : frames) pool.push_back(f.data);     // the storage is kept for the next bake
     frames.clear();
+}
+
+void FramePipe::progress(size_t& publishedFrames, size_t& pendingJobs) {
+    std::lock_guard<std::mutex> g(m);
+    publishedFrames = frames.size();
+    pendingJobs = inFlight;
+}
+
+void FramePipe::wait_pending_below(size_t below) {
+    std::unique_lock<std::mutex> g(m);
+    cvDone.wait(g, [&] { return inFlight < below; });
 }
 
 size_t FramePipe::published() {

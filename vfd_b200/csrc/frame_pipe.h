@@ -46,11 +46,19 @@ public:
     cudaError_t configure(int device, uint32_t n);
     // device buffer the next frame must be exported into (blocks while every slot is in flight)
     VfdParticleSimple* acquire();
-    // device slot for the frame's two scalars (float[2]: MaxVelocityMagnitude, dt) of the buffer returned by acquire()
+    // device slot for the frame's scalars (float[4]: MaxVelocityMagnitude, dt, "this step captured a frame" as 1.0 / 0.0, spare)
+    // of the buffer returned by acquire()
     float* meta_slot();
     // the export kernel has been enqueued on `solverStream` into the buffer returned by acquire(); fromDevice: the
-    // frame's scalars are read from meta_slot() (written by the export kernel), else the host values are used
-    cudaError_t submit(cudaStream_t solverStream, float maxVel2, float dt, bool fromDevice = false);
+    // frame's scalars are read from meta_slot() (written by the export kernel), else the host values are used.
+    // conditional: whether the step captured a frame at all was decided on the device (FrameTime against FrameLength,
+    // DFSPHImplementation.cu:148): the worker publishes the frame only if meta_slot()[2] says so, else the storage goes
+    // back to the pool — the host never waits for the decision.
+    cudaError_t submit(cudaStream_t solverStream, float maxVel2, float dt, bool fromDevice = false, bool conditional = false);
+    // frames published so far and submitted jobs not yet decided / published
+    void progress(size_t& publishedFrames, size_t& pendingJobs);
+    // blocks until fewer than `below` jobs are pending
+    void wait_pending_below(size_t below);
     // wait until every submitted frame is published; returns the first asynchronous error, if any
     cudaError_t drain();
     void clear();                       // drain + drop all published frames
@@ -60,7 +68,7 @@ public:
     uint64_t bytesCopied = 0;
 
 private:
-    struct Job { int slot; HostBuf dst; bool metaFromDevice; float maxVel2, dt; };
+    struct Job { int slot; HostBuf dst; bool metaFromDevice, conditional; float maxVel2, dt; };
     HostBuf take_buffer();
     void release_pool();
     void worker_main();
@@ -69,7 +77,7 @@ private:
     uint32_t n = 0;
     VfdParticleSimple* dBuf[SLOTS] = {};
     VfdParticleSimple* hBuf[SLOTS] = {};          // pinned staging, only for frames in pageable storage
-    float* dMeta = nullptr;                         // SLOTS x float[2]
+    float* dMeta = nullptr;                         // SLOTS x float[4]
     float* hMeta = nullptr;                         // pinned mirror
     std::vector<HostBuf> pool;                      // free frame buffers (n particles each)
     size_t pinnedBytes = 0, pinnedBudget = 0;

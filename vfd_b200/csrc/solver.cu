@@ -77,10 +77,21 @@ __global__ void k_pack_posvel(uint32_t n, const float* __restrict__ pos, const f
     vel4[i] = vel ? make_float4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
-// K15: ConvertParticlesToBuffer (DFSPHKernels.cu:6-22), written in original particle order
-__global__ void k_export_frame(Params P, Arrays A, VfdParticleSimple* __restrict__ out, const DevState* __restrict__ S, float* __restrict__ meta) {
+// The frame decision of DFSPHImplementation::OnUpdate (:148: FrameTime >= FrameLength, FrameTime accumulated with every new
+// time step in the CFL update, :427) taken on the device, so that the host need not read the time step back every step.
+__global__ void k_frame_decide(DevState* S, float frameLength, uint32_t frameCount) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (S->frameIndex < frameCount && S->frameTime >= frameLength) { S->captureFlag = 1u; S->frameTime = 0.0f; S->frameIndex += 1u; }
+    else S->captureFlag = 0u;
+}
+
+// K15: ConvertParticlesToBuffer (DFSPHKernels.cu:6-22), written in original particle order.  conditional: only if
+// k_frame_decide said so (meta[2] tells the frame pipe's worker)
+__global__ void k_export_frame(Params P, Arrays A, VfdParticleSimple* __restrict__ out, const DevState* __restrict__ S, float* __restrict__ meta, int conditional) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0 && meta) { meta[0] = S->vmax2; meta[1] = S->dt; }     // DFSPHParticleFrame::MaxVelocityMagnitude, CurrentTimeStep
+    const bool capture = !conditional || S->captureFlag != 0u;
+    if (p == 0 && meta) { meta[0] = S->vmax2; meta[1] = S->dt; meta[2] = capture ? 1.0f : 0.0f; }     // DFSPHParticleFrame::MaxVelocityMagnitude, CurrentTimeStep
+    if (!capture) return;
     if (p >= P.n) return;
     const float4 x = A.pos[p], v = A.vel[p], a = A.acc[p];
     VfdParticleSimple q;
@@ -290,7 +301,11 @@ void Solver::refresh_params() {
 }
 
 // + 32 elements: the bulk copies of an 8-byte payload array read whole 16-byte granules, i.e. up to one element past a range's end (tile.cuh)
-template<typename T> static cudaError_t dalloc(T*& p, size_t count) { return cudaMalloc((void**)&p, (std::max<size_t>(count, 1) + 32) * sizeof(T)); }
+template<typename T> static cudaError_t dalloc(T*& p, size_t count) {
+    const size_t bytes = (std::max<size_t>(count, 1) + 32) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)&p, bytes);
+    return e == cudaSuccess ? cudaMemset(p, 0, bytes) : e;        // the slack is read (never used): keep it defined
+}
 
 void Solver::free_particles() {
     Arrays& A = arrays;
@@ -690,11 +705,21 @@ int Solver::step() {
     if (frameIndexHost < desc.FrameCount && desc.FrameLength <= 0.0f && !T && state == VFD_STATE_SIMULATING) {
         VfdParticleSimple* d = pipe.acquire();
         if (!d) { cudaGetLastError(); return fail(VFD_E_CUDA, "frame capture: cannot allocate the frame ring buffers"); }
-        k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d, dState, pipe.meta_slot());
+        k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d, dState, pipe.meta_slot(), 0);
         launches += 1;
         CK(pipe.submit(stream, 0.0f, 0.0f, true));
         frameTimeHost = 0.0f;
         frameIndexHost++;
+    } else if (asyncFrames) {
+        // Simulate() with a frame length (the reference's default, 0.0016 s): whether this step's state is a frame depends on the
+        // time steps the device chose.  The device decides (k_frame_decide), the export and the copy to the host are enqueued
+        // for every step, and the frame pipe's worker keeps the frame or drops it: no host round trip per step.
+        VfdParticleSimple* d = pipe.acquire();
+        if (!d) { cudaGetLastError(); return fail(VFD_E_CUDA, "frame capture: cannot allocate the frame ring buffers"); }
+        k_frame_decide<<<1, 32, 0, stream>>>(dState, desc.FrameLength, desc.FrameCount);
+        k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d, dState, pipe.meta_slot(), 1);
+        launches += 2;
+        CK(pipe.submit(stream, 0.0f, 0.0f, true, true));
     } else if (frameIndexHost < desc.FrameCount || T) {
         DevState s;
         int rc = read_state(s);
@@ -736,7 +761,7 @@ int Solver::capture_frame(const DevState& s) {
     // asynchronous pipe (copy stream + host worker): the next step does not wait for PCIe or for the host copy.
     VfdParticleSimple* d = pipe.acquire();
     if (!d) { cudaGetLastError(); return fail(VFD_E_CUDA, "frame capture: cannot allocate the frame ring buffers"); }
-    k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d, dState, nullptr);
+    k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, d, dState, nullptr, 0);
     launches += 1;
     CK(pipe.submit(stream, s.vmax2, s.dt));
     frameTimeHost = 0.0f;              // FrameTime = 0 (:164)
@@ -750,6 +775,21 @@ int Solver::simulate() {
     int rc = begin();
     if (rc) return rc;
     state = VFD_STATE_SIMULATING;
+    // frame length > 0 on one GPU: the device decides which steps are frames (see step()); the host only has to stop in time —
+    // it issues a step only if the bake would be incomplete even if every step still in flight turned out to be a frame
+    asyncFrames = desc.FrameLength > 0.0f && !optTimers && !dist && info.ParticleCount != 0 && getenv("VFD_SYNC_FRAMES") == nullptr;
+    if (asyncFrames) {
+        for (;;) {
+            size_t pub = 0, pend = 0;
+            pipe.progress(pub, pend);
+            if (pub >= desc.FrameCount) break;
+            if (pub + pend >= desc.FrameCount) { pipe.wait_pending_below(pend); continue; }
+            rc = step();
+            if (rc) { state = VFD_STATE_NONE; asyncFrames = false; return rc; }
+        }
+        asyncFrames = false;
+        frameIndexHost = desc.FrameCount;
+    }
     while (frameIndexHost < desc.FrameCount) {
         if (info.ParticleCount == 0) break;    // the reference would spin forever here (OnUpdate returns at once)
         rc = step();
@@ -848,7 +888,7 @@ int Solver::get_current_frame(VfdParticleSimple* out) {
         dFrameCapacity = info.ParticleCount;
     }
     refresh_params();
-    k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dFrame, dState, nullptr);
+    k_export_frame<<<nblk(params.n), VFD_TPB, 0, stream>>>(params, arrays, dFrame, dState, nullptr, 0);
     launches += 1;
     CK(cudaMemcpyAsync(out, dFrame, (size_t)info.ParticleCount * sizeof(VfdParticleSimple), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));

@@ -162,6 +162,7 @@ private:
     size_t allocParticles = 0;        // particle slots the arrays are currently sized for
     bool began = false, searched = false;
     float frameTimeHost = 0.0f;
+    bool asyncFrames = false;                 // Simulate() with a frame length on one GPU: the device decides which steps are frames (solver.cu: step)
     uint64_t stepsIssued = 0;
 };
 
