@@ -102,3 +102,27 @@ def test_scene_round_trip(tmp_path):
     lo, hi = scene_io.unit_cube_box(s["fluid_objects"][0]["transform"])
     pts = scene_io.sample_box_volume(lo, hi, 0.025)
     assert len(pts) == 20 * 10 * 20 and pts.min() > -0.5 and np.all(pts[:, 1] > 0.75)
+
+
+def test_writer_emits_the_loaders_pool_sequence(tmp_path):
+    sys.path.insert(0, ROOT)
+    from vfd_b200 import scene_io
+    """Scene::Load reads the component pools by position (entt snapshot_loader: ID, Tag, Relationship, Transform, SPHSimulation,
+    Material, Mesh, RigidBody, FluidObject, DFSPHSimulation) and every name of the description by name: a written scene must have
+    the same pool sequence as the reference's own default.json — the empty SPH pool, the material pool and all 27 description
+    members, in the reference's order — whatever subset of the description the caller passed."""
+    if not os.path.exists(REF_SCENE):
+        pytest.skip("reference scene not present")
+    p = str(tmp_path / "w.json")
+    scene_io.write_scene(p, {"FrameCount": 3, "Gravity": (0.0, -9.81, 0.0)},
+                         fluid_objects=[dict(mesh="Resources/Models/Cone.obj", transform=np.eye(4), inverted=False, resolution=(20, 20, 20), sample_mode=1)],
+                         rigid_bodies=[dict(mesh="Resources/Models/Cube.obj", transform=np.eye(4), inverted=False, padding=0.0, resolution=(20, 20, 20))])
+    ents_w, pools_w = scene_io.pool_sequence(p)
+    ents_r, pools_r = scene_io.pool_sequence(REF_SCENE)
+    assert ents_w == ents_r == 3
+    assert len(pools_w) == len(pools_r) == len(scene_io.POOL_ORDER)
+    for name, (sw, kw), (sr, kr) in zip(scene_io.POOL_ORDER, pools_w, pools_r):
+        assert sw == sr, name
+        assert kw == kr, name
+    s = scene_io.read_scene(p)
+    assert s["description"]["FrameCount"] == 3 and s["description"]["Viscosity"] == 10.0

@@ -95,9 +95,36 @@ def read_scene(path):
     return out
 
 
+# what DFSPHSimulationDescription's member initialisers give (Structures/DFSPHSimulationDescription.h:9-50): the loader reads
+# every name-value pair, in this order (DFSPHSimulationComponent.h:11-37), so a scene file carries all of them
+DESCRIPTION_DEFAULTS = {
+    "TimeStepSize": 0.001, "MinTimeStepSize": 0.0001, "MaxTimeStepSize": 0.005, "FrameLength": 0.0016, "FrameCount": 200,
+    "MinPressureSolverIterations": 0, "MaxPressureSolverIterations": 100, "MaxPressureSolverError": 10.0,
+    "EnableDivergenceSolverError": True, "MinDivergenceSolverIterations": 0, "MaxDivergenceSolverIterations": 100, "MaxDivergenceSolverError": 10.0,
+    "EnableViscositySolver": True, "MinViscositySolverIterations": 0, "MaxViscositySolverIterations": 100, "MaxViscositySolverError": 0.1,
+    "Viscosity": 10.0, "BoundaryViscosity": 10.0, "TangentialDistanceFactor": 0.5,
+    "EnableSurfaceTensionSolver": False, "SurfaceTensionSmoothPassCount": 1, "SurfaceTension": 1.0, "TemporalSmoothing": False,
+    "CSDFix": -1, "CSD": 10000, "ParticleRadius": 0.025, "Gravity": (0.0, -9.81, 0.0),
+}
+_BOOL_FIELDS = ("EnableDivergenceSolverError", "EnableViscositySolver", "EnableSurfaceTensionSolver", "TemporalSmoothing")
+
+# MaterialComponent of the three kinds of entity (shader + its property block as raw bytes), as the editor saves them
+_MATERIALS = {
+    "sim": ("Resources/Shaders/Normal/DFSPHParticleSimpleShader.glsl",
+            np.array([0.0, 0.843, 0.561, 1.0, 0.0, 0.2, 0.976, 1.0], np.float32)),
+    "rb": ("Resources/Shaders/Normal/BasicDiffuseShader.glsl", np.array([0.4, 0.4, 0.4, 1.0], np.float32)),
+    "fo": ("Resources/Shaders/Normal/ColorShader.glsl", np.array([1.0, 1.0, 1.0, 1.0], np.float32)),
+}
+
+# the component pools of the snapshot, in the order Scene::Save / Scene::Load name them (Scene.cpp:204-260): the loader reads
+# them by position, so an absent component type still needs its (empty) pool
+POOL_ORDER = ("ID", "Tag", "Relationship", "Transform", "SPHSimulation", "Material", "Mesh", "RigidBody", "FluidObject", "DFSPHSimulation")
+
+
 def write_scene(path, description, fluid_objects=(), rigid_bodies=()):
-    """Writes a scene in the same archive layout (what `read_scene` and the editor's `Scene::Load` expect): entity 0 is the
-    simulation, then the rigid bodies, then the fluid objects."""
+    """Writes a scene in the archive layout the editor's `Scene::Load` reads (and `read_scene`): the entity list, then one pool
+    per component type in POOL_ORDER — the (empty) SPH pool and the material pool included — with the complete description.
+    Entity 0 is the simulation, then the rigid bodies, then the fluid objects."""
     inv = {v: k for k, v in DESCRIPTION_FIELDS.items()}
     ents = [dict(tag="GPU Simulation", sim=description)]
     ents += [dict(tag=b.get("tag", "Rigid Body"), rb=b) for b in rigid_bodies]
@@ -110,29 +137,63 @@ def write_scene(path, description, fluid_objects=(), rigid_bodies=()):
     def mat(T):
         T = np.asarray(T, np.float32)
         return {"transform": {"value%d" % c: xyz(T[:, c], "xyzw") for c in range(4)}}
+
+    def material(e):
+        shader, props = _MATERIALS["sim" if "sim" in e else ("rb" if "rb" in e else "fo")]
+        return {"shaderSource": shader, "properties": [int(b) for b in props.tobytes()]}
     seq = [n + 1, 4294967295] + list(range(n))
 
     def pool(items):
         seq.append(len(items))
         for e, c in items:
             seq.extend([e, c])
-    pool([(i, {"id": {"UUID32": 1000 + i}}) for i in range(n)])
-    pool([(i, {"tag": e["tag"]}) for i, e in enumerate(ents)])
-    pool([(i, {"parent": {"UUID32": 0}, "children": []}) for i in range(n)])
-    pool([(i, mat((e.get("rb") or e.get("fo") or {}).get("transform", np.eye(4)))) for i, e in enumerate(ents)])
-    pool([(i, {"meshSource": (e.get("rb") or e.get("fo"))["mesh"]}) for i, e in enumerate(ents) if "rb" in e or "fo" in e])
-    pool([(i, {"inverted": bool(e["rb"]["inverted"]), "padding": float(e["rb"]["padding"]), "collisionMapResolution": xyz(e["rb"]["resolution"])})
-          for i, e in enumerate(ents) if "rb" in e])
-    pool([(i, {"inverted": bool(e["fo"]["inverted"]), "resolution": xyz(e["fo"]["resolution"]), "sampleMode": int(e["fo"]["sample_mode"]),
-               "velocity": xyz(e["fo"].get("velocity", (0.0, 0.0, 0.0)))}) for i, e in enumerate(ents) if "fo" in e])
+    full = dict(DESCRIPTION_DEFAULTS)
+    full.update(description)
     d = {}
-    for k, v in description.items():
-        d[inv[k]] = xyz(v) if isinstance(v, (tuple, list)) else v
-    pool([(0, {"description": d})])
+    for name, field in DESCRIPTION_FIELDS.items():                 # the reference's order
+        v = full[field]
+        d[name] = xyz(v) if isinstance(v, (tuple, list, np.ndarray)) else (bool(v) if field in _BOOL_FIELDS else v)
+    pools = {
+        "ID": [(i, {"id": {"UUID32": 1000 + i}}) for i in range(n)],
+        "Tag": [(i, {"tag": e["tag"]}) for i, e in enumerate(ents)],
+        "Relationship": [(i, {"parent": {"UUID32": 0}, "children": []}) for i in range(n)],
+        "Transform": [(i, mat((e.get("rb") or e.get("fo") or {}).get("transform", np.eye(4)))) for i, e in enumerate(ents)],
+        "SPHSimulation": [],
+        "Material": [(i, material(e)) for i, e in enumerate(ents)],
+        "Mesh": [(i, {"meshSource": (e.get("rb") or e.get("fo"))["mesh"]}) for i, e in enumerate(ents) if "rb" in e or "fo" in e],
+        "RigidBody": [(i, {"inverted": bool(e["rb"]["inverted"]), "padding": float(e["rb"]["padding"]), "collisionMapResolution": xyz(e["rb"]["resolution"])})
+                      for i, e in enumerate(ents) if "rb" in e],
+        "FluidObject": [(i, {"inverted": bool(e["fo"]["inverted"]), "resolution": xyz(e["fo"]["resolution"]), "sampleMode": int(e["fo"]["sample_mode"]),
+                             "velocity": xyz(e["fo"].get("velocity", (0.0, 0.0, 0.0)))}) for i, e in enumerate(ents) if "fo" in e],
+        "DFSPHSimulation": [(0, {"description": d})],
+    }
+    for name in POOL_ORDER:
+        pool(pools[name])
     doc = {"value%d" % i: v for i, v in enumerate(seq)}
     doc["sceneData"] = {"cameraPosition": xyz((4.0, 4.0, 4.0)), "cameraPivot": xyz((0.0, 0.0, 0.0)), "readMe": ""}
     with open(path, "w") as f:
         json.dump(doc, f, indent=1)
+
+
+def pool_sequence(path):
+    """The archive's shape: entity count, then for every pool (its size, the member names of its first component).  Two files
+    the editor's loader treats alike have the same pool sequence up to the sizes."""
+    with open(path) as f:
+        doc = json.load(f)
+    seq, i = [], 0
+    while "value%d" % i in doc:
+        seq.append(doc["value%d" % i])
+        i += 1
+    ents = int(seq[0]) - 1
+    k, out = 2 + ents, []
+    while k < len(seq):
+        size = int(seq[k])
+        keys = tuple(seq[k + 2].keys()) if size else ()
+        if keys == ("description",):
+            keys = ("description",) + tuple(seq[k + 2]["description"].keys())
+        out.append((size, keys))
+        k += 1 + 2 * size
+    return ents, out
 
 
 def unit_cube_box(transform):
