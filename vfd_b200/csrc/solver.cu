@@ -133,7 +133,7 @@ __global__ void k_export_boundary(Params P, Arrays A, uint32_t body, float* __re
     vol[o] = b.w;
 }
 
-static inline uint32_t nblk(uint32_t n) { return (n + VFD_TPB - 1) / VFD_TPB; }
+static inline uint32_t nblk(uint32_t n) { return n ? (n + VFD_TPB - 1) / VFD_TPB : 1u; }     // never a zero-block launch (a rank that owns no particle yet); the kernels bound-check
 
 // ---------------------------------------------------------------------------------------------
 // per-kernel device timers
@@ -225,6 +225,8 @@ Solver::~Solver() {
     pipe.drain();
     free_particles();
     free_bodies();
+    if (dStagePos) cudaFree(dStagePos);
+    if (dStageVel) cudaFree(dStageVel);
     cudaFree(dState); cudaFreeHost(hState); cudaFreeHost(hFlags);
     cudaFree(dLutW); cudaFree(dLutG); cudaFree(dHalton);
     for (int i = 0; i < 4; i++) if (pollEvent[i]) cudaEventDestroy(pollEvent[i]);
@@ -318,6 +320,7 @@ void Solver::free_particles() {
     if (dFrame) { cudaFree(dFrame); dFrame = nullptr; dFrameCapacity = 0; }
     for (int b = 0; b < VFD_MAX_BODIES; b++) { if (A.bx[b]) cudaFree(A.bx[b]); if (A.bcoef[b]) cudaFree(A.bcoef[b]); if (A.bgrad[b]) cudaFree(A.bgrad[b]); }
     memset(&A, 0, sizeof A);
+    bodySampleSlots = 0;
     dPos0 = dVel0 = nullptr;
     allocBytes = 0;
     allocParticles = 0;
@@ -409,14 +412,21 @@ int Solver::set_particles(const float* pos, const float* vel, uint32_t n, bool o
     CK(pipe.configure(device, n));
     if (onDevice) { dPos = const_cast<float*>(pos); dVel = const_cast<float*>(vel); }
     else {
-        CK(cudaMalloc(&dPos, (size_t)12 * n));
+        // the upload's staging buffers stay with the handle (see set_rigid_bodies: no cudaMalloc / cudaFree per bake)
+        if (stageSlots < n) {
+            if (dStagePos) cudaFree(dStagePos);
+            if (dStageVel) cudaFree(dStageVel);
+            dStagePos = dStageVel = nullptr; stageSlots = 0;
+            CK(cudaMalloc(&dStagePos, (size_t)12 * n)); CK(cudaMalloc(&dStageVel, (size_t)12 * n));
+            stageSlots = n;
+        }
+        dPos = dStagePos;
         CK(cudaMemcpyAsync(dPos, pos, (size_t)12 * n, cudaMemcpyHostToDevice, stream));
-        if (vel) { CK(cudaMalloc(&dVel, (size_t)12 * n)); CK(cudaMemcpyAsync(dVel, vel, (size_t)12 * n, cudaMemcpyHostToDevice, stream)); }
+        if (vel) { dVel = dStageVel; CK(cudaMemcpyAsync(dVel, vel, (size_t)12 * n, cudaMemcpyHostToDevice, stream)); }
     }
     k_pack_posvel<<<nblk(n), VFD_TPB, 0, stream>>>(n, dPos, dVel, dPos0, dVel0);
     launches += 1;
     CK(cudaStreamSynchronize(stream));
-    if (!onDevice) { cudaFree(dPos); if (dVel) cudaFree(dVel); }
     return begin();
 }
 
@@ -462,6 +472,7 @@ int Solver::dist_set_particles(const float* pos, const float* vel, const uint32_
 void Solver::free_bodies() {
     for (auto& p : bodyAllocs) cudaFree(p);
     bodyAllocs.clear();
+    bodyAllocBytes.clear();
     memset(&bodies, 0, sizeof bodies);
 }
 
@@ -471,35 +482,47 @@ int Solver::set_rigid_bodies(uint32_t count, const VfdVolumeMap* maps) {
     if (count && !maps) return fail(VFD_E_INVALID, "set_rigid_bodies: null maps");
     CK(cudaStreamSynchronize(stream));
     state = VFD_STATE_NONE;
-    free_bodies();
+    // Re-baking calls this with the same bodies again and again (the editor's "Bake": SetFluidObjects + SetRigidBodies + Simulate):
+    // device allocations of unchanged size are kept — cudaFree / cudaMalloc of tens of megabytes stall for up to seconds now and
+    // then once gigabytes of pinned frame storage exist, which showed as a 2x spread of the end-to-end figure.
+    std::vector<size_t> want;
     for (uint32_t b = 0; b < count; b++) {
         const VfdVolumeMap& m = maps[b];
         if (m.fieldCount < 2 || !m.nodes || !m.cells || !m.cellMap) return fail(VFD_E_INVALID, "volume map needs two fields (SDF, volume) and its three arrays");
+        want.push_back((size_t)m.fieldCount * m.nodeCount * 4); want.push_back((size_t)m.fieldCount * m.cellCount * 32 * 4); want.push_back((size_t)m.fieldCount * m.cellMapCount * 4);
+    }
+    if (want != bodyAllocBytes) {
+        free_bodies();
+        for (size_t bytes : want) { void* p = nullptr; CK(cudaMalloc(&p, std::max<size_t>(bytes, 4))); bodyAllocs.push_back(p); }
+        bodyAllocBytes = want;
+    }
+    memset(&bodies, 0, sizeof bodies);
+    for (uint32_t b = 0; b < count; b++) {
+        const VfdVolumeMap& m = maps[b];
         DevVolumeMap& d = bodies.map[b];
         for (int k = 0; k < 3; k++) { d.dmin[k] = m.domainMin[k]; d.dmax[k] = m.domainMax[k]; d.res[k] = m.resolution[k]; d.cell[k] = m.cellSize[k]; d.cellInv[k] = m.cellSizeInverse[k]; }
         d.fieldCount = m.fieldCount; d.nodeCount = m.nodeCount; d.cellCount = m.cellCount; d.cellMapCount = m.cellMapCount;
-        float* dn; uint32_t *dc, *dm;
-        const size_t nn = (size_t)m.fieldCount * m.nodeCount, nc = (size_t)m.fieldCount * m.cellCount * 32, nm = (size_t)m.fieldCount * m.cellMapCount;
-        CK(cudaMalloc(&dn, nn * 4)); bodyAllocs.push_back(dn);
-        CK(cudaMalloc(&dc, nc * 4)); bodyAllocs.push_back(dc);
-        CK(cudaMalloc(&dm, nm * 4)); bodyAllocs.push_back(dm);
-        CK(cudaMemcpy(dn, m.nodes, nn * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dc, m.cells, nc * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dm, m.cellMap, nm * 4, cudaMemcpyHostToDevice));
+        float* dn = (float*)bodyAllocs[3 * b]; uint32_t* dc = (uint32_t*)bodyAllocs[3 * b + 1]; uint32_t* dm = (uint32_t*)bodyAllocs[3 * b + 2];
+        CK(cudaMemcpy(dn, m.nodes, want[3 * b], cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dc, m.cells, want[3 * b + 1], cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dm, m.cellMap, want[3 * b + 2], cudaMemcpyHostToDevice));
         d.nodes = dn; d.cells = dc; d.cellMap = dm;
     }
     // per-body boundary sample arrays are sized by the particle count (RigidBody.cu:13-16): particles first
     const size_t np = ((size_t)(dist ? std::max(dist->capacity, info.ParticleCount) : info.ParticleCount) + 31) / 32 * 32;
+    const bool need = info.ParticleCount || dist;
     for (int b = 0; b < VFD_MAX_BODIES; b++) {
+        const bool keep = need && (uint32_t)b < count && arrays.bx[b] && bodySampleSlots == np;
+        if (keep) continue;
         if (arrays.bx[b]) { cudaFree(arrays.bx[b]); arrays.bx[b] = nullptr; }
         if (arrays.bcoef[b]) { cudaFree(arrays.bcoef[b]); arrays.bcoef[b] = nullptr; }
         if (arrays.bgrad[b]) { cudaFree(arrays.bgrad[b]); arrays.bgrad[b] = nullptr; }
     }
-    for (uint32_t b = 0; b < count && (info.ParticleCount || dist); b++) {
-        CK(dalloc(arrays.bx[b], np)); CK(cudaMemset(arrays.bx[b], 0, np * 16));
-        CK(dalloc(arrays.bcoef[b], np)); CK(cudaMemset(arrays.bcoef[b], 0, np * 16));
-        CK(dalloc(arrays.bgrad[b], np)); CK(cudaMemset(arrays.bgrad[b], 0, np * 16));
+    for (uint32_t b = 0; b < count && need; b++) {
+        if (!arrays.bx[b]) { CK(dalloc(arrays.bx[b], np)); CK(dalloc(arrays.bcoef[b], np)); CK(dalloc(arrays.bgrad[b], np)); }
+        else { CK(cudaMemset(arrays.bx[b], 0, np * 16)); CK(cudaMemset(arrays.bcoef[b], 0, np * 16)); CK(cudaMemset(arrays.bgrad[b], 0, np * 16)); }
     }
+    bodySampleSlots = np;
     info.RigidBodyCount = count;
     refresh_params();
     return VFD_OK;

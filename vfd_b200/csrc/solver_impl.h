@@ -161,6 +161,9 @@ private:
     uint32_t cellEstimate = 27, cellCapacity = 0;
     size_t allocParticles = 0;        // particle slots the arrays are currently sized for
     bool began = false, searched = false;
+    std::vector<size_t> bodyAllocBytes;      // sizes of bodyAllocs (three per body): re-baking the same bodies keeps them
+    size_t bodySampleSlots = 0;              // particle slots the per-body sample arrays are sized for
+    float *dStagePos = nullptr, *dStageVel = nullptr; uint32_t stageSlots = 0;   // set_particles' upload staging
     float frameTimeHost = 0.0f;
     bool asyncFrames = false;                 // Simulate() with a frame length on one GPU: the device decides which steps are frames (solver.cu: step)
     uint64_t stepsIssued = 0;
