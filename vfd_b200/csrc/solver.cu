@@ -315,7 +315,8 @@ void Solver::free_particles() {
     void* ptrs[] = { A.pos, A.vel, A.dv, A.nbar, A.curv, A.curvS, A.curvD, A.id, A.pos2, A.vel2, A.dv2, A.nbar2, A.curv2, A.curvS2, A.curvD2, A.id2,
                      A.posRho, A.acc, A.pacc, A.nrm, A.res, A.rho, A.rhoAdv, A.kappa, A.kappaV, A.alpha, A.cgG, A.cgR, A.cgQ, A.cgZ, A.cgXG, A.cgXP, A.cgGyz, A.cgPyz, A.minv,
                      A.cnt, A.list16, A.coef, A.gcoef, A.key, A.rank, A.tmpIdx, A.cellCount, A.cellBegin, A.tileSums, A.tileList, A.partials, A.slotSums, dPos0, dVel0 };
-    for (void* p : ptrs) if (p) cudaFree(p);
+    for (void* p : ptrs) if (p && !(pcgArena && (char*)p >= (char*)pcgArena && (char*)p < (char*)pcgArena + pcgArenaBytes)) cudaFree(p);
+    if (pcgArena) { cudaFree(pcgArena); pcgArena = nullptr; pcgArenaBytes = 0; }
     if (dIds0) { cudaFree(dIds0); dIds0 = nullptr; }
     if (dFrame) { cudaFree(dFrame); dFrame = nullptr; dFrameCapacity = 0; }
     for (int b = 0; b < VFD_MAX_BODIES; b++) { if (A.bx[b]) cudaFree(A.bx[b]); if (A.bcoef[b]) cudaFree(A.bcoef[b]); if (A.bgrad[b]) cudaFree(A.bgrad[b]); }
@@ -324,6 +325,35 @@ void Solver::free_particles() {
     dPos0 = dVel0 = nullptr;
     allocBytes = 0;
     allocParticles = 0;
+}
+
+// L2 residency of an address range for everything launched on the solver's stream from now on (persisting carve-out of the
+// L2 cache; VFD_L2_PERSIST_MB caps it, 0 switches it off)
+void Solver::l2_window(void* base, size_t bytes) {
+    const char* e = getenv("VFD_L2_PERSIST_MB");
+    int maxPersist = 0, maxWindow = 0;
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, device);
+    cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, device);
+    size_t carve = e ? (size_t)atoll(e) << 20 : (size_t)maxPersist;
+    carve = std::min(carve, (size_t)maxPersist);
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    if (carve == 0 || bytes == 0 || maxWindow <= 0) {
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+        return;
+    }
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    const size_t win = std::min(bytes, (size_t)maxWindow);
+    attr.accessPolicyWindow.base_ptr = base;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)win);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+    l2Carve = carve; l2Window = win;
 }
 
 int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxMax) {
@@ -345,6 +375,21 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
     allocParticles = np;
     // several ranks: the arrays that halo exchanges touch come from one slab that the other ranks map (distributed.cu)
     if (dist) { int rc = dist_alloc_slab(np); if (rc) return rc; allocBytes += dist->slabBytes; }
+    // One GPU: the vectors every PCG iteration reads and rewrites — direction (x, y, z, p.x) + (p.y, p.z), q = A p, residual,
+    // solution: 72 B per particle — come from one arena, so that one access-policy window can keep them resident in L2 across
+    // the ~45 iterations of a solve while the neighbour list and the pair coefficients (430 MB per product) stream past them.
+    if (!dist) {
+        pcgArenaBytes = (np + 32) * 72;
+        CK(cudaMalloc(&pcgArena, pcgArenaBytes));
+        CK(cudaMemset(pcgArena, 0, pcgArenaBytes));
+        char* a = (char*)pcgArena;
+        A.cgXP = (float4*)a; a += (np + 8) * 16;
+        A.cgQ = (float4*)a;  a += (np + 8) * 16;
+        A.cgR = (float4*)a;  a += (np + 8) * 16;
+        A.cgG = (float4*)a;  a += (np + 8) * 16;
+        A.cgPyz = (float2*)a;
+        l2_window(pcgArena, pcgArenaBytes);
+    }
     float4** f4s[] = { &A.pos, &A.vel, &A.dv, &A.nbar, &A.pos2, &A.vel2, &A.dv2, &A.nbar2, &A.posRho, &A.acc, &A.pacc, &A.nrm,
                        &A.cgG, &A.cgR, &A.cgQ, &A.cgZ, &A.cgXG, &A.cgXP, &dPos0, &dVel0 };
     CK(dalloc(dIds0, np));
@@ -352,7 +397,8 @@ int Solver::alloc_particles(uint32_t n, const float* bboxMin, const float* bboxM
     float** f1s[] = { &A.curv, &A.curvS, &A.curvD, &A.curv2, &A.curvS2, &A.curvD2, &A.res, &A.rho, &A.rhoAdv, &A.kappa, &A.kappaV, &A.alpha };
     for (float** p : f1s) if (!*p) { CK(dalloc(*p, np)); allocBytes += np * 4; }
     CK(dalloc(A.minv, np * 9)); allocBytes += np * 36;
-    if (!A.cgGyz) { CK(dalloc(A.cgGyz, np)); CK(dalloc(A.cgPyz, np)); allocBytes += np * 16; }
+    if (!A.cgGyz) { CK(dalloc(A.cgGyz, np)); allocBytes += np * 8; }
+    if (!A.cgPyz) { CK(dalloc(A.cgPyz, np)); allocBytes += np * 8; }
     uint32_t** u1s[] = { &A.id, &A.id2, &A.cnt, &A.key, &A.rank, &A.tmpIdx };
     for (uint32_t** p : u1s) { CK(dalloc(*p, np)); allocBytes += np * 4; }
     CK(dalloc(A.list16, np * ELL_SLOTS)); searchBytes = np * ELL_SLOTS * 2 + np * 4 * 4;

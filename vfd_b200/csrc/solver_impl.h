@@ -134,6 +134,7 @@ private:
     int dist_alloc_slab(size_t np);
     void dist_free_slab();
     int dist_upload_grid();
+    void l2_window(void* base, size_t bytes);
     void dist_halo_targets(Params& P) const;
     void dist_count_fused_halo(uint64_t bytesPerItem);
     int halo4(float4* a) { return dist ? dist_halo(a, 4) : VFD_OK; }
@@ -161,6 +162,8 @@ private:
     uint32_t cellEstimate = 27, cellCapacity = 0;
     size_t allocParticles = 0;        // particle slots the arrays are currently sized for
     bool began = false, searched = false;
+    void* pcgArena = nullptr; size_t pcgArenaBytes = 0;      // one GPU: the PCG's vectors in one allocation (L2 residency window)
+    size_t l2Carve = 0, l2Window = 0;
     std::vector<size_t> bodyAllocBytes;      // sizes of bodyAllocs (three per body): re-baking the same bodies keeps them
     size_t bodySampleSlots = 0;              // particle slots the per-body sample arrays are sized for
     float *dStagePos = nullptr, *dStageVel = nullptr; uint32_t stageSlots = 0;   // set_particles' upload staging

@@ -548,13 +548,20 @@ __device__ __forceinline__ void pipe_scout(DevState* __restrict__ S, const Array
         mbar_wait(&ps.empty[s], (u & 1u) ^ 1u);          // every consumer warp has released the slot's previous tile
         ptrace(2, k, 0);
         uint32_t run = inc - mine;
+        bool real0 = false;                              // does a particle sit in local slot 0?
         #pragma unroll
         for (int i = 0; i < CPL; i++) {
             const int c = (int)lane * CPL + i;
             if (c < HALO_CELLS) { H.cellG[c] = beg[i]; H.local[c] = run + pre[i]; H.cellE[c] = fin[i]; }
+            real0 = real0 || (run + pre[i] == 0u && fin[i] > beg[i]);
             run += slots[i];
         }
+        const bool anyReal0 = __any_sync(0xffffffffu, real0);
         if (lane == 0) {
+            // Unused slots of a particle's last neighbour group hold index 0, and the pair passes gather it with a zero
+            // coefficient ("a valid read"): if slot 0 is segment padding nothing is copied there, and whatever an earlier
+            // kernel left in shared memory (an Inf, a NaN pattern) would turn 0 x garbage into NaN — the copy warps zero it
+            H.pad[0] = anyReal0 ? 0u : 1u;
             H.local[HALO_CELLS] = total;
             H.begin = end ? NONE : tb; H.end = end ? NONE : te; H.total = end ? 0u : total; H.li = tli;
             if (!end && checkIndexRange && total > 65535u) atomicOr(&S->errorFlags, 2u);
@@ -616,6 +623,13 @@ __device__ __forceinline__ void pipe_copier(PipeShared& ps, unsigned char* pay, 
             // particle, no per-sector shared-memory write.  16-byte arrays copy the exact range; the 8-byte array copies the
             // enclosing aligned 16-byte granules into the segment's (even, padded) slots.
             unsigned long long* fb = &ps.full[s];
+            if (ct == 0 && H.pad[0]) {                    // slot 0 is padding: give it a finite value (see the scout)
+                *reinterpret_cast<float4*>(sA) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (BBYTES == 16) *reinterpret_cast<float4*>(sB) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                // (an 8- or 4-byte array's copy may cover the slot as well, with the finite value of a real particle: either is fine)
+                if (BBYTES == 8) *reinterpret_cast<float2*>(sB) = make_float2(0.0f, 0.0f);
+                if (BBYTES == 4) *reinterpret_cast<float*>(sB) = 0.0f;
+            }
             for (uint32_t seg = ct; seg < 108u; seg += PIPE_COPY_THREADS) {
                 const uint32_t r = seg / 3u, q = seg - 3u * r, c0 = r * 6u;
                 const uint32_t cb = q == 0u ? c0 : (q == 1u ? c0 + 1u : c0 + 5u), cl = q == 0u ? c0 : (q == 1u ? c0 + 4u : c0 + 5u);

@@ -205,9 +205,14 @@ struct ViscMatvecOp {
         own[6] = __ldg(A.rho + p);                          // for the epilogue; in flight during the gather
     }
     __device__ __forceinline__ void pair(const float (&o)[NOWN], float4 a, float4 b, float& c, float (&acc)[NSUM]) const {
-        const float dx = o[0] - a.x, dy = o[1] - a.y, dz = o[2] - a.z;
-        const float w = c * __fmaf_rn(o[5] - b.y, dz, __fmaf_rn(o[4] - b.x, dy, (o[3] - a.w) * dx));
-        acc[0] = __fmaf_rn(w, dx, acc[0]); acc[1] = __fmaf_rn(w, dy, acc[1]); acc[2] = __fmaf_rn(w, dz, acc[2]);
+        // the six differences as three packed operations (sm_100 FFMA2: a * -1 + o is o - a exactly): 10 floating-point
+        // instructions per pair instead of 13, the same roundings in the same order as the scalar form
+        const float2 m1 = make_float2(-1.0f, -1.0f);
+        const float2 dxy = __ffma2_rn(make_float2(a.x, a.y), m1, make_float2(o[0], o[1]));       // (dx, dy)
+        const float2 dzp = __ffma2_rn(make_float2(a.z, a.w), m1, make_float2(o[2], o[3]));       // (dz, p_i.x - p_j.x)
+        const float2 dpq = __ffma2_rn(make_float2(b.x, b.y), m1, make_float2(o[4], o[5]));       // (p_i.y - p_j.y, p_i.z - p_j.z)
+        const float w = c * __fmaf_rn(dpq.y, dzp.x, __fmaf_rn(dpq.x, dxy.y, dzp.y * dxy.x));
+        acc[0] = __fmaf_rn(w, dxy.x, acc[0]); acc[1] = __fmaf_rn(w, dxy.y, acc[1]); acc[2] = __fmaf_rn(w, dzp.x, acc[2]);
     }
     __device__ __forceinline__ void finish(uint32_t p, uint32_t mf, const float (&o)[NOWN], const float (&acc)[NSUM]) {
         const float3 xi = f3(o[0], o[1], o[2]), vi = f3(o[3], o[4], o[5]);
