@@ -320,19 +320,42 @@ def cpu_baseline(state, dt, st, pos0, box, res, steps=10, gpu_step=None):
     par = None
     if gpu_step is not None:
         gpu_step = gpu_step(ref_map)
-        worst = ("", 0.0)
+        # the reference's own run-to-run spread on this very step (its neighbour order and its reductions depend on the thread
+        # schedule: SURVEY.md Appendix E): a second, single-threaded run of the same step — affordable up to a few 100k particles
+        noise = {}
+        if n <= 200000:
+            with refsim.quiet_stdout():
+                again = refsim.RefSim(description(refsim.Desc), serial=True)
+                again.set_particles(pos0)
+                again.add_box_body(box[0], box[1], inverted=True, padding=0.0, res=res)
+                again.commit_bodies()
+                again.set_particles_full(state)
+                again.set_time_step(dt)
+                again.set_st_state(*st)
+                again.step(1)
+                second = again.particles()
+            for f in PARITY_FIELDS:
+                y, z = np.asarray(first[f], np.float64), np.asarray(second[f], np.float64)
+                scale = np.abs(y).max()
+                noise[f] = 0.0 if scale == 0.0 else float(np.abs(y - z).max() / scale)
+        worst = ("", 0.0, 2.0e-5, 0.0)
+        ok = True
         for f in PARITY_FIELDS:
             x, y = np.asarray(gpu_step[f], np.float64), np.asarray(first[f], np.float64)
             scale = np.abs(y).max()
             e = 0.0 if scale == 0.0 else float(np.abs(x - y).max() / scale)
-            if e > worst[1]:
-                worst = (f, e)
-        par = {"worst_field": worst[0], "value": worst[1], "tol": 2.0e-5, "ok": bool(worst[1] <= 2.0e-5), "particles": n,
+            tol = max(2.0e-5, 3.0 * noise.get(f, 0.0))
+            ok = ok and e <= tol
+            if e / tol > worst[3]:
+                worst = (f, e, tol, e / tol)
+        par = {"worst_field": worst[0], "value": worst[1], "tol": worst[2], "ok": bool(ok), "particles": n,
+               "reference_self_deviation": (noise.get(worst[0]) if noise else None),
                "note": "one step from the timed run's settled state, both sides fed the reference's own volume map (its mesh distance is evaluated in "
                        "fp32 on a 10-m box, which moves wall distances by up to 1e-3 against the analytic box distance the timed run's GPU-built map "
                        "uses: DESIGN.md section 2): vfd_b200 (search without FMA contraction, as the host-compiled oracle) vs the reference's sources "
                        "on the host cores; max |error| / max |field| over the fields of the 120-B particle state; tolerance as in "
-                       "tests/test_gpu_scale.py (the reference moves by ~1e-5 against itself between two runs)"}
+                       "tests/test_gpu_scale.py: max(2e-5, 3 x the reference's own deviation between a threaded and a single-threaded run of this "
+                       "step — measured here up to 200k particles; it moves by ~1e-5 against itself at 1M)"}
     return {"value": n * steps / el, "unit": "particle-steps/s", "cores": threads, "kind": "reference",
             "sample": "%d steps of the same %d-particle settled state (after 1 untimed step), %.1f s; PCG it of last step %d" % (
                 steps, n, el, sim.debug()["visc_it"])}, par
@@ -388,6 +411,7 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=12, help="--impl reference: timed steps (a bounded sample: ~1 s each at 1M on 16 cores)")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA build on this GPU")
     ap.add_argument("--scene", default="dam", choices=["dam", "tank"], help="N > 1: the dam break stretched along x (default; the N = 1 scene at N = 1) or a closed tank")
+    ap.add_argument("--strong", action="store_true", help="N > 1: strong scaling — ONE side^3 scene (BASELINE.json config 4: --side 200) cut into N slabs, instead of side^3 per GPU")
     ap.add_argument("--ref-side", type=int, default=50)
     ap.add_argument("--ref-settle", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -31,9 +31,16 @@ def dist_scene(side, world, kind="dam"):
     return nx, box, res
 
 
-def rank_positions(side, world, rank):
-    """This rank's share of the lattice (x-range [rank*side, (rank+1)*side) of the global block) and its global ids."""
+def rank_positions(side, world, rank, strong=False):
+    """This rank's share of the lattice and its global ids: weak scaling — the x-range [rank*side, (rank+1)*side) of a block of
+    world*side x side x side; strong scaling (BASELINE.json config 4) — the x-range [rank*side/world, (rank+1)*side/world) of ONE
+    side^3 block, whatever the number of GPUs."""
     from vfd_b200 import api
+    if strong:
+        lo, hi = rank * side // world, (rank + 1) * side // world
+        pos = api.block_positions(hi - lo, side, side, R, origin=(2 * D + lo * D, 2 * D, 2 * D))
+        ids = (np.arange(len(pos), dtype=np.uint64) + np.uint64(lo) * np.uint64(side * side)).astype(np.uint32)
+        return pos, ids
     pos = api.block_positions(side, side, side, R, origin=(2 * D + rank * side * D, 2 * D, 2 * D))
     ids = (np.arange(len(pos), dtype=np.uint64) + np.uint64(rank) * np.uint64(side ** 3)).astype(np.uint32)
     return pos, ids
@@ -44,7 +51,9 @@ def setup(args, rank, local, world, description, frames=0):
     import torch
     import torch.distributed as dist
     from vfd_b200 import api, partition
-    nx, box, res = dist_scene(args.side, world, getattr(args, "scene", "dam"))
+    strong = bool(getattr(args, "strong", False))
+    # strong scaling: the ONE side^3 scene (= the 1-GPU scene of that size) cut into `world` slabs
+    nx, box, res = dist_scene(args.side, 1 if strong else world, getattr(args, "scene", "dam"))
     sim = api.DFSPHSimulation(description(api.DFSPHSimulationDescription, frames=frames), device=local)
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
@@ -52,7 +61,7 @@ def setup(args, rank, local, world, description, frames=0):
     dist.broadcast(uid, 0)
     sim.init_distributed(rank, world, uid.cpu().numpy().tobytes(), box[0], box[1])
     origin, cell, tiles = sim.grid()
-    pos, ids = rank_positions(args.side, world, rank)
+    pos, ids = rank_positions(args.side, world, rank, strong)
     hist = torch.from_numpy(partition.column_histogram(pos[:, 0], origin[0], H, tiles[0])).cuda()
     dist.all_reduce(hist)
     bounds = partition.plan_slabs(hist.cpu().numpy(), world)
@@ -60,7 +69,7 @@ def setup(args, rank, local, world, description, frames=0):
     owner = partition.owner_of(partition.tile_columns(pos[:, 0], origin[0], H, tiles[0]), bounds)
     pos, ids = redistribute(pos, ids, owner, rank, world)
     sim.set_slab(int(bounds[rank]), int(bounds[rank + 1]))
-    n_global = world * args.side ** 3
+    n_global = args.side ** 3 if strong else world * args.side ** 3
     ghost = int(tiles[1]) * int(tiles[2]) * 64 * 12 * 2
     sim.set_particles_distributed(pos, None, ids, n_global, int(1.5 * len(pos)) + 2 * ghost)
     vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R, device=local)
@@ -136,10 +145,10 @@ def main(args, rank, local, world):
         per_step = {k: (stats1[k] - stats0[k]) / args.steps for k in stats1}
         out = {
             "metric": "DFSPH particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": bench.workload(args.side, world, args.settle) if args.scene == "dam" else
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if getattr(args, "strong", False) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": bench.workload(args.side, 1 if getattr(args, "strong", False) else world, args.settle) if args.scene == "dam" else
                                    "closed tank, %d x %d^3 = %d particles, DFSPH (2+2 Jacobi iterations) + implicit viscosity PCG (nu 10) + surface tension; %d settle steps" % (world, args.side, n_global, args.settle),
-                       "notes": "%d^3 particles per GPU, the 1-GPU scene repeated along x (it collapses along z); slabs of tile columns along x re-balanced while stepping, halos and "
+                       "notes": ("strong scaling: ONE %d^3 scene cut into slabs; " % args.side if getattr(args, "strong", False) else "") + "%d^3 particles per GPU, the 1-GPU scene repeated along x (it collapses along z); slabs of tile columns along x re-balanced while stepping, halos and "
                                 "all-reduces through peer memory (%s); working set > L2, no flush" % (args.side, "CUDA IPC over NVLink" if sim.slab()["peer_memory"] else "off: NCCL only"),
                        "baseline_config": args.config,
                        "slab_rank0_now": sim.slab(),

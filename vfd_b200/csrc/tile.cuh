@@ -399,6 +399,9 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
 }
 // A waiting warp must not eat the issue slots of the working ones (ncu of round 1's mat-vec: a quarter of all executed warp
 // instructions were these polls): after a failed try it sleeps before the next one (PIPE_WAIT_NS, 0 = poll flat out).
+#ifndef PIPE_COEF_CA
+#define PIPE_COEF_CA 0
+#endif
 #ifndef PIPE_WAIT_NS
 #define PIPE_WAIT_NS 100
 #endif
@@ -428,7 +431,11 @@ __device__ __forceinline__ void cp_async8_zfill(uint32_t dstShared, const void* 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dstShared), "l"(src), "r"(srcBytes) : "memory");
 }
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dstShared, const void* src, uint32_t srcBytes) {
+#if PIPE_COEF_CA
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dstShared), "l"(src), "r"(srcBytes) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dstShared), "l"(src), "r"(srcBytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
