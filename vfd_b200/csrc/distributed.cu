@@ -220,6 +220,7 @@ int Solver::dist_init(int rank, int nranks, const char* id128, const float* dmin
     dist->colLo = 0; dist->colHi = dist->gtiles[0];
     CK(cudaMalloc(&dist->dCounters, 64 * sizeof(uint32_t)));
     { const char* e = getenv("VFD_DIST_REBALANCE"); if (e) dist->rebalanceEvery = atoi(e); }
+    { const char* e = getenv("VFD_DIST_FUSED_HALO"); dist->fusedHalo = e && atoi(e) == 1; }
     CK(cudaMallocHost(&dist->hCounters, 16 * sizeof(uint32_t)));
     return VFD_OK;
 }
@@ -279,8 +280,8 @@ void Solver::dist_halo_targets(Params& P) const {
     for (int k = 0; k < 2; k++) {
         const int region = k == 0 ? SR_CGXP : SR_CGPYZ;
         const size_t eb = kRegionBytes[region];
-        P.haloP[0][k] = (D.p2p && hasL) ? D.peerSlab[D.rank - 1] + slab_offset(region, D.slabNp[D.rank - 1]) + (size_t)D.leftOwnE * eb : nullptr;
-        P.haloP[1][k] = (D.p2p && hasR) ? D.peerSlab[D.rank + 1] + slab_offset(region, D.slabNp[D.rank + 1]) : nullptr;
+        P.haloP[0][k] = (D.fusedNow && hasL) ? D.peerSlab[D.rank - 1] + slab_offset(region, D.slabNp[D.rank - 1]) + (size_t)D.leftOwnE * eb : nullptr;
+        P.haloP[1][k] = (D.fusedNow && hasR) ? D.peerSlab[D.rank + 1] + slab_offset(region, D.slabNp[D.rank + 1]) : nullptr;
     }
     P.haloRange[0] = D.ownB; P.haloRange[1] = D.edgeLEnd; P.haloRange[2] = D.edgeRBegin; P.haloRange[3] = D.ownE;
 }
@@ -459,6 +460,19 @@ int Solver::dist_read_ranges() {
     CK(cudaStreamSynchronize(stream));
     h[4] = got[0]; h[5] = got[4];
     D.leftOwnE = got[1];
+    D.maxOwned = nOwn;
+    if (D.fusedHalo && D.p2p) {
+        // Whether the fused vector kernel carries the step must be the SAME decision on every rank (it replaces an exchange
+        // kernel that the neighbours would otherwise wait in): it depends on the largest owned count over all ranks
+        uint32_t* dm = D.dCounters + 48;
+        CK(cudaMemcpyAsync(dm, &nOwn, 4, cudaMemcpyHostToDevice, stream));
+        NK(D.api.AllReduce(dm, dm + 1, 1, ncclUint32, ncclMax, D.comm, stream));
+        uint32_t mx = 0;
+        CK(cudaMemcpyAsync(&mx, dm + 1, 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        D.maxOwned = mx;
+    }
+    D.fusedNow = D.fusedHalo && D.p2p && (uint64_t)D.maxOwned <= (uint64_t)numSMs * 8u * 1024u - 32ull * (uint64_t)numSMs;
     dist_halo_targets(params);
     D.stepsDone++;
     if (D.rebalanceEvery > 0 && D.stepsDone % (uint64_t)D.rebalanceEvery == 0) {

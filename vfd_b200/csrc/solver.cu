@@ -713,7 +713,8 @@ int Solver::step() {
         const bool fusedStep = viscosity_step_fits(L, P);
         // several ranks over peer memory: the fused vector kernel writes the new direction of the edge columns straight into
         // the neighbours' ghost ranges, and the next mat-vec waits for their "landed" flags: no exchange kernel per iteration
-        const bool fusedHalo = fusedStep && dist && P.nRanks > 1u && P.peerCtl[0] != nullptr;
+        // (VFD_DIST_FUSED_HALO=1; every rank takes the same decision: from the largest owned count over all ranks)
+        const bool fusedHalo = fusedStep && dist && dist->fusedNow && P.nRanks > 1u && P.peerCtl[0] != nullptr;
         bool haloPending = false;
         auto iteration = [&]() -> int {
             launch_viscosity_matvec(L, P, A, dState, false, haloPending);

@@ -43,6 +43,10 @@ struct Dist {
     // into every other rank of the box; halos are written straight into the neighbour's ghost ranges, solver decisions are
     // all-reduced through the control blocks (control.cuh: PeerCtl) — no NCCL call per solver iteration
     bool p2p = false;
+    bool fusedHalo = false;                   // VFD_DIST_FUSED_HALO=1: the PCG direction's halo is written by the fused vector kernel (see solver.cu);
+                                              // off by default: validated on 2 GPUs only
+    bool fusedNow = false;                    // ... and it carries this step (the same on every rank)
+    uint32_t maxOwned = 0;                    // largest owned-particle count over all ranks this step (only maintained with fusedHalo)
     unsigned char* slab = nullptr; size_t slabBytes = 0;
     uint64_t slabNp[8] = {};                  // particle slots of every rank's arrays (region offsets follow from it)
     unsigned char* peerSlab[8] = {};          // every rank's slab in this process' address space (own: slab)

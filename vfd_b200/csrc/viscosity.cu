@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_visc_step(const __grid_cons
             }
         }
     }
-    if (P.nRanks > 1u && P.peerCtl[0]) {
+    if (P.nRanks > 1u && P.peerCtl[0] && (P.haloP[0][0] || P.haloP[1][0])) {
         // "the direction has landed": told to both neighbours by the block that finishes last; their next mat-vec waits for it
         __threadfence_system();
         __syncthreads();
@@ -496,7 +496,9 @@ void launch_viscosity_update(const LaunchCfg& L, const Params& P, const Arrays& 
 // true when the fused kernel can carry this scene: the decision is taken inside the kernel (one rank, or ranks that all-reduce
 // through peer memory) and the rank holds <= STEP_MAXK x 1024 particles per SM
 bool viscosity_step_fits(const LaunchCfg& L, const Params& P) {
-    return (P.nRanks == 1 || P.peerCtl[0] != nullptr) && P.tune[5] != 1 && (uint64_t)P.n <= (uint64_t)L.numSMs * STEP_MAXK * STEP_THREADS - 32ull * (uint64_t)L.numSMs;
+    // the kernel walks the OWNED particles only (ghost copies of the neighbour slabs are not updated here)
+    const uint64_t owned = P.nRanks > 1u ? (uint64_t)(P.haloRange[3] - P.haloRange[0]) : (uint64_t)P.n;
+    return (P.nRanks == 1 || P.peerCtl[0] != nullptr) && P.tune[5] != 1 && owned <= (uint64_t)L.numSMs * STEP_MAXK * STEP_THREADS - 32ull * (uint64_t)L.numSMs;
 }
 int launch_viscosity_step(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     const size_t sm = (size_t)STEP_MAXK * STEP_THREADS * (sizeof(float4) + sizeof(float2));
