@@ -40,6 +40,45 @@ def test_committed_bench_line_has_the_contract_keys():
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] <= d["value"] * 1.05
     k = d["clocks"]
     assert "sm_mhz" in k and "sm_max_mhz" in k and not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if os.path.basename(paths[-1]) >= "r02":
+        # round 2 on: the 1M parity block (the cpu_baseline leg's first reference step checks the GPU's step) and the reference's
+        # own CUDA solver on the same GPU and state
+        p = d["parity"]
+        assert p["particles"] == 1000000 and p["ok"] is True and p["value"] <= p["tol"]
+        assert d["steps"] >= 100
+        assert d["reference_cuda"]["ieee"]["ms_per_step"] > d["ms_per_step"]
+        assert d["e2e"]["default_frame_length"]["frames"] > 0
+
+
+def test_scene_of_n_gpus_repeats_the_one_gpu_scene_along_x():
+    """bench.scene(side, world): the block and the box grow along x only (slabs side by side), y and z — the direction the block
+    collapses in — are the 1-GPU scene's; bench_multi builds the same box and its ranks' lattice shares tile the block exactly."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    import bench_multi
+    bench.CONFIG_NAME = bench.CONFIGS[3]["name"]
+    p1, b1, r1 = bench.scene(6, 1)
+    p3, b3, r3 = bench.scene(6, 3)
+    assert len(p3) == 3 * len(p1)
+    assert b3[1][1] == b1[1][1] and b3[1][2] == b1[1][2] and b3[1][0] > b1[1][0]
+    assert b1[1][2] > b1[1][0]                         # twice the block's depth along z: that is where it flows
+    nx, box, res = bench_multi.dist_scene(6, 3, "dam")
+    assert nx == 18 and np.allclose(box[1], b3[1]) and tuple(res) == tuple(r3)
+    # weak scaling: the ranks' shares are the block, each particle once, ids = index in bench.scene's order along x-slabs
+    parts = [bench_multi.rank_positions(6, 3, r) for r in range(3)]
+    allp = np.concatenate([p for p, _ in parts])
+    ids = np.concatenate([i for _, i in parts])
+    assert len(np.unique(ids)) == len(p3) == len(allp)
+    assert {tuple(np.round(x, 5)) for x in allp} == {tuple(np.round(x, 5)) for x in p3}
+    # strong scaling: ONE 6^3 block cut into three x-ranges
+    parts = [bench_multi.rank_positions(6, 3, r, strong=True) for r in range(3)]
+    allp = np.concatenate([p for p, _ in parts])
+    ids = np.concatenate([i for _, i in parts])
+    assert len(allp) == 216 and sorted(ids.tolist()) == list(range(216))
+    assert {tuple(np.round(x, 5)) for x in allp} == {tuple(np.round(x, 5)) for x in p1}
+    assert "8 x 100^3 = 8000000" in bench.workload(100, 8, 200) and "100^3 = 1000000" in bench.workload(100, 1, 200)
 
 
 def test_ncu_traffic_file_matches_the_bench_workload():
