@@ -6,14 +6,13 @@
 // and every neighbour of a tile's particle lies in the 6x6x6-cell "halo box" around it.
 //
 // A tile pass is executed by persistent CTAs (one per SM) as an asynchronous pipeline (pipe_pass below):
-//   1. producer warps draw tiles from a queue, read the 216 halo cells' particle ranges from the cell table and prefix-sum
-//      them, which defines a tile-LOCAL index space (box order: hz, hy, hx; the x-adjacent cells of a stencil row are
-//      contiguous in it);
-//   2. they copy the payload the pass gathers per neighbour (position, plus kappa / velocity / pressure acceleration / PCG
-//      direction ...) ONCE for all halo particles from HBM/L2 into a shared-memory ring (cp.async or bulk copies), several
-//      tiles ahead of the consumers;
-//   3. each consumer thread owns one particle of the tile and streams its neighbour list — 16-bit tile-local indices in a
-//      warp-blocked ELL layout, so a warp reads one 256-B block per four neighbour slots, several groups ahead of their
+//   1. a scout warp draws tiles from a queue, reads the 216 halo cells' particle ranges from the cell table and prefix-sums
+//      them, which defines a tile-LOCAL index space (box order: hz, hy, hx; see "the tile-local index space" below);
+//   2. copy warps stage the payload the pass gathers per neighbour (position, plus kappa / velocity / pressure acceleration /
+//      PCG direction ...) ONCE for all halo particles from HBM/L2 into a shared-memory ring with bulk (TMA) copies, ahead of
+//      the consumers;
+//   3. each consumer thread owns one particle of a 32-particle batch and streams its neighbour list — 16-bit tile-local
+//      indices in a warp-blocked ELL layout, so a warp reads one 256-B block per four neighbour slots, groups ahead of their
 //      use — and the per-pair coefficient stream next to it, gathering payloads from shared memory instead of through L1/L2.
 // Per pass and particle HBM sees: own fields once + 2 B (index) + 4 B (coefficient) per neighbour; neighbour fields never.
 //
@@ -242,21 +241,20 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 // tile_pass above runs  setup | stage | compute  as phases separated by __syncthreads; ncu shows the price
 // (profiles/r01_ncu_matvec_before_pipeline.txt: 36 % of the warp-stall samples at barriers, the pair loop only a third of the
 // kernel).  pipe_pass splits the CTA into roles that meet only at shared-memory mbarriers:
-//   * PIPE_PRODUCER_WARPS warps build the halo cell table of the CTA's NEXT tile and copy its payload
-//     HBM/L2 -> shared memory with cp.async (LDGSTS: no registers, no binary search — a halo row of six
-//     x-adjacent cells is three contiguous global segments), tracked by the stage's `full` mbarrier
-//     (cp.async.mbarrier.arrive.noinc);
-//   * PIPE_CONSUMER_WARPS warps own one 32-particle batch of the current tile each, gather from the
-//     stage's shared memory, and release the stage through its `empty` mbarrier.
-// A warp that finishes its batch early starts on the next tile (already resident) instead of waiting for
-// the slowest warp; the copy of tile k+2 overlaps the pair loop of tile k+1.  One CTA per SM.
-// Work assignment is static (tile -> CTA round robin, batch -> warp rotating with the running batch count), so every
-// per-thread partial sum is accumulated in the same order run after run: reductions stay bit-reproducible.
+//   * one SCOUT warp draws tiles from the queue and builds their cell tables (`table` mbarrier per stage);
+//   * PIPE_COPY_WARPS copy warps claim ring space and stage the payload HBM/L2 -> shared memory with bulk (TMA) copies, one
+//     per contiguous segment and array (a halo row of six x-adjacent cells is three contiguous global segments), tracked by
+//     the stage's `full` mbarrier (complete_tx);
+//   * the consumer warps take 32-particle batches by ticket, gather from the stage's shared memory, and release the stage
+//     through its `empty` mbarrier.
+// A warp that finishes its batch takes the CTA's oldest batch not yet started, in the same tile or the next; staging of later
+// tiles overlaps the pair loops.  One CTA per SM.  Which warp computes which batch does not matter for the result: every
+// batch's partial sums go to the batch's own slot of its tile's record, folded in a fixed order (bit-reproducible).
+// (profiles/r02_pipeline_trace.md has the timeline of one CTA before and after these roles were introduced.)
 //
 // Op interface of a pipelined pass.  All ops:  NPAY (1|2), BBYTES (16: payload B is a float4 array, 4: a float array),
 //   const float4* srcA(), const void* srcB()      global payload arrays the producers copy from
 //   float4 loadA(g), loadB(g)                     the same payload for the exact fallback path
-//   void prefetch_own(pt, b0, e0)                 optional L2 prefetch of the op's per-particle arrays (producer thread pt)
 // Pair ops (CUSTOM == false): NOWN, NSUM, COEF (bit 0: a per-pair coefficient stream is read, bit 1: one is written;
 //   both in the list's ELL layout), const float* coef_in(), float* coef_out(), load_own, pair(own, a, b, coef&, acc),
 //   finish(p, m, own, sum) — as for tile_pass.  Custom ops: particle(p, valid, acc, H), called by all 32 lanes.
@@ -275,7 +273,6 @@ __device__ __forceinline__ void tile_pass(DevState* __restrict__ S, const Arrays
 #define PIPE_PRODUCER_WARPS 4
 #endif
 #define PIPE_PRODUCER_THREADS (PIPE_PRODUCER_WARPS * 32)
-#define PIPE_CELLS_PER_THREAD ((HALO_CELLS + PIPE_PRODUCER_THREADS - 1) / PIPE_PRODUCER_THREADS)
 #define PIPE_CAP 2816          // largest halo box that is staged (larger ones take the exact global-memory path)
 // The payload ring takes whatever shared memory the pass has left (pipe_ring_slots below): how many tiles a CTA has in
 // flight — staged or being gathered — is what bounds its throughput once the consumers no longer wait for memory (a batch
@@ -461,7 +458,6 @@ __device__ __forceinline__ void l2_prefetch(const void* base, size_t byteBegin, 
     const size_t a = byteBegin & ~(size_t)15, e = (byteEnd + 15) & ~(size_t)15;
     if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(reinterpret_cast<const unsigned char*>(base) + a), "r"((uint32_t)(e - a)) : "memory");
 }
-__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(PIPE_PRODUCER_THREADS) : "memory"); }
 
 __device__ __forceinline__ uint32_t hdr_local_to_global(const StageHeader& H, uint32_t L) {
     int lo = 0, hi = HALO_CELLS;
