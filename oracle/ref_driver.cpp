@@ -26,6 +26,7 @@
 #include "Simulation/DFSPH/DFSPHImplementation.h"
 #include "Utility/SDF/SDF.cuh"
 #include "Utility/Sampler/ParticleSampler.h"
+#include "Utility/SDF/MeshDistance.h"
 #undef private
 #undef protected
 
@@ -170,6 +171,38 @@ uint32_t ref_sample_mesh_volume(const float* verts, uint32_t nv, const uint32_t*
     const uint32_t n = (uint32_t)p.size();
     for (uint32_t i = 0; i < n && i < capacity; i++) { out[3 * i] = p[i].x; out[3 * i + 1] = p[i].y; out[3 * i + 2] = p[i].z; }
     return n;
+}
+
+// Rigid body from a raw triangle mesh under a transform (what the editor does with an .obj: RigidBody.cu:10-73).
+void ref_add_mesh_body(RefSim* s, const float* verts, uint32_t nv, const uint32_t* tris, uint32_t nt, const float* transform16,
+                       int inverted, float padding, const uint32_t* res) {
+    std::vector<glm::vec3> v(nv);
+    std::vector<glm::uvec3> t(nt);
+    for (uint32_t i = 0; i < nv; i++) v[i] = { verts[3 * i], verts[3 * i + 1], verts[3 * i + 2] };
+    for (uint32_t i = 0; i < nt; i++) t[i] = { tris[3 * i], tris[3 * i + 1], tris[3 * i + 2] };
+    RigidBodyDescription rd;
+    rd.Inverted = inverted != 0;
+    rd.Padding = padding;
+    rd.CollisionMapResolution = { res[0], res[1], res[2] };
+    rd.Transform = glm::mat4(1.0f);
+    if (transform16) memcpy(&rd.Transform[0][0], transform16, 16 * sizeof(float));
+    rd.Mesh = Ref<TriangleMesh>::Create(v, t);
+    s->bodies.push_back(Ref<RigidBody>::Create(rd, s->impl->GetInfo(), s->impl->GetKernel()));
+}
+
+// MeshDistance::SignedDistance (MeshDistance.cpp:187-222) at `n` points of a raw triangle mesh under a transform, one
+// thread (the per-thread "closest face of the previous query" then evolves in point order: deterministic).
+void ref_mesh_signed_distance(const float* verts, uint32_t nv, const uint32_t* tris, uint32_t nt, const float* transform16,
+                              const float* points, uint32_t n, float* out) {
+    std::vector<glm::vec3> v(nv);
+    std::vector<glm::uvec3> t(nt);
+    glm::mat4 T(1.0f);
+    if (transform16) memcpy(&T[0][0], transform16, 16 * sizeof(float));
+    for (uint32_t i = 0; i < nv; i++) v[i] = T * glm::vec4(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2], 1.0f);
+    for (uint32_t i = 0; i < nt; i++) t[i] = { tris[3 * i], tris[3 * i + 1], tris[3 * i + 2] };
+    const Ref<EdgeMesh> mesh = Ref<EdgeMesh>::Create(v, t);
+    MeshDistance md(mesh);
+    for (uint32_t i = 0; i < n; i++) out[i] = md.SignedDistance(glm::vec3(points[3 * i], points[3 * i + 1], points[3 * i + 2]));
 }
 
 // Volume-map extraction = exactly what SDF::GetDeviceData flattens (SDF.cu:227-306).

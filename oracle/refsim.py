@@ -107,6 +107,9 @@ def _load(kind):
     if hasattr(L, "ref_sample_mesh_volume"):
         L.ref_sample_mesh_volume.restype = u32
         L.ref_sample_mesh_volume.argtypes = [vp, u32, vp, u32, vp, f32, vp, C.c_int, C.c_int, vp, u32]
+    if hasattr(L, "ref_mesh_signed_distance"):
+        L.ref_mesh_signed_distance.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp]
+        L.ref_add_mesh_body.argtypes = [vp, vp, u32, vp, u32, vp, C.c_int, f32, vp]
     L.ref_set_serial.argtypes = [C.c_int]
     L.ref_set_threads.argtypes = [C.c_int]
     L.ref_get_max_threads.restype = C.c_int
@@ -135,6 +138,23 @@ def sample_mesh_volume(verts, tris, radius, resolution=(20, 20, 20), inverted=Fa
     out = np.zeros((max(n, 1), 3), np.float32)
     L.ref_sample_mesh_volume(_p(v), len(v), _p(t), len(t), None if T is None else _p(T), float(radius), _p(r), int(inverted), int(mode), _p(out), n)
     return out[:n]
+
+
+def _mesh_args(verts, tris, transform):
+    v = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(tris, np.uint32).reshape(-1, 3)
+    T = None if transform is None else np.ascontiguousarray(np.asarray(transform, np.float32).T).reshape(16)   # row-major matrix -> glm columns
+    return v, t, T
+
+
+def mesh_signed_distance(verts, tris, points, transform=None, kind="cpu"):
+    """The reference's MeshDistance::SignedDistance (MeshDistance.cpp:187-222) of a raw triangle mesh at `points`."""
+    L = _load(kind)
+    v, t, T = _mesh_args(verts, tris, transform)
+    p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    out = np.zeros(len(p), np.float32)
+    L.ref_mesh_signed_distance(_p(v), len(v), _p(t), len(t), None if T is None else _p(T), _p(p), len(p), _p(out))
+    return out
 
 
 class quiet_stdout:
@@ -188,6 +208,13 @@ class RefSim:
         b = np.asarray(bmax, dtype=np.float32)
         r = np.asarray(res, dtype=np.uint32)
         self.L.ref_add_box_body(self.h, _p(a), _p(b), 1 if inverted else 0, float(padding), _p(r))
+        self.nbodies += 1
+
+    def add_mesh_body(self, verts, tris, transform=None, inverted=False, padding=0.0, res=(20, 20, 20)):
+        """A rigid body from a raw triangle mesh under a transform (row-major 4x4), through RigidBody::RigidBody."""
+        v, t, T = _mesh_args(verts, tris, transform)
+        r = np.asarray(res, dtype=np.uint32)
+        self.L.ref_add_mesh_body(self.h, _p(v), len(v), _p(t), len(t), None if T is None else _p(T), 1 if inverted else 0, float(padding), _p(r))
         self.nbodies += 1
 
     def commit_bodies(self):

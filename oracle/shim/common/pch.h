@@ -113,4 +113,14 @@ namespace vfd {
         mutable T* m_Instance;
     };
 }
+// MSVC-ism: the reference is written against MSVC's RAND_MAX = 32767.  BoundingSphere.h:154 forms
+// i * rand() in int before dividing by RAND_MAX; with glibc's RAND_MAX = 2^31 - 1 the product overflows, the "random
+// permutation" index goes negative and the smallest-enclosing-sphere code reads and writes outside its vertex array —
+// after which MeshDistance's sphere tree prunes the wrong branches now and then (observed: 193 078 of 200 000 queries of
+// one call wrong, the repeated call right).  Give the reference the 15-bit rand() it was written for.
+#include <cstdlib>
+static inline int vfd_ref_rand15() { return std::rand() & 0x7fff; }
+#undef RAND_MAX
+#define RAND_MAX 0x7fff
+#define rand vfd_ref_rand15
 #endif
