@@ -258,6 +258,30 @@ int  vfd_volume_map_build_box(const float bmin[3], const float bmax[3], int inve
                               const uint32_t resolution[3], float particleRadius, int device, VfdVolumeMap* out);
 void vfd_volume_map_free(VfdVolumeMap* map);
 
+/* ---- scene preparation for general triangle meshes ----
+ * A mesh is `vertexCount` vertices (3 floats each) and `triangleCount` triangles (3 vertex ids each), closed and
+ * outward-facing, under an optional column-major 4x4 transform (glm::mat4 memory order; NULL = identity) — what the editor
+ * hands to RigidBody / FluidObject after loading an .obj (TriangleMesh::GetVertices / GetTriangles).
+ *
+ * vfd_volume_map_build_mesh: RigidBody::RigidBody (RigidBody.cu:10-73) — the two-field volume map of the body, field 0 from
+ * the reference's mesh distance (MeshDistance::SignedDistance, MeshDistance.cpp:187-222; every node against every triangle on
+ * the GPU instead of a sphere-tree walk per OpenMP thread), field 1 integrated from it as for a box.
+ * vfd_mesh_signed_distance: that signed distance at `count` points (3 floats each) -> out[count].
+ * vfd_sample_mesh_volume: FluidObject::FluidObject (FluidObject.cpp:6-26) -> ParticleSampler::SampleMeshVolume
+ * (ParticleSampler.cpp:7-91): particle positions inside the mesh on the lattice of sampleMode (0 MinDensity, 1 MediumDensity,
+ * 2 MaxDensity), in the reference's order; `resolution` is the resolution of the intermediate distance grid
+ * (FluidObjectDescription::Resolution).  *positions is malloc'ed (3 floats per sample; NULL when there is none): release it
+ * with vfd_free. */
+int  vfd_volume_map_build_mesh(const float* vertices, uint32_t vertexCount, const uint32_t* triangles, uint32_t triangleCount,
+                               const float* transform16, int inverted, float padding, const uint32_t resolution[3],
+                               float particleRadius, int device, VfdVolumeMap* out);
+int  vfd_mesh_signed_distance(const float* vertices, uint32_t vertexCount, const uint32_t* triangles, uint32_t triangleCount,
+                              const float* transform16, const float* points, uint32_t count, int device, float* out);
+int  vfd_sample_mesh_volume(const float* vertices, uint32_t vertexCount, const uint32_t* triangles, uint32_t triangleCount,
+                            const float* transform16, float particleRadius, const uint32_t resolution[3], int inverted, int sampleMode,
+                            int device, float** positions, uint32_t* count);
+void vfd_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

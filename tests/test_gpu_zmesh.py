@@ -1,0 +1,146 @@
+"""Scene preparation for general triangle meshes on the GPU (csrc/volume_map.cu) against
+tests/golden/mesh.npz — outputs of the reference's own MeshDistance / SDF / ParticleSampler / RigidBody
+(tests/golden/make_golden_mesh.py) — and, last, the shape of the reference's shipped DFSPH scene (a cone of fluid above a
+slab) prepared on the GPU from meshes and stepped against the reference prepared by its own host code.
+
+The per-point arithmetic of these kernels is pinned on the CPU (tests/test_mesh_prep_cpu.py: the same host+device headers
+compiled with g++, bit for bit); what runs here for the first time is the kernels' plumbing.  (File name: sorts after the
+solver's parity tests.)"""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+R = 0.025
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(HERE, "golden", "mesh.npz"))
+
+
+@pytest.mark.parametrize("name", ["cone", "torus"])
+def test_mesh_signed_distance_matches_the_reference(lib_built, g, name):
+    from vfd_b200 import api
+    sd = api.mesh_signed_distance(g[name + "_verts"], g[name + "_tris"], g["points_" + name], transform=g[name + "_T"])
+    ref = g["sd_" + name]
+    # bit for bit: the kernels run the arithmetic the CPU test pins (IEEE sqrt and division, no contraction)
+    assert np.array_equal(sd, ref), "differ at %d of %d points, max %g" % ((sd != ref).sum(), len(ref), np.abs(sd - ref).max())
+
+
+def test_mesh_signed_distance_of_a_box_is_the_box_distance(lib_built):
+    """Independent of any fixture: against the analytic distance of a box (fp32 cancellation in the point-triangle quadratic
+    allows ~1e-6 relative to the squared lengths involved), many points in one launch, a ragged last block."""
+    import meshes
+    from vfd_b200 import api
+    lo, hi = np.array([-0.5, -0.25, -1.0]), np.array([1.5, 0.75, 0.5])
+    v, t = meshes.box(lo, hi)
+    rng = np.random.default_rng(3)
+    p = (lo - 1.0 + (hi - lo + 2.0) * rng.random((100001, 3))).astype(np.float32)
+    sd = api.mesh_signed_distance(v, t, p)
+    q = np.maximum(lo - p, p - hi)
+    exact = np.where((q > 0).any(1), np.sqrt((np.maximum(q, 0) ** 2).sum(1)), q.max(1))
+    assert np.abs(sd - exact).max() < 2e-4 and np.array_equal(np.sign(sd[np.abs(exact) > 1e-3]), np.sign(exact[np.abs(exact) > 1e-3]))
+    # many faces: more than one shared-memory chunk of triangles (a finely tessellated torus), against the coarse-mesh-free truth
+    tv, tt = meshes.torus(1.0, 0.35, 96, 48)                       # 9 216 faces
+    pt = (np.array([-1.6, -0.6, -1.6]) + np.array([3.2, 1.2, 3.2]) * rng.random((20000, 3))).astype(np.float32)
+    sdt = api.mesh_signed_distance(tv, tt, pt)
+    exact_t = np.sqrt((np.sqrt(pt[:, 0].astype(np.float64) ** 2 + pt[:, 2] ** 2) - 1.0) ** 2 + pt[:, 1] ** 2) - 0.35
+    assert np.abs(sdt - exact_t).max() < 4e-3                      # the polyhedron is inscribed: chord error 0.35 (1 - cos(pi/48)) + 1 (1 - cos(pi/96))
+
+
+@pytest.mark.parametrize("name,mesh", [("slabmap", "slab"), ("conemap", "cone")])
+def test_mesh_volume_map_matches_the_references(lib_built, g, name, mesh):
+    from vfd_b200 import api
+    vm = api.VolumeMap.build_mesh(g[mesh + "_verts"], g[mesh + "_tris"], transform=g[mesh + "_T"], inverted=False, padding=0.0,
+                                  resolution=g[name + "_resolution"], particle_radius=R)
+    n = int(g[name + "_node_count"])
+    assert vm.node_count == n and vm.field_count == 2
+    assert np.array_equal(vm.domain_min, g[name + "_domain_min"]) and np.array_equal(vm.domain_max, g[name + "_domain_max"])
+    assert np.array_equal(vm.cell_size, g[name + "_cell_size"]) and np.array_equal(vm.cell_size_inv, g[name + "_cell_size_inv"])
+    ref0, ref1 = g[name + "_nodes"][:n], g[name + "_nodes"][n:]
+    assert np.array_equal(vm.nodes[:n], ref0), "field 0 differs at %d nodes, max %g" % ((vm.nodes[:n] != ref0).sum(), np.abs(vm.nodes[:n] - ref0).max())
+    # field 1: 4 096-point quadrature summed in another order than the host's (as for the box map, test_gpu_scale.py)
+    scale = float(np.abs(ref1).max())
+    assert scale > 0 and np.abs(vm.nodes[n:] - ref1).max() <= 1e-4 * scale, np.abs(vm.nodes[n:] - ref1).max() / scale
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_mesh_volume_sampling_matches_the_references(lib_built, g, mode):
+    from vfd_b200 import api
+    got = api.sample_mesh_volume(g["cone_verts"], g["cone_tris"], R, (20, 20, 20), False, mode, transform=g["cone_T"])
+    ref = g["sample_%d" % mode]
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert np.array_equal(got, ref)
+
+
+def test_sampling_a_box_mesh_is_the_lattice_block(lib_built):
+    """No fixture: MinDensity sampling of a box whose edges are multiples of the particle diameter is the (i + 1/2) d lattice."""
+    import meshes
+    from vfd_b200 import api
+    v, t = meshes.box((0.0, 0.0, 0.0), (0.5, 0.4, 0.3))
+    got = api.sample_mesh_volume(v, t, R, (20, 20, 20), False, 0)
+    assert len(got) == 10 * 8 * 6
+    cells = np.floor(got / 0.05).astype(np.int64)
+    assert len(np.unique(cells, axis=0)) == len(got) and cells.min() >= 0 and np.all(cells.max(0) == [9, 7, 5])
+    assert np.abs(got - (cells + 0.5) * 0.05).max() < 1e-5
+    # an inverted mesh has nothing inside its bounds; a mesh with an index out of range is refused
+    assert len(api.sample_mesh_volume(v, t, R, (20, 20, 20), True, 0)) == 0
+    bad = t.copy(); bad[3, 1] = 99
+    with pytest.raises(api.VfdError):
+        api.sample_mesh_volume(v, bad, R)
+
+
+def test_cone_scene_prepared_on_the_gpu_steps_like_the_reference(lib_built, g):
+    """The reference's shipped scene in shape (default.json: a cone of fluid, MediumDensity sampling, above a non-inverted slab;
+    viscosity 10, surface tension off): sampled and mapped on the GPU from the meshes, stepped, and compared with the reference
+    prepared by its own host code (FluidObject / RigidBody) when oracle/_ref travelled.
+
+    Yardstick (measured on the reference alone, OpenMP threads against one thread): the free fall of the first 50 steps is
+    deterministic in the reference (self-deviation 0), and the viscous impact that follows stays within 5e-4 particle diameters
+    (mean) / 5e-3 (max) of itself after 150 steps.  Stated tolerances: 1e-3 d (max) after 50 steps; 0.05 d (mean), 0.5 d (max),
+    0.02 d (centre of mass) after 150 — the GPU-built map's volume field differs from the host's by up to 1e-4 of its scale."""
+    from oracle import refsim
+    from vfd_b200 import api
+    if not refsim.available("cpu") or not hasattr(refsim._load("cpu"), "ref_add_mesh_body"):
+        pytest.skip("oracle/_ref without the mesh hooks")
+    cfg = dict(EnableViscositySolver=1, EnableSurfaceTensionSolver=0, MinPressureSolverIterations=2, MaxPressureSolverIterations=2,
+               MinDivergenceSolverIterations=2, MaxDivergenceSolverIterations=2)
+    # half the cone, lower down, so that it lands within the test: its tip 0.4 above the slab's top face (y = 0.2)
+    T = g["cone_T"].copy(); T[:3, :3] *= 0.5; T[1, 3] = 1.1
+    pos = api.sample_mesh_volume(g["cone_verts"], g["cone_tris"], R, (20, 20, 20), False, 1, transform=T)
+    vm = api.VolumeMap.build_mesh(g["slab_verts"], g["slab_tris"], transform=g["slab_T"], resolution=(20, 20, 20), particle_radius=R)
+    with refsim.quiet_stdout():
+        # the reference's sampling: the most frequent of three calls (its randomised sphere tree: tests/golden/make_golden_mesh.py)
+        runs = [refsim.sample_mesh_volume(g["cone_verts"], g["cone_tris"], R, (20, 20, 20), False, 1, transform=T) for _ in range(3)]
+        rpos = max(runs, key=lambda r: sum(r.shape == q.shape and np.array_equal(r, q) for q in runs))
+        ref = refsim.RefSim(refsim.Desc(**cfg))
+        ref.set_particles(pos)
+        ref.add_mesh_body(g["slab_verts"], g["slab_tris"], transform=g["slab_T"], res=(20, 20, 20))
+        ref.commit_bodies()
+    assert 1500 < len(pos) < 4000
+    assert rpos.shape == pos.shape and np.array_equal(rpos, pos), "the GPU sampled %d particles, the reference %d" % (len(pos), len(rpos))
+    sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(FrameCount=0, **cfg))
+    sim.set_option(api.VFD_OPT_SEARCH_FMA, 0)
+    sim.SetFluidObjects([api.FluidObject(pos)])
+    sim.SetRigidBodies([vm])
+    D = 2 * R
+    for k, (steps, tol_max, tol_mean, tol_com) in enumerate([(50, 1e-3, 1e-3, 1e-3), (100, 0.5, 0.05, 0.02)]):
+        sim.steps(steps)
+        sim.synchronize()
+        with refsim.quiet_stdout():
+            ref.step(steps)
+        a, b = sim.particles()["Position"].astype(np.float64), ref.particles()["Position"].astype(np.float64)
+        assert np.isfinite(a).all()
+        d = np.sqrt(((a - b) ** 2).sum(axis=1)) / D
+        com = np.abs(a.mean(axis=0) - b.mean(axis=0)).max() / D
+        print("\n[cone scene] after %d steps: displacement vs the reference mean %.3e d, max %.3e d, centre of mass %.3e d; lowest particle %.4f (reference %.4f)"
+              % (50 + 100 * k, d.mean(), d.max(), com, a[:, 1].min(), b[:, 1].min()))
+        assert d.max() <= tol_max and d.mean() <= tol_mean and com <= tol_com, (d.max(), d.mean(), com)
+    assert a[:, 1].min() > 0.2 and b[:, 1].min() > 0.2                  # nothing sank into the slab (top face at y = 0.2)
+    assert a[:, 1].min() < 0.3                                           # and the fluid did arrive
+    sim.close()

@@ -167,6 +167,10 @@ SYMBOLS = [
     ("vfd_dfsph_elapsed_ms", _i, [_vp, _u32, _u32, C.POINTER(_f32)]),
     ("vfd_volume_map_build_box", _i, [_vp, _vp, _i, _f32, _vp, _f32, _i, C.POINTER(VfdVolumeMap)]),
     ("vfd_volume_map_free", None, [C.POINTER(VfdVolumeMap)]),
+    ("vfd_volume_map_build_mesh", _i, [_vp, _u32, _vp, _u32, _vp, _i, _f32, _vp, _f32, _i, C.POINTER(VfdVolumeMap)]),
+    ("vfd_mesh_signed_distance", _i, [_vp, _u32, _vp, _u32, _vp, _vp, _u32, _i, _vp]),
+    ("vfd_sample_mesh_volume", _i, [_vp, _u32, _vp, _u32, _vp, _f32, _vp, _i, _i, _i, C.POINTER(_vp), C.POINTER(_u32)]),
+    ("vfd_free", None, [_vp]),
 ]
 
 _lib = None
@@ -228,6 +232,21 @@ class VolumeMap:
         r = np.ascontiguousarray(resolution, np.uint32)
         m = VfdVolumeMap()
         rc = lib().vfd_volume_map_build_box(_p(a), _p(b), 1 if inverted else 0, float(padding), _p(r), float(particle_radius), int(device), C.byref(m))
+        return VolumeMap._take(rc, m)
+
+    @staticmethod
+    def build_mesh(vertices, triangles, transform=None, inverted=False, padding=0.0, resolution=(20, 20, 20), particle_radius=0.025, device=0):
+        """GPU volume-map precompute for any closed triangle mesh under a (row-major 4x4) transform — RigidBody::RigidBody
+        (RigidBody.cu:10-73) with the reference's mesh distance (MeshDistance.cpp:187-222)."""
+        v, t, T = _mesh_args(vertices, triangles, transform)
+        r = np.ascontiguousarray(resolution, np.uint32)
+        m = VfdVolumeMap()
+        rc = lib().vfd_volume_map_build_mesh(_p(v), len(v), _p(t), len(t), None if T is None else _p(T), 1 if inverted else 0, float(padding),
+                                             _p(r), float(particle_radius), int(device), C.byref(m))
+        return VolumeMap._take(rc, m)
+
+    @staticmethod
+    def _take(rc, m):
         if rc:
             raise VfdError(rc, (lib().vfd_dfsph_last_error(None) or b"").decode())
         try:
@@ -239,6 +258,42 @@ class VolumeMap:
                              m.fieldCount, m.nodeCount, m.cellCount, m.cellMapCount, nodes, cells, cmap)
         finally:
             lib().vfd_volume_map_free(C.byref(m))
+
+
+def _mesh_args(vertices, triangles, transform):
+    v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(triangles, np.uint32).reshape(-1, 3)
+    T = None if transform is None else np.ascontiguousarray(np.asarray(transform, np.float32).reshape(4, 4).T).reshape(16)   # row-major -> glm columns
+    return v, t, T
+
+
+def mesh_signed_distance(vertices, triangles, points, transform=None, device=0):
+    """MeshDistance::SignedDistance (MeshDistance.cpp:187-222) of a triangle mesh at `points`, on the GPU."""
+    v, t, T = _mesh_args(vertices, triangles, transform)
+    p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    out = np.zeros(len(p), np.float32)
+    rc = lib().vfd_mesh_signed_distance(_p(v), len(v), _p(t), len(t), None if T is None else _p(T), _p(p), len(p), int(device), _p(out))
+    if rc:
+        raise VfdError(rc, "vfd_mesh_signed_distance")
+    return out
+
+
+def sample_mesh_volume(vertices, triangles, particle_radius=0.025, resolution=(20, 20, 20), inverted=False, sample_mode=0, transform=None, device=0):
+    """FluidObject::FluidObject -> ParticleSampler::SampleMeshVolume (FluidObject.cpp:6-26, ParticleSampler.cpp:7-91) on the GPU:
+    the particle positions inside the mesh, in the reference's order."""
+    v, t, T = _mesh_args(vertices, triangles, transform)
+    r = np.ascontiguousarray(resolution, np.uint32)
+    ptr, n = C.c_void_p(), C.c_uint32(0)
+    rc = lib().vfd_sample_mesh_volume(_p(v), len(v), _p(t), len(t), None if T is None else _p(T), float(particle_radius), _p(r),
+                                      1 if inverted else 0, int(sample_mode), int(device), C.byref(ptr), C.byref(n))
+    if rc:
+        raise VfdError(rc, "vfd_sample_mesh_volume")
+    try:
+        if n.value == 0:
+            return np.zeros((0, 3), np.float32)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), (n.value * 3,)).copy().reshape(-1, 3)
+    finally:
+        lib().vfd_free(ptr)
 
 
 class FluidObject:

@@ -215,5 +215,45 @@ inline bool prepare_mesh(const float* vertices, uint32_t nv, const uint32_t* tri
     }
     return true;
 }
+// ---- the sampling lattice of ParticleSampler::SampleMeshVolume (Utility/Sampler/ParticleSampler.cpp:7-91) -----------------
+// Three nested float loops (z outermost, x innermost) over the mesh bounds; every axis is its own accumulation
+// v0, v0 + step, (v0 + step) + step, ... , so the lattice is the product of three coordinate lists (lattice_axis) and the
+// candidate at (ix, iy, iz) depends on the parities of ix and iy only (the reference's counterX / counterY).
+enum SampleMode : int { SAMPLE_MIN_DENSITY = 0, SAMPLE_MEDIUM_DENSITY = 1, SAMPLE_MAX_DENSITY = 2 };
+
+struct Lattice {
+    uint32_t nx, ny, nz;
+    int mode;
+    float radius, diameter, shiftX;
+};
+
+inline void lattice_axis(float lo, float hi, float step, std::vector<float>& out) {
+    out.clear();
+    if (!(step > 0.0f)) return;
+    for (float v = lo; v <= hi; v += step) {
+        out.push_back(v);
+        if (out.size() > (size_t)1 << 24) break;          // a degenerate step (v + step == v) would never end
+    }
+}
+
+// shiftX, shiftY of the mode (:22-31)
+inline void lattice_steps(int mode, float radius, float& stepX, float& stepY, float& stepZ) {
+    const float diameter = 2.0f * radius;
+    stepX = diameter; stepY = diameter; stepZ = diameter;
+    if (mode == SAMPLE_MEDIUM_DENSITY) stepY = sqrtf(3.0f) * radius;
+    else if (mode == SAMPLE_MAX_DENSITY) { stepX = sqrtf(3.0f) * radius; stepY = sqrtf(6.0f) * diameter / 3.0f; }
+}
+
+VFD_MESH_HD V3 lattice_position(const Lattice& L, float x, float y, float z, uint32_t ix, uint32_t iy) {
+    const float r = L.radius;
+    if (L.mode == SAMPLE_MIN_DENSITY) return v3(x + r, y + r, z + r);
+    if (L.mode == SAMPLE_MEDIUM_DENSITY) return (iy & 1u) == 0u ? v3(x, y + r, z + r) : v3(x + r, y + r, z);
+    V3 p = v3(x, y + r, z + r);
+    float sx = 0.0f, sz = 0.0f;
+    if (ix & 1u) sz += L.diameter / (2.0f * ((iy & 1u) ? -1.0f : 1.0f));
+    if (iy & 1u) { sx += L.shiftX / 2.0f; sz += L.diameter / 2.0f; }
+    return v3(p.x + sx, p.y + 0.0f, p.z + sz);
+}
+
 } // namespace meshd
 } // namespace vfd

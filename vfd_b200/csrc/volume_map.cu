@@ -1,4 +1,6 @@
-// volume_map.cu — scene preparation on the GPU: the two-field volume map of an axis-aligned box.
+// volume_map.cu — scene preparation on the GPU: the two-field volume map of a rigid body
+// (an axis-aligned box by its analytic distance, or any closed triangle mesh by the reference's mesh distance), the signed
+// distance to a mesh at arbitrary points, and the sampling of a mesh volume with particles.
 //
 // Restates RigidBody::RigidBody (reference: Simulation/DFSPH/RigidBody/RigidBody.cu:10-73) over
 // SDF::AddFunction / IndexToNodePosition (Utility/SDF/SDF.cu:45-139, :313-373) and
@@ -11,55 +13,17 @@
 // so maps built here and maps flattened from the reference's SDF are interchangeable.
 #include "solver.h"
 #include "volume_map.cuh"
+#include "mesh_distance.cuh"
+#include "map_geometry.cuh"
+#include <cfloat>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
 namespace vfd {
-
-struct MapGeom {
-    float dmin[3], dmax[3], cell[3], cellInv[3];
-    uint32_t res[3];
-    uint32_t nv, nex, ney, nez, nodeCount, cellCount;
-};
-
-// SDF::IndexToNodePosition (SDF.cu:313-373)
-__host__ __device__ inline void node_position(const MapGeom& G, uint32_t i, float out[3]) {
-    const uint32_t nx = G.res[0], ny = G.res[1], nz = G.res[2];
-    float idx[3];
-    if (i < G.nv) {
-        idx[2] = (float)(i / ((ny + 1u) * (nx + 1u)));
-        const uint32_t t = i % ((ny + 1u) * (nx + 1u));
-        idx[1] = (float)(t / (nx + 1u)); idx[0] = (float)(t % (nx + 1u));
-        for (int k = 0; k < 3; k++) out[k] = G.dmin[k] + G.cell[k] * idx[k];
-    } else if (i < G.nv + 2u * G.nex) {
-        i -= G.nv;
-        const uint32_t e = i / 2u;
-        idx[2] = (float)(e / ((ny + 1u) * nx));
-        const uint32_t t = e % ((ny + 1u) * nx);
-        idx[1] = (float)(t / nx); idx[0] = (float)(t % nx);
-        for (int k = 0; k < 3; k++) out[k] = G.dmin[k] + G.cell[k] * idx[k];
-        out[0] += (1.0f + (float)(i % 2u)) / 3.0f * G.cell[0];
-    } else if (i < G.nv + 2u * (G.nex + G.ney)) {
-        i -= G.nv + 2u * G.nex;
-        const uint32_t e = i / 2u;
-        idx[0] = (float)(e / ((nz + 1u) * ny));
-        const uint32_t t = e % ((nz + 1u) * ny);
-        idx[2] = (float)(t / ny); idx[1] = (float)(t % ny);
-        for (int k = 0; k < 3; k++) out[k] = G.dmin[k] + G.cell[k] * idx[k];
-        out[1] += (1.0f + (float)(i % 2u)) / 3.0f * G.cell[1];
-    } else {
-        i -= G.nv + 2u * (G.nex + G.ney);
-        const uint32_t e = i / 2u;
-        idx[1] = (float)(e / ((nx + 1u) * nz));
-        const uint32_t t = e % ((nx + 1u) * nz);
-        idx[0] = (float)(t / nz); idx[2] = (float)(t % nz);
-        for (int k = 0; k < 3; k++) out[k] = G.dmin[k] + G.cell[k] * idx[k];
-        out[2] += (1.0f + (float)(i % 2u)) / 3.0f * G.cell[2];
-    }
-}
 
 // field 0 at every node: signed distance to the box surface (negative inside), shifted and signed
 __global__ void k_map_sdf(MapGeom G, float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
@@ -168,42 +132,115 @@ static void gauss_legendre16(double* x, double* w) {
     }
 }
 
-static std::string g_mapError;
+// ---- general triangle meshes --------------------------------------------------------------------------------------------
+// Signed distance to a mesh at n points (map nodes when `points` is null): every thread owns one point and walks ALL faces —
+// staged MESH_CHUNK at a time in shared memory, every lane of a warp reads the same face (a broadcast) — keeping the first
+// face with the smallest squared distance; then the sign from that face's closest feature (mesh_distance.cuh).  The
+// reference prunes with a sphere tree on the host (MeshDistance.cpp:61-185); here 62 k nodes x 100 k faces is still only
+// ~6e9 point-triangle tests.
+#define MESH_CHUNK 512
+__global__ void __launch_bounds__(256) k_mesh_sdf(meshd::MeshView M, MapGeom G, const float* __restrict__ points, uint32_t n,
+                                                   float sign, float tolerance, float* __restrict__ out) {
+    __shared__ float4 sTri[3 * MESH_CHUNK];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    meshd::V3 p = meshd::v3(0.0f, 0.0f, 0.0f);
+    if (live) {
+        if (points) p = meshd::v3(points[3 * (size_t)i], points[3 * (size_t)i + 1], points[3 * (size_t)i + 2]);
+        else { float x[3]; node_position(G, i, x); p = meshd::v3(x[0], x[1], x[2]); }
+    }
+    const float4* tri4 = reinterpret_cast<const float4*>(M.tri);
+    float best = FLT_MAX;
+    uint32_t face = 0u;
+    for (uint32_t base = 0u; base < M.faceCount; base += MESH_CHUNK) {
+        const uint32_t cnt = min((uint32_t)MESH_CHUNK, M.faceCount - base);
+        __syncthreads();                                          // the previous chunk has been read by every thread
+        for (uint32_t k = threadIdx.x; k < 3u * cnt; k += blockDim.x) sTri[k] = tri4[3 * (size_t)base + k];
+        __syncthreads();
+        if (live) {
+            for (uint32_t k = 0u; k < cnt; k++) {
+                const float4 a = sTri[3u * k], b = sTri[3u * k + 1u], c = sTri[3u * k + 2u];
+                const float d2 = meshd::closest_on_triangle(p, meshd::v3(a.x, a.y, a.z), meshd::v3(b.x, b.y, b.z), meshd::v3(c.x, c.y, c.z)).d2;
+                if (d2 < best) { best = d2; face = base + k; }
+            }
+        }
+    }
+    if (live) out[i] = sign * (meshd::signed_distance_on_face(M, face, p) - tolerance);
+}
 
-} // namespace vfd
+// ParticleSampler::SampleMeshVolume (ParticleSampler.cpp:33-87): lattice candidate idx = (iz ny + iy) nx + ix is a sample where
+// the interpolated signed distance is negative.  Pass 1 flags the candidates and counts them per block; the host turns the
+// counts into offsets; pass 2 writes the samples in lattice order (the reference's push_back order).
+__device__ __forceinline__ meshd::V3 sample_candidate(const meshd::Lattice& L, const float* __restrict__ xs, const float* __restrict__ ys,
+                                                      const float* __restrict__ zs, uint64_t idx) {
+    const uint32_t ix = (uint32_t)(idx % L.nx), iy = (uint32_t)((idx / L.nx) % L.ny), iz = (uint32_t)(idx / ((uint64_t)L.nx * L.ny));
+    return meshd::lattice_position(L, xs[ix], ys[iy], zs[iz], ix, iy);
+}
 
-using namespace vfd;
+__global__ void __launch_bounds__(256) k_sample_flag(meshd::Lattice L, const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ zs,
+                                                      MapGeom G, const float* __restrict__ nodes0, const uint32_t* __restrict__ cells, uint64_t total,
+                                                      unsigned char* __restrict__ flags, uint32_t* __restrict__ blockCounts) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int inside = 0;
+    if (idx < total) {
+        const meshd::V3 p = sample_candidate(L, xs, ys, zs, idx);
+        inside = map_phi(G, nodes0, cells, f3(p.x, p.y, p.z)) < 0.0f ? 1 : 0;          // SDF::GetDistance(p, 0) < 0 (FLT_MAX outside the grid)
+        flags[idx] = (unsigned char)inside;
+    }
+    const int c = __syncthreads_count(inside);
+    if (threadIdx.x == 0) blockCounts[blockIdx.x] = (uint32_t)c;
+}
 
-extern "C" int vfd_volume_map_build_box(const float bmin[3], const float bmax[3], int inverted, float padding,
-                                        const uint32_t resolution[3], float particleRadius, int device, VfdVolumeMap* out) {
-    if (!bmin || !bmax || !resolution || !out) return VFD_E_INVALID;
-    memset(out, 0, sizeof *out);
+__global__ void __launch_bounds__(256) k_sample_write(meshd::Lattice L, const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ zs,
+                                                       uint64_t total, const unsigned char* __restrict__ flags, const uint64_t* __restrict__ blockOffsets,
+                                                       float* __restrict__ out) {
+    __shared__ uint32_t warpBase[8];
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool inside = idx < total && flags[idx] != 0;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, inside);
+    if (lane == 0u) warpBase[warp] = (uint32_t)__popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0u; for (int w = 0; w < 8; w++) { const uint32_t c = warpBase[w]; warpBase[w] = run; run += c; } }
+    __syncthreads();
+    if (inside) {
+        const uint64_t slot = blockOffsets[blockIdx.x] + warpBase[warp] + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+        const meshd::V3 p = sample_candidate(L, xs, ys, zs, idx);
+        out[3 * slot] = p.x; out[3 * slot + 1] = p.y; out[3 * slot + 2] = p.z;
+    }
+}
+
+// a prepared mesh in device memory
+struct MeshDev {
+    meshd::MeshView view;
+    void* mem[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaError_t upload(const meshd::MeshHost& H) {
+        const void* src[5] = { H.tri.data(), H.faceNormal.data(), H.vertNormal.data(), H.corner.data(), H.across.data() };
+        const size_t bytes[5] = { H.tri.size() * 4, H.faceNormal.size() * 4, H.vertNormal.size() * 4, H.corner.size() * 4, H.across.size() * 4 };
+        for (int k = 0; k < 5; k++) {
+            cudaError_t e = cudaMalloc(&mem[k], bytes[k] ? bytes[k] : 16);
+            if (e == cudaSuccess && bytes[k]) e = cudaMemcpy(mem[k], src[k], bytes[k], cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return e;
+        }
+        view.tri = (const float*)mem[0]; view.faceNormal = (const float*)mem[1]; view.vertNormal = (const float*)mem[2];
+        view.corner = (const uint32_t*)mem[3]; view.across = (const int32_t*)mem[4];
+        view.faceCount = H.faceCount; view.vertexCount = H.vertexCount;
+        return cudaSuccess;
+    }
+    ~MeshDev() { for (int k = 0; k < 5; k++) if (mem[k]) cudaFree(mem[k]); }
+};
+
+static int pick_device(int device) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) { cudaGetLastError(); return VFD_E_CUDA; }
     if (cudaSetDevice(device) != cudaSuccess) return VFD_E_CUDA;
-    for (int k = 0; k < 3; k++) if (resolution[k] == 0 || resolution[k] > 1024 || !(bmax[k] > bmin[k])) return VFD_E_INVALID;
+    return VFD_OK;
+}
 
-    const float h = 4.0f * particleRadius;
-    const float tolerance = padding - particleRadius;
-    const float sign = inverted ? -1.0f : 1.0f;
-    MapGeom G;
-    // BoundingBox(vertices) starts from min = max = 0, i.e. always contains the origin
-    for (int k = 0; k < 3; k++) {
-        const float lo = fminf(0.0f, bmin[k]), hi = fmaxf(0.0f, bmax[k]);
-        G.dmax[k] = hi + (8.0f * h + tolerance);
-        G.dmin[k] = lo - (8.0f * h + tolerance);
-        G.res[k] = resolution[k];
-        G.cell[k] = (G.dmax[k] - G.dmin[k]) / (float)resolution[k];
-        G.cellInv[k] = 1.0f / G.cell[k];
-    }
+// cell -> node table (SDF.cu:81-131)
+static void map_cell_table(const MapGeom& G, std::vector<uint32_t>& cells) {
     const uint32_t nx = G.res[0], ny = G.res[1], nz = G.res[2];
-    G.nv = (nx + 1) * (ny + 1) * (nz + 1);
-    G.nex = nx * (ny + 1) * (nz + 1); G.ney = (nx + 1) * ny * (nz + 1); G.nez = (nx + 1) * (ny + 1) * nz;
-    G.nodeCount = G.nv + 2 * (G.nex + G.ney + G.nez);
-    G.cellCount = nx * ny * nz;
-
-    // cell -> node table (SDF.cu:81-131)
-    std::vector<uint32_t> cells((size_t)G.cellCount * 32);
+    cells.resize((size_t)G.cellCount * 32);
     for (uint32_t l = 0; l < G.cellCount; l++) {
         const uint32_t k = l / (ny * nx), t = l % (ny * nx), j = t / nx, i = t % nx;
         uint32_t* c = &cells[(size_t)l * 32];
@@ -215,7 +252,13 @@ extern "C" int vfd_volume_map_build_box(const float bmin[3], const float bmax[3]
         off += 2 * G.ney;
         for (uint32_t b = 0; b < 4; b++) { const uint32_t by = b & 1, bx = (b >> 1) & 1; c[24 + 2 * b] = off + 2 * (nz * (nx + 1) * (j + by) + nz * (i + bx) + k); c[25 + 2 * b] = c[24 + 2 * b] + 1; }
     }
+}
 
+// The two-field map over G: `field0` launches the kernel that fills field 0 at every node (device array), field 1 is
+// integrated from it; both come back in malloc'ed host arrays (vfd_volume_map_free).
+static int build_two_field_map(const MapGeom& G, float h, const std::function<cudaError_t(float*)>& field0, VfdVolumeMap* out) {
+    std::vector<uint32_t> cells;
+    map_cell_table(G, cells);
     KernelTables T;
     T.build(h);
     double gx[16], gw[16];
@@ -229,8 +272,8 @@ extern "C" int vfd_volume_map_build_box(const float bmin[3], const float bmax[3]
     if (e == cudaSuccess) e = cudaMalloc(&dW, VFD_LUT_RES * 4);
     if (e == cudaSuccess) e = cudaMemcpy(dC, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(dW, T.Wc.data(), VFD_LUT_RES * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = field0(dN0);
     if (e == cudaSuccess) {
-        k_map_sdf<<<(G.nodeCount + 255) / 256, 256>>>(G, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], sign, tolerance, dN0);
         const uint64_t threads = (uint64_t)G.nodeCount * 32;
         k_map_volume<<<(uint32_t)((threads + 255) / 256), 256>>>(G, Q, dN0, dC, dW, T.invStep, T.wZero, h, dN1);
         e = cudaDeviceSynchronize();
@@ -253,6 +296,168 @@ extern "C" int vfd_volume_map_build_box(const float bmin[3], const float bmax[3]
     out->nodes = nodes; out->cells = cellsOut; out->cellMap = cmap;
     return VFD_OK;
 }
+
+static bool resolution_ok(const uint32_t resolution[3]) {
+    for (int k = 0; k < 3; k++) if (resolution[k] == 0 || resolution[k] > 1024) return false;
+    return true;
+}
+
+} // namespace vfd
+
+using namespace vfd;
+
+extern "C" int vfd_volume_map_build_box(const float bmin[3], const float bmax[3], int inverted, float padding,
+                                        const uint32_t resolution[3], float particleRadius, int device, VfdVolumeMap* out) {
+    if (!bmin || !bmax || !resolution || !out) return VFD_E_INVALID;
+    memset(out, 0, sizeof *out);
+    if (int rc = pick_device(device)) return rc;
+    if (!resolution_ok(resolution)) return VFD_E_INVALID;
+    for (int k = 0; k < 3; k++) if (!(bmax[k] > bmin[k])) return VFD_E_INVALID;
+
+    const float h = 4.0f * particleRadius;
+    const float tolerance = padding - particleRadius;
+    const float sign = inverted ? -1.0f : 1.0f;
+    MapGeom G;
+    body_map_geometry(bmin, bmax, h, tolerance, resolution, G);
+    return build_two_field_map(G, h, [&](float* dN0) -> cudaError_t {
+        k_map_sdf<<<(G.nodeCount + 255) / 256, 256>>>(G, bmin[0], bmin[1], bmin[2], bmax[0], bmax[1], bmax[2], sign, tolerance, dN0);
+        return cudaGetLastError();
+    }, out);
+}
+
+// RigidBody::RigidBody for any closed triangle mesh (RigidBody.cu:10-73): vertices under the body's transform, the map
+// domain from their bounds, field 0 = sign (d_mesh(x) - (padding - r)) with the reference's mesh distance.
+extern "C" int vfd_volume_map_build_mesh(const float* vertices, uint32_t vertexCount, const uint32_t* triangles, uint32_t triangleCount,
+                                         const float* transform16, int inverted, float padding, const uint32_t resolution[3],
+                                         float particleRadius, int device, VfdVolumeMap* out) {
+    if (!vertices || !triangles || !resolution || !out || vertexCount == 0 || triangleCount == 0) return VFD_E_INVALID;
+    memset(out, 0, sizeof *out);
+    if (int rc = pick_device(device)) return rc;
+    if (!resolution_ok(resolution)) return VFD_E_INVALID;
+    meshd::MeshHost H;
+    if (!meshd::prepare_mesh(vertices, vertexCount, triangles, triangleCount, transform16, H)) return VFD_E_INVALID;
+
+    const float h = 4.0f * particleRadius;
+    const float tolerance = padding - particleRadius;
+    const float sign = inverted ? -1.0f : 1.0f;
+    MapGeom G;
+    body_map_geometry(H.lo, H.hi, h, tolerance, resolution, G);
+    MeshDev D;
+    if (D.upload(H) != cudaSuccess) { cudaGetLastError(); return VFD_E_CUDA; }
+    return build_two_field_map(G, h, [&](float* dN0) -> cudaError_t {
+        k_mesh_sdf<<<(G.nodeCount + 255) / 256, 256>>>(D.view, G, nullptr, G.nodeCount, sign, tolerance, dN0);
+        return cudaGetLastError();
+    }, out);
+}
+
+// MeshDistance::SignedDistance (MeshDistance.cpp:187-222) at `count` points
+extern "C" int vfd_mesh_signed_distance(const float* vertices, uint32_t vertexCount, const uint32_t* triangles, uint32_t triangleCount,
+                                        const float* transform16, const float* points, uint32_t count, int device, float* out) {
+    if (!vertices || !triangles || vertexCount == 0 || triangleCount == 0 || (count && (!points || !out))) return VFD_E_INVALID;
+    if (int rc = pick_device(device)) return rc;
+    if (count == 0) return VFD_OK;
+    meshd::MeshHost H;
+    if (!meshd::prepare_mesh(vertices, vertexCount, triangles, triangleCount, transform16, H)) return VFD_E_INVALID;
+    MeshDev D;
+    float *dP = nullptr, *dO = nullptr;
+    cudaError_t e = D.upload(H);
+    if (e == cudaSuccess) e = cudaMalloc(&dP, (size_t)count * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&dO, (size_t)count * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(dP, points, (size_t)count * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        MapGeom G;
+        memset(&G, 0, sizeof G);
+        k_mesh_sdf<<<(count + 255) / 256, 256>>>(D.view, G, dP, count, 1.0f, 0.0f, dO);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dO, (size_t)count * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dP); cudaFree(dO);
+    if (e != cudaSuccess) { cudaGetLastError(); return VFD_E_CUDA; }
+    return VFD_OK;
+}
+
+// FluidObject::FluidObject (FluidObject.cpp:6-26) -> ParticleSampler::SampleMeshVolume (ParticleSampler.cpp:7-91): the
+// mesh under the object's transform, a signed-distance grid over its bounds (SDF::SDF(mesh, bounds, resolution, inverted),
+// SDF.cu:16-37), the lattice of the sample mode, a sample wherever the interpolated distance is negative.
+extern "C" int vfd_sample_mesh_volume(const float* vertices, uint32_t vertexCount, const uint32_t* triangles, uint32_t triangleCount,
+                                      const float* transform16, float particleRadius, const uint32_t resolution[3], int inverted, int sampleMode,
+                                      int device, float** positions, uint32_t* count) {
+    if (!vertices || !triangles || !resolution || !positions || !count || vertexCount == 0 || triangleCount == 0) return VFD_E_INVALID;
+    *positions = nullptr; *count = 0;
+    if (sampleMode < 0 || sampleMode > 2 || !(particleRadius > 0.0f)) return VFD_E_INVALID;
+    if (int rc = pick_device(device)) return rc;
+    if (!resolution_ok(resolution)) return VFD_E_INVALID;
+    meshd::MeshHost H;
+    if (!meshd::prepare_mesh(vertices, vertexCount, triangles, triangleCount, transform16, H)) return VFD_E_INVALID;
+
+    MapGeom G;
+    sampler_grid_geometry(H.lo, H.hi, resolution, G);
+    std::vector<uint32_t> cells;
+    map_cell_table(G, cells);
+
+    // the lattice over the ORIGINAL bounds (ParticleSampler.cpp:33-35)
+    meshd::Lattice L;
+    float stepX, stepY, stepZ;
+    meshd::lattice_steps(sampleMode, particleRadius, stepX, stepY, stepZ);
+    std::vector<float> xs, ys, zs;
+    meshd::lattice_axis(H.lo[0], H.hi[0], stepX, xs);
+    meshd::lattice_axis(H.lo[1], H.hi[1], stepY, ys);
+    meshd::lattice_axis(H.lo[2], H.hi[2], stepZ, zs);
+    L.nx = (uint32_t)xs.size(); L.ny = (uint32_t)ys.size(); L.nz = (uint32_t)zs.size();
+    L.mode = sampleMode; L.radius = particleRadius; L.diameter = 2.0f * particleRadius; L.shiftX = stepX;
+    const uint64_t total = (uint64_t)L.nx * L.ny * L.nz;
+    if (total == 0) return VFD_OK;
+    if (total > (1ull << 32)) return VFD_E_CAPACITY;
+    const uint32_t blocks = (uint32_t)((total + 255) / 256);
+
+    MeshDev D;
+    float *dN0 = nullptr, *dX = nullptr, *dY = nullptr, *dZ = nullptr, *dOut = nullptr;
+    uint32_t *dC = nullptr, *dCounts = nullptr; uint64_t* dOffsets = nullptr; unsigned char* dFlags = nullptr;
+    std::vector<uint32_t> counts(blocks);
+    std::vector<uint64_t> offsets(blocks);
+    uint64_t kept = 0;
+    float* host = nullptr;
+    cudaError_t e = D.upload(H);
+    if (e == cudaSuccess) e = cudaMalloc(&dN0, (size_t)G.nodeCount * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dC, cells.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dX, xs.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dY, ys.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dZ, zs.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dFlags, (size_t)total);
+    if (e == cudaSuccess) e = cudaMalloc(&dCounts, (size_t)blocks * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dOffsets, (size_t)blocks * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(dC, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dX, xs.data(), xs.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dY, ys.data(), ys.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dZ, zs.data(), zs.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const float factor = inverted ? -1.0f : 1.0f;
+        k_mesh_sdf<<<(G.nodeCount + 255) / 256, 256>>>(D.view, G, nullptr, G.nodeCount, factor, 0.0f, dN0);
+        k_sample_flag<<<blocks, 256>>>(L, dX, dY, dZ, G, dN0, dC, total, dFlags, dCounts);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(counts.data(), dCounts, (size_t)blocks * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) {
+        for (uint32_t b = 0; b < blocks; b++) { offsets[b] = kept; kept += counts[b]; }
+        if (kept > 0xffffffffull) e = cudaErrorInvalidValue;
+    }
+    if (e == cudaSuccess && kept) {
+        e = cudaMemcpy(dOffsets, offsets.data(), (size_t)blocks * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&dOut, (size_t)kept * 12);
+        if (e == cudaSuccess) {
+            k_sample_write<<<blocks, 256>>>(L, dX, dY, dZ, total, dFlags, dOffsets, dOut);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) { host = (float*)malloc((size_t)kept * 12); if (!host) e = cudaErrorMemoryAllocation; }
+        if (e == cudaSuccess) e = cudaMemcpy(host, dOut, (size_t)kept * 12, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dN0); cudaFree(dC); cudaFree(dX); cudaFree(dY); cudaFree(dZ); cudaFree(dFlags); cudaFree(dCounts); cudaFree(dOffsets); cudaFree(dOut);
+    if (e != cudaSuccess) { free(host); cudaGetLastError(); return VFD_E_CUDA; }
+    *positions = host; *count = (uint32_t)kept;
+    return VFD_OK;
+}
+
+extern "C" void vfd_free(void* p) { free(p); }
 
 extern "C" void vfd_volume_map_free(VfdVolumeMap* m) {
     if (!m) return;

@@ -12,9 +12,11 @@
   lattice points lie ON the faces, where the reference's answer is decided by the interpolation error of its 20^3 SDF grid:
   it keeps some points on (or up to 2e-3 outside) the surface that the exact test drops — tests/test_scene_io_cpu.py
   states that tolerance.
-* `build_simulation(scene)` turns a scene whose meshes are axis-aligned boxes (the unit `Cube.obj` under a scale /
-  translation transform) into a ready `api.DFSPHSimulation`: fluid blocks sampled here, rigid bodies as volume maps
-  integrated on the GPU (csrc/volume_map.cu).  Other meshes need the mesh distance field, which stays reference code.
+* `read_obj(path)` reads the vertices and triangles the reference's loaders take from an .obj file.
+* `build_simulation(scene)` turns a scene into a ready `api.DFSPHSimulation` the way the editor's "Bake Objects" does: every
+  fluid object's mesh sampled with particles, every rigid body's mesh turned into a volume map — any closed triangle mesh
+  under any transform, on the GPU (csrc/volume_map.cu: the reference's mesh distance, sampling lattice and map quadrature).
+  `sample_box_volume` stays as a host-side statement of the sampling lattice for boxes (tests).
 """
 import json
 import os
@@ -259,8 +261,38 @@ def sample_box_volume(bmin, bmax, radius, mode=MIN_DENSITY, inverted=False):
     return P[dist < 0.0]
 
 
-def build_simulation(scene, device=0, resources_root=None, **overrides):
-    """A ready `DFSPHSimulation` for a scene whose meshes are unit cubes under scale/translation transforms."""
+def read_obj(path):
+    """The (vertices, triangles) the reference's loaders take from an .obj file (TriangleMesh::LoadOBJ, Renderer/Mesh/
+    TriangleMesh.cpp:39-107; EdgeMesh.cpp:62-100, both through tinyobjloader): every `v` line in file order, every `f` line as
+    vertex indices (1-based, negative = relative to the vertices read so far; texture / normal indices ignored), polygons
+    with more than three corners fan-triangulated around their first corner."""
+    verts, tris = [], []
+    with open(path) as f:
+        for line in f:
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == "v":
+                verts.append([float(t[1]), float(t[2]), float(t[3])])
+            elif t[0] == "f":
+                ids = []
+                for c in t[1:]:
+                    k = int(c.split("/")[0])
+                    ids.append(k - 1 if k > 0 else len(verts) + k)
+                for j in range(1, len(ids) - 1):
+                    tris.append([ids[0], ids[j], ids[j + 1]])
+    return np.array(verts, np.float32).reshape(-1, 3), np.array(tris, np.uint32).reshape(-1, 3)
+
+
+def build_simulation(scene, device=0, resources_root=None, meshes=None, **overrides):
+    """A ready `DFSPHSimulation` for a scene as `read_scene` returns it — what the editor's "Bake Objects" does
+    (SURVEY.md section 3.1): every fluid object's mesh under its transform is sampled with particles, every rigid body's mesh
+    becomes a volume map, both on the GPU (csrc/volume_map.cu: vfd_sample_mesh_volume, vfd_volume_map_build_mesh — the
+    reference's mesh distance, sampling lattice and map integration).
+
+    Meshes are looked up in `meshes` ({mesh source or its file name: (vertices, triangles)}) and otherwise read from
+    `resources_root`/<mesh source> with `read_obj`.  Without either, the unit cube (Cube.obj spans [-1, 1]^3) is the only
+    mesh known by name."""
     from . import api
     desc = dict(scene["description"] or {})
     desc.update(overrides)
@@ -270,22 +302,31 @@ def build_simulation(scene, device=0, resources_root=None, **overrides):
     sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(**desc), device=device)
     radius = float(desc.get("ParticleRadius", 0.025))
 
-    def box_of(obj):
-        if not obj.get("mesh") or os.path.basename(obj["mesh"]).lower() != "cube.obj":
-            raise NotImplementedError("mesh %r: only the unit cube is sampled here (mesh distance fields stay reference code)" % obj.get("mesh"))
-        b = unit_cube_box(obj["transform"])
-        if b is None:
-            raise NotImplementedError("rotated or sheared cube: not an axis-aligned box")
-        return b
+    def mesh_of(obj):
+        src = obj.get("mesh") or ""
+        for key in (src, os.path.basename(src)):
+            if meshes and key in meshes:
+                return meshes[key]
+        if resources_root and src and os.path.exists(os.path.join(resources_root, src)):
+            return read_obj(os.path.join(resources_root, src))
+        if os.path.basename(src).lower() == "cube.obj":
+            return UNIT_CUBE
+        raise FileNotFoundError("mesh %r: pass it in `meshes` or give `resources_root`" % src)
     fluids = []
     for fo in scene["fluid_objects"]:
-        lo, hi = box_of(fo)
-        fluids.append(api.FluidObject(sample_box_volume(lo, hi, radius, fo["sample_mode"], fo["inverted"]), velocity=fo["velocity"]))
+        v, t = mesh_of(fo)
+        pos = api.sample_mesh_volume(v, t, radius, fo["resolution"], fo["inverted"], fo["sample_mode"], transform=fo["transform"], device=device)
+        fluids.append(api.FluidObject(pos, velocity=fo["velocity"]))
     sim.SetFluidObjects(fluids)
     maps = []
     for rb in scene["rigid_bodies"]:
-        lo, hi = box_of(rb)
-        maps.append(api.VolumeMap.build_box(lo, hi, inverted=rb["inverted"], padding=rb["padding"], resolution=rb["resolution"],
-                                            particle_radius=radius, device=device))
+        v, t = mesh_of(rb)
+        maps.append(api.VolumeMap.build_mesh(v, t, transform=rb["transform"], inverted=rb["inverted"], padding=rb["padding"],
+                                             resolution=rb["resolution"], particle_radius=radius, device=device))
     sim.SetRigidBodies(maps)
     return sim
+
+
+# the reference's TriangleMesh(AABB) topology (TriangleMesh.cpp:18-37) on [-1, 1]^3
+UNIT_CUBE = (np.array([[-1, -1, -1], [1, -1, -1], [1, -1, 1], [-1, -1, 1], [-1, 1, -1], [1, 1, -1], [1, 1, 1], [-1, 1, 1]], np.float32),
+             np.array([[0, 1, 2], [0, 2, 3], [4, 7, 6], [4, 6, 5], [0, 3, 7], [0, 7, 4], [1, 5, 6], [1, 6, 2], [0, 4, 5], [0, 5, 1], [3, 2, 6], [3, 6, 7]], np.uint32))
