@@ -9,7 +9,8 @@ upside down above a flat slab — with procedural meshes of tests/meshes.py, not
   cone_*, slab_*          vertices, triangles, row-major 4x4 transforms
   points, sd_cone, sd_torus   query points and MeshDistance::SignedDistance there (torus: 576 faces under a general transform)
   sample_<mode>           ParticleSampler::SampleMeshVolume of the cone (radius 0.025, distance grid 20^3), modes 0 1 2
-  slabmap_*, conemap_*    RigidBody volume maps (field 0 and 1) of the slab (20^3) and of the cone as a body (12^3)
+  slabmap_*, conemap_*, oddmap_*   RigidBody volume maps (field 0 and 1) of the slab (20^3), of the cone as a body (12^3) and of
+                          the torus on a non-cubic grid (5 x 9 x 7: the node numbering's axis order)
 
 Every reference output is the MODAL result of RUNS consecutive calls.  The reference's MeshDistance prunes its search with a
 sphere tree whose spheres come from a randomised smallest-enclosing-sphere routine (Core/Structures/BoundingSphere.h:133-172,
@@ -83,7 +84,7 @@ def main():
         out["sample_%d" % mode] = modal(lambda: refsim.sample_mesh_volume(cv, ct, RADIUS, (20, 20, 20), False, mode, transform=cT))
         print("mode", mode, len(out["sample_%d" % mode]), "samples")
 
-    for name, (v, t, T, res) in {"slabmap": (sv, st, sT, (20, 20, 20)), "conemap": (cv, ct, cT, (12, 12, 12))}.items():
+    for name, (v, t, T, res) in {"slabmap": (sv, st, sT, (20, 20, 20)), "conemap": (cv, ct, cT, (12, 12, 12)), "oddmap": (tv, tt, tT, (5, 9, 7))}.items():
         with refsim.quiet_stdout():
             m = body_map(v, t, T, res)
             m["nodes"] = modal(lambda: body_map(v, t, T, res)["nodes"])

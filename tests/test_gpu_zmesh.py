@@ -54,7 +54,7 @@ def test_mesh_signed_distance_of_a_box_is_the_box_distance(lib_built):
     assert np.abs(sdt - exact_t).max() < 4e-3                      # the polyhedron is inscribed: chord error 0.35 (1 - cos(pi/48)) + 1 (1 - cos(pi/96))
 
 
-@pytest.mark.parametrize("name,mesh", [("slabmap", "slab"), ("conemap", "cone")])
+@pytest.mark.parametrize("name,mesh", [("slabmap", "slab"), ("conemap", "cone"), ("oddmap", "torus")])
 def test_mesh_volume_map_matches_the_references(lib_built, g, name, mesh):
     from vfd_b200 import api
     vm = api.VolumeMap.build_mesh(g[mesh + "_verts"], g[mesh + "_tris"], transform=g[mesh + "_T"], inverted=False, padding=0.0,

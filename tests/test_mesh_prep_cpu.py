@@ -96,7 +96,7 @@ def body_field0(hc, v, t, T, res, inverted=False, padding=0.0):
     return geom, nodes
 
 
-@pytest.mark.parametrize("name,mesh", [("slabmap", "slab"), ("conemap", "cone")])
+@pytest.mark.parametrize("name,mesh", [("slabmap", "slab"), ("conemap", "cone"), ("oddmap", "torus")])
 def test_body_map_grid_and_distance_field_are_the_references(hc, g, name, mesh):
     geom, nodes = body_field0(hc, g[mesh + "_verts"], g[mesh + "_tris"], g[mesh + "_T"], g[name + "_resolution"])
     assert np.array_equal(geom[0:3], g[name + "_domain_min"]) and np.array_equal(geom[3:6], g[name + "_domain_max"])

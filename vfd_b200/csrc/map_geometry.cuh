@@ -19,40 +19,30 @@ struct MapGeom {
     uint32_t nv, nex, ney, nez, nodeCount, cellCount;
 };
 
-// SDF::IndexToNodePosition (SDF.cu:313-373)
+// Position of node i (the numbering SDF::IndexToNodePosition decodes, SDF.cu:313-373 — it is the interchange format of the
+// map, so the arithmetic is the reference's).  Nodes come in four groups: the (nx+1)(ny+1)(nz+1) cell corners, x fastest;
+// then for each axis a = x, y, z the two interior nodes (at 1/3 and 2/3) of every cell edge along a.  The edges along a are
+// numbered with the coordinate along a fastest (res[a] values), then axis a+1 (res+1 values), then axis a+2.
 VFD_GEOM_HD void node_position(const MapGeom& G, uint32_t i, float out[3]) {
-    const uint32_t nx = G.res[0], ny = G.res[1], nz = G.res[2];
-    float idx[3];
+    uint32_t digit[3];
+    int along = -1;                 // corner nodes: no edge
+    uint32_t third = 0u;            // 0: the node at 1/3 of its edge, 1: at 2/3
     if (i < G.nv) {
-        idx[2] = (float)(i / ((ny + 1u) * (nx + 1u)));
-        const uint32_t t = i % ((ny + 1u) * (nx + 1u));
-        idx[1] = (float)(t / (nx + 1u)); idx[0] = (float)(t % (nx + 1u));
-        for (int k = 0; k < 3; k++) out[k] = G.dmin[k] + G.cell[k] * idx[k];
-    } else if (i < G.nv + 2u * G.nex) {
-        i -= G.nv;
-        const uint32_t e = i / 2u;
-        idx[2] = (float)(e / ((ny + 1u) * nx));
-        const uint32_t t = e % ((ny + 1u) * nx);
-        idx[1] = (float)(t / nx); idx[0] = (float)(t % nx);
-        for (int k = 0; k < 3; k++) out[k] = G.dmin[k] + G.cell[k] * idx[k];
-        out[0] += (1.0f + (float)(i % 2u)) / 3.0f * G.cell[0];
-    } else if (i < G.nv + 2u * (G.nex + G.ney)) {
-        i -= G.nv + 2u * G.nex;
-        const uint32_t e = i / 2u;
-        idx[0] = (float)(e / ((nz + 1u) * ny));
-        const uint32_t t = e % ((nz + 1u) * ny);
-        idx[2] = (float)(t / ny); idx[1] = (float)(t % ny);
-        for (int k = 0; k < 3; k++) out[k] = G.dmin[k] + G.cell[k] * idx[k];
-        out[1] += (1.0f + (float)(i % 2u)) / 3.0f * G.cell[1];
+        const uint32_t ex = G.res[0] + 1u, ey = G.res[1] + 1u;
+        digit[0] = i % ex; digit[1] = (i / ex) % ey; digit[2] = i / (ex * ey);
     } else {
-        i -= G.nv + 2u * (G.nex + G.ney);
-        const uint32_t e = i / 2u;
-        idx[1] = (float)(e / ((nx + 1u) * nz));
-        const uint32_t t = e % ((nx + 1u) * nz);
-        idx[0] = (float)(t / nz); idx[2] = (float)(t % nz);
-        for (int k = 0; k < 3; k++) out[k] = G.dmin[k] + G.cell[k] * idx[k];
-        out[2] += (1.0f + (float)(i % 2u)) / 3.0f * G.cell[2];
+        uint32_t r = i - G.nv;
+        const uint32_t perAxis[3] = { 2u * G.nex, 2u * G.ney, 2u * G.nez };
+        along = 0;
+        while (along < 2 && r >= perAxis[along]) { r -= perAxis[along]; along++; }
+        third = r & 1u;
+        const uint32_t e = r >> 1;
+        const int f = along, m = (along + 1) % 3, s = (along + 2) % 3;
+        const uint32_t ef = G.res[f], em = G.res[m] + 1u;
+        digit[f] = e % ef; digit[m] = (e / ef) % em; digit[s] = e / (ef * em);
     }
+    for (int k = 0; k < 3; k++) out[k] = G.dmin[k] + G.cell[k] * (float)digit[k];
+    if (along >= 0) out[along] += (1.0f + (float)third) / 3.0f * G.cell[along];
 }
 
 // cell sizes and node counts of a grid whose domain (dmin, dmax) is set (SDF::SDF, SDF.cu:8-14; AddFunction :47-56)
