@@ -126,3 +126,31 @@ def test_writer_emits_the_loaders_pool_sequence(tmp_path):
         assert kw == kr, name
     s = scene_io.read_scene(p)
     assert s["description"]["FrameCount"] == 3 and s["description"]["Viscosity"] == 10.0
+
+
+def test_obj_reader_takes_what_the_references_loaders_take(tmp_path):
+    from vfd_b200 import scene_io
+    """`v` lines in file order; `f` lines as vertex indices whatever their v/vt/vn form, 1-based or negative (relative), polygons
+    fan-triangulated around their first corner (TriangleMesh.cpp:39-107 / EdgeMesh.cpp:62-100 through tinyobjloader)."""
+    p = tmp_path / "m.obj"
+    p.write_text("# comment\no Thing\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nvt 0 0\ns off\n"
+                 "f 1//1 2//1 3//1\nf 1/1/1 3/1/1 4/1/1\nv 0.5 0.5 1\nf -1 1 2\nf 1 2 3 4\n")
+    v, t = scene_io.read_obj(str(p))
+    assert v.dtype == np.float32 and v.shape == (5, 3) and np.array_equal(v[4], [0.5, 0.5, 1.0])
+    assert t.dtype == np.uint32 and t.tolist() == [[0, 1, 2], [0, 2, 3], [4, 0, 1], [0, 1, 2], [0, 2, 3]]
+
+
+def test_obj_reader_on_the_references_cone():
+    """The cone of the reference's shipped DFSPH scene, when the reference tree is present: 33 vertices, 62 triangles, closed
+    (every edge shared by exactly two triangles, once in each direction) — what the mesh-distance sign needs."""
+    from vfd_b200 import scene_io
+    path = "/root/reference/VFD/Resources/Models/Cone.obj"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    v, t = scene_io.read_obj(path)
+    assert v.shape == (33, 3) and t.shape == (62, 3)
+    half = {}
+    for a, b, c in t.tolist():
+        for e in ((a, b), (b, c), (c, a)):
+            half[e] = half.get(e, 0) + 1
+    assert all(n == 1 for n in half.values()) and all((b, a) in half for (a, b) in half)
