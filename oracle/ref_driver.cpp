@@ -237,6 +237,21 @@ void ref_mesh_signed_distance(const float* verts, uint32_t nv, const uint32_t* t
     memcpy(out, d.data(), n * sizeof(float));
 }
 
+// The same with ONE build of the reference's MeshDistance, whatever state rand() is in: the reference's raw behaviour
+// (tests/test_mesh_prep_cpu.py shows the unsound trees with it; nothing else uses it).
+void ref_mesh_signed_distance_once(const float* verts, uint32_t nv, const uint32_t* tris, uint32_t nt, const float* transform16,
+                                   const float* points, uint32_t n, float* out) {
+    std::vector<glm::vec3> v(nv);
+    std::vector<glm::uvec3> t(nt);
+    glm::mat4 T(1.0f);
+    if (transform16) memcpy(&T[0][0], transform16, 16 * sizeof(float));
+    for (uint32_t i = 0; i < nv; i++) v[i] = T * glm::vec4(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2], 1.0f);
+    for (uint32_t i = 0; i < nt; i++) t[i] = { tris[3 * i], tris[3 * i + 1], tris[3 * i + 2] };
+    const Ref<EdgeMesh> mesh = Ref<EdgeMesh>::Create(v, t);
+    MeshDistance md(mesh);
+    for (uint32_t i = 0; i < n; i++) out[i] = md.SignedDistance(glm::vec3(points[3 * i], points[3 * i + 1], points[3 * i + 2]));
+}
+
 // Volume-map extraction = exactly what SDF::GetDeviceData flattens (SDF.cu:227-306).
 // sizes: [fieldCount, nodeCount, cellCount, cellMapCount, res.x, res.y, res.z]
 void ref_get_map_sizes(RefSim* s, uint32_t body, uint32_t* sizes, float* domain6, float* cell3, float* cellInv3) {

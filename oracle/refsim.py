@@ -110,6 +110,8 @@ def _load(kind):
     if hasattr(L, "ref_mesh_signed_distance"):
         L.ref_mesh_signed_distance.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp]
         L.ref_add_mesh_body.argtypes = [vp, vp, u32, vp, u32, vp, C.c_int, f32, vp]
+    if hasattr(L, "ref_mesh_signed_distance_once"):
+        L.ref_mesh_signed_distance_once.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp]
     L.ref_set_serial.argtypes = [C.c_int]
     L.ref_set_threads.argtypes = [C.c_int]
     L.ref_get_max_threads.restype = C.c_int
@@ -147,13 +149,14 @@ def _mesh_args(verts, tris, transform):
     return v, t, T
 
 
-def mesh_signed_distance(verts, tris, points, transform=None, kind="cpu"):
-    """The reference's MeshDistance::SignedDistance (MeshDistance.cpp:187-222) of a raw triangle mesh at `points`."""
+def mesh_signed_distance(verts, tris, points, transform=None, kind="cpu", once=False):
+    """The reference's MeshDistance::SignedDistance (MeshDistance.cpp:187-222) of a raw triangle mesh at `points`: from two
+    builds of its randomised sphere tree that agree (oracle/ref_driver.cpp), or — `once` — from one build, as is."""
     L = _load(kind)
     v, t, T = _mesh_args(verts, tris, transform)
     p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
     out = np.zeros(len(p), np.float32)
-    L.ref_mesh_signed_distance(_p(v), len(v), _p(t), len(t), None if T is None else _p(T), _p(p), len(p), _p(out))
+    (L.ref_mesh_signed_distance_once if once else L.ref_mesh_signed_distance)(_p(v), len(v), _p(t), len(t), None if T is None else _p(T), _p(p), len(p), _p(out))
     return out
 
 

@@ -130,3 +130,20 @@ def test_sampling_grid_lattice_and_inside_test_select_the_references_samples(hc,
     ref = g["sample_%d" % mode]
     assert got.shape == ref.shape, (got.shape, ref.shape)
     assert np.array_equal(got, ref)
+
+
+def test_the_references_sphere_tree_is_what_disagrees_not_the_distance(hc, g):
+    """Why the fixtures hold modal outputs and the oracle builds until two builds agree: single builds of the reference's
+    MeshDistance on the cone (cocircular rim vertices) — each with the next rand() state — against the minimum over all faces.
+    A build either reproduces it (up to one point in 20 000 on an fp32 tie between faces) or misses nearest faces wholesale;
+    agreeing builds always reproduce it.  The count of unsound builds is printed, not asserted (it depends on rand())."""
+    from oracle import refsim
+    if not refsim.available("cpu") or not hasattr(refsim._load("cpu"), "ref_mesh_signed_distance_once"):
+        pytest.skip("oracle/_ref without the single-build hook")
+    v, t, T, p = g["cone_verts"], g["cone_tris"], g["cone_T"], g["points_cone"][:5000]
+    brute = host_sd(hc, v, t, T, p)
+    wrong = [int((refsim.mesh_signed_distance(v, t, p, transform=T, once=True) != brute).sum()) for _ in range(24)]
+    print("\nsingle builds: points differing from the minimum over all faces, per build:", wrong)
+    for _ in range(6):
+        agreed = refsim.mesh_signed_distance(v, t, p, transform=T)
+        assert (agreed != brute).sum() <= 2 and np.abs(agreed - brute).max() < 5e-6
