@@ -162,6 +162,12 @@ uint32_t vfd_dfsph_get_rigid_body_count(const VfdDfsph* h);
  * frames: VFD/Source/Scene/Scene.cpp:361-368). */
 int vfd_dfsph_get_frame_count(const VfdDfsph* h, uint32_t* baked);
 int vfd_dfsph_get_frame(VfdDfsph* h, uint32_t index, VfdParticleSimple* out, float* maxVelocityMagnitude, float* currentTimeStep);
+/* The same frame where it lies in the handle's frame store, without a copy — what DFSPHParticleBuffer::GetFrame
+ * (ParticleBuffer/DFSPHParticleBuffer.cu:54-57) hands out by reference: *data points at *count records in host memory (pinned
+ * up to the store's budget, so DFSPHParticleBuffer::SetActiveFrame's upload :38-49 can read it directly); valid until the next
+ * bake, the next vfd_dfsph_set_particles or vfd_dfsph_destroy. */
+int vfd_dfsph_get_frame_data(VfdDfsph* h, uint32_t index, const VfdParticleSimple** data, uint32_t* count,
+                             float* maxVelocityMagnitude, float* currentTimeStep);
 /* the current state in frame format (what the next captured frame would hold) */
 int vfd_dfsph_get_current_frame(VfdDfsph* h, VfdParticleSimple* out);
 

@@ -38,3 +38,27 @@ def test_frames_in_pageable_storage_equal_the_pinned_ones(lib_built, monkeypatch
             assert va == vb and da == db, (budget, i)
             for f in ("Position", "Velocity", "Acceleration"):
                 assert np.array_equal(np.asarray(a[f]).view(np.uint32), np.asarray(b[f]).view(np.uint32)), "frame %d field %s differs with a pinned budget of %d MB" % (i, f, budget)
+
+
+def test_frame_views_are_the_frames(lib_built, monkeypatch):
+    """vfd_dfsph_get_frame_data hands out a frame where it lies in the store (DFSPHParticleBuffer::GetFrame returns a
+    reference as well): same records as the copying getter, the same address when asked twice, in pinned and in pageable storage."""
+    from vfd_b200 import api
+    import test_gpu_scale as big
+    monkeypatch.setenv("VFD_FRAME_PINNED_MB", "3")
+    pos, box, res = big.scene(30)
+    vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=big.R)
+    sim = api.DFSPHSimulation(api.DFSPHSimulationDescription(FrameCount=6, FrameLength=0.0, **big.CONFIGS["dfsph"]))
+    sim.SetFluidObjects([api.FluidObject(pos)])
+    sim.SetRigidBodies([vm])
+    sim.Simulate()
+    for i in range(6):
+        copy, vmax, dt = sim.GetFrame(i)
+        view, vmax2, dt2 = sim.GetFrameView(i)
+        again, _, _ = sim.GetFrameView(i)
+        assert (vmax, dt) == (vmax2, dt2) and len(view) == len(pos)
+        assert view.__array_interface__["data"][0] == again.__array_interface__["data"][0]
+        assert np.array_equal(view.view(np.uint8), copy.view(np.uint8))
+    with pytest.raises(api.VfdError):
+        sim.GetFrameView(6)
+    sim.close()

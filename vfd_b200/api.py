@@ -136,6 +136,7 @@ SYMBOLS = [
     ("vfd_dfsph_get_rigid_body_count", _u32, [_vp]),
     ("vfd_dfsph_get_frame_count", _i, [_vp, C.POINTER(_u32)]),
     ("vfd_dfsph_get_frame", _i, [_vp, _u32, _vp, C.POINTER(_f32), C.POINTER(_f32)]),
+    ("vfd_dfsph_get_frame_data", _i, [_vp, _u32, C.POINTER(_vp), C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_f32)]),
     ("vfd_dfsph_get_current_frame", _i, [_vp, _vp]),
     ("vfd_dfsph_get_search_bytes", _i, [_vp, C.POINTER(_u64)]),
     ("vfd_dfsph_get_bounds", _i, [_vp, _vp, _vp]),
@@ -415,6 +416,18 @@ class DFSPHSimulation:
         mv, dt = C.c_float(), C.c_float()
         self._ck(self.L.vfd_dfsph_get_frame(self.h, index, _p(out), C.byref(mv), C.byref(dt)))
         return out, mv.value, dt.value
+
+    def GetFrameView(self, index):
+        """The same frame where it lies in the handle's frame store — no copy (DFSPHParticleBuffer::GetFrame returns a reference
+        too); a read-only array valid until the next bake, SetFluidObjects or close()."""
+        ptr, cnt, mv, dt = C.c_void_p(), C.c_uint32(0), C.c_float(), C.c_float()
+        self._ck(self.L.vfd_dfsph_get_frame_data(self.h, index, C.byref(ptr), C.byref(cnt), C.byref(mv), C.byref(dt)))
+        if cnt.value == 0:
+            return np.zeros(0, PARTICLE_SIMPLE_DTYPE), mv.value, dt.value
+        raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), (cnt.value * PARTICLE_SIMPLE_DTYPE.itemsize,))
+        view = raw.view(PARTICLE_SIMPLE_DTYPE)
+        view.flags.writeable = False
+        return view, mv.value, dt.value
 
     # ---- extensions (no reference equivalent) ----------------------------------------------
     def begin(self):

@@ -114,6 +114,16 @@ int vfd_dfsph_get_frame(VfdDfsph* h, uint32_t index, VfdParticleSimple* out, flo
     }
     return h->s.fail(VFD_E_INVALID, "frame index out of range");
 }
+int vfd_dfsph_get_frame_data(VfdDfsph* h, uint32_t index, const VfdParticleSimple** data, uint32_t* count, float* maxVel, float* dt) {
+    GUARD(h);
+    if (!data) return VFD_E_INVALID;
+    if (h->s.pipe.view(index, data, count, maxVel, dt)) return VFD_OK;
+    if (index < h->s.frameIndexHost && h->s.state != VFD_STATE_SIMULATING) {
+        if (h->s.pipe.drain() != cudaSuccess) return h->s.fail(VFD_E_CUDA, "asynchronous frame copy failed");
+        if (h->s.pipe.view(index, data, count, maxVel, dt)) return VFD_OK;
+    }
+    return h->s.fail(VFD_E_INVALID, "frame index out of range");
+}
 int vfd_dfsph_get_current_frame(VfdDfsph* h, VfdParticleSimple* out) { GUARD(h); LOCKED(h); TRY(h->s.get_current_frame(out)); }
 
 int vfd_dfsph_get_search_bytes(const VfdDfsph* h, uint64_t* bytes) { GUARD(h); if (!bytes) return VFD_E_INVALID; *bytes = h->s.searchBytes; return VFD_OK; }

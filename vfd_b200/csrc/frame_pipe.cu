@@ -204,4 +204,15 @@ bool FramePipe::read(uint32_t index, VfdParticleSimple* out, float* maxVel2, flo
     return true;
 }
 
+bool FramePipe::view(uint32_t index, const VfdParticleSimple** data, uint32_t* count, float* maxVel2, float* dt) {
+    std::lock_guard<std::mutex> g(m);
+    if (index >= frames.size()) return false;
+    const Frame& f = frames[index];
+    if (data) *data = f.data.p;
+    if (count) *count = (uint32_t)f.count;
+    if (maxVel2) *maxVel2 = f.maxVel2;
+    if (dt) *dt = f.dt;
+    return true;
+}
+
 } // namespace vfd

@@ -65,6 +65,8 @@ public:
     size_t published();
     // copy a published frame out (false: index not published)
     bool read(uint32_t index, VfdParticleSimple* out, float* maxVel2, float* dt);
+    // a published frame where it lies in the store (no copy): valid until the store is cleared (next bake, new particle count, destroy)
+    bool view(uint32_t index, const VfdParticleSimple** data, uint32_t* count, float* maxVel2, float* dt);
     uint64_t bytesCopied = 0;
 
 private:
