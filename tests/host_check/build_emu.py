@@ -53,5 +53,39 @@ def build(force=False):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+FRAME_OUT = os.path.join(HERE, "_bin", "libvfd_framepipe_emu.so")
+
+
+def build_frame_pipe(force=False):
+    """csrc/frame_pipe.cu (pure host code over the CUDA runtime) compiled unchanged against the emulated runtime with
+    asynchronous streams and events (emu/cuda_runtime.h), plus the driver tests/host_check/frame_pipe_host.cpp."""
+    srcs = [os.path.join(CSRC, "frame_pipe.cu"), os.path.join(CSRC, "frame_pipe.h"), os.path.join(HERE, "frame_pipe_host.cpp")]
+    emu = [os.path.join(HERE, "emu", f) for f in os.listdir(os.path.join(HERE, "emu"))]
+    if not force and os.path.exists(FRAME_OUT) and os.path.getmtime(FRAME_OUT) > max(os.path.getmtime(d) for d in srcs + emu + [__file__]):
+        return FRAME_OUT
+    os.makedirs(os.path.dirname(FRAME_OUT), exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="vfd_emu_")
+    try:
+        for f in emu:
+            shutil.copy(f, tmp)
+        # frame_pipe.h includes "../../include/vfd_dfsph.h" relative to csrc/: mirror that layout
+        os.makedirs(os.path.join(tmp, "include"))
+        shutil.copy(os.path.join(ROOT, "include", "vfd_dfsph.h"), os.path.join(tmp, "include"))
+        csrc = os.path.join(tmp, "vfd_b200", "csrc")
+        os.makedirs(csrc)
+        shutil.copy(os.path.join(CSRC, "frame_pipe.h"), csrc)
+        shutil.copy(os.path.join(CSRC, "frame_pipe.cu"), os.path.join(csrc, "frame_pipe_cu.cpp"))
+        shutil.copy(os.path.join(HERE, "frame_pipe_host.cpp"), csrc)
+        cmd = ["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-pthread", "-w", "-I", tmp, "-I", csrc, "-o", FRAME_OUT,
+               os.path.join(csrc, "frame_pipe_cu.cpp"), os.path.join(csrc, "frame_pipe_host.cpp"), os.path.join(tmp, "emu.cpp")]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("emulation build failed:\n" + r.stdout[-6000:])
+        return FRAME_OUT
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_frame_pipe(force=True))
