@@ -107,3 +107,15 @@ def test_sampling_edge_cases(api):
     bad = t.copy(); bad[3, 1] = 99
     with pytest.raises(api.VfdError):
         api.sample_mesh_volume(v, bad, R)
+
+
+def test_the_gpu_tests_themselves_pass_on_the_emulation(api, g):
+    """tests/test_gpu_zmesh.py's own test functions (the scene-preparation ones), called with the emulated library behind the
+    wrappers: their expectations and the fixture's full-size cases hold before the hardware run.  (The larger ones — the slab's
+    62 181-node map, sampling modes 0 and 2 of the whole cone — pass the same way in ~70 s; they are left to the GPU.)"""
+    import test_gpu_zmesh as T
+    for name in ("cone", "torus"):
+        T.test_mesh_signed_distance_matches_the_reference(None, g, name)
+    T.test_mesh_volume_map_matches_the_references(None, g, "conemap", "cone")
+    T.test_mesh_volume_sampling_matches_the_references(None, g, 1)
+    T.test_sampling_a_box_mesh_is_the_lattice_block(None)
