@@ -416,6 +416,7 @@ def main():
     ap.add_argument("--ref-settle", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scene-prep", action="store_true", help="skip the scene-preparation block (tools_scene_prep.py in a child process)")
     ap.add_argument("--ncu-visc-it", type=int, default=0, help="with --ncu: cap the PCG at this many iterations for the profiled steps "
                                                                   "(keeps an `ncu --set full` capture of one step short)")
     ap.add_argument("--ncu", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop (run under ncu --profile-from-start off); "
@@ -565,6 +566,18 @@ def main():
                 out["reference_cuda"]["speedup_over_ieee"] = ie["ms_per_step"] / (ms / args.steps)
         except Exception as ex:
             out["reference_cuda"] = {"error": repr(ex)}
+    if not args.no_cpu_baseline and not args.no_scene_prep:
+        # the steps next to the path: mesh sampling and volume-map precompute on this GPU, checked
+        # against and timed beside the reference's host code — part of the CPU-baseline leg (the one place the bench runs
+        # oracle/), in a child process so that nothing there can touch the numbers above
+        try:
+            import subprocess
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools_scene_prep.py"), "--device", str(local)], stdout=subprocess.PIPE,
+                               stderr=subprocess.PIPE, text=True, timeout=240)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            out["scene_prep"] = json.loads(lines[-1]) if r.returncode == 0 and lines else {"error": "exit code %d: %s" % (r.returncode, r.stderr[-300:])}
+        except Exception as ex:
+            out["scene_prep"] = {"error": repr(ex)}
     print(json.dumps(out))
     return 0
 
