@@ -408,7 +408,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--side", type=int, default=None, help="block edge in particles (default: the config's; 100 -> 1M)")
     ap.add_argument("--settle", type=int, default=None, help="scene-preparation steps before warm-up (SURVEY.md §8d; default 200)")
-    ap.add_argument("--ref-steps", type=int, default=12, help="--impl reference: timed steps (a bounded sample: ~1 s each at 1M on 16 cores)")
+    ap.add_argument("--ref-steps", type=int, default=24, help="--impl reference: at most this many timed steps, divided by the GPU count (a step is ~1.2 s of 16 cores per "
+                                                              "million particles: the driver's 20 steps run in full at N = 1, a bounded sample of them at N > 1)")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA build on this GPU")
     ap.add_argument("--scene", default="dam", choices=["dam", "tank"], help="N > 1: the dam break stretched along x (default; the N = 1 scene at N = 1) or a closed tank")
     ap.add_argument("--strong", action="store_true", help="N > 1: strong scaling — ONE side^3 scene (BASELINE.json config 4: --side 200) cut into N slabs, instead of side^3 per GPU")
