@@ -119,3 +119,28 @@ def test_the_gpu_tests_themselves_pass_on_the_emulation(api, g):
     T.test_mesh_volume_map_matches_the_references(None, g, "conemap", "cone")
     T.test_mesh_volume_sampling_matches_the_references(None, g, 1)
     T.test_sampling_a_box_mesh_is_the_lattice_block(None)
+
+
+def test_the_headless_scene_of_the_gpu_suite_is_prepared_like_the_reference(api):
+    """tests/test_gpu_scale.py::test_scene_file_runs_headless bakes a scene file through scene_io.build_simulation, i.e. through
+    these kernels: its fluid block (a unit cube scaled to 0.5^3, MinDensity sampling) and its slab (20 x 10 x 20 map) prepared by the
+    emulated library are the reference's — the 1 000 particles that test expects, the distance field bit for bit."""
+    from oracle import refsim
+    from vfd_b200 import scene_io
+    if not refsim.available("cpu") or not hasattr(refsim._load("cpu"), "ref_add_mesh_body"):
+        pytest.skip("oracle/_ref without the mesh hooks")
+    v, t = scene_io.UNIT_CUBE
+    block = np.eye(4, dtype=np.float32); block[:3, :3] = np.diag([0.25, 0.25, 0.25]); block[:3, 3] = [0.0, 0.6, 0.0]
+    floor = np.eye(4, dtype=np.float32); floor[:3, :3] = np.diag([1.0, 0.1, 1.0])
+    pos = api.sample_mesh_volume(v, t, R, (20, 20, 20), False, 0, transform=block)
+    vm = api.VolumeMap.build_mesh(v, t, transform=floor, inverted=False, padding=0.0, resolution=(20, 10, 20), particle_radius=R)
+    with refsim.quiet_stdout():
+        rpos = refsim.sample_mesh_volume(v, t, R, (20, 20, 20), False, 0, transform=block)
+        sim = refsim.RefSim(refsim.Desc(ParticleRadius=R))
+        sim.set_particles(np.zeros((1, 3), np.float32))
+        sim.add_mesh_body(v, t, transform=floor, inverted=False, padding=0.0, res=(20, 10, 20))
+        m = sim.volume_map(0)
+    assert len(pos) == 1000 and rpos.shape == pos.shape and np.array_equal(rpos, pos)
+    n = int(m["node_count"])
+    assert vm.node_count == n and np.array_equal(vm.nodes[:n], m["nodes"][:n])
+    assert np.abs(vm.nodes[n:] - m["nodes"][n:]).max() <= 3e-4 * np.abs(m["nodes"][n:]).max()
