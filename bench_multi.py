@@ -140,6 +140,16 @@ def main(args, rank, local, world):
         sim.synchronize()
         roof, table = None, {}
     dist.barrier()
+    # end to end at N GPUs: the settled state of every rank goes through host memory into a NEW decomposed solver that bakes K
+    # frames (each gathered by persistent id into a host frame on rank 0) — in child processes, one per GPU, so that nothing
+    # there (a hang, a crash) can take the numbers above with it
+    e2e = None
+    if not getattr(args, "no_e2e", False):
+        try:
+            e2e = e2e_children(args, rank, local, world, sim, n_global)
+        except Exception as ex:
+            e2e = {"error": repr(ex)}
+        dist.barrier()
     if rank == 0:
         value = n_global * args.steps / (ms_max * 1e-3)
         per_step = {k: (stats1[k] - stats0[k]) / args.steps for k in stats1}
@@ -159,10 +169,252 @@ def main(args, rank, local, world):
                        "kernels_rank0": table},
             "gpu_launches": int(launches), "clocks": clk.summary(),
             "roofline": roof, "cpu_baseline": None,     # cpu_baseline: reported at N = 1 only
-            "e2e": None,                                   # end to end through host buffers is measured at N = 1 (bench.py)
+            "e2e": e2e,
         }
         print(json.dumps(out))
     clk.stop()
     dist.barrier()
     dist.destroy_process_group()
     return 0
+
+
+# ---- end to end at N GPUs -------------------------------------------------------------------------------------------------
+E2E_TIMEOUT_S = 300
+
+
+def e2e_children(args, rank, local, world, sim, n_global):
+    """Parent side: every rank writes its owned particles (positions, velocities, persistent ids: host memory) and the slab
+    bounds to a file and starts ONE child process on its GPU (`bench_multi.py --e2e-child`); the children build their own
+    decomposed solver (a new communicator; they meet through files in a scratch directory — one node, no second network
+    rendezvous), bake, and rank 0's child leaves a JSON file.  Returns that JSON on rank 0 (None elsewhere); a child that fails
+    or outlives E2E_TIMEOUT_S is killed and reported as an error.  Every rank runs the same sequence of collectives whatever
+    goes wrong locally."""
+    import shutil
+    import signal
+    import subprocess
+    import sys
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+
+    def gather(values):
+        t = torch.tensor(values, dtype=torch.int64, device=dev)
+        outs = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return [[int(v) for v in o.cpu().tolist()] for o in outs]
+
+    port = int(os.environ.get("MASTER_PORT", "29500"))
+    tmp = os.path.join(tempfile.gettempdir(), "vfd_e2e_%d" % port)
+    state, result, log = os.path.join(tmp, "state_%d.npz" % rank), os.path.join(tmp, "result.json"), os.path.join(tmp, "child_%d.log" % rank)
+    err, lo, hi = None, 0, 0
+    try:
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
+    except Exception as ex:
+        err = repr(ex)
+    dist.barrier()
+    try:
+        os.makedirs(tmp, exist_ok=True)
+        ids, part = sim.owned()
+        sl = sim.slab()
+        lo, hi = int(sl["lo"]), int(sl["hi"])
+    except Exception as ex:
+        err = repr(ex)
+    slabs = gather([lo, hi, 0 if err is None else 1])
+    if any(f for _, _, f in slabs):
+        return {"error": "preparing the end-to-end leg failed on %d rank(s): %s" % (sum(f for _, _, f in slabs), err)} if rank == 0 else None
+    bounds = [l for l, _, _ in slabs] + [slabs[-1][1]]
+    proc = None
+    try:
+        np.savez(state, pos=np.ascontiguousarray(part["Position"], np.float32), vel=np.ascontiguousarray(part["Velocity"], np.float32),
+                 ids=np.ascontiguousarray(ids, np.uint32), bounds=np.asarray(bounds, np.int64), n_global=np.int64(n_global))
+        env = dict(os.environ)
+        env["RANK"], env["LOCAL_RANK"], env["WORLD_SIZE"] = str(rank), str(local), str(world)
+        cmd = [sys.executable, os.path.abspath(__file__), "--e2e-child", state, "--out", result, "--meet", tmp, "--steps", str(args.steps),
+               "--config", str(args.config), "--side", str(args.side), "--scene", str(getattr(args, "scene", "dam"))]
+        if getattr(args, "strong", False):
+            cmd.append("--strong")
+        with open(log, "w") as lf:
+            proc = subprocess.Popen(cmd, env=env, stdout=lf, stderr=subprocess.STDOUT, start_new_session=True)
+    except Exception as ex:
+        err = repr(ex)
+    if proc is not None:
+        try:
+            rc = proc.wait(timeout=E2E_TIMEOUT_S)
+            if rc != 0:
+                err = "child of rank %d: exit code %d" % (rank, rc)
+        except subprocess.TimeoutExpired:
+            try:
+                os.killpg(proc.pid, signal.SIGKILL)          # the child's own process group (start_new_session): nothing else
+            except OSError:
+                pass
+            proc.wait()
+            err = "child of rank %d: killed after %d s" % (rank, E2E_TIMEOUT_S)
+    failed = sum(f for f, in gather([0 if err is None else 1]))
+    if rank != 0:
+        return None
+    out = None
+    try:
+        if os.path.exists(result):
+            with open(result) as f:
+                out = json.load(f)
+    except Exception as ex:
+        err = err or repr(ex)
+    if out is None:
+        tail = ""
+        try:
+            tail = open(log).read()[-400:]
+        except OSError:
+            pass
+        return {"error": "no result; %d child(ren) failed; rank 0: %s" % (failed, err), "log_tail": tail}
+    if failed:
+        out["children_failed"] = failed
+    return out
+
+
+class FileMeet:
+    """The children's rendezvous: one node, one scratch directory.  put / get of small pickled objects by (tag, rank), with
+    atomic renames; barrier and all-gather on top.  (No second network rendezvous beside the parents' — nothing to collide
+    with the launcher's store, nothing that depends on the host name resolving.)"""
+
+    def __init__(self, root, rank, world, timeout_s):
+        self.root, self.rank, self.world, self.timeout, self.n = root, rank, world, timeout_s, 0
+
+    def _path(self, tag, r):
+        return os.path.join(self.root, "meet_%s_%d.pkl" % (tag, r))
+
+    def put(self, tag, obj):
+        import pickle
+        p = self._path(tag, self.rank)
+        with open(p + ".tmp", "wb") as f:
+            pickle.dump(obj, f)
+        os.replace(p + ".tmp", p)
+
+    def get(self, tag, r):
+        import pickle
+        p, t0 = self._path(tag, r), time.perf_counter()
+        while not os.path.exists(p):
+            if time.perf_counter() - t0 > self.timeout:
+                raise TimeoutError("rank %d waited %d s for rank %d at %r" % (self.rank, self.timeout, r, tag))
+            time.sleep(0.0005)
+        with open(p, "rb") as f:
+            return pickle.load(f)
+
+    def all_gather(self, obj):
+        self.n += 1
+        tag = "g%d" % self.n
+        self.put(tag, obj)
+        return [self.get(tag, r) for r in range(self.world)]
+
+    def barrier(self):
+        self.all_gather(None)
+
+    def broadcast(self, obj, src=0):
+        self.n += 1
+        tag = "b%d" % self.n
+        if self.rank == src:
+            self.put(tag, obj)
+        return self.get(tag, src)
+
+
+def e2e_child_main(argv):
+    """Child side (one process per GPU): a new decomposed solver is given this rank's particles from HOST arrays
+    (set_particles_distributed: H2D), bakes K steps with every step a whole-scene frame gathered on rank 0 and copied to host
+    memory there (D2H), and rank 0 reads the last frame.  Wall clock from before the upload to after the read, MAX over
+    ranks.  The first bake also allocates (device arrays, the pinned frame store): as in bench.py's N = 1 leg the figure of
+    record is a SECOND bake of the same handle, which must reproduce the first one's last frame bit for bit; the first
+    bake's figure is written out before the second is attempted."""
+    import argparse
+    import importlib
+    import bench
+    from vfd_b200 import partition
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--e2e-child")
+    ap.add_argument("--out")
+    ap.add_argument("--meet")
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--side", type=int, default=100)
+    ap.add_argument("--scene", default="dam")
+    ap.add_argument("--strong", action="store_true")
+    a = ap.parse_args(argv)
+    api = importlib.import_module(os.environ.get("VFD_E2E_API", "vfd_b200.api"))       # (the CPU test of this plumbing substitutes a stand-in)
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    meet = FileMeet(a.meet, rank, world, E2E_TIMEOUT_S)
+    cfg = bench.CONFIGS[a.config]
+    bench.CONFIG_DESC.clear(); bench.CONFIG_DESC.update(cfg["desc"])
+    d = np.load(a.e2e_child)
+    pos, vel, ids, bounds, n_global = d["pos"], d["vel"], d["ids"], d["bounds"], int(d["n_global"])
+    K = a.steps
+    _, box, res = dist_scene(a.side, 1 if a.strong else world, a.scene)
+    sim = api.DFSPHSimulation(bench.description(api.DFSPHSimulationDescription, frames=K), device=local)
+    uid = meet.broadcast(api.dist_unique_id() if rank == 0 else None)
+    sim.init_distributed(rank, world, uid, box[0], box[1])
+    origin, cell, tiles = sim.grid()
+    sim.set_slab(int(bounds[rank]), int(bounds[rank + 1]))
+    ghost = int(tiles[1]) * int(tiles[2]) * 64 * 12 * 2
+    vm = api.VolumeMap.build_box(box[0], box[1], inverted=True, padding=0.0, resolution=res, particle_radius=R, device=local)
+    held = {"pos": pos, "vel": vel, "ids": ids}
+
+    def rehome():
+        """Every particle to the rank whose slab holds its tile column NOW (host-side partitioning, like bench_multi.setup's, not
+        timed): a particle may have crossed its slab's boundary in the timed run's last step (the running solver migrates it at the
+        start of the next one), and the slabs of this handle have moved if its previous bake re-balanced them."""
+        sl = sim.slab()
+        now = meet.all_gather((int(sl["lo"]), int(sl["hi"])))
+        b = np.asarray([lo for lo, _ in now] + [now[-1][1]], np.int64)
+        p, v, i = held["pos"], held["vel"], held["ids"]
+        owner = partition.owner_of(partition.tile_columns(p[:, 0], origin[0], H, tiles[0]), b)
+        away = owner != rank
+        sent = meet.all_gather((p[away], v[away], i[away], owner[away]))
+        mine = [(sp[so == rank], sv[so == rank], si[so == rank]) for sp, sv, si, so in sent]
+        held["pos"] = np.ascontiguousarray(np.concatenate([p[~away]] + [m[0] for m in mine]), np.float32)
+        held["vel"] = np.ascontiguousarray(np.concatenate([v[~away]] + [m[1] for m in mine]), np.float32)
+        held["ids"] = np.ascontiguousarray(np.concatenate([i[~away]] + [m[2] for m in mine]), np.uint32)
+
+    def bake():
+        rehome()
+        p, v, i = held["pos"], held["vel"], held["ids"]
+        capacity = int(1.5 * len(p)) + 2 * ghost
+        meet.barrier()
+        t0 = time.perf_counter()
+        sim.set_particles_distributed(p, v, i, n_global, capacity)             # H2D of the inputs
+        sim.SetRigidBodies([vm])
+        sim.Simulate()                                                          # K steps, each a gathered host frame on rank 0
+        last = sim.GetFrame(K - 1)[0] if rank == 0 else None                   # the frame pipe's D2H copy, read from the host store
+        sim.synchronize()
+        return max(meet.all_gather(time.perf_counter() - t0)), last
+
+    def report(el, which, extra):
+        if rank != 0:
+            return
+        out = {"value": n_global * K / el, "unit": "particle-steps/s", "h2d_bytes_per_step": int(28 * n_global / K), "d2h_bytes_per_step": 36 * n_global,
+               "ms_per_step": 1e3 * el / K, "n_gpus": world, "bake": which,
+               "note": "every rank: vfd_dfsph_set_particles_distributed (positions, velocities, ids from host arrays) + set_rigid_bodies + simulate "
+                       "(FrameLength 0: every step baked — owned particles gathered by persistent id on rank 0, whole-scene frame copied to host "
+                       "memory) + get_frame of the last one on rank 0; wall clock, max over ranks; a new solver per rank in a child process, from the "
+                       "timed run's settled state"}
+        out.update(extra)
+        with open(a.out + ".tmp", "w") as f:
+            json.dump(out, f)
+        os.replace(a.out + ".tmp", a.out)
+
+    first = "first bake of the handle (includes allocating device arrays and the pinned frame store)"
+    el1, f1 = bake()
+    report(el1, first, {})
+    el2, f2 = bake()
+    same = all(meet.all_gather(bool(rank != 0 or (f1 is not None and f2 is not None and f1.tobytes() == f2.tobytes()))))
+    if same:
+        report(el2, "second bake of the handle (an untimed first bake sized the buffers)", {"rebake_identical": True, "first_bake_ms_per_step": 1e3 * el1 / K})
+    else:
+        report(el1, first, {"rebake_identical": False})
+    meet.barrier()
+    os._exit(0)            # the figure is on disk: the teardown of a decomposed handle must not decide the exit code
+
+
+if __name__ == "__main__":
+    import sys
+    if "--e2e-child" in sys.argv:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        e2e_child_main(sys.argv[1:])
