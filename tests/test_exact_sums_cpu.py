@@ -1,7 +1,7 @@
 """The oracle's density and DFSPH factor against an independent restatement (tests/exact_sums.py): the same fp32 per-pair
 terms, summed in float64, on the four committed fixtures — the reference's results lie within fp32 summation round-off of the
 exactly summed value, and within the kernel table's discretisation of the analytic cubic spline.  (The hardware twin of this
-file, tests/test_gpu_zzz_exact_sums.py, measures the same distance for the CUDA path.)"""
+file, tests/test_gpu_y_exact_sums.py, measures the same distance for the CUDA path.)"""
 import os
 
 import numpy as np

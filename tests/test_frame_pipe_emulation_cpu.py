@@ -3,7 +3,7 @@ unchanged against an emulated CUDA runtime whose streams are threads, whose even
 whose copies take time (tests/host_check/emu/cuda_runtime.h), driven like Solver::step drives it
 (tests/host_check/frame_pipe_host.cpp).  Covered here, before any GPU: frames complete and in order however export, copy and
 worker interleave; the device's keep/drop decision; the pageable fallback beyond the pinned budget (all frames, or the ones
-after the budget is used up); re-use of device slots and staging buffers; the zero-copy view.  tests/test_gpu_zz_frame_store.py
+after the budget is used up); re-use of device slots and staging buffers; the zero-copy view.  tests/test_gpu_z_frame_store.py
 repeats the storage cases on hardware."""
 import ctypes as C
 import os

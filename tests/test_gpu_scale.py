@@ -349,29 +349,3 @@ def test_box_volume_map_built_on_the_gpu_matches_the_reference(lib_built):
     e1 = np.abs(ours[1] - theirs[1]).max() / max(np.abs(theirs[1]).max(), 1e-30)
     print("\nbox volume map %s nodes: distance field max abs err %.2e, volume field max err %.2e of scale %.3g" % (n, e0, e1, np.abs(theirs[1]).max()))
     assert e0 < 5e-5 and e1 < 1e-4          # distances of order 1: the reference goes through a triangle mesh and fp32 point-triangle distances
-
-
-def test_scene_file_runs_headless(tmp_path, lib_built):
-    """a scene in the editor's file format (unit cubes under scale/translation transforms) is read,
-    its fluid block sampled like the reference's MinDensity sampler, its rigid body integrated on the GPU, and baked."""
-    from vfd_b200 import scene_io
-    floor = np.eye(4, dtype=np.float32)
-    floor[:3, :3] = np.diag([1.0, 0.1, 1.0])                      # cube [-1, 1]^3 -> slab 2 x 0.2 x 2 around the origin
-    block = np.eye(4, dtype=np.float32)
-    block[:3, :3] = np.diag([0.25, 0.25, 0.25]); block[:3, 3] = [0.0, 0.6, 0.0]
-    p = str(tmp_path / "scene.json")
-    scene_io.write_scene(p, {"TimeStepSize": 0.001, "FrameCount": 40, "FrameLength": 0.0, "ParticleRadius": 0.025, "Gravity": (0.0, -9.81, 0.0),
-                             "EnableSurfaceTensionSolver": False, **PINNED},
-                         fluid_objects=[dict(mesh="Resources/Models/Cube.obj", transform=block, inverted=False, resolution=(20, 20, 20), sample_mode=0)],
-                         rigid_bodies=[dict(mesh="Resources/Models/Cube.obj", transform=floor, inverted=False, padding=0.0, resolution=(20, 10, 20))])
-    sim = scene_io.build_simulation(scene_io.read_scene(p))
-    n = sim.GetParticleCount()
-    assert n == 10 * 10 * 10
-    sim.Simulate()
-    assert sim.GetFrameCount() == 40
-    first, _, _ = sim.GetFrame(0)
-    last, _, _ = sim.GetFrame(39)
-    y0, y1 = np.asarray(first["Position"])[:, 1], np.asarray(last["Position"])[:, 1]
-    assert np.isfinite(y1).all() and y1.mean() < y0.mean() - 0.01           # the block falls ...
-    assert y1.min() > 0.1 - 0.05                                              # ... and does not pass through the slab's top face (y = 0.1)
-    sim.close()

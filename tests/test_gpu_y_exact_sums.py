@@ -6,7 +6,8 @@ the CUDA path's distance is measured on the same fixtures and printed beside it.
 
 The asserted bound is the parity tolerance of tests/test_gpu_golden.py plus the reference's distance (triangle inequality),
 so this file can only fail where the golden test fails; the printed numbers are its content.
-(File name: sorts after every other GPU test — written after the round's GPU budget was spent.)"""
+(Written after the round's GPU budget was spent; the hardware-unvalidated files run last, the least risky first: this one, then
+test_gpu_z_frame_store.py, then test_gpu_zmesh.py.)"""
 import os
 
 import numpy as np

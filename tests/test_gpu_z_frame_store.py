@@ -3,7 +3,7 @@ memory up to a budget (VFD_FRAME_PINNED_MB, default 8 GB — 227 frames of a mil
 into a pinned staging slot and moved to pageable storage by the pipe's worker.  The bench and the other tests stay below
 the budget: here the budget is squeezed so that a bake mixes both kinds of storage, or uses pageable storage only, and the
 frames must be the ones of the all-pinned bake, bit for bit (the solver is bit-reproducible run to run).
-(File name: sorts last — this path had no hardware run before the round's end.)"""
+(File name: sorts after the solver's parity tests — this path had no hardware run before the round's end.)"""
 import numpy as np
 import pytest
 

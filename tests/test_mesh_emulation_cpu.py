@@ -122,7 +122,7 @@ def test_the_gpu_tests_themselves_pass_on_the_emulation(api, g):
 
 
 def test_the_headless_scene_of_the_gpu_suite_is_prepared_like_the_reference(api):
-    """tests/test_gpu_scale.py::test_scene_file_runs_headless bakes a scene file through scene_io.build_simulation, i.e. through
+    """tests/test_gpu_zmesh.py::test_scene_file_runs_headless bakes a scene file through scene_io.build_simulation, i.e. through
     these kernels: its fluid block (a unit cube scaled to 0.5^3, MinDensity sampling) and its slab (20 x 10 x 20 map) prepared by the
     emulated library are the reference's — the 1 000 particles that test expects, the distance field bit for bit."""
     from oracle import refsim
