@@ -33,6 +33,8 @@ def api():
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
     assert all(hasattr(L, n) for n in ("vfd_volume_map_build_mesh", "vfd_volume_map_build_box", "vfd_mesh_signed_distance", "vfd_sample_mesh_volume", "vfd_free", "vfd_volume_map_free"))
+    if not hasattr(L, "vfd_dfsph_last_error"):            # lives in api.cu, which is not part of the emulated translation unit
+        L.vfd_dfsph_last_error = lambda h: b"(emulated library: no message)"
     saved = real.lib
     real.lib = lambda: L
     yield real
@@ -107,6 +109,12 @@ def test_sampling_edge_cases(api):
     bad = t.copy(); bad[3, 1] = 99
     with pytest.raises(api.VfdError):
         api.sample_mesh_volume(v, bad, R)
+    # a grid whose 32-bit node / cell counts (the interchange format's) would wrap is refused, not built
+    for res in ((1024, 1024, 1024), (900, 900, 900), (0, 4, 4)):
+        with pytest.raises(api.VfdError):
+            api.VolumeMap.build_mesh(v, t, resolution=res, particle_radius=R)
+        with pytest.raises(api.VfdError):
+            api.sample_mesh_volume(v, t, R, res, False, 0)
 
 
 def test_the_gpu_tests_themselves_pass_on_the_emulation(api, g):

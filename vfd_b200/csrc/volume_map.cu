@@ -299,7 +299,10 @@ static int build_two_field_map(const MapGeom& G, float h, const std::function<cu
 
 static bool resolution_ok(const uint32_t resolution[3]) {
     for (int k = 0; k < 3; k++) if (resolution[k] == 0 || resolution[k] > 1024) return false;
-    return true;
+    // node and cell counts are 32-bit in the interchange format (SDFDeviceData): refuse a grid whose counts would wrap
+    const uint64_t nx = resolution[0], ny = resolution[1], nz = resolution[2];
+    const uint64_t nodes = (nx + 1) * (ny + 1) * (nz + 1) + 2 * (nx * (ny + 1) * (nz + 1) + (nx + 1) * ny * (nz + 1) + (nx + 1) * (ny + 1) * nz);
+    return nodes <= 0x7fffffffull && nx * ny * nz * 32ull <= 0xffffffffull;
 }
 
 } // namespace vfd
