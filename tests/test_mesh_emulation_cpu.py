@@ -152,3 +152,12 @@ def test_the_headless_scene_of_the_gpu_suite_is_prepared_like_the_reference(api)
     n = int(m["node_count"])
     assert vm.node_count == n and np.array_equal(vm.nodes[:n], m["nodes"][:n])
     assert np.abs(vm.nodes[n:] - m["nodes"][n:]).max() <= 3e-4 * np.abs(m["nodes"][n:]).max()
+
+
+def test_the_box_map_test_of_the_gpu_suite_passes_on_the_emulation(api):
+    """The box-map kernels (k_map_sdf, k_map_volume: the map every bench scene and most GPU tests are built with) changed after
+    their last hardware run — the node numbering was rewritten (map_geometry.cuh).  The GPU suite's own check of them against the
+    reference's host precompute, run here on the emulated library: same numbers as the hardware run printed before the rewrite
+    (distance field 1.05e-05, volume field 3.85e-05 of scale)."""
+    import test_gpu_scale as T
+    T.test_box_volume_map_built_on_the_gpu_matches_the_reference(None)
