@@ -106,11 +106,11 @@ class ClockSampler:
 
     def start(self):
         """nvidia-smi takes ~0.1 s to deliver its first line: started before the warm-up so that it is streaming (one line per
-        100 ms) when the timed region begins."""
+        50 ms: the driver's 20-step run times ~0.2 s) when the timed region begins."""
         if self.proc is not None:
             return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -145,7 +145,7 @@ class ClockSampler:
         window = "timed region"
         if not rows:
             rows = [r for t, r in self.rows if t0 - 0.5 <= t <= t1 + 0.5]
-            window = "timed region +- 0.5 s (region shorter than the 100 ms sampling period)"
+            window = "timed region +- 0.5 s (region shorter than the 50 ms sampling period)"
         sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
