@@ -574,7 +574,7 @@ def main():
         try:
             import subprocess
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools_scene_prep.py"), "--device", str(local)], stdout=subprocess.PIPE,
-                               stderr=subprocess.PIPE, text=True, timeout=240)
+                               stderr=subprocess.PIPE, text=True, timeout=150)
             lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
             out["scene_prep"] = json.loads(lines[-1]) if r.returncode == 0 and lines else {"error": "exit code %d: %s" % (r.returncode, r.stderr[-300:])}
         except Exception as ex:
