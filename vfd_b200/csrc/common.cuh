@@ -165,6 +165,18 @@ __device__ __forceinline__ void load_lut(float* dst, const float* __restrict__ s
     for (int i = threadIdx.x; i < (VFD_LUT_RES / 4); i += blockDim.x) d4[i] = __ldg(s4 + i);
 }
 
+// ---- opting kernels into > 48 KB of dynamic shared memory -----------------------------------------
+// cudaFuncSetAttribute acts on the CURRENT device, so "already done" is a fact about (kernel, device).  The launchers cache it per
+// host thread and forget it when that thread's current device is another one than at their last call (a process that drives
+// handles on two GPUs); with one device per thread — the only pattern this repo's tests and bench use — nothing changes.
+static inline bool launch_device_changed(int& lastDevice) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }      // (then: behave as with one device)
+    if (dev == lastDevice) return false;
+    lastDevice = dev;
+    return true;
+}
+
 // ---- deterministic grid-wide reductions ------------------------------------------------------
 // Each block reduces to one double per quantity, stores it in `partials`, and the last block to
 // finish (ticket counter) folds the partials in a fixed order: bit-reproducible run to run,

@@ -324,6 +324,8 @@ __global__ void k_clear_acc(Params P, Arrays A) {
 template<typename Kern>
 static void pipe_attr(Kern kern, size_t smem) {
     static thread_local const void* done[32]; static thread_local int nd = 0;
+    static thread_local int dev = -1;
+    if (launch_device_changed(dev)) nd = 0;
     for (int i = 0; i < nd; i++) if (done[i] == (const void*)kern) return;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (nd < 32) done[nd++] = (const void*)kern;

@@ -347,11 +347,10 @@ void launch_search(const LaunchCfg& L, const Params& P, Arrays& A, DevState* S, 
     {
         LaunchScope ls(L, KID_BUILD_LIST);
         const size_t smem = tile_smem_bytes<0, 1>(STAGE_CAP);
-        static bool attr = false;
-        if (!attr) {
+        static thread_local int dev = -1;
+        if (launch_device_changed(dev)) {
             cudaFuncSetAttribute(k_build_list<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(k_build_list<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr = true;
         }
         const uint32_t grid = (uint32_t)L.numSMs * 3u;
         if (P.searchFma) k_build_list<true><<<grid, TT_PLAIN, smem, L.stream>>>(P, A, S);

@@ -221,15 +221,15 @@ __global__ void __launch_bounds__(VFD_TPB) k_st_apply(Params P, Arrays A) {
 
 void launch_st_classify(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S, const float* halton) {
     const size_t sp = pipe_smem_bytes<StClassifyOp>();
-    static thread_local bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_st_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp); attr = true; }
+    static thread_local int dev = -1;
+    if (launch_device_changed(dev)) cudaFuncSetAttribute(k_st_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
     LaunchScope ls(L, KID_ST_CLASSIFY);
     k_st_classify<<<L.numSMs, StClassifyOp::Cfg::THREADS, sp, L.stream>>>(P, A, S, halton);
 }
 void launch_st_smooth(const LaunchCfg& L, const Params& P, const Arrays& A, DevState* S) {
     const size_t sp = pipe_smem_bytes<StSmoothOp>();
-    static thread_local bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_st_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp); attr = true; }
+    static thread_local int dev = -1;
+    if (launch_device_changed(dev)) cudaFuncSetAttribute(k_st_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp);
     LaunchScope ls(L, KID_ST_SMOOTH);
     k_st_smooth<<<L.numSMs, StSmoothOp::Cfg::THREADS, sp, L.stream>>>(P, A, S);
 }

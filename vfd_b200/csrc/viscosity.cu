@@ -437,6 +437,8 @@ __global__ void __launch_bounds__(VFD_TPB) k_visc_apply(Params P, Arrays A, DevS
 template<typename Kern>
 static void pipe_attr(Kern kern, size_t smem) {
     static thread_local const void* done[16]; static thread_local int nd = 0;
+    static thread_local int dev = -1;
+    if (launch_device_changed(dev)) nd = 0;
     for (int i = 0; i < nd; i++) if (done[i] == (const void*)kern) return;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (nd < 16) done[nd++] = (const void*)kern;
