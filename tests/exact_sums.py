@@ -67,7 +67,8 @@ def density_terms_f64(pos, counts, offsets, ids, bxj, bvol, K, volume, rho0):
     t = (F(volume) * _lookup_w(K, pos[i] - pos[j])).astype(F)
     s = np.full(len(pos), float(F(volume) * K["w_zero"]), np.float64)
     np.add.at(s, i, t.astype(np.float64))
-    tb = np.where(bvol > 0, bvol.astype(F) * _lookup_w(K, pos - bxj.astype(F)), F(0.0)).astype(F)
+    bxj = np.where((bvol > 0)[:, None], bxj.astype(F), pos)           # (a body that is out of reach leaves no sample: whatever is stored there is not read)
+    tb = np.where(bvol > 0, bvol.astype(F) * _lookup_w(K, pos - bxj), F(0.0)).astype(F)
     return (s + tb.astype(np.float64)) * float(rho0)
 
 
@@ -81,7 +82,8 @@ def factor_terms_f64(pos, counts, offsets, ids, bxj, bvol, K, volume, eps=1.0e-6
     np.add.at(spk, i, gg.astype(np.float64))
     gi = np.zeros((len(pos), 3), np.float64)
     np.add.at(gi, i, -g.astype(np.float64))
-    gb = np.where((bvol > 0)[:, None], -bvol.astype(F)[:, None] * _lookup_grad(K, pos - bxj.astype(F)), F(0.0)).astype(F)
+    bxj = np.where((bvol > 0)[:, None], bxj.astype(F), pos)
+    gb = np.where((bvol > 0)[:, None], -bvol.astype(F)[:, None] * _lookup_grad(K, pos - bxj), F(0.0)).astype(F)
     gi -= gb.astype(np.float64)
     tot = spk + (gi * gi).sum(1)
     return np.where(tot > eps, 1.0 / np.where(tot > eps, tot, 1.0), 0.0)
