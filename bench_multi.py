@@ -149,7 +149,10 @@ def main(args, rank, local, world):
             e2e = e2e_children(args, rank, local, world, sim, n_global)
         except Exception as ex:
             e2e = {"error": repr(ex)}
-        dist.barrier()
+        try:
+            dist.barrier()
+        except Exception:                   # the line below needs no collective: print it whatever became of this leg
+            pass
     if rank == 0:
         value = n_global * args.steps / (ms_max * 1e-3)
         per_step = {k: (stats1[k] - stats0[k]) / args.steps for k in stats1}
